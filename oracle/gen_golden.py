@@ -1,0 +1,212 @@
+"""TEST INFRASTRUCTURE ONLY -- freezes golden vectors by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shims.py) on seeded synthetic episodes.
+
+    python -m oracle.gen_golden [case ...]          # run from the repo root, in the
+                                                    # authoring container only
+
+For every case it (1) builds the reference `EdgeCape` detector from the reference's own
+config file (configs/test/1shot_split1.py) with the documented overrides, the hub
+backbone replaced by oracle/dinov2_oracle.py:DinoV2Oracle, (2) loads the deterministic
+weights of edgecape_b200/synthetic.py, (3) calls `model(return_loss=False, **data)` and
+captures the intermediates SURVEY.md section 8a names with forward hooks, (4) checks the
+CPU restatement oracle/edgecape_oracle.py against them, and (5) writes
+tests/golden/<case>.npz (outputs only -- weights and inputs are regenerated from the
+seeds recorded in CASES, so the files stay small).
+
+The reference cannot travel to the GPU box; these files and this script can.
+"""
+import copy
+import json
+import os
+import runpy
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from edgecape_b200.synthetic import make_episode, make_state_dict  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+from oracle.dinov2_oracle import DinoV2Oracle  # noqa: E402
+from oracle import edgecape_oracle  # noqa: E402
+
+TINY_VIT = dict(embed_dim=64, depth=2, num_heads=4, patch_size=16, img_size=80)
+
+# name -> (model overrides, episode kwargs, weight seed)
+CASES = {
+    # BASELINE.json configs[0]: 1-shot, 1 query 64x64, 5-kpt chain, tiny ViT, CPU plumbing
+    "c1_tiny": dict(pretrained=TINY_VIT, episode=dict(batch=1, image_size=64, num_kpts=5, shots=1,
+                                                      seed=11, skeleton="chain"), wseed=0),
+    # tiny ViT but the real head sizes, ragged visibility + 2 shots: fast kernel-parity case
+    "tiny_k100_2shot_masked": dict(pretrained=TINY_VIT,
+                                   episode=dict(batch=3, image_size=96, num_kpts=100, shots=2, seed=12,
+                                                masked_tail=0.32), wseed=1),
+    # all keypoints of batch row 1 masked + empty skeleton (all-masked guard, nan_to_num path)
+    "tiny_allmasked": dict(pretrained=TINY_VIT,
+                           episode=dict(batch=2, image_size=64, num_kpts=17, shots=1, seed=13,
+                                        masked_tail=0.0, skeleton="tree+extra"), wseed=2,
+                           mask_row=1),
+    # BASELINE.json configs[1] (reduced batch): ViT-B/14, 256^2 -> 18x18, K=100, 1-shot
+    "c2_vitb_256_k100": dict(pretrained="dinov2_vitb14",
+                             episode=dict(batch=2, image_size=256, num_kpts=100, shots=1, seed=21,
+                                          masked_tail=0.25), wseed=3),
+    # reference-native config: ViT-S/14 at 224^2, 5-shot (configs[3] shape at reduced batch)
+    "c4_vits_224_5shot": dict(pretrained="dinov2_vits14",
+                              episode=dict(batch=2, image_size=224, num_kpts=100, shots=5, seed=41,
+                                           masked_tail=0.4), wseed=4),
+    # BASELINE.json configs[4] (batch 1): ViT-L/14, 384^2 -> 27x27, K=200 fully connected
+    "c5_vitl_384_k200_full": dict(pretrained="dinov2_vitl14",
+                                  episode=dict(batch=1, image_size=384, num_kpts=200, shots=1, seed=51,
+                                               skeleton="full"), wseed=5),
+}
+
+
+def model_cfg_for(pretrained):
+    """The reference's own test config with the overrides SURVEY.md appendix A.14 requires
+    (in_channels / skeleton dim_feedforward follow the backbone width)."""
+    ref_cfg = os.path.join(ref_shims.REFERENCE_ROOT, "configs/test/1shot_split1.py")
+    if os.path.exists(ref_cfg):
+        model = copy.deepcopy(runpy.run_path(ref_cfg)["model"])
+    else:
+        from edgecape_b200.config import default_model_cfg
+        model = default_model_cfg()
+    from oracle.dinov2_oracle import vit_config
+    C = vit_config(pretrained)["embed_dim"]
+    model["pretrained"] = pretrained
+    model["keypoint_head"]["in_channels"] = C
+    model["keypoint_head"]["skeleton_head"]["dim_feedforward"] = C
+    return model
+
+
+def build_case(name):
+    case = CASES[name]
+    cfg = model_cfg_for(case["pretrained"])
+    data = make_episode(**case["episode"])
+    if "mask_row" in case:
+        for w in data["target_weight_s"]:
+            w[case["mask_row"]] = 0.0
+        data["img_metas"][case["mask_row"]]["sample_skeleton"] = [[]]
+    return cfg, data, case["wseed"]
+
+
+def run_reference(cfg, data, wseed):
+    bb = DinoV2Oracle(cfg["pretrained"])
+    det = ref_shims.build_reference_detector({k: v for k, v in cfg.items()}, bb)
+    shapes = {k: tuple(v.shape) for k, v in det.state_dict().items()}
+    sd = make_state_dict(shapes, wseed)
+    missing, unexpected = det.load_state_dict(sd, strict=True)
+    det.eval()
+    cap = {}
+    head = det.keypoint_head_module
+    hooks = [
+        head.query_proj.register_forward_hook(lambda m, i, o: cap.__setitem__("support_keypoints", o)),
+        head.skeleton_head.register_forward_hook(lambda m, i, o: cap.__setitem__("skel", o)),
+        head.transformer.encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("enc", o)),
+        head.transformer.proposal_generator.register_forward_hook(
+            lambda m, i, o: cap.__setitem__("prop", o)),
+        head.transformer.decoder.register_forward_hook(lambda m, i, o: cap.__setitem__("dec", o)),
+        head.register_forward_hook(lambda m, i, o: cap.__setitem__("head", o)),
+    ]
+    orig_refine = head.skeleton_head.refine_features
+
+    def refine(*a, **k):
+        r = orig_refine(*a, **k)
+        cap["skeleton_kp_features"] = r
+        return r
+
+    head.skeleton_head.refine_features = refine
+    orig_extract = det.extract_features
+
+    def extract(img_s, img_q):
+        fq, fs = orig_extract(img_s, img_q)
+        cap["feature_q"] = fq
+        return fq, fs
+
+    det.extract_features = extract
+    t0 = time.time()
+    with torch.no_grad():
+        res = det(return_loss=False, **data)
+    dt = time.time() - t0
+    for h in hooks:
+        h.remove()
+    adj, attn_adj, unnorm = cap["skel"]
+    enc_img, enc_kp = cap["enc"]
+    prop_loss, sim, prop = cap["prop"]
+    hs, qpts = cap["dec"][0], cap["dec"][1]
+    B = sim.shape[0]
+    g = dict(
+        feature_q=cap["feature_q"].flatten(2).transpose(1, 2),          # token-major [B,S,C]
+        support_keypoints=cap["support_keypoints"],
+        skeleton_kp_features=cap["skeleton_kp_features"],
+        adj=adj, unnormalized_adj=unnorm.to(torch.float32),
+        encoder_image=enc_img.transpose(0, 1), encoder_kp=enc_kp.transpose(0, 1),
+        initial_proposals_for_loss=prop_loss, similarity_map=sim, initial_proposals=prop,
+        argmax=sim.reshape(B, sim.shape[1], -1).argmax(dim=-1),
+        decoder_hs=hs.transpose(1, 2), out_points=torch.stack(list(qpts)),
+        output=cap["head"][0],
+    )
+    if attn_adj is not None:
+        g["attn_adj"] = attn_adj
+    g = {k: v.detach().cpu().numpy() for k, v in g.items()}
+    for k in ("preds", "boxes", "points", "skeleton"):
+        g[k] = np.asarray(res[k])
+    return g, sd, dt, res
+
+
+def compare(name, got, want, tol=2e-4):
+    """relative-to-scale max error; argmax must be identical."""
+    worst = 0.0
+    for k, w in want.items():
+        if k not in got:
+            continue
+        a = got[k].detach().cpu().numpy() if torch.is_tensor(got[k]) else np.asarray(got[k])
+        if k == "argmax":
+            assert np.array_equal(a, w), f"{name}:{k} argmax mismatch"
+            continue
+        a = a.astype(np.float64)
+        w64 = w.astype(np.float64)
+        assert a.shape == w64.shape, (name, k, a.shape, w64.shape)
+        err = np.abs(a - w64).max() / (np.abs(w64).max() + 1e-12)
+        worst = max(worst, err)
+        print(f"   {k:32s} shape={str(w.shape):20s} rel_err={err:.2e}")
+        assert err < tol, f"{name}:{k} rel err {err:.3e} >= {tol}"
+    return worst
+
+
+def main(argv):
+    assert ref_shims.reference_available(), "needs /root/reference (authoring container only)"
+    names = argv or list(CASES)
+    os.makedirs(os.path.join(REPO, "tests/golden"), exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    summary = {}
+    for name in names:
+        print(f"== {name}")
+        cfg, data, wseed = build_case(name)
+        g, sd, dt, _ = run_reference(cfg, data, wseed)
+        print(f"   reference forward_test: {dt:.2f}s")
+        t0 = time.time()
+        with torch.no_grad():
+            o32 = edgecape_oracle.detector_forward_test(sd, cfg, data, torch.float32)
+        print(f"   oracle fp32: {time.time() - t0:.2f}s")
+        worst32 = compare(name + "[fp32]", o32, g)
+        with torch.no_grad():
+            o64 = edgecape_oracle.detector_forward_test(sd, cfg, data, torch.float64)
+        worst64 = compare(name + "[fp64]", o64, g)
+        # keep files small: feature_q only for batch row 0
+        g["feature_q"] = g["feature_q"][:1]
+        g["encoder_image"] = g["encoder_image"][:1]
+        np.savez_compressed(os.path.join(REPO, "tests/golden", name + ".npz"), **g)
+        summary[name] = dict(oracle_fp32_vs_ref=worst32, oracle_fp64_vs_ref=worst64,
+                             ref_seconds=round(dt, 2))
+    path = os.path.join(REPO, "tests/golden/SUMMARY.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old.update(summary)
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+    print(json.dumps(summary, indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
