@@ -1,0 +1,214 @@
+// Skeleton / graph kernels: adjacency from edge lists, soft normalisation, edge-weight
+// prediction with Markov hop matrices, and the GCN feed-forward (aggregate + packed GEMM).
+#include "common.cuh"
+
+namespace ec {
+
+// One CTA per batch element.  `binary` (global, [K,K]) doubles as the scatter target.
+__global__ void __launch_bounds__(256) adj_from_edges_kernel(const int32_t* __restrict__ edges,
+                                                             const int32_t* __restrict__ offsets,
+                                                             const uint8_t* __restrict__ kp_mask,
+                                                             float* __restrict__ adj, float* __restrict__ binary,
+                                                             int K) {
+  const int b = blockIdx.x;
+  float* bin = binary + (long long)b * K * K;
+  const uint8_t* mk = kp_mask + (long long)b * K;
+  const int KK = K * K;
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) bin[i] = 0.f;
+  __syncthreads();
+  const int e0 = offsets[b], e1 = offsets[b + 1];
+  for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    int i = edges[2 * e], j = edges[2 * e + 1];
+    if (i < 0) i += K;   // torch advanced indexing wraps negative indices
+    if (j < 0) j += K;
+    if (i < 0 || j < 0 || i >= K || j >= K) continue;
+    if (mk[i] || mk[j]) continue;          // masked rows / columns are zeroed afterwards anyway
+    bin[i * K + j] = 1.f;
+    bin[j * K + i] = 1.f;
+  }
+  __syncthreads();
+  float* a0 = adj + (long long)b * 2 * KK;
+  float* a1 = a0 + KK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < K; i += nw) {
+    float s = 0.f;
+    for (int j = lane; j < K; j += 32) s += bin[i * K + j];
+    s = warp_sum(s);
+    const float valid = mk[i] ? 0.f : 1.f;
+    for (int j = lane; j < K; j += 32) {
+      // nan_to_num(0/0) = 0; a non-empty row has s >= 1
+      a1[i * K + j] = s > 0.f ? bin[i * K + j] / s : 0.f;
+      a0[i * K + j] = (i == j) ? valid : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) soft_normalize_kernel(const float* __restrict__ U,
+                                                             const uint8_t* __restrict__ kp_mask,
+                                                             float* __restrict__ adj, int K) {
+  const int b = blockIdx.x;
+  const int KK = K * K;
+  const float* u = U + (long long)b * KK;
+  const uint8_t* mk = kp_mask + (long long)b * K;
+  float* a0 = adj + (long long)b * 2 * KK;
+  float* a1 = a0 + KK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < K; i += nw) {
+    const float vi = mk[i] ? 0.f : 1.f;
+    float s = 0.f;
+    for (int j = lane; j < K; j += 32) s += u[i * K + j] * (vi * (mk[j] ? 0.f : 1.f));
+    s = warp_sum(s);
+    for (int j = lane; j < K; j += 32) {
+      a1[i * K + j] = u[i * K + j] * (vi * (mk[j] ? 0.f : 1.f)) / (s + 1e-8f);
+      a0[i * K + j] = (i == j) ? vi : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_weights_kernel(const float* __restrict__ S,
+                                                           const float* __restrict__ binary,
+                                                           const uint8_t* __restrict__ kp_mask, float zc_w,
+                                                           float zc_b, int use_zc, float* __restrict__ adj,
+                                                           float* __restrict__ unnorm, float* __restrict__ hop0,
+                                                           float* __restrict__ hop1, int K) {
+  const int b = blockIdx.x;
+  const int KK = K * K;
+  const float* s = S + (long long)b * KK;
+  const float* bin = binary + (long long)b * KK;
+  const uint8_t* mk = kp_mask + (long long)b * K;
+  float* a0 = adj + (long long)b * 2 * KK;
+  float* a1 = a0 + KK;
+  float* un = unnorm ? unnorm + (long long)b * KK : nullptr;
+  float* h0 = hop0 ? hop0 + (long long)b * KK : nullptr;
+  float* h1 = hop1 ? hop1 + (long long)b * KK : nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < K; i += nw) {
+    const float vi = mk[i] ? 0.f : 1.f;
+    auto value = [&](int j) {
+      float v = (s[i * K + j] + s[j * K + i]) / 2.0f;
+      if (use_zc) v = v * zc_w + zc_b;
+      v = fmaxf(bin[i * K + j] + v, 0.f);
+      return v * (vi * (mk[j] ? 0.f : 1.f));
+    };
+    float sum1 = 0.f;
+    for (int j = lane; j < K; j += 32) sum1 += value(j);
+    sum1 = warp_sum(sum1);
+    float sum2 = 0.f;
+    for (int j = lane; j < K; j += 32) sum2 += value(j) / (sum1 + 1e-8f);
+    sum2 = warp_sum(sum2);
+    for (int j = lane; j < K; j += 32) {
+      const float um = value(j);
+      const float a = um / (sum1 + 1e-8f);
+      a1[i * K + j] = a;
+      a0[i * K + j] = (i == j) ? vi : 0.f;
+      if (un) un[i * K + j] = um;
+      if (h0) h0[i * K + j] = (i == j) ? 1.f : 0.f;
+      if (h1) h1[i * K + j] = a / (sum2 + 1e-8f);
+    }
+  }
+}
+
+// Z[b,w,:] = [ a0[w] * X[b,w,:] | (A1 X)[b,w,:] (written by the batched GEMM) | a0[w] | rowsum(A1[w,:]) | 0 0 ]
+__global__ void __launch_bounds__(256) gcn_fill_kernel(const float* __restrict__ X,
+                                                       const float* __restrict__ adj, float* __restrict__ Z,
+                                                       int K, int d, int ldz) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= K) return;
+  const int w = warp;
+  const int KK = K * K;
+  const float* a0p = adj + (long long)b * 2 * KK;
+  const float* a1p = a0p + KK;
+  const float a0 = a0p[w * K + w];
+  float rs = 0.f;
+  for (int v = lane; v < K; v += 32) rs += a1p[w * K + v];
+  rs = warp_sum(rs);
+  const float* x = X + ((long long)b * K + w) * d;
+  float* z = Z + ((long long)b * K + w) * ldz;
+  for (int c = lane; c < d; c += 32) z[c] = a0 * x[c];
+  if (lane == 0) {
+    z[2 * d + 0] = a0;
+    z[2 * d + 1] = rs;
+    z[2 * d + 2] = 0.f;
+    z[2 * d + 3] = 0.f;
+  }
+}
+
+// Wp[c, :] = [ W[c, 0:d] | W[dff + c, 0:d] | bias[c] | bias[dff + c] | 0 0 ]
+__global__ void gcn_pack_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                float* __restrict__ Wp, int d, int dff) {
+  const int ld = 2 * d + 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)dff * ld) return;
+  int c = (int)(i / ld), k = (int)(i % ld);
+  float v = 0.f;
+  if (k < d) v = W[(long long)c * d + k];
+  else if (k < 2 * d) v = W[(long long)(dff + c) * d + (k - d)];
+  else if (k == 2 * d) v = bias[c];
+  else if (k == 2 * d + 1) v = bias[dff + c];
+  Wp[i] = v;
+}
+
+}  // namespace ec
+
+using namespace ec;
+
+extern "C" int ec_adj_from_edges(const int32_t* edges, const int32_t* offsets, const uint8_t* kp_mask,
+                                 float* adj, float* binary, int B, int K, void* stream) {
+  EC_REQUIRE(offsets && kp_mask && adj && binary, "ec_adj_from_edges: null pointer");
+  if (B == 0) return EC_OK;
+  adj_from_edges_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(edges, offsets, kp_mask, adj, binary, K);
+  return check_launch("ec_adj_from_edges");
+}
+
+extern "C" int ec_soft_normalize_adj(const float* U, const uint8_t* kp_mask, float* adj, int B, int K,
+                                     void* stream) {
+  EC_REQUIRE(U && kp_mask && adj, "ec_soft_normalize_adj: null pointer");
+  if (B == 0) return EC_OK;
+  soft_normalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(U, kp_mask, adj, K);
+  return check_launch("ec_soft_normalize_adj");
+}
+
+extern "C" int ec_edge_weights(const float* S, const float* binary, const uint8_t* kp_mask, float zc_w,
+                               float zc_b, int use_zero_conv, float* adj, float* unnorm, float* hop0,
+                               float* hop1, int B, int K, void* stream) {
+  EC_REQUIRE(S && binary && kp_mask && adj, "ec_edge_weights: null pointer");
+  if (B == 0) return EC_OK;
+  edge_weights_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(S, binary, kp_mask, zc_w, zc_b, use_zero_conv, adj,
+                                                           unnorm, hop0, hop1, K);
+  return check_launch("ec_edge_weights");
+}
+
+extern "C" size_t ec_workspace_bytes_gcn(int B, int K, int d, int dff) {
+  (void)dff;
+  return (size_t)B * K * (2 * d + 4) * sizeof(float);
+}
+
+extern "C" int ec_gcn_pack_weights(const float* W, const float* bias, float* Wp, int d, int dff, void* stream) {
+  EC_REQUIRE(W && bias && Wp, "ec_gcn_pack_weights: null pointer");
+  long long total = (long long)dff * (2 * d + 4);
+  gcn_pack_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(W, bias, Wp, d, dff);
+  return check_launch("ec_gcn_pack_weights");
+}
+
+extern "C" int ec_gcn(const float* X, const float* adj, const float* Wp, float* Y, int B, int K, int d, int dff,
+                      float* workspace, size_t workspace_bytes, void* stream) {
+  EC_REQUIRE(X && adj && Wp && Y && workspace, "ec_gcn: null pointer");
+  EC_REQUIRE(workspace_bytes >= ec_workspace_bytes_gcn(B, K, d, dff), "ec_gcn: workspace too small");
+  EC_REQUIRE(d % 4 == 0, "ec_gcn: d must be a multiple of 4");
+  if (B == 0 || K == 0) return EC_OK;
+  const int ldz = 2 * d + 4;
+  const long long KK = (long long)K * K;
+  // Z[:, d:2d] = A1 X   (batched [K,K] x [K,d])
+  int rc = ec_gemm(adj + KK, X, workspace + d, K, d, K, K, d, ldz, /*b_kmajor=*/0, B, 2 * KK, (long long)K * d,
+                   (long long)K * ldz, nullptr, EC_ACT_NONE, nullptr, nullptr, 0, 0, EC_RES_NONE, stream);
+  if (rc) return rc;
+  dim3 grid(cdiv(K, 8), B);
+  gcn_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, adj, workspace, K, d, ldz);
+  rc = check_launch("ec_gcn(fill)");
+  if (rc) return rc;
+  // Y = relu(Z Wp^T): biases ride along as the two extra K columns
+  return ec_gemm(workspace, Wp, Y, B * K, dff, ldz, ldz, ldz, dff, /*b_kmajor=*/1, 1, 0, 0, 0, nullptr,
+                 EC_ACT_RELU, nullptr, nullptr, 0, 0, EC_RES_NONE, stream);
+}

@@ -1,0 +1,207 @@
+// Row-wise kernels: LayerNorm (+ fused residual), positional adds, row copies, L2 normalisation,
+// mask bookkeeping and the sigmoid-space point update.  One warp per row, shuffle reductions.
+#include "common.cuh"
+
+namespace ec {
+
+// ------------------------------------------------------------------------------ LayerNorm
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ X, int ldx, int seg,
+                                                        long long seg_stride, const float* __restrict__ R,
+                                                        int ldr, float* __restrict__ sum_out, int ld_sum,
+                                                        float* __restrict__ Y, int ldy,
+                                                        const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps, int M, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int m = warp;
+  const float* x = seg > 0 ? X + (long long)(m / seg) * seg_stride + (long long)(m % seg) * ldx
+                           : X + (long long)m * ldx;
+  const float* r = R ? R + (long long)m * ldr : nullptr;
+  float* so = sum_out ? sum_out + (long long)m * ld_sum : nullptr;
+  // pass 1: mean (and optional materialisation of x + r)
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float v = x[c];
+    if (r) v += r[c];
+    if (so) so[c] = v;
+    s += v;
+  }
+  const float mean = warp_sum(s) / (float)C;
+  // pass 2: centred second moment (two-pass variance, as torch's CPU/CUDA kernels)
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float v = x[c];
+    if (r) v += r[c];
+    float d = v - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = warp_sum(q) / (float)C;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  float* y = Y + (long long)m * ldy;
+  for (int c = lane; c < C; c += 32) {
+    float v = x[c];
+    if (r) v += r[c];
+    y[c] = (v - mean) * rstd * w[c] + b[c];
+  }
+}
+
+__global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__ P, int T, int S, int C,
+                                long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long row = i / C;
+  int s = (int)(row % S);
+  long long b = row / S;
+  X[(b * T + s) * C + c] += P[(long long)s * C + c];
+}
+
+__global__ void copy_rows_kernel(const float* __restrict__ X, int ldx, int segx, long long sstridex,
+                                 float* __restrict__ Y, int ldy, int segy, long long sstridey, int C,
+                                 int bcast_rows, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long m = i / C;
+  long long ms = bcast_rows > 0 ? (m % bcast_rows) : m;
+  const float* x = segx > 0 ? X + (ms / segx) * sstridex + (ms % segx) * ldx : X + ms * ldx;
+  float* y = segy > 0 ? Y + (m / segy) * sstridey + (m % segy) * ldy : Y + m * ldy;
+  y[c] = x[c];
+}
+
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ X, float* __restrict__ Y,
+                                                           int M, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* x = X + (long long)warp * C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) q = fmaf(x[c], x[c], q);
+  const float nrm = sqrtf(warp_sum(q)) + eps;
+  float* y = Y + (long long)warp * C;
+  for (int c = lane; c < C; c += 32) y[c] = x[c] / nrm;
+}
+
+__global__ void mask_accumulate_kernel(const float* __restrict__ tw, float* __restrict__ mask_s, int n,
+                                       int first) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = tw[i];
+  mask_s[i] = first ? t * t : mask_s[i] * t;
+}
+
+__global__ void kp_masks_kernel(const float* __restrict__ mask_s, uint8_t* __restrict__ kp_mask,
+                                uint8_t* __restrict__ kp_fixed, int K) {
+  // one block per batch row
+  const int b = blockIdx.x;
+  __shared__ int any_valid;
+  if (threadIdx.x == 0) any_valid = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    // reference: kp_mask = ~mask_s.to(bool): masked iff mask_s == 0
+    uint8_t m = (mask_s[(long long)b * K + k] == 0.0f) ? 1 : 0;
+    kp_mask[(long long)b * K + k] = m;
+    kp_fixed[(long long)b * K + k] = m;
+    if (!m) any_valid = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && !any_valid) kp_fixed[(long long)b * K] = 0;
+}
+
+__device__ __forceinline__ float inv_sigmoid(float x) {
+  const float eps = 1e-3f;
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  float x1 = fmaxf(x, eps);
+  float x2 = fmaxf(1.0f - x, eps);
+  return logf(x1 / x2);
+}
+
+__global__ void point_update_kernel(const float* __restrict__ bi, const float* __restrict__ delta, int ldd,
+                                    float* __restrict__ out, int M) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * M) return;
+  int m = i >> 1, c = i & 1;
+  float z = inv_sigmoid(bi[i]) + delta[(long long)m * ldd + c];
+  out[i] = 1.0f / (1.0f + expf(-z));
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                             float a, float b, float div, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = a * x[i];
+  if (b != 0.f) v += b * y[i];
+  out[i] = div != 1.0f ? v / div : v;
+}
+
+}  // namespace ec
+
+using namespace ec;
+
+extern "C" int ec_axpby(const float* x, const float* y, float* out, float a, float b, float div, long long n,
+                        void* stream) {
+  EC_REQUIRE(x && y && out, "ec_axpby: null pointer");
+  if (n == 0) return EC_OK;
+  axpby_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, out, a, b, div, n);
+  return check_launch("ec_axpby");
+}
+
+extern "C" int ec_layernorm(const float* X, int ldx, int seg, long long seg_stride, const float* R, int ldr,
+                            float* sum_out, int ld_sum, float* Y, int ldy, const float* w, const float* b,
+                            float eps, int M, int C, void* stream) {
+  EC_REQUIRE(X && Y && w && b, "ec_layernorm: null pointer");
+  EC_REQUIRE(M >= 0 && C > 0, "ec_layernorm: bad shape");
+  if (M == 0) return EC_OK;
+  const int warps_per_block = 8;
+  layernorm_kernel<<<cdiv(M, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C);
+  return check_launch("ec_layernorm");
+}
+
+extern "C" int ec_add_rows(float* X, const float* P, int batch, int T, int S, int C, void* stream) {
+  EC_REQUIRE(X && P && S <= T, "ec_add_rows: bad arguments");
+  long long total = (long long)batch * S * C;
+  if (total == 0) return EC_OK;
+  add_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(X, P, T, S, C, total);
+  return check_launch("ec_add_rows");
+}
+
+extern "C" int ec_copy_rows(const float* X, int ldx, int seg_x, long long seg_stride_x, float* Y, int ldy,
+                            int seg_y, long long seg_stride_y, int M, int C, int bcast_rows, void* stream) {
+  EC_REQUIRE(X && Y, "ec_copy_rows: null pointer");
+  long long total = (long long)M * C;
+  if (total == 0) return EC_OK;
+  copy_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, seg_x, seg_stride_x, Y, ldy, seg_y,
+                                                                       seg_stride_y, C, bcast_rows, total);
+  return check_launch("ec_copy_rows");
+}
+
+extern "C" int ec_l2_normalize(const float* X, float* Y, int M, int C, float eps, void* stream) {
+  EC_REQUIRE(X && Y, "ec_l2_normalize: null pointer");
+  if (M == 0) return EC_OK;
+  l2_normalize_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(X, Y, M, C, eps);
+  return check_launch("ec_l2_normalize");
+}
+
+extern "C" int ec_mask_accumulate(const float* tw, float* mask_s, int n, int first, void* stream) {
+  EC_REQUIRE(tw && mask_s, "ec_mask_accumulate: null pointer");
+  if (n == 0) return EC_OK;
+  mask_accumulate_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(tw, mask_s, n, first);
+  return check_launch("ec_mask_accumulate");
+}
+
+extern "C" int ec_kp_masks(const float* mask_s, uint8_t* kp_mask, uint8_t* kp_mask_fixed, int B, int K,
+                           void* stream) {
+  EC_REQUIRE(mask_s && kp_mask && kp_mask_fixed, "ec_kp_masks: null pointer");
+  if (B == 0) return EC_OK;
+  kp_masks_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(mask_s, kp_mask, kp_mask_fixed, K);
+  return check_launch("ec_kp_masks");
+}
+
+extern "C" int ec_point_update(const float* bi, const float* delta, int ldd, float* out, int M, void* stream) {
+  EC_REQUIRE(bi && delta && out, "ec_point_update: null pointer");
+  if (M == 0) return EC_OK;
+  point_update_kernel<<<cdiv(2LL * M, 256), 256, 0, (cudaStream_t)stream>>>(bi, delta, ldd, out, M);
+  return check_launch("ec_point_update");
+}

@@ -1,0 +1,376 @@
+"""Tensor-level wrappers over the C ABI (include/edgecape_b200.h).
+
+Every function takes CUDA fp32 torch tensors (views with a unit innermost stride are fine: row
+and batch strides are forwarded as ld / stride arguments), enqueues the kernels on torch's
+current stream and returns the output tensor.  PyTorch is used for allocation and streams only;
+no torch compute op is called here, and nothing falls back to the CPU.
+"""
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
+RES_NONE, RES_ADD, RES_GATE = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.EdgeCapeLibraryError(
+            f"{name} is on {t.device}: edgecape_b200 has no CPU path (the CUDA library is the product)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rows(t, name):
+    """2-D / 3-D view with unit inner stride -> (batch, rows, cols, ld, batch_stride)."""
+    _chk(t, name)
+    if t.dim() == 2:
+        M, C = t.shape
+        assert C <= 1 or t.stride(1) == 1, f"{name}: inner stride must be 1"
+        return 1, M, C, (t.stride(0) if M > 1 else max(C, t.stride(0))), 0
+    assert t.dim() == 3, f"{name}: expected 2-D or 3-D"
+    B, M, C = t.shape
+    assert C <= 1 or t.stride(2) == 1, f"{name}: inner stride must be 1"
+    ld = t.stride(1) if M > 1 else max(C, t.stride(1))
+    return B, M, C, ld, (t.stride(0) if B > 1 else 0)
+
+
+def empty(*shape, dtype=torch.float32, device=None):
+    return torch.empty(*shape, dtype=dtype, device=device or torch.device("cuda", torch.cuda.current_device()))
+
+
+def gemm(a, b, out=None, b_kmajor=True, bias=None, act=ACT_NONE, colscale=None, residual=None,
+         res_mode=RES_ADD):
+    """out = epilogue(a @ b^T) (b_kmajor: b is [N,K]) or a @ b (b is [K,N]); 2-D or batched 3-D."""
+    ba, M, K, lda, sA = _rows(a, "a")
+    bb, r0, r1, ldb, sB = _rows(b, "b")
+    N, Kb = (r0, r1) if b_kmajor else (r1, r0)
+    assert Kb == K, f"gemm: inner dimensions differ ({K} vs {Kb})"
+    batch = max(ba, bb)
+    assert ba in (1, batch) and bb in (1, batch)
+    if out is None:
+        out = empty(batch, M, N, device=a.device) if (a.dim() == 3 or b.dim() == 3) else empty(M, N, device=a.device)
+    bo, Mo, No, ldc, sC = _rows(out, "out")
+    assert (Mo, No) == (M, N) and bo == batch, f"gemm: out shape {tuple(out.shape)} != {(batch, M, N)}"
+    ldr, sR = 0, 0
+    if residual is not None:
+        br, Mr, Nr, ldr, sR = _rows(residual, "residual")
+        assert (Mr, Nr) == (M, N) and br in (1, batch)
+    else:
+        res_mode = RES_NONE
+    _chk(bias, "bias")
+    _chk(colscale, "colscale")
+    _lib.call("ec_gemm", _p(a), _p(b), _p(out), M, N, K, lda, ldb, ldc, 1 if b_kmajor else 0, batch,
+              sA if ba > 1 else 0, sB if bb > 1 else 0, sC, _p(bias), act, _p(colscale), _p(residual), ldr, sR,
+              res_mode, _stream())
+    return out
+
+
+def linear(x, w, bias=None, **kw):
+    """nn.Linear on the last dimension of a 2-D/3-D view; w is [N,K] (conv 1x1 weights are reshaped)."""
+    if w.dim() > 2:
+        w = w.reshape(w.shape[0], -1)
+    return gemm(x, w, b_kmajor=True, bias=bias, **kw)
+
+
+def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None):
+    """LayerNorm over the last dim of x (+ residual).  A 3-D x view [B,S,C] with a batch stride
+    larger than S*ld (e.g. ViT tokens without the cls row) is read in place."""
+    _chk(x, "x")
+    seg, seg_stride = 0, 0
+    if x.dim() == 3:
+        B, S, C = x.shape
+        ldx = x.stride(1)
+        if x.stride(0) != S * ldx:
+            seg, seg_stride = S, x.stride(0)
+        M = B * S
+    else:
+        M, C = x.shape
+        ldx = x.stride(0)
+    assert x.stride(-1) == 1
+    if out is None:
+        out = empty(*x.shape, device=x.device)
+    o2 = out.reshape(M, C) if out.is_contiguous() else out
+    assert o2.dim() == 2 and o2.stride(1) == 1
+    ldr = ld_sum = 0
+    if residual is not None:
+        _chk(residual, "residual")
+        r2 = residual.reshape(M, C) if residual.is_contiguous() else residual
+        assert r2.dim() == 2 and r2.stride(1) == 1
+        residual, ldr = r2, r2.stride(0)
+    if sum_out is not None:
+        s2 = sum_out.reshape(M, C) if sum_out.is_contiguous() else sum_out
+        assert s2.dim() == 2 and s2.stride(1) == 1
+        sum_out, ld_sum = s2, s2.stride(0)
+    _lib.call("ec_layernorm", _p(x), ldx, seg, seg_stride, _p(residual), ldr, _p(sum_out), ld_sum, _p(o2),
+              o2.stride(0), _p(w), _p(b), float(eps), M, C, _stream())
+    return out
+
+
+def add_rows_(x, pos, S):
+    """x[b, :S, :] += pos[:S, :]  in place; x contiguous [B,T,C]."""
+    _chk(x, "x"); _chk(pos, "pos")
+    assert x.is_contiguous() and pos.is_contiguous()
+    B, T, C = x.shape
+    _lib.call("ec_add_rows", _p(x), _p(pos), B, T, S, C, _stream())
+    return x
+
+
+def _seg(t, name):
+    """2-D [M,C] or 3-D [B,S,C] view -> (M, C, ld, seg, seg_stride)."""
+    _chk(t, name)
+    assert t.shape[-1] <= 1 or t.stride(-1) == 1, f"{name}: inner stride must be 1"
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], t.stride(0), 0, 0
+    B, S, C = t.shape
+    if t.stride(0) == S * t.stride(1):
+        return B * S, C, t.stride(1), 0, 0
+    return B * S, C, t.stride(1), S, t.stride(0)
+
+
+def copy_rows(x, out, bcast_rows=0):
+    """out[m, :] = x[m % bcast_rows if bcast_rows else m, :] for 2-D / 3-D row views."""
+    Mx, C, ldx, sx, ssx = _seg(x, "x")
+    M, Co, ldy, sy, ssy = _seg(out, "out")
+    assert C == Co and (bcast_rows > 0 or Mx == M)
+    _lib.call("ec_copy_rows", _p(x), ldx, sx, ssx, _p(out), ldy, sy, ssy, M, C, bcast_rows, _stream())
+    return out
+
+
+def axpby(x, y, a=1.0, b=1.0, div=1.0, out=None):
+    """(a*x + b*y) / div elementwise on contiguous tensors of equal size."""
+    _chk(x, "x"); _chk(y, "y")
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    if out is None:
+        out = empty(*x.shape, device=x.device)
+    _lib.call("ec_axpby", _p(x), _p(y), _p(out), float(a), float(b), float(div), x.numel(), _stream())
+    return out
+
+
+def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None):
+    """q [B,Lq,H*D], k [B,Lk,H*D], v [B,Lk,H*D] views (unit inner stride) -> [B,Lq,H*D]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, n)
+        assert t.dim() == 3 and t.stride(2) == 1
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    D = E // nheads
+    assert k.shape[2] == E and v.shape[2] == E and v.shape[1] == Lk
+    if out is None:
+        out = empty(B, Lq, E, device=q.device)
+    assert out.stride(2) == 1
+    if scale is None:
+        scale = D ** -0.5
+    _chk(key_mask, "key_mask", torch.uint8)
+    _chk(bias, "bias")
+    if key_mask is not None:
+        assert key_mask.is_contiguous() and tuple(key_mask.shape) == (B, Lk)
+    if bias is not None:
+        assert bias.is_contiguous() and tuple(bias.shape) == (B, nheads, Lq, Lk)
+    _lib.call("ec_attention", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
+              v.stride(1), out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale),
+              _p(key_mask), _p(bias), _stream())
+    return out
+
+
+def hop_bias(attn_adj, w0, b0, w1, b1, out=None):
+    """attn_adj [n_hops,B,K,K] -> bias [B,H,K,K] through Linear(n_hops,hidden)-ReLU-Linear(hidden,H)."""
+    _chk(attn_adj, "attn_adj")
+    assert attn_adj.is_contiguous()
+    n_hops, B, K, _ = attn_adj.shape
+    hidden, H = w0.shape[0], w1.shape[0]
+    if out is None:
+        out = empty(B, H, K, K, device=attn_adj.device)
+    _lib.call("ec_hop_bias", _p(attn_adj), _p(w0), _p(b0), _p(w1), _p(b1), _p(out), B, K, n_hops, hidden, H,
+              _stream())
+    return out
+
+
+def mask_accumulate_(tw, mask_s, first):
+    _chk(tw, "tw"); _chk(mask_s, "mask_s")
+    assert tw.is_contiguous() and mask_s.is_contiguous() and tw.numel() == mask_s.numel()
+    _lib.call("ec_mask_accumulate", _p(tw), _p(mask_s), mask_s.numel(), 1 if first else 0, _stream())
+    return mask_s
+
+
+def kp_masks(mask_s):
+    """mask_s [B,K] float -> (kp_mask, kp_mask_fixed) uint8 [B,K] (1 = padded keypoint)."""
+    _chk(mask_s, "mask_s")
+    B, K = mask_s.shape
+    m = empty(B, K, dtype=torch.uint8, device=mask_s.device)
+    mf = empty(B, K, dtype=torch.uint8, device=mask_s.device)
+    _lib.call("ec_kp_masks", _p(mask_s), _p(m), _p(mf), B, K, _stream())
+    return m, mf
+
+
+def adj_from_edges(edges, offsets, kp_mask, K):
+    """CSR edge lists (int32 device tensors) -> adj [B,2,K,K], binary [B,K,K]."""
+    _chk(edges, "edges", torch.int32); _chk(offsets, "offsets", torch.int32); _chk(kp_mask, "kp_mask", torch.uint8)
+    B = kp_mask.shape[0]
+    adj = empty(B, 2, K, K, device=kp_mask.device)
+    binary = empty(B, K, K, device=kp_mask.device)
+    _lib.call("ec_adj_from_edges", _p(edges), _p(offsets), _p(kp_mask), _p(adj), _p(binary), B, K, _stream())
+    return adj, binary
+
+
+def soft_normalize_adj(U, kp_mask):
+    _chk(U, "U"); _chk(kp_mask, "kp_mask", torch.uint8)
+    B, K, _ = U.shape
+    assert U.is_contiguous()
+    adj = empty(B, 2, K, K, device=U.device)
+    _lib.call("ec_soft_normalize_adj", _p(U), _p(kp_mask), _p(adj), B, K, _stream())
+    return adj
+
+
+def l2_normalize(x, eps=1e-8):
+    _chk(x, "x")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    out = empty(*x.shape, device=x.device)
+    _lib.call("ec_l2_normalize", _p(x), _p(out), x.numel() // C, C, float(eps), _stream())
+    return out
+
+
+def edge_weights(S, binary, kp_mask, zc_w, zc_b, use_zero_conv, hops=None):
+    """Gram matrix S [B,K,K] -> adj [B,2,K,K], unnorm [B,K,K]; fills hops[0], hops[1] if given."""
+    _chk(S, "S"); _chk(binary, "binary"); _chk(kp_mask, "kp_mask", torch.uint8)
+    B, K, _ = S.shape
+    assert S.is_contiguous() and binary.is_contiguous()
+    adj = empty(B, 2, K, K, device=S.device)
+    unnorm = empty(B, K, K, device=S.device)
+    h0 = hops[0] if hops is not None else None
+    h1 = hops[1] if hops is not None and hops.shape[0] > 1 else None
+    _lib.call("ec_edge_weights", _p(S), _p(binary), _p(kp_mask), float(zc_w), float(zc_b), int(use_zero_conv),
+              _p(adj), _p(unnorm), _p(h0), _p(h1), B, K, _stream())
+    return adj, unnorm
+
+
+def gcn_pack_weights(W, bias):
+    """Conv1d(k=1) weight [2*dff, d(,1)] + bias [2*dff] -> packed [dff, 2d+4]."""
+    _chk(W, "W"); _chk(bias, "bias")
+    W = W.reshape(W.shape[0], -1).contiguous()
+    dff, d = W.shape[0] // 2, W.shape[1]
+    Wp = empty(dff, 2 * d + 4, device=W.device)
+    _lib.call("ec_gcn_pack_weights", _p(W), _p(bias), _p(Wp), d, dff, _stream())
+    return Wp
+
+
+def gcn(x, adj, Wp, out=None):
+    """x [B,K,d], adj [B,2,K,K] (plane 0 diagonal), packed weights -> relu(GCN) [B,K,dff]."""
+    _chk(x, "x"); _chk(adj, "adj"); _chk(Wp, "Wp")
+    assert x.is_contiguous() and adj.is_contiguous()
+    B, K, d = x.shape
+    dff = Wp.shape[0]
+    assert Wp.shape[1] == 2 * d + 4
+    if out is None:
+        out = empty(B, K, dff, device=x.device)
+    assert out.is_contiguous()
+    nbytes = _lib.load().ec_workspace_bytes_gcn(B, K, d, dff)
+    ws = empty(nbytes // 4, device=x.device)
+    _lib.call("ec_gcn", _p(x), _p(adj), _p(Wp), _p(out), B, K, d, dff, _p(ws), nbytes, _stream())
+    return out
+
+
+def support_weights(target, rowscale, h, w, out=None):
+    """target [B,K,hm,hm] heat-maps -> pooling weights [B,K,h*w] (see include/edgecape_b200.h)."""
+    _chk(target, "target"); _chk(rowscale, "rowscale")
+    assert target.is_contiguous()
+    B, K, hm_h, hm_w = target.shape
+    if out is None:
+        out = empty(B, K, h * w, device=target.device)
+    assert out.stride(2) == 1 and out.stride(0) == K * out.stride(1)
+    _lib.call("ec_support_weights", _p(target), _p(rowscale), _p(out), out.stride(1), B * K, hm_h, hm_w, h, w,
+              _stream())
+    return out
+
+
+def sine_pe_coords(coord, num_feats=128, temperature=10000.0, scale=6.283185307179586, out=None):
+    """coord [..., 2] (x,y) -> [..., 2*num_feats] DETR sine encoding, channels [y-half | x-half]."""
+    _chk(coord, "coord")
+    assert coord.is_contiguous() and coord.shape[-1] == 2
+    M = coord.numel() // 2
+    if out is None:
+        out = empty(*coord.shape[:-1], 2 * num_feats, device=coord.device)
+    o2 = out.reshape(M, -1) if out.is_contiguous() else out
+    assert o2.dim() == 2 and o2.stride(1) == 1
+    _lib.call("ec_sine_pe_coords", _p(coord), _p(o2), o2.stride(0), M, num_feats, float(temperature), float(scale),
+              _stream())
+    return out
+
+
+def proposal(sim, h, w):
+    """sim [B,K,h*w] -> (proposal_for_loss [B,K,2], proposals [B,K,2], argmax int64 [B,K])."""
+    _chk(sim, "sim")
+    assert sim.is_contiguous()
+    B, K = sim.shape[:2]
+    pl = empty(B, K, 2, device=sim.device)
+    pr = empty(B, K, 2, device=sim.device)
+    am = empty(B, K, dtype=torch.int64, device=sim.device)
+    _lib.call("ec_proposal", _p(sim), _p(pl), _p(pr), _p(am), B * K, h, w, _stream())
+    return pl, pr, am
+
+
+def point_update(bi, delta, out=None):
+    """sigmoid(inverse_sigmoid(bi) + delta); bi [...,2] contiguous, delta [M,2] view."""
+    _chk(bi, "bi"); _chk(delta, "delta")
+    assert bi.is_contiguous()
+    M = bi.numel() // 2
+    d2 = delta.reshape(M, 2) if delta.is_contiguous() else delta
+    assert d2.stride(1) == 1
+    if out is None:
+        out = empty(*bi.shape, device=bi.device)
+    _lib.call("ec_point_update", _p(bi), _p(d2), d2.stride(0), _p(out), M, _stream())
+    return out
+
+
+def im2col_patches(img, P, ldc=None):
+    _chk(img, "img")
+    assert img.is_contiguous()
+    B, C3, H, W = img.shape
+    assert C3 == 3
+    h0, w0 = H // P, W // P
+    ldc = ldc or 3 * P * P
+    cols = empty(B * h0 * w0, ldc, device=img.device)
+    _lib.call("ec_im2col_patches", _p(img), _p(cols), B, H, W, P, ldc, _stream())
+    return cols
+
+
+def interp_pos_embed(pos_embed, h0, w0, offset=0.1):
+    """pos_embed [1, 1+M*M, C] -> [1+h0*w0, C] (DINOv2 interpolate_pos_encoding)."""
+    _chk(pos_embed, "pos_embed")
+    pe = pos_embed.reshape(-1, pos_embed.shape[-1]).contiguous()
+    N = pe.shape[0] - 1
+    Mg = int(round(N ** 0.5))
+    assert Mg * Mg == N
+    out = empty(1 + h0 * w0, pe.shape[1], device=pe.device)
+    _lib.call("ec_interp_pos_embed", _p(pe), _p(out), Mg, h0, w0, pe.shape[1], float(offset), _stream())
+    return out
+
+
+def write_cls_(tokens, cls, pos0):
+    _chk(tokens, "tokens")
+    B, T, C = tokens.shape
+    assert tokens.stride(2) == 1
+    _lib.call("ec_write_cls", _p(cls), _p(pos0), _p(tokens), B, tokens.stride(0), C, _stream())
+    return tokens
+
+
+def pck_accumulate_(counters, pred, gt, valid, norm, thr):
+    _chk(pred, "pred"); _chk(gt, "gt"); _chk(valid, "valid", torch.uint8); _chk(norm, "norm"); _chk(thr, "thr")
+    _chk(counters, "counters", torch.float64)
+    B, K, _ = pred.shape
+    assert pred.is_contiguous() and gt.is_contiguous() and valid.is_contiguous() and norm.is_contiguous()
+    assert counters.numel() >= thr.numel() + 1
+    _lib.call("ec_pck_accumulate", _p(pred), _p(gt), _p(valid), _p(norm), _p(thr), thr.numel(), _p(counters), B, K,
+              _stream())
+    return counters

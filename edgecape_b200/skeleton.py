@@ -1,0 +1,147 @@
+"""@HEADS SkeletonPredictor (edge-weight predictor) on the edgecape_b200 kernels.
+
+Same constructor kwargs and state-dict keys as
+/root/reference/EdgeCape/models/keypoint_heads/skeleton.py:9-56; arithmetic of `forward` (:58-80),
+`refine_features` (:82-115), `predict_skeleton` / `combine_adj` (:134-150),
+`markov_transition_matrix` (:152-161), `adj_mx_from_edges` / `normalize_adj` (:171-194) and
+`soft_normalize_adj` (:196-205).  `k_proj`, `q_proj` and `mh_linear` exist as parameters only
+(the reference never uses them in forward, :49-51) so checkpoints load without missing keys.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import decoder_layer_shapes, _lin_keys
+from .params import PackedMixin, ParamTree, xavier_uniform_all_
+from .registry import HEADS
+from .transformer import decoder_layer_forward, pack_decoder_layer
+
+
+def edges_to_csr(skeleton, device):
+    """list (batch) of edge lists [[i,j],...] -> (edges int32 [E,2], offsets int32 [B+1]) on `device`.
+    Ragged / empty lists are fine (the reference skips 1-D edge tensors, skeleton.py:177)."""
+    offs = [0]
+    flat = []
+    for e in skeleton:
+        a = np.asarray(e.cpu() if torch.is_tensor(e) else e, dtype=np.int64)
+        if a.ndim > 1 and a.size > 0:
+            flat.append(a.reshape(-1, a.shape[-1])[:, :2])
+            offs.append(offs[-1] + flat[-1].shape[0])
+        else:
+            offs.append(offs[-1])
+    edges = np.concatenate(flat, axis=0) if flat else np.zeros((0, 2), dtype=np.int64)
+    host = torch.from_numpy(np.concatenate((np.asarray(offs, dtype=np.int32),
+                                            edges.astype(np.int32).reshape(-1))))
+    buf = host.to(device, non_blocking=True)          # one small H2D copy
+    B = len(skeleton)
+    offsets = buf[:B + 1]
+    e = buf[B + 1:]
+    if e.numel() == 0:
+        e = torch.zeros(2, dtype=torch.int32, device=device)
+    return e, offsets
+
+
+@HEADS.register_module(force=True)
+class SkeletonPredictor(PackedMixin, nn.Module):
+    def __init__(self, d_model=256, nhead=8, num_layers=3, dim_feedforward=384, dropout=0.1, activation="relu",
+                 normalize_before=False, learn_skeleton: bool = False, max_hop: int = 5,
+                 adj_normalization: bool = True, markov_bias: bool = True, mask_res: bool = False,
+                 use_zero_conv: bool = True, max_hops: int = 4, two_way_attn: bool = True, gcn_norm: bool = False):
+        super().__init__()
+        self._init_packed()
+        if normalize_before or activation != "relu" or not adj_normalization or mask_res or gcn_norm:
+            raise NotImplementedError(
+                "SkeletonPredictor: only the configuration used by the EdgeCape configs is implemented "
+                "(relu, post-norm, adj_normalization=True, mask_res=False, gcn_norm=False)")
+        self.d_model, self.num_heads, self.num_layers = d_model, nhead, num_layers
+        self.dim_feedforward = dim_feedforward
+        self.learn_skeleton = learn_skeleton
+        self.max_hop = max_hop
+        self.markov_bias = markov_bias
+        self.use_zero_conv = use_zero_conv
+        self.two_way_attn = two_way_attn
+        s = {}
+        for i in range(num_layers):
+            s.update(decoder_layer_shapes(str(i), d_model, nhead, dim_feedforward, False, max_hops, two_way_attn))
+        if num_layers > 0:
+            self.skeleton_predictor = ParamTree(s)
+        top = {"image_project.weight": (d_model, dim_feedforward, 1, 1), "image_project.bias": (d_model,),
+               "mh_linear.weight": (1, nhead, 1, 1), "mh_linear.bias": (1,)}
+        top.update(_lin_keys("k_proj", d_model, d_model))
+        top.update(_lin_keys("q_proj", d_model, d_model))
+        if use_zero_conv:
+            top.update({"zero_conv.weight": (1, 1, 1, 1), "zero_conv.bias": (1,)})
+        tree = ParamTree(top)
+        for name, child in tree.named_children():
+            self.add_module(name, child)
+        for n, p in self.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                nn.init.ones_(p)
+
+    def init_weights(self):
+        xavier_uniform_all_(self)
+
+    def _pack(self):
+        pk = {"layers": [pack_decoder_layer(getattr(self.skeleton_predictor, str(i)), False, False,
+                                            self.two_way_attn) for i in range(self.num_layers)]}
+        if self.use_zero_conv:
+            # two scalars of the 1x1 zero-conv: read once per checkpoint, not per forward
+            pk["zc"] = (float(self.zero_conv.weight.reshape(-1)[0]), float(self.zero_conv.bias.reshape(-1)[0]))
+        else:
+            pk["zc"] = (1.0, 0.0)
+        return pk
+
+    @torch.no_grad()
+    def forward_tokens(self, skeleton, kp_feat, feats_s, kp_mask, kp_mask_fixed, grid_pos):
+        """skeleton: list (batch) of edge lists; kp_feat [B,K,d]; feats_s: list (shots) of token-major
+        support ViT features [B,S,C] (views are fine); kp_mask / kp_mask_fixed uint8 [B,K];
+        grid_pos [S,d].  Returns (adj [B,2,K,K], attn_adj [max_hop+1,B,K,K] or None, unnormalized
+        adjacency [B,K,K], refined keypoint features or None)."""
+        B, K, d = kp_feat.shape
+        dev = kp_feat.device
+        edges, offsets = edges_to_csr(skeleton, dev)
+        gt_adj, binary = ops.adj_from_edges(edges, offsets, kp_mask, K)
+        if not self.learn_skeleton:
+            return gt_adj, None, binary, None
+        pk = self.packed()
+        # refine_features (:82-115): binary GT adjacency, keypoint positional embedding = 0
+        adj_b = ops.soft_normalize_adj(binary, kp_mask)
+        S = feats_s[0].shape[1]
+        acc = None
+        for si, feat in enumerate(feats_s):
+            img_cat = ops.empty(B, S, 2 * d, device=dev)
+            ops.linear(feat, self.image_project.weight, self.image_project.bias, out=img_cat[:, :, :d])
+            ops.copy_rows(grid_pos, img_cat.view(B * S, 2 * d)[:, d:], bcast_rows=S)
+            kp_cat = torch.zeros(B, K, 2 * d, dtype=torch.float32, device=dev)
+            kp = kp_feat
+            for i in range(self.num_layers):
+                kp = decoder_layer_forward(getattr(self.skeleton_predictor, str(i)), pk["layers"][i],
+                                           self.num_heads, kp, img_cat, kp_cat, kp_mask_fixed, adj_b, None,
+                                           two_way=self.two_way_attn)
+            acc = kp if acc is None else ops.axpby(acc, kp)
+        if len(feats_s) > 1:
+            acc = ops.axpby(acc, acc, 1.0, 0.0, float(len(feats_s)))         # torch.mean = sum / shots
+        # predict_skeleton (:134-150) + markov_transition_matrix (:152-161)
+        fn = ops.l2_normalize(acc, 1e-8)
+        gram = ops.gemm(fn, fn, b_kmajor=True)                                   # [B,K,K]
+        hops = ops.empty(self.max_hop + 1, B, K, K, device=dev)
+        adj, unnorm = ops.edge_weights(gram, binary, kp_mask, pk["zc"][0], pk["zc"][1], self.use_zero_conv, hops)
+        for hpow in range(2, self.max_hop + 1):
+            # P^h: torch.matrix_power association is irrelevant at fp32 round-off
+            left = hops[hpow // 2]
+            right = hops[hpow - hpow // 2]
+            ops.gemm(left, right, out=hops[hpow], b_kmajor=False)
+        return adj, hops, unnorm, acc
+
+    def forward(self, skeleton, kp_features, image_features, kp_mask, query_image_pos_embed):
+        """Reference signature (:58-64): image_features list of NCHW maps, kp_mask bool [B,K],
+        query_image_pos_embed [bs, d, h, w].  Layout adapter around forward_tokens."""
+        B, K, _ = kp_features.shape
+        feats = [f.flatten(2).transpose(1, 2).contiguous() for f in image_features]
+        grid_pos = query_image_pos_embed[0].flatten(1).transpose(0, 1).contiguous()
+        m = kp_mask.to(torch.uint8).contiguous()
+        mf = m.clone()
+        mf[(m == 0).sum(dim=-1) == 0, 0] = 0
+        adj, hops, unnorm, _ = self.forward_tokens(skeleton, kp_features.contiguous(), feats, m, mf, grid_pos)
+        return adj, hops, unnorm

@@ -1,0 +1,115 @@
+"""DINOv2 ViT backbone on the edgecape_b200 kernels.
+
+The reference obtains its backbone from `torch.hub.load('facebookresearch/dinov2', name)`
+(/root/reference/EdgeCape/models/detectors/EdgeCape.py:35-36) and calls
+`get_intermediate_layers(img, n=1, reshape=True)[0]` (:188-189).  This module owns parameters
+under upstream's state-dict names (`cls_token`, `pos_embed`, `patch_embed.proj.*`,
+`blocks.N.{norm1,attn.qkv,attn.proj,ls1,norm2,mlp.fc1,mlp.fc2,ls2}.*`, `norm.*`) so hub /
+EdgeCape checkpoints load unchanged, and runs: im2col + GEMM patch embedding (fused bias +
+position add), then per block LayerNorm -> QKV GEMM -> fused attention -> proj GEMM with fused
+LayerScale + residual -> LayerNorm -> fc1 GEMM + exact GELU -> fc2 GEMM with fused LayerScale +
+residual, and the final LayerNorm.  Activations stay token-major [B, 1+S, C]; the NCHW reshape
+of the reference is never materialised on the product path.
+
+Inputs whose side is not a multiple of the patch size follow floor semantics (256 -> 18x18).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import vit_config, vit_shapes
+from .params import PackedMixin, ParamTree
+
+
+class DinoVisionTransformerB200(PackedMixin, ParamTree):
+    def __init__(self, pretrained="dinov2_vits14"):
+        cfg = vit_config(pretrained)
+        ParamTree.__init__(self, vit_shapes(cfg, ""))
+        self._init_packed()
+        self.cfg = cfg
+        self.embed_dim = cfg["embed_dim"]
+        self.patch_size = cfg["patch_size"]
+        self.num_heads = cfg["num_heads"]
+        self.depth = cfg["depth"]
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if name.endswith("gamma") or (name.endswith("weight") and p.dim() == 1):
+                    p.fill_(1.0)
+                elif p.dim() > 1:
+                    p.normal_(0.0, 0.02)
+
+    # ------------------------------------------------------------------ packed weights
+    def _pack(self):
+        pk = {"pos": {}}
+        w = self["patch_embed.proj.weight"]
+        pk["pe_w"] = w.reshape(w.shape[0], -1).contiguous()
+        return pk
+
+    def _pos(self, h0, w0):
+        pk = self.packed()
+        key = (h0, w0)
+        if key not in pk["pos"]:
+            pk["pos"][key] = ops.interp_pos_embed(self["pos_embed"], h0, w0, self.cfg.get("interpolate_offset", 0.1))
+        return pk["pos"][key]
+
+    # -------------------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward_tokens(self, images):
+        """images: tensor [B,3,H,W] or list of such tensors (concatenated along the batch without a
+        copy of the pixels).  Returns final-LayerNorm'ed tokens [Btot, 1+S, C] and (h0, w0)."""
+        if torch.is_tensor(images):
+            images = [images]
+        P, C, H = self.patch_size, self.embed_dim, self.num_heads
+        Hh, Ww = images[0].shape[-2:]
+        h0, w0 = Hh // P, Ww // P
+        S = h0 * w0
+        N = S + 1
+        Btot = sum(int(im.shape[0]) for im in images)
+        dev = images[0].device
+        pk = self.packed()
+        KP = 3 * P * P
+        cols = ops.empty(Btot * S, KP, device=dev)
+        r = 0
+        for im in images:
+            assert im.shape[-2:] == (Hh, Ww), "all images of one call must share a resolution"
+            b = int(im.shape[0])
+            ops._lib.call("ec_im2col_patches", im.contiguous().data_ptr(), cols[r * S:].data_ptr(), b, Hh, Ww, P, KP,
+                          ops._stream())
+            r += b
+        pos = self._pos(h0, w0)                                           # [1+S, C]
+        t = ops.empty(Btot, N, C, device=dev)
+        ops.gemm(cols.view(Btot, S, KP), pk["pe_w"], out=t[:, 1:, :], bias=self["patch_embed.proj.bias"],
+                 residual=pos[1:], res_mode=ops.RES_ADD)
+        ops.write_cls_(t, self["cls_token"].reshape(-1), pos[0])
+        t2 = t.view(Btot * N, C)
+        y = ops.empty(Btot * N, C, device=dev)
+        qkv = ops.empty(Btot, N, 3 * C, device=dev)
+        att = ops.empty(Btot, N, C, device=dev)
+        hid = ops.empty(Btot * N, int(C * self.cfg["mlp_ratio"]), device=dev)
+        for i in range(self.depth):
+            blk = getattr(self.blocks, str(i))
+            ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, out=y)
+            ops.linear(y, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
+            ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, out=att)
+            ops.linear(att.view(Btot * N, C), blk.attn.proj.weight, blk.attn.proj.bias, colscale=blk.ls1.gamma,
+                       residual=t2, out=t2)
+            ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, out=y)
+            ops.linear(y, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, out=hid)
+            ops.linear(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, colscale=blk.ls2.gamma, residual=t2, out=t2)
+        out = ops.empty(Btot, N, C, device=dev)
+        ops.layernorm(t2, self["norm.weight"], self["norm.bias"], 1e-6, out=out.view(Btot * N, C))
+        return out, (h0, w0)
+
+    def get_intermediate_layers(self, x, n=1, reshape=False, return_class_token=False, norm=True):
+        """Upstream-compatible entry (only the form the reference calls: n=1, norm=True)."""
+        if n != 1 or not norm or return_class_token:
+            raise NotImplementedError("only get_intermediate_layers(x, n=1, norm=True) is on the EdgeCape path")
+        tok, (h0, w0) = self.forward_tokens(x)
+        feat = tok[:, 1:, :]
+        if reshape:
+            # layout adapter for callers that want upstream's NCHW view (pure data movement)
+            feat = feat.reshape(x.shape[0], h0, w0, -1).permute(0, 3, 1, 2).contiguous()
+        return (feat,)
+
+    def forward(self, x):
+        return self.forward_tokens(x)[0]

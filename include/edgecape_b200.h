@@ -1,0 +1,196 @@
+/*
+ * edgecape_b200 -- C ABI of the B200-native EdgeCape inference hot path.
+ *
+ * This header is the drop-in boundary below the reference's Python operator layer
+ * (mmpose registry classes EdgeCape / TwoStageHead / SkeletonPredictor /
+ * TwoStageSupportRefineTransformer).  The reference has no native code, so every entry
+ * point replaces a block of PyTorch-eager calls; the replaced reference lines are cited
+ * per function (paths relative to /root/reference/EdgeCape/models/).  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions:
+ *   - every function returns 0 on success or a negative EC_ERR_* code; ec_last_error_string()
+ *     describes the last failure on the calling thread.  Nothing throws.
+ *   - nothing allocates and nothing synchronises: all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*); the caller owns buffers and synchronisation.
+ *   - all tensors are device pointers to dense row-major fp32 unless stated; `ld*` are row
+ *     strides in elements.  Masks are uint8 (1 = masked / padded), indices int32/int64.
+ *   - the device is the caller's current CUDA device.
+ */
+#ifndef EDGECAPE_B200_H
+#define EDGECAPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EC_OK 0
+#define EC_ERR_INVALID -1      /* bad argument (shape, alignment, null pointer) */
+#define EC_ERR_CUDA -2         /* a CUDA runtime/driver call failed */
+#define EC_ERR_UNSUPPORTED -3  /* shape outside what the kernels are instantiated for */
+
+/* activation codes for ec_gemm / ec_gemm_f16x3 epilogues */
+#define EC_ACT_NONE 0
+#define EC_ACT_RELU 1
+#define EC_ACT_GELU 2 /* exact erf GELU (torch.nn.GELU default) */
+#define EC_ACT_TANH 3
+
+/* residual modes */
+#define EC_RES_NONE 0
+#define EC_RES_ADD 1  /* y = R + colscale * act(acc + bias) */
+#define EC_RES_GATE 2 /* y = (act(acc + bias) + 1) * R   (ProposalGenerator gate) */
+
+int ec_version(void);
+const char* ec_last_error_string(void);
+/* number of kernel launches enqueued by this library in this process so far */
+long long ec_launch_count(void);
+
+/* ---------------------------------------------------------------- dense contractions
+ * C[b] = epilogue(A[b] (MxK, row stride lda) * op(B[b])) for b < batch.
+ * b_kmajor = 1: B is [N,K] row-major (an nn.Linear / 1x1-conv weight), C = A * B^T.
+ * b_kmajor = 0: B is [K,N] row-major, C = A * B.
+ * epilogue: y = act(acc + bias[n]); y *= colscale[n]; then the residual mode with R (row stride
+ * ldr, batch stride strideR; strideR = 0 broadcasts R over the batch).  C may alias R.
+ * Replaces every nn.Linear / Conv1d(k=1) / Conv2d(1x1) / torch.bmm on the path, e.g.
+ * keypoint_heads/head.py:169,188, encoder_decoder.py:56-63,471-482,508-524, skeleton.py:92.
+ * fp32 SIMT kernel (FFMA); exact fp32 arithmetic. */
+int ec_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+            int b_kmajor, int batch, long long strideA, long long strideB, long long strideC,
+            const float* bias, int act, const float* colscale, const float* R, int ldr,
+            long long strideR, int res_mode, void* stream);
+
+/* ------------------------------------------------------------------------- normalisation
+ * Y[m,:] = LayerNorm(X[m,:] (+ R[m,:])) * w + b  (biased variance, eps inside the sqrt).
+ * Row m of X lives at X + (m / seg) * seg_stride + (m % seg) * ldx  (seg = 0: plain m * ldx) so a
+ * ViT token matrix can be read with its cls row dropped.  If sum_out != NULL the pre-norm sum
+ * X+R is stored there (row stride ld_sum).  torch.nn.LayerNorm on the path:
+ * encoder_decoder.py:477-482,612-637, ViT norm1/norm2/norm (DINOv2, eps 1e-6). */
+int ec_layernorm(const float* X, int ldx, int seg, long long seg_stride, const float* R, int ldr,
+                 float* sum_out, int ld_sum, float* Y, int ldy, const float* w, const float* b,
+                 float eps, int M, int C, void* stream);
+
+/* X[b, t, :] += P[t, :] for t < S (rows S..T-1 untouched): the encoder adds the grid positional
+ * encoding to the residual stream every layer (encoder_decoder.py:467). */
+int ec_add_rows(float* X, const float* P, int batch, int T, int S, int C, void* stream);
+
+/* Y[row(m), 0:C] = X[row(m % bcast_rows if bcast_rows else m), 0:C] with independent strides:
+ * row(m) = (m / seg) * seg_stride + (m % seg) * ld  (seg = 0: m * ld).  Concatenation / slicing
+ * helper (torch.cat at encoder_decoder.py:198-203,620-622; the token split at :307-308). */
+int ec_copy_rows(const float* X, int ldx, int seg_x, long long seg_stride_x, float* Y, int ldy,
+                 int seg_y, long long seg_stride_y, int M, int C, int bcast_rows, void* stream);
+
+/* out = (a*x + b*y) / div elementwise: the mean over shots (head.py:186, skeleton.py:113). */
+int ec_axpby(const float* x, const float* y, float* out, float a, float b, float div, long long n,
+             void* stream);
+
+/* ----------------------------------------------------------------------------- attention
+ * O[b, i, h*DV:(h+1)*DV] = softmax_j( scale * <Q[b,i,h], K[b,j,h]> + bias[b,h,i,j] , masked ) V[b,j,h]
+ * Q/K/V are [B, L, H*D] views with row strides ldq/ldk/ldv and batch strides in elements
+ * (they may point into one packed QKV buffer).  key_mask: uint8 [B, Lk], 1 = ignore key
+ * (key_padding_mask), may be NULL.  bias: fp32 [B, H, Lq, Lk] or NULL.  D in {16, 32, 64}.
+ * Replaces F.multi_head_attention_forward / SDPA (encoder_decoder.py:471-477, 606-631,
+ * 638-649), BiasedMultiheadAttention's bmm/softmax/bmm (utils/bias_attn.py:176-222) and the
+ * DINOv2 block attention. */
+int ec_attention(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq,
+                 int Lk, int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk,
+                 long long sv, long long so, float scale, const uint8_t* key_mask,
+                 const float* bias, void* stream);
+
+/* bias[b,h,i,j] = W1 relu(W0 hops[:,b,i,j] + b0) + b1 with hops = attn_adj [n_hops, B, K, K]:
+ * the Graphormer-style structural bias MLP (utils/bias_attn.py:82-83,188-191). */
+int ec_hop_bias(const float* attn_adj, const float* w0, const float* b0, const float* w1,
+                const float* b1, float* bias, int B, int K, int n_hops, int hidden, int H,
+                void* stream);
+
+/* ------------------------------------------------------------------------------ skeleton
+ * mask bookkeeping (detectors/EdgeCape.py:175-177, head.py:189, encoder_decoder.py:359-360):
+ * mask_s[b,k] = (first ? tw*tw : mask_s*tw); ec_kp_masks derives kp_mask = (mask_s == 0) and
+ * kp_mask_fixed (column 0 un-masked for rows whose keypoints are all masked). */
+int ec_mask_accumulate(const float* tw, float* mask_s, int n, int first, void* stream);
+int ec_kp_masks(const float* mask_s, uint8_t* kp_mask, uint8_t* kp_mask_fixed, int B, int K,
+                void* stream);
+
+/* adjacency from edge lists (keypoint_heads/skeleton.py:171-194): edges int32 [E_total,2],
+ * offsets int32 [B+1] (CSR).  adj [B,2,K,K] = [diag(valid), nan_to_num(A / rowsum)],
+ * binary [B,K,K] = (masked symmetric 0/1 adjacency).  Edges with an index outside [0,K) are
+ * an error in the reference (IndexError); here they are ignored. */
+int ec_adj_from_edges(const int32_t* edges, const int32_t* offsets, const uint8_t* kp_mask,
+                      float* adj, float* binary, int B, int K, void* stream);
+
+/* soft_normalize_adj (skeleton.py:196-205): adj [B,2,K,K] = [diag(valid), (U*vv)/(rowsum+1e-8)]. */
+int ec_soft_normalize_adj(const float* U, const uint8_t* kp_mask, float* adj, int B, int K,
+                          void* stream);
+
+/* edge-weight prediction (skeleton.py:134-150) from the Gram matrix S = Fn Fn^T of the
+ * L2-normalised refined keypoint tokens (ec_l2_normalize + ec_gemm):
+ * U = relu(binary + w*(S+S^T)/2 + b); adj = soft_normalize(U); unnorm = U * valid x valid;
+ * hops[0..n_hops-1] (skeleton.py:152-161) get P^0 = I and P^1 = adj1/(rowsum+1e-8); higher
+ * powers are ec_gemm products. */
+int ec_l2_normalize(const float* X, float* Y, int M, int C, float eps, void* stream);
+int ec_edge_weights(const float* S, const float* binary, const uint8_t* kp_mask, float zc_w,
+                    float zc_b, int use_zero_conv, float* adj, float* unnorm, float* hop0,
+                    float* hop1, int B, int K, void* stream);
+
+/* GCN feed-forward (encoder_decoder.py:508-524), aggregate-first form:
+ * Y[b,w,:] = relu( a0[b,w] * (X[b,w,:] W0^T + b0) + sum_v A1[b,w,v] (X[b,v,:] W1^T + b1) )
+ *          = relu( Z[b,w,:] Wp^T ),  Z = [ a0*X | A1 X | a0 | rowsum(A1) | 0 0 ]  (K' = 2d+4)
+ * adj [B,2,K,K]; plane 0 must be diagonal (it always is: skeleton.py:193,204 build it with
+ * diag_embed), a0 is its diagonal.  W [2*dff, d] is the Conv1d(k=1) weight, bias [2*dff];
+ * ec_gcn_pack_weights builds Wp [dff, 2d+4] = [W0 | W1 | b0 | b1 | 0 0] once per checkpoint.
+ * X [B,K,d] -> Y [B,K,dff].  workspace holds Z (ec_workspace_bytes_gcn). */
+int ec_gcn_pack_weights(const float* W, const float* bias, float* Wp, int d, int dff, void* stream);
+int ec_gcn(const float* X, const float* adj, const float* Wp, float* Y, int B, int K, int d, int dff,
+           float* workspace, size_t workspace_bytes, void* stream);
+size_t ec_workspace_bytes_gcn(int B, int K, int d, int dff);
+
+/* ----------------------------------------------------------------------------- head ops
+ * support-keypoint pooling weights (head.py:175-184, exact by linearity):
+ * Tw[b,k,s] = scale[b,k] / (sum(t[b,k]) + 1e-8) * sum_p t[b,k,p] U[p,s], U = bilinear
+ * (align_corners=False) interpolation matrix from the h x w feature grid to the hm x hm map.
+ * pooled = Tw @ feat is then one batched ec_gemm.  rowscale [B,K] (mask / shots) may be NULL. */
+int ec_support_weights(const float* target, const float* rowscale, float* Tw, int ldtw, int BK,
+                       int hm_h, int hm_w, int h, int w, void* stream);
+
+/* DETR sine positional encoding of continuous coordinates (utils/positional_encoding.py:96-122):
+ * coord [M,2] (x,y) in [0,1] -> out[m, :] = [PE(y) | PE(x)], 2*num_feats channels. */
+int ec_sine_pe_coords(const float* coord, float* out, int ldo, int M, int num_feats,
+                      float temperature, float scale, void* stream);
+
+/* ProposalGenerator tail (encoder_decoder.py:66-112) on sim [BK, S] (S = h*w):
+ * proposal_for_loss (global soft-argmax), argmax (first max), proposals (3x3 local soft-argmax
+ * with the reference's (w,h) reshape). */
+int ec_proposal(const float* sim, float* prop_loss, float* prop, int64_t* argmax, int BK, int h,
+                int w, void* stream);
+
+/* bi' = sigmoid(inverse_sigmoid(bi) + delta), eps = 1e-3 (encoder_decoder.py:395-403,427-431,
+ * head.py:27-31,216-220).  Also used for the final per-layer decode. */
+int ec_point_update(const float* bi, const float* delta, int ldd, float* out, int M, void* stream);
+
+/* ------------------------------------------------------------------------------ ViT ops
+ * im2col for the stride-P patch embedding (floor semantics): img [B,3,H,W] ->
+ * cols [B*h0*w0, ldc] with (c,py,px) ordering = Conv2d weight flattening; columns 3*P*P..ldc-1
+ * are zero-filled. */
+int ec_im2col_patches(const float* img, float* cols, int B, int H, int W, int P, int ldc,
+                      void* stream);
+/* bicubic (A=-0.75, align_corners=False, scale_factor=(n+offset)/M) resampling of the M x M
+ * patch position table to h0 x w0 (DINOv2 interpolate_pos_encoding); pos_out [1+h0*w0, C]. */
+int ec_interp_pos_embed(const float* pos_embed, float* pos_out, int Mgrid, int h0, int w0, int C,
+                        double offset, void* stream);
+/* tokens[b, 0, :] = cls + pos[0]  (cls row of every image) */
+int ec_write_cls(const float* cls, const float* pos0, float* tokens, int B, long long stride, int C,
+                 void* stream);
+
+/* -------------------------------------------------------------------------- evaluation
+ * per-sample PCK (mmpose keypoint_pck_accuracy semantics, datasets/.../test_base_dataset.py:
+ * 104-133): pred/gt [B,K,2], valid uint8 [B,K], norm [B,2]; counters[0..T-1] += per-sample
+ * PCK@thr[t]; counters[T] += number of samples.  Accumulated in fp64 for one ncclAllReduce. */
+int ec_pck_accumulate(const float* pred, const float* gt, const uint8_t* valid, const float* norm,
+                      const float* thr, int T, double* counters, int B, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

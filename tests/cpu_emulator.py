@@ -1,0 +1,337 @@
+"""TEST INFRASTRUCTURE ONLY -- a numpy/torch emulation of the C ABI (include/edgecape_b200.h)
+working on raw host pointers, so the *host-side orchestration* of the product (views, strides,
+argument order, buffer reuse, control flow) can be exercised against the golden vectors on a box
+without a GPU.  It is installed by monkeypatching from tests (`install(monkeypatch)`); the product
+has no hook for it and never runs without its CUDA library.  Each function restates the header's
+contract independently of the CUDA sources.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_ITEM = {np.float32: 4, np.uint8: 1, np.int32: 4, np.int64: 8, np.float64: 8}
+_CT = {np.float32: ctypes.c_float, np.uint8: ctypes.c_uint8, np.int32: ctypes.c_int32, np.int64: ctypes.c_int64,
+       np.float64: ctypes.c_double}
+
+
+def arr(ptr, shape, strides=None, dtype=np.float32):
+    """numpy view of host memory at `ptr` with element strides."""
+    shape = tuple(int(s) for s in shape)
+    if strides is None:
+        strides, acc = [], 1
+        for s in reversed(shape):
+            strides.append(acc)
+            acc *= s
+        strides = tuple(reversed(strides))
+    strides = tuple(int(s) for s in strides)
+    if 0 in shape:
+        return np.zeros(shape, dtype=dtype)
+    span = 1 + sum((n - 1) * st for n, st in zip(shape, strides))
+    buf = (_CT[dtype] * span).from_address(ptr)
+    base = np.ctypeslib.as_array(buf)
+    return np.lib.stride_tricks.as_strided(base, shape=shape, strides=tuple(st * _ITEM[dtype] for st in strides))
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def rows(ptr, M, C, ld, seg=0, seg_stride=0):
+    if seg and seg > 0:
+        return _SegView(ptr, M, C, ld, seg, seg_stride)
+    return arr(ptr, (M, C), (ld, 1))
+
+
+class _SegView:
+    """[M,C] rows addressed as (m // seg) * seg_stride + (m % seg) * ld (read or write)."""
+
+    def __init__(self, ptr, M, C, ld, seg, seg_stride):
+        assert M % seg == 0
+        self.v = arr(ptr, (M // seg, seg, C), (seg_stride, ld, 1))
+        self.M, self.C = M, C
+
+    def get(self):
+        return np.ascontiguousarray(self.v).reshape(self.M, self.C)
+
+    def set(self, x):
+        self.v[...] = x.reshape(self.v.shape)
+
+
+def _get(v):
+    return v.get() if isinstance(v, _SegView) else v
+
+
+def _set(v, x):
+    if isinstance(v, _SegView):
+        v.set(x)
+    else:
+        v[...] = x
+
+
+def _act(y, act):
+    if act == 1:
+        return F.relu(y)
+    if act == 2:
+        return F.gelu(y)
+    if act == 3:
+        return torch.tanh(y)
+    return y
+
+
+def ec_gemm(A, B, C, M, N, K, lda, ldb, ldc, b_kmajor, batch, sA, sB, sC, bias, act, colscale, R, ldr, sR,
+            res_mode, stream):
+    a = T(arr(A, (batch, M, K), (sA, lda, 1)))
+    b = T(arr(B, (batch, N, K), (sB, ldb, 1))) if b_kmajor else T(arr(B, (batch, K, N), (sB, ldb, 1)))
+    y = a @ (b.transpose(1, 2) if b_kmajor else b)
+    if bias:
+        y = y + T(arr(bias, (N,)))
+    y = _act(y, act)
+    if colscale:
+        y = y * T(arr(colscale, (N,)))
+    if R:
+        r = T(arr(R, (batch, M, N), (sR, ldr, 1)))
+        y = (y + 1) * r if res_mode == 2 else r + y
+    arr(C, (batch, M, N), (sC, ldc, 1))[...] = y.numpy()
+
+
+def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, stream):
+    x = T(_get(rows(X, M, C, ldx, seg, seg_stride)))
+    if R:
+        x = x + T(arr(R, (M, C), (ldr, 1)))
+    if sum_out:
+        arr(sum_out, (M, C), (ld_sum, 1))[...] = x.numpy()
+    y = F.layer_norm(x, (C,), T(arr(w, (C,))), T(arr(b, (C,))), eps)
+    arr(Y, (M, C), (ldy, 1))[...] = y.numpy()
+
+
+def ec_add_rows(X, P, batch, Tt, S, C, stream):
+    arr(X, (batch, Tt, C))[:, :S, :] += arr(P, (S, C))[None]
+
+
+def ec_copy_rows(X, ldx, segx, ssx, Y, ldy, segy, ssy, M, C, bcast, stream):
+    Mx = bcast if bcast > 0 else M
+    x = _get(rows(X, Mx, C, ldx, segx, ssx))
+    if bcast > 0:
+        x = x[np.arange(M) % bcast]
+    _set(rows(Y, M, C, ldy, segy, ssy), np.ascontiguousarray(x))
+
+
+def ec_axpby(x, y, out, a, b, div, n, stream):
+    v = np.float32(a) * arr(x, (n,))
+    if b != 0:
+        v = v + np.float32(b) * arr(y, (n,))
+    arr(out, (n,))[...] = v / np.float32(div) if div != 1.0 else v
+
+
+def ec_attention(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, key_mask, bias, stream):
+    q = T(arr(Q, (B, Lq, H, D), (sq, ldq, D, 1))).transpose(1, 2) * np.float32(scale)
+    k = T(arr(K, (B, Lk, H, D), (sk, ldk, D, 1))).transpose(1, 2)
+    v = T(arr(V, (B, Lk, H, D), (sv, ldv, D, 1))).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if bias:
+        s = s + T(arr(bias, (B, H, Lq, Lk)))
+    if key_mask:
+        m = T(arr(key_mask, (B, Lk), dtype=np.uint8)).bool()
+        s = s.masked_fill(m[:, None, None, :], float("-inf"))
+    o = (s.softmax(-1) @ v).transpose(1, 2)
+    arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o.numpy()
+
+
+def ec_hop_bias(attn_adj, w0, b0, w1, b1, bias, B, K, n_hops, hidden, H, stream):
+    hops = T(arr(attn_adj, (n_hops, B, K, K))).permute(1, 2, 3, 0)
+    y = F.linear(F.relu(F.linear(hops, T(arr(w0, (hidden, n_hops))), T(arr(b0, (hidden,))))),
+                 T(arr(w1, (H, hidden))), T(arr(b1, (H,))))
+    arr(bias, (B, H, K, K))[...] = y.permute(0, 3, 1, 2).numpy()
+
+
+def ec_mask_accumulate(tw, mask_s, n, first, stream):
+    t, m = arr(tw, (n,)), arr(mask_s, (n,))
+    m[...] = t * t if first else m * t
+
+
+def ec_kp_masks(mask_s, kp_mask, kp_fixed, B, K, stream):
+    m = (arr(mask_s, (B, K)) == 0).astype(np.uint8)
+    arr(kp_mask, (B, K), dtype=np.uint8)[...] = m
+    f = m.copy()
+    f[m.sum(1) == K, 0] = 0
+    arr(kp_fixed, (B, K), dtype=np.uint8)[...] = f
+
+
+def _soft_norm(U, mk):
+    valid = (1 - mk).astype(np.float32)
+    A = U * valid[:, :, None] * valid[:, None, :]
+    A = A / (A.sum(-1, keepdims=True) + np.float32(1e-8))
+    diag = np.zeros_like(A)
+    idx = np.arange(A.shape[1])
+    diag[:, idx, idx] = valid
+    return np.stack((diag, A), axis=1)
+
+
+def ec_adj_from_edges(edges, offsets, kp_mask, adj, binary, B, K, stream):
+    offs = arr(offsets, (B + 1,), dtype=np.int32)
+    mk = arr(kp_mask, (B, K), dtype=np.uint8)
+    e = arr(edges, (max(int(offs[-1]), 1), 2), dtype=np.int32)
+    A = np.zeros((B, K, K), dtype=np.float32)
+    for b in range(B):
+        for i, j in e[offs[b]:offs[b + 1]]:
+            A[b, i, j] = 1
+            A[b, j, i] = 1
+    valid = (1 - mk).astype(np.float32)
+    A = A * valid[:, :, None] * valid[:, None, :]
+    arr(binary, (B, K, K))[...] = A
+    with np.errstate(invalid="ignore", divide="ignore"):
+        An = np.nan_to_num(A / A.sum(-1, keepdims=True))
+    diag = np.zeros_like(A)
+    idx = np.arange(K)
+    diag[:, idx, idx] = valid
+    arr(adj, (B, 2, K, K))[...] = np.stack((diag, An), axis=1)
+
+
+def ec_soft_normalize_adj(U, kp_mask, adj, B, K, stream):
+    arr(adj, (B, 2, K, K))[...] = _soft_norm(arr(U, (B, K, K)), arr(kp_mask, (B, K), dtype=np.uint8))
+
+
+def ec_l2_normalize(X, Y, M, C, eps, stream):
+    x = arr(X, (M, C))
+    arr(Y, (M, C))[...] = x / (np.sqrt((x * x).sum(-1, keepdims=True)) + np.float32(eps))
+
+
+def ec_edge_weights(S, binary, kp_mask, zw, zb, use_zc, adj, unnorm, hop0, hop1, B, K, stream):
+    s = arr(S, (B, K, K))
+    mk = arr(kp_mask, (B, K), dtype=np.uint8)
+    s = (s + s.transpose(0, 2, 1)) / np.float32(2)
+    if use_zc:
+        s = s * np.float32(zw) + np.float32(zb)
+    U = np.maximum(arr(binary, (B, K, K)) + s, 0)
+    a = _soft_norm(U, mk)
+    arr(adj, (B, 2, K, K))[...] = a
+    valid = (1 - mk).astype(np.float32)
+    if unnorm:
+        arr(unnorm, (B, K, K))[...] = U * valid[:, :, None] * valid[:, None, :]
+    if hop0:
+        arr(hop0, (B, K, K))[...] = np.eye(K, dtype=np.float32)[None]
+    if hop1:
+        arr(hop1, (B, K, K))[...] = a[:, 1] / (a[:, 1].sum(-1, keepdims=True) + np.float32(1e-8))
+
+
+def ec_gcn_pack_weights(W, bias, Wp, d, dff, stream):
+    w, b = arr(W, (2 * dff, d)), arr(bias, (2 * dff,))
+    out = arr(Wp, (dff, 2 * d + 4))
+    out[...] = 0
+    out[:, :d], out[:, d:2 * d] = w[:dff], w[dff:]
+    out[:, 2 * d], out[:, 2 * d + 1] = b[:dff], b[dff:]
+
+
+def ec_gcn(X, adj, Wp, Y, B, K, d, dff, ws, wsbytes, stream):
+    assert wsbytes >= B * K * (2 * d + 4) * 4
+    x, a, wp = T(arr(X, (B, K, d))), T(arr(adj, (B, 2, K, K))), T(arr(Wp, (dff, 2 * d + 4)))
+    w0, w1, b0, b1 = wp[:, :d], wp[:, d:2 * d], wp[:, 2 * d], wp[:, 2 * d + 1]
+    h0, h1 = F.linear(x, w0, b0), F.linear(x, w1, b1)
+    y = torch.diagonal(a[:, 0], dim1=1, dim2=2)[..., None] * h0 + a[:, 1] @ h1
+    arr(Y, (B, K, dff))[...] = F.relu(y).numpy()
+
+
+def ec_support_weights(target, rowscale, Tw, ldtw, BK, hm_h, hm_w, h, w, stream):
+    t = T(arr(target, (BK, hm_h * hm_w)))
+    # U[p, s]: bilinear interpolation matrix = upsampled one-hot basis images
+    basis = torch.eye(h * w).reshape(h * w, 1, h, w)
+    U = F.interpolate(basis, size=(hm_h, hm_w), mode="bilinear", align_corners=False).reshape(h * w, -1).T
+    scale = 1.0 / (t.sum(-1, keepdim=True) + 1e-8)
+    if rowscale:
+        scale = scale * T(arr(rowscale, (BK,)))[:, None]
+    arr(Tw, (BK, h * w), (ldtw, 1))[...] = ((t @ U) * scale).numpy()
+
+
+def ec_sine_pe_coords(coord, out, ldo, M, num_feats, temperature, scale, stream):
+    c = T(arr(coord, (M, 2)))
+    dt = torch.arange(num_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dt, 2, rounding_mode="floor") / num_feats)
+    px = (c[:, 0] * np.float32(scale))[:, None] / dim_t
+    py = (c[:, 1] * np.float32(scale))[:, None] / dim_t
+    px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)
+    py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)
+    arr(out, (M, 2 * num_feats), (ldo, 1))[...] = torch.cat((py, px), dim=1).numpy()
+
+
+def ec_proposal(sim, prop_loss, prop, argmax, BK, h, w, stream):
+    S = h * w
+    s = T(arr(sim, (BK, S)))
+    sm = s.softmax(-1)
+    gy, gx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h), torch.linspace(0.5, w - 0.5, w), indexing="ij")
+    grid = torch.stack((gx, gy), -1).reshape(S, 2)
+    nrm = torch.tensor([w, h], dtype=torch.float32)
+    arr(prop_loss, (BK, 2))[...] = ((sm[..., None] * grid).sum(1) / nrm).numpy()
+    am = s.argmax(-1)
+    local = F.max_pool2d(F.one_hot(am, S).reshape(BK, 1, w, h).float(), 3, 1, 1).reshape(BK, S)
+    l = sm * local
+    l = l / (l.sum(-1, keepdim=True) + 1e-10)
+    arr(prop, (BK, 2))[...] = ((l[..., None] * grid).sum(1) / nrm).numpy()
+    arr(argmax, (BK,), dtype=np.int64)[...] = am.numpy()
+
+
+def ec_point_update(bi, delta, ldd, out, M, stream):
+    b = T(arr(bi, (M, 2))).clamp(0, 1)
+    z = torch.log(b.clamp(min=1e-3) / (1 - b).clamp(min=1e-3)) + T(arr(delta, (M, 2), (ldd, 1)))
+    arr(out, (M, 2))[...] = z.sigmoid().numpy()
+
+
+def ec_im2col_patches(img, cols, B, H, W, P, ldc, stream):
+    x = T(arr(img, (B, 3, H, W)))
+    h0, w0 = H // P, W // P
+    x = x[:, :, :h0 * P, :w0 * P].reshape(B, 3, h0, P, w0, P).permute(0, 2, 4, 1, 3, 5).reshape(B * h0 * w0, 3 * P * P)
+    out = arr(cols, (B * h0 * w0, ldc))
+    out[...] = 0
+    out[:, :3 * P * P] = x.numpy()
+
+
+def ec_interp_pos_embed(pos, out, Mg, h0, w0, C, offset, stream):
+    pe = T(arr(pos, (1 + Mg * Mg, C)))
+    if h0 == Mg and w0 == Mg:
+        arr(out, (1 + h0 * w0, C))[...] = pe.numpy()
+        return
+    patch = pe[1:].reshape(1, Mg, Mg, C).permute(0, 3, 1, 2)
+    kw = dict(scale_factor=((h0 + offset) / Mg, (w0 + offset) / Mg)) if offset else dict(size=(h0, w0))
+    y = F.interpolate(patch, mode="bicubic", antialias=False, **kw)
+    assert y.shape[-2:] == (h0, w0)
+    o = arr(out, (1 + h0 * w0, C))
+    o[0] = pe[0].numpy()
+    o[1:] = y.permute(0, 2, 3, 1).reshape(h0 * w0, C).numpy()
+
+
+def ec_write_cls(cls, pos0, tokens, B, stride, C, stream):
+    arr(tokens, (B, C), (stride, 1))[...] = (arr(cls, (C,)) + arr(pos0, (C,)))[None]
+
+
+def ec_pck_accumulate(pred, gt, valid, norm, thr, Tn, counters, B, K, stream):
+    p, g = arr(pred, (B, K, 2)), arr(gt, (B, K, 2))
+    v, n, th = arr(valid, (B, K), dtype=np.uint8).astype(bool), arr(norm, (B, 2)), arr(thr, (Tn,))
+    c = arr(counters, (Tn + 1,), dtype=np.float64)
+    for b in range(B):
+        d = np.sqrt((((p[b] - g[b]) / n[b]) ** 2).sum(-1))
+        for t in range(Tn):
+            if v[b].any():
+                c[t] += float((d[v[b]] < th[t]).mean())
+        c[Tn] += 1
+
+
+FUNCS = {k: v for k, v in list(globals().items()) if k.startswith("ec_")}
+
+
+def install(monkeypatch):
+    """Route edgecape_b200's C-ABI calls to the emulation above and lift the CUDA-only guards."""
+    from edgecape_b200 import _lib, ops, detector
+
+    def call(name, *args):
+        FUNCS[name](*[0 if a is None else a for a in args])
+
+    def chk(t, name, dtype=torch.float32):
+        if t is not None and t.dtype != dtype:
+            raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+    monkeypatch.setattr(_lib, "call", call)
+    monkeypatch.setattr(ops, "_chk", chk)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(detector, "_require_cuda", lambda dev: None)

@@ -1,0 +1,98 @@
+"""GPU: the drop-in detector, called through the reference's own API
+(`model(return_loss=False, **data)`), against the golden vectors frozen from the UNMODIFIED
+reference (tests/golden/*.npz, made by oracle/gen_golden.py) and against the CPU oracle.
+
+Bar (BASELINE.json north_star): heat-maps / coordinates within 1e-3 relative (to the tensor's
+max magnitude) of the fp32 reference, arg-max keypoint indices bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import edgecape_b200 as E  # noqa: E402
+from edgecape_b200.config import state_dict_shapes  # noqa: E402
+from edgecape_b200.synthetic import make_episode, make_state_dict  # noqa: E402
+from oracle.gen_golden import CASES, build_case  # noqa: E402
+
+TOL = 1e-3
+REPORT = {}
+
+
+def _build(cfg, wseed):
+    model = E.build_model(dict(model=cfg))
+    model.load_state_dict(make_state_dict(state_dict_shapes(cfg), wseed), strict=True)
+    return model.cuda().eval()
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def _compare(name, got, want, report):
+    worst = 0.0
+    for k, w in want.items():
+        if k not in got or got[k] is None:
+            continue
+        a = _np(got[k])
+        if k in ("feature_q", "encoder_image"):
+            a = a[:1]
+        if k == "argmax":
+            assert np.array_equal(a.astype(np.int64), w.astype(np.int64)), f"{name}: argmax differs from the reference"
+            report[k] = 0.0
+            continue
+        assert a.shape == w.shape, (name, k, a.shape, w.shape)
+        err = float(np.abs(a.astype(np.float64) - w).max() / (np.abs(w).max() + 1e-12))
+        report[k] = err
+        worst = max(worst, err)
+    bad = {k: v for k, v in report.items() if v >= TOL}
+    assert not bad, f"{name}: beyond {TOL}: {bad}"
+    return worst
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_detector_matches_reference_golden(name, golden_dir):
+    golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    cfg, data, wseed = build_case(name)
+    model = _build(cfg, wseed)
+    # (1) the reference-facing call: result dict of numpy arrays
+    res = model(return_loss=False, **data)
+    assert set(res) >= {"preds", "boxes", "image_paths", "bbox_ids", "points", "sample_image_file", "skeleton"}
+    # (2) the same forward with intermediates exposed
+    out5, inter = model.predict(data["img_s"], data["target_s"], data["target_weight_s"], data["img_q"],
+                                data["img_metas"], return_intermediates=True)
+    feat_q, _ = model.extract_features([t.cuda() for t in data["img_s"]], data["img_q"].cuda())
+    got = dict(inter)
+    got.update(feature_q=feat_q, preds=res["preds"], boxes=res["boxes"], points=res["points"],
+               skeleton=res["skeleton"])
+    rep = {}
+    worst = _compare(name, got, golden, rep)
+    REPORT[name] = rep
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/e2e_parity.json", "w") as fh:
+        json.dump(REPORT, fh, indent=1, sort_keys=True)
+    print(f"{name}: worst rel err {worst:.2e}")
+
+
+def test_detector_matches_oracle_on_fresh_episode():
+    """Seeded episode that has no golden file: compare against the CPU oracle run here."""
+    from oracle import edgecape_oracle
+    from oracle.gen_golden import TINY_VIT, model_cfg_for
+    cfg = model_cfg_for(TINY_VIT)
+    data = make_episode(batch=4, image_size=112, num_kpts=33, shots=3, seed=99, masked_tail=0.2)
+    sd = make_state_dict(state_dict_shapes(cfg), 7)
+    with torch.no_grad():
+        want = edgecape_oracle.detector_forward_test(sd, cfg, data, torch.float32)
+    model = _build(cfg, 7)
+    res = model(return_loss=False, **data)
+    _, inter = model.predict(data["img_s"], data["target_s"], data["target_weight_s"], data["img_q"],
+                             data["img_metas"], return_intermediates=True)
+    got = dict(inter)
+    got.update(preds=res["preds"], points=res["points"], skeleton=res["skeleton"])
+    keys = ["support_keypoints", "skeleton_kp_features", "adj", "attn_adj", "encoder_kp", "similarity_map",
+            "argmax", "initial_proposals", "decoder_hs", "output", "preds", "points", "skeleton"]
+    wantd = {k: _np(want[k]) for k in keys}
+    _compare("fresh_tiny_3shot", got, wantd, {})

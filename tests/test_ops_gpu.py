@@ -1,0 +1,345 @@
+"""GPU: every C-ABI kernel against the CPU oracle (oracle/edgecape_oracle.py) or the plain torch
+fp32 statement of the same op, on seeded inputs including ragged / unaligned / masked cases.
+Tolerances are relative to the tensor's max magnitude; indices must be bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from edgecape_b200 import ops  # noqa: E402
+from oracle import edgecape_oracle as O  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def close(got, want, tol=2e-5, what=""):
+    got = got.detach().float().cpu()
+    want = want.detach().float().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs().max().item() / (want.abs().max().item() + 1e-12)
+    assert err < tol, f"{what}: rel err {err:.3e} >= {tol}"
+    return err
+
+
+# ----------------------------------------------------------------------------------- gemm
+@pytest.mark.parametrize("M,N,K", [(1600, 256, 768), (100, 2, 256), (37, 53, 19), (324, 768, 588), (128, 128, 16),
+                                   (5, 7, 3), (1, 1, 1)])
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_RELU, ops.ACT_GELU, ops.ACT_TANH])
+def test_gemm_linear_epilogues(M, N, K, act):
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    g, r = rnd(N, seed=4), rnd(M, N, seed=5)
+    y = F.linear(x, w, b)
+    y = [y, F.relu(y), F.gelu(y), torch.tanh(y)][act]
+    want = r + g * y
+    got = ops.linear(x.to(dev()), w.to(dev()), b.to(dev()), act=act, colscale=g.to(dev()), residual=r.to(dev()))
+    close(got, want, what=f"linear {M}x{N}x{K} act{act}")
+    want = (y + 1) * r
+    got = ops.linear(x.to(dev()), w.to(dev()), b.to(dev()), act=act, residual=r.to(dev()), res_mode=ops.RES_GATE)
+    close(got, want, what="gate")
+
+
+def test_gemm_inplace_residual_and_strided_views():
+    B, S, C, N = 3, 36, 64, 48
+    t = rnd(B, S + 1, N, seed=1).to(dev())
+    t0 = t.clone()
+    a = rnd(B, S, C, seed=2).to(dev())
+    w = rnd(N, C, seed=3, scale=0.1).to(dev())
+    pos = rnd(S, N, seed=4).to(dev())
+    # out is a strided 3-D view (cls row skipped), residual broadcast over the batch
+    ops.gemm(a, w, out=t[:, 1:, :], residual=pos, res_mode=ops.RES_ADD)
+    want = torch.einsum("bsc,nc->bsn", a.cpu(), w.cpu()) + pos.cpu()
+    close(t[:, 1:, :], want, what="strided out")
+    assert torch.equal(t[:, 0, :], t0[:, 0, :])
+    # in-place residual (C aliases R)
+    x = rnd(50, 64, seed=5).to(dev())
+    acc = rnd(50, 48, seed=6).to(dev())
+    want = acc.cpu() + x.cpu() @ w.cpu().T
+    ops.linear(x, w, None, residual=acc, out=acc)
+    close(acc, want, what="in-place")
+
+
+@pytest.mark.parametrize("K", [100, 17, 200])
+def test_gemm_batched_nn_and_tn(K):
+    B, d = 3, 64
+    A = rnd(B, K, K, seed=1).to(dev())
+    X = rnd(B, K, d, seed=2).to(dev())
+    close(ops.gemm(A, X, b_kmajor=False), torch.bmm(A.cpu(), X.cpu()), what="bmm NN")
+    close(ops.gemm(X, X, b_kmajor=True), torch.bmm(X.cpu(), X.cpu().transpose(1, 2)), what="bmm TN")
+    # column-slice views of a wider buffer
+    buf = rnd(B * K, 2 * d, seed=3).to(dev())
+    w = rnd(24, d, seed=4).to(dev())
+    close(ops.linear(buf[:, d:], w), buf.cpu()[:, d:] @ w.cpu().T, what="ld view")
+
+
+# ------------------------------------------------------------------------------- rowwise
+@pytest.mark.parametrize("M,C", [(650, 768), (7, 64), (33, 1024), (5, 100)])
+def test_layernorm(M, C):
+    x, r = rnd(M, C, seed=1, scale=3.0), rnd(M, C, seed=2)
+    w, b = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
+    want = F.layer_norm(x + r, (C,), w, b, 1e-6)
+    s = ops.empty(M, C)
+    got = ops.layernorm(x.to(dev()), w.to(dev()), b.to(dev()), 1e-6, residual=r.to(dev()), sum_out=s)
+    close(got, want, what="ln")
+    close(s, x + r, tol=1e-7, what="sum_out")
+
+
+def test_layernorm_drops_cls_row_by_striding():
+    B, S, C = 3, 16, 64
+    t = rnd(B, S + 1, C, seed=1)
+    w, b = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
+    want = F.layer_norm(t[:, 1:], (C,), w, b, 1e-5)
+    got = ops.layernorm(t.to(dev())[:, 1:, :], w.to(dev()), b.to(dev()), 1e-5)
+    close(got, want, what="ln seg")
+
+
+def test_add_copy_axpby_l2():
+    B, T, S, C = 2, 12, 9, 32
+    x, p = rnd(B, T, C, seed=1), rnd(S, C, seed=2)
+    want = x.clone()
+    want[:, :S] += p
+    close(ops.add_rows_(x.to(dev()), p.to(dev()), S), want, tol=1e-7)
+    xd = x.to(dev())
+    out = torch.zeros(B, S, 2 * C, device=dev())
+    ops.copy_rows(xd[:, :S, :], out[:, :, :C])
+    ops.copy_rows(p.to(dev()), out.view(B * S, 2 * C)[:, C:], bcast_rows=S)
+    close(out, torch.cat((x[:, :S], p[None].expand(B, -1, -1)), dim=-1), tol=1e-7)
+    close(ops.axpby(xd, xd, 2.0, 1.0, 5.0), (2 * x + x) / 5.0, tol=1e-6)
+    close(ops.l2_normalize(xd), x / (x.norm(dim=-1, keepdim=True) + 1e-8), tol=1e-6)
+
+
+# ----------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(2, 12, 325, 325, 64), (3, 8, 100, 324, 64), (2, 8, 424, 424, 32),
+                                         (2, 4, 17, 17, 16), (1, 8, 324, 100, 64), (2, 8, 200, 200, 32)])
+def test_attention_plain_and_masked(B, H, Lq, Lk, D):
+    E = H * D
+    q, k, v = rnd(B, Lq, E, seed=1), rnd(B, Lk, E, seed=2), rnd(B, Lk, E, seed=3)
+    mask = torch.zeros(B, Lk, dtype=torch.bool)
+    mask[:, Lk - Lk // 3:] = True
+    mask[0, 0] = True
+    for m in (None, mask):
+        qh = q.view(B, Lq, H, D).transpose(1, 2) * D ** -0.5
+        kh = k.view(B, Lk, H, D).transpose(1, 2)
+        vh = v.view(B, Lk, H, D).transpose(1, 2)
+        s = qh @ kh.transpose(-1, -2)
+        if m is not None:
+            s = s.masked_fill(m[:, None, None, :], float("-inf"))
+        want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E)
+        got = ops.attention(q.to(dev()), k.to(dev()), v.to(dev()), H,
+                            key_mask=None if m is None else m.to(torch.uint8).to(dev()))
+        close(got, want, what=f"attn {B},{H},{Lq},{Lk},{D} mask={m is not None}")
+
+
+def test_attention_packed_qkv_views_and_bias_matches_oracle_mha():
+    """BiasedMultiheadAttention (utils/bias_attn.py:106-231) via oracle.mha with attn_bias."""
+    B, K, d, H = 2, 100, 256, 8
+    x = rnd(B, K, d, seed=1)
+    wq, wk, wv, wo = (rnd(d, d, seed=s, scale=d ** -0.5) for s in (2, 3, 4, 5))
+    bq, bk, bv, bo = (0.1 * rnd(d, seed=s) for s in (6, 7, 8, 9))
+    hops = torch.rand(5, B, K, K, generator=torch.Generator().manual_seed(10))
+    w0, b0, w1, b1 = rnd(12, 5, seed=11), rnd(12, seed=12), rnd(8, 12, seed=13), rnd(8, seed=14)
+    mask = torch.zeros(B, K, dtype=torch.bool)
+    mask[1, 70:] = True
+    bias = F.linear(F.relu(F.linear(hops.permute(1, 2, 3, 0), w0, b0)), w1, b1).permute(0, 3, 1, 2)
+    want = O.mha(x, x, x, wq, wk, wv, bq, bk, bv, wo, bo, H, mask, attn_bias=bias)
+    D = dev()
+    qkv = ops.linear(x.to(D).view(B * K, d), torch.cat((wq, wk, wv)).to(D), torch.cat((bq, bk, bv)).to(D)).view(B, K, 3 * d)
+    gb = ops.hop_bias(hops.to(D), w0.to(D), b0.to(D), w1.to(D), b1.to(D))
+    close(gb, bias, what="hop bias")
+    a = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, key_mask=mask.to(torch.uint8).to(D), bias=gb)
+    got = ops.linear(a.view(B * K, d), wo.to(D), bo.to(D)).view(B, K, d)
+    close(got, want, what="biased mha")
+
+
+# -------------------------------------------------------------------------------- graph
+def _edges(skeleton, D):
+    from edgecape_b200.skeleton import edges_to_csr
+    return edges_to_csr(skeleton, D)
+
+
+@pytest.mark.parametrize("K", [100, 17, 5])
+def test_adjacency_from_edges_and_soft_normalize(K):
+    rng = np.random.default_rng(K)
+    B = 4
+    from edgecape_b200.synthetic import random_skeleton
+    skel = [random_skeleton(rng, K, K - K // 4), [], random_skeleton(rng, K, K, "chain"), [[0, 1], [1, 0], [0, 1]]]
+    mask = torch.zeros(B, K, dtype=torch.bool)
+    mask[0, K - K // 4:] = True
+    mask[1, :] = True
+    mask[3, 1] = True
+    want = O.adj_from_edges(skel, K, mask, torch.float32)
+    D = dev()
+    e, o = _edges(skel, D)
+    adj, binary = ops.adj_from_edges(e, o, mask.to(torch.uint8).to(D), K)
+    close(adj, want, tol=1e-6, what="adj")
+    assert torch.equal(binary.cpu() > 0, want[:, 1] > 0)
+    U = torch.rand(B, K, K, generator=torch.Generator().manual_seed(1))
+    close(ops.soft_normalize_adj(U.to(D), mask.to(torch.uint8).to(D)), O.soft_normalize_adj(U, mask), tol=1e-6)
+
+
+@pytest.mark.parametrize("B,K,d,dff", [(4, 100, 256, 384), (2, 17, 256, 64), (2, 200, 256, 384), (3, 100, 256, 768)])
+def test_gcn_matches_oracle(B, K, d, dff):
+    x = rnd(B, K, d, seed=1)
+    W, b = rnd(2 * dff, d, 1, seed=2, scale=d ** -0.5), 0.1 * rnd(2 * dff, seed=3)
+    mask = torch.zeros(B, K, dtype=torch.bool)
+    mask[0, K - K // 5:] = True
+    U = torch.rand(B, K, K, generator=torch.Generator().manual_seed(4))
+    adj = O.soft_normalize_adj(U, mask)
+    want = O.gcn(x, adj, W, b)
+    D = dev()
+    Wp = ops.gcn_pack_weights(W.to(D), b.to(D))
+    got = ops.gcn(x.to(D), adj.to(D).contiguous(), Wp)
+    close(got, want, what="gcn")
+
+
+def test_edge_weights_and_markov_match_oracle():
+    B, K, d = 3, 100, 256
+    f = rnd(B, K, d, seed=1)
+    mask = torch.zeros(B, K, dtype=torch.bool)
+    mask[0, 80:] = True
+    mask[2, :] = True
+    binary = (torch.rand(B, K, K, generator=torch.Generator().manual_seed(2)) > 0.9)
+    binary = (binary | binary.transpose(1, 2)) & ~mask[:, :, None] & ~mask[:, None, :]
+    zw, zb = 0.6, 0.05
+    fn = f / (f.norm(dim=-1, keepdim=True) + 1e-8)
+    S = fn @ fn.transpose(1, 2)
+    S = (S + S.transpose(1, 2)) / 2 * zw + zb
+    U = F.relu(binary.float() + S)
+    want_adj = O.soft_normalize_adj(U, mask)
+    P = want_adj[:, 1] / (want_adj[:, 1].sum(-1, keepdim=True) + 1e-8)
+    want_h = torch.stack([torch.matrix_power(P, h) for h in range(5)])
+    D = dev()
+    g = ops.gemm(ops.l2_normalize(f.to(D)), ops.l2_normalize(f.to(D)), b_kmajor=True)
+    hops = ops.empty(5, B, K, K)
+    adj, un = ops.edge_weights(g, binary.float().to(D), mask.to(torch.uint8).to(D), zw, zb, True, hops)
+    for h in range(2, 5):
+        ops.gemm(hops[h // 2], hops[h - h // 2], out=hops[h], b_kmajor=False)
+    close(adj, want_adj, what="edge adj")
+    close(un, U * (~mask[:, :, None]) * (~mask[:, None, :]), what="unnorm")
+    close(hops, want_h, what="markov")
+
+
+# ---------------------------------------------------------------------------- head ops
+@pytest.mark.parametrize("h,hm", [(18, 64), (4, 64), (27, 64), (16, 64)])
+def test_support_pooling_matches_reference_form(h, hm):
+    B, K, C = 2, 9, 48
+    feat = rnd(B, h * h, C, seed=1)
+    g = torch.Generator().manual_seed(2)
+    target = torch.rand(B, K, hm, hm, generator=g) * (torch.rand(B, K, hm, hm, generator=g) > 0.9)
+    target[0, 0] = 0            # empty heat-map: sum + 1e-8 guard
+    mask = torch.ones(B, K)
+    mask[1, 5:] = 0
+    f4 = feat.transpose(1, 2).reshape(B, C, h, h)
+    up = F.interpolate(f4, size=(hm, hm), mode="bilinear", align_corners=False)
+    t = target / (target.sum(-1).sum(-1)[:, :, None, None] + 1e-8)
+    want = (t.flatten(2) @ up.flatten(2).permute(0, 2, 1)) * mask[..., None]
+    D = dev()
+    tw = ops.support_weights(target.to(D), mask.to(D), h, h)
+    got = ops.gemm(tw, feat.to(D), b_kmajor=False)
+    close(got, want, tol=5e-5, what="pool")
+
+
+def test_sine_pe_matches_oracle():
+    c = torch.rand(3, 50, 2, generator=torch.Generator().manual_seed(1))
+    close(ops.sine_pe_coords(c.to(dev())), O.sine_pe_coords(c), tol=5e-6, what="pe coords")
+    from edgecape_b200.positional_encoding import SinePositionalEncoding
+    pe = SinePositionalEncoding(num_feats=128, normalize=True)
+    for h in (18, 4, 27):
+        close(pe.grid_tokens(h, h, dev()), O.sine_pe_grid(h, h, torch.float32), tol=5e-6, what="pe grid")
+
+
+@pytest.mark.parametrize("h", [18, 4, 27, 16])
+def test_proposal_argmax_bit_exact(h):
+    B, K, S = 2, 100, h * h
+    sim = rnd(B, K, S, seed=h, scale=3.0)
+    sim[0, 0, 5] = sim[0, 0].max() + 1          # corner / border maxima
+    sim[0, 1, S - 1] = sim[0, 1].max() + 1
+    sim[0, 2, :] = 0.25                           # full tie -> first index
+    sim[0, 3, 7] = sim[0, 3, 3] = sim[0, 3].max() + 2   # two-way tie -> first
+    sm = sim.softmax(-1)
+    gy, gx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h), torch.linspace(0.5, h - 0.5, h), indexing="ij")
+    grid = torch.stack((gx, gy), -1).reshape(S, 2)
+    want_pl = (sm[..., None] * grid).sum(2) / h
+    am = sim.argmax(-1)
+    local = F.max_pool2d(F.one_hot(am, S).reshape(B, K, h, h).float(), 3, 1, 1).reshape(B, K, S)
+    l = sm * local
+    l = l / (l.sum(-1, keepdim=True) + 1e-10)
+    want_pr = (l[..., None] * grid).sum(2) / h
+    pl, pr, gam = ops.proposal(sim.to(dev()), h, h)
+    assert torch.equal(gam.cpu(), am)
+    close(pl, want_pl, tol=1e-5, what="prop loss")
+    close(pr, want_pr, tol=1e-5, what="prop")
+
+
+def test_point_update_and_masks():
+    bi = torch.rand(4, 100, 2, generator=torch.Generator().manual_seed(1))
+    bi[0, 0] = torch.tensor([0.0, 1.0])
+    bi[0, 1] = torch.tensor([1e-4, 0.9999])
+    delta = rnd(400, 2, seed=2)
+    want = (O.inverse_sigmoid(bi) + delta.view(4, 100, 2)).sigmoid()
+    close(ops.point_update(bi.to(dev()), delta.to(dev())), want, tol=2e-6)
+    tw = torch.ones(3, 7, 1)
+    tw[0, 4:] = 0
+    tw[2, :] = 0
+    D = dev()
+    ms = ops.empty(3, 7)
+    ops.mask_accumulate_(tw.to(D).reshape(3, 7), ms, True)
+    ops.mask_accumulate_(tw.to(D).reshape(3, 7), ms, False)
+    m, mf = ops.kp_masks(ms)
+    want_m = ~(tw.squeeze(-1).bool())
+    assert torch.equal(m.cpu().bool(), want_m)
+    wf = want_m.clone()
+    wf[2, 0] = False
+    assert torch.equal(mf.cpu().bool(), wf)
+
+
+# ----------------------------------------------------------------------------- ViT ops
+def test_patch_embed_pos_embed_and_vit_block_match_oracle():
+    from oracle.dinov2_oracle import interpolate_pos_embed
+    B, P, R, C = 2, 14, 256, 64
+    img = rnd(B, 3, R, R, seed=1)
+    w, b = rnd(C, 3, P, P, seed=2, scale=0.05), rnd(C, seed=3)
+    want = F.conv2d(img, w, b, stride=P).flatten(2).transpose(1, 2)
+    D = dev()
+    cols = ops.im2col_patches(img.to(D), P)
+    got = ops.linear(cols, w.reshape(C, -1).to(D), b.to(D)).view(B, -1, C)
+    close(got, want, what="patch embed")
+    pos = rnd(1, 1 + 37 * 37, C, seed=4)
+    for h0 in (18, 16, 27, 37):
+        close(ops.interp_pos_embed(pos.to(D), h0, h0, 0.1), interpolate_pos_embed(pos, h0, h0, 0.1)[0], tol=5e-6,
+              what=f"pos {h0}")
+    pos5 = rnd(1, 26, C, seed=5)
+    for h0 in (4, 6):
+        close(ops.interp_pos_embed(pos5.to(D), h0, h0, 0.1), interpolate_pos_embed(pos5, h0, h0, 0.1)[0], tol=5e-6)
+
+
+def test_pck_counters():
+    B, K = 5, 20
+    g = torch.Generator().manual_seed(0)
+    gt = torch.rand(B, K, 2, generator=g) * 200
+    pred = gt + torch.randn(B, K, 2, generator=g) * 20
+    valid = torch.rand(B, K, generator=g) > 0.3
+    valid[4] = False
+    norm = torch.full((B, 2), 200.0)
+    thr = torch.tensor([0.05, 0.1, 0.15, 0.2, 0.25])
+    want = torch.zeros(6, dtype=torch.float64)
+    for b in range(B):
+        d = ((pred[b] - gt[b]) / norm[b]).norm(dim=-1)
+        for t in range(5):
+            if valid[b].any():
+                want[t] += (d[valid[b]] < thr[t]).double().mean()
+        want[5] += 1
+    D = dev()
+    c = torch.zeros(6, dtype=torch.float64, device=D)
+    ops.pck_accumulate_(c, pred.to(D), gt.to(D), valid.to(torch.uint8).to(D), norm.to(D), thr.to(D))
+    assert torch.allclose(c.cpu(), want, atol=1e-9)
