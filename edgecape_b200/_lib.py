@@ -26,6 +26,9 @@ SIGNATURES = {
     "ec_launch_count": (c_ll, []),
     "ec_gemm": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll,
                         c_ll, c_fp, c_int, c_fp, c_fp, c_int, c_ll, c_int, c_fp]),
+    "ec_split_f16": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_ll, c_int, c_f, c_fp]),
+    "ec_gemm_f16x3": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_ll, c_f, c_fp, c_int, c_fp, c_fp, c_int,
+                              c_int, c_fp, c_int, c_f, c_fp]),
     "ec_layernorm": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_f,
                              c_int, c_int, c_fp]),
     "ec_add_rows": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),

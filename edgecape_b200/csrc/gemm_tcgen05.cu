@@ -1,0 +1,395 @@
+// Tensor-core GEMM for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma -> TMEM -> fused
+// epilogue.  fp32-grade accuracy from fp16 tensor cores by operand splitting:
+//     a = a_hi + a_lo,  b = b_hi + b_lo   (fp16 pairs; |a - a_hi - a_lo| <= max(2^-22 |a|, 2^-25))
+//     a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo      (fp32 accumulation in TMEM)
+// Each pipeline stage holds the four 128x64 fp16 tiles {A_hi, A_lo, B_hi, B_lo} of one 64-wide k-block
+// and feeds 3 x 4 UMMA 128x128x16 instructions, i.e. 4 tile loads per 3 products instead of 6.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (TMEM -> registers -> bias/activation/LayerScale/residual -> global, and
+// optionally the split-fp16 form of the result for the next GEMM).  Two TMEM accumulator stages overlap
+// the epilogue of tile i with the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace ec {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64;           // fp16 elements; BK * 2 B = 128 B = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;               // 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int NUM_ACC = 2;
+constexpr int TMEM_COLS = NUM_ACC * BN;               // 256 fp32 columns
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = BN.
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+  float* C;
+  int M, N, num_kb, Kp, ldc, seg_c;
+  long long seg_stride_c;
+  int vec_c;
+  float out_scale;
+  const float* bias;
+  const float* colscale;
+  const float* R;
+  int ldr, act, res_mode;
+  __half* split_out;   // optional [M, 2*split_kp] = [hi | lo] of the result (next GEMM's A operand)
+  int split_kp;
+  float split_scale;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[NUM_ACC], tmem_empty[NUM_ACC]; then the TMEM address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sb = base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(sb + 0 * TILE_BYTES, &tmA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
+          tma_load_2d(sb + 2 * TILE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+          tma_load_2d(sb + 3 * TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int acc = t & 1;
+        mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sb = base + stage * STAGE_BYTES;
+          const uint64_t a_hi = make_smem_desc(sb + 0 * TILE_BYTES), a_lo = make_smem_desc(sb + 1 * TILE_BYTES);
+          const uint64_t b_hi = make_smem_desc(sb + 2 * TILE_BYTES), b_lo = make_smem_desc(sb + 3 * TILE_BYTES);
+          // small terms first, then hi*hi
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, 1u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, 1u);
+          umma_commit(empty_bar(stage));           // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));               // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      mbar_wait(tfull_bar(acc), (t >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < p.N) {
+          float* crow = (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
+                                     : p.C + (long long)row * p.ldc) + col0;
+          const float* rrow = p.R ? p.R + (long long)row * p.ldr + col0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int n = col0 + j + u;
+              float v = __uint_as_float(r[j + u]) * p.out_scale;
+              if (n < p.N) {
+                if (p.bias) v += __ldg(p.bias + n);
+                v = apply_act(v, p.act);
+                if (p.colscale) v *= __ldg(p.colscale + n);
+                if (rrow) v = (p.res_mode == EC_RES_GATE) ? (v + 1.0f) * rrow[j + u] : rrow[j + u] + v;
+              }
+              y[u] = v;
+            }
+            if (col0 + j + 3 < p.N && p.vec_c) {
+              *reinterpret_cast<float4*>(crow + j) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (col0 + j + u < p.N) crow[j + u] = y[u];
+            }
+            if (p.split_out) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int n = col0 + j + u;
+                if (n < p.N) {
+                  const float s = y[u] * p.split_scale;
+                  const __half hi = __float2half_rn(s);
+                  p.split_out[(long long)row * (2 * p.split_kp) + n] = hi;
+                  p.split_out[(long long)row * (2 * p.split_kp) + p.split_kp + n] = __float2half_rn(s - __half2float(hi));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// X [M, K] fp32 (row stride ldx) -> X2 [M, 2*Kp] fp16 = [hi | lo] of X*scale, zero padded to Kp.
+__global__ void split_f16_kernel(const float* __restrict__ X, __half* __restrict__ X2, int M, int K, int ldx, int seg,
+                                 long long seg_stride, int Kp, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 2 elements
+  const int half_kp = Kp >> 1;
+  if (i >= (long long)M * half_kp) return;
+  const int m = (int)(i / half_kp), k = (int)(i % half_kp) * 2;
+  const float* x = seg > 0 ? X + (long long)(m / seg) * seg_stride + (long long)(m % seg) * ldx : X + (long long)m * ldx;
+  float v0 = 0.f, v1 = 0.f;
+  if (k < K) v0 = x[k] * scale;
+  if (k + 1 < K) v1 = x[k + 1] * scale;
+  const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+  const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+  __half2* row = reinterpret_cast<__half2*>(X2 + (long long)m * 2 * Kp);
+  row[k >> 1] = __halves2half2(h0, h1);
+  row[(Kp + k) >> 1] = __halves2half2(l0, l1);
+}
+
+// ------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int rows, kp;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kp == o.kp; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.kp) * 7919u);
+  }
+};
+
+static int get_tensor_map(const void* ptr, int rows, int kp, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  MapKey key{ptr, rows, kp};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EC_OK;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return EC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)(2 * kp), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(2 * kp) * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %d kp %d)", (int)r, ptr, rows, kp);
+    return EC_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return EC_OK;
+}
+
+}  // namespace tc
+}  // namespace ec
+
+using namespace ec;
+
+extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int seg, long long seg_stride, int Kp,
+                            float scale, void* stream) {
+  EC_REQUIRE(X && X2, "ec_split_f16: null pointer");
+  EC_REQUIRE(Kp % tc::BK == 0 && Kp >= K && K > 0, "ec_split_f16: Kp must be a multiple of 64 and >= K");
+  if (M == 0) return EC_OK;
+  long long total = (long long)M * (Kp / 2);
+  tc::split_f16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(X, (__half*)X2, M, K, ldx, seg, seg_stride, Kp,
+                                                                              scale);
+  return check_launch("ec_split_f16");
+}
+
+extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp, int ldc, int seg_c,
+                             long long seg_stride_c, float out_scale,
+                             const float* bias, int act, const float* colscale, const float* R, int ldr,
+                             int res_mode, void* split_out, int split_kp, float split_scale, void* stream) {
+  EC_REQUIRE(A2 && B2 && C, "ec_gemm_f16x3: null operand");
+  EC_REQUIRE(Kp > 0 && Kp % tc::BK == 0, "ec_gemm_f16x3: Kp must be a positive multiple of 64");
+  EC_REQUIRE(aligned16(A2) && aligned16(B2) && aligned16(C), "ec_gemm_f16x3: operands must be 16-byte aligned");
+  EC_REQUIRE((res_mode == EC_RES_NONE) == (R == nullptr), "ec_gemm_f16x3: residual pointer/mode mismatch");
+  EC_REQUIRE(!split_out || (split_kp % tc::BK == 0 && split_kp >= N), "ec_gemm_f16x3: bad split_kp");
+  if (M == 0 || N == 0) return EC_OK;
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int dev = 0;
+    EC_CUDA(cudaGetDevice(&dev));
+    EC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = tc::get_tensor_map(A2, M, Kp, &tmA);
+  if (rc) return rc;
+  rc = tc::get_tensor_map(B2, N, Kp, &tmB);
+  if (rc) return rc;
+  tc::TcParams p;
+  p.C = C; p.M = M; p.N = N; p.num_kb = Kp / tc::BK; p.Kp = Kp; p.ldc = ldc;
+  p.seg_c = seg_c; p.seg_stride_c = seg_stride_c;
+  p.vec_c = (ldc % 4 == 0) && (seg_stride_c % 4 == 0);
+  p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
+  p.res_mode = res_mode; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
+  const int tiles = cdiv(M, tc::BM) * cdiv(N, tc::BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  tc::gemm_f16x3_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return check_launch("ec_gemm_f16x3");
+}

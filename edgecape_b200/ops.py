@@ -5,6 +5,10 @@ and batch strides are forwarded as ld / stride arguments), enqueues the kernels 
 current stream and returns the output tensor.  PyTorch is used for allocation and streams only;
 no torch compute op is called here, and nothing falls back to the CPU.
 """
+import math
+import os
+import weakref
+
 import torch
 
 from . import _lib
@@ -76,11 +80,116 @@ def gemm(a, b, out=None, b_kmajor=True, bias=None, act=ACT_NONE, colscale=None, 
     return out
 
 
-def linear(x, w, bias=None, **kw):
-    """nn.Linear on the last dimension of a 2-D/3-D view; w is [N,K] (conv 1x1 weights are reshaped)."""
+# ------------------------------------------------------------- tensor-core (tcgen05) linears
+# EDGECAPE_TC=0 routes every linear through the fp32 SIMT GEMM (bit-faithful FFMA reference path);
+# the default uses the split-fp16 tcgen05 GEMM wherever the shape fills a 128x128 tile reasonably.
+TENSOR_CORES = os.environ.get("EDGECAPE_TC", "1") != "0"
+TC_MIN_M, TC_MIN_N, TC_MIN_K = 64, 32, 32
+_SPLIT_WEIGHTS = {}
+
+
+class SplitOperand:
+    """fp16 [rows, 2*Kp] = [hi | lo] form of an fp32 matrix (scaled by `scale`, a power of two)."""
+    __slots__ = ("data", "rows", "K", "Kp", "scale")
+
+    def __init__(self, data, rows, K, Kp, scale):
+        self.data, self.rows, self.K, self.Kp, self.scale = data, rows, K, Kp, scale
+
+
+def _kp(K):
+    return (K + 63) // 64 * 64
+
+
+def split_f16(x, scale=1.0, out=None):
+    """fp32 rows (2-D view, or 3-D [B,S,K] view read in place) -> SplitOperand."""
+    M, K, ldx, seg, seg_stride = _seg(x, "x")
+    Kp = _kp(K)
+    if out is None:
+        out = empty(M, 2 * Kp, dtype=torch.float16, device=x.device)
+    assert out.is_contiguous() and out.dtype == torch.float16 and out.numel() == M * 2 * Kp
+    _lib.call("ec_split_f16", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), _stream())
+    return SplitOperand(out, M, K, Kp, float(scale))
+
+
+def split_weight(w):
+    """Cached split form of a weight matrix [N,K] (one-time repack per checkpoint: the power-of-two
+    scale is picked from the tensor's absmax so that small weights stay out of the fp16 subnormals)."""
+    owner = w._base if w._base is not None else w        # the nn.Parameter behind a reshaped view
+    key = (id(owner), w.data_ptr(), owner._version, tuple(w.shape))
+    hit = _SPLIT_WEIGHTS.get(key)
+    sw = hit[1] if hit is not None and hit[0]() is owner else None   # guards against id / address reuse
+    if sw is None:
+        amax = float(w.detach().abs().max())
+        scale = 1.0
+        if amax > 0 and math.isfinite(amax):
+            scale = 2.0 ** max(-8, min(14, math.floor(math.log2(16384.0 / amax))))
+        sw = split_f16(w.detach(), scale)
+        if len(_SPLIT_WEIGHTS) > 4096:
+            _SPLIT_WEIGHTS.clear()
+        _SPLIT_WEIGHTS[key] = (weakref.ref(owner), sw)
+    return sw
+
+
+def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
+            split_out=False):
+    """out = epilogue(A @ B^T) on the tcgen05 tensor cores from two SplitOperands.  `out` may be a
+    2-D view or a 3-D [B,S,N] view with B*S == M (batch-strided rows).  With split_out=True also
+    returns the SplitOperand of the result (produced by the epilogue)."""
+    assert a2.Kp == b2.Kp, f"gemm_tc: padded K differs ({a2.Kp} vs {b2.Kp})"
+    M, N = a2.rows, b2.rows
+    dev = a2.data.device
+    if out is None:
+        out = empty(M, N, device=dev)
+    Mo, No, ldc, seg_c, seg_stride_c = _seg(out, "out")
+    assert (Mo, No) == (M, N), f"gemm_tc: out {tuple(out.shape)} does not hold {(M, N)}"
+    ldr = 0
+    if residual is not None:
+        Mr, Nr, ldr, seg_r, _ = _seg(residual, "residual")
+        assert (Mr, Nr) == (M, N) and seg_r == 0, "gemm_tc: residual must be a plain 2-D row view"
+    else:
+        res_mode = RES_NONE
+    _chk(bias, "bias")
+    _chk(colscale, "colscale")
+    so, so_ptr, so_kp = None, None, 0
+    if split_out:
+        so_kp = _kp(N)
+        buf = (torch.zeros if so_kp != N else torch.empty)(M, 2 * so_kp, dtype=torch.float16, device=dev)
+        so = SplitOperand(buf, M, N, so_kp, 1.0)
+        so_ptr = buf.data_ptr()
+    _lib.call("ec_gemm_f16x3", _p(a2.data), _p(b2.data), _p(out), M, N, a2.Kp, ldc, seg_c, seg_stride_c,
+              1.0 / (a2.scale * b2.scale), _p(bias), act, _p(colscale), _p(residual), ldr, res_mode, so_ptr, so_kp,
+              1.0, _stream())
+    return (out, so) if split_out else out
+
+
+def _tc_ok(x, w, residual):
+    if not TENSOR_CORES:
+        return False
+    if residual is not None and residual.dim() == 3 and _seg(residual, "residual")[3] != 0:
+        return False
+    if isinstance(x, SplitOperand):
+        return True
+    M = x.numel() // x.shape[-1]
+    return M >= TC_MIN_M and w.shape[0] >= TC_MIN_N and w.shape[1] >= TC_MIN_K
+
+
+def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
+           split_out=False):
+    """nn.Linear on the last dimension of a 2-D/3-D view (or an already split A operand); w is [N,K]
+    (conv 1x1 weights are reshaped).  Dispatches to the tcgen05 kernel or the fp32 SIMT kernel."""
     if w.dim() > 2:
         w = w.reshape(w.shape[0], -1)
-    return gemm(x, w, b_kmajor=True, bias=bias, **kw)
+    if _tc_ok(x, w, residual):
+        a2 = x if isinstance(x, SplitOperand) else split_f16(x)
+        if out is None and not isinstance(x, SplitOperand) and x.dim() == 3:
+            out = empty(x.shape[0], x.shape[1], w.shape[0], device=x.device)
+        res = gemm_tc(a2, split_weight(w), out=out, bias=bias, act=act, colscale=colscale, residual=residual,
+                      res_mode=res_mode, split_out=split_out)
+        return res
+    assert not isinstance(x, SplitOperand), "a split operand needs the tensor-core path"
+    y = gemm(x, w, out=out, b_kmajor=True, bias=bias, act=act, colscale=colscale, residual=residual,
+             res_mode=res_mode)
+    return (y, None) if split_out else y
 
 
 def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None):

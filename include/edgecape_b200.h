@@ -62,6 +62,25 @@ int ec_gemm(const float* A, const float* B, float* C, int M, int N, int K, int l
             const float* bias, int act, const float* colscale, const float* R, int ldr,
             long long strideR, int res_mode, void* stream);
 
+/* ------------------------------------------------- tensor-core contraction (tcgen05, sm_100a)
+ * C = epilogue(out_scale * A * B^T) with the epilogue of ec_gemm (b_kmajor = 1, batch = 1),
+ * computed on the 5th-gen tensor cores with fp32-grade accuracy: both operands are pre-split
+ * into fp16 (hi, lo) pairs, A2 = [M, 2*Kp] and B2 = [N, 2*Kp] halves laid out [hi | lo] per row
+ * (Kp = K rounded up to a multiple of 64, zero padded), and the kernel accumulates
+ * lo*hi + hi*lo + hi*hi into one fp32 TMEM accumulator (TMA-fed, 128B-swizzled shared-memory
+ * tiles, 128x128x16 UMMA).  ec_split_f16 produces the split layout from fp32 rows
+ * (row m at X + (m / seg) * seg_stride + (m % seg) * ldx; seg = 0: m * ldx), multiplying by
+ * `scale` first (a power of two chosen per weight tensor keeps small weights out of the fp16
+ * subnormal range; out_scale undoes it).  If split_out != NULL the epilogue also stores the
+ * split form of the result, [M, 2*split_kp], ready to be the next GEMM's A operand.  Row m of C
+ * lives at C + (m / seg_c) * seg_stride_c + (m % seg_c) * ldc (seg_c = 0: m * ldc). */
+int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int seg, long long seg_stride,
+                 int Kp, float scale, void* stream);
+int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp, int ldc,
+                  int seg_c, long long seg_stride_c, float out_scale, const float* bias, int act, const float* colscale,
+                  const float* R, int ldr, int res_mode, void* split_out, int split_kp,
+                  float split_scale, void* stream);
+
 /* ------------------------------------------------------------------------- normalisation
  * Y[m,:] = LayerNorm(X[m,:] (+ R[m,:])) * w + b  (biased variance, eps inside the sqrt).
  * Row m of X lives at X + (m / seg) * seg_stride + (m % seg) * ldx  (seg = 0: plain m * ldx) so a

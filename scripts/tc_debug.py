@@ -1,0 +1,74 @@
+"""Stand-alone bring-up of the tcgen05 GEMM (run on the GPU box, each stage under its own timeout)."""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from edgecape_b200 import ops  # noqa: E402
+
+
+def check(M, N, K, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.02
+    D = torch.device("cuda")
+    a2, b2 = ops.split_f16(x.to(D)), ops.split_f16(w.to(D), 1024.0)
+    got = ops.gemm_tc(a2, b2)
+    torch.cuda.synchronize()
+    want = (x.double() @ w.double().T).float()
+    g_ = got.cpu()
+    err = (g_ - want).abs().max().item() / want.abs().max().item()
+    print(f"tc {M}x{N}x{K}: rel err {err:.3e}  got[0,:4]={g_[0, :4].tolist()} want[0,:4]={want[0, :4].tolist()}", flush=True)
+    if err > 1e-4:
+        # diagnostics: hi*hi only? row/col permutation?
+        hh = (a2.data[:, :a2.Kp].float() @ b2.data[:, :b2.Kp].float().T / 1024.0).cpu()
+        print("   vs hi*hi only:", ((g_ - hh).abs().max() / hh.abs().max()).item())
+        print("   nonzero frac:", (g_ != 0).float().mean().item(), " nan:", torch.isnan(g_).any().item())
+        for r in (0, 1, 8, 32, 64, 127):
+            if r < M:
+                best = (want - g_[r][None]).abs().sum(1).argmin().item()
+                print(f"   got row {r} is closest to want row {best}")
+    return err
+
+
+def bench(M, N, K, iters=20):
+    D = torch.device("cuda")
+    x = torch.randn(M, K, device=D)
+    w = torch.randn(N, K, device=D) * 0.02
+    a2, b2 = ops.split_f16(x), ops.split_f16(w, 1024.0)
+    out = torch.empty(M, N, device=D)
+    for _ in range(3):
+        ops.gemm_tc(a2, b2, out=out)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        ops.gemm_tc(a2, b2, out=out)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    s.record()
+    for _ in range(iters):
+        ops.gemm(x, w, out=out)
+    e.record()
+    torch.cuda.synchronize()
+    ms2 = s.elapsed_time(e) / iters
+    print(f"bench {M}x{N}x{K}: tc {ms:.3f} ms = {tf:.1f} algorithmic TFLOP/s ({3 * tf:.1f} issued); simt {ms2:.3f} ms "
+          f"= {2.0 * M * N * K / ms2 / 1e9:.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    stage = sys.argv[1]
+    if stage == "tiny":
+        check(128, 128, 64)
+    elif stage == "k2":
+        check(128, 128, 256)
+    elif stage == "multi":
+        check(512, 384, 768)
+        check(1300, 768, 768)
+        check(200, 96, 100)
+    elif stage == "bench":
+        for shp in [(10400, 2304, 768), (10400, 768, 768), (10400, 3072, 768), (10400, 768, 3072), (5184, 256, 768),
+                    (1600, 256, 256)]:
+            bench(*shp)

@@ -12,9 +12,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-_ITEM = {np.float32: 4, np.uint8: 1, np.int32: 4, np.int64: 8, np.float64: 8}
+_ITEM = {np.float32: 4, np.uint8: 1, np.int32: 4, np.int64: 8, np.float64: 8, np.float16: 2}
 _CT = {np.float32: ctypes.c_float, np.uint8: ctypes.c_uint8, np.int32: ctypes.c_int32, np.int64: ctypes.c_int64,
-       np.float64: ctypes.c_double}
+       np.float64: ctypes.c_double, np.float16: ctypes.c_uint16}
 
 
 def arr(ptr, shape, strides=None, dtype=np.float32):
@@ -32,6 +32,8 @@ def arr(ptr, shape, strides=None, dtype=np.float32):
     span = 1 + sum((n - 1) * st for n, st in zip(shape, strides))
     buf = (_CT[dtype] * span).from_address(ptr)
     base = np.ctypeslib.as_array(buf)
+    if dtype is np.float16:
+        base = base.view(np.float16)
     return np.lib.stride_tricks.as_strided(base, shape=shape, strides=tuple(st * _ITEM[dtype] for st in strides))
 
 
@@ -95,6 +97,37 @@ def ec_gemm(A, B, C, M, N, K, lda, ldb, ldc, b_kmajor, batch, sA, sB, sC, bias, 
         r = T(arr(R, (batch, M, N), (sR, ldr, 1)))
         y = (y + 1) * r if res_mode == 2 else r + y
     arr(C, (batch, M, N), (sC, ldc, 1))[...] = y.numpy()
+
+
+def ec_split_f16(X, X2, M, K, ldx, seg, seg_stride, Kp, scale, stream):
+    x = _get(rows(X, M, K, ldx, seg, seg_stride)).astype(np.float32) * np.float32(scale)
+    hi = x.astype(np.float16)
+    lo = (x - hi.astype(np.float32)).astype(np.float16)
+    out = arr(X2, (M, 2 * Kp), dtype=np.float16)
+    out[...] = 0
+    out[:, :K], out[:, Kp:Kp + K] = hi, lo
+
+
+def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act, colscale, R, ldr, res_mode,
+                  split_out, split_kp, split_scale, stream):
+    a = T(arr(A2, (M, 2 * Kp), dtype=np.float16).astype(np.float32))
+    b = T(arr(B2, (N, 2 * Kp), dtype=np.float16).astype(np.float32))
+    ah, al, bh, bl = a[:, :Kp], a[:, Kp:], b[:, :Kp], b[:, Kp:]
+    y = (al @ bh.T + ah @ bl.T + ah @ bh.T) * np.float32(out_scale)
+    if bias:
+        y = y + T(arr(bias, (N,)))
+    y = _act(y, act)
+    if colscale:
+        y = y * T(arr(colscale, (N,)))
+    if R:
+        r = T(arr(R, (M, N), (ldr, 1)))
+        y = (y + 1) * r if res_mode == 2 else r + y
+    _set(rows(C, M, N, ldc, seg_c, seg_stride_c), y.numpy())
+    if split_out:
+        s = y.numpy() * np.float32(split_scale)
+        hi = s.astype(np.float16)
+        out = arr(split_out, (M, 2 * split_kp), dtype=np.float16)
+        out[:, :N], out[:, split_kp:split_kp + N] = hi, (s - hi.astype(np.float32)).astype(np.float16)
 
 
 def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, stream):

@@ -53,8 +53,11 @@ def _compare(name, got, want, report):
     return worst
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False], ids=["tcgen05", "simt_fp32"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_detector_matches_reference_golden(name, golden_dir):
+def test_detector_matches_reference_golden(name, tensor_cores, golden_dir, monkeypatch):
+    from edgecape_b200 import ops
+    monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     cfg, data, wseed = build_case(name)
     model = _build(cfg, wseed)
@@ -70,7 +73,7 @@ def test_detector_matches_reference_golden(name, golden_dir):
                skeleton=res["skeleton"])
     rep = {}
     worst = _compare(name, got, golden, rep)
-    REPORT[name] = rep
+    REPORT[name + ("[tc]" if tensor_cores else "[simt]")] = rep
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/e2e_parity.json", "w") as fh:
         json.dump(REPORT, fh, indent=1, sort_keys=True)

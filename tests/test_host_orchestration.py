@@ -23,9 +23,12 @@ def _np(t):
     return t.detach().float().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False], ids=["split_f16_path", "fp32_path"])
 @pytest.mark.parametrize("name", CASES)
-def test_host_orchestration_against_golden(name, golden_dir, monkeypatch):
+def test_host_orchestration_against_golden(name, tensor_cores, golden_dir, monkeypatch):
+    from edgecape_b200 import ops
     cpu_emulator.install(monkeypatch)
+    monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     cfg, data, wseed = build_case(name)
     model = E.build_model(dict(model=cfg))

@@ -343,3 +343,84 @@ def test_pck_counters():
     c = torch.zeros(6, dtype=torch.float64, device=D)
     ops.pck_accumulate_(c, pred.to(D), gt.to(D), valid.to(torch.uint8).to(D), norm.to(D), thr.to(D))
     assert torch.allclose(c.cpu(), want, atol=1e-9)
+
+
+# ------------------------------------------------------------- tensor-core (tcgen05) GEMM
+def test_split_f16_reconstructs_fp32():
+    x = rnd(300, 588, seed=1, scale=2.0)
+    x[0, :4] = torch.tensor([1e-6, -3e-5, 1000.0, 0.0])
+    so = ops.split_f16(x.to(dev()))
+    assert so.Kp == 640 and tuple(so.data.shape) == (300, 1280)
+    d = so.data.float().cpu()
+    rec = d[:, :588] + d[:, 640:640 + 588]
+    assert (d[:, 588:640] == 0).all() and (d[:, 640 + 588:] == 0).all()
+    err = (rec - x).abs()
+    bound = torch.maximum(x.abs() * 2.0 ** -21, torch.full_like(x, 2.0 ** -24))
+    assert (err <= bound).all(), f"split error {err.max().item():.3e}"
+    # strided 3-D view (cls row dropped) read in place
+    t = rnd(3, 17, 64, seed=2).to(dev())
+    so = ops.split_f16(t[:, 1:, :])
+    rec = (so.data[:, :64].float() + so.data[:, 64:].float()).cpu()
+    close(rec, t[:, 1:, :].reshape(48, 64), tol=1e-6, what="split seg")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (128, 256, 192), (1300, 768, 768),
+                                   (200, 96, 100), (5184, 256, 768), (650, 3072, 768), (650, 768, 3072), (77, 33, 516)])
+def test_gemm_tc_fp32_grade(M, N, K):
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.02), rnd(N, seed=3)
+    want = (x.double() @ w.double().T + b.double())
+    D = dev()
+    got = ops.gemm_tc(ops.split_f16(x.to(D)), ops.split_f16(w.to(D), 2.0 ** 10), bias=b.to(D))
+    err = close(got, want.float(), tol=3e-6, what=f"tc {M}x{N}x{K}")
+    # and it must be at least as accurate as the fp32 FFMA kernel is
+    ref = ops.gemm(x.to(D), w.to(D), bias=b.to(D))
+    e32 = (ref.double().cpu() - want).abs().max().item() / want.abs().max().item()
+    assert err <= max(4 * e32, 3e-6), (err, e32)
+
+
+def test_gemm_tc_epilogues_views_and_split_out():
+    M, N, K = 700, 320, 256
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    g, r = rnd(N, seed=4), rnd(M, N, seed=5)
+    D = dev()
+    a2, b2 = ops.split_f16(x.to(D)), ops.split_f16(w.to(D), 64.0)
+    y = F.linear(x, w, b)
+    for act, fn in ((ops.ACT_NONE, lambda t: t), (ops.ACT_RELU, F.relu), (ops.ACT_GELU, F.gelu), (ops.ACT_TANH, torch.tanh)):
+        got = ops.gemm_tc(a2, b2, bias=b.to(D), act=act, colscale=g.to(D), residual=r.to(D))
+        close(got, r + g * fn(y), tol=1e-5, what=f"tc act{act}")
+    got = ops.gemm_tc(a2, b2, bias=b.to(D), act=ops.ACT_TANH, residual=r.to(D), res_mode=ops.RES_GATE)
+    close(got, (torch.tanh(y) + 1) * r, tol=1e-5, what="tc gate")
+    # in-place residual, column-slice output view, batch-strided 3-D output view
+    acc = r.to(D).clone()
+    ops.gemm_tc(a2, b2, bias=b.to(D), residual=acc, out=acc)
+    close(acc, r + y, tol=1e-5, what="tc in-place")
+    wide = torch.zeros(M, 2 * N, device=D)
+    ops.gemm_tc(a2, b2, bias=b.to(D), out=wide[:, N:])
+    close(wide[:, N:], y, tol=1e-5, what="tc ld view")
+    assert (wide[:, :N] == 0).all()
+    tok = torch.zeros(7, 101, N, device=D)
+    ops.gemm_tc(a2, b2, bias=b.to(D), out=tok[:, 1:, :])
+    close(tok[:, 1:, :].reshape(M, N), y, tol=1e-5, what="tc seg view")
+    assert (tok[:, 0, :] == 0).all()
+    # fused split of the result
+    got, so = ops.gemm_tc(a2, b2, bias=b.to(D), act=ops.ACT_GELU, split_out=True)
+    rec = so.data[:, :N].float() + so.data[:, so.Kp:so.Kp + N].float()
+    close(rec, got, tol=1e-6, what="split_out")
+
+
+def test_linear_dispatch_uses_tensor_cores_and_matches_simt(monkeypatch):
+    from edgecape_b200 import _lib
+    x, w, b = rnd(3, 324, 768, seed=1), rnd(256, 768, seed=2, scale=0.03), rnd(256, seed=3)
+    D = dev()
+    xd, wd, bd = x.to(D), torch.nn.Parameter(w.to(D), requires_grad=False), b.to(D)
+    names = []
+    orig = _lib.call
+    monkeypatch.setattr(_lib, "call", lambda n, *a: (names.append(n), orig(n, *a))[1])
+    monkeypatch.setattr(ops, "TENSOR_CORES", True)
+    y_tc = ops.linear(xd, wd, bd)
+    assert "ec_gemm_f16x3" in names and "ec_gemm" not in names
+    monkeypatch.setattr(ops, "TENSOR_CORES", False)
+    y_32 = ops.linear(xd, wd, bd)
+    assert names[-1] == "ec_gemm"
+    close(y_tc, y_32, tol=3e-6, what="tc vs simt")
+    close(y_tc, F.linear(x, w, b), tol=3e-6, what="tc vs torch")
