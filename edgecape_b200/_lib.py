@@ -76,11 +76,18 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise EdgeCapeLibraryError(f"{LIB_PATH} is missing; run `python -m edgecape_b200.build`")
+    if build_if_missing:
+        # cheap digest check of csrc/ + include/: rebuilds a missing or stale library when nvcc exists
         from .build import build
-        build()
+        try:
+            build()
+        except Exception as e:
+            if not os.path.exists(LIB_PATH):
+                raise EdgeCapeLibraryError(f"cannot build {LIB_PATH}: {e}") from e
+            if "nvcc not found" not in str(e):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise EdgeCapeLibraryError(f"{LIB_PATH} is missing; run `python -m edgecape_b200.build`")
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:  # pragma: no cover
