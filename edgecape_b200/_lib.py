@@ -30,12 +30,12 @@ SIGNATURES = {
     "ec_gemm_f16x3": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_ll, c_f, c_fp, c_int, c_fp, c_fp, c_int,
                               c_int, c_fp, c_int, c_f, c_fp]),
     "ec_layernorm": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_f,
-                             c_int, c_int, c_fp]),
+                             c_int, c_int, c_fp, c_int, c_fp]),
     "ec_add_rows": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "ec_copy_rows": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_int, c_ll, c_int, c_int, c_int, c_fp]),
     "ec_axpby": (c_int, [c_fp, c_fp, c_fp, c_f, c_f, c_f, c_ll, c_fp]),
     "ec_attention": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                             c_int, c_ll, c_ll, c_ll, c_ll, c_f, c_fp, c_fp, c_fp]),
+                             c_int, c_ll, c_ll, c_ll, c_ll, c_f, c_fp, c_fp, c_fp, c_int, c_fp]),
     "ec_hop_bias": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_mask_accumulate": (c_int, [c_fp, c_fp, c_int, c_int, c_fp]),
     "ec_kp_masks": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_fp]),

@@ -6,6 +6,7 @@
 // online-softmax rescale per chunk.  Exact fp32 arithmetic (expf, no fast-math): this kernel is
 // the parity path for all attentions of the head and, until the tcgen05 attention is enabled,
 // the ViT.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -25,6 +26,8 @@ struct AttnParams {
   float scale;
   const uint8_t* key_mask;
   const float* bias;
+  __half* split_out;   // optional [B*Lq, 2*split_kp] split-fp16 form of O
+  int split_kp;
 };
 
 template <int D>
@@ -128,10 +131,23 @@ __global__ void __launch_bounds__(ATT_ROWS) attention_kernel(AttnParams p) {
     // a fully masked row is NaN in the reference (softmax of all -inf); the reference guards
     // against it (encoder_decoder.py:359-360) so it never occurs on the path.  We return 0.
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    float4* op = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)row * p.ldo + h * D);
+    if (p.O) {
+      float4* op = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)row * p.ldo + h * D);
 #pragma unroll
-    for (int d = 0; d < D / 4; ++d)
-      op[d] = make_float4(o[4 * d + 0] * inv, o[4 * d + 1] * inv, o[4 * d + 2] * inv, o[4 * d + 3] * inv);
+      for (int d = 0; d < D / 4; ++d)
+        op[d] = make_float4(o[4 * d + 0] * inv, o[4 * d + 1] * inv, o[4 * d + 2] * inv, o[4 * d + 3] * inv);
+    }
+    if (p.split_out) {
+      __half* sp = p.split_out + ((long long)b * p.Lq + row) * (2 * p.split_kp) + h * D;
+#pragma unroll
+      for (int d = 0; d < D; d += 2) {
+        const float v0 = o[d] * inv, v1 = o[d + 1] * inv;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        *reinterpret_cast<__half2*>(sp + d) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(sp + p.split_kp + d) =
+            __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+      }
+    }
   }
 }
 
@@ -179,15 +195,18 @@ using namespace ec;
 extern "C" int ec_attention(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq,
                             int Lk, int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk,
                             long long sv, long long so, float scale, const uint8_t* key_mask,
-                            const float* bias, void* stream) {
-  EC_REQUIRE(Q && K && V && O, "ec_attention: null pointer");
+                            const float* bias, void* split_out, int split_kp, void* stream) {
+  EC_REQUIRE(Q && K && V && (O || split_out), "ec_attention: null pointer");
+  EC_REQUIRE(!split_out || split_kp == H * D, "ec_attention: split_out needs split_kp == H*D (a multiple of 64)");
+  EC_REQUIRE(!split_out || (H * D) % 64 == 0, "ec_attention: split_out needs H*D to be a multiple of 64");
   EC_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, "ec_attention: bad shape");
-  EC_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) && ldq % 4 == 0 && ldk % 4 == 0 &&
+  EC_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && (!O || aligned16(O)) && ldq % 4 == 0 && ldk % 4 == 0 &&
                  ldv % 4 == 0 && ldo % 4 == 0 && sq % 4 == 0 && sk % 4 == 0 && sv % 4 == 0 && so % 4 == 0,
              "ec_attention: operands must be 16-byte aligned with strides that are multiples of 4");
   if (B == 0 || Lq == 0) return EC_OK;
   EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention: grid too large");
-  AttnParams p{Q, K, V, O, B, H, Lq, Lk, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, key_mask, bias};
+  AttnParams p{Q, K, V, O, B, H, Lq, Lk, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, key_mask, bias,
+               (__half*)split_out, split_kp};
   dim3 grid(cdiv(Lq, ATT_ROWS), H, B);
   cudaStream_t st = (cudaStream_t)stream;
   switch (D) {

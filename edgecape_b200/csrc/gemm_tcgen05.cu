@@ -27,7 +27,9 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
 constexpr int NUM_ACC = 2;
 constexpr int TMEM_COLS = NUM_ACC * BN;               // 256 fp32 columns
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 36;                           // staging row stride (floats)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;       // one 32 x 32 staging tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,7 +104,7 @@ struct TcParams {
   float* C;
   int M, N, num_kb, Kp, ldc, seg_c;
   long long seg_stride_c;
-  int vec_c;
+  int vec_c, vec_r;
   float out_scale;
   const float* bias;
   const float* colscale;
@@ -124,6 +126,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
+  const uint32_t epi_base = bar_base + 256u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,64 +198,98 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ---------------------------------------------------------------------- epilogue
+    // TMEM gives each lane one accumulator row; rows are transposed through a per-warp shared-memory
+    // staging tile (row stride 36 floats: conflict-free float4 writes and reads) so that global
+    // traffic is full 128 B lines: 8 lanes cover one 32-column row segment, a warp covers 4 rows.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    float* stage = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
+    const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
-          float* crow = (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
-                                     : p.C + (long long)row * p.ldc) + col0;
-          const float* rrow = p.R ? p.R + (long long)row * p.ldr + col0 : nullptr;
+        if (c == BN / 32 - 1) {
+          // accumulator fully drained into registers: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float y[4];
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int gcol = n0 + c * 32 + c4;
+        if (gcol < p.N) {
+          const bool full = gcol + 3 < p.N;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int n = col0 + j + u;
-              float v = __uint_as_float(r[j + u]) * p.out_scale;
-              if (n < p.N) {
-                if (p.bias) v += __ldg(p.bias + n);
-                v = apply_act(v, p.act);
-                if (p.colscale) v *= __ldg(p.colscale + n);
-                if (rrow) v = (p.res_mode == EC_RES_GATE) ? (v + 1.0f) * rrow[j + u] : rrow[j + u] + v;
-              }
-              y[u] = v;
+          for (int u = 0; u < 4; ++u)
+            if (gcol + u < p.N) {
+              if (p.bias) bv[u] = __ldg(p.bias + gcol + u);
+              if (p.colscale) sv[u] = __ldg(p.colscale + gcol + u);
             }
-            if (col0 + j + 3 < p.N && p.vec_c) {
-              *reinterpret_cast<float4*>(crow + j) = make_float4(y[0], y[1], y[2], y[3]);
-            } else {
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (col0 + j + u < p.N) crow[j + u] = y[u];
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + sub_row;
+            const int row = m0 + quarter * 32 + rl;
+            if (row >= p.M) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * EPI_LD + c4);
+            float y[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) y[u] = apply_act(fmaf(y[u], p.out_scale, bv[u]), p.act) * sv[u];
+            if (p.R) {
+              const float* rp = p.R + (long long)row * p.ldr + gcol;
+              float rr[4] = {0.f, 0.f, 0.f, 0.f};
+              if (full && p.vec_r) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rp);
+                rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (gcol + u < p.N) rr[u] = rp[u];
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) y[u] = (p.res_mode == EC_RES_GATE) ? (y[u] + 1.0f) * rr[u] : rr[u] + y[u];
+            }
+            if (p.C) {
+              float* cp = (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
+                                       : p.C + (long long)row * p.ldc) + gcol;
+              if (full && p.vec_c) {
+                *reinterpret_cast<float4*>(cp) = make_float4(y[0], y[1], y[2], y[3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (gcol + u < p.N) cp[u] = y[u];
+              }
             }
             if (p.split_out) {
+              __half hi[4], lo[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const int n = col0 + j + u;
-                if (n < p.N) {
-                  const float s = y[u] * p.split_scale;
-                  const __half hi = __float2half_rn(s);
-                  p.split_out[(long long)row * (2 * p.split_kp) + n] = hi;
-                  p.split_out[(long long)row * (2 * p.split_kp) + p.split_kp + n] = __float2half_rn(s - __half2float(hi));
-                }
+                const float sc = (gcol + u < p.N) ? y[u] * p.split_scale : 0.f;
+                hi[u] = __float2half_rn(sc);
+                lo[u] = __float2half_rn(sc - __half2float(hi[u]));
               }
+              __half* sp = p.split_out + (long long)row * (2 * p.split_kp) + gcol;   // gcol % 4 == 0: 8 B aligned
+              *reinterpret_cast<uint2*>(sp) = make_uint2(
+                  (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16),
+                  (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16));
+              *reinterpret_cast<uint2*>(sp + p.split_kp) = make_uint2(
+                  (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16),
+                  (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16));
             }
           }
         }
+        __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
   tc_fence_before();
@@ -362,9 +399,10 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
                              long long seg_stride_c, float out_scale,
                              const float* bias, int act, const float* colscale, const float* R, int ldr,
                              int res_mode, void* split_out, int split_kp, float split_scale, void* stream) {
-  EC_REQUIRE(A2 && B2 && C, "ec_gemm_f16x3: null operand");
+  EC_REQUIRE(A2 && B2 && (C || split_out), "ec_gemm_f16x3: null operand");
   EC_REQUIRE(Kp > 0 && Kp % tc::BK == 0, "ec_gemm_f16x3: Kp must be a positive multiple of 64");
-  EC_REQUIRE(aligned16(A2) && aligned16(B2) && aligned16(C), "ec_gemm_f16x3: operands must be 16-byte aligned");
+  EC_REQUIRE(aligned16(A2) && aligned16(B2), "ec_gemm_f16x3: split operands must be 16-byte aligned");
+  EC_REQUIRE(!split_out || (((uintptr_t)split_out & 7) == 0), "ec_gemm_f16x3: split_out must be 8-byte aligned");
   EC_REQUIRE((res_mode == EC_RES_NONE) == (R == nullptr), "ec_gemm_f16x3: residual pointer/mode mismatch");
   EC_REQUIRE(!split_out || (split_kp % tc::BK == 0 && split_kp >= N), "ec_gemm_f16x3: bad split_kp");
   if (M == 0 || N == 0) return EC_OK;
@@ -385,7 +423,8 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   tc::TcParams p;
   p.C = C; p.M = M; p.N = N; p.num_kb = Kp / tc::BK; p.Kp = Kp; p.ldc = ldc;
   p.seg_c = seg_c; p.seg_stride_c = seg_stride_c;
-  p.vec_c = (ldc % 4 == 0) && (seg_stride_c % 4 == 0);
+  p.vec_c = C && aligned16(C) && (ldc % 4 == 0) && (seg_stride_c % 4 == 0);
+  p.vec_r = R && aligned16(R) && (ldr % 4 == 0);
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
   p.res_mode = res_mode; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
   const int tiles = cdiv(M, tc::BM) * cdiv(N, tc::BN);

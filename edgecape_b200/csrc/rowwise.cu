@@ -1,5 +1,7 @@
 // Row-wise kernels: LayerNorm (+ fused residual), positional adds, row copies, L2 normalisation,
 // mask bookkeeping and the sigmoid-space point update.  One warp per row, shuffle reductions.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ec {
@@ -10,7 +12,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         int ldr, float* __restrict__ sum_out, int ld_sum,
                                                         float* __restrict__ Y, int ldy,
                                                         const float* __restrict__ w,
-                                                        const float* __restrict__ b, float eps, int M, int C) {
+                                                        const float* __restrict__ b, float eps, int M, int C,
+                                                        __half* __restrict__ split_out, int split_kp) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -38,12 +41,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   const float var = warp_sum(q) / (float)C;
   const float rstd = 1.0f / sqrtf(var + eps);
-  float* y = Y + (long long)m * ldy;
+  float* y = Y ? Y + (long long)m * ldy : nullptr;
+  __half* sp = split_out ? split_out + (long long)m * 2 * split_kp : nullptr;
   for (int c = lane; c < C; c += 32) {
     float v = x[c];
     if (r) v += r[c];
-    y[c] = (v - mean) * rstd * w[c] + b[c];
+    const float o = (v - mean) * rstd * w[c] + b[c];
+    if (y) y[c] = o;
+    if (sp) {   // split-fp16 form for the tensor-core GEMM that consumes this row
+      const __half hi = __float2half_rn(o);
+      sp[c] = hi;
+      sp[split_kp + c] = __float2half_rn(o - __half2float(hi));
+    }
   }
+  if (sp)
+    for (int c = C + lane; c < split_kp; c += 32) { sp[c] = __float2half_rn(0.f); sp[split_kp + c] = __float2half_rn(0.f); }
 }
 
 __global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__ P, int T, int S, int C,
@@ -149,13 +161,14 @@ extern "C" int ec_axpby(const float* x, const float* y, float* out, float a, flo
 
 extern "C" int ec_layernorm(const float* X, int ldx, int seg, long long seg_stride, const float* R, int ldr,
                             float* sum_out, int ld_sum, float* Y, int ldy, const float* w, const float* b,
-                            float eps, int M, int C, void* stream) {
-  EC_REQUIRE(X && Y && w && b, "ec_layernorm: null pointer");
+                            float eps, int M, int C, void* split_out, int split_kp, void* stream) {
+  EC_REQUIRE(X && (Y || split_out) && w && b, "ec_layernorm: null pointer");
+  EC_REQUIRE(!split_out || (split_kp >= C && split_kp % 64 == 0), "ec_layernorm: bad split_kp");
   EC_REQUIRE(M >= 0 && C > 0, "ec_layernorm: bad shape");
   if (M == 0) return EC_OK;
   const int warps_per_block = 8;
   layernorm_kernel<<<cdiv(M, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-      X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C);
+      X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, (__half*)split_out, split_kp);
   return check_launch("ec_layernorm");
 }
 

@@ -13,7 +13,59 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .registry import POSENETS, build_head
+from .skeleton import edges_to_csr, edges_to_csr_host
 from .vit import DinoVisionTransformerB200
+
+
+class _GraphedForward:
+    """One captured CUDA graph of EdgeCape._forward_device for a fixed input signature, with static
+    input buffers (images, heat-maps, visibility weights, CSR edge lists up to `edge_capacity`)."""
+
+    def __init__(self, model, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev):
+        mk = lambda t: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
+        self.img_q = mk(img_q)
+        self.img_s = [mk(t) for t in img_s]
+        self.target_s = [mk(t) for t in target_s]
+        self.tw_s = [mk(t) for t in target_weight_s]
+        B = img_q.shape[0]
+        self.edge_capacity = max(1024, 2 * int(e_np.shape[0]))
+        self.edges = torch.zeros(self.edge_capacity, 2, dtype=torch.int32, device=dev)
+        self.offsets = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.host = torch.empty(2 * self.edge_capacity + B + 1, dtype=torch.int32).pin_memory()
+        self.staged = None
+        self._load(img_q, img_s, target_s, target_weight_s, e_np, o_np)
+        # warm-up on a side stream (packs weights, fills caches, sets kernel attributes), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                model._forward_device(self.img_q, self.img_s, self.target_s, self.tw_s, (self.edges, self.offsets))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = model._forward_device(self.img_q, self.img_s, self.target_s, self.tw_s,
+                                             (self.edges, self.offsets))
+
+    def _load(self, img_q, img_s, target_s, target_weight_s, e_np, o_np):
+        if self.staged is not None:
+            self.staged.synchronize()      # the pinned CSR staging buffer is reused: wait for its last H2D
+        self.img_q.copy_(img_q, non_blocking=True)
+        for d, s_ in zip(self.img_s + self.target_s + self.tw_s, list(img_s) + list(target_s) + list(target_weight_s)):
+            d.copy_(s_, non_blocking=True)
+        ne, no = e_np.shape[0], o_np.shape[0]
+        self.host[:no] = torch.from_numpy(o_np)
+        self.host[no:no + 2 * ne] = torch.from_numpy(e_np.reshape(-1))
+        self.offsets.copy_(self.host[:no], non_blocking=True)
+        if ne:
+            self.edges[:ne].view(-1).copy_(self.host[no:no + 2 * ne], non_blocking=True)
+        self.staged = torch.cuda.Event()
+        self.staged.record()
+
+    def run(self, img_q, img_s, target_s, target_weight_s, e_np, o_np):
+        self._load(img_q, img_s, target_s, target_weight_s, e_np, o_np)
+        self.graph.replay()
+        return self.out
 
 
 def _require_cuda(dev):
@@ -33,7 +85,17 @@ class EdgeCape(nn.Module):
         self.train_cfg = train_cfg
         self.test_cfg = test_cfg if test_cfg is not None else {}
         self.target_type = self.test_cfg.get("target_type", "GaussianHeatMap")
+        self.use_cuda_graph = bool(self.test_cfg.get("cuda_graph", True))
+        self._graphs = {}
         self.eval()
+
+    def _apply(self, fn, *a, **k):
+        self._graphs = {}           # captured graphs hold the old parameter addresses
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._graphs = {}           # repacked weight copies (split fp16, fused QKV) change
+        return super().load_state_dict(*a, **k)
 
     @property
     def with_keypoint(self):
@@ -78,14 +140,23 @@ class EdgeCape(nn.Module):
 
     @torch.no_grad()
     def predict(self, img_s, target_s, target_weight_s, img_q, img_metas=None, return_intermediates=False):
-        """(:165-184).  Accepts CPU or CUDA tensors; CPU inputs are uploaded (pinned or pageable)."""
+        """(:165-184).  Accepts CPU or CUDA tensors; CPU inputs are uploaded (pinned or pageable).
+        With `use_cuda_graph` (default; test_cfg['cuda_graph']=False disables) the whole device-side
+        forward of one input signature is captured once into a CUDA graph and replayed, which removes
+        the ~300 per-launch host costs of a step; intermediates are only available eagerly."""
         dev = self.device
         _require_cuda(dev)
-        up =lambda t: t.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-        img_q = up(img_q)
-        img_s = [up(t) for t in img_s]
-        target_s = [up(t) for t in target_s]
-        target_weight_s = [up(t) for t in target_weight_s]
+        skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
+        if self.use_cuda_graph and not return_intermediates and dev.type == "cuda":
+            return self._predict_graphed(img_s, target_s, target_weight_s, img_q, skeleton_lst)
+        up = lambda t: t.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        edges, offsets = edges_to_csr(skeleton_lst, dev)
+        return self._forward_device(up(img_q), [up(t) for t in img_s], [up(t) for t in target_s],
+                                    [up(t) for t in target_weight_s], (edges, offsets), return_intermediates)
+
+    def _forward_device(self, img_q, img_s, target_s, target_weight_s, skeleton, return_intermediates=False):
+        """Device-resident forward: every argument is a CUDA tensor, `skeleton` = (edges, offsets) CSR."""
+        dev = img_q.device
         B, K = target_weight_s[0].shape[:2]
         # mask_s = prod of visibility weights; the first one enters twice (:175-177)
         mask_s = ops.empty(B, K, device=dev)
@@ -93,9 +164,21 @@ class EdgeCape(nn.Module):
         for tw in target_weight_s[1:]:
             ops.mask_accumulate_(tw.reshape(B, K), mask_s, first=False)
         feat_q, feats_s = self.extract_features(img_s, img_q)
-        skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
-        return self.keypoint_head_module.forward_tokens(feat_q, feats_s, target_s, mask_s, skeleton_lst,
+        return self.keypoint_head_module.forward_tokens(feat_q, feats_s, target_s, mask_s, skeleton,
                                                         return_intermediates=return_intermediates)
+
+    # ------------------------------------------------------------------------ CUDA graphs
+    def _predict_graphed(self, img_s, target_s, target_weight_s, img_q, skeleton_lst):
+        dev = self.device
+        e_np, o_np = edges_to_csr_host(skeleton_lst)
+        key = (tuple(img_q.shape), len(img_s), tuple(target_s[0].shape), ops.TENSOR_CORES)
+        g = self._graphs.get(key)
+        if g is None or g.edge_capacity < e_np.shape[0]:
+            g = _GraphedForward(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev)
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            self._graphs[key] = g
+        return g.run(img_q, img_s, target_s, target_weight_s, e_np, o_np)
 
     @torch.no_grad()
     def extract_features(self, img_s, img_q):

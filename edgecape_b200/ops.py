@@ -131,17 +131,21 @@ def split_weight(w):
 
 
 def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
-            split_out=False):
+            split_out=False, fp32_out=True):
     """out = epilogue(A @ B^T) on the tcgen05 tensor cores from two SplitOperands.  `out` may be a
     2-D view or a 3-D [B,S,N] view with B*S == M (batch-strided rows).  With split_out=True also
     returns the SplitOperand of the result (produced by the epilogue)."""
     assert a2.Kp == b2.Kp, f"gemm_tc: padded K differs ({a2.Kp} vs {b2.Kp})"
     M, N = a2.rows, b2.rows
     dev = a2.data.device
-    if out is None:
-        out = empty(M, N, device=dev)
-    Mo, No, ldc, seg_c, seg_stride_c = _seg(out, "out")
-    assert (Mo, No) == (M, N), f"gemm_tc: out {tuple(out.shape)} does not hold {(M, N)}"
+    ldc = seg_c = seg_stride_c = 0
+    if fp32_out:
+        if out is None:
+            out = empty(M, N, device=dev)
+        Mo, No, ldc, seg_c, seg_stride_c = _seg(out, "out")
+        assert (Mo, No) == (M, N), f"gemm_tc: out {tuple(out.shape)} does not hold {(M, N)}"
+    else:
+        assert split_out and out is None, "fp32_out=False only makes sense with split_out=True"
     ldr = 0
     if residual is not None:
         Mr, Nr, ldr, seg_r, _ = _seg(residual, "residual")
@@ -174,7 +178,7 @@ def _tc_ok(x, w, residual):
 
 
 def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
-           split_out=False):
+           split_out=False, fp32_out=True):
     """nn.Linear on the last dimension of a 2-D/3-D view (or an already split A operand); w is [N,K]
     (conv 1x1 weights are reshaped).  Dispatches to the tcgen05 kernel or the fp32 SIMT kernel."""
     if w.dim() > 2:
@@ -183,18 +187,21 @@ def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None
         a2 = x if isinstance(x, SplitOperand) else split_f16(x)
         if out is None and not isinstance(x, SplitOperand) and x.dim() == 3:
             out = empty(x.shape[0], x.shape[1], w.shape[0], device=x.device)
-        res = gemm_tc(a2, split_weight(w), out=out, bias=bias, act=act, colscale=colscale, residual=residual,
-                      res_mode=res_mode, split_out=split_out)
-        return res
+        if not fp32_out:
+            out = None
+        return gemm_tc(a2, split_weight(w), out=out, bias=bias, act=act, colscale=colscale, residual=residual,
+                       res_mode=res_mode, split_out=split_out, fp32_out=fp32_out)
     assert not isinstance(x, SplitOperand), "a split operand needs the tensor-core path"
     y = gemm(x, w, out=out, b_kmajor=True, bias=bias, act=act, colscale=colscale, residual=residual,
              res_mode=res_mode)
     return (y, None) if split_out else y
 
 
-def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None):
+def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None, split="no"):
     """LayerNorm over the last dim of x (+ residual).  A 3-D x view [B,S,C] with a batch stride
-    larger than S*ld (e.g. ViT tokens without the cls row) is read in place."""
+    larger than S*ld (e.g. ViT tokens without the cls row) is read in place.
+    split: "no" -> fp32 result; "also" -> (fp32, SplitOperand); "only" -> SplitOperand (the fp32
+    result is never written: the consumer is a tensor-core GEMM)."""
     _chk(x, "x")
     seg, seg_stride = 0, 0
     if x.dim() == 3:
@@ -207,10 +214,18 @@ def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None):
         M, C = x.shape
         ldx = x.stride(0)
     assert x.stride(-1) == 1
-    if out is None:
-        out = empty(*x.shape, device=x.device)
-    o2 = out.reshape(M, C) if out.is_contiguous() else out
-    assert o2.dim() == 2 and o2.stride(1) == 1
+    o2, ldy = None, 0
+    if split != "only":
+        if out is None:
+            out = empty(*x.shape, device=x.device)
+        o2 = out.reshape(M, C) if out.is_contiguous() else out
+        assert o2.dim() == 2 and o2.stride(1) == 1
+        ldy = o2.stride(0)
+    so, so_ptr, so_kp = None, None, 0
+    if split != "no":
+        so_kp = _kp(C)
+        so = SplitOperand(empty(M, 2 * so_kp, dtype=torch.float16, device=x.device), M, C, so_kp, 1.0)
+        so_ptr = so.data.data_ptr()
     ldr = ld_sum = 0
     if residual is not None:
         _chk(residual, "residual")
@@ -222,8 +237,8 @@ def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None):
         assert s2.dim() == 2 and s2.stride(1) == 1
         sum_out, ld_sum = s2, s2.stride(0)
     _lib.call("ec_layernorm", _p(x), ldx, seg, seg_stride, _p(residual), ldr, _p(sum_out), ld_sum, _p(o2),
-              o2.stride(0), _p(w), _p(b), float(eps), M, C, _stream())
-    return out
+              ldy, _p(w), _p(b), float(eps), M, C, so_ptr, so_kp, _stream())
+    return so if split == "only" else ((out, so) if split == "also" else out)
 
 
 def add_rows_(x, pos, S):
@@ -266,8 +281,9 @@ def axpby(x, y, a=1.0, b=1.0, div=1.0, out=None):
     return out
 
 
-def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None):
-    """q [B,Lq,H*D], k [B,Lk,H*D], v [B,Lk,H*D] views (unit inner stride) -> [B,Lq,H*D]."""
+def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, split="no"):
+    """q [B,Lq,H*D], k [B,Lk,H*D], v [B,Lk,H*D] views (unit inner stride) -> [B,Lq,H*D].
+    split as in layernorm(): "only" returns just the SplitOperand [B*Lq, 2*H*D] of the output."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, n)
         assert t.dim() == 3 and t.stride(2) == 1
@@ -275,9 +291,19 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None):
     Lk = k.shape[1]
     D = E // nheads
     assert k.shape[2] == E and v.shape[2] == E and v.shape[1] == Lk
-    if out is None:
-        out = empty(B, Lq, E, device=q.device)
-    assert out.stride(2) == 1
+    ldo = so_ = 0
+    if split != "only":
+        if out is None:
+            out = empty(B, Lq, E, device=q.device)
+        assert out.stride(2) == 1
+        ldo, so_ = out.stride(1), out.stride(0)
+    else:
+        out = None
+    sp, sp_ptr = None, None
+    if split != "no":
+        assert E % 64 == 0, "split attention output needs H*D to be a multiple of 64"
+        sp = SplitOperand(empty(B * Lq, 2 * E, dtype=torch.float16, device=q.device), B * Lq, E, E, 1.0)
+        sp_ptr = sp.data.data_ptr()
     if scale is None:
         scale = D ** -0.5
     _chk(key_mask, "key_mask", torch.uint8)
@@ -287,9 +313,9 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None):
     if bias is not None:
         assert bias.is_contiguous() and tuple(bias.shape) == (B, nheads, Lq, Lk)
     _lib.call("ec_attention", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
-              v.stride(1), out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale),
-              _p(key_mask), _p(bias), _stream())
-    return out
+              v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale),
+              _p(key_mask), _p(bias), sp_ptr, E if sp is not None else 0, _stream())
+    return sp if split == "only" else ((out, sp) if split == "also" else out)
 
 
 def hop_bias(attn_adj, w0, b0, w1, b1, out=None):

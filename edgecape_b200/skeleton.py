@@ -18,8 +18,8 @@ from .registry import HEADS
 from .transformer import decoder_layer_forward, pack_decoder_layer
 
 
-def edges_to_csr(skeleton, device):
-    """list (batch) of edge lists [[i,j],...] -> (edges int32 [E,2], offsets int32 [B+1]) on `device`.
+def edges_to_csr_host(skeleton):
+    """list (batch) of edge lists [[i,j],...] -> numpy (edges int32 [E,2], offsets int32 [B+1]).
     Ragged / empty lists are fine (the reference skips 1-D edge tensors, skeleton.py:177)."""
     offs = [0]
     flat = []
@@ -30,16 +30,19 @@ def edges_to_csr(skeleton, device):
             offs.append(offs[-1] + flat[-1].shape[0])
         else:
             offs.append(offs[-1])
-    edges = np.concatenate(flat, axis=0) if flat else np.zeros((0, 2), dtype=np.int64)
-    host = torch.from_numpy(np.concatenate((np.asarray(offs, dtype=np.int32),
-                                            edges.astype(np.int32).reshape(-1))))
-    buf = host.to(device, non_blocking=True)          # one small H2D copy
+    edges = np.concatenate(flat, axis=0).astype(np.int32) if flat else np.zeros((0, 2), dtype=np.int32)
+    return np.ascontiguousarray(edges), np.asarray(offs, dtype=np.int32)
+
+
+def edges_to_csr(skeleton, device):
+    """Same, uploaded with one small H2D copy -> (edges int32 [E,2], offsets int32 [B+1]) on `device`."""
+    edges, offs = edges_to_csr_host(skeleton)
+    buf = torch.from_numpy(np.concatenate((offs, edges.reshape(-1)))).to(device, non_blocking=True)
     B = len(skeleton)
-    offsets = buf[:B + 1]
     e = buf[B + 1:]
     if e.numel() == 0:
         e = torch.zeros(2, dtype=torch.int32, device=device)
-    return e, offsets
+    return e, buf[:B + 1]
 
 
 @HEADS.register_module(force=True)
@@ -94,13 +97,13 @@ class SkeletonPredictor(PackedMixin, nn.Module):
 
     @torch.no_grad()
     def forward_tokens(self, skeleton, kp_feat, feats_s, kp_mask, kp_mask_fixed, grid_pos):
-        """skeleton: list (batch) of edge lists; kp_feat [B,K,d]; feats_s: list (shots) of token-major
+        """skeleton: list (batch) of edge lists, or the (edges, offsets) CSR pair already on the device; kp_feat [B,K,d]; feats_s: list (shots) of token-major
         support ViT features [B,S,C] (views are fine); kp_mask / kp_mask_fixed uint8 [B,K];
         grid_pos [S,d].  Returns (adj [B,2,K,K], attn_adj [max_hop+1,B,K,K] or None, unnormalized
         adjacency [B,K,K], refined keypoint features or None)."""
         B, K, d = kp_feat.shape
         dev = kp_feat.device
-        edges, offsets = edges_to_csr(skeleton, dev)
+        edges, offsets = skeleton if isinstance(skeleton, tuple) else edges_to_csr(skeleton, dev)
         gt_adj, binary = ops.adj_from_edges(edges, offsets, kp_mask, K)
         if not self.learn_skeleton:
             return gt_adj, None, binary, None

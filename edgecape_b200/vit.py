@@ -82,20 +82,34 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
                  residual=pos[1:], res_mode=ops.RES_ADD)
         ops.write_cls_(t, self["cls_token"].reshape(-1), pos[0])
         t2 = t.view(Btot * N, C)
-        y = ops.empty(Btot * N, C, device=dev)
         qkv = ops.empty(Btot, N, 3 * C, device=dev)
-        att = ops.empty(Btot, N, C, device=dev)
-        hid = ops.empty(Btot * N, int(C * self.cfg["mlp_ratio"]), device=dev)
-        for i in range(self.depth):
-            blk = getattr(self.blocks, str(i))
-            ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, out=y)
-            ops.linear(y, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
-            ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, out=att)
-            ops.linear(att.view(Btot * N, C), blk.attn.proj.weight, blk.attn.proj.bias, colscale=blk.ls1.gamma,
-                       residual=t2, out=t2)
-            ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, out=y)
-            ops.linear(y, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, out=hid)
-            ops.linear(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, colscale=blk.ls2.gamma, residual=t2, out=t2)
+        if ops.TENSOR_CORES and C % 64 == 0 and Btot * N >= ops.TC_MIN_M:
+            # tensor-core path: every GEMM input is produced directly in split-fp16 form by the kernel
+            # before it (LayerNorm, attention, GELU epilogue); only the residual stream t stays fp32
+            for i in range(self.depth):
+                blk = getattr(self.blocks, str(i))
+                y2 = ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, split="only")
+                ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
+                a2 = ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, split="only")
+                ops.linear(a2, blk.attn.proj.weight, blk.attn.proj.bias, colscale=blk.ls1.gamma, residual=t2, out=t2)
+                y2 = ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, split="only")
+                _, h2 = ops.linear(y2, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, split_out=True,
+                                   fp32_out=False)
+                ops.linear(h2, blk.mlp.fc2.weight, blk.mlp.fc2.bias, colscale=blk.ls2.gamma, residual=t2, out=t2)
+        else:
+            y = ops.empty(Btot * N, C, device=dev)
+            att = ops.empty(Btot, N, C, device=dev)
+            hid = ops.empty(Btot * N, int(C * self.cfg["mlp_ratio"]), device=dev)
+            for i in range(self.depth):
+                blk = getattr(self.blocks, str(i))
+                ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, out=y)
+                ops.linear(y, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
+                ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, out=att)
+                ops.linear(att.view(Btot * N, C), blk.attn.proj.weight, blk.attn.proj.bias, colscale=blk.ls1.gamma,
+                           residual=t2, out=t2)
+                ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, out=y)
+                ops.linear(y, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, out=hid)
+                ops.linear(hid, blk.mlp.fc2.weight, blk.mlp.fc2.bias, colscale=blk.ls2.gamma, residual=t2, out=t2)
         out = ops.empty(Btot, N, C, device=dev)
         ops.layernorm(t2, self["norm.weight"], self["norm.bias"], 1e-6, out=out.view(Btot * N, C))
         return out, (h0, w0)

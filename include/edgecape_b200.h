@@ -86,10 +86,12 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
  * Row m of X lives at X + (m / seg) * seg_stride + (m % seg) * ldx  (seg = 0: plain m * ldx) so a
  * ViT token matrix can be read with its cls row dropped.  If sum_out != NULL the pre-norm sum
  * X+R is stored there (row stride ld_sum).  torch.nn.LayerNorm on the path:
- * encoder_decoder.py:477-482,612-637, ViT norm1/norm2/norm (DINOv2, eps 1e-6). */
+ * encoder_decoder.py:477-482,612-637, ViT norm1/norm2/norm (DINOv2, eps 1e-6).
+ * split_out (optional, fp16 [M, 2*split_kp]) receives the split-fp16 form of the result for a
+ * following ec_gemm_f16x3; Y may then be NULL. */
 int ec_layernorm(const float* X, int ldx, int seg, long long seg_stride, const float* R, int ldr,
                  float* sum_out, int ld_sum, float* Y, int ldy, const float* w, const float* b,
-                 float eps, int M, int C, void* stream);
+                 float eps, int M, int C, void* split_out, int split_kp, void* stream);
 
 /* X[b, t, :] += P[t, :] for t < S (rows S..T-1 untouched): the encoder adds the grid positional
  * encoding to the residual stream every layer (encoder_decoder.py:467). */
@@ -112,11 +114,12 @@ int ec_axpby(const float* x, const float* y, float* out, float a, float b, float
  * (key_padding_mask), may be NULL.  bias: fp32 [B, H, Lq, Lk] or NULL.  D in {16, 32, 64}.
  * Replaces F.multi_head_attention_forward / SDPA (encoder_decoder.py:471-477, 606-631,
  * 638-649), BiasedMultiheadAttention's bmm/softmax/bmm (utils/bias_attn.py:176-222) and the
- * DINOv2 block attention. */
+ * DINOv2 block attention.  split_out (optional, fp16 [B*Lq, 2*split_kp], split_kp == H*D)
+ * receives the split-fp16 form of O for a following ec_gemm_f16x3; O may then be NULL. */
 int ec_attention(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq,
                  int Lk, int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk,
                  long long sv, long long so, float scale, const uint8_t* key_mask,
-                 const float* bias, void* stream);
+                 const float* bias, void* split_out, int split_kp, void* stream);
 
 /* bias[b,h,i,j] = W1 relu(W0 hops[:,b,i,j] + b0) + b1 with hops = attn_adj [n_hops, B, K, K]:
  * the Graphormer-style structural bias MLP (utils/bias_attn.py:82-83,188-191). */

@@ -122,7 +122,8 @@ def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias
     if R:
         r = T(arr(R, (M, N), (ldr, 1)))
         y = (y + 1) * r if res_mode == 2 else r + y
-    _set(rows(C, M, N, ldc, seg_c, seg_stride_c), y.numpy())
+    if C:
+        _set(rows(C, M, N, ldc, seg_c, seg_stride_c), y.numpy())
     if split_out:
         s = y.numpy() * np.float32(split_scale)
         hi = s.astype(np.float16)
@@ -130,14 +131,25 @@ def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias
         out[:, :N], out[:, split_kp:split_kp + N] = hi, (s - hi.astype(np.float32)).astype(np.float16)
 
 
-def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, stream):
+def _write_split(ptr, kp, y):
+    M, N = y.shape
+    hi = y.astype(np.float16)
+    out = arr(ptr, (M, 2 * kp), dtype=np.float16)
+    out[...] = 0
+    out[:, :N], out[:, kp:kp + N] = hi, (y - hi.astype(np.float32)).astype(np.float16)
+
+
+def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, split_out, split_kp, stream):
     x = T(_get(rows(X, M, C, ldx, seg, seg_stride)))
     if R:
         x = x + T(arr(R, (M, C), (ldr, 1)))
     if sum_out:
         arr(sum_out, (M, C), (ld_sum, 1))[...] = x.numpy()
     y = F.layer_norm(x, (C,), T(arr(w, (C,))), T(arr(b, (C,))), eps)
-    arr(Y, (M, C), (ldy, 1))[...] = y.numpy()
+    if Y:
+        arr(Y, (M, C), (ldy, 1))[...] = y.numpy()
+    if split_out:
+        _write_split(split_out, split_kp, y.numpy())
 
 
 def ec_add_rows(X, P, batch, Tt, S, C, stream):
@@ -159,7 +171,8 @@ def ec_axpby(x, y, out, a, b, div, n, stream):
     arr(out, (n,))[...] = v / np.float32(div) if div != 1.0 else v
 
 
-def ec_attention(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, key_mask, bias, stream):
+def ec_attention(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, key_mask, bias, split_out,
+                 split_kp, stream):
     q = T(arr(Q, (B, Lq, H, D), (sq, ldq, D, 1))).transpose(1, 2) * np.float32(scale)
     k = T(arr(K, (B, Lk, H, D), (sk, ldk, D, 1))).transpose(1, 2)
     v = T(arr(V, (B, Lk, H, D), (sv, ldv, D, 1))).transpose(1, 2)
@@ -170,7 +183,10 @@ def ec_attention(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so
         m = T(arr(key_mask, (B, Lk), dtype=np.uint8)).bool()
         s = s.masked_fill(m[:, None, None, :], float("-inf"))
     o = (s.softmax(-1) @ v).transpose(1, 2)
-    arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o.numpy()
+    if O:
+        arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o.numpy()
+    if split_out:
+        _write_split(split_out, split_kp, np.ascontiguousarray(o.numpy()).reshape(B * Lq, H * D))
 
 
 def ec_hop_bias(attn_adj, w0, b0, w1, b1, bias, B, K, n_hops, hidden, H, stream):
