@@ -1,0 +1,357 @@
+// Tensor-core attention for sm_100a (head dim 64, no mask / bias: the DINOv2 block attention and the
+// decoder / skeleton cross-attentions).  One CTA = one (batch, head, 128-query tile):
+//
+//   stage   Q tile and all keys as split-fp16 (hi, lo) tiles in 128B-swizzled shared memory
+//   S       = Q K^T on tcgen05 (q_lo k_hi + q_hi k_lo + q_hi k_hi), fp32, the whole row block [128 x Lk]
+//           stays in TMEM (Lk <= 448 columns) -- no online-softmax rescaling is needed
+//   softmax row max from TMEM (tcgen05.ld, one lane = one row), then per 64-key chunk p = exp(s - max)
+//           is written back to shared memory as split-fp16 P tiles while V^T of the same chunk is staged
+//   O      += P V on tcgen05 (p_lo v_hi + p_hi v_lo + p_hi v_hi) into TMEM; chunks are double buffered so
+//           the exponentials of chunk i+1 overlap the MMAs of chunk i
+//   out     O / rowsum, as fp32 and / or directly in the split-fp16 form the next GEMM consumes.
+//
+// fp32-grade by construction: every operand is represented to 2^-22 and accumulation is fp32.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ec {
+namespace atc {
+
+constexpr int D = 64;
+constexpr int BM = 128;                 // query rows per CTA (UMMA M)
+constexpr int KC = 64;                  // keys per P/V chunk (one 128-byte swizzle span of fp16)
+constexpr int THREADS = 256;
+constexpr int MAX_LKP = 448;            // S columns in TMEM; O uses columns [448, 512)
+constexpr int O_COL = 448;
+constexpr int Q_BYTES = 2 * BM * 128;   // Q_hi + Q_lo
+constexpr int PBUF_BYTES = 2 * BM * 128;      // P_hi + P_lo of one chunk (32 KB)
+constexpr int VBUF_BYTES = 2 * D * 128;       // V_hi^T + V_lo^T of one chunk (16 KB)
+constexpr int REUSE_BYTES = 2 * PBUF_BYTES + 2 * VBUF_BYTES;   // 96 KB, aliases Q and K after S is done
+constexpr int MISC_BYTES = 64 + 4 * BM * 4;   // barriers + tmem slot, row max / row sum exchange
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B, SBO = 1024 B
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {           // f16 x f16 -> f32, M = 128, N = n
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// byte offset of the 16-byte chunk `c` (8 fp16) of row `row` inside a 128B-swizzled K-major tile
+__device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)); }
+
+// 8 fp32 -> 8 hi + 8 lo fp16, packed as two 16-byte vectors
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
+    const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
+    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct Params {
+  const float *Q, *K, *V;
+  float* O;
+  int B, H, Lq, Lk, LKP;
+  int ldq, ldk, ldv, ldo;
+  long long sq, sk, sv, so;
+  float scale;
+  __half* split_out;
+  int split_kp;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int data_bytes = max(Q_BYTES + 2 * p.LKP * 128, REUSE_BYTES);
+  const uint32_t misc = base + data_bytes;
+  const uint32_t bar_s = misc, bar_pv0 = misc + 8, bar_pv1 = misc + 16, tmem_slot = misc + 24;
+  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [2][BM]
+  float* xsum = xmax + 2 * BM;                                        // [2][BM]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_pv0, 1);
+    mbar_init(bar_pv1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+
+  // ------------------------------------------------------------------ stage Q (scaled) and K
+  const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + p.LKP * 128;
+  {
+    const float* Qb = p.Q + (long long)b * p.sq + h * D;
+    for (int it = tid; it < BM * 8; it += THREADS) {
+      const int row = it >> 3, c = it & 7;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (q0 + row < p.Lq) {
+        const float4* src = reinterpret_cast<const float4*>(Qb + (long long)(q0 + row) * p.ldq + c * 8);
+        const float4 a = __ldg(src), bb = __ldg(src + 1);
+        v[0] = a.x * p.scale; v[1] = a.y * p.scale; v[2] = a.z * p.scale; v[3] = a.w * p.scale;
+        v[4] = bb.x * p.scale; v[5] = bb.y * p.scale; v[6] = bb.z * p.scale; v[7] = bb.w * p.scale;
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      const uint32_t off = swz(row, c);
+      *reinterpret_cast<uint4*>(gbase + (q_hi - base) + off) = hi;
+      *reinterpret_cast<uint4*>(gbase + (q_lo - base) + off) = lo;
+    }
+    const float* Kb = p.K + (long long)b * p.sk + h * D;
+    for (int it = tid; it < p.LKP * 8; it += THREADS) {
+      const int row = it >> 3, c = it & 7;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (row < p.Lk) {
+        const float4* src = reinterpret_cast<const float4*>(Kb + (long long)row * p.ldk + c * 8);
+        const float4 a = __ldg(src), bb = __ldg(src + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      const uint32_t off = swz(row, c);
+      *reinterpret_cast<uint4*>(gbase + (k_hi - base) + off) = hi;
+      *reinterpret_cast<uint4*>(gbase + (k_lo - base) + off) = lo;
+    }
+  }
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+
+  // ------------------------------------------------------------------ S = Q K^T  (all keys, into TMEM)
+  if (tid == 0) {
+    int n0 = p.LKP <= 256 ? p.LKP : ((p.LKP / 2 + 15) / 16) * 16;
+    for (int part = 0, noff = 0; noff < p.LKP; ++part, noff += n0) {
+      const int n = min(n0, p.LKP - noff);
+      const uint32_t idesc = make_idesc(n);
+      const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+      const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+    }
+    umma_commit(bar_s);
+  }
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+
+  // ------------------------------------------------------------------ row max (two warps per lane quarter)
+  const int row = quarter * 32 + lane;                 // TMEM lane == row of the query tile
+  const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const int nchunk32 = (p.Lk + 31) / 32;
+  float mymax = -INFINITY;
+  for (int j = half; j < nchunk32; j += 2) {
+    float s[32];
+    tmem_ld32(t_row + j * 32, s);
+#pragma unroll
+    for (int u = 0; u < 32; ++u)
+      if (j * 32 + u < p.Lk) mymax = fmaxf(mymax, s[u]);
+  }
+  xmax[half * BM + row] = mymax;
+  __syncthreads();                                     // also: every warp is done with Q / K shared memory
+  const float rmax = fmaxf(xmax[row], xmax[BM + row]);
+
+  // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
+  const float* Vb = p.V + (long long)b * p.sv + h * D;
+  const int nchunks = (p.Lk + KC - 1) / KC;
+  const uint32_t idesc_o = make_idesc(D);
+  float rsum = 0.f;
+  for (int i = 0; i < nchunks; ++i) {
+    const int buf = i & 1;
+    const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
+    const uint32_t v_hi = base + 2 * PBUF_BYTES + buf * VBUF_BYTES, v_lo = v_hi + D * 128;
+    if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this buffer
+    // V^T of this chunk: tile rows = head-dim index, columns = keys
+    for (int it = tid; it < KC * 8; it += THREADS) {
+      const int kl = it >> 3, dc = it & 7;
+      const int key = i * KC + kl;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (key < p.Lk) {
+        const float4* src = reinterpret_cast<const float4*>(Vb + (long long)key * p.ldv + dc * 8);
+        const float4 a = __ldg(src), bb = __ldg(src + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int drow = dc * 8 + e;
+        const __half hi = __float2half_rn(v[e]);
+        const __half lo = __float2half_rn(v[e] - __half2float(hi));
+        const uint32_t off = swz(drow, kl >> 3) + (kl & 7) * 2;
+        *reinterpret_cast<__half*>(gbase + (v_hi - base) + off) = hi;
+        *reinterpret_cast<__half*>(gbase + (v_lo - base) + off) = lo;
+      }
+    }
+    // P of this chunk: this warp covers keys [i*64 + 32*half, +32) of its 32 rows
+    {
+      float s[32];
+      const int kbase = i * KC + 32 * half;
+      tmem_ld32(t_row + kbase, s);
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const float e = (kbase + u < p.Lk) ? exp2f((s[u] - rmax) * 1.4426950408889634f) : 0.f;
+        s[u] = e;
+        rsum += e;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 hi, lo;
+        split8(s + 8 * j, hi, lo);
+        const uint32_t off = swz(row, 4 * half + j);
+        *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
+        *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
+      }
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const int valid = min(KC, p.Lk - i * KC);
+      const int ksteps = (valid + 15) / 16;
+      const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo), bv_hi = make_desc(v_hi), bv_lo = make_desc(v_lo);
+      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_lo + 2 * k, bv_hi + 2 * k, idesc_o, (i | k) ? 1u : 0u);
+      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_lo + 2 * k, idesc_o, 1u);
+      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_hi + 2 * k, idesc_o, 1u);
+      umma_commit(buf ? bar_pv1 : bar_pv0);
+    }
+  }
+  // drain: the last commit on each buffer
+  {
+    const int c0 = (nchunks + 1) / 2, c1 = nchunks / 2;
+    if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
+    if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
+  }
+  tc_fence_after();
+  xsum[half * BM + row] = rsum;
+  __syncthreads();
+  const float inv = 1.0f / (xsum[row] + xsum[BM + row]);
+
+  // ------------------------------------------------------------------ epilogue: O / rowsum
+  {
+    float o[32];
+    tmem_ld32(t_row + O_COL + 32 * half, o);
+    const int grow = q0 + row;
+    if (grow < p.Lq) {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) o[u] *= inv;
+      if (p.O) {
+        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + 32 * half);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+      }
+      if (p.split_out) {
+        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + 32 * half;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 hi, lo;
+          split8(o + 8 * j, hi, lo);
+          *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
+          *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace atc
+}  // namespace ec
+
+using namespace ec;
+
+extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq, int Lk,
+                               int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk, long long sv,
+                               long long so, float scale, void* split_out, int split_kp, void* stream) {
+  EC_REQUIRE(Q && K && V && (O || split_out), "ec_attention_tc: null pointer");
+  EC_REQUIRE(D == atc::D, "ec_attention_tc: head dim must be 64");
+  EC_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, "ec_attention_tc: bad shape");
+  const int LKP = (Lk + 15) / 16 * 16;
+  if (LKP > atc::MAX_LKP) {
+    set_error("ec_attention_tc: %d keys exceed the %d S columns that fit in TMEM", Lk, atc::MAX_LKP);
+    return EC_ERR_UNSUPPORTED;
+  }
+  EC_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && (!O || aligned16(O)) && ldq % 4 == 0 && ldk % 4 == 0 &&
+                 ldv % 4 == 0 && ldo % 4 == 0 && sq % 4 == 0 && sk % 4 == 0 && sv % 4 == 0 && so % 4 == 0,
+             "ec_attention_tc: operands must be 16-byte aligned with strides that are multiples of 4");
+  EC_REQUIRE(!split_out || (split_kp == H * D && (((uintptr_t)split_out) & 15) == 0),
+             "ec_attention_tc: split_out needs split_kp == H*D and 16-byte alignment");
+  if (B == 0 || Lq == 0) return EC_OK;
+  EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc: grid too large");
+  const int data_bytes = atc::Q_BYTES + 2 * LKP * 128 > atc::REUSE_BYTES ? atc::Q_BYTES + 2 * LKP * 128 : atc::REUSE_BYTES;
+  const int smem = data_bytes + atc::MISC_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 atc::Q_BYTES + 2 * atc::MAX_LKP * 128 + atc::MISC_BYTES + 1024));
+    attr_set = true;
+  }
+  atc::Params p{Q, K, V, O, B, H, Lq, Lk, LKP, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, (__half*)split_out, split_kp};
+  dim3 grid(cdiv(Lq, atc::BM), H, B);
+  atc::attention_tc_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("ec_attention_tc");
+}

@@ -84,6 +84,7 @@ def gemm(a, b, out=None, b_kmajor=True, bias=None, act=ACT_NONE, colscale=None, 
 # EDGECAPE_TC=0 routes every linear through the fp32 SIMT GEMM (bit-faithful FFMA reference path);
 # the default uses the split-fp16 tcgen05 GEMM wherever the shape fills a 128x128 tile reasonably.
 TENSOR_CORES = os.environ.get("EDGECAPE_TC", "1") != "0"
+ATTENTION_TC = os.environ.get("EDGECAPE_ATTN_TC", "1") != "0"     # tcgen05 attention for head dim 64
 TC_MIN_M, TC_MIN_N, TC_MIN_K = 64, 32, 32
 _SPLIT_WEIGHTS = {}
 
@@ -312,6 +313,11 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, s
         assert key_mask.is_contiguous() and tuple(key_mask.shape) == (B, Lk)
     if bias is not None:
         assert bias.is_contiguous() and tuple(bias.shape) == (B, nheads, Lq, Lk)
+    if TENSOR_CORES and ATTENTION_TC and D == 64 and key_mask is None and bias is None and Lk <= 448:
+        _lib.call("ec_attention_tc", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
+                  v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale), sp_ptr,
+                  E if sp is not None else 0, _stream())
+        return sp if split == "only" else ((out, sp) if split == "also" else out)
     _lib.call("ec_attention", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
               v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale),
               _p(key_mask), _p(bias), sp_ptr, E if sp is not None else 0, _stream())

@@ -121,6 +121,16 @@ int ec_attention(const float* Q, const float* K, const float* V, float* O, int B
                  long long sv, long long so, float scale, const uint8_t* key_mask,
                  const float* bias, void* split_out, int split_kp, void* stream);
 
+/* Tensor-core attention (tcgen05, sm_100a): same contract as ec_attention without key_mask / bias,
+ * head dim 64, Lk <= 448 (the whole [128 x Lk] score block lives in TMEM).  Q, K, V, P are split into
+ * fp16 (hi, lo) pairs in shared memory and both contractions run as 3-product UMMAs with fp32 TMEM
+ * accumulation (fp32-grade results).  Used for the DINOv2 block attention and the 8 x 64 cross
+ * attentions (encoder_decoder.py:620-631, 638-649). */
+int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq,
+                    int Lk, int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk,
+                    long long sv, long long so, float scale, void* split_out, int split_kp,
+                    void* stream);
+
 /* bias[b,h,i,j] = W1 relu(W0 hops[:,b,i,j] + b0) + b1 with hops = attn_adj [n_hops, B, K, K]:
  * the Graphormer-style structural bias MLP (utils/bias_attn.py:82-83,188-191). */
 int ec_hop_bias(const float* attn_adj, const float* w0, const float* b0, const float* w1,

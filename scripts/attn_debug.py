@@ -1,0 +1,70 @@
+"""Stand-alone bring-up of the tcgen05 attention kernel (run on the GPU box under a timeout per stage)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from edgecape_b200 import ops  # noqa: E402
+
+
+def check(B, H, Lq, Lk, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    E = H * 64
+    q, k, v = (torch.randn(B, L, E, generator=g) for L in (Lq, Lk, Lk))
+    qh = q.double().view(B, Lq, H, 64).transpose(1, 2) / 8.0
+    kh = k.double().view(B, Lk, H, 64).transpose(1, 2)
+    vh = v.double().view(B, Lk, H, 64).transpose(1, 2)
+    want = ((qh @ kh.transpose(-1, -2)).softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    D = torch.device("cuda")
+    ops.TENSOR_CORES, ops.ATTENTION_TC = True, True
+    got = ops.attention(q.to(D), k.to(D), v.to(D), H).cpu()
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    print(f"attn_tc B{B} H{H} Lq{Lq} Lk{Lk}: rel err {err:.3e} nan={torch.isnan(got).any().item()} "
+          f"got[0,0,:3]={got[0, 0, :3].tolist()} want={want[0, 0, :3].tolist()}", flush=True)
+    if err > 1e-3:
+        # is it plain averaging (softmax broken) or permuted rows?
+        mean_v = v.view(B, Lk, H, 64).mean(1)[0].reshape(-1)[:3]
+        print("   mean of V[0,:,0:3] =", mean_v.tolist())
+        for r in (0, 1, 8, 31, 32, 64, 127):
+            if r < Lq:
+                best = (want[0] - got[0, r][None]).abs().sum(1).argmin().item()
+                print(f"   got row {r} closest to want row {best}")
+    return err
+
+
+def bench(B, H, L, iters=20):
+    D = torch.device("cuda")
+    C = H * 64
+    qkv = torch.randn(B, L, 3 * C, device=D)
+    out = torch.empty(B, L, C, device=D)
+    for tc in (True, False):
+        ops.ATTENTION_TC = tc
+        for _ in range(3):
+            ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, out=out)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, out=out)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / iters
+        fl = 4.0 * B * H * L * L * 64
+        print(f"bench attention B{B} H{H} L{L} {'tcgen05' if tc else 'simt'}: {ms:.3f} ms = {fl / ms / 1e9:.1f} algorithmic TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    st = sys.argv[1]
+    if st == "tiny":
+        check(1, 1, 128, 64)
+    elif st == "two":
+        check(1, 2, 128, 128)
+        check(1, 1, 100, 17)
+    elif st == "vit":
+        check(2, 12, 325, 325)
+        check(1, 8, 100, 324)
+        check(1, 8, 324, 100)
+        check(1, 4, 130, 448)
+    elif st == "bench":
+        bench(32, 12, 325)
+        bench(32, 16, 257)

@@ -1,0 +1,14 @@
+#!/bin/bash
+# pass D: tcgen05 attention bring-up, then the whole suite + bench
+mkdir -p gpurun_out
+for st in tiny two vit bench; do
+  timeout -s KILL 120 python scripts/attn_debug.py $st > gpurun_out/attn_$st.log 2>&1
+  echo "stage $st exit $?" >> gpurun_out/attn_$st.log
+  tail -12 gpurun_out/attn_$st.log
+done
+timeout -s KILL 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
+timeout -s KILL 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1
+echo "bench exit $?" >> gpurun_out/bench.log
+tail -3 gpurun_out/bench.log

@@ -189,6 +189,29 @@ def ec_attention(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so
         _write_split(split_out, split_kp, np.ascontiguousarray(o.numpy()).reshape(B * Lq, H * D))
 
 
+def _h2(x):
+    hi = x.astype(np.float16).astype(np.float32)
+    return hi, (x - hi).astype(np.float16).astype(np.float32)
+
+
+def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, split_out, split_kp, stream):
+    assert D == 64 and Lk <= 448
+    q = np.ascontiguousarray(arr(Q, (B, Lq, H, D), (sq, ldq, D, 1)).transpose(0, 2, 1, 3)) * np.float32(scale)
+    k = np.ascontiguousarray(arr(K, (B, Lk, H, D), (sk, ldk, D, 1)).transpose(0, 2, 1, 3))
+    v = np.ascontiguousarray(arr(V, (B, Lk, H, D), (sv, ldv, D, 1)).transpose(0, 2, 1, 3))
+    (qh, ql), (kh, kl), (vh, vl) = _h2(q), _h2(k), _h2(v)
+    kt = lambda a: a.transpose(0, 1, 3, 2)
+    s = ql @ kt(kh) + qh @ kt(kl) + qh @ kt(kh)
+    p = np.exp2((s - s.max(-1, keepdims=True)) * np.float32(1.4426950408889634)).astype(np.float32)
+    ph, pl = _h2(p)
+    o = (pl @ vh + ph @ vl + ph @ vh) / p.sum(-1, keepdims=True)
+    o = np.ascontiguousarray(o.transpose(0, 2, 1, 3)).astype(np.float32)
+    if O:
+        arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o
+    if split_out:
+        _write_split(split_out, split_kp, o.reshape(B * Lq, H * D))
+
+
 def ec_hop_bias(attn_adj, w0, b0, w1, b1, bias, B, K, n_hops, hidden, H, stream):
     hops = T(arr(attn_adj, (n_hops, B, K, K))).permute(1, 2, 3, 0)
     y = F.linear(F.relu(F.linear(hops, T(arr(w0, (hidden, n_hops))), T(arr(b0, (hidden,))))),

@@ -434,6 +434,43 @@ def test_fused_split_outputs_of_layernorm_attention_and_gemm():
     close(got, F.linear(F.gelu(F.linear(want, w1, b1)), w2), tol=2e-5, what="chained tc")
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 12, 325, 325), (3, 8, 100, 324), (1, 8, 324, 100), (2, 2, 128, 64),
+                                       (1, 1, 5, 17), (2, 16, 130, 448), (1, 6, 257, 257)])
+def test_attention_tc_matches_fp32_attention(B, H, Lq, Lk, monkeypatch):
+    D_, E = 64, H * 64
+    q, k, v = rnd(B, Lq, E, seed=1), rnd(B, Lk, E, seed=2), rnd(B, Lk, E, seed=3, scale=2.0)
+    qh = q.double().view(B, Lq, H, D_).transpose(1, 2) * D_ ** -0.5
+    kh = k.double().view(B, Lk, H, D_).transpose(1, 2)
+    vh = v.double().view(B, Lk, H, D_).transpose(1, 2)
+    want = ((qh @ kh.transpose(-1, -2)).softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    D = dev()
+    monkeypatch.setattr(ops, "TENSOR_CORES", True)
+    monkeypatch.setattr(ops, "ATTENTION_TC", True)
+    names = []
+    from edgecape_b200 import _lib
+    orig = _lib.call
+    monkeypatch.setattr(_lib, "call", lambda n, *a: (names.append(n), orig(n, *a))[1])
+    got, sp = ops.attention(q.to(D), k.to(D), v.to(D), H, split="also")
+    assert names[-1] == "ec_attention_tc"
+    close(got, want, tol=5e-6, what=f"attention_tc {B},{H},{Lq},{Lk}")
+    close(sp.data[:, :E].float() + sp.data[:, E:].float(), want.reshape(B * Lq, E), tol=5e-6, what="attention_tc split")
+    monkeypatch.setattr(ops, "ATTENTION_TC", False)
+    ref = ops.attention(q.to(D), k.to(D), v.to(D), H)
+    assert names[-1] == "ec_attention"
+    close(got, ref, tol=5e-6, what="tc vs simt attention")
+
+
+def test_attention_tc_on_packed_qkv_views(monkeypatch):
+    monkeypatch.setattr(ops, "TENSOR_CORES", True)
+    monkeypatch.setattr(ops, "ATTENTION_TC", True)
+    B, N, H, C = 4, 325, 12, 768
+    qkv = rnd(B, N, 3 * C, seed=5).to(dev())
+    got = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
+    monkeypatch.setattr(ops, "ATTENTION_TC", False)
+    ref = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
+    close(got, ref, tol=5e-6, what="packed qkv")
+
+
 def test_linear_dispatch_uses_tensor_cores_and_matches_simt(monkeypatch):
     from edgecape_b200 import _lib
     x, w, b = rnd(3, 324, 768, seed=1), rnd(256, 768, seed=2, scale=0.03), rnd(256, seed=3)
