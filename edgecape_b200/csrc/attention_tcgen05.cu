@@ -155,19 +155,33 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
       *reinterpret_cast<uint4*>(gbase + (q_lo - base) + off) = lo;
     }
     const float* Kb = p.K + (long long)b * p.sk + h * D;
-    for (int it = tid; it < p.LKP * 8; it += THREADS) {
-      const int row = it >> 3, c = it & 7;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (row < p.Lk) {
-        const float4* src = reinterpret_cast<const float4*>(Kb + (long long)row * p.ldk + c * 8);
-        const float4 a = __ldg(src), bb = __ldg(src + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+    // 4 items (= 8 float4 loads) in flight per thread before any conversion: hides the global latency
+    for (int it0 = tid; it0 < p.LKP * 8; it0 += 4 * THREADS) {
+      float4 ra[4], rb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * THREADS;
+        const int row = it >> 3, c = it & 7;
+        ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[u] = ra[u];
+        if (it < p.LKP * 8 && row < p.Lk) {
+          const float4* src = reinterpret_cast<const float4*>(Kb + (long long)row * p.ldk + c * 8);
+          ra[u] = __ldg(src);
+          rb[u] = __ldg(src + 1);
+        }
       }
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      const uint32_t off = swz(row, c);
-      *reinterpret_cast<uint4*>(gbase + (k_hi - base) + off) = hi;
-      *reinterpret_cast<uint4*>(gbase + (k_lo - base) + off) = lo;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * THREADS;
+        if (it >= p.LKP * 8) continue;
+        const int row = it >> 3, c = it & 7;
+        const float v[8] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w, rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const uint32_t off = swz(row, c);
+        *reinterpret_cast<uint4*>(gbase + (k_hi - base) + off) = hi;
+        *reinterpret_cast<uint4*>(gbase + (k_lo - base) + off) = lo;
+      }
     }
   }
   proxy_fence();
@@ -217,21 +231,35 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   const int nchunks = (p.Lk + KC - 1) / KC;
   const uint32_t idesc_o = make_idesc(D);
   float rsum = 0.f;
+  float4 va[2], vb[2];                                   // V rows of the next chunk (2 items of 8 floats per thread)
+  auto load_v = [&](int chunk) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int it = tid + w * THREADS;
+      const int kl = it >> 3, dc = it & 7;
+      const int key = chunk * KC + kl;
+      va[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[w] = va[w];
+      if (key < p.Lk) {
+        const float4* src = reinterpret_cast<const float4*>(Vb + (long long)key * p.ldv + dc * 8);
+        va[w] = __ldg(src);
+        vb[w] = __ldg(src + 1);
+      }
+    }
+  };
+  load_v(0);
   for (int i = 0; i < nchunks; ++i) {
     const int buf = i & 1;
     const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
     const uint32_t v_hi = base + 2 * PBUF_BYTES + buf * VBUF_BYTES, v_lo = v_hi + D * 128;
     if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this buffer
-    // V^T of this chunk: tile rows = head-dim index, columns = keys
-    for (int it = tid; it < KC * 8; it += THREADS) {
+    // V^T of this chunk (tile rows = head-dim index, columns = keys) from the registers prefetched one
+    // iteration ago; then the loads of the next chunk are issued so they overlap the exponentials below
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int it = tid + w * THREADS;
       const int kl = it >> 3, dc = it & 7;
-      const int key = i * KC + kl;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (key < p.Lk) {
-        const float4* src = reinterpret_cast<const float4*>(Vb + (long long)key * p.ldv + dc * 8);
-        const float4 a = __ldg(src), bb = __ldg(src + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
-      }
+      const float v[8] = {va[w].x, va[w].y, va[w].z, va[w].w, vb[w].x, vb[w].y, vb[w].z, vb[w].w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int drow = dc * 8 + e;
@@ -242,6 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
         *reinterpret_cast<__half*>(gbase + (v_lo - base) + off) = lo;
       }
     }
+    load_v(i + 1);
     // P of this chunk: this warp covers keys [i*64 + 32*half, +32) of its 32 rows
     {
       float s[32];

@@ -20,16 +20,24 @@
 namespace ec {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64;           // fp16 elements; BK * 2 B = 128 B = one swizzle row
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 2;               // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int BM = 128, BK = 64;                     // fp16 elements; BK * 2 B = 128 B = one swizzle row
+constexpr int TILE_BYTES = BM * BK * 2;               // one 128-row operand tile: 16 KB
+// Two tile shapes: 128x128 (3 stages of 64 KB) and 128x256 (2 stages of 96 KB).  The main loop is bound by
+// L2->SM operand traffic (profiles/r01_c): the wide tile moves 62.5 B per MMA-cycle per SM instead of 85.
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 128 ? 3 : 2;
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr int TMEM_COLS = 2 * BN;                                // two fp32 accumulator stages
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 constexpr int NUM_ACC = 2;
-constexpr int TMEM_COLS = NUM_ACC * BN;               // 256 fp32 columns
 constexpr int THREADS = 192;
 constexpr int EPI_LD = 36;                           // staging row stride (floats)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;       // one 32 x 32 staging tile per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+template <int BN> constexpr int smem_bytes() {
+  return Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,15 +81,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = BN.
-constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor (Cfg<BN>::IDESC): D = f32, A = B = f16, both K-major, M = 128, N = BN.
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -115,8 +123,12 @@ struct TcParams {
   float split_scale;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, B_TILE_BYTES = Cfg<BN>::B_TILE_BYTES;
+  constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  constexpr uint32_t IDESC = Cfg<BN>::IDESC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -161,7 +173,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_2d(sb + 0 * TILE_BYTES, &tmA, full_bar(stage), kb * BK, m0);
           tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
           tma_load_2d(sb + 2 * TILE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
-          tma_load_2d(sb + 3 * TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
+          tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -182,14 +194,15 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t sb = base + stage * STAGE_BYTES;
           const uint64_t a_hi = make_smem_desc(sb + 0 * TILE_BYTES), a_lo = make_smem_desc(sb + 1 * TILE_BYTES);
-          const uint64_t b_hi = make_smem_desc(sb + 2 * TILE_BYTES), b_lo = make_smem_desc(sb + 3 * TILE_BYTES);
+          const uint64_t b_hi = make_smem_desc(sb + 2 * TILE_BYTES);
+          const uint64_t b_lo = make_smem_desc(sb + 2 * TILE_BYTES + B_TILE_BYTES);
           // small terms first, then hi*hi
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, IDESC, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, 1u);
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, IDESC, 1u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, 1u);
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, 1u);
           umma_commit(empty_bar(stage));           // frees the smem stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -337,20 +350,21 @@ static EncodeTiledFn get_encode() {
 
 struct MapKey {
   const void* ptr;
-  int rows, kp;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kp == o.kp; }
+  int rows, kp, box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kp == o.kp && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.kp) * 7919u);
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.kp) * 7919u) ^
+           (std::hash<int>()(k.box_rows) * 104729u);
   }
 };
 
-static int get_tensor_map(const void* ptr, int rows, int kp, CUtensorMap* out) {
+static int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   std::lock_guard<std::mutex> lock(mu);
-  MapKey key{ptr, rows, kp};
+  MapKey key{ptr, rows, kp, box_rows};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -363,7 +377,7 @@ static int get_tensor_map(const void* ptr, int rows, int kp, CUtensorMap* out) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)(2 * kp), (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(2 * kp) * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -383,6 +397,13 @@ static int get_tensor_map(const void* ptr, int rows, int kp, CUtensorMap* out) {
 }  // namespace ec
 
 using namespace ec;
+
+static int ec_tc_force_bn = 0;   // 0 = heuristic; 128 / 256 force a tile width (tuning / tests)
+extern "C" int ec_tc_set_tile_n(int bn) {
+  EC_REQUIRE(bn == 0 || bn == 128 || bn == 256, "ec_tc_set_tile_n: 0, 128 or 256");
+  ec_tc_force_bn = bn;
+  return EC_OK;
+}
 
 extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int seg, long long seg_stride, int Kp,
                             float scale, void* stream) {
@@ -412,13 +433,20 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
     int dev = 0;
     EC_CUDA(cudaGetDevice(&dev));
     EC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc::smem_bytes<128>()));
+    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc::smem_bytes<256>()));
     attr_set = true;
   }
+  // wide tiles when they still give every SM at least ~1.5 tiles and N fills them
+  const long long tiles256 = (long long)cdiv(M, tc::BM) * cdiv(N, 256);
+  const bool wide = ec_tc_force_bn == 256 || (ec_tc_force_bn == 0 && N % 256 == 0 && tiles256 * 2 >= 3LL * num_sms);
+  const int BN = wide ? 256 : 128;
   CUtensorMap tmA, tmB;
-  int rc = tc::get_tensor_map(A2, M, Kp, &tmA);
+  int rc = tc::get_tensor_map(A2, M, Kp, tc::BM, &tmA);
   if (rc) return rc;
-  rc = tc::get_tensor_map(B2, N, Kp, &tmB);
+  rc = tc::get_tensor_map(B2, N, Kp, BN, &tmB);
   if (rc) return rc;
   tc::TcParams p;
   p.C = C; p.M = M; p.N = N; p.num_kb = Kp / tc::BK; p.Kp = Kp; p.ldc = ldc;
@@ -427,8 +455,11 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.vec_r = R && aligned16(R) && (ldr % 4 == 0);
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
   p.res_mode = res_mode; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
-  const int tiles = cdiv(M, tc::BM) * cdiv(N, tc::BN);
+  const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  tc::gemm_f16x3_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  if (wide)
+    tc::gemm_f16x3_kernel<256><<<grid, tc::THREADS, tc::smem_bytes<256>(), (cudaStream_t)stream>>>(tmA, tmB, p);
+  else
+    tc::gemm_f16x3_kernel<128><<<grid, tc::THREADS, tc::smem_bytes<128>(), (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("ec_gemm_f16x3");
 }

@@ -81,6 +81,10 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
                   const float* R, int ldr, int res_mode, void* split_out, int split_kp,
                   float split_scale, void* stream);
 
+/* tuning knob for ec_gemm_f16x3: 0 = pick the tile width per shape (128x256 tiles for wide, large
+ * problems, 128x128 otherwise), 128 / 256 = force it. */
+int ec_tc_set_tile_n(int bn);
+
 /* ------------------------------------------------------------------------- normalisation
  * Y[m,:] = LayerNorm(X[m,:] (+ R[m,:])) * w + b  (biased variance, eps inside the sqrt).
  * Row m of X lives at X + (m / seg) * seg_stride + (m % seg) * ldx  (seg = 0: plain m * ldx) so a

@@ -65,10 +65,23 @@ if __name__ == "__main__":
     elif stage == "k2":
         check(128, 128, 256)
     elif stage == "multi":
-        check(512, 384, 768)
-        check(1300, 768, 768)
-        check(200, 96, 100)
+        from edgecape_b200 import _lib
+        for bn in (128, 256):
+            _lib.load().ec_tc_set_tile_n(bn)
+            print("tile width", bn)
+            check(512, 384, 768)
+            check(1300, 768, 768)
+            check(200, 96, 100)
+            check(650, 3072, 768)
     elif stage == "bench":
+        from edgecape_b200 import _lib
+        for bn in (128, 256):
+            _lib.load().ec_tc_set_tile_n(bn)
+            print("tile width", bn)
+            for shp in [(10400, 2304, 768), (10400, 768, 768), (10400, 3072, 768), (10400, 768, 3072)]:
+                bench(*shp)
+        _lib.load().ec_tc_set_tile_n(0)
+        print("tile width: heuristic")
         for shp in [(10400, 2304, 768), (10400, 768, 768), (10400, 3072, 768), (10400, 768, 3072), (5184, 256, 768),
                     (1600, 256, 256)]:
             bench(*shp)

@@ -366,7 +366,11 @@ def test_split_f16_reconstructs_fp32():
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (128, 256, 192), (1300, 768, 768),
                                    (200, 96, 100), (5184, 256, 768), (650, 3072, 768), (650, 768, 3072), (77, 33, 516)])
-def test_gemm_tc_fp32_grade(M, N, K):
+@pytest.mark.parametrize("tile_n", [128, 256])
+def test_gemm_tc_fp32_grade(M, N, K, tile_n, request):
+    from edgecape_b200 import _lib
+    _lib.load().ec_tc_set_tile_n(tile_n)
+    request.addfinalizer(lambda: _lib.load().ec_tc_set_tile_n(0))
     x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.02), rnd(N, seed=3)
     want = (x.double() @ w.double().T + b.double())
     D = dev()
