@@ -56,13 +56,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// erff / tanhf expand to ~50-100 instructions each: kept out of line so that heavily unrolled epilogues
+// (32+ call sites per loop body) stay inside the instruction cache
+__device__ __noinline__ float apply_act_transcendental(float x, int act) {
+  return act == EC_ACT_GELU ? gelu_erf(x) : tanhf(x);
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case EC_ACT_RELU: return fmaxf(x, 0.0f);
-    case EC_ACT_GELU: return gelu_erf(x);
-    case EC_ACT_TANH: return tanhf(x);
-    default: return x;
-  }
+  if (act == EC_ACT_NONE) return x;
+  if (act == EC_ACT_RELU) return fmaxf(x, 0.0f);
+  return apply_act_transcendental(x, act);
 }
 
 }  // namespace ec

@@ -22,22 +22,14 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64;                     // fp16 elements; BK * 2 B = 128 B = one swizzle row
 constexpr int TILE_BYTES = BM * BK * 2;               // one 128-row operand tile: 16 KB
-// Two tile shapes: 128x128 (3 stages of 64 KB) and 128x256 (2 stages of 96 KB).  The main loop is bound by
-// L2->SM operand traffic (profiles/r01_c): the wide tile moves 62.5 B per MMA-cycle per SM instead of 85.
-template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 128 ? 3 : 2;
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
-  static constexpr int TMEM_COLS = 2 * BN;                                // two fp32 accumulator stages
-  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-};
+// Tile shapes: 128x128 (3 stages of 64 KB), 128x256 (2 stages of 96 KB) on one CTA, and 256x256 on a CTA pair
+// (cta_group::2, 3 stages of 64 KB per CTA).  The main loop is bound by how many operand bytes can be in flight
+// in shared memory per unit of math (profiles/r01_d): the pair tile feeds twice the math per staged byte.
 constexpr int NUM_ACC = 2;
 constexpr int THREADS = 192;
 constexpr int EPI_LD = 36;                           // staging row stride (floats)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;       // one 32 x 32 staging tile per epilogue warp
-template <int BN> constexpr int smem_bytes() {
-  return Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
-}
+constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;   // all variants
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -113,6 +105,7 @@ struct TcParams {
   int M, N, num_kb, Kp, ldc, seg_c;
   long long seg_stride_c;
   int vec_c, vec_r;
+  int dbg;   // experiment flags (ec_tc_set_debug): 1 = no TMA after the pipeline is primed, 2 = hi*hi only, 4 = no epilogue stores
   float out_scale;
   const float* bias;
   const float* colscale;
@@ -123,12 +116,61 @@ struct TcParams {
   float split_scale;
 };
 
-template <int BN>
+// ---- cluster / 2-CTA helpers (cta_group::2: one UMMA spans the tensor cores and shared memory of an SM pair)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  __syncwarp();   // .aligned: the whole warp must arrive together (role lanes re-converge here)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+// TWO = false: one CTA per 128 x BN tile (cta_group::1).
+// TWO = true : a cluster of two CTAs per 256 x 256 tile (cta_group::2, BN must be 256): each CTA stages its own
+//              128 rows of A and 128 rows of B (64 KB per k-block, 3 stages), the leader issues M = 256 UMMAs that
+//              read both CTAs' shared memory, so every staged byte feeds twice the math of the single-CTA tile.
+template <int BN, bool TWO>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, B_TILE_BYTES = Cfg<BN>::B_TILE_BYTES;
-  constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
-  constexpr uint32_t IDESC = Cfg<BN>::IDESC;
+  constexpr int B_ROWS = TWO ? BN / 2 : BN;                      // B rows staged by one CTA
+  constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
+  constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int STAGES = STAGE_BYTES <= 64 * 1024 ? 3 : 2;
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int TM = TWO ? 2 * BM : BM;                           // rows of the (pair) tile
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  static_assert(!TWO || BN == 256, "the 2-CTA kernel uses 256 x 256 tiles");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -142,49 +184,72 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int rank = TWO ? (int)cluster_ctarank() : 0;              // 0 = leader of the pair
+  const int worker = TWO ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int num_workers = TWO ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int m_tiles = (p.M + TM - 1) / TM, n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync(); else __syncthreads();                  // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m0 = (tile % m_tiles) * TM + rank * BM, n0 = (tile / m_tiles) * BN + rank * B_ROWS;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sb = base + stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sb + 0 * TILE_BYTES, &tmA, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
-          tma_load_2d(sb + 2 * TILE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
-          tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
+          if (!TWO && (p.dbg & 1) && (tile != worker || kb >= STAGES)) {   // experiment: operands stay resident
+            mbar_arrive(full_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (TWO) {
+            // both CTAs' bytes are accounted on the leader's barrier: it expects 2 x STAGE_BYTES
+            const uint32_t lbar = mapa(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            tma_load_2d_2sm(sb + 0 * TILE_BYTES, &tmA, lbar, kb * BK, m0);
+            tma_load_2d_2sm(sb + 1 * TILE_BYTES, &tmA, lbar, p.Kp + kb * BK, m0);
+            tma_load_2d_2sm(sb + 2 * TILE_BYTES, &tmB, lbar, kb * BK, n0);
+            tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, lbar, p.Kp + kb * BK, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sb + 0 * TILE_BYTES, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
+            tma_load_2d(sb + 2 * TILE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+            tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // -------------------------------------------------------------------- MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
         const int acc = t & 1;
         mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -197,16 +262,29 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t b_hi = make_smem_desc(sb + 2 * TILE_BYTES);
           const uint64_t b_lo = make_smem_desc(sb + 2 * TILE_BYTES + B_TILE_BYTES);
           // small terms first, then hi*hi
+          if (TWO) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(tmem_d, a_lo + 2 * k, b_hi + 2 * k, IDESC, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, IDESC, 1u);
+            for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(tmem_d, a_hi + 2 * k, b_lo + 2 * k, IDESC, 1u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, 1u);
-          umma_commit(empty_bar(stage));           // frees the smem stage when these MMAs retire
+            for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, 1u);
+            umma_commit_2sm(empty_bar(stage));       // frees the stage in both CTAs when these MMAs retire
+          } else {
+            if (!(p.dbg & 2)) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, IDESC, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, ((p.dbg & 2) && !(kb | k)) ? 0u : 1u);
+            umma_commit(empty_bar(stage));           // frees the smem stage when these MMAs retire
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));               // accumulator complete -> epilogue
+        if (TWO) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
       }
     }
   } else {
@@ -218,9 +296,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
     const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    const uint32_t tempty_leader0 = TWO ? mapa(tempty_bar(0), 0) : 0u, tempty_leader1 = TWO ? mapa(tempty_bar(1), 0) : 0u;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
       const int acc = t & 1;
-      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      const int m0 = (tile % m_tiles) * TM + rank * BM, n0 = (tile / m_tiles) * BN;
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -231,7 +310,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // accumulator fully drained into registers: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (TWO) mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);   // the leader's MMA thread waits for 8 warps
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -272,7 +354,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 4; ++u) y[u] = (p.res_mode == EC_RES_GATE) ? (y[u] + 1.0f) * rr[u] : rr[u] + y[u];
             }
-            if (p.C) {
+            if (p.C && !(p.dbg & 4)) {
               float* cp = (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
                                        : p.C + (long long)row * p.ldc) + gcol;
               if (full && p.vec_c) {
@@ -306,9 +388,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync(); else __syncthreads();   // the peer's shared memory / barriers stay alive until both are done
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -398,9 +481,14 @@ static int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUten
 
 using namespace ec;
 
+static int ec_tc_debug = 0;
+extern "C" int ec_tc_set_debug(int flags) {   // bring-up / profiling experiments only (results are wrong when != 0)
+  ec_tc_debug = flags;
+  return EC_OK;
+}
 static int ec_tc_force_bn = 0;   // 0 = heuristic; 128 / 256 force a tile width (tuning / tests)
 extern "C" int ec_tc_set_tile_n(int bn) {
-  EC_REQUIRE(bn == 0 || bn == 128 || bn == 256, "ec_tc_set_tile_n: 0, 128 or 256");
+  EC_REQUIRE(bn == 0 || bn == 128 || bn == 256 || bn == 512, "ec_tc_set_tile_n: 0, 128, 256 or 512 (CTA pair)");
   ec_tc_force_bn = bn;
   return EC_OK;
 }
@@ -433,20 +521,23 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
     int dev = 0;
     EC_CUDA(cudaGetDevice(&dev));
     EC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 tc::smem_bytes<128>()));
-    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 tc::smem_bytes<256>()));
+    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc::SMEM_BYTES));
+    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc::SMEM_BYTES));
+    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc::SMEM_BYTES));
     attr_set = true;
   }
-  // wide tiles when they still give every SM at least ~1.5 tiles and N fills them
-  const long long tiles256 = (long long)cdiv(M, tc::BM) * cdiv(N, 256);
-  const bool wide = ec_tc_force_bn == 256 || (ec_tc_force_bn == 0 && N % 256 == 0 && tiles256 * 2 >= 3LL * num_sms);
-  const int BN = wide ? 256 : 128;
+  // tile selection: CTA-pair 256x256 tiles for problems that give every SM pair >= 1.5 tiles, else 128x128
+  const long long pair_tiles = (long long)cdiv(M, 256) * cdiv(N, 256);
+  int mode = ec_tc_force_bn;                     // 0 heuristic, 128, 256, 512 (= pair)
+  if (mode == 0) mode = (N >= 256 && pair_tiles * 4 >= 3LL * num_sms) ? 512 : 128;
+  const int BN = mode == 128 ? 128 : 256;
   CUtensorMap tmA, tmB;
   int rc = tc::get_tensor_map(A2, M, Kp, tc::BM, &tmA);
   if (rc) return rc;
-  rc = tc::get_tensor_map(B2, N, Kp, BN, &tmB);
+  rc = tc::get_tensor_map(B2, N, Kp, mode == 256 ? 256 : 128, &tmB);
   if (rc) return rc;
   tc::TcParams p;
   p.C = C; p.M = M; p.N = N; p.num_kb = Kp / tc::BK; p.Kp = Kp; p.ldc = ldc;
@@ -455,11 +546,30 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.vec_r = R && aligned16(R) && (ldr % 4 == 0);
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
   p.res_mode = res_mode; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
-  const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  if (wide)
-    tc::gemm_f16x3_kernel<256><<<grid, tc::THREADS, tc::smem_bytes<256>(), (cudaStream_t)stream>>>(tmA, tmB, p);
-  else
-    tc::gemm_f16x3_kernel<128><<<grid, tc::THREADS, tc::smem_bytes<128>(), (cudaStream_t)stream>>>(tmA, tmB, p);
+  p.dbg = ec_tc_debug;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 512) {
+    const int pairs = (int)(pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true>, tmA, tmB, p));
+  } else {
+    const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (BN == 256)
+      tc::gemm_f16x3_kernel<256, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);
+    else
+      tc::gemm_f16x3_kernel<128, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);
+  }
   return check_launch("ec_gemm_f16x3");
 }

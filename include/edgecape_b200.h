@@ -84,6 +84,9 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
 /* tuning knob for ec_gemm_f16x3: 0 = pick the tile width per shape (128x256 tiles for wide, large
  * problems, 128x128 otherwise), 128 / 256 = force it. */
 int ec_tc_set_tile_n(int bn);
+/* profiling experiments on ec_gemm_f16x3 (results are WRONG when flags != 0): 1 = operands stay resident
+ * (no TMA after the pipeline is primed), 2 = hi*hi product only, 4 = no epilogue stores. */
+int ec_tc_set_debug(int flags);
 
 /* ------------------------------------------------------------------------- normalisation
  * Y[m,:] = LayerNorm(X[m,:] (+ R[m,:])) * w + b  (biased variance, eps inside the sqrt).

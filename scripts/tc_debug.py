@@ -32,7 +32,7 @@ def check(M, N, K, seed=0):
     return err
 
 
-def bench(M, N, K, iters=20):
+def bench(M, N, K, iters=20, simt=True):
     D = torch.device("cuda")
     x = torch.randn(M, K, device=D)
     w = torch.randn(N, K, device=D) * 0.02
@@ -48,6 +48,9 @@ def bench(M, N, K, iters=20):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / iters
     tf = 2.0 * M * N * K / ms / 1e9
+    if not simt:
+        print(f"   {M}x{N}x{K}: {ms:.3f} ms = {tf:.1f} algorithmic TFLOP/s", flush=True)
+        return
     s.record()
     for _ in range(iters):
         ops.gemm(x, w, out=out)
@@ -58,8 +61,47 @@ def bench(M, N, K, iters=20):
           f"= {2.0 * M * N * K / ms2 / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def experiments():
+    """Where does the main loop lose time?  (results are wrong while a flag is set)"""
+    from edgecape_b200 import _lib
+    lib = _lib.load()
+    for bn in (128, 256):
+        lib.ec_tc_set_tile_n(bn)
+        for flags, what in ((0, "baseline"), (4, "no epilogue stores"), (1, "no TMA (operands resident)"),
+                            (2, "hi*hi only (1 product, same loads)"), (3, "hi*hi only + no TMA"), (5, "no TMA + no stores"),
+                            (7, "hi*hi only, no TMA, no stores")):
+            lib.ec_tc_set_debug(flags)
+            print(f"[tile {bn}] {what}:")
+            bench(10400, 2304, 768, simt=False)
+            bench(10400, 768, 3072, simt=False)
+    lib.ec_tc_set_debug(0)
+    lib.ec_tc_set_tile_n(0)
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
+    if stage == "pair":
+        from edgecape_b200 import _lib
+        _lib.load().ec_tc_set_tile_n(512)
+        check(256, 256, 64)
+        check(256, 256, 256)
+        check(512, 768, 768)
+        check(1300, 768, 768)
+        check(200, 96, 100)
+        check(650, 3072, 768)
+        check(10400, 2304, 768)
+        sys.exit(0)
+    if stage == "pairbench":
+        from edgecape_b200 import _lib
+        for bn in (512, 128):
+            _lib.load().ec_tc_set_tile_n(bn)
+            print("tile mode", bn)
+            for shp in [(10400, 2304, 768), (10400, 768, 768), (10400, 3072, 768), (10400, 768, 3072), (5184, 256, 768)]:
+                bench(*shp, simt=False)
+        sys.exit(0)
+    if stage == "exp":
+        experiments()
+        sys.exit(0)
     if stage == "tiny":
         check(128, 128, 64)
     elif stage == "k2":

@@ -366,7 +366,7 @@ def test_split_f16_reconstructs_fp32():
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (128, 256, 192), (1300, 768, 768),
                                    (200, 96, 100), (5184, 256, 768), (650, 3072, 768), (650, 768, 3072), (77, 33, 516)])
-@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("tile_n", [128, 256, 512])
 def test_gemm_tc_fp32_grade(M, N, K, tile_n, request):
     from edgecape_b200 import _lib
     _lib.load().ec_tc_set_tile_n(tile_n)
