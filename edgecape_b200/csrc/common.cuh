@@ -58,7 +58,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // erff / tanhf expand to ~50-100 instructions each: kept out of line so that heavily unrolled epilogues
 // (32+ call sites per loop body) stay inside the instruction cache
-__device__ __noinline__ float apply_act_transcendental(float x, int act) {
+static __device__ __noinline__ float apply_act_transcendental(float x, int act) {
   return act == EC_ACT_GELU ? gelu_erf(x) : tanhf(x);
 }
 __device__ __forceinline__ float apply_act(float x, int act) {
