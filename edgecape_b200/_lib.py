@@ -49,6 +49,7 @@ SIGNATURES = {
     "ec_edge_weights": (c_int, [c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "ec_gcn_pack_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "ec_gcn": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp, c_sz, c_fp]),
+    "ec_gcn_aggregate_split": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "ec_workspace_bytes_gcn": (c_sz, [c_int, c_int, c_int, c_int]),
     "ec_support_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),

@@ -22,14 +22,16 @@ namespace atc {
 constexpr int D = 64;
 constexpr int BM = 128;                 // query rows per CTA (UMMA M)
 constexpr int KC = 64;                  // keys per P/V chunk (one 128-byte swizzle span of fp16)
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;            // 16 warps: 4 per TMEM lane quarter (latency hiding for the softmax / staging work)
+constexpr int NPART = THREADS / 128;    // warps sharing one lane quarter split the keys NPART ways
+constexpr int PW = KC / NPART;          // keys of a chunk handled by one warp (16)
 constexpr int MAX_LKP = 448;            // S columns in TMEM; O uses columns [448, 512)
 constexpr int O_COL = 448;
 constexpr int Q_BYTES = 2 * BM * 128;   // Q_hi + Q_lo
 constexpr int PBUF_BYTES = 2 * BM * 128;      // P_hi + P_lo of one chunk (32 KB)
 constexpr int VBUF_BYTES = 2 * D * 128;       // V_hi^T + V_lo^T of one chunk (16 KB)
 constexpr int REUSE_BYTES = 2 * PBUF_BYTES + 2 * VBUF_BYTES;   // 96 KB, aliases Q and K after S is done
-constexpr int MISC_BYTES = 64 + 4 * BM * 4;   // barriers + tmem slot, row max / row sum exchange
+constexpr int MISC_BYTES = 64 + 2 * NPART * BM * 4;   // barriers + tmem slot, row max / row sum exchange
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -82,6 +84,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // byte offset of the 16-byte chunk `c` (8 fp16) of row `row` inside a 128B-swizzled K-major tile
 __device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)); }
 
@@ -117,11 +130,11 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   const int data_bytes = max(Q_BYTES + 2 * p.LKP * 128, REUSE_BYTES);
   const uint32_t misc = base + data_bytes;
   const uint32_t bar_s = misc, bar_pv0 = misc + 8, bar_pv1 = misc + 16, tmem_slot = misc + 24;
-  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [2][BM]
-  float* xsum = xmax + 2 * BM;                                        // [2][BM]
+  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
+  float* xsum = xmax + NPART * BM;                                    // [NPART][BM]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, part = warp >> 2;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
 
   if (tid == 0) {
@@ -215,26 +228,29 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
   const int nchunk32 = (p.Lk + 31) / 32;
   float mymax = -INFINITY;
-  for (int j = half; j < nchunk32; j += 2) {
+  for (int j = part; j < nchunk32; j += NPART) {
     float s[32];
     tmem_ld32(t_row + j * 32, s);
 #pragma unroll
     for (int u = 0; u < 32; ++u)
       if (j * 32 + u < p.Lk) mymax = fmaxf(mymax, s[u]);
   }
-  xmax[half * BM + row] = mymax;
+  xmax[part * BM + row] = mymax;
   __syncthreads();                                     // also: every warp is done with Q / K shared memory
-  const float rmax = fmaxf(xmax[row], xmax[BM + row]);
+  float rmax = xmax[row];
+#pragma unroll
+  for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
 
   // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
   const float* Vb = p.V + (long long)b * p.sv + h * D;
   const int nchunks = (p.Lk + KC - 1) / KC;
   const uint32_t idesc_o = make_idesc(D);
   float rsum = 0.f;
-  float4 va[2], vb[2];                                   // V rows of the next chunk (2 items of 8 floats per thread)
+  constexpr int VI = KC * 8 / THREADS;                   // V items (8 floats of one key) per thread and chunk
+  float4 va[VI], vb[VI];                                 // V rows of the next chunk, prefetched
   auto load_v = [&](int chunk) {
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < VI; ++w) {
       const int it = tid + w * THREADS;
       const int kl = it >> 3, dc = it & 7;
       const int key = chunk * KC + kl;
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
     // V^T of this chunk (tile rows = head-dim index, columns = keys) from the registers prefetched one
     // iteration ago; then the loads of the next chunk are issued so they overlap the exponentials below
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < VI; ++w) {
       const int it = tid + w * THREADS;
       const int kl = it >> 3, dc = it & 7;
       const float v[8] = {va[w].x, va[w].y, va[w].z, va[w].w, vb[w].x, vb[w].y, vb[w].z, vb[w].w};
@@ -271,22 +287,22 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
       }
     }
     load_v(i + 1);
-    // P of this chunk: this warp covers keys [i*64 + 32*half, +32) of its 32 rows
+    // P of this chunk: this warp covers keys [i*64 + PW*part, +PW) of its 32 rows
     {
-      float s[32];
-      const int kbase = i * KC + 32 * half;
-      tmem_ld32(t_row + kbase, s);
+      float s[PW];
+      const int kbase = i * KC + PW * part;
+      tmem_ld16(t_row + kbase, s);
 #pragma unroll
-      for (int u = 0; u < 32; ++u) {
+      for (int u = 0; u < PW; ++u) {
         const float e = (kbase + u < p.Lk) ? exp2f((s[u] - rmax) * 1.4426950408889634f) : 0.f;
         s[u] = e;
         rsum += e;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < PW / 8; ++j) {
         uint4 hi, lo;
         split8(s + 8 * j, hi, lo);
-        const uint32_t off = swz(row, 4 * half + j);
+        const uint32_t off = swz(row, (PW / 8) * part + j);
         *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
         *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
       }
@@ -312,27 +328,31 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
     if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
   }
   tc_fence_after();
-  xsum[half * BM + row] = rsum;
+  xsum[part * BM + row] = rsum;
   __syncthreads();
-  const float inv = 1.0f / (xsum[row] + xsum[BM + row]);
+  float tot = 0.f;
+#pragma unroll
+  for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
+  const float inv = 1.0f / tot;
 
   // ------------------------------------------------------------------ epilogue: O / rowsum
   {
-    float o[32];
-    tmem_ld32(t_row + O_COL + 32 * half, o);
+    constexpr int OW = D / NPART;                        // output columns per warp (16)
+    float o[OW];
+    tmem_ld16(t_row + O_COL + OW * part, o);
     const int grow = q0 + row;
     if (grow < p.Lq) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) o[u] *= inv;
+      for (int u = 0; u < OW; ++u) o[u] *= inv;
       if (p.O) {
-        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + 32 * half);
+        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
       }
       if (p.split_out) {
-        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + 32 * half;
+        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < OW / 8; ++j) {
           uint4 hi, lo;
           split8(o + 8 * j, hi, lo);
           *reinterpret_cast<uint4*>(sp + 8 * j) = hi;

@@ -1,5 +1,7 @@
 // Skeleton / graph kernels: adjacency from edge lists, soft normalisation, edge-weight
 // prediction with Markov hop matrices, and the GCN feed-forward (aggregate + packed GEMM).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ec {
@@ -135,6 +137,81 @@ __global__ void __launch_bounds__(256) gcn_fill_kernel(const float* __restrict__
   }
 }
 
+// Fused aggregate for the tensor-core GCN: one pass produces the GEMM A operand
+//   Z[b,w,:] = [ a0[w] X[b,w,:] | sum_v A1[b,w,v] X[b,v,:] | a0[w] | rowsum(A1[b,w,:]) | 0 ... ]
+// directly in split-fp16 form Z2 [B*K, 2*Kp] (hi | lo).  CTA = (16 rows of one sample); the 16 x K block of
+// A1 sits in shared memory and is read as float4 broadcasts, X rows stream through coalesced loads.
+constexpr int GA_ROWS = 16;
+__global__ void __launch_bounds__(256) gcn_aggregate_split_kernel(const float* __restrict__ X,
+                                                                  const float* __restrict__ adj,
+                                                                  __half* __restrict__ Z2, int K, int d, int Kp) {
+  extern __shared__ float a1s[];                 // [GA_ROWS][KP4] (KP4 = K rounded up to 4, zero padded)
+  __shared__ float rs[GA_ROWS], a0s[GA_ROWS];
+  const int b = blockIdx.y, w0 = blockIdx.x * GA_ROWS;
+  const int KP4 = (K + 3) & ~3;
+  const long long KK = (long long)K * K;
+  const float* a0p = adj + (long long)b * 2 * KK;
+  const float* a1p = a0p + KK;
+  for (int i = threadIdx.x; i < GA_ROWS * KP4; i += blockDim.x) {
+    const int r = i / KP4, v = i % KP4;
+    a1s[i] = (w0 + r < K && v < K) ? a1p[(long long)(w0 + r) * K + v] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < GA_ROWS; r += 8) {
+    float sacc = 0.f;
+    for (int v = lane; v < KP4; v += 32) sacc += a1s[r * KP4 + v];
+    sacc = warp_sum(sacc);
+    if (lane == 0) {
+      rs[r] = sacc;
+      a0s[r] = (w0 + r < K) ? a0p[(long long)(w0 + r) * K + (w0 + r)] : 0.f;
+    }
+  }
+  __syncthreads();
+  const float* Xb = X + (long long)b * K * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc[GA_ROWS];
+#pragma unroll
+    for (int r = 0; r < GA_ROWS; ++r) acc[r] = 0.f;
+    for (int v = 0; v < KP4; v += 4) {
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = (v + u < K) ? __ldg(Xb + (long long)(v + u) * d + c) : 0.f;
+#pragma unroll
+      for (int r = 0; r < GA_ROWS; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(&a1s[r * KP4 + v]);
+        acc[r] = fmaf(a.x, x[0], acc[r]);
+        acc[r] = fmaf(a.y, x[1], acc[r]);
+        acc[r] = fmaf(a.z, x[2], acc[r]);
+        acc[r] = fmaf(a.w, x[3], acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < GA_ROWS; ++r) {
+      const int w = w0 + r;
+      if (w >= K) continue;
+      __half* z = Z2 + ((long long)b * K + w) * 2 * Kp;
+      const float y0 = a0s[r] * __ldg(Xb + (long long)w * d + c), y1 = acc[r];
+      const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+      z[c] = h0;
+      z[Kp + c] = __float2half_rn(y0 - __half2float(h0));
+      z[d + c] = h1;
+      z[Kp + d + c] = __float2half_rn(y1 - __half2float(h1));
+    }
+  }
+  // tail columns: a0, rowsum, zero padding
+  for (int i = threadIdx.x; i < GA_ROWS * (Kp - 2 * d); i += blockDim.x) {
+    const int r = i / (Kp - 2 * d), c = 2 * d + i % (Kp - 2 * d);
+    const int w = w0 + r;
+    if (w >= K) continue;
+    const float y = c == 2 * d ? a0s[r] : (c == 2 * d + 1 ? rs[r] : 0.f);
+    __half* z = Z2 + ((long long)b * K + w) * 2 * Kp;
+    const __half hi = __float2half_rn(y);
+    z[c] = hi;
+    z[Kp + c] = __float2half_rn(y - __half2float(hi));
+  }
+}
+
 // Wp[c, :] = [ W[c, 0:d] | W[dff + c, 0:d] | bias[c] | bias[dff + c] | 0 0 ]
 __global__ void gcn_pack_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                 float* __restrict__ Wp, int d, int dff) {
@@ -190,6 +267,18 @@ extern "C" int ec_gcn_pack_weights(const float* W, const float* bias, float* Wp,
   long long total = (long long)dff * (2 * d + 4);
   gcn_pack_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(W, bias, Wp, d, dff);
   return check_launch("ec_gcn_pack_weights");
+}
+
+extern "C" int ec_gcn_aggregate_split(const float* X, const float* adj, void* Z2, int B, int K, int d, int Kp,
+                                      void* stream) {
+  EC_REQUIRE(X && adj && Z2, "ec_gcn_aggregate_split: null pointer");
+  EC_REQUIRE(Kp % 64 == 0 && Kp >= 2 * d + 2, "ec_gcn_aggregate_split: Kp must be a multiple of 64 and >= 2d+2");
+  if (B == 0 || K == 0) return EC_OK;
+  const size_t smem = (size_t)GA_ROWS * ((K + 3) & ~3) * sizeof(float);
+  EC_REQUIRE(smem <= 48 * 1024, "ec_gcn_aggregate_split: K too large for the shared-memory tile");
+  dim3 grid(cdiv(K, GA_ROWS), B);
+  gcn_aggregate_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(X, adj, (__half*)Z2, K, d, Kp);
+  return check_launch("ec_gcn_aggregate_split");
 }
 
 extern "C" int ec_gcn(const float* X, const float* adj, const float* Wp, float* Y, int B, int K, int d, int dff,

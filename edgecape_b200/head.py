@@ -84,6 +84,8 @@ class TwoStageHead(PackedMixin, nn.Module):
         self.transformer.masking_ratio = masking_ratio
         self.use_zero_conv = skeleton_head.get("use_zero_conv", False)
         self.freeze, self.model_freeze = freeze, model_freeze
+        self.concurrent_skeleton = bool(self.test_cfg.get("concurrent_skeleton", True))
+        self._side = None
 
     def init_weights(self):
         """head.py:143-159 (xavier everywhere, zero last kpt_branch layer and zero_conv)."""
@@ -135,12 +137,37 @@ class TwoStageHead(PackedMixin, nn.Module):
             pooled = ops.gemm(tw, feat, b_kmajor=False, residual=pooled, res_mode=ops.RES_ADD)   # [B,K,C]
         ops.linear(pooled, self.query_proj.weight, self.query_proj.bias, out=x[:, S:, :])
         kp_tokens = ops.copy_rows(x[:, S:, :], ops.empty(B, K, d, device=dev))
-        # skeleton / edge-weight predictor (head.py:196)
-        adj, attn_adj, unnorm, refined = self.skeleton_head.forward_tokens(skeleton_lst, kp_tokens, feats_s, kp_mask,
-                                                                           kp_mask_fixed, grid_pos)
+        # skeleton / edge-weight predictor (head.py:196) on a side stream: it only depends on the support
+        # features and the pooled keypoint tokens, so it overlaps the query encoder + proposal generator; the
+        # decoder (first consumer of adj / attn_adj) joins.  Inside a CUDA graph this becomes a parallel branch.
+        main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+        sk = {}
+        if main is not None and self.concurrent_skeleton:
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                sk["out"] = self.skeleton_head.forward_tokens(skeleton_lst, kp_tokens, feats_s, kp_mask, kp_mask_fixed,
+                                                              grid_pos)
+
+            def join():
+                main.wait_stream(side)
+                if not torch.cuda.is_current_stream_capturing():   # (a graph's private pool needs no stream tracking)
+                    for t_ in sk["out"]:
+                        if torch.is_tensor(t_):
+                            t_.record_stream(main)
+                return sk["out"][0], sk["out"][1]
+        else:
+            sk["out"] = self.skeleton_head.forward_tokens(skeleton_lst, kp_tokens, feats_s, kp_mask, kp_mask_fixed,
+                                                          grid_pos)
+
+            def join():
+                return sk["out"][0], sk["out"][1]
         # encoder -> proposals -> graph decoder (head.py:203)
         tr = self.transformer.forward_tokens(x, S, (h, w), grid_pos, kp_mask, kp_mask_fixed,
-                                             self.positional_encoding, self.kpt_branch, adj, attn_adj)
+                                             self.positional_encoding, self.kpt_branch, join, None)
+        adj, attn_adj, unnorm, refined = sk["out"]
         # final per-layer decode (head.py:216-220)
         L = tr["hs"].shape[0]
         output = ops.empty(L, B, K, 2, device=dev)

@@ -406,13 +406,32 @@ def gcn_pack_weights(W, bias):
     return Wp
 
 
-def gcn(x, adj, Wp, out=None):
-    """x [B,K,d], adj [B,2,K,K] (plane 0 diagonal), packed weights -> relu(GCN) [B,K,dff]."""
+def gcn_tc_ok(B, K):
+    """True when gcn() takes the tensor-core route (and can therefore hand back a split result)."""
+    return TENSOR_CORES and B * K >= TC_MIN_M and ((K + 3) // 4 * 4) * 64 <= 48 * 1024
+
+
+def gcn(x, adj, Wp, out=None, split="no"):
+    """x [B,K,d], adj [B,2,K,K] (plane 0 diagonal), packed weights -> relu(GCN) [B,K,dff].
+    Tensor-core mode: fused aggregate -> split-fp16 Z, then the tcgen05 GEMM with a ReLU epilogue; split="only"
+    returns the SplitOperand of the result (the A operand of the ffn2 GEMM that follows)."""
     _chk(x, "x"); _chk(adj, "adj"); _chk(Wp, "Wp")
     assert x.is_contiguous() and adj.is_contiguous()
     B, K, d = x.shape
     dff = Wp.shape[0]
     assert Wp.shape[1] == 2 * d + 4
+    if gcn_tc_ok(B, K):
+        Kp = _kp(2 * d + 4)
+        z2 = SplitOperand(empty(B * K, 2 * Kp, dtype=torch.float16, device=x.device), B * K, 2 * d + 4, Kp, 1.0)
+        _lib.call("ec_gcn_aggregate_split", _p(x), _p(adj), _p(z2.data), B, K, d, Kp, _stream())
+        if split == "only":
+            return gemm_tc(z2, split_weight(Wp), act=ACT_RELU, split_out=True, fp32_out=False)[1]
+        o2 = None if out is None else out.view(B * K, dff)
+        res = gemm_tc(z2, split_weight(Wp), out=o2, act=ACT_RELU, split_out=(split == "also"))
+        y = res[0] if split == "also" else res
+        y = out if out is not None else y.view(B, K, dff)
+        return (y, res[1]) if split == "also" else y
+    assert split == "no", "split outputs need the tensor-core path"
     if out is None:
         out = empty(B, K, dff, device=x.device)
     assert out.is_contiguous()

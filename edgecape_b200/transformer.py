@@ -74,8 +74,11 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     t = ops.linear(a, node.choker.weight, node.choker.bias, residual=kp1)
     kp2 = ops.layernorm(t, node.norm2.weight, node.norm2.bias, 1e-5)
     # (iii) GCN feed-forward, ffn2, residual, norm3
-    g = ops.gcn(kp2.view(B, K, d), adj, pk["gcn_w"])
-    t = ops.linear(g.view(B * K, -1), node.ffn2.weight, node.ffn2.bias, residual=kp2)
+    if ops.gcn_tc_ok(B, K):       # the GCN GEMM epilogue emits the split-fp16 operand of ffn2 directly
+        g = ops.gcn(kp2.view(B, K, d), adj, pk["gcn_w"], split="only")
+    else:
+        g = ops.gcn(kp2.view(B, K, d), adj, pk["gcn_w"]).view(B * K, -1)
+    t = ops.linear(g, node.ffn2.weight, node.ffn2.bias, residual=kp2)
     if not two_way:
         return ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5).view(B, K, d)
     # (iv) image tokens attend to the (un-masked!) keypoint tokens, choker, residual, norm4
@@ -238,7 +241,10 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
             self.encode(x, grid_pos, S, enc_mask)
         img, kp = x[:, :S, :], x[:, S:, :]
         pl, sim, pr, am = self.propose(img, kp, h, w)
-        # decoder (:330-425)
+        # decoder (:330-425).  `adj` may be a callable: the head runs the skeleton predictor on a side stream
+        # concurrently with the encoder above and joins here, where its result is first needed
+        if callable(adj):
+            adj, attn_adj = adj()
         pk = self.packed()["dec"]
         img_cat = ops.empty(B, S, 2 * d, device=dev)                 # [img | grid pos]  (torch.cat of :621)
         ops.copy_rows(img, img_cat[:, :, :d])

@@ -184,6 +184,10 @@ int ec_gcn_pack_weights(const float* W, const float* bias, float* Wp, int d, int
 int ec_gcn(const float* X, const float* adj, const float* Wp, float* Y, int B, int K, int d, int dff,
            float* workspace, size_t workspace_bytes, void* stream);
 size_t ec_workspace_bytes_gcn(int B, int K, int d, int dff);
+/* Tensor-core form of the same layer: one fused kernel writes Z directly as the split-fp16 A operand
+ * Z2 [B*K, 2*Kp] (Kp = 2d+4 rounded up to 64), then ec_gemm_f16x3(Z2, split(Wp), act = ReLU) finishes it. */
+int ec_gcn_aggregate_split(const float* X, const float* adj, void* Z2, int B, int K, int d, int Kp,
+                           void* stream);
 
 /* ----------------------------------------------------------------------------- head ops
  * support-keypoint pooling weights (head.py:175-184, exact by linearity):

@@ -306,6 +306,17 @@ def ec_gcn(X, adj, Wp, Y, B, K, d, dff, ws, wsbytes, stream):
     arr(Y, (B, K, dff))[...] = F.relu(y).numpy()
 
 
+def ec_gcn_aggregate_split(X, adj, Z2, B, K, d, Kp, stream):
+    x, a = arr(X, (B, K, d)), arr(adj, (B, 2, K, K))
+    a0 = np.stack([np.diag(a[b, 0]) for b in range(B)])                      # [B,K]
+    z = np.zeros((B, K, Kp), dtype=np.float32)
+    z[:, :, :d] = a0[:, :, None] * x
+    z[:, :, d:2 * d] = a[:, 1] @ x
+    z[:, :, 2 * d] = a0
+    z[:, :, 2 * d + 1] = a[:, 1].sum(-1)
+    _write_split(Z2, Kp, z.reshape(B * K, Kp))
+
+
 def ec_support_weights(target, rowscale, Tw, ldtw, BK, hm_h, hm_w, h, w, stream):
     t = T(arr(target, (BK, hm_h * hm_w)))
     # U[p, s]: bilinear interpolation matrix = upsampled one-hot basis images

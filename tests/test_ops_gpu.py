@@ -188,7 +188,9 @@ def test_adjacency_from_edges_and_soft_normalize(K):
 
 
 @pytest.mark.parametrize("B,K,d,dff", [(4, 100, 256, 384), (2, 17, 256, 64), (2, 200, 256, 384), (3, 100, 256, 768)])
-def test_gcn_matches_oracle(B, K, d, dff):
+@pytest.mark.parametrize("tensor_cores", [True, False], ids=["tcgen05", "simt"])
+def test_gcn_matches_oracle(B, K, d, dff, tensor_cores, monkeypatch):
+    monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     x = rnd(B, K, d, seed=1)
     W, b = rnd(2 * dff, d, 1, seed=2, scale=d ** -0.5), 0.1 * rnd(2 * dff, seed=3)
     mask = torch.zeros(B, K, dtype=torch.bool)
@@ -200,6 +202,9 @@ def test_gcn_matches_oracle(B, K, d, dff):
     Wp = ops.gcn_pack_weights(W.to(D), b.to(D))
     got = ops.gcn(x.to(D), adj.to(D).contiguous(), Wp)
     close(got, want, what="gcn")
+    if tensor_cores and B * K >= ops.TC_MIN_M:
+        so = ops.gcn(x.to(D), adj.to(D).contiguous(), Wp, split="only")
+        close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), what="gcn split")
 
 
 def test_edge_weights_and_markov_match_oracle():
