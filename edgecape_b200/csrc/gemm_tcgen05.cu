@@ -6,7 +6,7 @@
 // and feeds 3 x 4 UMMA 128x128x16 instructions, i.e. 4 tile loads per 3 products instead of 6.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM -> registers -> bias/activation/LayerScale/residual -> global, and
+// lane), warps 2..9 = epilogue (TMEM -> registers -> bias/activation/LayerScale/residual -> global, and
 // optionally the split-fp16 form of the result for the next GEMM).  Two TMEM accumulator stages overlap
 // the epilogue of tile i with the MMAs of tile i+1.
 #include <cuda.h>
@@ -26,9 +26,9 @@ constexpr int TILE_BYTES = BM * BK * 2;               // one 128-row operand til
 // (cta_group::2, 3 stages of 64 KB per CTA).  The main loop is bound by how many operand bytes can be in flight
 // in shared memory per unit of math (profiles/r01_d): the pair tile feeds twice the math per staged byte.
 constexpr int NUM_ACC = 2;
-constexpr int THREADS = 192;
-constexpr int EPI_LD = 36;                           // staging row stride (floats)
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;       // one 32 x 32 staging tile per epilogue warp
+constexpr int THREADS = 320;                         // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_LD = 20;                           // staging row stride (floats)
+constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;       // one 32 x 16 staging tile per epilogue warp
 constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;   // all variants
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,6 +96,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -192,7 +202,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 8 : 4); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -288,13 +298,17 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ---------------------------------------------------------------------- epilogue
-    // TMEM gives each lane one accumulator row; rows are transposed through a per-warp shared-memory
-    // staging tile (row stride 36 floats: conflict-free float4 writes and reads) so that global
-    // traffic is full 128 B lines: 8 lanes cover one 32-column row segment, a warp covers 4 rows.
+    // ---------------------------------------------------------------------- epilogue (8 warps)
+    // TMEM gives each lane one accumulator row.  Two warps share a lane quarter and alternate over 16-column
+    // sub-chunks; each sub-chunk is transposed through a per-warp shared-memory tile (row stride 20 floats:
+    // conflict-free float4 writes) so that global traffic is row-contiguous: 4 lanes cover one 16-column
+    // row segment (64 B), a warp covers 8 rows per step.  Eight warps (two per scheduler) hide the latency
+    // of the residual loads and of erf / tanh, which four could not (profiles/r01_f).
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int group = (warp - 2) >> 2;             // which of the two warps of the quarter
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
-    const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
+    const int sub_row = lane >> 2, c4 = (lane & 3) * 4;
+    constexpr int NSUB = BN / 16;
     int t = 0;
     const uint32_t tempty_leader0 = TWO ? mapa(tempty_bar(0), 0) : 0u, tempty_leader1 = TWO ? mapa(tempty_bar(1), 0) : 0u;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
@@ -303,25 +317,25 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        if (c == BN / 32 - 1) {
-          // accumulator fully drained into registers: hand it back to the MMA warp early
+      for (int sc = group; sc < NSUB; sc += 2) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + sc * 16), r);
+        if (sc + 2 >= NSUB) {
+          // this warp has drained its share of the accumulator: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (TWO) mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);   // the leader's MMA thread waits for 8 warps
+            if (TWO) mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);   // the leader's MMA thread waits for 16 warps
             else mbar_arrive(tempty_bar(acc));
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                           __uint_as_float(r[j + 3]));
         __syncwarp();
-        const int gcol = n0 + c * 32 + c4;
+        const int gcol = n0 + sc * 16 + c4;
         if (gcol < p.N) {
           const bool full = gcol + 3 < p.N;
           float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f};
@@ -331,15 +345,36 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.bias) bv[u] = __ldg(p.bias + gcol + u);
               if (p.colscale) sv[u] = __ldg(p.colscale + gcol + u);
             }
+          float y[4][4];
+          // accumulator * out_scale + bias, activation (transcendental ones in a rolled loop: code size)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + sub_row;
-            const int row = m0 + quarter * 32 + rl;
+          for (int i = 0; i < 4; ++i) {
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + (i * 8 + sub_row) * EPI_LD + c4);
+            y[i][0] = fmaf(a4.x, p.out_scale, bv[0]); y[i][1] = fmaf(a4.y, p.out_scale, bv[1]);
+            y[i][2] = fmaf(a4.z, p.out_scale, bv[2]); y[i][3] = fmaf(a4.w, p.out_scale, bv[3]);
+          }
+          if (p.act == EC_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) y[i][u] = fmaxf(y[i][u], 0.f);
+          } else if (p.act == EC_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) y[i][u] = gelu_erf(y[i][u]);
+          } else if (p.act == EC_ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) y[i][u] = tanhf(y[i][u]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = m0 + quarter * 32 + i * 8 + sub_row;
             if (row >= p.M) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * EPI_LD + c4);
-            float y[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) y[u] = apply_act(fmaf(y[u], p.out_scale, bv[u]), p.act) * sv[u];
+            for (int u = 0; u < 4; ++u) y[i][u] *= sv[u];
             if (p.R) {
               const float* rp = p.R + (long long)row * p.ldr + gcol;
               float rr[4] = {0.f, 0.f, 0.f, 0.f};
@@ -352,26 +387,26 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   if (gcol + u < p.N) rr[u] = rp[u];
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) y[u] = (p.res_mode == EC_RES_GATE) ? (y[u] + 1.0f) * rr[u] : rr[u] + y[u];
+              for (int u = 0; u < 4; ++u) y[i][u] = (p.res_mode == EC_RES_GATE) ? (y[i][u] + 1.0f) * rr[u] : rr[u] + y[i][u];
             }
             if (p.C && !(p.dbg & 4)) {
               float* cp = (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
                                        : p.C + (long long)row * p.ldc) + gcol;
               if (full && p.vec_c) {
-                *reinterpret_cast<float4*>(cp) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4*>(cp) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
               } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (gcol + u < p.N) cp[u] = y[u];
+                  if (gcol + u < p.N) cp[u] = y[i][u];
               }
             }
             if (p.split_out) {
               __half hi[4], lo[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const float sc = (gcol + u < p.N) ? y[u] * p.split_scale : 0.f;
-                hi[u] = __float2half_rn(sc);
-                lo[u] = __float2half_rn(sc - __half2float(hi[u]));
+                const float sc_ = (gcol + u < p.N) ? y[i][u] * p.split_scale : 0.f;
+                hi[u] = __float2half_rn(sc_);
+                lo[u] = __float2half_rn(sc_ - __half2float(hi[u]));
               }
               __half* sp = p.split_out + (long long)row * (2 * p.split_kp) + gcol;   // gcol % 4 == 0: 8 B aligned
               *reinterpret_cast<uint2*>(sp) = make_uint2(

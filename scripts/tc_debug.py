@@ -99,6 +99,43 @@ if __name__ == "__main__":
             for shp in [(10400, 2304, 768), (10400, 768, 768), (10400, 3072, 768), (10400, 768, 3072), (5184, 256, 768)]:
                 bench(*shp, simt=False)
         sys.exit(0)
+    if stage == "epi":
+        # the four ViT-B GEMMs with their real epilogues (M = 32 images x 325 tokens)
+        D = torch.device("cuda")
+        M, C = 10400, 768
+        x = torch.randn(M, C, device=D)
+        h = torch.randn(M, 4 * C, device=D)
+        t = torch.randn(M, C, device=D)
+        g = torch.rand(C, device=D)
+        ws = {n: ops.split_f16(torch.randn(o, i, device=D) * 0.02, 1024.0) for n, (o, i) in
+              dict(qkv=(3 * C, C), proj=(C, C), fc1=(4 * C, C), fc2=(C, 4 * C)).items()}
+        bs = {n: torch.randn(w.rows, device=D) for n, w in ws.items()}
+        x2, h2 = ops.split_f16(x), ops.split_f16(h)
+        qkv = torch.empty(M, 3 * C, device=D)
+        cases = dict(
+            qkv=lambda: ops.gemm_tc(x2, ws["qkv"], out=qkv, bias=bs["qkv"]),
+            proj=lambda: ops.gemm_tc(x2, ws["proj"], out=t, bias=bs["proj"], colscale=g, residual=t),
+            fc1=lambda: ops.gemm_tc(x2, ws["fc1"], bias=bs["fc1"], act=ops.ACT_GELU, split_out=True, fp32_out=False),
+            fc2=lambda: ops.gemm_tc(h2, ws["fc2"], out=t, bias=bs["fc2"], colscale=g, residual=t))
+        from edgecape_b200 import _lib
+        for mode in (512, 128):
+            _lib.load().ec_tc_set_tile_n(mode)
+            tot = 0.0
+            for n, fn in cases.items():
+                for _ in range(3):
+                    fn()
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                for _ in range(20):
+                    fn()
+                e_.record()
+                torch.cuda.synchronize()
+                ms = s_.elapsed_time(e_) / 20
+                tot += ms
+                K = 4 * C if n == "fc2" else C
+                print(f"[mode {mode}] {n}: {ms:.3f} ms = {2.0 * M * ws[n].rows * K / ms / 1e9:.1f} algorithmic TFLOP/s", flush=True)
+            print(f"[mode {mode}] one ViT-B layer of GEMMs: {tot:.3f} ms")
+        sys.exit(0)
     if stage == "exp":
         experiments()
         sys.exit(0)
