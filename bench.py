@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--kpts", type=int, default=100)
     ap.add_argument("--shots", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=2, help="queries per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="queries per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -100,7 +100,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 10))
     cb, ms = cpu_reference_rate(args, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "query images/s",
@@ -283,8 +283,8 @@ def run_ours(args):
         ms_eager, launches = timed(step_resident, args.steps, 2, gt_timer)
         model.use_cuda_graph = not args.no_graph
         roof = gt_timer.summary()
-    if world > 1:
-        dist.all_reduce(counters)          # the single collective of the path: fp64 PCK counters
+    from edgecape_b200.parallel import allreduce_counters, summarize_pck
+    allreduce_counters(counters)           # the single collective of the path: fp64 PCK counters (NCCL all-reduce)
     torch.cuda.synchronize()
 
     peaks = {}
@@ -316,6 +316,7 @@ def run_ours(args):
         "eager_ms_per_step": ms_eager / args.steps,
         "clocks": clocks.summary(),
         "pck_counters": [float(x) for x in counters.cpu().tolist()[:6]],
+        "pck_vs_random_gt": summarize_pck(counters[:6]),
         "algorithmic_gflop_per_query": flops_per_query(cfg, R, K, args.shots) / 1e9,
     }
     if roof:
