@@ -18,8 +18,12 @@ from .vit import DinoVisionTransformerB200
 
 
 class _GraphedForward:
-    """One captured CUDA graph of EdgeCape._forward_device for a fixed input signature, with static
-    input buffers (images, heat-maps, visibility weights, CSR edge lists up to `edge_capacity`)."""
+    """Captured CUDA graphs of EdgeCape._forward_device for a fixed input signature, with static input
+    buffers (images, heat-maps, visibility weights, CSR edge lists up to `edge_capacity`).
+
+    Two graphs: (A) the batched ViT over [query; supports], (B) mask + head.  Per call the images are
+    copied on the launch stream and A is replayed, while heat-maps / weights / edge lists (half of the
+    H2D bytes, only needed by B) are copied on a side stream concurrently with A; B joins them."""
 
     def __init__(self, model, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev):
         mk = lambda t: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
@@ -28,43 +32,62 @@ class _GraphedForward:
         self.target_s = [mk(t) for t in target_s]
         self.tw_s = [mk(t) for t in target_weight_s]
         B = img_q.shape[0]
+        self.B = B
         self.edge_capacity = max(1024, 2 * int(e_np.shape[0]))
         self.edges = torch.zeros(self.edge_capacity, 2, dtype=torch.int32, device=dev)
         self.offsets = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         self.host = torch.empty(2 * self.edge_capacity + B + 1, dtype=torch.int32).pin_memory()
         self.staged = None
-        self._load(img_q, img_s, target_s, target_weight_s, e_np, o_np)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        self._load_images(img_q, img_s)
+        self._load_head_inputs(main, target_s, target_weight_s, e_np, o_np)
+        main.wait_stream(self.copy_stream)
         # warm-up on a side stream (packs weights, fills caches, sets kernel attributes), then capture
         side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
+        side.wait_stream(main)
         with torch.cuda.stream(side):
             for _ in range(2):
                 model._forward_device(self.img_q, self.img_s, self.target_s, self.tw_s, (self.edges, self.offsets))
-        torch.cuda.current_stream(dev).wait_stream(side)
+        main.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = model._forward_device(self.img_q, self.img_s, self.target_s, self.tw_s,
-                                             (self.edges, self.offsets))
+        self.graph_vit = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_vit):
+            self.feat_q, self.feats_s = model.extract_features(self.img_s, self.img_q)
+        self.graph_head = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_head, pool=self.graph_vit.pool()):
+            self.out = model._head_device(self.feat_q, self.feats_s, self.target_s, self.tw_s,
+                                          (self.edges, self.offsets))
 
-    def _load(self, img_q, img_s, target_s, target_weight_s, e_np, o_np):
+    def _load_images(self, img_q, img_s):
+        self.img_q.copy_(img_q, non_blocking=True)
+        for d, s_ in zip(self.img_s, img_s):
+            d.copy_(s_, non_blocking=True)
+
+    def _load_head_inputs(self, main, target_s, target_weight_s, e_np, o_np):
         if self.staged is not None:
             self.staged.synchronize()      # the pinned CSR staging buffer is reused: wait for its last H2D
-        self.img_q.copy_(img_q, non_blocking=True)
-        for d, s_ in zip(self.img_s + self.target_s + self.tw_s, list(img_s) + list(target_s) + list(target_weight_s)):
-            d.copy_(s_, non_blocking=True)
         ne, no = e_np.shape[0], o_np.shape[0]
         self.host[:no] = torch.from_numpy(o_np)
         self.host[no:no + 2 * ne] = torch.from_numpy(e_np.reshape(-1))
-        self.offsets.copy_(self.host[:no], non_blocking=True)
-        if ne:
-            self.edges[:ne].view(-1).copy_(self.host[no:no + 2 * ne], non_blocking=True)
-        self.staged = torch.cuda.Event()
-        self.staged.record()
+        cs = self.copy_stream
+        cs.wait_stream(main)               # the previous replay of graph B may still read these buffers
+        with torch.cuda.stream(cs):
+            for d, s_ in zip(self.target_s + self.tw_s, list(target_s) + list(target_weight_s)):
+                d.copy_(s_, non_blocking=True)
+            self.offsets.copy_(self.host[:no], non_blocking=True)
+            if ne:
+                self.edges[:ne].view(-1).copy_(self.host[no:no + 2 * ne], non_blocking=True)
+            self.staged = torch.cuda.Event()
+            self.staged.record(cs)
 
     def run(self, img_q, img_s, target_s, target_weight_s, e_np, o_np):
-        self._load(img_q, img_s, target_s, target_weight_s, e_np, o_np)
-        self.graph.replay()
+        main = torch.cuda.current_stream(self.img_q.device)
+        self._load_head_inputs(main, target_s, target_weight_s, e_np, o_np)   # side stream, overlaps graph A
+        self._load_images(img_q, img_s)
+        self.graph_vit.replay()
+        main.wait_stream(self.copy_stream)
+        self.graph_head.replay()
         return self.out
 
 
@@ -87,6 +110,7 @@ class EdgeCape(nn.Module):
         self.target_type = self.test_cfg.get("target_type", "GaussianHeatMap")
         self.use_cuda_graph = bool(self.test_cfg.get("cuda_graph", True))
         self._graphs = {}
+        self._host_out = {}
         self.eval()
 
     def _apply(self, fn, *a, **k):
@@ -127,15 +151,29 @@ class EdgeCape(nn.Module):
         batch_size, _, img_height, img_width = img_q.shape
         output, initial_proposals, similarity_map, _, adj = self.predict(img_s, target_s, target_weight_s, img_q,
                                                                          img_metas)
-        predicted_pose = output[-1].detach().cpu().numpy()
+        # one synchronisation for all three device->host reads (the reference does three .cpu() calls)
+        L, B, K, _ = output.shape
+        host = self._host_out.get((L, B, K))
+        if host is None:
+            host = (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K))
+            if output.is_cuda:
+                host = tuple(t.pin_memory() for t in host)
+            self._host_out = {(L, B, K): host}
+        host[0][0].copy_(initial_proposals, non_blocking=True)
+        host[0][1:].copy_(output, non_blocking=True)
+        host[1].copy_(adj[0], non_blocking=True)
+        if output.is_cuda:
+            torch.cuda.current_stream(output.device).synchronize()
+        points = host[0].numpy().copy()
+        predicted_pose = points[-1]
         result = {}
         if self.with_keypoint:
             keypoint_result = self.keypoint_head_module.decode(img_metas, predicted_pose,
                                                                img_size=[img_width, img_height])
             result.update(keypoint_result)
-        result.update({"points": torch.cat((initial_proposals[None], output)).cpu().numpy()})
+        result.update({"points": points})
         result.update({"sample_image_file": [img_metas[i]["sample_image_file"] for i in range(len(img_metas))]})
-        result.update({"skeleton": adj[0].cpu().numpy()})
+        result.update({"skeleton": host[1].numpy().copy()})
         return result
 
     @torch.no_grad()
@@ -166,6 +204,16 @@ class EdgeCape(nn.Module):
         feat_q, feats_s = self.extract_features(img_s, img_q)
         return self.keypoint_head_module.forward_tokens(feat_q, feats_s, target_s, mask_s, skeleton,
                                                         return_intermediates=return_intermediates)
+
+    def _head_device(self, feat_q, feats_s, target_s, target_weight_s, skeleton):
+        """The part of _forward_device after the backbone (captured as its own CUDA graph)."""
+        dev = feat_q.device
+        B, K = target_weight_s[0].shape[:2]
+        mask_s = ops.empty(B, K, device=dev)
+        ops.mask_accumulate_(target_weight_s[0].reshape(B, K), mask_s, first=True)
+        for tw in target_weight_s[1:]:
+            ops.mask_accumulate_(tw.reshape(B, K), mask_s, first=False)
+        return self.keypoint_head_module.forward_tokens(feat_q, feats_s, target_s, mask_s, skeleton)
 
     # ------------------------------------------------------------------------ CUDA graphs
     def _predict_graphed(self, img_s, target_s, target_weight_s, img_q, skeleton_lst):
