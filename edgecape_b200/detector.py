@@ -83,8 +83,10 @@ class _GraphedForward:
 
     def run(self, img_q, img_s, target_s, target_weight_s, e_np, o_np):
         main = torch.cuda.current_stream(self.img_q.device)
-        self._load_head_inputs(main, target_s, target_weight_s, e_np, o_np)   # side stream, overlaps graph A
+        # images first: the DMA engine serves copies in issue order and graph A only needs the images; the
+        # head inputs follow on the copy stream and overlap graph A
         self._load_images(img_q, img_s)
+        self._load_head_inputs(main, target_s, target_weight_s, e_np, o_np)
         self.graph_vit.replay()
         main.wait_stream(self.copy_stream)
         self.graph_head.replay()
