@@ -15,6 +15,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ec {
 namespace atc {
@@ -368,6 +369,225 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   }
 }
 
+// =====================================================================================================
+// TMA-fed variant: Q, K, V arrive already split into fp16 (hi | lo) halves -- the QKV GEMM epilogue writes
+// them -- so the kernel stages nothing by hand: one thread issues TMA loads (128B-swizzled 64 x 64 boxes)
+// and the UMMAs; all 16 warps do only the softmax.  V is consumed as an MN-major B operand straight from
+// its [keys][head-dim] tile, so there is no transposition either.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// MN-major, SWIZZLE_128B: rows (= k index) of 128 B holding 64 contiguous MN elements, 8-row atoms of 1024 B
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc_bmn(int n) {       // as make_idesc, B operand MN-major
+  return make_idesc(n) | (1u << 16);
+}
+
+struct ParamsT {
+  float* O;
+  int B, H, Lq, Lk, LKP, NKB;      // NKB = 64-row K boxes staged (>= LKP / 64)
+  int ldo;
+  long long so;
+  float scale;
+  __half* split_out;
+  int split_kp;
+  int q_col, k_col, v_col;          // column of head 0 in the hi half of each buffer
+  int q_kp, k_kp, v_kp;             // columns per half
+  int q_rows, k_rows;               // rows per batch element in the Q and K/V buffers
+};
+
+constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, ParamsT p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int data_bytes = max(Q_BYTES + 2 * p.NKB * BOX_BYTES, REUSE_BYTES);
+  const uint32_t misc = base + data_bytes;
+  const uint32_t bar_qk = misc, bar_s = misc + 8, bar_pv0 = misc + 16, bar_pv1 = misc + 24, bar_v0 = misc + 32,
+                 bar_v1 = misc + 40, tmem_slot = misc + 48;
+  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
+  float* xsum = xmax + NPART * BM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, part = warp >> 2;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+  const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + p.NKB * BOX_BYTES;
+
+  if (tid == 0) {
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 1);
+    mbar_init(bar_pv0, 1); mbar_init(bar_pv1, 1);
+    mbar_init(bar_v0, 1); mbar_init(bar_v1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // Q tile (2 boxes) and all keys (NKB boxes), hi and lo halves
+    mbar_expect_tx(bar_qk, (uint32_t)((2 + p.NKB) * 2 * BOX_BYTES));
+    const int qrow = b * p.q_rows + q0, krow = b * p.k_rows;
+    for (int j = 0; j < 2; ++j) {
+      tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * D, qrow + 64 * j);
+      tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * D, qrow + 64 * j);
+    }
+    for (int j = 0; j < p.NKB; ++j) {
+      tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * D, krow + 64 * j);
+      tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * D, krow + 64 * j);
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+
+  // ------------------------------------------------------------------ S = Q K^T
+  if (tid == 0) {
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    int n0 = p.LKP <= 256 ? p.LKP : ((p.LKP / 2 + 15) / 16) * 16;
+    for (int noff = 0; noff < p.LKP; noff += n0) {
+      const int n = min(n0, p.LKP - noff);
+      const uint32_t idesc = make_idesc(n);
+      const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+      const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+    }
+    umma_commit(bar_s);
+  }
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+
+  // ------------------------------------------------------------------ row max of scale * S
+  const int row = quarter * 32 + lane;
+  const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const int nchunk32 = (p.Lk + 31) / 32;
+  float mymax = -INFINITY;
+  for (int j = part; j < nchunk32; j += NPART) {
+    float s[32];
+    tmem_ld32(t_row + j * 32, s);
+#pragma unroll
+    for (int u = 0; u < 32; ++u)
+      if (j * 32 + u < p.Lk) mymax = fmaxf(mymax, s[u]);
+  }
+  xmax[part * BM + row] = mymax;
+  __syncthreads();                                     // also: Q / K shared memory is dead from here on
+  float rmax = xmax[row];
+#pragma unroll
+  for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+  const float sl2 = p.scale * 1.4426950408889634f;     // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
+
+  // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
+  const int nchunks = (p.Lk + KC - 1) / KC;
+  const uint32_t idesc_o = make_idesc_bmn(D);
+  const int vrow0 = b * p.k_rows;
+  float rsum = 0.f;
+  for (int i = 0; i < nchunks; ++i) {
+    const int buf = i & 1;
+    const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
+    const uint32_t v_hi = base + 2 * PBUF_BYTES + buf * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
+    if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this buffer
+    if (tid == 0) {                                                        // V chunk i: [64 keys][64 d], hi and lo
+      const uint32_t bv = buf ? bar_v1 : bar_v0;
+      mbar_expect_tx(bv, 2 * BOX_BYTES);
+      tma_load_2d(v_hi, &tmV, bv, p.v_col + h * D, vrow0 + i * KC);
+      tma_load_2d(v_lo, &tmV, bv, p.v_kp + p.v_col + h * D, vrow0 + i * KC);
+    }
+    {
+      float s[PW];
+      const int kbase = i * KC + PW * part;
+      tmem_ld16(t_row + kbase, s);
+#pragma unroll
+      for (int u = 0; u < PW; ++u) {
+        const float e = (kbase + u < p.Lk) ? exp2f((s[u] - rmax) * sl2) : 0.f;
+        s[u] = e;
+        rsum += e;
+      }
+#pragma unroll
+      for (int j = 0; j < PW / 8; ++j) {
+        uint4 hi, lo;
+        split8(s + 8 * j, hi, lo);
+        const uint32_t off = swz(row, (PW / 8) * part + j);
+        *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
+        *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
+      }
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(buf ? bar_v1 : bar_v0, (i >> 1) & 1);
+      tc_fence_after();
+      const int valid = min(KC, p.Lk - i * KC);
+      const int ksteps = (valid + 15) / 16;
+      const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo);
+      const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
+      // P: K-major, +32 B per 16-key step; V: MN-major, 16 key rows = two 1024 B atoms per step
+      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_lo + 2 * k, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_lo + 128 * k, idesc_o, 1u);
+      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_hi + 128 * k, idesc_o, 1u);
+      umma_commit(buf ? bar_pv1 : bar_pv0);
+    }
+  }
+  {
+    const int c0 = (nchunks + 1) / 2, c1 = nchunks / 2;
+    if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
+    if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
+  }
+  tc_fence_after();
+  xsum[part * BM + row] = rsum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
+  const float inv = 1.0f / tot;
+  {
+    constexpr int OW = D / NPART;
+    float o[OW];
+    tmem_ld16(t_row + O_COL + OW * part, o);
+    const int grow = q0 + row;
+    if (grow < p.Lq) {
+#pragma unroll
+      for (int u = 0; u < OW; ++u) o[u] *= inv;
+      if (p.O) {
+        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
+#pragma unroll
+        for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+      }
+      if (p.split_out) {
+        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
+#pragma unroll
+        for (int j = 0; j < OW / 8; ++j) {
+          uint4 hi, lo;
+          split8(o + 8 * j, hi, lo);
+          *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
+          *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 }  // namespace atc
 }  // namespace ec
 
@@ -403,4 +623,49 @@ extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, f
   dim3 grid(cdiv(Lq, atc::BM), H, B);
   atc::attention_tc_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("ec_attention_tc");
+}
+
+/* Q2 / K2 / V2: split-fp16 buffers [rows, 2*kp] (hi | lo); head h of Q lives in columns q_col + 64 h of each
+ * half, rows b * q_rows + i; likewise K, V (k_rows rows per batch element).  The three may be one buffer. */
+extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
+                                     const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
+                                     int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H, int Lq,
+                                     int Lk, int ldo, long long so, float scale, void* split_out, int split_kp,
+                                     void* stream) {
+  EC_REQUIRE(Q2 && K2 && V2 && (O || split_out), "ec_attention_tc_split: null pointer");
+  EC_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, "ec_attention_tc_split: bad shape");
+  EC_REQUIRE(q_kp % 64 == 0 && k_kp % 64 == 0 && v_kp % 64 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0,
+             "ec_attention_tc_split: halves must be multiples of 64 columns, head offsets multiples of 8");
+  const int LKP = (Lk + 15) / 16 * 16;
+  if (LKP > atc::MAX_LKP) {
+    set_error("ec_attention_tc_split: %d keys exceed the %d S columns that fit in TMEM", Lk, atc::MAX_LKP);
+    return EC_ERR_UNSUPPORTED;
+  }
+  EC_REQUIRE(!split_out || (split_kp == H * atc::D && (((uintptr_t)split_out) & 15) == 0),
+             "ec_attention_tc_split: split_out needs split_kp == H*64 and 16-byte alignment");
+  EC_REQUIRE(!O || (aligned16(O) && ldo % 4 == 0 && so % 4 == 0), "ec_attention_tc_split: O must be 16-byte aligned");
+  if (B == 0 || Lq == 0) return EC_OK;
+  EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc_split: grid too large");
+  const int NKB = (LKP + 63) / 64;
+  const int kq = atc::Q_BYTES + 2 * NKB * atc::BOX_BYTES;
+  const int data_bytes = kq > atc::REUSE_BYTES ? kq : atc::REUSE_BYTES;
+  const int smem = data_bytes + atc::MISC_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = tc::get_tensor_map(Q2, q_total_rows, q_kp, 64, &tmQ);
+  if (rc) return rc;
+  rc = tc::get_tensor_map(K2, k_total_rows, k_kp, 64, &tmK);
+  if (rc) return rc;
+  rc = tc::get_tensor_map(V2, v_total_rows, v_kp, 64, &tmV);
+  if (rc) return rc;
+  atc::ParamsT p{O, B, H, Lq, Lk, LKP, NKB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
+                 q_kp, k_kp, v_kp, q_rows, k_rows};
+  dim3 grid(cdiv(Lq, atc::BM), H, B);
+  atc::attention_tc_tma_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("ec_attention_tc_split");
 }

@@ -478,7 +478,7 @@ struct MapKeyHash {
   }
 };
 
-static int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {
+int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   std::lock_guard<std::mutex> lock(mu);

@@ -85,6 +85,7 @@ def gemm(a, b, out=None, b_kmajor=True, bias=None, act=ACT_NONE, colscale=None, 
 # the default uses the split-fp16 tcgen05 GEMM wherever the shape fills a 128x128 tile reasonably.
 TENSOR_CORES = os.environ.get("EDGECAPE_TC", "1") != "0"
 ATTENTION_TC = os.environ.get("EDGECAPE_ATTN_TC", "1") != "0"     # tcgen05 attention for head dim 64
+ATTENTION_TMA = os.environ.get("EDGECAPE_ATTN_TMA", "1") != "0"   # TMA-fed variant on pre-split QKV (ViT)
 TC_MIN_M, TC_MIN_N, TC_MIN_K = 64, 32, 32
 _SPLIT_WEIGHTS = {}
 
@@ -321,6 +322,33 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, s
     _lib.call("ec_attention", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
               v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale),
               _p(key_mask), _p(bias), sp_ptr, E if sp is not None else 0, _stream())
+    return sp if split == "only" else ((out, sp) if split == "also" else out)
+
+
+def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only"):
+    """Self-attention over a packed split-fp16 QKV operand (the split output of the QKV GEMM):
+    qkv2 rows = B*N tokens, columns [q | k | v] of C = nheads*64 each per half.  TMA-fed tcgen05 kernel."""
+    C = qkv2.K // 3
+    D = C // nheads
+    assert D == 64 and qkv2.rows == B * N and qkv2.Kp == qkv2.K and N <= 448
+    dev = qkv2.data.device
+    ldo = so_ = 0
+    if split != "only":
+        if out is None:
+            out = empty(B, N, C, device=dev)
+        ldo, so_ = out.stride(1), out.stride(0)
+    else:
+        out = None
+    sp, sp_ptr = None, None
+    if split != "no":
+        sp = SplitOperand(empty(B * N, 2 * C, dtype=torch.float16, device=dev), B * N, C, C, 1.0)
+        sp_ptr = sp.data.data_ptr()
+    if scale is None:
+        scale = D ** -0.5
+    ptr = qkv2.data.data_ptr()
+    _lib.call("ec_attention_tc_split", ptr, qkv2.rows, qkv2.Kp, 0, N, ptr, qkv2.rows, qkv2.Kp, C, ptr, qkv2.rows,
+              qkv2.Kp, 2 * C, N, _p(out), B, nheads, N, N, ldo, so_, float(scale) / qkv2.scale ** 2, sp_ptr,
+              C if sp is not None else 0, _stream())
     return sp if split == "only" else ((out, sp) if split == "also" else out)
 
 

@@ -86,11 +86,17 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
         if ops.TENSOR_CORES and C % 64 == 0 and Btot * N >= ops.TC_MIN_M:
             # tensor-core path: every GEMM input is produced directly in split-fp16 form by the kernel
             # before it (LayerNorm, attention, GELU epilogue); only the residual stream t stays fp32
+            packed_attn = ops.ATTENTION_TC and ops.ATTENTION_TMA and C // H == 64 and N <= 448 and (3 * C) % 64 == 0
             for i in range(self.depth):
                 blk = getattr(self.blocks, str(i))
                 y2 = ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, split="only")
-                ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
-                a2 = ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, split="only")
+                if packed_attn:
+                    # the QKV GEMM writes q, k, v already split; the attention kernel TMA-loads them
+                    _, qkv2 = ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, split_out=True, fp32_out=False)
+                    a2 = ops.attention_packed_split(qkv2, Btot, N, H)
+                else:
+                    ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
+                    a2 = ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, split="only")
                 ops.linear(a2, blk.attn.proj.weight, blk.attn.proj.bias, colscale=blk.ls1.gamma, residual=t2, out=t2)
                 y2 = ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, split="only")
                 _, h2 = ops.linear(y2, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, split_out=True,

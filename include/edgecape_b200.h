@@ -138,6 +138,17 @@ int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, in
                     long long sv, long long so, float scale, void* split_out, int split_kp,
                     void* stream);
 
+/* TMA-fed form of ec_attention_tc: Q, K, V are already split-fp16 buffers [rows, 2*kp] (hi | lo halves),
+ * e.g. the split output of the QKV GEMM (one buffer, q_col = 0, k_col = C, v_col = 2C).  Head h of Q lives in
+ * columns q_col + 64 h of each half and rows b * q_rows + i; K / V likewise with k_rows rows per batch
+ * element.  Nothing is staged by hand: 64 x 64 boxes are loaded by TMA, V is consumed as an MN-major UMMA
+ * operand.  Same output contract (O fp32 and / or split_out). */
+int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
+                          const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
+                          int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H,
+                          int Lq, int Lk, int ldo, long long so, float scale, void* split_out,
+                          int split_kp, void* stream);
+
 /* bias[b,h,i,j] = W1 relu(W0 hops[:,b,i,j] + b0) + b1 with hops = attn_adj [n_hops, B, K, K]:
  * the Graphormer-style structural bias MLP (utils/bias_attn.py:82-83,188-191). */
 int ec_hop_bias(const float* attn_adj, const float* w0, const float* b0, const float* w1,

@@ -53,8 +53,57 @@ def bench(B, H, L, iters=20):
         print(f"bench attention B{B} H{H} L{L} {'tcgen05' if tc else 'simt'}: {ms:.3f} ms = {fl / ms / 1e9:.1f} algorithmic TFLOP/s", flush=True)
 
 
+def check_tma(B, N, H, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    C = H * 64
+    qkv = torch.randn(B * N, 3 * C, generator=g)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].double().view(B, N, H, 64).transpose(1, 2) for i in range(3))
+    want = (((q / 8.0) @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(B, N, C).float()
+    D = torch.device("cuda")
+    got = ops.attention_packed_split(ops.split_f16(qkv.to(D)), B, N, H, split="no").cpu()
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    print(f"attn_tma B{B} N{N} H{H}: rel err {err:.3e} nan={torch.isnan(got).any().item()} got={got[0, 0, :3].tolist()} "
+          f"want={want[0, 0, :3].tolist()}", flush=True)
+    if err > 1e-3:
+        mean_v = v.float().mean(2)[0, 0, :3]
+        print("   mean of V =", mean_v.tolist(), " (a softmax-less average would give this)")
+        for r in (0, 1, 8, 63, 64, 127):
+            if r < N:
+                best = (want[0] - got[0, r][None]).abs().sum(1).argmin().item()
+                print(f"   got row {r} closest to want row {best}")
+        # which output columns are right?
+        cerr = (got - want).abs().amax(dim=(0, 1))[:64]
+        print("   per-column max err (head 0):", [round(float(x), 3) for x in cerr.tolist()])
+
+
+def bench_tma(B, H, N, iters=20):
+    D = torch.device("cuda")
+    C = H * 64
+    qkv2 = ops.split_f16(torch.randn(B * N, 3 * C, device=D))
+    for _ in range(3):
+        ops.attention_packed_split(qkv2, B, N, H)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        ops.attention_packed_split(qkv2, B, N, H)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    print(f"bench attention TMA-fed B{B} H{H} L{N}: {ms:.3f} ms = {4.0 * B * H * N * N * 64 / ms / 1e9:.1f} algorithmic TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
+    if st == "tma":
+        check_tma(1, 64, 1)
+        check_tma(1, 128, 1)
+        check_tma(2, 325, 12)
+        check_tma(1, 448, 2)
+        check_tma(3, 17, 2)
+        bench_tma(32, 12, 325)
+        bench(32, 12, 325)
+        sys.exit(0)
     if st == "tiny":
         check(1, 1, 128, 64)
     elif st == "two":

@@ -212,6 +212,31 @@ def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv,
         _write_split(split_out, split_kp, o.reshape(B * Lq, H * D))
 
 
+def ec_attention_tc_split(Q2, q_total, q_kp, q_col, q_rows, K2, k_total, k_kp, k_col, V2, v_total, v_kp, v_col, k_rows,
+                          O, B, H, Lq, Lk, ldo, so, scale, split_out, split_kp, stream):
+    D = 64
+
+    def grab(ptr, total, kp, col, rows_per_b, L):
+        a = arr(ptr, (total, 2 * kp), dtype=np.float16).astype(np.float32)
+        hi = np.stack([a[b * rows_per_b:b * rows_per_b + L, col:col + H * D] for b in range(B)])
+        lo = np.stack([a[b * rows_per_b:b * rows_per_b + L, kp + col:kp + col + H * D] for b in range(B)])
+        f = lambda x: x.reshape(B, L, H, D).transpose(0, 2, 1, 3)
+        return f(hi), f(lo)
+
+    (qh, ql), (kh, kl), (vh, vl) = grab(Q2, q_total, q_kp, q_col, q_rows, Lq), grab(K2, k_total, k_kp, k_col, k_rows, Lk), \
+        grab(V2, v_total, v_kp, v_col, k_rows, Lk)
+    kt = lambda a: a.transpose(0, 1, 3, 2)
+    s = (ql @ kt(kh) + qh @ kt(kl) + qh @ kt(kh)) * np.float32(scale)
+    p = np.exp2((s - s.max(-1, keepdims=True)) * np.float32(1.4426950408889634)).astype(np.float32)
+    ph, pl = _h2(p)
+    o = (pl @ vh + ph @ vl + ph @ vh) / p.sum(-1, keepdims=True)
+    o = np.ascontiguousarray(o.transpose(0, 2, 1, 3)).astype(np.float32)
+    if O:
+        arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o
+    if split_out:
+        _write_split(split_out, split_kp, o.reshape(B * Lq, H * D))
+
+
 def ec_hop_bias(attn_adj, w0, b0, w1, b1, bias, B, K, n_hops, hidden, H, stream):
     hops = T(arr(attn_adj, (n_hops, B, K, K))).permute(1, 2, 3, 0)
     y = F.linear(F.relu(F.linear(hops, T(arr(w0, (hidden, n_hops))), T(arr(b0, (hidden,))))),

@@ -469,6 +469,20 @@ def test_attention_tc_matches_fp32_attention(B, H, Lq, Lk, monkeypatch):
     close(got, ref, tol=5e-6, what="tc vs simt attention")
 
 
+@pytest.mark.parametrize("B,N,H", [(2, 325, 12), (3, 257, 6), (1, 64, 1), (2, 130, 4), (1, 448, 2), (4, 17, 2)])
+def test_attention_tma_on_split_qkv(B, N, H, monkeypatch):
+    """TMA-fed tcgen05 attention on the split-fp16 output of the QKV GEMM (MN-major V operand)."""
+    C = H * 64
+    qkv = rnd(B * N, 3 * C, seed=11)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].double().view(B, N, H, 64).transpose(1, 2) for i in range(3))
+    want = (((q / 8.0) @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(B, N, C).float()
+    D = dev()
+    qkv2 = ops.split_f16(qkv.to(D))
+    got, sp = ops.attention_packed_split(qkv2, B, N, H, split="also")
+    close(got, want, tol=5e-6, what=f"attention_tma {B},{N},{H}")
+    close(sp.data[:, :C].float() + sp.data[:, C:].float(), want.reshape(B * N, C), tol=5e-6, what="attention_tma split")
+
+
 def test_attention_tc_on_packed_qkv_views(monkeypatch):
     monkeypatch.setattr(ops, "TENSOR_CORES", True)
     monkeypatch.setattr(ops, "ATTENTION_TC", True)
