@@ -413,10 +413,11 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const int data_bytes = max(Q_BYTES + 2 * p.NKB * BOX_BYTES, REUSE_BYTES);
+  const int nchunks = (p.Lk + KC - 1) / KC;
+  const int data_bytes = max(Q_BYTES + 2 * p.NKB * BOX_BYTES, 2 * PBUF_BYTES + nchunks * VBUF_BYTES);
   const uint32_t misc = base + data_bytes;
-  const uint32_t bar_qk = misc, bar_s = misc + 8, bar_pv0 = misc + 16, bar_pv1 = misc + 24, bar_v0 = misc + 32,
-                 bar_v1 = misc + 40, tmem_slot = misc + 48;
+  const uint32_t bar_qk = misc, bar_s = misc + 8, bar_pv0 = misc + 16, bar_pv1 = misc + 24, bar_v = misc + 32,
+                 tmem_slot = misc + 40;   // bar_v: all V chunks
   float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;
 
@@ -428,7 +429,7 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (tid == 0) {
     mbar_init(bar_qk, 1); mbar_init(bar_s, 1);
     mbar_init(bar_pv0, 1); mbar_init(bar_pv1, 1);
-    mbar_init(bar_v0, 1); mbar_init(bar_v1, 1);
+    mbar_init(bar_v, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // Q tile (2 boxes) and all keys (NKB boxes), hi and lo halves
     mbar_expect_tx(bar_qk, (uint32_t)((2 + p.NKB) * 2 * BOX_BYTES));
@@ -472,6 +473,17 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
   mbar_wait(bar_s, 0);
   tc_fence_after();
+  // Q / K shared memory is dead once S is complete: every V chunk ([64 keys][64 d], hi and lo) is loaded now, behind
+  // the P double buffer, so its latency hides under the row-max pass
+  const int vrow0 = b * p.k_rows;
+  if (tid == 0) {
+    mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
+    for (int i = 0; i < nchunks; ++i) {
+      const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES;
+      tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, vrow0 + i * KC);
+      tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, vrow0 + i * KC);
+    }
+  }
 
   // ------------------------------------------------------------------ row max of scale * S
   const int row = quarter * 32 + lane;
@@ -493,21 +505,13 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const float sl2 = p.scale * 1.4426950408889634f;     // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
 
   // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
-  const int nchunks = (p.Lk + KC - 1) / KC;
   const uint32_t idesc_o = make_idesc_bmn(D);
-  const int vrow0 = b * p.k_rows;
   float rsum = 0.f;
   for (int i = 0; i < nchunks; ++i) {
     const int buf = i & 1;
     const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
-    const uint32_t v_hi = base + 2 * PBUF_BYTES + buf * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
-    if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this buffer
-    if (tid == 0) {                                                        // V chunk i: [64 keys][64 d], hi and lo
-      const uint32_t bv = buf ? bar_v1 : bar_v0;
-      mbar_expect_tx(bv, 2 * BOX_BYTES);
-      tma_load_2d(v_hi, &tmV, bv, p.v_col + h * D, vrow0 + i * KC);
-      tma_load_2d(v_lo, &tmV, bv, p.v_kp + p.v_col + h * D, vrow0 + i * KC);
-    }
+    const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
+    if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this P buffer
     {
       float s[PW];
       const int kbase = i * KC + PW * part;
@@ -531,7 +535,7 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(buf ? bar_v1 : bar_v0, (i >> 1) & 1);
+      if (i == 0) mbar_wait(bar_v, 0);
       tc_fence_after();
       const int valid = min(KC, p.Lk - i * KC);
       const int ksteps = (valid + 15) / 16;
@@ -648,12 +652,13 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc_split: grid too large");
   const int NKB = (LKP + 63) / 64;
   const int kq = atc::Q_BYTES + 2 * NKB * atc::BOX_BYTES;
-  const int data_bytes = kq > atc::REUSE_BYTES ? kq : atc::REUSE_BYTES;
+  const int pv = 2 * atc::PBUF_BYTES + ((Lk + atc::KC - 1) / atc::KC) * atc::VBUF_BYTES;
+  const int data_bytes = kq > pv ? kq : pv;
   const int smem = data_bytes + atc::MISC_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
+                                 2 * atc::PBUF_BYTES + 7 * atc::VBUF_BYTES + atc::MISC_BYTES + 1024));
     attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
