@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(256) gcn_fill_kernel(const float* __restrict__
 
 // Fused aggregate for the tensor-core GCN: one pass produces the GEMM A operand
 //   Z[b,w,:] = [ a0[w] X[b,w,:] | sum_v A1[b,w,v] X[b,v,:] | a0[w] | rowsum(A1[b,w,:]) | 0 ... ]
-// directly in split-fp16 form Z2 [B*K, 2*Kp] (hi | lo).  CTA = (16 rows of one sample); the 16 x K block of
+// directly in split-fp16 form Z2 [B*K, 2*Kp] (hi | lo).  CTA = (8 rows of one sample); the 8 x K block of
 // A1 sits in shared memory and is read as float4 broadcasts, X rows stream through coalesced loads.
-constexpr int GA_ROWS = 16;
-__global__ void __launch_bounds__(256) gcn_aggregate_split_kernel(const float* __restrict__ X,
+constexpr int GA_ROWS = 8;     // rows of one sample per CTA: 13 x B CTAs at K = 100 (several co-resident per SM)
+__global__ void __launch_bounds__(256, 3) gcn_aggregate_split_kernel(const float* __restrict__ X,
                                                                   const float* __restrict__ adj,
                                                                   __half* __restrict__ Z2, int K, int d, int Kp) {
   extern __shared__ float a1s[];                 // [GA_ROWS][KP4] (KP4 = K rounded up to 4, zero padded)
@@ -173,17 +173,23 @@ __global__ void __launch_bounds__(256) gcn_aggregate_split_kernel(const float* _
     float acc[GA_ROWS];
 #pragma unroll
     for (int r = 0; r < GA_ROWS; ++r) acc[r] = 0.f;
-    for (int v = 0; v < KP4; v += 4) {
-      float x[4];
+    // 16 X rows in flight per thread before the FMAs (the loop is latency bound otherwise)
+    for (int v0 = 0; v0 < KP4; v0 += 16) {
+      float x[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = (v + u < K) ? __ldg(Xb + (long long)(v + u) * d + c) : 0.f;
+      for (int u = 0; u < 16; ++u) x[u] = (v0 + u < K) ? __ldg(Xb + (long long)(v0 + u) * d + c) : 0.f;
 #pragma unroll
-      for (int r = 0; r < GA_ROWS; ++r) {
-        const float4 a = *reinterpret_cast<const float4*>(&a1s[r * KP4 + v]);
-        acc[r] = fmaf(a.x, x[0], acc[r]);
-        acc[r] = fmaf(a.y, x[1], acc[r]);
-        acc[r] = fmaf(a.z, x[2], acc[r]);
-        acc[r] = fmaf(a.w, x[3], acc[r]);
+      for (int q = 0; q < 4; ++q) {
+        const int v = v0 + 4 * q;
+        if (v >= KP4) break;
+#pragma unroll
+        for (int r = 0; r < GA_ROWS; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(&a1s[r * KP4 + v]);
+          acc[r] = fmaf(a.x, x[4 * q + 0], acc[r]);
+          acc[r] = fmaf(a.y, x[4 * q + 1], acc[r]);
+          acc[r] = fmaf(a.z, x[4 * q + 2], acc[r]);
+          acc[r] = fmaf(a.w, x[4 * q + 3], acc[r]);
+        }
       }
     }
 #pragma unroll

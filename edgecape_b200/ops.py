@@ -436,7 +436,7 @@ def gcn_pack_weights(W, bias):
 
 def gcn_tc_ok(B, K):
     """True when gcn() takes the tensor-core route (and can therefore hand back a split result)."""
-    return TENSOR_CORES and B * K >= TC_MIN_M and ((K + 3) // 4 * 4) * 64 <= 48 * 1024
+    return TENSOR_CORES and B * K >= TC_MIN_M and ((K + 3) // 4 * 4) * 32 <= 48 * 1024
 
 
 def gcn(x, adj, Wp, out=None, split="no"):

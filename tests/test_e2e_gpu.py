@@ -99,3 +99,32 @@ def test_detector_matches_oracle_on_fresh_episode():
             "argmax", "initial_proposals", "decoder_hs", "output", "preds", "points", "skeleton"]
     wantd = {k: _np(want[k]) for k in keys}
     _compare("fresh_tiny_3shot", got, wantd, {})
+
+
+def test_pck_agrees_with_reference(golden_dir):
+    """North-star: PCK@0.2 within +-0.1 of the reference.  GT := reference prediction + Gaussian noise on a seeded
+    episode; the PCK of this implementation (device counters, ec_pck_accumulate) must match the PCK of the reference's
+    own golden prediction (numpy statement of mmpose keypoint_pck_accuracy) at every threshold."""
+    from edgecape_b200 import ops
+    from edgecape_b200.parallel import PCK_THRESHOLDS, new_counters, summarize_pck
+    name = "c2_vitb_256_k100"
+    golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    cfg, data, wseed = build_case(name)
+    model = _build(cfg, wseed)
+    res = model(return_loss=False, **data)
+    ref = golden["preds"][:, :, :2].astype(np.float32)
+    rng = np.random.default_rng(3)
+    gt = ref + rng.normal(0, 256 * 0.12, ref.shape).astype(np.float32)
+    B, K, _ = ref.shape
+    valid = (data["target_weight_s"][0].reshape(B, K) > 0).numpy()
+    norm = np.full((B, 2), 256.0, dtype=np.float32)
+    dev = torch.device("cuda", 0)
+    c = new_counters(dev)
+    ops.pck_accumulate_(c, torch.from_numpy(res["preds"][:, :, :2].copy()).to(dev), torch.from_numpy(gt).to(dev),
+                        torch.from_numpy(valid.astype(np.uint8)).to(dev), torch.from_numpy(norm).to(dev),
+                        torch.tensor(PCK_THRESHOLDS, dtype=torch.float32, device=dev))
+    ours = summarize_pck(c)
+    for t in PCK_THRESHOLDS:
+        want = np.mean([((np.linalg.norm((ref[b] - gt[b]) / norm[b], axis=-1) < t)[valid[b]]).mean() for b in range(B)])
+        assert abs(ours[f"PCK@{t}"] - want) <= 0.01, (t, ours, want)
+    assert 0.2 < ours["PCK@0.2"] < 0.99          # the noise level makes the metric informative
