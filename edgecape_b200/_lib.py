@@ -39,7 +39,7 @@ SIGNATURES = {
     "ec_attention": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_ll, c_ll, c_ll, c_ll, c_f, c_fp, c_fp, c_fp, c_int, c_fp]),
     "ec_attention_tc": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_int, c_ll, c_ll, c_ll, c_ll, c_f, c_fp, c_int, c_fp]),
+                                c_int, c_ll, c_ll, c_ll, c_ll, c_f, c_fp, c_fp, c_fp, c_int, c_fp]),
     "ec_attention_tc_split": (c_int, [c_fp, c_int, c_int, c_int, c_int, c_fp, c_int, c_int, c_int, c_fp, c_int, c_int,
                                       c_int, c_int, c_fp, c_int, c_int, c_int, c_int, c_int, c_ll, c_f, c_fp, c_int,
                                       c_fp]),

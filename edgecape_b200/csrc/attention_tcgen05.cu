@@ -32,7 +32,7 @@ constexpr int Q_BYTES = 2 * BM * 128;   // Q_hi + Q_lo
 constexpr int PBUF_BYTES = 2 * BM * 128;      // P_hi + P_lo of one chunk (32 KB)
 constexpr int VBUF_BYTES = 2 * D * 128;       // V_hi^T + V_lo^T of one chunk (16 KB)
 constexpr int REUSE_BYTES = 2 * PBUF_BYTES + 2 * VBUF_BYTES;   // 96 KB, aliases Q and K after S is done
-constexpr int MISC_BYTES = 64 + 2 * NPART * BM * 4;   // barriers + tmem slot, row max / row sum exchange
+constexpr int MISC_BYTES = 64 + 2 * NPART * BM * 4 + 512;   // barriers + tmem slot, row max / row sum exchange, key mask
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -122,6 +122,9 @@ struct Params {
   float scale;
   __half* split_out;
   int split_kp;
+  int dv;                      // valid head dim (32 or 64); the tiles are zero padded to 64
+  const uint8_t* key_mask;     // [B, Lk], 1 = ignore key, or NULL
+  const float* bias;           // [B, H, Lq, Lk] additive, or NULL
 };
 
 __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   const uint32_t bar_s = misc, bar_pv0 = misc + 8, bar_pv1 = misc + 16, tmem_slot = misc + 24;
   float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;                                    // [NPART][BM]
+  uint8_t* msk = reinterpret_cast<uint8_t*>(xsum + NPART * BM);       // [MAX_LKP] key-padding mask of this batch row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, part = warp >> 2;
@@ -152,11 +156,12 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   // ------------------------------------------------------------------ stage Q (scaled) and K
   const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + p.LKP * 128;
   {
-    const float* Qb = p.Q + (long long)b * p.sq + h * D;
+    for (int j = tid; j < p.LKP; j += THREADS) msk[j] = (j < p.Lk && p.key_mask) ? p.key_mask[(long long)b * p.Lk + j] : 0;
+    const float* Qb = p.Q + (long long)b * p.sq + h * p.dv;
     for (int it = tid; it < BM * 8; it += THREADS) {
       const int row = it >> 3, c = it & 7;
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (q0 + row < p.Lq) {
+      if (q0 + row < p.Lq && c * 8 < p.dv) {
         const float4* src = reinterpret_cast<const float4*>(Qb + (long long)(q0 + row) * p.ldq + c * 8);
         const float4 a = __ldg(src), bb = __ldg(src + 1);
         v[0] = a.x * p.scale; v[1] = a.y * p.scale; v[2] = a.z * p.scale; v[3] = a.w * p.scale;
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
       *reinterpret_cast<uint4*>(gbase + (q_hi - base) + off) = hi;
       *reinterpret_cast<uint4*>(gbase + (q_lo - base) + off) = lo;
     }
-    const float* Kb = p.K + (long long)b * p.sk + h * D;
+    const float* Kb = p.K + (long long)b * p.sk + h * p.dv;
     // 4 items (= 8 float4 loads) in flight per thread before any conversion: hides the global latency
     for (int it0 = tid; it0 < p.LKP * 8; it0 += 4 * THREADS) {
       float4 ra[4], rb[4];
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
         const int row = it >> 3, c = it & 7;
         ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         rb[u] = ra[u];
-        if (it < p.LKP * 8 && row < p.Lk) {
+        if (it < p.LKP * 8 && row < p.Lk && c * 8 < p.dv) {
           const float4* src = reinterpret_cast<const float4*>(Kb + (long long)row * p.ldk + c * 8);
           ra[u] = __ldg(src);
           rb[u] = __ldg(src + 1);
@@ -228,22 +233,27 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   const int row = quarter * 32 + lane;                 // TMEM lane == row of the query tile
   const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
   const int nchunk32 = (p.Lk + 31) / 32;
+  const float* bias_row = (p.bias && q0 + row < p.Lq)
+                              ? p.bias + (((long long)b * p.H + h) * p.Lq + (q0 + row)) * p.Lk : nullptr;
   float mymax = -INFINITY;
   for (int j = part; j < nchunk32; j += NPART) {
     float s[32];
     tmem_ld32(t_row + j * 32, s);
 #pragma unroll
-    for (int u = 0; u < 32; ++u)
-      if (j * 32 + u < p.Lk) mymax = fmaxf(mymax, s[u]);
+    for (int u = 0; u < 32; ++u) {
+      const int key = j * 32 + u;
+      if (key < p.Lk && !msk[key]) mymax = fmaxf(mymax, bias_row ? s[u] + __ldg(bias_row + key) : s[u]);
+    }
   }
   xmax[part * BM + row] = mymax;
   __syncthreads();                                     // also: every warp is done with Q / K shared memory
   float rmax = xmax[row];
 #pragma unroll
   for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+  if (rmax == -INFINITY) rmax = 0.f;                   // fully masked row: every p below is 0
 
   // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
-  const float* Vb = p.V + (long long)b * p.sv + h * D;
+  const float* Vb = p.V + (long long)b * p.sv + h * p.dv;
   const int nchunks = (p.Lk + KC - 1) / KC;
   const uint32_t idesc_o = make_idesc(D);
   float rsum = 0.f;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
       const int key = chunk * KC + kl;
       va[w] = make_float4(0.f, 0.f, 0.f, 0.f);
       vb[w] = va[w];
-      if (key < p.Lk) {
+      if (key < p.Lk && dc * 8 < p.dv) {
         const float4* src = reinterpret_cast<const float4*>(Vb + (long long)key * p.ldv + dc * 8);
         va[w] = __ldg(src);
         vb[w] = __ldg(src + 1);
@@ -295,7 +305,10 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
       tmem_ld16(t_row + kbase, s);
 #pragma unroll
       for (int u = 0; u < PW; ++u) {
-        const float e = (kbase + u < p.Lk) ? exp2f((s[u] - rmax) * 1.4426950408889634f) : 0.f;
+        const int key = kbase + u;
+        const bool ok = key < p.Lk && !msk[key];
+        const float sv_ = (ok && bias_row) ? s[u] + __ldg(bias_row + key) : s[u];
+        const float e = ok ? exp2f((sv_ - rmax) * 1.4426950408889634f) : 0.f;
         s[u] = e;
         rsum += e;
       }
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   float tot = 0.f;
 #pragma unroll
   for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
-  const float inv = 1.0f / tot;
+  const float inv = tot > 0.f ? 1.0f / tot : 0.f;      // fully masked row -> 0 (as the fp32 kernel)
 
   // ------------------------------------------------------------------ epilogue: O / rowsum
   {
@@ -342,16 +355,16 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
     float o[OW];
     tmem_ld16(t_row + O_COL + OW * part, o);
     const int grow = q0 + row;
-    if (grow < p.Lq) {
+    if (grow < p.Lq && OW * part < p.dv) {
 #pragma unroll
       for (int u = 0; u < OW; ++u) o[u] *= inv;
       if (p.O) {
-        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
+        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * p.dv + OW * part);
 #pragma unroll
         for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
       }
       if (p.split_out) {
-        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
+        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * p.dv + OW * part;
 #pragma unroll
         for (int j = 0; j < OW / 8; ++j) {
           uint4 hi, lo;
@@ -599,9 +612,10 @@ using namespace ec;
 
 extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq, int Lk,
                                int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk, long long sv,
-                               long long so, float scale, void* split_out, int split_kp, void* stream) {
+                               long long so, float scale, const uint8_t* key_mask, const float* bias, void* split_out,
+                               int split_kp, void* stream) {
   EC_REQUIRE(Q && K && V && (O || split_out), "ec_attention_tc: null pointer");
-  EC_REQUIRE(D == atc::D, "ec_attention_tc: head dim must be 64");
+  EC_REQUIRE(D == 64 || D == 32, "ec_attention_tc: head dim must be 32 or 64");
   EC_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, "ec_attention_tc: bad shape");
   const int LKP = (Lk + 15) / 16 * 16;
   if (LKP > atc::MAX_LKP) {
@@ -611,8 +625,8 @@ extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, f
   EC_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && (!O || aligned16(O)) && ldq % 4 == 0 && ldk % 4 == 0 &&
                  ldv % 4 == 0 && ldo % 4 == 0 && sq % 4 == 0 && sk % 4 == 0 && sv % 4 == 0 && so % 4 == 0,
              "ec_attention_tc: operands must be 16-byte aligned with strides that are multiples of 4");
-  EC_REQUIRE(!split_out || (split_kp == H * D && (((uintptr_t)split_out) & 15) == 0),
-             "ec_attention_tc: split_out needs split_kp == H*D and 16-byte alignment");
+  EC_REQUIRE(!split_out || (split_kp == H * D && split_kp % 64 == 0 && (((uintptr_t)split_out) & 15) == 0),
+             "ec_attention_tc: split_out needs split_kp == H*D (a multiple of 64) and 16-byte alignment");
   if (B == 0 || Lq == 0) return EC_OK;
   EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc: grid too large");
   const int data_bytes = atc::Q_BYTES + 2 * LKP * 128 > atc::REUSE_BYTES ? atc::Q_BYTES + 2 * LKP * 128 : atc::REUSE_BYTES;
@@ -623,7 +637,8 @@ extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, f
                                  atc::Q_BYTES + 2 * atc::MAX_LKP * 128 + atc::MISC_BYTES + 1024));
     attr_set = true;
   }
-  atc::Params p{Q, K, V, O, B, H, Lq, Lk, LKP, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, (__half*)split_out, split_kp};
+  atc::Params p{Q, K, V, O, B, H, Lq, Lk, LKP, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, (__half*)split_out, split_kp,
+                D, key_mask, bias};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
   atc::attention_tc_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("ec_attention_tc");

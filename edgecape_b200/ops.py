@@ -314,10 +314,10 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, s
         assert key_mask.is_contiguous() and tuple(key_mask.shape) == (B, Lk)
     if bias is not None:
         assert bias.is_contiguous() and tuple(bias.shape) == (B, nheads, Lq, Lk)
-    if TENSOR_CORES and ATTENTION_TC and D == 64 and key_mask is None and bias is None and Lk <= 448:
+    if TENSOR_CORES and ATTENTION_TC and D in (32, 64) and Lk <= 448:
         _lib.call("ec_attention_tc", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
-                  v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale), sp_ptr,
-                  E if sp is not None else 0, _stream())
+                  v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale), _p(key_mask), _p(bias),
+                  sp_ptr, E if sp is not None else 0, _stream())
         return sp if split == "only" else ((out, sp) if split == "also" else out)
     _lib.call("ec_attention", _p(q), _p(k), _p(v), _p(out), B, nheads, Lq, Lk, D, q.stride(1), k.stride(1),
               v.stride(1), ldo, q.stride(0), k.stride(0), v.stride(0), so_, float(scale),

@@ -128,15 +128,15 @@ int ec_attention(const float* Q, const float* K, const float* V, float* O, int B
                  long long sv, long long so, float scale, const uint8_t* key_mask,
                  const float* bias, void* split_out, int split_kp, void* stream);
 
-/* Tensor-core attention (tcgen05, sm_100a): same contract as ec_attention without key_mask / bias,
- * head dim 64, Lk <= 448 (the whole [128 x Lk] score block lives in TMEM).  Q, K, V, P are split into
+/* Tensor-core attention (tcgen05, sm_100a): same contract as ec_attention (key_mask / bias included),
+ * head dim 64 or 32 (tiles zero padded to 64), Lk <= 448 (the whole [128 x Lk] score block lives in TMEM).  Q, K, V, P are split into
  * fp16 (hi, lo) pairs in shared memory and both contractions run as 3-product UMMAs with fp32 TMEM
  * accumulation (fp32-grade results).  Used for the DINOv2 block attention and the 8 x 64 cross
  * attentions (encoder_decoder.py:620-631, 638-649). */
 int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, int B, int H, int Lq,
                     int Lk, int D, int ldq, int ldk, int ldv, int ldo, long long sq, long long sk,
-                    long long sv, long long so, float scale, void* split_out, int split_kp,
-                    void* stream);
+                    long long sv, long long so, float scale, const uint8_t* key_mask,
+                    const float* bias, void* split_out, int split_kp, void* stream);
 
 /* TMA-fed form of ec_attention_tc: Q, K, V are already split-fp16 buffers [rows, 2*kp] (hi | lo halves),
  * e.g. the split output of the QKV GEMM (one buffer, q_col = 0, k_col = C, v_col = 2C).  Head h of Q lives in

@@ -194,17 +194,26 @@ def _h2(x):
     return hi, (x - hi).astype(np.float16).astype(np.float32)
 
 
-def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, split_out, split_kp, stream):
-    assert D == 64 and Lk <= 448
+def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, key_mask, bias, split_out,
+                    split_kp, stream):
+    assert D in (32, 64) and Lk <= 448
     q = np.ascontiguousarray(arr(Q, (B, Lq, H, D), (sq, ldq, D, 1)).transpose(0, 2, 1, 3)) * np.float32(scale)
     k = np.ascontiguousarray(arr(K, (B, Lk, H, D), (sk, ldk, D, 1)).transpose(0, 2, 1, 3))
     v = np.ascontiguousarray(arr(V, (B, Lk, H, D), (sv, ldv, D, 1)).transpose(0, 2, 1, 3))
     (qh, ql), (kh, kl), (vh, vl) = _h2(q), _h2(k), _h2(v)
     kt = lambda a: a.transpose(0, 1, 3, 2)
     s = ql @ kt(kh) + qh @ kt(kl) + qh @ kt(kh)
-    p = np.exp2((s - s.max(-1, keepdims=True)) * np.float32(1.4426950408889634)).astype(np.float32)
+    if bias:
+        s = s + arr(bias, (B, H, Lq, Lk))
+    if key_mask:
+        m = arr(key_mask, (B, Lk), dtype=np.uint8).astype(bool)
+        s = np.where(m[:, None, None, :], -np.inf, s)
+    mx = s.max(-1, keepdims=True)
+    mx = np.where(np.isinf(mx), 0.0, mx)
+    p = np.exp2((s - mx) * np.float32(1.4426950408889634)).astype(np.float32)
     ph, pl = _h2(p)
-    o = (pl @ vh + ph @ vl + ph @ vh) / p.sum(-1, keepdims=True)
+    tot = p.sum(-1, keepdims=True)
+    o = (pl @ vh + ph @ vl + ph @ vh) * np.where(tot > 0, 1.0 / np.maximum(tot, 1e-30), 0.0)
     o = np.ascontiguousarray(o.transpose(0, 2, 1, 3)).astype(np.float32)
     if O:
         arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o

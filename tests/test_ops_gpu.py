@@ -469,6 +469,35 @@ def test_attention_tc_matches_fp32_attention(B, H, Lq, Lk, monkeypatch):
     close(got, ref, tol=5e-6, what="tc vs simt attention")
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk,D_", [(2, 8, 424, 424, 32), (3, 8, 100, 100, 32), (2, 8, 100, 324, 64), (2, 4, 130, 200, 32)])
+def test_attention_tc_with_mask_and_bias(B, H, Lq, Lk, D_, monkeypatch):
+    """tcgen05 attention with key-padding mask and additive per-head bias, head dims 32 and 64 (encoder / biased decoder
+    self-attention shapes), vs the fp64 statement and the fp32 SIMT kernel; one batch row is fully masked."""
+    monkeypatch.setattr(ops, "TENSOR_CORES", True)
+    monkeypatch.setattr(ops, "ATTENTION_TC", True)
+    E = H * D_
+    q, k, v = rnd(B, Lq, E, seed=1), rnd(B, Lk, E, seed=2), rnd(B, Lk, E, seed=3)
+    bias = rnd(B, H, Lq, Lk, seed=4)
+    mask = torch.zeros(B, Lk, dtype=torch.bool)
+    mask[0, Lk - Lk // 3:] = True
+    mask[0, 3] = True
+    D = dev()
+    for use_bias in (False, True):
+        s = (q.double().view(B, Lq, H, D_).transpose(1, 2) * D_ ** -0.5) @ k.double().view(B, Lk, H, D_).transpose(1, 2).transpose(-1, -2)
+        if use_bias:
+            s = s + bias.double()
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+        want = (s.softmax(-1) @ v.double().view(B, Lk, H, D_).transpose(1, 2)).transpose(1, 2).reshape(B, Lq, E).float()
+        got = ops.attention(q.to(D), k.to(D), v.to(D), H, key_mask=mask.to(torch.uint8).to(D),
+                            bias=bias.to(D) if use_bias else None)
+        close(got, want, tol=5e-6, what=f"attention_tc mask bias={use_bias} D={D_}")
+    # a fully masked batch row gives zeros (as the fp32 kernel), not NaN
+    full = torch.ones(B, Lk, dtype=torch.uint8)
+    full[0] = 0
+    got = ops.attention(q.to(D), k.to(D), v.to(D), H, key_mask=full.to(D))
+    assert torch.isfinite(got).all() and (got[1:] == 0).all()
+
+
 @pytest.mark.parametrize("B,N,H", [(2, 325, 12), (3, 257, 6), (1, 64, 1), (2, 130, 4), (1, 448, 2), (4, 17, 2)])
 def test_attention_tma_on_split_qkv(B, N, H, monkeypatch):
     """TMA-fed tcgen05 attention on the split-fp16 output of the QKV GEMM (MN-major V operand)."""
