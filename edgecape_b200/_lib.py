@@ -28,7 +28,7 @@ SIGNATURES = {
                         c_ll, c_fp, c_int, c_fp, c_fp, c_int, c_ll, c_int, c_fp]),
     "ec_split_f16": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_ll, c_int, c_f, c_fp]),
     "ec_gemm_f16x3": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_ll, c_f, c_fp, c_int, c_fp, c_fp, c_int,
-                              c_int, c_fp, c_int, c_f, c_fp]),
+                              c_int, c_int, c_fp, c_int, c_f, c_fp]),
     "ec_tc_set_tile_n": (c_int, [c_int]),
     "ec_tc_set_debug": (c_int, [c_int]),
     "ec_layernorm": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_f,
@@ -58,7 +58,7 @@ SIGNATURES = {
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),
     "ec_proposal": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "ec_point_update": (c_int, [c_fp, c_fp, c_int, c_fp, c_int, c_fp]),
-    "ec_im2col_patches": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
+    "ec_im2col_patches": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_int, c_fp]),
     "ec_interp_pos_embed": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_d, c_fp]),
     "ec_write_cls": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_fp]),
     "ec_pck_accumulate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_fp]),

@@ -115,12 +115,14 @@ struct TcParams {
   int M, N, num_kb, Kp, ldc, seg_c;
   long long seg_stride_c;
   int vec_c, vec_r;
+  int n_fastest;   // tile order: consecutive tiles walk N first (few N tiles, large A: every A tile is read once)
   int dbg;   // experiment flags (ec_tc_set_debug): 1 = no TMA after the pipeline is primed, 2 = hi*hi only, 4 = no epilogue stores
   float out_scale;
   const float* bias;
   const float* colscale;
   const float* R;
   int ldr, act, res_mode;
+  int res_rows;        // > 0: residual row = row % res_rows (broadcast over a batch of res_rows-row blocks)
   __half* split_out;   // optional [M, 2*split_kp] = [hi | lo] of the result (next GEMM's A operand)
   int split_kp;
   float split_scale;
@@ -225,7 +227,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m0 = (tile % m_tiles) * TM + rank * BM, n0 = (tile / m_tiles) * BN + rank * B_ROWS;
+        const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
+        const int m0 = tm * TM + rank * BM, n0 = tn * BN + rank * B_ROWS;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sb = base + stage * STAGE_BYTES;
@@ -313,7 +316,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tempty_leader0 = TWO ? mapa(tempty_bar(0), 0) : 0u, tempty_leader1 = TWO ? mapa(tempty_bar(1), 0) : 0u;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
       const int acc = t & 1;
-      const int m0 = (tile % m_tiles) * TM + rank * BM, n0 = (tile / m_tiles) * BN;
+      const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
+      const int m0 = tm * TM + rank * BM, n0 = tn * BN;
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -376,7 +380,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int u = 0; u < 4; ++u) y[i][u] *= sv[u];
             if (p.R) {
-              const float* rp = p.R + (long long)row * p.ldr + gcol;
+              const float* rp = p.R + (long long)(p.res_rows > 0 ? row % p.res_rows : row) * p.ldr + gcol;
               float rr[4] = {0.f, 0.f, 0.f, 0.f};
               if (full && p.vec_r) {
                 const float4 r4 = *reinterpret_cast<const float4*>(rp);
@@ -542,7 +546,8 @@ extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int
 extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp, int ldc, int seg_c,
                              long long seg_stride_c, float out_scale,
                              const float* bias, int act, const float* colscale, const float* R, int ldr,
-                             int res_mode, void* split_out, int split_kp, float split_scale, void* stream) {
+                             int res_mode, int res_rows, void* split_out, int split_kp, float split_scale,
+                             void* stream) {
   EC_REQUIRE(A2 && B2 && (C || split_out), "ec_gemm_f16x3: null operand");
   EC_REQUIRE(Kp > 0 && Kp % tc::BK == 0, "ec_gemm_f16x3: Kp must be a positive multiple of 64");
   EC_REQUIRE(aligned16(A2) && aligned16(B2), "ec_gemm_f16x3: split operands must be 16-byte aligned");
@@ -580,8 +585,10 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.vec_c = C && aligned16(C) && (ldc % 4 == 0) && (seg_stride_c % 4 == 0);
   p.vec_r = R && aligned16(R) && (ldr % 4 == 0);
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
-  p.res_mode = res_mode; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
+  p.res_mode = res_mode; p.res_rows = res_rows; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
   p.dbg = ec_tc_debug;
+  // with few N tiles the A operand (activations, up to 128 MB > L2) would be swept once per N tile: walk N first
+  p.n_fastest = cdiv(N, BN) <= 4 ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 512) {
     const int pairs = (int)(pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2);

@@ -1,4 +1,5 @@
 // ViT front-end kernels: patch im2col, bicubic position-table resampling, cls row.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -6,7 +7,7 @@
 namespace ec {
 
 __global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int H, int W, int P,
-                              int h0, int w0, int ldc, long long total) {
+                              int h0, int w0, int ldc, long long total, __half* __restrict__ split_out, int split_kp) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int col = (int)(i % ldc);
@@ -18,7 +19,12 @@ __global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__
     const int c = col / (P * P), iy = (col / P) % P, ix = col % P;
     v = img[((b * 3 + c) * H + (py * P + iy)) * W + (px * P + ix)];
   }
-  cols[i] = v;
+  if (cols) cols[i] = v;
+  if (split_out) {
+    const __half hi = __float2half_rn(v);
+    split_out[r * 2 * split_kp + col] = hi;
+    split_out[r * 2 * split_kp + split_kp + col] = __float2half_rn(v - __half2float(hi));
+  }
 }
 
 __device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
@@ -71,12 +77,14 @@ __global__ void write_cls_kernel(const float* __restrict__ cls, const float* __r
 using namespace ec;
 
 extern "C" int ec_im2col_patches(const float* img, float* cols, int B, int H, int W, int P, int ldc,
-                                 void* stream) {
-  EC_REQUIRE(img && cols && P > 0 && ldc >= 3 * P * P, "ec_im2col_patches: bad arguments");
+                                 void* split_out, int split_kp, void* stream) {
+  EC_REQUIRE(img && (cols || split_out) && P > 0 && ldc >= 3 * P * P, "ec_im2col_patches: bad arguments");
+  EC_REQUIRE(!split_out || (split_kp == ldc && split_kp % 64 == 0), "ec_im2col_patches: split_out needs ldc == split_kp (multiple of 64)");
   const int h0 = H / P, w0 = W / P;
   long long total = (long long)B * h0 * w0 * ldc;
   if (total == 0) return EC_OK;
-  im2col_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, cols, H, W, P, h0, w0, ldc, total);
+  im2col_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, cols, H, W, P, h0, w0, ldc, total,
+                                                                    (__half*)split_out, split_kp);
   return check_launch("ec_im2col_patches");
 }
 

@@ -133,7 +133,7 @@ def split_weight(w):
 
 
 def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
-            split_out=False, fp32_out=True):
+            split_out=False, fp32_out=True, res_rows=0):
     """out = epilogue(A @ B^T) on the tcgen05 tensor cores from two SplitOperands.  `out` may be a
     2-D view or a 3-D [B,S,N] view with B*S == M (batch-strided rows).  With split_out=True also
     returns the SplitOperand of the result (produced by the epilogue)."""
@@ -151,7 +151,7 @@ def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=N
     ldr = 0
     if residual is not None:
         Mr, Nr, ldr, seg_r, _ = _seg(residual, "residual")
-        assert (Mr, Nr) == (M, N) and seg_r == 0, "gemm_tc: residual must be a plain 2-D row view"
+        assert (Mr, Nr) == (res_rows or M, N) and seg_r == 0, "gemm_tc: residual must be a plain 2-D row view"
     else:
         res_mode = RES_NONE
     _chk(bias, "bias")
@@ -163,8 +163,8 @@ def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=N
         so = SplitOperand(buf, M, N, so_kp, 1.0)
         so_ptr = buf.data_ptr()
     _lib.call("ec_gemm_f16x3", _p(a2.data), _p(b2.data), _p(out), M, N, a2.Kp, ldc, seg_c, seg_stride_c,
-              1.0 / (a2.scale * b2.scale), _p(bias), act, _p(colscale), _p(residual), ldr, res_mode, so_ptr, so_kp,
-              1.0, _stream())
+              1.0 / (a2.scale * b2.scale), _p(bias), act, _p(colscale), _p(residual), ldr, res_mode, res_rows, so_ptr,
+              so_kp, 1.0, _stream())
     return (out, so) if split_out else out
 
 
@@ -529,8 +529,27 @@ def im2col_patches(img, P, ldc=None):
     h0, w0 = H // P, W // P
     ldc = ldc or 3 * P * P
     cols = empty(B * h0 * w0, ldc, device=img.device)
-    _lib.call("ec_im2col_patches", _p(img), _p(cols), B, H, W, P, ldc, _stream())
+    _lib.call("ec_im2col_patches", _p(img), _p(cols), B, H, W, P, ldc, None, 0, _stream())
     return cols
+
+
+def im2col_patches_split(images, P):
+    """list of [b,3,H,W] images -> SplitOperand [sum(b)*h0*w0, 2*Kp] of the patch matrix (Kp = 3*P*P rounded to 64)."""
+    H, W = images[0].shape[-2:]
+    h0, w0 = H // P, W // P
+    S = h0 * w0
+    K = 3 * P * P
+    Kp = _kp(K)
+    rows = sum(int(im.shape[0]) for im in images) * S
+    so = SplitOperand(empty(rows, 2 * Kp, dtype=torch.float16, device=images[0].device), rows, K, Kp, 1.0)
+    r = 0
+    for im in images:
+        _chk(im, "img")
+        assert im.is_contiguous() and tuple(im.shape[-2:]) == (H, W)
+        b = int(im.shape[0])
+        _lib.call("ec_im2col_patches", _p(im), None, b, H, W, P, Kp, so.data[r * S:].data_ptr(), Kp, _stream())
+        r += b
+    return so
 
 
 def interp_pos_embed(pos_embed, h0, w0, offset=0.1):

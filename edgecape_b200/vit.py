@@ -68,18 +68,26 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
         dev = images[0].device
         pk = self.packed()
         KP = 3 * P * P
-        cols = ops.empty(Btot * S, KP, device=dev)
-        r = 0
         for im in images:
             assert im.shape[-2:] == (Hh, Ww), "all images of one call must share a resolution"
-            b = int(im.shape[0])
-            ops._lib.call("ec_im2col_patches", im.contiguous().data_ptr(), cols[r * S:].data_ptr(), b, Hh, Ww, P, KP,
-                          ops._stream())
-            r += b
         pos = self._pos(h0, w0)                                           # [1+S, C]
         t = ops.empty(Btot, N, C, device=dev)
-        ops.gemm(cols.view(Btot, S, KP), pk["pe_w"], out=t[:, 1:, :], bias=self["patch_embed.proj.bias"],
-                 residual=pos[1:], res_mode=ops.RES_ADD)
+        if ops.TENSOR_CORES and Btot * S >= ops.TC_MIN_M and C >= ops.TC_MIN_N:
+            # patch embedding on the tensor cores: im2col writes the split-fp16 patch matrix, the GEMM epilogue adds
+            # bias + position embedding (table broadcast over the batch) and scatters past each image's cls row
+            cols2 = ops.im2col_patches_split([im.contiguous() for im in images], P)
+            ops.gemm_tc(cols2, ops.split_weight(pk["pe_w"]), out=t[:, 1:, :], bias=self["patch_embed.proj.bias"],
+                        residual=pos[1:], res_mode=ops.RES_ADD, res_rows=S)
+        else:
+            cols = ops.empty(Btot * S, KP, device=dev)
+            r = 0
+            for im in images:
+                b = int(im.shape[0])
+                ops._lib.call("ec_im2col_patches", im.contiguous().data_ptr(), cols[r * S:].data_ptr(), b, Hh, Ww, P, KP,
+                              None, 0, ops._stream())
+                r += b
+            ops.gemm(cols.view(Btot, S, KP), pk["pe_w"], out=t[:, 1:, :], bias=self["patch_embed.proj.bias"],
+                     residual=pos[1:], res_mode=ops.RES_ADD)
         ops.write_cls_(t, self["cls_token"].reshape(-1), pos[0])
         t2 = t.view(Btot * N, C)
         qkv = ops.empty(Btot, N, 3 * C, device=dev)

@@ -73,12 +73,13 @@ int ec_gemm(const float* A, const float* B, float* C, int M, int N, int K, int l
  * `scale` first (a power of two chosen per weight tensor keeps small weights out of the fp16
  * subnormal range; out_scale undoes it).  If split_out != NULL the epilogue also stores the
  * split form of the result, [M, 2*split_kp], ready to be the next GEMM's A operand.  Row m of C
- * lives at C + (m / seg_c) * seg_stride_c + (m % seg_c) * ldc (seg_c = 0: m * ldc). */
+ * lives at C + (m / seg_c) * seg_stride_c + (m % seg_c) * ldc (seg_c = 0: m * ldc); res_rows > 0 reads
+ * residual row m % res_rows (a [res_rows, N] table broadcast over the batch, e.g. the position embedding). */
 int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int seg, long long seg_stride,
                  int Kp, float scale, void* stream);
 int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp, int ldc,
                   int seg_c, long long seg_stride_c, float out_scale, const float* bias, int act, const float* colscale,
-                  const float* R, int ldr, int res_mode, void* split_out, int split_kp,
+                  const float* R, int ldr, int res_mode, int res_rows, void* split_out, int split_kp,
                   float split_scale, void* stream);
 
 /* tuning knob for ec_gemm_f16x3: 0 = pick the tile width per shape (128x256 tiles for wide, large
@@ -226,9 +227,10 @@ int ec_point_update(const float* bi, const float* delta, int ldd, float* out, in
 /* ------------------------------------------------------------------------------ ViT ops
  * im2col for the stride-P patch embedding (floor semantics): img [B,3,H,W] ->
  * cols [B*h0*w0, ldc] with (c,py,px) ordering = Conv2d weight flattening; columns 3*P*P..ldc-1
- * are zero-filled. */
+ * are zero-filled.  split_out (optional, fp16 [B*h0*w0, 2*split_kp]) receives the split-fp16 form for
+ * ec_gemm_f16x3; cols may then be NULL. */
 int ec_im2col_patches(const float* img, float* cols, int B, int H, int W, int P, int ldc,
-                      void* stream);
+                      void* split_out, int split_kp, void* stream);
 /* bicubic (A=-0.75, align_corners=False, scale_factor=(n+offset)/M) resampling of the M x M
  * patch position table to h0 x w0 (DINOv2 interpolate_pos_encoding); pos_out [1+h0*w0, C]. */
 int ec_interp_pos_embed(const float* pos_embed, float* pos_out, int Mgrid, int h0, int w0, int C,

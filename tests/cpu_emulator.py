@@ -109,7 +109,7 @@ def ec_split_f16(X, X2, M, K, ldx, seg, seg_stride, Kp, scale, stream):
 
 
 def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act, colscale, R, ldr, res_mode,
-                  split_out, split_kp, split_scale, stream):
+                  res_rows, split_out, split_kp, split_scale, stream):
     a = T(arr(A2, (M, 2 * Kp), dtype=np.float16).astype(np.float32))
     b = T(arr(B2, (N, 2 * Kp), dtype=np.float16).astype(np.float32))
     ah, al, bh, bl = a[:, :Kp], a[:, Kp:], b[:, :Kp], b[:, Kp:]
@@ -120,7 +120,9 @@ def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias
     if colscale:
         y = y * T(arr(colscale, (N,)))
     if R:
-        r = T(arr(R, (M, N), (ldr, 1)))
+        r = T(arr(R, (res_rows or M, N), (ldr, 1)))
+        if res_rows:
+            r = r[torch.arange(M) % res_rows]
         y = (y + 1) * r if res_mode == 2 else r + y
     if C:
         _set(rows(C, M, N, ldc, seg_c, seg_stride_c), y.numpy())
@@ -395,13 +397,16 @@ def ec_point_update(bi, delta, ldd, out, M, stream):
     arr(out, (M, 2))[...] = z.sigmoid().numpy()
 
 
-def ec_im2col_patches(img, cols, B, H, W, P, ldc, stream):
+def ec_im2col_patches(img, cols, B, H, W, P, ldc, split_out, split_kp, stream):
     x = T(arr(img, (B, 3, H, W)))
     h0, w0 = H // P, W // P
     x = x[:, :, :h0 * P, :w0 * P].reshape(B, 3, h0, P, w0, P).permute(0, 2, 4, 1, 3, 5).reshape(B * h0 * w0, 3 * P * P)
-    out = arr(cols, (B * h0 * w0, ldc))
-    out[...] = 0
-    out[:, :3 * P * P] = x.numpy()
+    if cols:
+        out = arr(cols, (B * h0 * w0, ldc))
+        out[...] = 0
+        out[:, :3 * P * P] = x.numpy()
+    if split_out:
+        _write_split(split_out, split_kp, x.numpy())
 
 
 def ec_interp_pos_embed(pos, out, Mg, h0, w0, C, offset, stream):
