@@ -588,7 +588,7 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.res_mode = res_mode; p.res_rows = res_rows; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
   p.dbg = ec_tc_debug;
   // with few N tiles the A operand (activations, up to 128 MB > L2) would be swept once per N tile: walk N first
-  p.n_fastest = cdiv(N, BN) <= 4 ? 1 : 0;
+  p.n_fastest = (cdiv(N, BN) <= 4 && (long long)M * Kp * 4 > (64LL << 20)) ? 1 : 0;   // A (hi+lo) beyond ~half of L2
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 512) {
     const int pairs = (int)(pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2);
