@@ -319,10 +319,15 @@ def run_ours(args):
         "pck_vs_random_gt": summarize_pck(counters[:6]),
         "algorithmic_gflop_per_query": flops_per_query(cfg, R, K, args.shots) / 1e9,
     }
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     if roof:
         ach = roof["flops"] / (roof["ms"] / 1e3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                            "frac": ach / peak_tf, "traffic": None,
+                            "frac": ach / peak_tf, "traffic": traffic,
                             "kernel": ("ec::tc::gemm_f16x3_kernel (tcgen05 kind::f16, 3-product split-fp16, fp32 TMEM accumulate; "
                                        "algorithmic FLOPs = 1/3 of the tensor-pipe FLOPs issued)") if roof["tensor_core_launches"]
                             else "ec::gemm_simt_kernel<128,128> (fp32 FFMA)",
