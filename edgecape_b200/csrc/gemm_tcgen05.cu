@@ -569,18 +569,12 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
                                  tc::SMEM_BYTES));
     attr_set = true;
   }
-  // tile selection by a small cost model (cycles): waves x (k-blocks x MMA cycles per k-block + fixed per-tile cost).
-  // CTA-pair 256x256 tiles halve the operand traffic per unit of math and quarter the tile count; 128x128 tiles
-  // fill the machine better on small problems.
+  // tile selection: CTA-pair 256x256 tiles (half the operand traffic per unit of math) for problems that give every
+  // SM pair >= 1.5 tiles; 128x128 single-CTA tiles otherwise.  (A waves x tile-cost model that also moved mid-size
+  // problems to pair tiles measured 1.5% slower end to end -- pass L -- the cluster launch has a higher fixed cost.)
   const long long pair_tiles = (long long)cdiv(M, 256) * cdiv(N, 256);
   int mode = ec_tc_force_bn;                     // 0 heuristic, 128, 256, 512 (= pair)
-  if (mode == 0) {
-    const long long kb = Kp / tc::BK, fixed = 12000;
-    const long long tiles1 = (long long)cdiv(M, 128) * cdiv(N, 128);
-    const long long cost1 = ((tiles1 + num_sms - 1) / num_sms) * (kb * 768 * 5 / 4 + fixed);   // 1-CTA loop runs ~25% under the MMA rate
-    const long long cost2 = ((pair_tiles + num_sms / 2 - 1) / (num_sms / 2)) * (kb * 1536 + fixed);
-    mode = (N > 128 && cost2 < cost1) ? 512 : 128;
-  }
+  if (mode == 0) mode = (N >= 256 && pair_tiles * 4 >= 3LL * num_sms) ? 512 : 128;
   const int BN = mode == 128 ? 128 : 256;
   CUtensorMap tmA, tmB;
   int rc = tc::get_tensor_map(A2, M, Kp, tc::BM, &tmA);
