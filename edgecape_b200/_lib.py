@@ -58,6 +58,7 @@ SIGNATURES = {
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),
     "ec_proposal": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "ec_point_update": (c_int, [c_fp, c_fp, c_int, c_fp, c_int, c_fp]),
+    "ec_decode_preds": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_f, c_f, c_int, c_fp]),
     "ec_im2col_patches": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_int, c_fp]),
     "ec_interp_pos_embed": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_d, c_fp]),
     "ec_write_cls": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_fp]),

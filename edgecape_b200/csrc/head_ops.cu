@@ -171,9 +171,32 @@ __global__ void __launch_bounds__(128) pck_kernel(const float* __restrict__ pred
   if (threadIdx.x == 0) atomicAdd(&counters[T], 1.0);
 }
 
+// preds[b,k,:] = (transform_preds(points[b,k] * [W,H], center[b], scale[b], [W,H]), 1): the heat-map-space ->
+// image-space affine of TwoStageHead.decode, cs = [cx, cy, sx, sy] per sample
+__global__ void decode_preds_kernel(const float* __restrict__ points, const float* __restrict__ cs,
+                                    float* __restrict__ preds, int K, float W, float H, int use_udp, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / K;
+  const float cx = cs[4 * b], cy = cs[4 * b + 1], sx = cs[4 * b + 2] * 200.0f, sy = cs[4 * b + 3] * 200.0f;
+  const float kx = use_udp ? sx / (W - 1.0f) : sx / W, ky = use_udp ? sy / (H - 1.0f) : sy / H;
+  preds[3 * i + 0] = points[2 * i] * W * kx + cx - sx * 0.5f;
+  preds[3 * i + 1] = points[2 * i + 1] * H * ky + cy - sy * 0.5f;
+  preds[3 * i + 2] = 1.0f;
+}
+
 }  // namespace ec
 
 using namespace ec;
+
+extern "C" int ec_decode_preds(const float* points, const float* center_scale, float* preds, int B, int K, float W,
+                               float H, int use_udp, void* stream) {
+  EC_REQUIRE(points && center_scale && preds, "ec_decode_preds: null pointer");
+  if (B * K == 0) return EC_OK;
+  decode_preds_kernel<<<cdiv((long long)B * K, 256), 256, 0, (cudaStream_t)stream>>>(points, center_scale, preds, K, W, H,
+                                                                                     use_udp, B * K);
+  return check_launch("ec_decode_preds");
+}
 
 extern "C" int ec_support_weights(const float* target, const float* rowscale, float* Tw, int ldtw, int BK,
                                   int hm_h, int hm_w, int h, int w, void* stream) {

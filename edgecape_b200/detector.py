@@ -153,26 +153,32 @@ class EdgeCape(nn.Module):
         batch_size, _, img_height, img_width = img_q.shape
         output, initial_proposals, similarity_map, _, adj = self.predict(img_s, target_s, target_weight_s, img_q,
                                                                          img_metas)
-        # one synchronisation for all three device->host reads (the reference does three .cpu() calls)
+        # decode on the device (heat-map space -> image space) and ONE synchronisation for every device->host read
+        # (the reference does three .cpu() calls and decodes on the host)
         L, B, K, _ = output.shape
+        dev = output.device
         host = self._host_out.get((L, B, K))
         if host is None:
-            host = (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K))
+            host = (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K), torch.empty(B, K, 3), torch.empty(B, 4))
             if output.is_cuda:
                 host = tuple(t.pin_memory() for t in host)
             self._host_out = {(L, B, K): host}
+        cs = host[3]
+        for i in range(B):
+            cs[i, 0:2] = torch.as_tensor(np.asarray(img_metas[i]["query_center"], dtype=np.float32).reshape(-1)[:2])
+            cs[i, 2:4] = torch.as_tensor(np.asarray(img_metas[i]["query_scale"], dtype=np.float32).reshape(-1)[:2])
+        preds_dev = ops.decode_preds(output[-1].contiguous(), cs.to(dev, non_blocking=True), img_width, img_height,
+                                     use_udp=self.keypoint_head_module.test_cfg.get("use_udp", False))
         host[0][0].copy_(initial_proposals, non_blocking=True)
         host[0][1:].copy_(output, non_blocking=True)
         host[1].copy_(adj[0], non_blocking=True)
+        host[2].copy_(preds_dev, non_blocking=True)
         if output.is_cuda:
-            torch.cuda.current_stream(output.device).synchronize()
+            torch.cuda.current_stream(dev).synchronize()
         points = host[0].numpy().copy()
-        predicted_pose = points[-1]
         result = {}
         if self.with_keypoint:
-            keypoint_result = self.keypoint_head_module.decode(img_metas, predicted_pose,
-                                                               img_size=[img_width, img_height])
-            result.update(keypoint_result)
+            result.update(self.keypoint_head_module.assemble_result(img_metas, host[2].numpy().copy()))
         result.update({"points": points})
         result.update({"sample_image_file": [img_metas[i]["sample_image_file"] for i in range(len(img_metas))]})
         result.update({"skeleton": host[1].numpy().copy()})

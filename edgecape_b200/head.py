@@ -193,6 +193,32 @@ class TwoStageHead(PackedMixin, nn.Module):
         return self.forward_tokens(fq, fs, list(target_s), mask_s.reshape(B, -1).contiguous().float(), skeleton_lst)
 
     # ----------------------------------------------------------------------------- decode
+    def assemble_result(self, img_metas, preds):
+        """The bookkeeping half of `decode` (head.py:341-387) around device-decoded `preds` [B,K,3]."""
+        batch_size = len(img_metas)
+        bbox_ids = []
+        c = np.zeros((batch_size, 2), dtype=np.float32)
+        s = np.zeros((batch_size, 2), dtype=np.float32)
+        image_paths = []
+        score = np.ones(batch_size)
+        for i in range(batch_size):
+            c[i, :] = img_metas[i]["query_center"]
+            s[i, :] = img_metas[i]["query_scale"]
+            image_paths.append(img_metas[i]["query_image_file"])
+            if "query_bbox_score" in img_metas[i]:
+                score[i] = np.array(img_metas[i]["query_bbox_score"]).reshape(-1)[0]
+            if "bbox_id" in img_metas[i]:
+                bbox_ids.append(img_metas[i]["bbox_id"])
+            elif "query_bbox_id" in img_metas[i]:
+                bbox_ids.append(img_metas[i]["query_bbox_id"])
+        all_boxes = np.zeros((batch_size, 6), dtype=np.float32)
+        all_boxes[:, 0:2] = c[:, 0:2]
+        all_boxes[:, 2:4] = s[:, 0:2]
+        all_boxes[:, 4] = np.prod(s * 200.0, axis=1)
+        all_boxes[:, 5] = score
+        return dict(preds=np.ascontiguousarray(preds, dtype=np.float32), boxes=all_boxes, image_paths=image_paths,
+                    bbox_ids=bbox_ids)
+
     def decode(self, img_metas, output, img_size, **kwargs):
         """head.py:324-387: scale to pixels, undo the top-down crop, assemble preds / boxes."""
         batch_size = len(img_metas)

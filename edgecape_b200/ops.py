@@ -521,6 +521,17 @@ def point_update(bi, delta, out=None):
     return out
 
 
+def decode_preds(points, center_scale, W, H, use_udp=False, out=None):
+    """points [B,K,2] in [0,1], center_scale [B,4] -> preds [B,K,3] in image coordinates (TwoStageHead.decode)."""
+    _chk(points, "points"); _chk(center_scale, "center_scale")
+    assert points.is_contiguous() and center_scale.is_contiguous()
+    B, K, _ = points.shape
+    if out is None:
+        out = empty(B, K, 3, device=points.device)
+    _lib.call("ec_decode_preds", _p(points), _p(center_scale), _p(out), B, K, float(W), float(H), int(use_udp), _stream())
+    return out
+
+
 def im2col_patches(img, P, ldc=None):
     _chk(img, "img")
     assert img.is_contiguous()

@@ -224,6 +224,11 @@ int ec_proposal(const float* sim, float* prop_loss, float* prop, int64_t* argmax
  * head.py:27-31,216-220).  Also used for the final per-layer decode. */
 int ec_point_update(const float* bi, const float* delta, int ldd, float* out, int M, void* stream);
 
+/* TwoStageHead.decode on the device (head.py:324-387, mmpose transform_preds): points [B,K,2] in [0,1],
+ * center_scale [B,4] = (cx, cy, sx, sy) -> preds [B,K,3] = (x, y, 1) in image coordinates. */
+int ec_decode_preds(const float* points, const float* center_scale, float* preds, int B, int K, float W,
+                    float H, int use_udp, void* stream);
+
 /* ------------------------------------------------------------------------------ ViT ops
  * im2col for the stride-P patch embedding (floor semantics): img [B,3,H,W] ->
  * cols [B*h0*w0, ldc] with (c,py,px) ordering = Conv2d weight flattening; columns 3*P*P..ldc-1

@@ -397,6 +397,15 @@ def ec_point_update(bi, delta, ldd, out, M, stream):
     arr(out, (M, 2))[...] = z.sigmoid().numpy()
 
 
+def ec_decode_preds(points, cs, preds, B, K, W, H, use_udp, stream):
+    pt, c = arr(points, (B, K, 2)), arr(cs, (B, 4))
+    s = c[:, 2:] * np.float32(200.0)
+    k = s / (np.array([W - 1, H - 1], dtype=np.float32) if use_udp else np.array([W, H], dtype=np.float32))
+    out = arr(preds, (B, K, 3))
+    out[:, :, :2] = pt * np.array([W, H], dtype=np.float32) * k[:, None, :] + c[:, None, :2] - s[:, None, :] * np.float32(0.5)
+    out[:, :, 2] = 1.0
+
+
 def ec_im2col_patches(img, cols, B, H, W, P, ldc, split_out, split_kp, stream):
     x = T(arr(img, (B, 3, H, W)))
     h0, w0 = H // P, W // P
