@@ -407,7 +407,8 @@ __device__ __forceinline__ uint32_t make_idesc_bmn(int n) {       // as make_ide
 
 struct ParamsT {
   float* O;
-  int B, H, Lq, Lk, LKP, NKB;      // NKB = 64-row K boxes staged (>= LKP / 64)
+  int B, H, Lq, Lk;
+  int NB, LB;                       // key blocks (1 or 2) of LB keys each (LB a multiple of 64, <= 448 / 384)
   int ldo;
   long long so;
   float scale;
@@ -420,41 +421,48 @@ struct ParamsT {
 
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
 
+// Up to 448 keys: one key block, S [128 x Lk] in TMEM columns [0, 448), O in [448, 512).
+// Up to 768 keys (ViT-L at 384^2: 730): two key blocks of <= 384 keys processed one after the other, each with
+// its own row max / row sum and its own O accumulator (TMEM columns [384, 448) and [448, 512)); the two partial
+// results are merged in registers at the end (no rescaling of an accumulator in TMEM).
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, ParamsT p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const int nchunks = (p.Lk + KC - 1) / KC;
-  const int data_bytes = max(Q_BYTES + 2 * p.NKB * BOX_BYTES, 2 * PBUF_BYTES + nchunks * VBUF_BYTES);
+  const int NKB = p.LB / 64;                            // 64-key boxes / chunks per block
+  const int data_bytes = max(Q_BYTES + 2 * NKB * BOX_BYTES, 2 * PBUF_BYTES + NKB * VBUF_BYTES);
   const uint32_t misc = base + data_bytes;
   const uint32_t bar_qk = misc, bar_s = misc + 8, bar_pv0 = misc + 16, bar_pv1 = misc + 24, bar_v = misc + 32,
-                 tmem_slot = misc + 40;   // bar_v: all V chunks
+                 tmem_slot = misc + 40;
   float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, part = warp >> 2;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
-  const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + p.NKB * BOX_BYTES;
+  const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + NKB * BOX_BYTES;
+  const int qrow = b * p.q_rows + q0, krow = b * p.k_rows;
+
+  auto load_qk = [&](int blk) {   // Q tile (2 boxes) and the keys of block `blk` (NKB boxes), hi and lo halves
+    mbar_expect_tx(bar_qk, (uint32_t)((2 + NKB) * 2 * BOX_BYTES));
+    for (int j = 0; j < 2; ++j) {
+      tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * D, qrow + 64 * j);
+      tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * D, qrow + 64 * j);
+    }
+    for (int j = 0; j < NKB; ++j) {
+      tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * D, krow + blk * p.LB + 64 * j);
+      tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * D, krow + blk * p.LB + 64 * j);
+    }
+  };
 
   if (tid == 0) {
     mbar_init(bar_qk, 1); mbar_init(bar_s, 1);
     mbar_init(bar_pv0, 1); mbar_init(bar_pv1, 1);
     mbar_init(bar_v, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // Q tile (2 boxes) and all keys (NKB boxes), hi and lo halves
-    mbar_expect_tx(bar_qk, (uint32_t)((2 + p.NKB) * 2 * BOX_BYTES));
-    const int qrow = b * p.q_rows + q0, krow = b * p.k_rows;
-    for (int j = 0; j < 2; ++j) {
-      tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * D, qrow + 64 * j);
-      tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * D, qrow + 64 * j);
-    }
-    for (int j = 0; j < p.NKB; ++j) {
-      tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * D, krow + 64 * j);
-      tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * D, krow + 64 * j);
-    }
+    load_qk(0);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
@@ -465,109 +473,134 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
-  // ------------------------------------------------------------------ S = Q K^T
-  if (tid == 0) {
-    mbar_wait(bar_qk, 0);
-    tc_fence_after();
-    int n0 = p.LKP <= 256 ? p.LKP : ((p.LKP / 2 + 15) / 16) * 16;
-    for (int noff = 0; noff < p.LKP; noff += n0) {
-      const int n = min(n0, p.LKP - noff);
-      const uint32_t idesc = make_idesc(n);
-      const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
-      const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
-    }
-    umma_commit(bar_s);
-  }
-  mbar_wait(bar_s, 0);
-  tc_fence_after();
-  // Q / K shared memory is dead once S is complete: every V chunk ([64 keys][64 d], hi and lo) is loaded now, behind
-  // the P double buffer, so its latency hides under the row-max pass
-  const int vrow0 = b * p.k_rows;
-  if (tid == 0) {
-    mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
-    for (int i = 0; i < nchunks; ++i) {
-      const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES;
-      tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, vrow0 + i * KC);
-      tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, vrow0 + i * KC);
-    }
-  }
-
-  // ------------------------------------------------------------------ row max of scale * S
   const int row = quarter * 32 + lane;
   const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-  const int nchunk32 = (p.Lk + 31) / 32;
-  float mymax = -INFINITY;
-  for (int j = part; j < nchunk32; j += NPART) {
-    float s[32];
-    tmem_ld32(t_row + j * 32, s);
-#pragma unroll
-    for (int u = 0; u < 32; ++u)
-      if (j * 32 + u < p.Lk) mymax = fmaxf(mymax, s[u]);
-  }
-  xmax[part * BM + row] = mymax;
-  __syncthreads();                                     // also: Q / K shared memory is dead from here on
-  float rmax = xmax[row];
-#pragma unroll
-  for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
   const float sl2 = p.scale * 1.4426950408889634f;     // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
-
-  // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
   const uint32_t idesc_o = make_idesc_bmn(D);
-  float rsum = 0.f;
-  for (int i = 0; i < nchunks; ++i) {
-    const int buf = i & 1;
-    const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
-    const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
-    if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this P buffer
-    {
-      float s[PW];
-      const int kbase = i * KC + PW * part;
-      tmem_ld16(t_row + kbase, s);
-#pragma unroll
-      for (int u = 0; u < PW; ++u) {
-        const float e = (kbase + u < p.Lk) ? exp2f((s[u] - rmax) * sl2) : 0.f;
-        s[u] = e;
-        rsum += e;
-      }
-#pragma unroll
-      for (int j = 0; j < PW / 8; ++j) {
-        uint4 hi, lo;
-        split8(s + 8 * j, hi, lo);
-        const uint32_t off = swz(row, (PW / 8) * part + j);
-        *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
-        *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
-      }
-    }
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
+  float bmax[2] = {-INFINITY, -INFINITY}, bsum[2] = {0.f, 0.f};
+  int g = 0;                                           // running chunk index: selects the P buffer / barrier parity
+
+  for (int blk = 0; blk < p.NB; ++blk) {
+    const int key0 = blk * p.LB;
+    const int nkeys = min(p.LB, p.Lk - key0);          // valid keys of this block
+    const int lkp = (nkeys + 15) / 16 * 16;
+    const int nchunks = (nkeys + KC - 1) / KC;
+    const uint32_t o_col = 512 - 64 * (p.NB - blk);
+    // ---------------------------------------------------------------- S = Q K^T for this key block
     if (tid == 0) {
-      if (i == 0) mbar_wait(bar_v, 0);
+      mbar_wait(bar_qk, blk & 1);
       tc_fence_after();
-      const int valid = min(KC, p.Lk - i * KC);
-      const int ksteps = (valid + 15) / 16;
-      const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo);
-      const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
-      // P: K-major, +32 B per 16-key step; V: MN-major, 16 key rows = two 1024 B atoms per step
-      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_lo + 2 * k, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
-      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_lo + 128 * k, idesc_o, 1u);
-      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_hi + 128 * k, idesc_o, 1u);
-      umma_commit(buf ? bar_pv1 : bar_pv0);
+      int n0 = lkp <= 256 ? lkp : ((lkp / 2 + 15) / 16) * 16;
+      for (int noff = 0; noff < lkp; noff += n0) {
+        const int n = min(n0, lkp - noff);
+        const uint32_t idesc = make_idesc(n);
+        const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+        const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+      }
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, blk & 1);
+    tc_fence_after();
+    // Q / K shared memory is dead once S is complete: every V chunk of the block ([64 keys][64 d], hi and lo) is
+    // loaded now, behind the P double buffer, so its latency hides under the row-max pass
+    if (tid == 0) {
+      mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
+      for (int i = 0; i < nchunks; ++i) {
+        const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES;
+        tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, krow + key0 + i * KC);
+        tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, krow + key0 + i * KC);
+      }
+    }
+    // ---------------------------------------------------------------- row max over the block
+    const int nchunk32 = (nkeys + 31) / 32;
+    float mymax = -INFINITY;
+    for (int j = part; j < nchunk32; j += NPART) {
+      float s[32];
+      tmem_ld32(t_row + j * 32, s);
+#pragma unroll
+      for (int u = 0; u < 32; ++u)
+        if (j * 32 + u < nkeys) mymax = fmaxf(mymax, s[u]);
+    }
+    __syncthreads();                                   // xmax / xsum of the previous block have been consumed
+    xmax[part * BM + row] = mymax;
+    __syncthreads();
+    float rmax = xmax[row];
+#pragma unroll
+    for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+    bmax[blk] = rmax;
+    // ---------------------------------------------------------------- O_blk = exp(S - max) V, 64 keys per chunk
+    float rsum = 0.f;
+    for (int i = 0; i < nchunks; ++i, ++g) {
+      const int buf = g & 1;
+      const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
+      const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
+      if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((g >> 1) - 1) & 1);   // MMAs two chunks back released this P buffer
+      {
+        float s[PW];
+        const int kbase = i * KC + PW * part;
+        tmem_ld16(t_row + kbase, s);
+#pragma unroll
+        for (int u = 0; u < PW; ++u) {
+          const float e = (kbase + u < nkeys) ? exp2f((s[u] - rmax) * sl2) : 0.f;
+          s[u] = e;
+          rsum += e;
+        }
+#pragma unroll
+        for (int j = 0; j < PW / 8; ++j) {
+          uint4 hi, lo;
+          split8(s + 8 * j, hi, lo);
+          const uint32_t off = swz(row, (PW / 8) * part + j);
+          *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
+          *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
+        }
+      }
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        if (i == 0) mbar_wait(bar_v, blk & 1);
+        tc_fence_after();
+        const int valid = min(KC, nkeys - i * KC);
+        const int ksteps = (valid + 15) / 16;
+        const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo);
+        const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
+        // P: K-major, +32 B per 16-key step; V: MN-major, 16 key rows = two 1024 B atoms per step
+        for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_lo + 2 * k, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+        for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_hi + 2 * k, bv_lo + 128 * k, idesc_o, 1u);
+        for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_hi + 2 * k, bv_hi + 128 * k, idesc_o, 1u);
+        umma_commit(buf ? bar_pv1 : bar_pv0);
+      }
+    }
+    bsum[blk] = rsum;
+    // drain the P / V consumers of this block (the next block's TMA loads overwrite the same shared memory,
+    // and the epilogue reads the accumulators)
+    {
+      const int c0 = (g + 1) / 2, c1 = g / 2;          // commits issued so far on bar_pv0 / bar_pv1
+      if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
+      if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
+    }
+    tc_fence_after();
+    if (blk + 1 < p.NB) {
+      tc_fence_before();
+      __syncthreads();                                 // every warp is done reading S of this block from TMEM
+      if (tid == 0) {
+        tc_fence_after();
+        load_qk(blk + 1);
+      }
     }
   }
-  {
-    const int c0 = (nchunks + 1) / 2, c1 = nchunks / 2;
-    if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
-    if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
-  }
-  tc_fence_after();
-  xsum[part * BM + row] = rsum;
+
+  // ------------------------------------------------------------------ merge the key blocks, normalise, store
+  const float m = fmaxf(bmax[0], bmax[1]);
+  const float w0 = exp2f((bmax[0] - m) * sl2), w1 = p.NB > 1 ? exp2f((bmax[1] - m) * sl2) : 0.f;
+  __syncthreads();
+  xsum[part * BM + row] = bsum[0] * w0 + bsum[1] * w1;
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
@@ -576,7 +609,13 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   {
     constexpr int OW = D / NPART;
     float o[OW];
-    tmem_ld16(t_row + O_COL + OW * part, o);
+    tmem_ld16(t_row + (512 - 64 * p.NB) + OW * part, o);
+    if (p.NB > 1) {
+      float o1[OW];
+      tmem_ld16(t_row + 448 + OW * part, o1);
+#pragma unroll
+      for (int u = 0; u < OW; ++u) o[u] = o[u] * w0 + o1[u] * w1;
+    }
     const int grow = q0 + row;
     if (grow < p.Lq) {
 #pragma unroll
@@ -655,19 +694,24 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   EC_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, "ec_attention_tc_split: bad shape");
   EC_REQUIRE(q_kp % 64 == 0 && k_kp % 64 == 0 && v_kp % 64 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0,
              "ec_attention_tc_split: halves must be multiples of 64 columns, head offsets multiples of 8");
-  const int LKP = (Lk + 15) / 16 * 16;
-  if (LKP > atc::MAX_LKP) {
-    set_error("ec_attention_tc_split: %d keys exceed the %d S columns that fit in TMEM", Lk, atc::MAX_LKP);
-    return EC_ERR_UNSUPPORTED;
+  // one key block up to 448 keys, two blocks (each a multiple of 64, <= 384) up to 768
+  int NB = 1, LB = (Lk + 63) / 64 * 64;
+  if (LB > atc::MAX_LKP) {
+    NB = 2;
+    LB = ((Lk + 1) / 2 + 63) / 64 * 64;
+    if (LB > 384) {
+      set_error("ec_attention_tc_split: %d keys exceed the two 384-key blocks that fit in TMEM", Lk);
+      return EC_ERR_UNSUPPORTED;
+    }
   }
   EC_REQUIRE(!split_out || (split_kp == H * atc::D && (((uintptr_t)split_out) & 15) == 0),
              "ec_attention_tc_split: split_out needs split_kp == H*64 and 16-byte alignment");
   EC_REQUIRE(!O || (aligned16(O) && ldo % 4 == 0 && so % 4 == 0), "ec_attention_tc_split: O must be 16-byte aligned");
   if (B == 0 || Lq == 0) return EC_OK;
   EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc_split: grid too large");
-  const int NKB = (LKP + 63) / 64;
+  const int NKB = LB / 64;
   const int kq = atc::Q_BYTES + 2 * NKB * atc::BOX_BYTES;
-  const int pv = 2 * atc::PBUF_BYTES + ((Lk + atc::KC - 1) / atc::KC) * atc::VBUF_BYTES;
+  const int pv = 2 * atc::PBUF_BYTES + NKB * atc::VBUF_BYTES;
   const int data_bytes = kq > pv ? kq : pv;
   const int smem = data_bytes + atc::MISC_BYTES + 1024;
   static bool attr_set = false;
@@ -683,7 +727,7 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   if (rc) return rc;
   rc = tc::get_tensor_map(V2, v_total_rows, v_kp, 64, &tmV);
   if (rc) return rc;
-  atc::ParamsT p{O, B, H, Lq, Lk, LKP, NKB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
+  atc::ParamsT p{O, B, H, Lq, Lk, NB, LB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
                  q_kp, k_kp, v_kp, q_rows, k_rows};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
   atc::attention_tc_tma_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);

@@ -330,7 +330,7 @@ def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only
     qkv2 rows = B*N tokens, columns [q | k | v] of C = nheads*64 each per half.  TMA-fed tcgen05 kernel."""
     C = qkv2.K // 3
     D = C // nheads
-    assert D == 64 and qkv2.rows == B * N and qkv2.Kp == qkv2.K and N <= 448
+    assert D == 64 and qkv2.rows == B * N and qkv2.Kp == qkv2.K and N <= 768
     dev = qkv2.data.device
     ldo = so_ = 0
     if split != "only":

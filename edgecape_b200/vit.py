@@ -94,7 +94,7 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
         if ops.TENSOR_CORES and C % 64 == 0 and Btot * N >= ops.TC_MIN_M:
             # tensor-core path: every GEMM input is produced directly in split-fp16 form by the kernel
             # before it (LayerNorm, attention, GELU epilogue); only the residual stream t stays fp32
-            packed_attn = ops.ATTENTION_TC and ops.ATTENTION_TMA and C // H == 64 and N <= 448 and (3 * C) % 64 == 0
+            packed_attn = ops.ATTENTION_TC and ops.ATTENTION_TMA and C // H == 64 and N <= 768 and (3 * C) % 64 == 0
             for i in range(self.depth):
                 blk = getattr(self.blocks, str(i))
                 y2 = ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, split="only")

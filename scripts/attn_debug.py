@@ -101,6 +101,10 @@ if __name__ == "__main__":
         check_tma(2, 325, 12)
         check_tma(1, 448, 2)
         check_tma(3, 17, 2)
+        check_tma(2, 449, 3)
+        check_tma(1, 730, 16)
+        check_tma(1, 768, 2)
+        bench_tma(8, 16, 730)
         bench_tma(32, 12, 325)
         bench(32, 12, 325)
         sys.exit(0)

@@ -498,7 +498,7 @@ def test_attention_tc_with_mask_and_bias(B, H, Lq, Lk, D_, monkeypatch):
     assert torch.isfinite(got).all() and (got[1:] == 0).all()
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 325, 12), (3, 257, 6), (1, 64, 1), (2, 130, 4), (1, 448, 2), (4, 17, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 325, 12), (3, 257, 6), (1, 64, 1), (2, 130, 4), (1, 448, 2), (4, 17, 2), (1, 730, 16), (2, 449, 3), (1, 768, 2), (2, 577, 2)])
 def test_attention_tma_on_split_qkv(B, N, H, monkeypatch):
     """TMA-fed tcgen05 attention on the split-fp16 output of the QKV GEMM (MN-major V operand)."""
     C = H * 64
