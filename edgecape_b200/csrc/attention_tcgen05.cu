@@ -127,25 +127,52 @@ struct Params {
   const float* bias;           // [B, H, Lq, Lk] additive, or NULL
 };
 
-__global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
+constexpr int THREADS_T = THREADS + 32;   // 16 softmax / staging warps + one control warp (MMA issue; TMA in the split variant)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {   // MN-major B operand, SWIZZLE_128B
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc_bmn(int n) {       // as make_idesc, B operand MN-major
+  return make_idesc(n) | (1u << 16);
+}
+
+// Warps 0..15 stage operands and do the softmax; lane 0 of warp 16 issues every tcgen05.mma and its commits
+// (bar_pr*: "P and V of this chunk are in shared memory", 16 warp arrivals; bar_pv*: "the MMAs reading that
+// buffer are done"), so MMA issue never sits on the softmax warps' critical path.
+__global__ void __launch_bounds__(THREADS_T, 1) attention_tc_kernel(Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const int data_bytes = max(Q_BYTES + 2 * p.LKP * 128, REUSE_BYTES);
   const uint32_t misc = base + data_bytes;
-  const uint32_t bar_s = misc, bar_pv0 = misc + 8, bar_pv1 = misc + 16, tmem_slot = misc + 24;
+  const uint32_t bar_s = misc, bar_pv0 = misc + 8, bar_pv1 = misc + 16, bar_pr0 = misc + 24, bar_pr1 = misc + 32,
+                 tmem_slot = misc + 40;
   float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;                                    // [NPART][BM]
   uint8_t* msk = reinterpret_cast<uint8_t*>(xsum + NPART * BM);       // [MAX_LKP] key-padding mask of this batch row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, part = warp >> 2;
+  const int quarter = warp & 3, part = (warp >> 2) & 3;
+  const bool control = warp == THREADS / 32;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int dsteps = (p.dv + 15) / 16;                  // k-steps of S = Q K^T that carry data (head dim 32: 2 of 4)
 
-  if (tid == 0) {
+  if (tid == THREADS) {
     mbar_init(bar_s, 1);
     mbar_init(bar_pv0, 1);
     mbar_init(bar_pv1, 1);
+    mbar_init(bar_pr0, THREADS / 32);
+    mbar_init(bar_pr1, THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -155,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
 
   // ------------------------------------------------------------------ stage Q (scaled) and K
   const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + p.LKP * 128;
-  {
+  if (!control) {
     for (int j = tid; j < p.LKP; j += THREADS) msk[j] = (j < p.Lk && p.key_mask) ? p.key_mask[(long long)b * p.Lk + j] : 0;
     const float* Qb = p.Q + (long long)b * p.sq + h * p.dv;
     for (int it = tid; it < BM * 8; it += THREADS) {
@@ -208,98 +235,98 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
-
-  // ------------------------------------------------------------------ S = Q K^T  (all keys, into TMEM)
-  if (tid == 0) {
-    int n0 = p.LKP <= 256 ? p.LKP : ((p.LKP / 2 + 15) / 16) * 16;
-    for (int part = 0, noff = 0; noff < p.LKP; ++part, noff += n0) {
-      const int n = min(n0, p.LKP - noff);
-      const uint32_t idesc = make_idesc(n);
-      const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
-      const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
-    }
-    umma_commit(bar_s);
-  }
-  mbar_wait(bar_s, 0);
-  tc_fence_after();
-
-  // ------------------------------------------------------------------ row max (two warps per lane quarter)
-  const int row = quarter * 32 + lane;                 // TMEM lane == row of the query tile
-  const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-  const int nchunk32 = (p.Lk + 31) / 32;
-  const float* bias_row = (p.bias && q0 + row < p.Lq)
-                              ? p.bias + (((long long)b * p.H + h) * p.Lq + (q0 + row)) * p.Lk : nullptr;
-  float mymax = -INFINITY;
-  for (int j = part; j < nchunk32; j += NPART) {
-    float s[32];
-    tmem_ld32(t_row + j * 32, s);
-#pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const int key = j * 32 + u;
-      if (key < p.Lk && !msk[key]) mymax = fmaxf(mymax, bias_row ? s[u] + __ldg(bias_row + key) : s[u]);
-    }
-  }
-  xmax[part * BM + row] = mymax;
-  __syncthreads();                                     // also: every warp is done with Q / K shared memory
-  float rmax = xmax[row];
-#pragma unroll
-  for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
-  if (rmax == -INFINITY) rmax = 0.f;                   // fully masked row: every p below is 0
-
-  // ------------------------------------------------------------------ O = softmax(S) V, 64 keys per chunk
-  const float* Vb = p.V + (long long)b * p.sv + h * p.dv;
   const int nchunks = (p.Lk + KC - 1) / KC;
-  const uint32_t idesc_o = make_idesc(D);
-  float rsum = 0.f;
-  constexpr int VI = KC * 8 / THREADS;                   // V items (8 floats of one key) per thread and chunk
-  float4 va[VI], vb[VI];                                 // V rows of the next chunk, prefetched
-  auto load_v = [&](int chunk) {
-#pragma unroll
-    for (int w = 0; w < VI; ++w) {
-      const int it = tid + w * THREADS;
-      const int kl = it >> 3, dc = it & 7;
-      const int key = chunk * KC + kl;
-      va[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-      vb[w] = va[w];
-      if (key < p.Lk && dc * 8 < p.dv) {
-        const float4* src = reinterpret_cast<const float4*>(Vb + (long long)key * p.ldv + dc * 8);
-        va[w] = __ldg(src);
-        vb[w] = __ldg(src + 1);
+
+  if (control) {
+    // ================================================================== control warp
+    if (lane == 0) {
+      // S = Q K^T  (all keys, into TMEM)
+      const int n0 = p.LKP <= 256 ? p.LKP : ((p.LKP / 2 + 15) / 16) * 16;
+      for (int noff = 0; noff < p.LKP; noff += n0) {
+        const int n = min(n0, p.LKP - noff);
+        const uint32_t idesc = make_idesc(n);
+        const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+        const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+        for (int k = 0; k < dsteps; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+        for (int k = 0; k < dsteps; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+        for (int k = 0; k < dsteps; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+      }
+      umma_commit(bar_s);
+      // O += P V per chunk; N = the head dim actually used (32 or 64)
+      const uint32_t idesc_o = make_idesc_bmn(dsteps * 16);
+      for (int i = 0; i < nchunks; ++i) {
+        const int buf = i & 1;
+        const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
+        const uint32_t v_hi = base + 2 * PBUF_BYTES + buf * VBUF_BYTES, v_lo = v_hi + KC * 128;
+        mbar_wait(buf ? bar_pr1 : bar_pr0, (i >> 1) & 1);
+        tc_fence_after();
+        const int valid = min(KC, p.Lk - i * KC);
+        const int ksteps = (valid + 15) / 16;
+        const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo);
+        const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
+        // P: K-major, +32 B per 16-key step; V: MN-major [key][d] rows, 16 keys = two 1024 B atoms per step
+        for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_lo + 2 * k, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+        for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_lo + 128 * k, idesc_o, 1u);
+        for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_hi + 128 * k, idesc_o, 1u);
+        umma_commit(buf ? bar_pv1 : bar_pv0);
       }
     }
-  };
-  load_v(0);
-  for (int i = 0; i < nchunks; ++i) {
-    const int buf = i & 1;
-    const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
-    const uint32_t v_hi = base + 2 * PBUF_BYTES + buf * VBUF_BYTES, v_lo = v_hi + D * 128;
-    if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this buffer
-    // V^T of this chunk (tile rows = head-dim index, columns = keys) from the registers prefetched one
-    // iteration ago; then the loads of the next chunk are issued so they overlap the exponentials below
+    __syncwarp();
+  } else {
+    // ================================================================== softmax / staging warps
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // ---------------------------------------------------------------- row max (four warps per lane quarter)
+    const int row = quarter * 32 + lane;               // TMEM lane == row of the query tile
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int nchunk32 = (p.Lk + 31) / 32;
+    const float* bias_row = (p.bias && q0 + row < p.Lq)
+                                ? p.bias + (((long long)b * p.H + h) * p.Lq + (q0 + row)) * p.Lk : nullptr;
+    float mymax = -INFINITY;
+    for (int j = part; j < nchunk32; j += NPART) {
+      float s[32];
+      tmem_ld32(t_row + j * 32, s);
 #pragma unroll
-    for (int w = 0; w < VI; ++w) {
-      const int it = tid + w * THREADS;
-      const int kl = it >> 3, dc = it & 7;
-      const float v[8] = {va[w].x, va[w].y, va[w].z, va[w].w, vb[w].x, vb[w].y, vb[w].z, vb[w].w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int drow = dc * 8 + e;
-        const __half hi = __float2half_rn(v[e]);
-        const __half lo = __float2half_rn(v[e] - __half2float(hi));
-        const uint32_t off = swz(drow, kl >> 3) + (kl & 7) * 2;
-        *reinterpret_cast<__half*>(gbase + (v_hi - base) + off) = hi;
-        *reinterpret_cast<__half*>(gbase + (v_lo - base) + off) = lo;
+      for (int u = 0; u < 32; ++u) {
+        const int key = j * 32 + u;
+        if (key < p.Lk && !msk[key]) mymax = fmaxf(mymax, bias_row ? s[u] + __ldg(bias_row + key) : s[u]);
       }
     }
-    load_v(i + 1);
-    // P of this chunk: this warp covers keys [i*64 + PW*part, +PW) of its 32 rows
-    {
+    xmax[part * BM + row] = mymax;
+    softmax_sync();
+    float rmax = xmax[row];
+#pragma unroll
+    for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+    if (rmax == -INFINITY) rmax = 0.f;                 // fully masked row: every p below is 0
+
+    // ---------------------------------------------------------------- P = exp(S - max) and V, 64 keys per chunk
+    const float* Vb = p.V + (long long)b * p.sv + h * p.dv;
+    const float L2E = 1.4426950408889634f;
+    const float nb = -rmax * L2E;
+    float rsum = 0.f;
+    constexpr int VI = KC * 8 / THREADS;               // V items (8 floats of one key) per thread and chunk
+    float4 va[VI], vb[VI];                             // V rows of the next chunk, prefetched
+    auto load_v = [&](int chunk) {
+#pragma unroll
+      for (int w = 0; w < VI; ++w) {
+        const int it = tid + w * THREADS;
+        const int kl = it >> 3, dc = it & 7;
+        const int key = chunk * KC + kl;
+        va[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[w] = va[w];
+        if (key < p.Lk && dc * 8 < p.dv) {
+          const float4* src = reinterpret_cast<const float4*>(Vb + (long long)key * p.ldv + dc * 8);
+          va[w] = __ldg(src);
+          vb[w] = __ldg(src + 1);
+        }
+      }
+    };
+    load_v(0);
+    for (int i = 0; i < nchunks; ++i) {
+      const int buf = i & 1;
+      const uint32_t p_off = buf * PBUF_BYTES;
+      const uint32_t v_off = 2 * PBUF_BYTES + buf * VBUF_BYTES;
+      // P of this chunk: this warp covers keys [i*64 + PW*part, +PW) of its 32 rows
       float s[PW];
       const int kbase = i * KC + PW * part;
       tmem_ld16(t_row + kbase, s);
@@ -308,69 +335,74 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
         const int key = kbase + u;
         const bool ok = key < p.Lk && !msk[key];
         const float sv_ = (ok && bias_row) ? s[u] + __ldg(bias_row + key) : s[u];
-        const float e = ok ? exp2f((sv_ - rmax) * 1.4426950408889634f) : 0.f;
+        const float e = ok ? ex2(fmaf(sv_, L2E, nb)) : 0.f;
         s[u] = e;
         rsum += e;
       }
+      if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 released this buffer
+      // V of this chunk as an MN-major tile ([key][d] rows, 128B swizzle -- the layout K uses), from the
+      // registers prefetched one iteration ago; then the loads of the next chunk are issued
+#pragma unroll
+      for (int w = 0; w < VI; ++w) {
+        const int it = tid + w * THREADS;
+        const int kl = it >> 3, dc = it & 7;
+        const float v[8] = {va[w].x, va[w].y, va[w].z, va[w].w, vb[w].x, vb[w].y, vb[w].z, vb[w].w};
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const uint32_t off = swz(kl, dc);
+        *reinterpret_cast<uint4*>(gbase + v_off + off) = hi;
+        *reinterpret_cast<uint4*>(gbase + v_off + KC * 128 + off) = lo;
+      }
+      load_v(i + 1);
 #pragma unroll
       for (int j = 0; j < PW / 8; ++j) {
         uint4 hi, lo;
         split8(s + 8 * j, hi, lo);
         const uint32_t off = swz(row, (PW / 8) * part + j);
-        *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
-        *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
+        *reinterpret_cast<uint4*>(gbase + p_off + off) = hi;
+        *reinterpret_cast<uint4*>(gbase + p_off + BM * 128 + off) = lo;
       }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(buf ? bar_pr1 : bar_pr0);
     }
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const int valid = min(KC, p.Lk - i * KC);
-      const int ksteps = (valid + 15) / 16;
-      const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo), bv_hi = make_desc(v_hi), bv_lo = make_desc(v_lo);
-      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_lo + 2 * k, bv_hi + 2 * k, idesc_o, (i | k) ? 1u : 0u);
-      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_lo + 2 * k, idesc_o, 1u);
-      for (int k = 0; k < ksteps; ++k) umma(tmem_base + O_COL, ap_hi + 2 * k, bv_hi + 2 * k, idesc_o, 1u);
-      umma_commit(buf ? bar_pv1 : bar_pv0);
+    // drain: the last commit on each buffer
+    {
+      const int c0 = (nchunks + 1) / 2, c1 = nchunks / 2;
+      if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
+      if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
     }
-  }
-  // drain: the last commit on each buffer
-  {
-    const int c0 = (nchunks + 1) / 2, c1 = nchunks / 2;
-    if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
-    if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
-  }
-  tc_fence_after();
-  xsum[part * BM + row] = rsum;
-  __syncthreads();
-  float tot = 0.f;
+    tc_fence_after();
+    xsum[part * BM + row] = rsum;
+    softmax_sync();
+    float tot = 0.f;
 #pragma unroll
-  for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
-  const float inv = tot > 0.f ? 1.0f / tot : 0.f;      // fully masked row -> 0 (as the fp32 kernel)
+    for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
+    const float inv = tot > 0.f ? 1.0f / tot : 0.f;    // fully masked row -> 0 (as the fp32 kernel)
 
-  // ------------------------------------------------------------------ epilogue: O / rowsum
-  {
-    constexpr int OW = D / NPART;                        // output columns per warp (16)
-    float o[OW];
-    tmem_ld16(t_row + O_COL + OW * part, o);
+    // ---------------------------------------------------------------- epilogue: O / rowsum
+    constexpr int OW = D / NPART;                      // output columns per warp (16)
     const int grow = q0 + row;
-    if (grow < p.Lq && OW * part < p.dv) {
+    if (OW * part < p.dv) {                            // warp-uniform
+      float o[OW];
+      tmem_ld16(t_row + O_COL + OW * part, o);
+      if (grow < p.Lq) {
 #pragma unroll
-      for (int u = 0; u < OW; ++u) o[u] *= inv;
-      if (p.O) {
-        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * p.dv + OW * part);
+        for (int u = 0; u < OW; ++u) o[u] *= inv;
+        if (p.O) {
+          float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * p.dv + OW * part);
 #pragma unroll
-        for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-      }
-      if (p.split_out) {
-        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * p.dv + OW * part;
+          for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        }
+        if (p.split_out) {
+          __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * p.dv + OW * part;
 #pragma unroll
-        for (int j = 0; j < OW / 8; ++j) {
-          uint4 hi, lo;
-          split8(o + 8 * j, hi, lo);
-          *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
-          *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+          for (int j = 0; j < OW / 8; ++j) {
+            uint4 hi, lo;
+            split8(o + 8 * j, hi, lo);
+            *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
+            *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+          }
         }
       }
     }
@@ -386,7 +418,8 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(Params p) {
 // TMA-fed variant: Q, K, V arrive already split into fp16 (hi | lo) halves -- the QKV GEMM epilogue writes
 // them -- so the kernel stages nothing by hand: one thread issues TMA loads (128B-swizzled 64 x 64 boxes)
 // and the UMMAs; all 16 warps do only the softmax.  V is consumed as an MN-major B operand straight from
-// its [keys][head-dim] tile, so there is no transposition either.
+// its [keys][head-dim] tile (MN-major, SWIZZLE_128B: rows (= k index) of 128 B holding 64 contiguous MN
+// elements, 8-row atoms of 1024 B), so there is no transposition either.
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -396,15 +429,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// MN-major, SWIZZLE_128B: rows (= k index) of 128 B holding 64 contiguous MN elements, 8-row atoms of 1024 B
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ uint32_t make_idesc_bmn(int n) {       // as make_idesc, B operand MN-major
-  return make_idesc(n) | (1u << 16);
-}
-
 struct ParamsT {
   float* O;
   int B, H, Lq, Lk;
@@ -417,15 +441,27 @@ struct ParamsT {
   int q_col, k_col, v_col;          // column of head 0 in the hi half of each buffer
   int q_kp, k_kp, v_kp;             // columns per half
   int q_rows, k_rows;               // rows per batch element in the Q and K/V buffers
+  long long* trace;                 // optional [trace_n][10] clock64 stamps of CTA phases (ec_attention_tc_set_trace)
+  int trace_n;
 };
 
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
 
+// Warp-specialised: warps 0..15 do the softmax (4 warps per TMEM lane quarter, 16 keys of every 64-key chunk
+// each) and never issue TMA / MMA; lane 0 of warp 16 owns every TMA load, every tcgen05.mma and its commits,
+// so descriptor building and instruction issue are off the softmax warps' critical path.  Hand-offs:
+//   bar_qk  TMA -> control      Q tile + keys of the block landed
+//   bar_s   MMA -> everyone     S = Q K^T of the block is complete (Q / K shared memory is dead)
+//   bar_v   TMA -> control      V chunks of the block landed
+//   bar_pr* softmax -> control  P chunk written to its buffer (16 warp arrivals)
+//   bar_pv* MMA -> softmax      the MMAs reading that P buffer are done (buffer free / O complete)
+//   bar_sf  softmax -> control  S of the block consumed and its PV drained (two-block case: next block may start)
+//
 // Up to 448 keys: one key block, S [128 x Lk] in TMEM columns [0, 448), O in [448, 512).
 // Up to 768 keys (ViT-L at 384^2: 730): two key blocks of <= 384 keys processed one after the other, each with
 // its own row max / row sum and its own O accumulator (TMEM columns [384, 448) and [448, 512)); the two partial
 // results are merged in registers at the end (no rescaling of an accumulator in TMEM).
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_T, 1)
 attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, ParamsT p) {
   extern __shared__ uint8_t smem_raw[];
@@ -435,13 +471,19 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int data_bytes = max(Q_BYTES + 2 * NKB * BOX_BYTES, 2 * PBUF_BYTES + NKB * VBUF_BYTES);
   const uint32_t misc = base + data_bytes;
   const uint32_t bar_qk = misc, bar_s = misc + 8, bar_pv0 = misc + 16, bar_pv1 = misc + 24, bar_v = misc + 32,
-                 tmem_slot = misc + 40;
-  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 64);   // [NPART][BM]
+                 bar_pr0 = misc + 40, bar_pr1 = misc + 48, bar_sf = misc + 56, tmem_slot = misc + 64;
+  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 128);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, part = warp >> 2;
+  const int quarter = warp & 3, part = (warp >> 2) & 3;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* trace = (p.trace && tid == 0 && cta < p.trace_n) ? p.trace + 10 * cta : nullptr;
+  auto stamp = [&](int i) {
+    if (trace) trace[i] = clock64();
+  };
+  stamp(0);
   const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + NKB * BOX_BYTES;
   const int qrow = b * p.q_rows + q0, krow = b * p.k_rows;
 
@@ -457,10 +499,12 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   };
 
-  if (tid == 0) {
+  if (tid == THREADS) {
     mbar_init(bar_qk, 1); mbar_init(bar_s, 1);
     mbar_init(bar_pv0, 1); mbar_init(bar_pv1, 1);
     mbar_init(bar_v, 1);
+    mbar_init(bar_pr0, THREADS / 32); mbar_init(bar_pr1, THREADS / 32);
+    mbar_init(bar_sf, THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     load_qk(0);
   }
@@ -472,177 +516,205 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  stamp(1);
 
-  const int row = quarter * 32 + lane;
-  const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-  const float sl2 = p.scale * 1.4426950408889634f;     // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
-  const uint32_t idesc_o = make_idesc_bmn(D);
-  float bmax[2] = {-INFINITY, -INFINITY}, bsum[2] = {0.f, 0.f};
-  int g = 0;                                           // running chunk index: selects the P buffer / barrier parity
-
-  for (int blk = 0; blk < p.NB; ++blk) {
-    const int key0 = blk * p.LB;
-    const int nkeys = min(p.LB, p.Lk - key0);          // valid keys of this block
-    const int lkp = (nkeys + 15) / 16 * 16;
-    const int nchunks = (nkeys + KC - 1) / KC;
-    const uint32_t o_col = 512 - 64 * (p.NB - blk);
-    // ---------------------------------------------------------------- S = Q K^T for this key block
-    if (tid == 0) {
-      mbar_wait(bar_qk, blk & 1);
+  if (warp == THREADS / 32) {
+    // ================================================================== control warp: TMA + MMA issue
+    if (lane == 0) {
+      const uint32_t idesc_o = make_idesc_bmn(D);
+      int g = 0;
+      for (int blk = 0; blk < p.NB; ++blk) {
+        const int key0 = blk * p.LB;
+        const int nkeys = min(p.LB, p.Lk - key0);
+        const int lkp = (nkeys + 15) / 16 * 16;
+        const int nchunks = (nkeys + KC - 1) / KC;
+        const uint32_t o_col = 512 - 64 * (p.NB - blk);
+        if (blk > 0) {                                   // S of the previous block consumed, its P / V buffers drained
+          mbar_wait(bar_sf, (blk - 1) & 1);
+          tc_fence_after();
+          load_qk(blk);
+        }
+        mbar_wait(bar_qk, blk & 1);
+        tc_fence_after();
+        {
+          const int n0 = lkp <= 256 ? lkp : ((lkp / 2 + 15) / 16) * 16;
+          for (int noff = 0; noff < lkp; noff += n0) {
+            const int n = min(n0, lkp - noff);
+            const uint32_t idesc = make_idesc(n);
+            const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+            const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+          }
+          umma_commit(bar_s);
+        }
+        // Q / K shared memory is dead once S is complete: every V chunk of the block ([64 keys][64 d], hi and
+        // lo) is loaded behind the P double buffer while the softmax warps take the row max
+        mbar_wait(bar_s, blk & 1);
+        mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
+        for (int i = 0; i < nchunks; ++i) {
+          const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES;
+          tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, krow + key0 + i * KC);
+          tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, krow + key0 + i * KC);
+        }
+        mbar_wait(bar_v, blk & 1);
+        for (int i = 0; i < nchunks; ++i, ++g) {
+          const int buf = g & 1;
+          const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
+          const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
+          mbar_wait(buf ? bar_pr1 : bar_pr0, (g >> 1) & 1);
+          tc_fence_after();
+          const int valid = min(KC, nkeys - i * KC);
+          const int ksteps = (valid + 15) / 16;
+          const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo);
+          const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
+          // P: K-major, +32 B per 16-key step; V: MN-major, 16 key rows = two 1024 B atoms per step
+          for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_lo + 2 * k, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+          for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_hi + 2 * k, bv_lo + 128 * k, idesc_o, 1u);
+          for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_hi + 2 * k, bv_hi + 128 * k, idesc_o, 1u);
+          umma_commit(buf ? bar_pv1 : bar_pv0);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== softmax warps
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;   // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
+    float bmax0 = -INFINITY, bmax1 = -INFINITY, bsum0 = 0.f, bsum1 = 0.f;
+    int g = 0;                                         // running chunk index: selects the P buffer / barrier parity
+    for (int blk = 0; blk < p.NB; ++blk) {
+      const int key0 = blk * p.LB;
+      const int nkeys = min(p.LB, p.Lk - key0);        // valid keys of this block
+      const int nchunks = (nkeys + KC - 1) / KC;
+      mbar_wait(bar_s, blk & 1);
       tc_fence_after();
-      int n0 = lkp <= 256 ? lkp : ((lkp / 2 + 15) / 16) * 16;
-      for (int noff = 0; noff < lkp; noff += n0) {
-        const int n = min(n0, lkp - noff);
-        const uint32_t idesc = make_idesc(n);
-        const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
-        const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+      if (blk == 0) stamp(2);
+      // -------------------------------------------------------------- row max over the block
+      const int nchunk32 = (nkeys + 31) / 32;
+      float mymax = -INFINITY;
+      for (int j = part; j < nchunk32; j += NPART) {
+        float s[32];
+        tmem_ld32(t_row + j * 32, s);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+        for (int u = 0; u < 32; ++u)
+          if (j * 32 + u < nkeys) mymax = fmaxf(mymax, s[u]);
       }
-      umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, blk & 1);
-    tc_fence_after();
-    // Q / K shared memory is dead once S is complete: every V chunk of the block ([64 keys][64 d], hi and lo) is
-    // loaded now, behind the P double buffer, so its latency hides under the row-max pass
-    if (tid == 0) {
-      mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
-      for (int i = 0; i < nchunks; ++i) {
-        const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES;
-        tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, krow + key0 + i * KC);
-        tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, krow + key0 + i * KC);
-      }
-    }
-    // ---------------------------------------------------------------- row max over the block
-    const int nchunk32 = (nkeys + 31) / 32;
-    float mymax = -INFINITY;
-    for (int j = part; j < nchunk32; j += NPART) {
-      float s[32];
-      tmem_ld32(t_row + j * 32, s);
+      if (blk > 0) softmax_sync();                     // xmax of the previous block has been consumed
+      xmax[part * BM + row] = mymax;
+      softmax_sync();
+      float rmax = xmax[row];
 #pragma unroll
-      for (int u = 0; u < 32; ++u)
-        if (j * 32 + u < nkeys) mymax = fmaxf(mymax, s[u]);
-    }
-    __syncthreads();                                   // xmax / xsum of the previous block have been consumed
-    xmax[part * BM + row] = mymax;
-    __syncthreads();
-    float rmax = xmax[row];
-#pragma unroll
-    for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
-    bmax[blk] = rmax;
-    // ---------------------------------------------------------------- O_blk = exp(S - max) V, 64 keys per chunk
-    float rsum = 0.f;
-    for (int i = 0; i < nchunks; ++i, ++g) {
-      const int buf = g & 1;
-      const uint32_t p_hi = base + buf * PBUF_BYTES, p_lo = p_hi + BM * 128;
-      const uint32_t v_hi = base + 2 * PBUF_BYTES + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
-      if (i >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((g >> 1) - 1) & 1);   // MMAs two chunks back released this P buffer
-      {
+      for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+      if (blk == 0) bmax0 = rmax; else bmax1 = rmax;
+      if (blk == 0) stamp(3);
+      // -------------------------------------------------------------- P = exp(S - max), 64 keys per chunk
+      const float nb = -rmax * sl2;
+      float rsum = 0.f;
+      for (int i = 0; i < nchunks; ++i, ++g) {
+        const int buf = g & 1;
+        const uint32_t p_off = buf * PBUF_BYTES;
         float s[PW];
         const int kbase = i * KC + PW * part;
         tmem_ld16(t_row + kbase, s);
 #pragma unroll
         for (int u = 0; u < PW; ++u) {
-          const float e = (kbase + u < nkeys) ? exp2f((s[u] - rmax) * sl2) : 0.f;
+          const float e = (kbase + u < nkeys) ? ex2(fmaf(s[u], sl2, nb)) : 0.f;
           s[u] = e;
           rsum += e;
         }
+        // the MMAs two chunks back released this P buffer (buffers are drained between key blocks: there the
+        // wait is on an already completed phase)
+        if (g >= 2) mbar_wait(buf ? bar_pv1 : bar_pv0, ((g >> 1) - 1) & 1);
 #pragma unroll
         for (int j = 0; j < PW / 8; ++j) {
           uint4 hi, lo;
           split8(s + 8 * j, hi, lo);
           const uint32_t off = swz(row, (PW / 8) * part + j);
-          *reinterpret_cast<uint4*>(gbase + (p_hi - base) + off) = hi;
-          *reinterpret_cast<uint4*>(gbase + (p_lo - base) + off) = lo;
+          *reinterpret_cast<uint4*>(gbase + p_off + off) = hi;
+          *reinterpret_cast<uint4*>(gbase + p_off + BM * 128 + off) = lo;
         }
+        proxy_fence();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(buf ? bar_pr1 : bar_pr0);
+        if (blk == 0 && i == 0) stamp(4);
       }
-      proxy_fence();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        if (i == 0) mbar_wait(bar_v, blk & 1);
-        tc_fence_after();
-        const int valid = min(KC, nkeys - i * KC);
-        const int ksteps = (valid + 15) / 16;
-        const uint64_t ap_hi = make_desc(p_hi), ap_lo = make_desc(p_lo);
-        const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
-        // P: K-major, +32 B per 16-key step; V: MN-major, 16 key rows = two 1024 B atoms per step
-        for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_lo + 2 * k, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
-        for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_hi + 2 * k, bv_lo + 128 * k, idesc_o, 1u);
-        for (int k = 0; k < ksteps; ++k) umma(tmem_base + o_col, ap_hi + 2 * k, bv_hi + 128 * k, idesc_o, 1u);
-        umma_commit(buf ? bar_pv1 : bar_pv0);
+      if (blk == 0) bsum0 = rsum; else bsum1 = rsum;
+      if (blk == 0) stamp(5);
+      // drain the P / V consumers of this block (the next block's TMA loads overwrite the same shared memory,
+      // and the epilogue reads the accumulators)
+      {
+        const int c0 = (g + 1) / 2, c1 = g / 2;        // commits issued so far on bar_pv0 / bar_pv1
+        if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
+        if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
       }
-    }
-    bsum[blk] = rsum;
-    // drain the P / V consumers of this block (the next block's TMA loads overwrite the same shared memory,
-    // and the epilogue reads the accumulators)
-    {
-      const int c0 = (g + 1) / 2, c1 = g / 2;          // commits issued so far on bar_pv0 / bar_pv1
-      if (c0 > 0) mbar_wait(bar_pv0, (c0 - 1) & 1);
-      if (c1 > 0) mbar_wait(bar_pv1, (c1 - 1) & 1);
-    }
-    tc_fence_after();
-    if (blk + 1 < p.NB) {
-      tc_fence_before();
-      __syncthreads();                                 // every warp is done reading S of this block from TMEM
-      if (tid == 0) {
-        tc_fence_after();
-        load_qk(blk + 1);
+      tc_fence_after();
+      if (blk == 0) stamp(6);
+      if (blk + 1 < p.NB) {
+        tc_fence_before();                             // this warp's tcgen05.ld of S are complete
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sf);
       }
     }
-  }
 
-  // ------------------------------------------------------------------ merge the key blocks, normalise, store
-  const float m = fmaxf(bmax[0], bmax[1]);
-  const float w0 = exp2f((bmax[0] - m) * sl2), w1 = p.NB > 1 ? exp2f((bmax[1] - m) * sl2) : 0.f;
-  __syncthreads();
-  xsum[part * BM + row] = bsum[0] * w0 + bsum[1] * w1;
-  __syncthreads();
-  float tot = 0.f;
+    // ---------------------------------------------------------------- merge the key blocks, normalise, store
+    const float m = fmaxf(bmax0, bmax1);
+    const float w0 = ex2((bmax0 - m) * sl2), w1 = p.NB > 1 ? ex2((bmax1 - m) * sl2) : 0.f;
+    xsum[part * BM + row] = bsum0 * w0 + bsum1 * w1;
+    softmax_sync();
+    float tot = 0.f;
 #pragma unroll
-  for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
-  const float inv = 1.0f / tot;
-  {
-    constexpr int OW = D / NPART;
-    float o[OW];
-    tmem_ld16(t_row + (512 - 64 * p.NB) + OW * part, o);
-    if (p.NB > 1) {
-      float o1[OW];
-      tmem_ld16(t_row + 448 + OW * part, o1);
+    for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
+    const float inv = 1.0f / tot;
+    {
+      constexpr int OW = D / NPART;
+      float o[OW];
+      tmem_ld16(t_row + (512 - 64 * p.NB) + OW * part, o);
+      if (p.NB > 1) {
+        float o1[OW];
+        tmem_ld16(t_row + 448 + OW * part, o1);
 #pragma unroll
-      for (int u = 0; u < OW; ++u) o[u] = o[u] * w0 + o1[u] * w1;
-    }
-    const int grow = q0 + row;
-    if (grow < p.Lq) {
-#pragma unroll
-      for (int u = 0; u < OW; ++u) o[u] *= inv;
-      if (p.O) {
-        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
-#pragma unroll
-        for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        for (int u = 0; u < OW; ++u) o[u] = o[u] * w0 + o1[u] * w1;
       }
-      if (p.split_out) {
-        __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
+      const int grow = q0 + row;
+      if (grow < p.Lq) {
 #pragma unroll
-        for (int j = 0; j < OW / 8; ++j) {
-          uint4 hi, lo;
-          split8(o + 8 * j, hi, lo);
-          *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
-          *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+        for (int u = 0; u < OW; ++u) o[u] *= inv;
+        if (p.O) {
+          float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
+#pragma unroll
+          for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        }
+        if (p.split_out) {
+          __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
+#pragma unroll
+          for (int j = 0; j < OW / 8; ++j) {
+            uint4 hi, lo;
+            split8(o + 8 * j, hi, lo);
+            *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
+            *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+          }
         }
       }
     }
+    stamp(7);
   }
   tc_fence_before();
   __syncthreads();
+  stamp(8);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+  stamp(9);
 }
+
+static long long* g_trace = nullptr;
+static int g_trace_n = 0;
 
 }  // namespace atc
 }  // namespace ec
@@ -679,7 +751,7 @@ extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, f
   atc::Params p{Q, K, V, O, B, H, Lq, Lk, LKP, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, (__half*)split_out, split_kp,
                 D, key_mask, bias};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
-  atc::attention_tc_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(p);
+  atc::attention_tc_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(p);
   return check_launch("ec_attention_tc");
 }
 
@@ -728,8 +800,14 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   rc = tc::get_tensor_map(V2, v_total_rows, v_kp, 64, &tmV);
   if (rc) return rc;
   atc::ParamsT p{O, B, H, Lq, Lk, NB, LB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
-                 q_kp, k_kp, v_kp, q_rows, k_rows};
+                 q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
-  atc::attention_tc_tma_kernel<<<grid, atc::THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   return check_launch("ec_attention_tc_split");
+}
+
+extern "C" int ec_attention_tc_set_trace(void* buf, int n_ctas) {
+  atc::g_trace = (long long*)buf;
+  atc::g_trace_n = buf ? n_ctas : 0;
+  return EC_OK;
 }

@@ -88,6 +88,9 @@ int ec_tc_set_tile_n(int bn);
 /* profiling experiments on ec_gemm_f16x3 (results are WRONG when flags != 0): 1 = operands stay resident
  * (no TMA after the pipeline is primed), 2 = hi*hi product only, 4 = no epilogue stores. */
 int ec_tc_set_debug(int flags);
+/* profiling aid for ec_attention_tc_split: when buf != NULL the first n_ctas CTAs of every launch write ten
+ * clock64() stamps (int64) of their phases to buf[cta][10] (device memory); NULL switches it off. */
+int ec_attention_tc_set_trace(void* buf, int n_ctas);
 
 /* ------------------------------------------------------------------------- normalisation
  * Y[m,:] = LayerNorm(X[m,:] (+ R[m,:])) * w + b  (biased variance, eps inside the sqrt).

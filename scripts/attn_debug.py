@@ -93,8 +93,36 @@ def bench_tma(B, H, N, iters=20):
     print(f"bench attention TMA-fed B{B} H{H} L{N}: {ms:.3f} ms = {4.0 * B * H * N * N * 64 / ms / 1e9:.1f} algorithmic TFLOP/s", flush=True)
 
 
+def trace_tma(B, H, N, n=512):
+    """Per-phase clock stamps of the first `n` CTAs of one launch (scripts only: profiling aid)."""
+    from edgecape_b200 import _lib
+    D = torch.device("cuda")
+    qkv2 = ops.split_f16(torch.randn(B * N, 3 * H * 64, device=D))
+    for _ in range(3):
+        ops.attention_packed_split(qkv2, B, N, H)
+    buf = torch.zeros(n, 10, dtype=torch.int64, device=D)
+    _lib.call("ec_attention_tc_set_trace", buf.data_ptr(), n)
+    ops.attention_packed_split(qkv2, B, N, H)
+    torch.cuda.synchronize()
+    _lib.call("ec_attention_tc_set_trace", None, 0)
+    t = buf.cpu().double()
+    d = t[:, 1:] - t[:, :-1]
+    names = ["setup+tmem_alloc", "Q/K TMA + S mma", "row max", "P chunk 0", "P chunks (rest)", "drain PV",
+             "epilogue", "final sync", "dealloc"]
+    tot = (t[:, 9] - t[:, 0])
+    print(f"trace B{B} H{H} N{N}: CTA total mean {tot.mean():.0f} clk (min {tot.min():.0f} max {tot.max():.0f})")
+    for i, nm in enumerate(names):
+        print(f"  {nm:28s} mean {d[:, i].mean():8.0f}  min {d[:, i].min():8.0f}  max {d[:, i].max():8.0f}")
+    first = t[:148, 0].min()
+    print(f"  span of first {n} CTAs: {(t[:, 9].max() - first):.0f} clk")
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
+    if st == "trace":
+        trace_tma(32, 12, 325)
+        trace_tma(8, 16, 730)
+        sys.exit(0)
     if st == "tma":
         check_tma(1, 64, 1)
         check_tma(1, 128, 1)
