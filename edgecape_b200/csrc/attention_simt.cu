@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(ATT_ROWS) attention_kernel(AttnParams p) {
 #pragma unroll
       for (int d = 0; d < D; d += 2) {
         const float v0 = o[d] * inv, v1 = o[d + 1] * inv;
-        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-        *reinterpret_cast<__half2*>(sp + d) = __halves2half2(h0, h1);
-        *reinterpret_cast<__half2*>(sp + p.split_kp + d) =
-            __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+        __half2 hi, lo;
+        split_pair(v0, v1, hi, lo);
+        *reinterpret_cast<__half2*>(sp + d) = hi;
+        *reinterpret_cast<__half2*>(sp + p.split_kp + d) = lo;
       }
     }
   }

@@ -1,5 +1,6 @@
 // Shared helpers for the edgecape_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -40,6 +41,21 @@ inline int check_launch(const char* what) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// (a, b) -> fp16 pairs hi = rn(a, b), lo = rn((a, b) - hi), so that a ~= hi.x + lo.x to 2^-22.  Uses the packed
+// conversion (cvt.rn.f16x2.f32 -> F2FP.PACK_AB, an ALU op); the scalar __float2half_rn form compiles to F2F,
+// which shares the quarter-rate unit with MUFU and was the limiter of the softmax / split epilogues.
+__device__ __forceinline__ void split_pair(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hi);
+  lo = __floats2half2_rn(a - f.x, b - f.y);
+}
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __half2 h, l;
+  split_pair(a, b, h, l);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

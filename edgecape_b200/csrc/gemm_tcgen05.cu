@@ -318,12 +318,37 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int acc = t & 1;
       const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
       const int m0 = tm * TM + rank * BM, n0 = tn * BN;
+      // residual rows of one sub-chunk (4 rows x 4 columns per lane).  They do not depend on the accumulator, so
+      // the first sub-chunk's are requested before waiting for the MMAs and every later one a sub-chunk ahead:
+      // loaded at the point of use, the four dependent L2 round trips per sub-chunk (the in-place store to C
+      // may alias R, so the compiler cannot hoist them) were the exposed tail of the narrow GEMMs.
+      auto load_res = [&](int sc, float4* out) {
+        const int gcol = n0 + sc * 16 + c4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int row = m0 + quarter * 32 + i * 8 + sub_row;
+          if (sc >= NSUB || gcol >= p.N || row >= p.M) continue;
+          const float* rp = p.R + (long long)(p.res_rows > 0 ? row % p.res_rows : row) * p.ldr + gcol;
+          if (gcol + 3 < p.N && p.vec_r) {
+            out[i] = *reinterpret_cast<const float4*>(rp);
+          } else {
+            out[i].x = rp[0];
+            if (gcol + 1 < p.N) out[i].y = rp[1];
+            if (gcol + 2 < p.N) out[i].z = rp[2];
+            if (gcol + 3 < p.N) out[i].w = rp[3];
+          }
+        }
+      };
+      float4 rcur[4], rnext[4];
+      if (p.R) load_res(group, rcur);
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int sc = group; sc < NSUB; sc += 2) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + sc * 16), r);
+        if (p.R) load_res(sc + 2, rnext);
         if (sc + 2 >= NSUB) {
           // this warp has drained its share of the accumulator: hand it back to the MMA warp early
           tc_fence_before();
@@ -380,16 +405,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int u = 0; u < 4; ++u) y[i][u] *= sv[u];
             if (p.R) {
-              const float* rp = p.R + (long long)(p.res_rows > 0 ? row % p.res_rows : row) * p.ldr + gcol;
-              float rr[4] = {0.f, 0.f, 0.f, 0.f};
-              if (full && p.vec_r) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rp);
-                rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
-              } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (gcol + u < p.N) rr[u] = rp[u];
-              }
+              const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) y[i][u] = (p.res_mode == EC_RES_GATE) ? (y[i][u] + 1.0f) * rr[u] : rr[u] + y[i][u];
             }
@@ -405,24 +421,23 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (p.split_out) {
-              __half hi[4], lo[4];
+              float sc_[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float sc_ = (gcol + u < p.N) ? y[i][u] * p.split_scale : 0.f;
-                hi[u] = __float2half_rn(sc_);
-                lo[u] = __float2half_rn(sc_ - __half2float(hi[u]));
-              }
+              for (int u = 0; u < 4; ++u) sc_[u] = (gcol + u < p.N) ? y[i][u] * p.split_scale : 0.f;
+              uint32_t h01, l01, h23, l23;
+              split_pair(sc_[0], sc_[1], h01, l01);
+              split_pair(sc_[2], sc_[3], h23, l23);
               __half* sp = p.split_out + (long long)row * (2 * p.split_kp) + gcol;   // gcol % 4 == 0: 8 B aligned
-              *reinterpret_cast<uint2*>(sp) = make_uint2(
-                  (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16),
-                  (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16));
-              *reinterpret_cast<uint2*>(sp + p.split_kp) = make_uint2(
-                  (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16),
-                  (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16));
+              *reinterpret_cast<uint2*>(sp) = make_uint2(h01, h23);
+              *reinterpret_cast<uint2*>(sp + p.split_kp) = make_uint2(l01, l23);
             }
           }
         }
         __syncwarp();
+        if (p.R) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+        }
       }
     }
   }
@@ -445,11 +460,11 @@ __global__ void split_f16_kernel(const float* __restrict__ X, __half* __restrict
   float v0 = 0.f, v1 = 0.f;
   if (k < K) v0 = x[k] * scale;
   if (k + 1 < K) v1 = x[k + 1] * scale;
-  const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-  const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+  __half2 hi, lo;
+  split_pair(v0, v1, hi, lo);
   __half2* row = reinterpret_cast<__half2*>(X2 + (long long)m * 2 * Kp);
-  row[k >> 1] = __halves2half2(h0, h1);
-  row[(Kp + k) >> 1] = __halves2half2(l0, l1);
+  row[k >> 1] = hi;
+  row[(Kp + k) >> 1] = lo;
 }
 
 // ------------------------------------------------------------------------- host side

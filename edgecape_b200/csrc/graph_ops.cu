@@ -198,11 +198,12 @@ __global__ void __launch_bounds__(256, 3) gcn_aggregate_split_kernel(const float
       if (w >= K) continue;
       __half* z = Z2 + ((long long)b * K + w) * 2 * Kp;
       const float y0 = a0s[r] * __ldg(Xb + (long long)w * d + c), y1 = acc[r];
-      const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
-      z[c] = h0;
-      z[Kp + c] = __float2half_rn(y0 - __half2float(h0));
-      z[d + c] = h1;
-      z[Kp + d + c] = __float2half_rn(y1 - __half2float(h1));
+      __half2 hi, lo;
+      split_pair(y0, y1, hi, lo);
+      z[c] = __low2half(hi);
+      z[Kp + c] = __low2half(lo);
+      z[d + c] = __high2half(hi);
+      z[Kp + d + c] = __high2half(lo);
     }
   }
   // tail columns: a0, rowsum, zero padding

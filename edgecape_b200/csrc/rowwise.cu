@@ -58,6 +58,73 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     for (int c = C + lane; c < split_kp; c += 32) { sp[c] = __float2half_rn(0.f); sp[split_kp + c] = __float2half_rn(0.f); }
 }
 
+// Vector form for C = NV * 128 with 16-byte aligned rows (every LayerNorm of the ViT and the head): the row
+// lives in registers (NV float4 per lane), so memory is read once; outputs are float4 / packed-fp16 stores.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ X, int ldx, int seg,
+                                                            long long seg_stride, const float* __restrict__ R,
+                                                            int ldr, float* __restrict__ sum_out, int ld_sum,
+                                                            float* __restrict__ Y, int ldy,
+                                                            const float* __restrict__ w,
+                                                            const float* __restrict__ b, float eps, int M,
+                                                            __half* __restrict__ split_out, int split_kp) {
+  constexpr int C = NV * 128;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float* x = seg > 0 ? X + (long long)(m / seg) * seg_stride + (long long)(m % seg) * ldx
+                           : X + (long long)m * ldx;
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const float4*>(x + (j * 32 + lane) * 4);
+  if (R) {
+    const float* r = R + (long long)m * ldr;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(r + (j * 32 + lane) * 4);
+      v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w;
+    }
+  }
+  if (sum_out) {
+    float* so = sum_out + (long long)m * ld_sum;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) *reinterpret_cast<float4*>(so + (j * 32 + lane) * 4) = v[j];
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+    q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q); q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  float* y = Y ? Y + (long long)m * ldy : nullptr;
+  __half* sp = split_out ? split_out + (long long)m * 2 * split_kp : nullptr;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    float4 o;
+    o.x = v[j].x * rstd * ww.x + bb.x;
+    o.y = v[j].y * rstd * ww.y + bb.y;
+    o.z = v[j].z * rstd * ww.z + bb.z;
+    o.w = v[j].w * rstd * ww.w + bb.w;
+    if (y) *reinterpret_cast<float4*>(y + c) = o;
+    if (sp) {
+      uint32_t h01, l01, h23, l23;
+      split_pair(o.x, o.y, h01, l01);
+      split_pair(o.z, o.w, h23, l23);
+      *reinterpret_cast<uint2*>(sp + c) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(sp + split_kp + c) = make_uint2(l01, l23);
+    }
+  }
+  if (sp)
+    for (int c = C + lane; c < split_kp; c += 32) { sp[c] = __float2half_rn(0.f); sp[split_kp + c] = __float2half_rn(0.f); }
+}
+
 __global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__ P, int T, int S, int C,
                                 long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,8 +234,23 @@ extern "C" int ec_layernorm(const float* X, int ldx, int seg, long long seg_stri
   EC_REQUIRE(M >= 0 && C > 0, "ec_layernorm: bad shape");
   if (M == 0) return EC_OK;
   const int warps_per_block = 8;
-  layernorm_kernel<<<cdiv(M, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+  const dim3 grid(cdiv(M, warps_per_block)), block(warps_per_block * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
+  const bool vec = C % 128 == 0 && al16(X) && ldx % 4 == 0 && (seg <= 0 || seg_stride % 4 == 0) &&
+                   (!R || (al16(R) && ldr % 4 == 0)) && (!sum_out || (al16(sum_out) && ld_sum % 4 == 0)) &&
+                   (!Y || (al16(Y) && ldy % 4 == 0)) && al16(w) && al16(b) && (!split_out || al16(split_out));
+#define EC_LN_VEC(NV)                                                                                             \
+  layernorm_vec_kernel<NV><<<grid, block, 0, st>>>(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, \
+                                                   eps, M, (__half*)split_out, split_kp)
+  if (vec && C == 256) EC_LN_VEC(2);
+  else if (vec && C == 384) EC_LN_VEC(3);
+  else if (vec && C == 768) EC_LN_VEC(6);
+  else if (vec && C == 1024) EC_LN_VEC(8);
+  else
+    layernorm_kernel<<<grid, block, 0, st>>>(
       X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, (__half*)split_out, split_kp);
+#undef EC_LN_VEC
   return check_launch("ec_layernorm");
 }
 

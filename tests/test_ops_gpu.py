@@ -83,7 +83,7 @@ def test_gemm_batched_nn_and_tn(K):
 
 
 # ------------------------------------------------------------------------------- rowwise
-@pytest.mark.parametrize("M,C", [(650, 768), (7, 64), (33, 1024), (5, 100)])
+@pytest.mark.parametrize("M,C", [(650, 768), (7, 64), (33, 1024), (5, 100), (100, 256), (13, 384), (9, 512)])
 def test_layernorm(M, C):
     x, r = rnd(M, C, seed=1, scale=3.0), rnd(M, C, seed=2)
     w, b = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
@@ -94,8 +94,9 @@ def test_layernorm(M, C):
     close(s, x + r, tol=1e-7, what="sum_out")
 
 
-def test_layernorm_drops_cls_row_by_striding():
-    B, S, C = 3, 16, 64
+@pytest.mark.parametrize("C", [64, 256])
+def test_layernorm_drops_cls_row_by_striding(C):
+    B, S = 3, 16
     t = rnd(B, S + 1, C, seed=1)
     w, b = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
     want = F.layer_norm(t[:, 1:], (C,), w, b, 1e-5)
