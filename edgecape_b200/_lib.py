@@ -32,6 +32,7 @@ SIGNATURES = {
     "ec_tc_set_tile_n": (c_int, [c_int]),
     "ec_tc_set_debug": (c_int, [c_int]),
     "ec_attention_tc_set_trace": (c_int, [c_fp, c_int]),
+    "ec_attention_tc_set_variant": (c_int, [c_int]),
     "ec_layernorm": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_f,
                              c_int, c_int, c_fp, c_int, c_fp]),
     "ec_add_rows": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(THREADS_T, 1) attention_tc_kernel(Params p) {
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
   const int dsteps = (p.dv + 15) / 16;                  // k-steps of S = Q K^T that carry data (head dim 32: 2 of 4)
 
-  if (tid == THREADS) {
+  if (warp == THREADS / 32 && elect_one()) {
     mbar_init(bar_s, 1);
     mbar_init(bar_pv0, 1);
     mbar_init(bar_pv1, 1);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(THREADS_T, 1) attention_tc_kernel(Params p) {
 
   if (control) {
     // ================================================================== control warp
-    if (lane == 0) {
+    if (elect_one()) {
       // S = Q K^T  (all keys, into TMEM)
       const int n0 = p.LKP <= 256 ? p.LKP : ((p.LKP / 2 + 15) / 16) * 16;
       for (int noff = 0; noff < p.LKP; noff += n0) {
@@ -438,6 +438,7 @@ struct ParamsT {
   int q_rows, k_rows;               // rows per batch element in the Q and K/V buffers
   long long* trace;                 // optional [trace_n][10] clock64 stamps of CTA phases (ec_attention_tc_set_trace)
   int trace_n;
+  int wide;                         // P-in-TMEM kernel: P_hi [V_hi | V_lo] as one N = 128 MMA (one key block <= 384 keys)
 };
 
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
@@ -494,7 +495,7 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   };
 
-  if (tid == THREADS) {
+  if (warp == THREADS / 32 && elect_one()) {
     mbar_init(bar_qk, 1); mbar_init(bar_s, 1);
     mbar_init(bar_pv0, 1); mbar_init(bar_pv1, 1);
     mbar_init(bar_v, 1);
@@ -515,7 +516,7 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   if (warp == THREADS / 32) {
     // ================================================================== control warp: TMA + MMA issue
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_o = make_idesc_bmn(D);
       int g = 0;
       for (int blk = 0; blk < p.NB; ++blk) {
@@ -708,6 +709,287 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   stamp(9);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// P-in-TMEM variant (the default).  The shared-memory P path above is bound by shared-memory bandwidth in the
+// P V phase: per 64-key chunk the MMAs re-read P three times (48 KB) and V three times (24 KB) and the softmax
+// warps write P once (32 KB) -- 104 KB at 128 B/clk is ~810 clk, more than the exponentials cost.  Here each
+// softmax warp writes its 16 probabilities back into the 16 TMEM columns it read them from, as packed fp16:
+// columns [c, c+8) = hi(p[2j], p[2j+1]), columns [c+8, c+16) = lo -- exactly one K = 16 A-operand slice each --
+// and the MMAs take A from TMEM (tcgen05.mma [d], [a], b_desc).  No P buffers, no buffer hand-back, the only
+// shared-memory traffic of the phase is V (24 KB per chunk), and every chunk has its own "P ready" barrier so
+// the softmax warps run ahead freely.
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+        "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+constexpr int MAX_CHUNKS = 8;
+
+__global__ void __launch_bounds__(THREADS_T, 1)
+attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, ParamsT p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int NKB = p.LB / 64;                            // 64-key boxes / chunks per block
+  const int data_bytes = Q_BYTES + 2 * NKB * BOX_BYTES; // V (NKB * 16 KB) aliases Q / K once S is complete
+  const uint32_t misc = base + data_bytes;
+  const uint32_t bar_qk = misc, bar_s = misc + 8, bar_v = misc + 16, bar_o = misc + 24, bar_sf = misc + 32,
+                 tmem_slot = misc + 40, bar_pr = misc + 48;            // bar_pr: MAX_CHUNKS barriers, one per chunk
+  float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 128);   // [NPART][BM]
+  float* xsum = xmax + NPART * BM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, part = (warp >> 2) & 3;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* trace = (p.trace && tid == 0 && cta < p.trace_n) ? p.trace + 10 * cta : nullptr;
+  auto stamp = [&](int i) {
+    if (trace) trace[i] = clock64();
+  };
+  stamp(0);
+  const uint32_t q_hi = base, q_lo = base + BM * 128, k_hi = base + Q_BYTES, k_lo = k_hi + NKB * BOX_BYTES;
+  const int qrow = b * p.q_rows + q0, krow = b * p.k_rows;
+
+  auto load_qk = [&](int blk) {   // Q tile (2 boxes) and the keys of block `blk` (NKB boxes), hi and lo halves
+    mbar_expect_tx(bar_qk, (uint32_t)((2 + NKB) * 2 * BOX_BYTES));
+    for (int j = 0; j < 2; ++j) {
+      tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * D, qrow + 64 * j);
+      tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * D, qrow + 64 * j);
+    }
+    for (int j = 0; j < NKB; ++j) {
+      tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * D, krow + blk * p.LB + 64 * j);
+      tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * D, krow + blk * p.LB + 64 * j);
+    }
+  };
+
+  if (warp == THREADS / 32 && elect_one()) {
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_sf, THREADS / 32);
+    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(bar_pr + 8 * i, THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    load_qk(0);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  stamp(1);
+
+  if (warp == THREADS / 32) {
+    // ================================================================== control warp: TMA + MMA issue
+    if (elect_one()) {
+      const uint32_t idesc_o = make_idesc_bmn(D), idesc_w = make_idesc_bmn(2 * D);
+      for (int blk = 0; blk < p.NB; ++blk) {
+        const int key0 = blk * p.LB;
+        const int nkeys = min(p.LB, p.Lk - key0);
+        const int lkp = (nkeys + 15) / 16 * 16;
+        const int nchunks = (nkeys + KC - 1) / KC;
+        const uint32_t o_col = 512 - 64 * (p.NB - blk);
+        if (blk > 0) {                                   // P of the previous block consumed by its MMAs, S consumed
+          mbar_wait(bar_sf, (blk - 1) & 1);
+          tc_fence_after();
+          load_qk(blk);
+        }
+        mbar_wait(bar_qk, blk & 1);
+        tc_fence_after();
+        {
+          const int n0 = lkp <= 256 ? lkp : ((lkp / 2 + 15) / 16) * 16;
+          for (int noff = 0; noff < lkp; noff += n0) {
+            const int n = min(n0, lkp - noff);
+            const uint32_t idesc = make_idesc(n);
+            const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+            const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+          }
+          umma_commit(bar_s);
+        }
+        // Q / K shared memory is dead once S is complete: the V chunks of the block ([64 keys][64 d], hi and lo)
+        // are loaded over it while the softmax warps take the row max
+        mbar_wait(bar_s, blk & 1);
+        mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
+        for (int i = 0; i < nchunks; ++i) {
+          const uint32_t v_hi = base + i * VBUF_BYTES;
+          tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, krow + key0 + i * KC);
+          tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, krow + key0 + i * KC);
+        }
+        mbar_wait(bar_v, blk & 1);
+        for (int i = 0; i < nchunks; ++i) {
+          const uint32_t v_hi = base + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
+          mbar_wait(bar_pr + 8 * i, blk & 1);
+          tc_fence_after();
+          const int valid = min(KC, nkeys - i * KC);
+          const int ksteps = (valid + 15) / 16;
+          const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
+          const uint32_t a0 = tmem_base + i * KC;        // P of keys [16k, 16k+16): hi at +16k, lo at +16k+8
+          // V: MN-major, 16 key rows = two 1024 B atoms per step
+          if (p.wide) {
+            // every tcgen05.mma costs >= ~99 clk whatever its N (scripts/probes/umma_probe.cu), so the MMA count is
+            // what matters: V_lo sits 8 KB after V_hi, exactly the MN-atom stride of the descriptor, and one N = 128
+            // MMA yields P_hi V_hi (columns 384..447) and P_hi V_lo (448..511); the epilogue adds the halves.
+            for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + 384, a0 + 16 * k, bv_hi + 128 * k, idesc_w, (i | k) ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + 384, a0 + 16 * k + 8, bv_hi + 128 * k, idesc_o, 1u);
+          } else {
+            for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + o_col, a0 + 16 * k + 8, bv_hi + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + o_col, a0 + 16 * k, bv_lo + 128 * k, idesc_o, 1u);
+            for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + o_col, a0 + 16 * k, bv_hi + 128 * k, idesc_o, 1u);
+          }
+        }
+        umma_commit(bar_o);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== softmax warps
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;   // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
+    float bmax0 = -INFINITY, bmax1 = -INFINITY, bsum0 = 0.f, bsum1 = 0.f;
+    for (int blk = 0; blk < p.NB; ++blk) {
+      const int key0 = blk * p.LB;
+      const int nkeys = min(p.LB, p.Lk - key0);        // valid keys of this block
+      const int nchunks = (nkeys + KC - 1) / KC;
+      mbar_wait(bar_s, blk & 1);
+      tc_fence_after();
+      if (blk == 0) stamp(2);
+      // -------------------------------------------------------------- row max over the block
+      const int nchunk32 = (nkeys + 31) / 32;
+      float mymax = -INFINITY;
+      for (int j = part; j < nchunk32; j += NPART) {
+        float s[32];
+        tmem_ld32(t_row + j * 32, s);
+        if (j * 32 + 32 <= nkeys) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) mymax = fmaxf(mymax, s[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (j * 32 + u < nkeys) mymax = fmaxf(mymax, s[u]);
+        }
+      }
+      if (blk > 0) softmax_sync();                     // xmax of the previous block has been consumed
+      xmax[part * BM + row] = mymax;
+      softmax_sync();                                  // also: every warp is done reading S for the max pass
+      float rmax = xmax[row];
+#pragma unroll
+      for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+      if (blk == 0) bmax0 = rmax; else bmax1 = rmax;
+      if (blk == 0) stamp(3);
+      // -------------------------------------------------------------- P = exp(S - max), in place in TMEM
+      const float nb = -rmax * sl2;
+      float rsum = 0.f;
+      for (int i = 0; i < nchunks; ++i) {
+        float s[PW];
+        const int kbase = i * KC + PW * part;
+        tmem_ld16(t_row + kbase, s);
+        if (kbase + PW <= nkeys) {
+#pragma unroll
+          for (int u = 0; u < PW; ++u) {
+            s[u] = ex2(fmaf(s[u], sl2, nb));
+            rsum += s[u];
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < PW; ++u) {
+            s[u] = (kbase + u < nkeys) ? ex2(fmaf(s[u], sl2, nb)) : 0.f;
+            rsum += s[u];
+          }
+        }
+        uint32_t pk[PW];
+#pragma unroll
+        for (int j = 0; j < PW / 2; ++j) split_pair(s[2 * j], s[2 * j + 1], pk[j], pk[PW / 2 + j]);
+        tmem_st16(t_row + kbase, pk);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pr + 8 * i);
+        if (blk == 0 && i == 0) stamp(4);
+      }
+      if (blk == 0) bsum0 = rsum; else bsum1 = rsum;
+      if (blk == 0) stamp(5);
+      mbar_wait(bar_o, blk & 1);                       // every P V MMA of the block is complete
+      tc_fence_after();
+      if (blk == 0) stamp(6);
+      if (blk + 1 < p.NB) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sf);
+      }
+    }
+
+    // ---------------------------------------------------------------- merge the key blocks, normalise, store
+    const float m = fmaxf(bmax0, bmax1);
+    const float w0 = ex2((bmax0 - m) * sl2), w1 = p.NB > 1 ? ex2((bmax1 - m) * sl2) : 0.f;
+    xsum[part * BM + row] = bsum0 * w0 + bsum1 * w1;
+    softmax_sync();
+    float tot = 0.f;
+#pragma unroll
+    for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
+    const float inv = 1.0f / tot;
+    {
+      constexpr int OW = D / NPART;
+      float o[OW];
+      tmem_ld16(t_row + (p.wide ? 384 : 512 - 64 * p.NB) + OW * part, o);
+      if (p.NB > 1 || p.wide) {
+        float o1[OW];
+        tmem_ld16(t_row + 448 + OW * part, o1);
+        const float wa = p.wide ? 1.f : w0, wb = p.wide ? 1.f : w1;
+#pragma unroll
+        for (int u = 0; u < OW; ++u) o[u] = o[u] * wa + o1[u] * wb;
+      }
+      const int grow = q0 + row;
+      if (grow < p.Lq) {
+#pragma unroll
+        for (int u = 0; u < OW; ++u) o[u] *= inv;
+        if (p.O) {
+          float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
+#pragma unroll
+          for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        }
+        if (p.split_out) {
+          __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
+#pragma unroll
+          for (int j = 0; j < OW / 8; ++j) {
+            uint4 hi, lo;
+            split8(o + 8 * j, hi, lo);
+            *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
+            *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+          }
+        }
+      }
+    }
+    stamp(7);
+  }
+  tc_fence_before();
+  __syncthreads();
+  stamp(8);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+  stamp(9);
+}
+
+static int g_variant = 0;   // 0: P in TMEM + wide P V MMAs, 2: P in TMEM, three N = 64 MMAs per k-step, 1: P through shared memory
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
 
@@ -795,14 +1077,32 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   rc = tc::get_tensor_map(V2, v_total_rows, v_kp, 64, &tmV);
   if (rc) return rc;
   atc::ParamsT p{O, B, H, Lq, Lk, NB, LB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
-                 q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n};
+                 q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n,
+                 (atc::g_variant == 0 && NB == 1 && LB <= 384) ? 1 : 0};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
-  atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  if (atc::g_variant != 1) {
+    static bool ts_attr_set = false;
+    if (!ts_attr_set) {
+      EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
+      ts_attr_set = true;
+    }
+    atc::attention_tc_ts_kernel<<<grid, atc::THREADS_T, kq + atc::MISC_BYTES + 1024, (cudaStream_t)stream>>>(tmQ, tmK,
+                                                                                                             tmV, p);
+  } else {
+    atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  }
   return check_launch("ec_attention_tc_split");
 }
 
 extern "C" int ec_attention_tc_set_trace(void* buf, int n_ctas) {
   atc::g_trace = (long long*)buf;
   atc::g_trace_n = buf ? n_ctas : 0;
+  return EC_OK;
+}
+
+extern "C" int ec_attention_tc_set_variant(int variant) {
+  EC_REQUIRE(variant >= 0 && variant <= 2, "ec_attention_tc_set_variant: 0, 1 or 2");
+  atc::g_variant = variant;
   return EC_OK;
 }

@@ -57,6 +57,17 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// One lane of a converged warp.  Code that issues tcgen05.mma / TMA / tcgen05.commit must be guarded by this
+// (inside a warp-uniform branch), not by `lane == 0`: those are uniform-datapath instructions, and under a
+// lane-id branch ptxas wraps EVERY one of them in an ELECT / BRA.U.ANY serialisation loop with R2UR operand
+// moves -- ~98 clk per tcgen05.mma whatever its shape (scripts/probes/umma_probe.cu), against 32..128 clk of
+// tensor-pipe time.  After elect.sync ptxas knows a single thread is active and emits them back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -223,7 +223,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -258,7 +258,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;

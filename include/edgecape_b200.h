@@ -91,6 +91,10 @@ int ec_tc_set_debug(int flags);
 /* profiling aid for ec_attention_tc_split: when buf != NULL the first n_ctas CTAs of every launch write ten
  * clock64() stamps (int64) of their phases to buf[cta][10] (device memory); NULL switches it off. */
 int ec_attention_tc_set_trace(void* buf, int n_ctas);
+/* ec_attention_tc_split kernel variant: 0 (default) keeps the probabilities in TMEM as the A operand of the
+ * P V MMAs and folds P_hi V_hi, P_hi V_lo into one N = 128 MMA; 2 = P in TMEM, three N = 64 MMAs per k-step;
+ * 1 = probabilities through shared memory.  1 and 2 are kept for A/B measurements. */
+int ec_attention_tc_set_variant(int variant);
 
 /* ------------------------------------------------------------------------- normalisation
  * Y[m,:] = LayerNorm(X[m,:] (+ R[m,:])) * w + b  (biased variance, eps inside the sqrt).

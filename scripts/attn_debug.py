@@ -119,6 +119,10 @@ def trace_tma(B, H, N, n=512):
 
 if __name__ == "__main__":
     st = sys.argv[1]
+    if "@" in st:                 # A/B: tma@1 = probabilities through shared memory, tma@2 = TMEM, narrow MMAs
+        from edgecape_b200 import _lib
+        st, v = st.split("@")
+        _lib.call("ec_attention_tc_set_variant", int(v))
     if st == "trace":
         trace_tma(32, 12, 325)
         trace_tma(8, 16, 730)
