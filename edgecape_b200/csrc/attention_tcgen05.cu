@@ -737,7 +737,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
 }
 constexpr int MAX_CHUNKS = 8;
 
-__global__ void __launch_bounds__(THREADS_T, 1)
+constexpr int THREADS_TS = THREADS + 64;   // 16 softmax warps, control warp, second S-issuing warp
+
+__global__ void __launch_bounds__(THREADS_TS, 1)
 attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, ParamsT p) {
   extern __shared__ uint8_t smem_raw[];
@@ -776,7 +778,7 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   };
 
   if (warp == THREADS / 32 && elect_one()) {
-    mbar_init(bar_qk, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 2); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
     mbar_init(bar_sf, THREADS / 32);
     for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(bar_pr + 8 * i, THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -792,7 +794,38 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
   stamp(1);
 
-  if (warp == THREADS / 32) {
+  // S = Q K^T of one key block.  A tcgen05.mma costs its issuing thread >= ~98 clk whatever its shape, so the
+  // two halves of the key range are issued by two warps concurrently (disjoint TMEM columns); each commits
+  // once to bar_s (count 2).
+  auto issue_s = [&](int half, int lkp) {
+    const int n0 = ((lkp / 2 + 15) / 16) * 16;
+    const int noff = half ? n0 : 0, n = half ? lkp - n0 : n0;
+    if (n > 0) {
+      const uint32_t idesc = make_idesc(n);
+      const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+      const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+    }
+    umma_commit(bar_s);
+  };
+
+  if (warp == THREADS / 32 + 1) {
+    // ================================================================== second S-issuing warp
+    if (elect_one()) {
+      for (int blk = 0; blk < p.NB; ++blk) {
+        const int nkeys = min(p.LB, p.Lk - blk * p.LB);
+        mbar_wait(bar_qk, blk & 1);
+        tc_fence_after();
+        issue_s(1, (nkeys + 15) / 16 * 16);
+      }
+    }
+    __syncwarp();
+  } else if (warp == THREADS / 32) {
     // ================================================================== control warp: TMA + MMA issue
     if (elect_one()) {
       const uint32_t idesc_o = make_idesc_bmn(D), idesc_w = make_idesc_bmn(2 * D);
@@ -809,22 +842,7 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         mbar_wait(bar_qk, blk & 1);
         tc_fence_after();
-        {
-          const int n0 = lkp <= 256 ? lkp : ((lkp / 2 + 15) / 16) * 16;
-          for (int noff = 0; noff < lkp; noff += n0) {
-            const int n = min(n0, lkp - noff);
-            const uint32_t idesc = make_idesc(n);
-            const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
-            const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
-#pragma unroll
-            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
-#pragma unroll
-            for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
-          }
-          umma_commit(bar_s);
-        }
+        issue_s(0, lkp);                                 // key columns [0, n0); warp 17 issues [n0, lkp)
         // Q / K shared memory is dead once S is complete: the V chunks of the block ([64 keys][64 d], hi and lo)
         // are loaded over it while the softmax warps take the row max
         mbar_wait(bar_s, blk & 1);
@@ -958,22 +976,38 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int u = 0; u < OW; ++u) o[u] = o[u] * wa + o1[u] * wb;
       }
       const int grow = q0 + row;
-      if (grow < p.Lq) {
 #pragma unroll
-        for (int u = 0; u < OW; ++u) o[u] *= inv;
+      for (int u = 0; u < OW; ++u) o[u] *= inv;
+      if (grow < p.Lq) {
         if (p.O) {
           float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
 #pragma unroll
           for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
         }
-        if (p.split_out) {
-          __half* sp = p.split_out + ((long long)b * p.Lq + grow) * (2 * p.split_kp) + h * D + OW * part;
+      }
+      if (p.split_out) {
+        // Written straight from the TMEM layout every lane owns a different row (16-byte pieces 3 KB apart: 2048
+        // store wavefronts per CTA, ~2K clk of LSU time).  Instead the tile goes through shared memory (dead by
+        // now: every MMA has retired) as [row][hi 128 B | lo 128 B], 16-byte chunks XOR-swizzled by the row, and
+        // is written out as whole 128-byte lines: 16 lanes per row.
 #pragma unroll
-          for (int j = 0; j < OW / 8; ++j) {
-            uint4 hi, lo;
-            split8(o + 8 * j, hi, lo);
-            *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
-            *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
+        for (int j = 0; j < OW / 8; ++j) {
+          uint4 hi, lo;
+          split8(o + 8 * j, hi, lo);
+          const int c = (OW / 8) * part + j;             // 16-byte chunk of the hi half; lo is chunk 8 + c
+          *reinterpret_cast<uint4*>(gbase + row * 256 + ((c ^ (row & 15)) << 4)) = hi;
+          *reinterpret_cast<uint4*>(gbase + row * 256 + (((8 + c) ^ (row & 15)) << 4)) = lo;
+        }
+        softmax_sync();
+        const int w16 = warp;                            // 0..15: rows [8 w16, 8 w16 + 8)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = 8 * w16 + 2 * it + (lane >> 4), c = lane & 15;
+          if (q0 + r < p.Lq) {
+            const uint4 v = *reinterpret_cast<const uint4*>(gbase + r * 256 + ((c ^ (r & 15)) << 4));
+            __half* sp = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp) + h * D +
+                         (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
+            *reinterpret_cast<uint4*>(sp) = v;
           }
         }
       }
@@ -1087,7 +1121,7 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
                                    atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
       ts_attr_set = true;
     }
-    atc::attention_tc_ts_kernel<<<grid, atc::THREADS_T, kq + atc::MISC_BYTES + 1024, (cudaStream_t)stream>>>(tmQ, tmK,
+    atc::attention_tc_ts_kernel<<<grid, atc::THREADS_TS, kq + atc::MISC_BYTES + 1024, (cudaStream_t)stream>>>(tmQ, tmK,
                                                                                                              tmV, p);
   } else {
     atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);

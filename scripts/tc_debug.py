@@ -91,6 +91,22 @@ if __name__ == "__main__":
         check(650, 3072, 768)
         check(10400, 2304, 768)
         sys.exit(0)
+    if stage == "modes":
+        # every tile mode on the ViT and head shapes: input to the mode heuristic of ec_gemm_f16x3
+        from edgecape_b200 import _lib
+        shapes = [(10400, 2304, 768), (10400, 768, 768), (10400, 3072, 768), (10400, 768, 3072), (5184, 256, 768),
+                  (5184, 1024, 512), (5184, 512, 512), (5184, 256, 512), (1600, 512, 512), (1600, 768, 256),
+                  (1600, 256, 512), (1600, 2048, 256), (1600, 256, 2048), (1600, 256, 256), (6784, 768, 256),
+                  (6784, 2048, 256), (6784, 256, 2048), (6784, 256, 256), (1600, 512, 1024)]
+        for shp in shapes:
+            print("shape", shp)
+            for bn in (128, 256, 512):
+                if bn == 512 and shp[1] < 256:
+                    continue
+                _lib.load().ec_tc_set_tile_n(bn)
+                print(f"  mode {bn}:", end="")
+                bench(*shp, iters=30, simt=False)
+        sys.exit(0)
     if stage == "pairbench":
         from edgecape_b200 import _lib
         for bn in (512, 128):
