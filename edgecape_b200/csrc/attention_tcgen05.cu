@@ -439,6 +439,9 @@ struct ParamsT {
   long long* trace;                 // optional [trace_n][10] clock64 stamps of CTA phases (ec_attention_tc_set_trace)
   int trace_n;
   int wide;                         // P-in-TMEM kernel: P_hi [V_hi | V_lo] as one N = 128 MMA (one key block <= 384 keys)
+  int dv;                           // head dim, 32 or 64 (P-in-TMEM kernel; boxes are 64 columns wide either way)
+  const uint8_t* key_mask;          // [B, Lk], 1 = ignore key, or NULL   (P-in-TMEM kernel, one key block)
+  const float* bias;                // [B, H, Lq, Lk] additive, or NULL   (P-in-TMEM kernel, one key block)
 };
 
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
@@ -752,6 +755,7 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                  tmem_slot = misc + 40, bar_pr = misc + 48;            // bar_pr: MAX_CHUNKS barriers, one per chunk
   float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 128);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;
+  uint8_t* msk = reinterpret_cast<uint8_t*>(xsum + NPART * BM);       // [<= 448] key-padding mask of this batch row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, part = (warp >> 2) & 3;
@@ -768,12 +772,12 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   auto load_qk = [&](int blk) {   // Q tile (2 boxes) and the keys of block `blk` (NKB boxes), hi and lo halves
     mbar_expect_tx(bar_qk, (uint32_t)((2 + NKB) * 2 * BOX_BYTES));
     for (int j = 0; j < 2; ++j) {
-      tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * D, qrow + 64 * j);
-      tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * D, qrow + 64 * j);
+      tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * p.dv, qrow + 64 * j);
+      tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * p.dv, qrow + 64 * j);
     }
     for (int j = 0; j < NKB; ++j) {
-      tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * D, krow + blk * p.LB + 64 * j);
-      tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * D, krow + blk * p.LB + 64 * j);
+      tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * p.dv, krow + blk * p.LB + 64 * j);
+      tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * p.dv, krow + blk * p.LB + 64 * j);
     }
   };
 
@@ -804,12 +808,10 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t idesc = make_idesc(n);
       const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
       const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+      const int dsteps = p.dv / 16;                   // head dim 32: the upper half of the box is the next head
+      for (int k = 0; k < dsteps; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+      for (int k = 0; k < dsteps; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+      for (int k = 0; k < dsteps; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
     }
     umma_commit(bar_s);
   };
@@ -849,8 +851,8 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_expect_tx(bar_v, (uint32_t)(nchunks * 2 * BOX_BYTES));
         for (int i = 0; i < nchunks; ++i) {
           const uint32_t v_hi = base + i * VBUF_BYTES;
-          tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, krow + key0 + i * KC);
-          tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, krow + key0 + i * KC);
+          tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * p.dv, krow + key0 + i * KC);
+          tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * p.dv, krow + key0 + i * KC);
         }
         mbar_wait(bar_v, blk & 1);
         for (int i = 0; i < nchunks; ++i) {
@@ -884,6 +886,15 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;   // exp(scale * (s - max)) = exp2((s - max) * scale * log2 e)
     float bmax0 = -INFINITY, bmax1 = -INFINITY, bsum0 = 0.f, bsum1 = 0.f;
+    // key mask / additive bias (the decoder and encoder attentions of the head; always one key block): the
+    // logits become x = s * scale + bias over the unmasked keys
+    const bool gen = p.key_mask != nullptr || p.bias != nullptr;
+    const float* bias_row = (p.bias && q0 + row < p.Lq)
+                                ? p.bias + (((long long)b * p.H + h) * p.Lq + (q0 + row)) * p.Lk : nullptr;
+    if (gen) {
+      for (int j = tid; j < p.LB; j += THREADS) msk[j] = (j < p.Lk && p.key_mask) ? p.key_mask[(long long)b * p.Lk + j] : 0;
+      softmax_sync();
+    }
     for (int blk = 0; blk < p.NB; ++blk) {
       const int key0 = blk * p.LB;
       const int nkeys = min(p.LB, p.Lk - key0);        // valid keys of this block
@@ -897,7 +908,14 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int j = part; j < nchunk32; j += NPART) {
         float s[32];
         tmem_ld32(t_row + j * 32, s);
-        if (j * 32 + 32 <= nkeys) {
+        if (gen) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const int key = j * 32 + u;
+            if (key < nkeys && !msk[key])
+              mymax = fmaxf(mymax, bias_row ? fmaf(s[u], p.scale, __ldg(bias_row + key)) : s[u] * p.scale);
+          }
+        } else if (j * 32 + 32 <= nkeys) {
 #pragma unroll
           for (int u = 0; u < 32; ++u) mymax = fmaxf(mymax, s[u]);
         } else {
@@ -912,6 +930,7 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float rmax = xmax[row];
 #pragma unroll
       for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+      if (rmax == -INFINITY) rmax = 0.f;               // fully masked row: every p below is 0
       if (blk == 0) bmax0 = rmax; else bmax1 = rmax;
       if (blk == 0) stamp(3);
       // -------------------------------------------------------------- P = exp(S - max), in place in TMEM
@@ -921,7 +940,17 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         float s[PW];
         const int kbase = i * KC + PW * part;
         tmem_ld16(t_row + kbase, s);
-        if (kbase + PW <= nkeys) {
+        if (gen) {
+          const float L2E = 1.4426950408889634f;
+#pragma unroll
+          for (int u = 0; u < PW; ++u) {
+            const int key = kbase + u;
+            const bool ok = key < nkeys && !msk[key];
+            const float x = (ok && bias_row) ? fmaf(s[u], p.scale, __ldg(bias_row + key)) : s[u] * p.scale;
+            s[u] = ok ? ex2((x - rmax) * L2E) : 0.f;
+            rsum += s[u];
+          }
+        } else if (kbase + PW <= nkeys) {
 #pragma unroll
           for (int u = 0; u < PW; ++u) {
             s[u] = ex2(fmaf(s[u], sl2, nb));
@@ -957,15 +986,15 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
     // ---------------------------------------------------------------- merge the key blocks, normalise, store
     const float m = fmaxf(bmax0, bmax1);
-    const float w0 = ex2((bmax0 - m) * sl2), w1 = p.NB > 1 ? ex2((bmax1 - m) * sl2) : 0.f;
+    const float w0 = p.NB > 1 ? ex2((bmax0 - m) * sl2) : 1.f, w1 = p.NB > 1 ? ex2((bmax1 - m) * sl2) : 0.f;
     xsum[part * BM + row] = bsum0 * w0 + bsum1 * w1;
     softmax_sync();
     float tot = 0.f;
 #pragma unroll
     for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
-    const float inv = 1.0f / tot;
-    {
-      constexpr int OW = D / NPART;
+    const float inv = tot > 0.f ? 1.0f / tot : 0.f;    // fully masked row -> 0 (as the fp32 kernels)
+    constexpr int OW = D / NPART;
+    if (OW * part < p.dv) {                            // warp-uniform: head dim 32 keeps parts 0 and 1
       float o[OW];
       tmem_ld16(t_row + (p.wide ? 384 : 512 - 64 * p.NB) + OW * part, o);
       if (p.NB > 1 || p.wide) {
@@ -980,7 +1009,7 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int u = 0; u < OW; ++u) o[u] *= inv;
       if (grow < p.Lq) {
         if (p.O) {
-          float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
+          float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * p.dv + OW * part);
 #pragma unroll
           for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
         }
@@ -998,17 +1027,20 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           *reinterpret_cast<uint4*>(gbase + row * 256 + ((c ^ (row & 15)) << 4)) = hi;
           *reinterpret_cast<uint4*>(gbase + row * 256 + (((8 + c) ^ (row & 15)) << 4)) = lo;
         }
-        softmax_sync();
-        const int w16 = warp;                            // 0..15: rows [8 w16, 8 w16 + 8)
+      }
+    }
+    if (p.split_out) {
+      softmax_sync();
+      const int w16 = warp;                              // 0..15: rows [8 w16, 8 w16 + 8)
+      const int nch = p.dv / 8;                          // 16-byte chunks per half
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = 8 * w16 + 2 * it + (lane >> 4), c = lane & 15;
-          if (q0 + r < p.Lq) {
-            const uint4 v = *reinterpret_cast<const uint4*>(gbase + r * 256 + ((c ^ (r & 15)) << 4));
-            __half* sp = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp) + h * D +
-                         (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
-            *reinterpret_cast<uint4*>(sp) = v;
-          }
+      for (int it = 0; it < 4; ++it) {
+        const int r = 8 * w16 + 2 * it + (lane >> 4), c = lane & 15;
+        if (q0 + r < p.Lq && (c & 7) < nch) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gbase + r * 256 + ((c ^ (r & 15)) << 4));
+          __half* sp = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp) + h * p.dv +
+                       (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
+          *reinterpret_cast<uint4*>(sp) = v;
         }
       }
     }
@@ -1071,10 +1103,11 @@ extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, f
 extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
                                      const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
                                      int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H, int Lq,
-                                     int Lk, int ldo, long long so, float scale, void* split_out, int split_kp,
-                                     void* stream) {
+                                     int Lk, int ldo, long long so, float scale, int dv, const uint8_t* key_mask,
+                                     const float* bias, void* split_out, int split_kp, void* stream) {
   EC_REQUIRE(Q2 && K2 && V2 && (O || split_out), "ec_attention_tc_split: null pointer");
   EC_REQUIRE(B >= 0 && H > 0 && Lq >= 0 && Lk > 0, "ec_attention_tc_split: bad shape");
+  EC_REQUIRE(dv == 32 || dv == 64, "ec_attention_tc_split: head dim must be 32 or 64");
   EC_REQUIRE(q_kp % 64 == 0 && k_kp % 64 == 0 && v_kp % 64 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0,
              "ec_attention_tc_split: halves must be multiples of 64 columns, head offsets multiples of 8");
   // one key block up to 448 keys, two blocks (each a multiple of 64, <= 384) up to 768
@@ -1087,8 +1120,13 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
       return EC_ERR_UNSUPPORTED;
     }
   }
-  EC_REQUIRE(!split_out || (split_kp == H * atc::D && (((uintptr_t)split_out) & 15) == 0),
-             "ec_attention_tc_split: split_out needs split_kp == H*64 and 16-byte alignment");
+  const bool general = dv != 64 || key_mask || bias;   // needs the P-in-TMEM kernel, one key block
+  if (general && NB != 1) {
+    set_error("ec_attention_tc_split: head dim 32 / key mask / bias need <= 448 keys (got %d)", Lk);
+    return EC_ERR_UNSUPPORTED;
+  }
+  EC_REQUIRE(!split_out || (split_kp == H * dv && split_kp % 64 == 0 && (((uintptr_t)split_out) & 15) == 0),
+             "ec_attention_tc_split: split_out needs split_kp == H*dv (a multiple of 64) and 16-byte alignment");
   EC_REQUIRE(!O || (aligned16(O) && ldo % 4 == 0 && so % 4 == 0), "ec_attention_tc_split: O must be 16-byte aligned");
   if (B == 0 || Lq == 0) return EC_OK;
   EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc_split: grid too large");
@@ -1112,9 +1150,9 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   if (rc) return rc;
   atc::ParamsT p{O, B, H, Lq, Lk, NB, LB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
                  q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n,
-                 (atc::g_variant == 0 && NB == 1 && LB <= 384) ? 1 : 0};
+                 (atc::g_variant != 2 && NB == 1 && LB <= 384) ? 1 : 0, dv, key_mask, bias};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
-  if (atc::g_variant != 1) {
+  if (atc::g_variant != 1 || general) {
     static bool ts_attr_set = false;
     if (!ts_attr_set) {
       EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

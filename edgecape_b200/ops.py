@@ -199,6 +199,19 @@ def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None
     return (y, None) if split_out else y
 
 
+def tc_linear_ok(x, w):
+    """Would linear(x, w) run on the tcgen05 kernel?  (callers use it to choose the split-fp16 chain)"""
+    if w.dim() > 2:
+        w = w.reshape(w.shape[0], -1)
+    return _tc_ok(x, w, None)
+
+
+def linear_split(x, w, bias=None, act=ACT_NONE):
+    """linear() whose only output is the split-fp16 operand the next tensor-core kernel consumes."""
+    assert tc_linear_ok(x, w)
+    return linear(x, w, bias, act=act, split_out=True, fp32_out=False)[1]
+
+
 def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None, split="no"):
     """LayerNorm over the last dim of x (+ residual).  A 3-D x view [B,S,C] with a batch stride
     larger than S*ld (e.g. ViT tokens without the cls row) is read in place.
@@ -325,31 +338,54 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, s
     return sp if split == "only" else ((out, sp) if split == "also" else out)
 
 
-def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only"):
-    """Self-attention over a packed split-fp16 QKV operand (the split output of the QKV GEMM):
-    qkv2 rows = B*N tokens, columns [q | k | v] of C = nheads*64 each per half.  TMA-fed tcgen05 kernel."""
-    C = qkv2.K // 3
-    D = C // nheads
-    assert D == 64 and qkv2.rows == B * N and qkv2.Kp == qkv2.K and N <= 768
-    dev = qkv2.data.device
+def attention_split(q2, q_col, q_rows, k2, k_col, v2, v_col, k_rows, B, nheads, Lq, Lk, D, scale=None,
+                    key_mask=None, bias=None, out=None, split="only"):
+    """softmax(Q K^T * scale + bias, masked) V on split-fp16 operands (the split outputs of the projections):
+    head h of Q is columns q_col + D*h of each half of q2, rows b*q_rows + i; K / V likewise with k_rows rows
+    per batch element.  TMA-fed tcgen05 kernel with the probabilities in TMEM.  D in (32, 64)."""
+    for t in (q2, k2, v2):
+        assert isinstance(t, SplitOperand) and t.scale == 1.0
+    C = nheads * D
+    dev = q2.data.device
     ldo = so_ = 0
     if split != "only":
         if out is None:
-            out = empty(B, N, C, device=dev)
+            out = empty(B, Lq, C, device=dev)
+        assert out.stride(2) == 1
         ldo, so_ = out.stride(1), out.stride(0)
     else:
         out = None
     sp, sp_ptr = None, None
     if split != "no":
-        sp = SplitOperand(empty(B * N, 2 * C, dtype=torch.float16, device=dev), B * N, C, C, 1.0)
+        sp = SplitOperand(empty(B * Lq, 2 * C, dtype=torch.float16, device=dev), B * Lq, C, C, 1.0)
         sp_ptr = sp.data.data_ptr()
     if scale is None:
         scale = D ** -0.5
-    ptr = qkv2.data.data_ptr()
-    _lib.call("ec_attention_tc_split", ptr, qkv2.rows, qkv2.Kp, 0, N, ptr, qkv2.rows, qkv2.Kp, C, ptr, qkv2.rows,
-              qkv2.Kp, 2 * C, N, _p(out), B, nheads, N, N, ldo, so_, float(scale) / qkv2.scale ** 2, sp_ptr,
-              C if sp is not None else 0, _stream())
+    if key_mask is not None:
+        _chk(key_mask, "key_mask", torch.uint8)
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and tuple(key_mask.shape) == (B, Lk)
+    if bias is not None:
+        _chk(bias, "bias")
+        assert bias.is_contiguous() and tuple(bias.shape) == (B, nheads, Lq, Lk)
+    _lib.call("ec_attention_tc_split", q2.data.data_ptr(), q2.rows, q2.Kp, q_col, q_rows, k2.data.data_ptr(), k2.rows,
+              k2.Kp, k_col, v2.data.data_ptr(), v2.rows, v2.Kp, v_col, k_rows, _p(out), B, nheads, Lq, Lk, ldo, so_,
+              float(scale), D, _p(key_mask), _p(bias), sp_ptr, C if sp is not None else 0, _stream())
     return sp if split == "only" else ((out, sp) if split == "also" else out)
+
+
+def attention_split_ok(D, Lk, masked=False):
+    """Can ec_attention_tc_split take this attention?  (tensor-core mode, head dim 32 / 64, key-count limits)"""
+    return bool(TENSOR_CORES and ATTENTION_TC and ATTENTION_TMA and D in (32, 64)
+                and Lk <= (768 if (D == 64 and not masked) else 448))
+
+
+def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only", key_mask=None, bias=None):
+    """Self-attention over a packed split-fp16 QKV operand (the split output of the QKV GEMM):
+    qkv2 rows = B*N tokens, columns [q | k | v] of C = nheads*D each per half."""
+    C = qkv2.K // 3
+    assert qkv2.rows == B * N and qkv2.Kp == qkv2.K
+    return attention_split(qkv2, 0, N, qkv2, C, qkv2, 2 * C, N, B, nheads, N, N, C // nheads, scale=scale,
+                           key_mask=key_mask, bias=bias, out=out, split=split)
 
 
 def hop_bias(attn_adj, w0, b0, w1, b1, out=None):

@@ -37,40 +37,68 @@ def pack_decoder_layer(node, biased, bias_mlp, two_way):
         E = a.q_proj_weight.shape[0]
         b = a.in_proj_bias
         pk[name] = dict(qb=b[:E].contiguous(), kb=b[E:2 * E].contiguous(), vb=b[2 * E:].contiguous())
+        # K and V projections as ONE GEMM over the [tokens | pos] operand: rows [0, E) = W_k, rows [E, 2E) =
+        # [W_v | 0] (the value projection reads only the token half, encoder_decoder.py:622-628, 640-646)
+        wv = torch.zeros_like(a.k_proj_weight)
+        wv[:, :a.v_proj_weight.shape[1]] = a.v_proj_weight
+        pk[name]["kv_w"] = torch.cat((a.k_proj_weight, wv)).contiguous()
+        pk[name]["kv_b"] = b[E:].contiguous()
     return pk
 
 
-def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, adj, attn_adj=None, two_way=False):
+def _split_attention_ok(x2d, w, D, Lk, masked=False):
+    """Tensor-core mode and shapes the split-fp16 path takes: the projections run on the tcgen05 GEMM with a
+    split-fp16 epilogue and ec_attention_tc_split consumes them (no fp32 Q/K/V round trip)."""
+    return ops.attention_split_ok(D, Lk, masked) and ops.tc_linear_ok(x2d, w)
+
+
+def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, adj, attn_adj=None, two_way=False,
+                          img_split=None):
     """One TransformerDecoderLayer (encoder_decoder.py:584-651), batch-first.
 
     kp       [B,K,d]   keypoint tokens (contiguous)
     img_cat  [B,S,2d]  [:, :, :d] image tokens, [:, :, d:] their positional encoding (cat of :621)
     kp_cat   [B,K,2d]  scratch; [:, :, d:] already holds the keypoint positional embedding (:620)
+    img_split          optional split-fp16 copy of img_cat (the caller keeps it across layers when the
+                       image tokens do not change, i.e. two_way=False)
     Returns the new keypoint tokens [B,K,d]; with two_way the image half of img_cat is updated in
     place (norm4 output feeds the next layer, :638-649)."""
     B, K, d = kp.shape
     S = img_cat.shape[1]
     dev = kp.device
+    kp2d = kp.view(B * K, d)
     # (i) self-attention over keypoints (+ structural bias), residual, norm1
-    qkv = ops.linear(kp.view(B * K, d), pk["qkv_w"], pk["qkv_b"]).view(B, K, 3 * d)
     bias = None
     if attn_adj is not None and "hop" in pk:
         bias = ops.hop_bias(attn_adj, *pk["hop"])
-    a = ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], nhead, key_mask=key_mask_fixed,
-                      bias=bias)
-    t = ops.linear(a.view(B * K, d), node.self_attn.out_proj.weight, node.self_attn.out_proj.bias,
-                   residual=kp.view(B * K, d))
+    if _split_attention_ok(kp2d, pk["qkv_w"], d // nhead, K, masked=True):
+        qkv2 = ops.linear_split(kp2d, pk["qkv_w"], pk["qkv_b"])
+        a = ops.attention_packed_split(qkv2, B, K, nhead, key_mask=key_mask_fixed, bias=bias)
+    else:
+        qkv = ops.linear(kp2d, pk["qkv_w"], pk["qkv_b"]).view(B, K, 3 * d)
+        a = ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], nhead, key_mask=key_mask_fixed,
+                          bias=bias).view(B * K, d)
+    t = ops.linear(a, node.self_attn.out_proj.weight, node.self_attn.out_proj.bias, residual=kp2d)
     kc2 = kp_cat.view(B * K, 2 * d)
     ops.layernorm(t, node.norm1.weight, node.norm1.bias, 1e-5, out=kc2[:, :d])
     kp1 = kc2[:, :d]
     # (ii) cross-attention: q = [kp | kp_pos], k = [img | pos], v = img  (8 heads x 64), choker
     ca, cp = node.multihead_attn, pk["multihead_attn"]
     ic2 = img_cat.view(B * S, 2 * d)
-    q = ops.linear(kc2, ca.q_proj_weight, cp["qb"]).view(B, K, 2 * d)
-    k = ops.linear(ic2, ca.k_proj_weight, cp["kb"]).view(B, S, 2 * d)
-    v = ops.linear(ic2[:, :d], ca.v_proj_weight, cp["vb"]).view(B, S, 2 * d)
-    a = ops.attention(q, k, v, nhead)
-    a = ops.linear(a.view(B * K, 2 * d), ca.out_proj.weight, ca.out_proj.bias)
+    Dc = 2 * d // nhead
+    split_x = _split_attention_ok(kc2, ca.q_proj_weight, Dc, max(S, K)) and ops.tc_linear_ok(ic2, cp["kv_w"])
+    if split_x:
+        if img_split is None:
+            img_split = ops.split_f16(ic2)
+        q2 = ops.linear_split(kc2, ca.q_proj_weight, cp["qb"])
+        kv2 = ops.linear_split(img_split, cp["kv_w"], cp["kv_b"])                     # [B*S, 4d]: k | v
+        a = ops.attention_split(q2, 0, K, kv2, 0, kv2, 2 * d, S, B, nhead, K, S, Dc)
+    else:
+        q = ops.linear(kc2, ca.q_proj_weight, cp["qb"]).view(B, K, 2 * d)
+        k = ops.linear(ic2, ca.k_proj_weight, cp["kb"]).view(B, S, 2 * d)
+        v = ops.linear(ic2[:, :d], ca.v_proj_weight, cp["vb"]).view(B, S, 2 * d)
+        a = ops.attention(q, k, v, nhead).view(B * K, 2 * d)
+    a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias)
     t = ops.linear(a, node.choker.weight, node.choker.bias, residual=kp1)
     kp2 = ops.layernorm(t, node.norm2.weight, node.norm2.bias, 1e-5)
     # (iii) GCN feed-forward, ffn2, residual, norm3
@@ -85,11 +113,16 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5, out=kc2[:, :d])
     kp3 = kc2[:, :d]
     ia, ip = node.cross_attn_image_to_token, pk["cross_attn_image_to_token"]
-    q = ops.linear(ic2, ia.q_proj_weight, ip["qb"]).view(B, S, 2 * d)
-    k = ops.linear(kc2, ia.k_proj_weight, ip["kb"]).view(B, K, 2 * d)
-    v = ops.linear(kp3, ia.v_proj_weight, ip["vb"]).view(B, K, 2 * d)
-    a = ops.attention(q, k, v, nhead)
-    a = ops.linear(a.view(B * S, 2 * d), ia.out_proj.weight, ia.out_proj.bias)
+    if split_x:
+        q2 = ops.linear_split(img_split, ia.q_proj_weight, ip["qb"])                  # image tokens unchanged since (ii)
+        kv2 = ops.linear_split(kc2, ip["kv_w"], ip["kv_b"])                           # [B*K, 4d]: k | v
+        a = ops.attention_split(q2, 0, S, kv2, 0, kv2, 2 * d, K, B, nhead, S, K, Dc)
+    else:
+        q = ops.linear(ic2, ia.q_proj_weight, ip["qb"]).view(B, S, 2 * d)
+        k = ops.linear(kc2, ia.k_proj_weight, ip["kb"]).view(B, K, 2 * d)
+        v = ops.linear(kp3, ia.v_proj_weight, ip["vb"]).view(B, K, 2 * d)
+        a = ops.attention(q, k, v, nhead).view(B * S, 2 * d)
+    a = ops.linear(a, ia.out_proj.weight, ia.out_proj.bias)
     t = ops.linear(a, node.cross_attn_image_to_token_choker.weight, node.cross_attn_image_to_token_choker.bias,
                    residual=ic2[:, :d])
     ops.layernorm(t, node.norm4.weight, node.norm4.bias, 1e-5, out=ic2[:, :d])
@@ -198,9 +231,14 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         for i in range(self.num_encoder_layers):
             L = getattr(self.encoder.layers, str(i))
             ops.add_rows_(x, grid_pos, S)
-            qkv = ops.linear(x2, L.self_attn.in_proj_weight, L.self_attn.in_proj_bias).view(B, T, 3 * d)
-            a = ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], self.nhead, key_mask=key_mask)
-            t = ops.linear(a.view(B * T, d), L.self_attn.out_proj.weight, L.self_attn.out_proj.bias, residual=x2)
+            if _split_attention_ok(x2, L.self_attn.in_proj_weight, d // self.nhead, T, masked=True):
+                qkv2 = ops.linear_split(x2, L.self_attn.in_proj_weight, L.self_attn.in_proj_bias)
+                a = ops.attention_packed_split(qkv2, B, T, self.nhead, key_mask=key_mask)
+            else:
+                qkv = ops.linear(x2, L.self_attn.in_proj_weight, L.self_attn.in_proj_bias).view(B, T, 3 * d)
+                a = ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], self.nhead,
+                                  key_mask=key_mask).view(B * T, d)
+            t = ops.linear(a, L.self_attn.out_proj.weight, L.self_attn.out_proj.bias, residual=x2)
             ops.layernorm(t, L.norm1.weight, L.norm1.bias, 1e-5, out=x2)
             f = ops.linear(x2, L.linear1.weight, L.linear1.bias, act=ops.ACT_RELU)
             t = ops.linear(f, L.linear2.weight, L.linear2.bias, residual=x2)
@@ -255,12 +293,15 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         points = [pr]
         hs = ops.empty(self.num_decoder_layers, B, K, d, device=dev)
         use_bias = self.attn_bias and attn_adj is not None
+        img_split = None
         for i in range(self.num_decoder_layers):
             L = getattr(self.decoder.layers, str(i))
             pe = position_embedding.forward_coordinates(bi)                               # [B,K,d]
             mlp_gelu(pe.view(B * K, d), self.decoder.ref_point_head, 2, out=kp_cat.view(B * K, 2 * d)[:, d:])
+            if i == 0 and ops.tc_linear_ok(img_cat.view(B * S, 2 * d), pk[0]["multihead_attn"]["kv_w"]):
+                img_split = ops.split_f16(img_cat.view(B * S, 2 * d))       # image tokens are fixed over the layers
             cur = decoder_layer_forward(L, pk[i], self.nhead, cur, img_cat, kp_cat, kp_mask_fixed, adj,
-                                        attn_adj if use_bias else None, two_way=False)
+                                        attn_adj if use_bias else None, two_way=False, img_split=img_split)
             ops.layernorm(cur.view(B * K, d), self.decoder.norm.weight, self.decoder.norm.bias, 1e-5,
                           out=hs[i].view(B * K, d))
             delta = token_decode_mlp(cur.view(B * K, d), getattr(kpt_branch, str(i)))

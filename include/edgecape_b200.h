@@ -148,14 +148,18 @@ int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, in
 
 /* TMA-fed form of ec_attention_tc: Q, K, V are already split-fp16 buffers [rows, 2*kp] (hi | lo halves),
  * e.g. the split output of the QKV GEMM (one buffer, q_col = 0, k_col = C, v_col = 2C).  Head h of Q lives in
- * columns q_col + 64 h of each half and rows b * q_rows + i; K / V likewise with k_rows rows per batch
+ * columns q_col + dv h of each half and rows b * q_rows + i; K / V likewise with k_rows rows per batch
  * element.  Nothing is staged by hand: 64 x 64 boxes are loaded by TMA, V is consumed as an MN-major UMMA
- * operand.  Same output contract (O fp32 and / or split_out). */
+ * operand, the probabilities stay in TMEM.  dv = 64 handles up to 768 keys; dv = 32, key_mask ([B, Lk], 1 =
+ * ignore) and bias ([B, H, Lq, Lk], added to the scaled logits) need Lk <= 448.  Same output contract as
+ * ec_attention_tc (O fp32 and / or split_out with split_kp == H * dv).  Every attention of the path goes
+ * through this entry in tensor-core mode (models/.../encoder_decoder.py:461-483, 584-651; DINOv2 blocks). */
 int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
                           const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
                           int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H,
-                          int Lq, int Lk, int ldo, long long so, float scale, void* split_out,
-                          int split_kp, void* stream);
+                          int Lq, int Lk, int ldo, long long so, float scale, int dv,
+                          const uint8_t* key_mask, const float* bias, void* split_out, int split_kp,
+                          void* stream);
 
 /* bias[b,h,i,j] = W1 relu(W0 hops[:,b,i,j] + b0) + b1 with hops = attn_adj [n_hops, B, K, K]:
  * the Graphormer-style structural bias MLP (utils/bias_attn.py:82-83,188-191). */

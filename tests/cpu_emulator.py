@@ -224,8 +224,8 @@ def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv,
 
 
 def ec_attention_tc_split(Q2, q_total, q_kp, q_col, q_rows, K2, k_total, k_kp, k_col, V2, v_total, v_kp, v_col, k_rows,
-                          O, B, H, Lq, Lk, ldo, so, scale, split_out, split_kp, stream):
-    D = 64
+                          O, B, H, Lq, Lk, ldo, so, scale, D, key_mask, bias, split_out, split_kp, stream):
+    assert D in (32, 64) and Lk <= (768 if (D == 64 and not key_mask and not bias) else 448)
 
     def grab(ptr, total, kp, col, rows_per_b, L):
         a = arr(ptr, (total, 2 * kp), dtype=np.float16).astype(np.float32)
@@ -238,9 +238,18 @@ def ec_attention_tc_split(Q2, q_total, q_kp, q_col, q_rows, K2, k_total, k_kp, k
         grab(V2, v_total, v_kp, v_col, k_rows, Lk)
     kt = lambda a: a.transpose(0, 1, 3, 2)
     s = (ql @ kt(kh) + qh @ kt(kl) + qh @ kt(kh)) * np.float32(scale)
-    p = np.exp2((s - s.max(-1, keepdims=True)) * np.float32(1.4426950408889634)).astype(np.float32)
+    if bias:
+        s = s + arr(bias, (B, H, Lq, Lk))
+    keep = np.ones((B, 1, 1, Lk), dtype=bool)
+    if key_mask:
+        keep = arr(key_mask, (B, Lk), dtype=np.uint8)[:, None, None, :] == 0
+    s = np.where(keep, s, -np.inf).astype(np.float32)
+    mx = s.max(-1, keepdims=True)
+    mx = np.where(np.isfinite(mx), mx, 0.0)
+    p = np.where(keep, np.exp2((s - mx) * np.float32(1.4426950408889634)), 0.0).astype(np.float32)
     ph, pl = _h2(p)
-    o = (pl @ vh + ph @ vl + ph @ vh) / p.sum(-1, keepdims=True)
+    tot = p.sum(-1, keepdims=True)
+    o = (pl @ vh + ph @ vl + ph @ vh) * np.where(tot > 0, 1.0 / np.where(tot > 0, tot, 1.0), 0.0)
     o = np.ascontiguousarray(o.transpose(0, 2, 1, 3)).astype(np.float32)
     if O:
         arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o

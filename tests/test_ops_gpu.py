@@ -513,6 +513,45 @@ def test_attention_tma_on_split_qkv(B, N, H, monkeypatch):
     close(sp.data[:, :C].float() + sp.data[:, C:].float(), want.reshape(B * N, C), tol=5e-6, what="attention_tma split")
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk,Dh,masked,biased", [
+    (2, 8, 100, 100, 32, True, True),      # decoder self-attention over keypoints: fixed key mask + hop bias
+    (2, 8, 424, 424, 32, True, False),     # encoder self-attention over image + keypoint tokens
+    (3, 8, 100, 324, 64, False, False),    # keypoints -> image cross-attention
+    (3, 8, 324, 100, 64, False, False),    # image -> keypoints cross-attention (two-way layers)
+    (1, 8, 17, 448, 32, True, True),
+    (2, 4, 130, 200, 64, True, True),
+    (1, 2, 5, 3, 32, False, True),
+])
+def test_attention_split_general(B, H, Lq, Lk, Dh, masked, biased):
+    """ec_attention_tc_split with separate Q / K / V operands, head dim 32 or 64, key mask and bias."""
+    C = H * Dh
+    q, k, v = rnd(B * Lq, C, seed=21), rnd(B * Lk, C, seed=22), rnd(B * Lk, C, seed=23)
+    mask = None
+    if masked:
+        mask = (torch.rand(B, Lk, generator=torch.Generator().manual_seed(3)) < 0.3)
+        mask[:, 0] = False
+        if B > 1 and Lk > 3:
+            mask[1, :] = True                     # a fully masked row block -> zeros
+    bias = 0.5 * rnd(B, H, Lq, Lk, seed=24) if biased else None
+    qh = q.double().view(B, Lq, H, Dh).transpose(1, 2)
+    kh = k.double().view(B, Lk, H, Dh).transpose(1, 2)
+    vh = v.double().view(B, Lk, H, Dh).transpose(1, 2)
+    s_ = qh @ kh.transpose(-1, -2) * Dh ** -0.5
+    if bias is not None:
+        s_ = s_ + bias.double()
+    if mask is not None:
+        s_ = s_.masked_fill(mask[:, None, None, :], float("-inf"))
+    p_ = torch.nan_to_num(s_.softmax(-1), nan=0.0)
+    want = (p_ @ vh).transpose(1, 2).reshape(B, Lq, C).float()
+    D = dev()
+    q2, k2, v2 = ops.split_f16(q.to(D)), ops.split_f16(k.to(D)), ops.split_f16(v.to(D))
+    got, sp = ops.attention_split(q2, 0, Lq, k2, 0, v2, 0, Lk, B, H, Lq, Lk, Dh,
+                                  key_mask=None if mask is None else mask.to(torch.uint8).to(D),
+                                  bias=None if bias is None else bias.to(D), split="also")
+    close(got, want, tol=5e-6, what=f"attention_split {B},{H},{Lq},{Lk},{Dh}")
+    close(sp.data[:, :C].float() + sp.data[:, C:].float(), want.reshape(B * Lq, C), tol=5e-6, what="attention_split split")
+
+
 def test_attention_tc_on_packed_qkv_views(monkeypatch):
     monkeypatch.setattr(ops, "TENSOR_CORES", True)
     monkeypatch.setattr(ops, "ATTENTION_TC", True)
