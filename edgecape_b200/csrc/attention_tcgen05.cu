@@ -786,7 +786,6 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(bar_sf, THREADS / 32);
     for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(bar_pr + 8 * i, THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    load_qk(0);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
@@ -796,6 +795,8 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  pdl_launch_dependents();     // TMEM is allocated: the next kernel in the stream may start its prologue
+  pdl_wait();                  // Q / K / V written by the previous kernel are visible from here on
   stamp(1);
 
   // S = Q K^T of one key block.  A tcgen05.mma costs its issuing thread >= ~98 clk whatever its shape, so the
@@ -840,8 +841,8 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (blk > 0) {                                   // P of the previous block consumed by its MMAs, S consumed
           mbar_wait(bar_sf, (blk - 1) & 1);
           tc_fence_after();
-          load_qk(blk);
         }
+        load_qk(blk);
         mbar_wait(bar_qk, blk & 1);
         tc_fence_after();
         issue_s(0, lkp);                                 // key columns [0, n0); warp 17 issues [n0, lkp)
@@ -1159,8 +1160,8 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
                                    atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
       ts_attr_set = true;
     }
-    atc::attention_tc_ts_kernel<<<grid, atc::THREADS_TS, kq + atc::MISC_BYTES + 1024, (cudaStream_t)stream>>>(tmQ, tmK,
-                                                                                                             tmV, p);
+    launch_pdl(atc::attention_tc_ts_kernel, grid, dim3(atc::THREADS_TS), (size_t)(kq + atc::MISC_BYTES + 1024),
+               (cudaStream_t)stream, tmQ, tmK, tmV, p);
   } else {
     atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   }

@@ -12,6 +12,35 @@ namespace ec {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Programmatic dependent launch.  The path is a chain of ~360 dependent launches per step, most of them far
+// from filling the GPU, so launch latency and per-kernel prologues (barrier init, TMEM allocation, tensor-map
+// fetch) are a sizeable share of the step.  Kernels launched through launch_pdl() may start while their
+// predecessor in the stream is still running; each of them calls pdl_wait() -- which returns once the
+// predecessor grid has completed and its writes are visible -- BEFORE its first global-memory access (read or
+// write), and pdl_launch_dependents() as early as it safely can (after TMEM allocation in the kernels that
+// allocate TMEM: a dependent CTA that grabbed TMEM first would wait for us while we wait for TMEM).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

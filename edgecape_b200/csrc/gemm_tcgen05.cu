@@ -220,6 +220,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (TWO) cluster_sync(); else __syncthreads();                  // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();     // TMEM is ours: the next kernel in the stream may start its prologue
+  pdl_wait();                  // ... and ours ends here: operands written by the previous kernel are visible
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
@@ -452,6 +454,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // X [M, K] fp32 (row stride ldx) -> X2 [M, 2*Kp] fp16 = [hi | lo] of X*scale, zero padded to Kp.
 __global__ void split_f16_kernel(const float* __restrict__ X, __half* __restrict__ X2, int M, int K, int ldx, int seg,
                                  long long seg_stride, int Kp, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 2 elements
   const int half_kp = Kp >> 1;
   if (i >= (long long)M * half_kp) return;
@@ -553,7 +557,7 @@ extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int
   EC_REQUIRE(Kp % tc::BK == 0 && Kp >= K && K > 0, "ec_split_f16: Kp must be a multiple of 64 and >= K");
   if (M == 0) return EC_OK;
   long long total = (long long)M * (Kp / 2);
-  tc::split_f16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(X, (__half*)X2, M, K, ldx, seg, seg_stride, Kp,
+  launch_pdl(tc::split_f16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, (cudaStream_t)stream, X, (__half*)X2, M, K, ldx, seg, seg_stride, Kp,
                                                                               scale);
   return check_launch("ec_split_f16");
 }
@@ -614,21 +618,23 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
     cfg.blockDim = dim3(tc::THREADS);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true>, tmA, tmB, p));
   } else {
     const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
     if (BN == 256)
-      tc::gemm_f16x3_kernel<256, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);
+      launch_pdl(tc::gemm_f16x3_kernel<256, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, p);
     else
-      tc::gemm_f16x3_kernel<128, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);
+      launch_pdl(tc::gemm_f16x3_kernel<128, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, p);
   }
   return check_launch("ec_gemm_f16x3");
 }

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps, int M, int C,
                                                         __half* __restrict__ split_out, int split_kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ b, float eps, int M,
                                                             __half* __restrict__ split_out, int split_kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int C = NV * 128;
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,15 +245,15 @@ extern "C" int ec_layernorm(const float* X, int ldx, int seg, long long seg_stri
                    (!R || (al16(R) && ldr % 4 == 0)) && (!sum_out || (al16(sum_out) && ld_sum % 4 == 0)) &&
                    (!Y || (al16(Y) && ldy % 4 == 0)) && al16(w) && al16(b) && (!split_out || al16(split_out));
 #define EC_LN_VEC(NV)                                                                                             \
-  layernorm_vec_kernel<NV><<<grid, block, 0, st>>>(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, \
-                                                   eps, M, (__half*)split_out, split_kp)
+  launch_pdl(layernorm_vec_kernel<NV>, grid, block, 0, st, X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, \
+             b, eps, M, (__half*)split_out, split_kp)
   if (vec && C == 256) EC_LN_VEC(2);
   else if (vec && C == 384) EC_LN_VEC(3);
   else if (vec && C == 768) EC_LN_VEC(6);
   else if (vec && C == 1024) EC_LN_VEC(8);
   else
-    layernorm_kernel<<<grid, block, 0, st>>>(
-      X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, (__half*)split_out, split_kp);
+    launch_pdl(layernorm_kernel, grid, block, 0, st, X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps,
+               M, C, (__half*)split_out, split_kp);
 #undef EC_LN_VEC
   return check_launch("ec_layernorm");
 }
