@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(256) hop_bias_kernel(const float* __restrict__
                                                        const float* __restrict__ w1,
                                                        const float* __restrict__ b1, float* __restrict__ bias,
                                                        int B, int K, int n_hops, int hidden, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sw0 = sm;                       // hidden * n_hops
   float* sb0 = sw0 + hidden * n_hops;    // hidden
@@ -229,7 +231,7 @@ extern "C" int ec_hop_bias(const float* attn_adj, const float* w0, const float* 
   if (total == 0) return EC_OK;
   size_t smem = sizeof(float) * (hidden * n_hops + hidden + H * hidden + H);
   int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
-  hop_bias_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(attn_adj, w0, b0, w1, b1, bias, B, K, n_hops,
+  launch_pdl(hop_bias_kernel, dim3(blocks), dim3(256), (size_t)(smem), (cudaStream_t)stream, attn_adj, w0, b0, w1, b1, bias, B, K, n_hops,
                                                                hidden, H);
   return check_launch("ec_hop_bias");
 }

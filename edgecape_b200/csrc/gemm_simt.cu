@@ -47,6 +47,8 @@ __device__ __forceinline__ float4 load4(const float* base, long long off, int c,
 
 template <int BM, int BN, bool B_KMAJOR>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int TM = BM / 16, TN = BN / 16;
   constexpr int CM = TM / 4, CN = TN / 4;       // float4 chunks per thread
   constexpr int PAD = 4;
@@ -204,9 +206,9 @@ template <int BM, int BN>
 static int launch_gemm(const GemmParams& p, int b_kmajor, int batch, cudaStream_t st) {
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch);
   if (b_kmajor)
-    gemm_simt_kernel<BM, BN, true><<<grid, 256, 0, st>>>(p);
+    launch_pdl(gemm_simt_kernel<BM, BN, true>, dim3(grid), dim3(256), (size_t)(0), st, p);
   else
-    gemm_simt_kernel<BM, BN, false><<<grid, 256, 0, st>>>(p);
+    launch_pdl(gemm_simt_kernel<BM, BN, false>, dim3(grid), dim3(256), (size_t)(0), st, p);
   return check_launch("ec_gemm");
 }
 

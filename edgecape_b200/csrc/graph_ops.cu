@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) adj_from_edges_kernel(const int32_t* __re
                                                              const uint8_t* __restrict__ kp_mask,
                                                              float* __restrict__ adj, float* __restrict__ binary,
                                                              int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   float* bin = binary + (long long)b * K * K;
   const uint8_t* mk = kp_mask + (long long)b * K;
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(256) adj_from_edges_kernel(const int32_t* __re
 __global__ void __launch_bounds__(256) soft_normalize_kernel(const float* __restrict__ U,
                                                              const uint8_t* __restrict__ kp_mask,
                                                              float* __restrict__ adj, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int KK = K * K;
   const float* u = U + (long long)b * KK;
@@ -73,6 +77,8 @@ __global__ void __launch_bounds__(256) edge_weights_kernel(const float* __restri
                                                            float zc_b, int use_zc, float* __restrict__ adj,
                                                            float* __restrict__ unnorm, float* __restrict__ hop0,
                                                            float* __restrict__ hop1, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int KK = K * K;
   const float* s = S + (long long)b * KK;
@@ -145,6 +151,8 @@ constexpr int GA_ROWS = 8;     // rows of one sample per CTA: 13 x B CTAs at K =
 __global__ void __launch_bounds__(256, 3) gcn_aggregate_split_kernel(const float* __restrict__ X,
                                                                   const float* __restrict__ adj,
                                                                   __half* __restrict__ Z2, int K, int d, int Kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float a1s[];                 // [GA_ROWS][KP4] (KP4 = K rounded up to 4, zero padded)
   __shared__ float rs[GA_ROWS], a0s[GA_ROWS];
   const int b = blockIdx.y, w0 = blockIdx.x * GA_ROWS;
@@ -242,7 +250,7 @@ extern "C" int ec_adj_from_edges(const int32_t* edges, const int32_t* offsets, c
                                  float* adj, float* binary, int B, int K, void* stream) {
   EC_REQUIRE(offsets && kp_mask && adj && binary, "ec_adj_from_edges: null pointer");
   if (B == 0) return EC_OK;
-  adj_from_edges_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(edges, offsets, kp_mask, adj, binary, K);
+  launch_pdl(adj_from_edges_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, edges, offsets, kp_mask, adj, binary, K);
   return check_launch("ec_adj_from_edges");
 }
 
@@ -250,7 +258,7 @@ extern "C" int ec_soft_normalize_adj(const float* U, const uint8_t* kp_mask, flo
                                      void* stream) {
   EC_REQUIRE(U && kp_mask && adj, "ec_soft_normalize_adj: null pointer");
   if (B == 0) return EC_OK;
-  soft_normalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(U, kp_mask, adj, K);
+  launch_pdl(soft_normalize_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, U, kp_mask, adj, K);
   return check_launch("ec_soft_normalize_adj");
 }
 
@@ -259,7 +267,7 @@ extern "C" int ec_edge_weights(const float* S, const float* binary, const uint8_
                                float* hop1, int B, int K, void* stream) {
   EC_REQUIRE(S && binary && kp_mask && adj, "ec_edge_weights: null pointer");
   if (B == 0) return EC_OK;
-  edge_weights_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(S, binary, kp_mask, zc_w, zc_b, use_zero_conv, adj,
+  launch_pdl(edge_weights_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, S, binary, kp_mask, zc_w, zc_b, use_zero_conv, adj,
                                                            unnorm, hop0, hop1, K);
   return check_launch("ec_edge_weights");
 }
@@ -284,7 +292,7 @@ extern "C" int ec_gcn_aggregate_split(const float* X, const float* adj, void* Z2
   const size_t smem = (size_t)GA_ROWS * ((K + 3) & ~3) * sizeof(float);
   EC_REQUIRE(smem <= 48 * 1024, "ec_gcn_aggregate_split: K too large for the shared-memory tile");
   dim3 grid(cdiv(K, GA_ROWS), B);
-  gcn_aggregate_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(X, adj, (__half*)Z2, K, d, Kp);
+  launch_pdl(gcn_aggregate_split_kernel, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, X, adj, (__half*)Z2, K, d, Kp);
   return check_launch("ec_gcn_aggregate_split");
 }
 

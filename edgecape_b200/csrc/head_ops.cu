@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) support_weights_kernel(const float* __res
                                                               const float* __restrict__ rowscale,
                                                               float* __restrict__ Tw, int ldtw, int hm_h, int hm_w,
                                                               int h, int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* t = sm;                    // hm_h * hm_w
   float* Wx = t + hm_h * hm_w;      // hm_w * w
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256) support_weights_kernel(const float* __res
 
 __global__ void sine_pe_kernel(const float* __restrict__ coord, float* __restrict__ out, int ldo, int M,
                                int num_feats, float temperature, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int C = 2 * num_feats;
   if (i >= (long long)M * C) return;
@@ -94,6 +98,8 @@ __global__ void sine_pe_kernel(const float* __restrict__ coord, float* __restric
 __global__ void __launch_bounds__(256) proposal_kernel(const float* __restrict__ sim,
                                                        float* __restrict__ prop_loss, float* __restrict__ prop,
                                                        long long* __restrict__ argmax, int BK, int h, int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= BK) return;
@@ -175,6 +181,8 @@ __global__ void __launch_bounds__(128) pck_kernel(const float* __restrict__ pred
 // image-space affine of TwoStageHead.decode, cs = [cx, cy, sx, sy] per sample
 __global__ void decode_preds_kernel(const float* __restrict__ points, const float* __restrict__ cs,
                                     float* __restrict__ preds, int K, float W, float H, int use_udp, int total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = i / K;
@@ -193,7 +201,7 @@ extern "C" int ec_decode_preds(const float* points, const float* center_scale, f
                                float H, int use_udp, void* stream) {
   EC_REQUIRE(points && center_scale && preds, "ec_decode_preds: null pointer");
   if (B * K == 0) return EC_OK;
-  decode_preds_kernel<<<cdiv((long long)B * K, 256), 256, 0, (cudaStream_t)stream>>>(points, center_scale, preds, K, W, H,
+  launch_pdl(decode_preds_kernel, dim3(cdiv((long long)B * K, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, points, center_scale, preds, K, W, H,
                                                                                      use_udp, B * K);
   return check_launch("ec_decode_preds");
 }
@@ -207,7 +215,7 @@ extern "C" int ec_support_weights(const float* target, const float* rowscale, fl
   EC_REQUIRE(smem <= 200 * 1024, "ec_support_weights: heat-map / grid too large for shared memory");
   if (smem > 48 * 1024)
     EC_CUDA(cudaFuncSetAttribute(support_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  support_weights_kernel<<<BK, 256, smem, (cudaStream_t)stream>>>(target, rowscale, Tw, ldtw, hm_h, hm_w, h, w);
+  launch_pdl(support_weights_kernel, dim3(BK), dim3(256), (size_t)(smem), (cudaStream_t)stream, target, rowscale, Tw, ldtw, hm_h, hm_w, h, w);
   return check_launch("ec_support_weights");
 }
 
@@ -216,7 +224,7 @@ extern "C" int ec_sine_pe_coords(const float* coord, float* out, int ldo, int M,
   EC_REQUIRE(coord && out && ldo >= 2 * num_feats, "ec_sine_pe_coords: bad arguments");
   long long total = (long long)M * 2 * num_feats;
   if (total == 0) return EC_OK;
-  sine_pe_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(coord, out, ldo, M, num_feats, temperature,
+  launch_pdl(sine_pe_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, coord, out, ldo, M, num_feats, temperature,
                                                                       scale);
   return check_launch("ec_sine_pe_coords");
 }
@@ -226,7 +234,7 @@ extern "C" int ec_proposal(const float* sim, float* prop_loss, float* prop, int6
   EC_REQUIRE(sim && prop_loss && prop && argmax, "ec_proposal: null pointer");
   EC_REQUIRE(h > 0 && w > 0, "ec_proposal: empty map");
   if (BK == 0) return EC_OK;
-  proposal_kernel<<<cdiv(BK, 8), 256, 0, (cudaStream_t)stream>>>(sim, prop_loss, prop, (long long*)argmax, BK, h, w);
+  launch_pdl(proposal_kernel, dim3(cdiv(BK, 8)), dim3(256), (size_t)(0), (cudaStream_t)stream, sim, prop_loss, prop, (long long*)argmax, BK, h, w);
   return check_launch("ec_proposal");
 }
 

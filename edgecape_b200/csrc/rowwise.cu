@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
 
 __global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__ P, int T, int S, int C,
                                 long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -143,6 +145,8 @@ __global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__
 __global__ void copy_rows_kernel(const float* __restrict__ X, int ldx, int segx, long long sstridex,
                                  float* __restrict__ Y, int ldy, int segy, long long sstridey, int C,
                                  int bcast_rows, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -155,6 +159,8 @@ __global__ void copy_rows_kernel(const float* __restrict__ X, int ldx, int segx,
 
 __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ X, float* __restrict__ Y,
                                                            int M, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -168,6 +174,8 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
 
 __global__ void mask_accumulate_kernel(const float* __restrict__ tw, float* __restrict__ mask_s, int n,
                                        int first) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float t = tw[i];
@@ -176,6 +184,8 @@ __global__ void mask_accumulate_kernel(const float* __restrict__ tw, float* __re
 
 __global__ void kp_masks_kernel(const float* __restrict__ mask_s, uint8_t* __restrict__ kp_mask,
                                 uint8_t* __restrict__ kp_fixed, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one block per batch row
   const int b = blockIdx.x;
   __shared__ int any_valid;
@@ -202,6 +212,8 @@ __device__ __forceinline__ float inv_sigmoid(float x) {
 
 __global__ void point_update_kernel(const float* __restrict__ bi, const float* __restrict__ delta, int ldd,
                                     float* __restrict__ out, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * M) return;
   int m = i >> 1, c = i & 1;
@@ -211,6 +223,8 @@ __global__ void point_update_kernel(const float* __restrict__ bi, const float* _
 
 __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
                              float a, float b, float div, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = a * x[i];
@@ -226,7 +240,7 @@ extern "C" int ec_axpby(const float* x, const float* y, float* out, float a, flo
                         void* stream) {
   EC_REQUIRE(x && y && out, "ec_axpby: null pointer");
   if (n == 0) return EC_OK;
-  axpby_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, out, a, b, div, n);
+  launch_pdl(axpby_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, y, out, a, b, div, n);
   return check_launch("ec_axpby");
 }
 
@@ -262,7 +276,7 @@ extern "C" int ec_add_rows(float* X, const float* P, int batch, int T, int S, in
   EC_REQUIRE(X && P && S <= T, "ec_add_rows: bad arguments");
   long long total = (long long)batch * S * C;
   if (total == 0) return EC_OK;
-  add_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(X, P, T, S, C, total);
+  launch_pdl(add_rows_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, X, P, T, S, C, total);
   return check_launch("ec_add_rows");
 }
 
@@ -271,7 +285,7 @@ extern "C" int ec_copy_rows(const float* X, int ldx, int seg_x, long long seg_st
   EC_REQUIRE(X && Y, "ec_copy_rows: null pointer");
   long long total = (long long)M * C;
   if (total == 0) return EC_OK;
-  copy_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, seg_x, seg_stride_x, Y, ldy, seg_y,
+  launch_pdl(copy_rows_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, X, ldx, seg_x, seg_stride_x, Y, ldy, seg_y,
                                                                        seg_stride_y, C, bcast_rows, total);
   return check_launch("ec_copy_rows");
 }
@@ -279,14 +293,14 @@ extern "C" int ec_copy_rows(const float* X, int ldx, int seg_x, long long seg_st
 extern "C" int ec_l2_normalize(const float* X, float* Y, int M, int C, float eps, void* stream) {
   EC_REQUIRE(X && Y, "ec_l2_normalize: null pointer");
   if (M == 0) return EC_OK;
-  l2_normalize_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(X, Y, M, C, eps);
+  launch_pdl(l2_normalize_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), (cudaStream_t)stream, X, Y, M, C, eps);
   return check_launch("ec_l2_normalize");
 }
 
 extern "C" int ec_mask_accumulate(const float* tw, float* mask_s, int n, int first, void* stream) {
   EC_REQUIRE(tw && mask_s, "ec_mask_accumulate: null pointer");
   if (n == 0) return EC_OK;
-  mask_accumulate_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(tw, mask_s, n, first);
+  launch_pdl(mask_accumulate_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, tw, mask_s, n, first);
   return check_launch("ec_mask_accumulate");
 }
 
@@ -294,13 +308,13 @@ extern "C" int ec_kp_masks(const float* mask_s, uint8_t* kp_mask, uint8_t* kp_ma
                            void* stream) {
   EC_REQUIRE(mask_s && kp_mask && kp_mask_fixed, "ec_kp_masks: null pointer");
   if (B == 0) return EC_OK;
-  kp_masks_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(mask_s, kp_mask, kp_mask_fixed, K);
+  launch_pdl(kp_masks_kernel, dim3(B), dim3(128), (size_t)(0), (cudaStream_t)stream, mask_s, kp_mask, kp_mask_fixed, K);
   return check_launch("ec_kp_masks");
 }
 
 extern "C" int ec_point_update(const float* bi, const float* delta, int ldd, float* out, int M, void* stream) {
   EC_REQUIRE(bi && delta && out, "ec_point_update: null pointer");
   if (M == 0) return EC_OK;
-  point_update_kernel<<<cdiv(2LL * M, 256), 256, 0, (cudaStream_t)stream>>>(bi, delta, ldd, out, M);
+  launch_pdl(point_update_kernel, dim3(cdiv(2LL * M, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, bi, delta, ldd, out, M);
   return check_launch("ec_point_update");
 }

@@ -8,6 +8,8 @@ namespace ec {
 
 __global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int H, int W, int P,
                               int h0, int w0, int ldc, long long total, __half* __restrict__ split_out, int split_kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int col = (int)(i % ldc);
@@ -66,6 +68,8 @@ __global__ void interp_pos_kernel(const float* __restrict__ pos, float* __restri
 
 __global__ void write_cls_kernel(const float* __restrict__ cls, const float* __restrict__ pos0,
                                  float* __restrict__ tokens, long long stride, int C, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
@@ -83,7 +87,7 @@ extern "C" int ec_im2col_patches(const float* img, float* cols, int B, int H, in
   const int h0 = H / P, w0 = W / P;
   long long total = (long long)B * h0 * w0 * ldc;
   if (total == 0) return EC_OK;
-  im2col_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, cols, H, W, P, h0, w0, ldc, total,
+  launch_pdl(im2col_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, img, cols, H, W, P, h0, w0, ldc, total,
                                                                     (__half*)split_out, split_kp);
   return check_launch("ec_im2col_patches");
 }
@@ -111,6 +115,6 @@ extern "C" int ec_write_cls(const float* cls, const float* pos0, float* tokens, 
                             void* stream) {
   EC_REQUIRE(cls && pos0 && tokens, "ec_write_cls: null pointer");
   if (B == 0) return EC_OK;
-  write_cls_kernel<<<cdiv((long long)B * C, 256), 256, 0, (cudaStream_t)stream>>>(cls, pos0, tokens, stride, C, B);
+  launch_pdl(write_cls_kernel, dim3(cdiv((long long)B * C, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, cls, pos0, tokens, stride, C, B);
   return check_launch("ec_write_cls");
 }

@@ -123,6 +123,9 @@ if __name__ == "__main__":
         from edgecape_b200 import _lib
         st, v = st.split("@")
         _lib.call("ec_attention_tc_set_variant", int(v))
+    if st == "tmabench":          # the ViT-B block attention alone (ncu target)
+        bench_tma(32, 12, 325, iters=5)
+        sys.exit(0)
     if st == "trace":
         trace_tma(32, 12, 325)
         trace_tma(8, 16, 730)
