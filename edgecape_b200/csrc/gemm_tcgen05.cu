@@ -593,7 +593,9 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   // problems to pair tiles measured 1.5% slower end to end -- pass L -- the cluster launch has a higher fixed cost.)
   const long long pair_tiles = (long long)cdiv(M, 256) * cdiv(N, 256);
   int mode = ec_tc_force_bn;                     // 0 heuristic, 128, 256, 512 (= pair)
-  if (mode == 0) mode = (N >= 256 && pair_tiles * 4 >= 3LL * num_sms) ? 512 : 128;
+  // (with ~1.7 waves of pair tiles and a short K loop -- the ViT proj GEMM -- the finer 128x128 tiles measure 10 % faster)
+  if (mode == 0)
+    mode = (N >= 256 && pair_tiles * 4 >= 3LL * num_sms && (pair_tiles >= num_sms || Kp >= 1024)) ? 512 : 128;
   const int BN = mode == 128 ? 128 : 256;
   CUtensorMap tmA, tmB;
   int rc = tc::get_tensor_map(A2, M, Kp, tc::BM, &tmA);

@@ -43,6 +43,11 @@ def pack_decoder_layer(node, biased, bias_mlp, two_way):
         wv[:, :a.v_proj_weight.shape[1]] = a.v_proj_weight
         pk[name]["kv_w"] = torch.cat((a.k_proj_weight, wv)).contiguous()
         pk[name]["kv_b"] = b[E:].contiguous()
+        # out_proj followed by the choker is one linear map (no non-linearity in between, :629-631 / :647-649):
+        # W = W_choker W_out, b = W_choker b_out + b_choker, formed once with the fp32 GEMM kernel
+        ch = node.choker if name == "multihead_attn" else node.cross_attn_image_to_token_choker
+        pk[name]["oc_w"] = ops.gemm(ch.weight, a.out_proj.weight, b_kmajor=False)
+        pk[name]["oc_b"] = ops.gemm(a.out_proj.bias.view(1, -1), ch.weight, b_kmajor=True, bias=ch.bias).view(-1)
     return pk
 
 
@@ -53,7 +58,7 @@ def _split_attention_ok(x2d, w, D, Lk, masked=False):
 
 
 def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, adj, attn_adj=None, two_way=False,
-                          img_split=None):
+                          img_split=None, kv_split=None, kv_col=0):
     """One TransformerDecoderLayer (encoder_decoder.py:584-651), batch-first.
 
     kp       [B,K,d]   keypoint tokens (contiguous)
@@ -61,6 +66,8 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     kp_cat   [B,K,2d]  scratch; [:, :, d:] already holds the keypoint positional embedding (:620)
     img_split          optional split-fp16 copy of img_cat (the caller keeps it across layers when the
                        image tokens do not change, i.e. two_way=False)
+    kv_split, kv_col   optional precomputed [k | v] projection of the image tokens (split-fp16, this layer's
+                       columns start at kv_col): the main decoder projects all its layers in one GEMM
     Returns the new keypoint tokens [B,K,d]; with two_way the image half of img_cat is updated in
     place (norm4 output feeds the next layer, :638-649)."""
     B, K, d = kp.shape
@@ -88,18 +95,22 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     Dc = 2 * d // nhead
     split_x = _split_attention_ok(kc2, ca.q_proj_weight, Dc, max(S, K)) and ops.tc_linear_ok(ic2, cp["kv_w"])
     if split_x:
-        if img_split is None:
+        if img_split is None and (kv_split is None or two_way):
             img_split = ops.split_f16(ic2)
         q2 = ops.linear_split(kc2, ca.q_proj_weight, cp["qb"])
-        kv2 = ops.linear_split(img_split, cp["kv_w"], cp["kv_b"])                     # [B*S, 4d]: k | v
-        a = ops.attention_split(q2, 0, K, kv2, 0, kv2, 2 * d, S, B, nhead, K, S, Dc)
+        if kv_split is None:
+            kv_split, kv_col = ops.linear_split(img_split, cp["kv_w"], cp["kv_b"]), 0     # [B*S, 4d]: k | v
+        a = ops.attention_split(q2, 0, K, kv_split, kv_col, kv_split, kv_col + 2 * d, S, B, nhead, K, S, Dc)
     else:
         q = ops.linear(kc2, ca.q_proj_weight, cp["qb"]).view(B, K, 2 * d)
         k = ops.linear(ic2, ca.k_proj_weight, cp["kb"]).view(B, S, 2 * d)
         v = ops.linear(ic2[:, :d], ca.v_proj_weight, cp["vb"]).view(B, S, 2 * d)
         a = ops.attention(q, k, v, nhead).view(B * K, 2 * d)
-    a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias)
-    t = ops.linear(a, node.choker.weight, node.choker.bias, residual=kp1)
+    if "oc_w" in cp:
+        t = ops.linear(a, cp["oc_w"], cp["oc_b"], residual=kp1)
+    else:
+        a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias)
+        t = ops.linear(a, node.choker.weight, node.choker.bias, residual=kp1)
     kp2 = ops.layernorm(t, node.norm2.weight, node.norm2.bias, 1e-5)
     # (iii) GCN feed-forward, ffn2, residual, norm3
     if ops.gcn_tc_ok(B, K):       # the GCN GEMM epilogue emits the split-fp16 operand of ffn2 directly
@@ -122,9 +133,12 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
         k = ops.linear(kc2, ia.k_proj_weight, ip["kb"]).view(B, K, 2 * d)
         v = ops.linear(kp3, ia.v_proj_weight, ip["vb"]).view(B, K, 2 * d)
         a = ops.attention(q, k, v, nhead).view(B * S, 2 * d)
-    a = ops.linear(a, ia.out_proj.weight, ia.out_proj.bias)
-    t = ops.linear(a, node.cross_attn_image_to_token_choker.weight, node.cross_attn_image_to_token_choker.bias,
-                   residual=ic2[:, :d])
+    if "oc_w" in ip:
+        t = ops.linear(a, ip["oc_w"], ip["oc_b"], residual=ic2[:, :d])
+    else:
+        a = ops.linear(a, ia.out_proj.weight, ia.out_proj.bias)
+        t = ops.linear(a, node.cross_attn_image_to_token_choker.weight, node.cross_attn_image_to_token_choker.bias,
+                       residual=ic2[:, :d])
     ops.layernorm(t, node.norm4.weight, node.norm4.bias, 1e-5, out=ic2[:, :d])
     out = ops.empty(B, K, d, device=dev)
     ops.copy_rows(kp3, out.view(B * K, d))
@@ -219,8 +233,12 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def _pack(self):
-        return {"dec": [pack_decoder_layer(getattr(self.decoder.layers, str(i)), self.biased, self.attn_bias, False)
-                        for i in range(self.num_decoder_layers)]}
+        dec = [pack_decoder_layer(getattr(self.decoder.layers, str(i)), self.biased, self.attn_bias, False)
+               for i in range(self.num_decoder_layers)]
+        # the image tokens are the same for every decoder layer: their K | V projections are one GEMM
+        kv_w = torch.cat([pk["multihead_attn"]["kv_w"] for pk in dec]).contiguous()
+        kv_b = torch.cat([pk["multihead_attn"]["kv_b"] for pk in dec]).contiguous()
+        return {"dec": dec, "kv_w": kv_w, "kv_b": kv_b}
 
     # --------------------------------------------------------------------------- pieces
     def encode(self, x, grid_pos, S, key_mask):
@@ -283,7 +301,8 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         # concurrently with the encoder above and joins here, where its result is first needed
         if callable(adj):
             adj, attn_adj = adj()
-        pk = self.packed()["dec"]
+        packed = self.packed()
+        pk = packed["dec"]
         img_cat = ops.empty(B, S, 2 * d, device=dev)                 # [img | grid pos]  (torch.cat of :621)
         ops.copy_rows(img, img_cat[:, :, :d])
         ops.copy_rows(grid_pos, img_cat.view(B * S, 2 * d)[:, d:], bcast_rows=S)
@@ -293,15 +312,18 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         points = [pr]
         hs = ops.empty(self.num_decoder_layers, B, K, d, device=dev)
         use_bias = self.attn_bias and attn_adj is not None
-        img_split = None
+        kv_all = None
         for i in range(self.num_decoder_layers):
             L = getattr(self.decoder.layers, str(i))
             pe = position_embedding.forward_coordinates(bi)                               # [B,K,d]
             mlp_gelu(pe.view(B * K, d), self.decoder.ref_point_head, 2, out=kp_cat.view(B * K, 2 * d)[:, d:])
-            if i == 0 and ops.tc_linear_ok(img_cat.view(B * S, 2 * d), pk[0]["multihead_attn"]["kv_w"]):
-                img_split = ops.split_f16(img_cat.view(B * S, 2 * d))       # image tokens are fixed over the layers
+            if i == 0 and ops.tc_linear_ok(img_cat.view(B * S, 2 * d), packed["kv_w"]) and \
+                    ops.attention_split_ok(2 * d // self.nhead, max(S, K)):
+                # image tokens are fixed over the layers: one split, one [k | v] projection GEMM for all of them
+                kv_all = ops.linear_split(ops.split_f16(img_cat.view(B * S, 2 * d)), packed["kv_w"], packed["kv_b"])
             cur = decoder_layer_forward(L, pk[i], self.nhead, cur, img_cat, kp_cat, kp_mask_fixed, adj,
-                                        attn_adj if use_bias else None, two_way=False, img_split=img_split)
+                                        attn_adj if use_bias else None, two_way=False, kv_split=kv_all,
+                                        kv_col=i * 4 * d)
             ops.layernorm(cur.view(B * K, d), self.decoder.norm.weight, self.decoder.norm.bias, 1e-5,
                           out=hs[i].view(B * K, d))
             delta = token_decode_mlp(cur.view(B * K, d), getattr(kpt_branch, str(i)))
