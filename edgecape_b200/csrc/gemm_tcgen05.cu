@@ -544,6 +544,12 @@ extern "C" int ec_tc_set_debug(int flags) {   // bring-up / profiling experiment
   ec_tc_debug = flags;
   return EC_OK;
 }
+static int ec_tc_cta_limit = 0;  // 0 = every SM; else the persistent grids use at most this many CTAs
+extern "C" int ec_tc_set_cta_limit(int ctas) {
+  EC_REQUIRE(ctas >= 0, "ec_tc_set_cta_limit: negative");
+  ec_tc_cta_limit = ctas & ~1;
+  return EC_OK;
+}
 static int ec_tc_force_bn = 0;   // 0 = heuristic; 128 / 256 force a tile width (tuning / tests)
 extern "C" int ec_tc_set_tile_n(int bn) {
   EC_REQUIRE(bn == 0 || bn == 128 || bn == 256 || bn == 512, "ec_tc_set_tile_n: 0, 128, 256 or 512 (CTA pair)");
@@ -614,7 +620,8 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.n_fastest = (cdiv(N, BN) <= 4 && (long long)M * Kp * 4 > (64LL << 20)) ? 1 : 0;   // A (hi+lo) beyond ~half of L2
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 512) {
-    const int pairs = (int)(pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2);
+    const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
+    const int pairs = (int)(pair_tiles < max_ctas / 2 ? pair_tiles : max_ctas / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(tc::THREADS);
@@ -632,7 +639,8 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
     EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true>, tmA, tmB, p));
   } else {
     const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
-    const int grid = tiles < num_sms ? tiles : num_sms;
+    const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
+    const int grid = tiles < max_ctas ? tiles : max_ctas;
     if (BN == 256)
       launch_pdl(tc::gemm_f16x3_kernel<256, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, p);
     else

@@ -17,80 +17,180 @@ from .skeleton import edges_to_csr, edges_to_csr_host
 from .vit import DinoVisionTransformerB200
 
 
+class _Slot:
+    """Static buffers, captured graphs and events of one in-flight batch."""
+    pass
+
+
+class PendingResult:
+    """A batch in flight.  `out` are the device tensors of `predict` (valid until `depth` more batches have been
+    submitted; ordered on `stream` / after `ready`); `result()` waits for the device->host copies and assembles the
+    reference's result dict."""
+
+    def __init__(self, engine, slot, img_metas, model):
+        self._engine, self._slot, self._metas, self._model = engine, slot, img_metas, model
+        self.out = slot.out
+        self.ready = slot.ev_head
+        self.stream = engine.head_stream
+        self._res = None
+
+    def wait_on(self, stream):
+        stream.wait_event(self.ready)
+        return self.out
+
+    def result(self):
+        if self._res is None:
+            s = self._slot
+            s.ev_out.synchronize()
+            host = s.host_out
+            res = {}
+            if self._model.with_keypoint:
+                res.update(self._model.keypoint_head_module.assemble_result(self._metas, host[2].numpy().copy()))
+            res.update({"points": host[0].numpy().copy()})
+            res.update({"sample_image_file": [m["sample_image_file"] for m in self._metas]})
+            res.update({"skeleton": host[1].numpy().copy()})
+            s.pending = None
+            self._res = res
+        return self._res
+
+
 class _GraphedForward:
-    """Captured CUDA graphs of EdgeCape._forward_device for a fixed input signature, with static input
-    buffers (images, heat-maps, visibility weights, CSR edge lists up to `edge_capacity`).
+    """Captured CUDA graphs of EdgeCape's device-side forward for a fixed input signature, as a `depth`-deep
+    software pipeline over consecutive batches.
 
-    Two graphs: (A) the batched ViT over [query; supports], (B) mask + head.  Per call the images are
-    copied on the launch stream and A is replayed, while heat-maps / weights / edge lists (half of the
-    H2D bytes, only needed by B) are copied on a side stream concurrently with A; B joins them."""
+    Per slot: static input buffers (images, heat-maps, visibility weights, CSR edge lists up to `edge_capacity`,
+    crop centre / scale), two graphs -- (A) the batched ViT over [query; supports], (B) mask + head + decode to image
+    coordinates -- and pinned host buffers for the results.  Three streams: copies, A, B.  For batch i in slot
+    s = i % depth:  copy(images) -> A ;  copy(head inputs) + A -> B -> device->host copies.  A of batch i+1 therefore
+    runs next to B of batch i (whose ~300 small kernels leave most SMs idle) and next to the H2D / D2H traffic of
+    its neighbours; the buffers of a slot are recycled under events (A(i) waits for B(i-depth), the copies wait for
+    the graph that last read the buffer)."""
 
-    def __init__(self, model, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev):
-        mk = lambda t: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
-        self.img_q = mk(img_q)
-        self.img_s = [mk(t) for t in img_s]
-        self.target_s = [mk(t) for t in target_s]
-        self.tw_s = [mk(t) for t in target_weight_s]
-        B = img_q.shape[0]
-        self.B = B
+    def __init__(self, model, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev, img_hw, depth=2):
+        self.model = model
+        self.dev = dev
+        self.depth = depth
+        self.B = B = img_q.shape[0]
         self.edge_capacity = max(1024, 2 * int(e_np.shape[0]))
-        self.edges = torch.zeros(self.edge_capacity, 2, dtype=torch.int32, device=dev)
-        self.offsets = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-        self.host = torch.empty(2 * self.edge_capacity + B + 1, dtype=torch.int32).pin_memory()
-        self.staged = None
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self.vit_stream = torch.cuda.Stream(device=dev)
+        self.head_stream = torch.cuda.Stream(device=dev)
+        self.img_hw = img_hw
+        self.count = 0
+        mk = lambda t: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
         main = torch.cuda.current_stream(dev)
-        self._load_images(img_q, img_s)
-        self._load_head_inputs(main, target_s, target_weight_s, e_np, o_np)
-        main.wait_stream(self.copy_stream)
-        # warm-up on a side stream (packs weights, fills caches, sets kernel attributes), then capture
+        self.slots = []
+        for _ in range(depth):
+            s = _Slot()
+            s.img_q = mk(img_q)
+            s.img_s = [mk(t) for t in img_s]
+            s.target_s = [mk(t) for t in target_s]
+            s.tw_s = [mk(t) for t in target_weight_s]
+            s.edges = torch.zeros(self.edge_capacity, 2, dtype=torch.int32, device=dev)
+            s.offsets = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+            s.cs = torch.zeros(B, 4, dtype=torch.float32, device=dev)
+            s.host_in = torch.empty(2 * self.edge_capacity + B + 1, dtype=torch.int32).pin_memory()
+            s.host_cs = torch.empty(B, 4, dtype=torch.float32).pin_memory()
+            s.ev_img, s.ev_hin, s.ev_vit, s.ev_head, s.ev_out = (torch.cuda.Event() for _ in range(5))
+            s.used = False
+            s.pending = None
+            self.slots.append(s)
+        # warm-up on a side stream (packs weights, fills caches, sets kernel attributes), then capture per slot
+        s0 = self.slots[0]
+        for d, t in zip([s0.img_q] + s0.img_s + s0.target_s + s0.tw_s,
+                        [img_q] + list(img_s) + list(target_s) + list(target_weight_s)):
+            d.copy_(t, non_blocking=True)
+        ne, no = e_np.shape[0], o_np.shape[0]
+        s0.offsets.copy_(torch.from_numpy(o_np))
+        if ne:
+            s0.edges[:ne].copy_(torch.from_numpy(e_np))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for _ in range(2):
-                model._forward_device(self.img_q, self.img_s, self.target_s, self.tw_s, (self.edges, self.offsets))
+                self._head(s0, *model.extract_features(s0.img_s, s0.img_q))
         main.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph_vit = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_vit):
-            self.feat_q, self.feats_s = model.extract_features(self.img_s, self.img_q)
-        self.graph_head = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_head, pool=self.graph_vit.pool()):
-            self.out = model._head_device(self.feat_q, self.feats_s, self.target_s, self.tw_s,
-                                          (self.edges, self.offsets))
+        for s in self.slots:
+            s.graph_vit = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(s.graph_vit):
+                s.feat_q, s.feats_s = model.extract_features(s.img_s, s.img_q)
+            s.graph_head = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(s.graph_head, pool=s.graph_vit.pool()):
+                s.out, s.preds = self._head(s, s.feat_q, s.feats_s)
+            L, _, K, _ = s.out[0].shape
+            s.host_out = tuple(t.pin_memory() for t in (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K),
+                                                        torch.empty(B, K, 3)))
 
-    def _load_images(self, img_q, img_s):
-        self.img_q.copy_(img_q, non_blocking=True)
-        for d, s_ in zip(self.img_s, img_s):
-            d.copy_(s_, non_blocking=True)
+    def _head(self, s, feat_q, feats_s):
+        """mask + head + decode to image coordinates (TwoStageHead.decode arithmetic on the device)."""
+        model = self.model
+        out = model._head_device(feat_q, feats_s, s.target_s, s.tw_s, (s.edges, s.offsets))
+        W, H = self.img_hw
+        preds = ops.decode_preds(out[0][-1].contiguous(), s.cs, W, H,
+                                 use_udp=model.keypoint_head_module.test_cfg.get("use_udp", False))
+        return out, preds
 
-    def _load_head_inputs(self, main, target_s, target_weight_s, e_np, o_np):
-        if self.staged is not None:
-            self.staged.synchronize()      # the pinned CSR staging buffer is reused: wait for its last H2D
+    def submit(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, img_metas, want_host=True):
+        dev = self.dev
+        s = self.slots[self.count % self.depth]
+        self.count += 1
+        if s.pending is not None:
+            s.pending.result()             # its pinned result buffers are about to be reused
+        if s.used:
+            s.ev_hin.synchronize()         # the pinned staging buffers of this slot: wait for their last H2D
         ne, no = e_np.shape[0], o_np.shape[0]
-        self.host[:no] = torch.from_numpy(o_np)
-        self.host[no:no + 2 * ne] = torch.from_numpy(e_np.reshape(-1))
-        cs = self.copy_stream
-        cs.wait_stream(main)               # the previous replay of graph B may still read these buffers
-        with torch.cuda.stream(cs):
-            for d, s_ in zip(self.target_s + self.tw_s, list(target_s) + list(target_weight_s)):
-                d.copy_(s_, non_blocking=True)
-            self.offsets.copy_(self.host[:no], non_blocking=True)
+        s.host_in[:no] = torch.from_numpy(o_np)
+        s.host_in[no:no + 2 * ne] = torch.from_numpy(e_np.reshape(-1))
+        if img_metas is not None and "query_center" in img_metas[0]:
+            cs = s.host_cs.numpy()
+            for i, m in enumerate(img_metas):
+                cs[i, 0:2] = np.asarray(m["query_center"], dtype=np.float32).reshape(-1)[:2]
+                cs[i, 2:4] = np.asarray(m["query_scale"], dtype=np.float32).reshape(-1)[:2]
+        cur = torch.cuda.current_stream(dev)
+        ev_in = torch.cuda.Event()
+        ev_in.record(cur)                  # device-resident inputs may still be in production on the caller's stream
+        cp, vs, hs = self.copy_stream, self.vit_stream, self.head_stream
+        with torch.cuda.stream(cp):
+            cp.wait_event(ev_in)
+            # images first: the DMA engine serves copies in issue order and graph A only needs the images
+            if s.used:
+                cp.wait_event(s.ev_vit)    # A(i - depth) has read the image buffers
+            s.img_q.copy_(img_q, non_blocking=True)
+            for d, t in zip(s.img_s, img_s):
+                d.copy_(t, non_blocking=True)
+            s.ev_img.record(cp)
+            if s.used:
+                cp.wait_event(s.ev_head)   # B(i - depth) has read the head inputs
+            for d, t in zip(s.target_s + s.tw_s, list(target_s) + list(target_weight_s)):
+                d.copy_(t, non_blocking=True)
+            s.offsets.copy_(s.host_in[:no], non_blocking=True)
             if ne:
-                self.edges[:ne].view(-1).copy_(self.host[no:no + 2 * ne], non_blocking=True)
-            self.staged = torch.cuda.Event()
-            self.staged.record(cs)
-
-    def run(self, img_q, img_s, target_s, target_weight_s, e_np, o_np):
-        main = torch.cuda.current_stream(self.img_q.device)
-        # images first: the DMA engine serves copies in issue order and graph A only needs the images; the
-        # head inputs follow on the copy stream and overlap graph A
-        self._load_images(img_q, img_s)
-        self._load_head_inputs(main, target_s, target_weight_s, e_np, o_np)
-        self.graph_vit.replay()
-        main.wait_stream(self.copy_stream)
-        self.graph_head.replay()
-        return self.out
+                s.edges[:ne].view(-1).copy_(s.host_in[no:no + 2 * ne], non_blocking=True)
+            s.cs.copy_(s.host_cs, non_blocking=True)
+            s.ev_hin.record(cp)
+        with torch.cuda.stream(vs):
+            vs.wait_event(s.ev_img)
+            if s.used:
+                vs.wait_event(s.ev_head)   # B(i - depth) has read this slot's features
+            s.graph_vit.replay()
+            s.ev_vit.record(vs)
+        with torch.cuda.stream(hs):
+            hs.wait_event(s.ev_vit)
+            hs.wait_event(s.ev_hin)
+            s.graph_head.replay()
+            s.ev_head.record(hs)
+            if want_host:
+                output, initial_proposals, _, _, adj = s.out
+                s.host_out[0][0].copy_(initial_proposals, non_blocking=True)
+                s.host_out[0][1:].copy_(output, non_blocking=True)
+                s.host_out[1].copy_(adj[0], non_blocking=True)
+                s.host_out[2].copy_(s.preds, non_blocking=True)
+                s.ev_out.record(hs)
+        s.used = True
+        h = PendingResult(self, s, img_metas, self.model)
+        s.pending = h if want_host else None
+        return h
 
 
 def _require_cuda(dev):
@@ -150,6 +250,9 @@ class EdgeCape(nn.Module):
                      vis_offset=True, **kwargs):
         """Returns the reference's result dict (:131-163): preds [B,K,3], boxes [B,6], image_paths,
         bbox_ids, points [1+L,B,K,2], sample_image_file, skeleton [2,K,K] (adjacency of batch item 0)."""
+        if self.use_cuda_graph and self.device.type == "cuda":
+            return self.forward_test_async(img_s, target_s, target_weight_s, img_q, target_q, target_weight_q,
+                                           img_metas, **kwargs).result()
         batch_size, _, img_height, img_width = img_q.shape
         output, initial_proposals, similarity_map, _, adj = self.predict(img_s, target_s, target_weight_s, img_q,
                                                                          img_metas)
@@ -185,6 +288,23 @@ class EdgeCape(nn.Module):
         return result
 
     @torch.no_grad()
+    def forward_test_async(self, img_s, target_s, target_weight_s, img_q, target_q=None, target_weight_q=None,
+                           img_metas=None, **kwargs):
+        """forward_test without the final wait: enqueues the batch (H2D copies, backbone graph, head graph, decode,
+        D2H copies) and returns a PendingResult; `.result()` gives forward_test's dict.  Up to `pipeline_depth`
+        (test_cfg, default 2) batches may be in flight: the backbone of batch i+1 then runs beside the head of batch
+        i and the copies of both -- this is what `edgecape_b200.apis.single_gpu_test` does."""
+        _require_cuda(self.device)
+        return self._submit(img_s, target_s, target_weight_s, img_q, img_metas, want_host=True)
+
+    @torch.no_grad()
+    def predict_async(self, img_s, target_s, target_weight_s, img_q, img_metas=None):
+        """Device-level form of forward_test_async: returns a PendingResult whose `.out` = the tuple `predict`
+        returns, ordered on `.stream` (enqueue consumers there, or `.wait_on(stream)`); no device->host traffic."""
+        _require_cuda(self.device)
+        return self._submit(img_s, target_s, target_weight_s, img_q, img_metas, want_host=False)
+
+    @torch.no_grad()
     def predict(self, img_s, target_s, target_weight_s, img_q, img_metas=None, return_intermediates=False):
         """(:165-184).  Accepts CPU or CUDA tensors; CPU inputs are uploaded (pinned or pageable).
         With `use_cuda_graph` (default; test_cfg['cuda_graph']=False disables) the whole device-side
@@ -194,7 +314,7 @@ class EdgeCape(nn.Module):
         _require_cuda(dev)
         skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
         if self.use_cuda_graph and not return_intermediates and dev.type == "cuda":
-            return self._predict_graphed(img_s, target_s, target_weight_s, img_q, skeleton_lst)
+            return self._predict_graphed(img_s, target_s, target_weight_s, img_q, img_metas)
         up = lambda t: t.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         edges, offsets = edges_to_csr(skeleton_lst, dev)
         return self._forward_device(up(img_q), [up(t) for t in img_s], [up(t) for t in target_s],
@@ -224,17 +344,27 @@ class EdgeCape(nn.Module):
         return self.keypoint_head_module.forward_tokens(feat_q, feats_s, target_s, mask_s, skeleton)
 
     # ------------------------------------------------------------------------ CUDA graphs
-    def _predict_graphed(self, img_s, target_s, target_weight_s, img_q, skeleton_lst):
+    def _submit(self, img_s, target_s, target_weight_s, img_q, img_metas, want_host):
         dev = self.device
+        skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
         e_np, o_np = edges_to_csr_host(skeleton_lst)
         key = (tuple(img_q.shape), len(img_s), tuple(target_s[0].shape), ops.TENSOR_CORES)
         g = self._graphs.get(key)
         if g is None or g.edge_capacity < e_np.shape[0]:
-            g = _GraphedForward(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev)
+            if g is not None:
+                torch.cuda.synchronize(dev)          # batches in flight on the engine being replaced
+            g = _GraphedForward(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev,
+                                (img_q.shape[-1], img_q.shape[-2]), depth=int(self.test_cfg.get("pipeline_depth", 2)))
             if len(self._graphs) >= 8:
+                torch.cuda.synchronize(dev)
                 self._graphs.clear()
             self._graphs[key] = g
-        return g.run(img_q, img_s, target_s, target_weight_s, e_np, o_np)
+        return g.submit(img_q, img_s, target_s, target_weight_s, e_np, o_np, img_metas, want_host=want_host)
+
+    def _predict_graphed(self, img_s, target_s, target_weight_s, img_q, img_metas):
+        """Synchronous-on-the-current-stream form: the outputs are ordered after everything the caller enqueues next."""
+        h = self._submit(img_s, target_s, target_weight_s, img_q, img_metas, want_host=False)
+        return h.wait_on(torch.cuda.current_stream(self.device))
 
     @torch.no_grad()
     def extract_features(self, img_s, img_q):

@@ -85,6 +85,9 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
 /* tuning knob for ec_gemm_f16x3: 0 = pick the tile width per shape (128x256 tiles for wide, large
  * problems, 128x128 otherwise), 128 / 256 = force it. */
 int ec_tc_set_tile_n(int bn);
+/* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
+ * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
+int ec_tc_set_cta_limit(int ctas);
 /* programmatic dependent launch of the library's kernels (default on; EDGECAPE_PDL=0 or ec_set_pdl(0) = plain
  * stream-ordered launches, for A/B measurements) */
 int ec_set_pdl(int on);

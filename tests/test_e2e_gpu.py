@@ -128,3 +128,33 @@ def test_pck_agrees_with_reference(golden_dir):
         want = np.mean([((np.linalg.norm((ref[b] - gt[b]) / norm[b], axis=-1) < t)[valid[b]]).mean() for b in range(B)])
         assert abs(ours[f"PCK@{t}"] - want) <= 0.01, (t, ours, want)
     assert 0.2 < ours["PCK@0.2"] < 0.99          # the noise level makes the metric informative
+
+
+def test_pipelined_test_loop_equals_one_call_per_batch():
+    """edgecape_b200.apis.single_gpu_test keeps two batches in flight (backbone of batch i+1 beside the head of batch
+    i, copies beside both).  Same kernels on the same inputs: the results must equal the synchronous
+    model(return_loss=False, **data) calls bit for bit, in order, also when a slot is reused several times and when
+    the skeletons (edge counts) change from batch to batch."""
+    from edgecape_b200.apis import single_gpu_test
+    from edgecape_b200.config import default_model_cfg
+    cfg = default_model_cfg("dinov2_vits14")
+    model = _build(cfg, 3)
+    batches = [make_episode(batch=3, image_size=224, num_kpts=17, shots=1, seed=50 + i, pin_memory=True)
+               for i in range(7)]
+    want = [model(return_loss=False, **d) for d in batches]
+    got = single_gpu_test(model, batches)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in ("preds", "boxes", "points", "skeleton"):
+            assert np.array_equal(np.asarray(g[k]), np.asarray(w[k])), k
+        assert g["image_paths"] == w["image_paths"] and g["bbox_ids"] == w["bbox_ids"]
+    # device-level handles: outputs stay valid until `depth` more submissions
+    h0 = model.predict_async(batches[0]["img_s"], batches[0]["target_s"], batches[0]["target_weight_s"],
+                             batches[0]["img_q"], batches[0]["img_metas"])
+    out0 = h0.wait_on(torch.cuda.current_stream())[0].clone()
+    h1 = model.predict_async(batches[1]["img_s"], batches[1]["target_s"], batches[1]["target_weight_s"],
+                             batches[1]["img_q"], batches[1]["img_metas"])
+    torch.cuda.synchronize()
+    assert torch.equal(h0.out[0], out0)
+    assert np.array_equal(h0.out[0][-1].cpu().numpy(), want[0]["points"][-1])
+    assert np.array_equal(h1.out[0][-1].cpu().numpy(), want[1]["points"][-1])
