@@ -67,6 +67,7 @@ SIGNATURES = {
     "ec_interp_pos_embed": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_d, c_fp]),
     "ec_write_cls": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_fp]),
     "ec_pck_accumulate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_fp]),
+    "ec_metrics_accumulate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp, c_int, c_int, c_fp]),
 }
 
 

@@ -177,6 +177,68 @@ __global__ void __launch_bounds__(128) pck_kernel(const float* __restrict__ pred
   if (threadIdx.x == 0) atomicAdd(&counters[T], 1.0);
 }
 
+// All four metrics of the reference's test loop for one sample per CTA (test_base_dataset.py:119-154 on mmpose 0.29
+// keypoint_pck_accuracy / keypoint_nme / keypoint_auc / keypoint_epe with N = 1):
+//   counters[0..T-1] += PCK@thr[t]   (valid keypoints with normalised distance < thr) / valid
+//   counters[T]      += NME          mean normalised distance over valid keypoints
+//   counters[T+1]    += AUC          mean over i < auc_steps of PCK@(i / auc_steps), normaliser norm[b,0] on both axes
+//   counters[T+2]    += EPE          mean un-normalised distance over valid keypoints
+//   counters[T+3]    += 1
+// A zero in the normaliser masks the whole sample for PCK / NME / AUC; a negative one becomes 1e6 (_calc_distances).
+// Distances are formed in fp64 and rounded to fp32 as mmpose does (float64 inputs, float32 distance table).
+__global__ void __launch_bounds__(128) metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                      const uint8_t* __restrict__ valid, const float* __restrict__ norm,
+                                                      const float* __restrict__ thr, int T, int auc_steps,
+                                                      double* counters, int K) {
+  const int b = blockIdx.x;
+  __shared__ int hits[16], auc_hits[64];
+  __shared__ int nvalid, nvalid_n;
+  __shared__ double sum_n, sum_e;
+  if (threadIdx.x < 16) hits[threadIdx.x] = 0;
+  if (threadIdx.x < 64) auc_hits[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { nvalid = 0; nvalid_n = 0; sum_n = 0.0; sum_e = 0.0; }
+  __syncthreads();
+  float nx = norm[2 * b], ny = norm[2 * b + 1];
+  const bool norm_ok = nx != 0.f && ny != 0.f;          // a zero normaliser masks the sample (not for EPE)
+  if (nx <= 0.f) nx = 1e6f;
+  if (ny <= 0.f) ny = 1e6f;
+  const float ax = norm[2 * b] <= 0.f ? 1e6f : norm[2 * b];   // keypoint_auc tiles norm[b,0] on both axes
+  const bool auc_ok = norm[2 * b] != 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (!valid[(long long)b * K + k]) continue;
+    const double ex = (double)pred[((long long)b * K + k) * 2] - (double)gt[((long long)b * K + k) * 2];
+    const double ey = (double)pred[((long long)b * K + k) * 2 + 1] - (double)gt[((long long)b * K + k) * 2 + 1];
+    const float d_e = (float)sqrt(ex * ex + ey * ey);
+    atomicAdd(&nvalid, 1);
+    atomicAdd(&sum_e, (double)d_e);
+    if (norm_ok) {
+      const double dx = ex / (double)nx, dy = ey / (double)ny;
+      const float d_n = (float)sqrt(dx * dx + dy * dy);
+      atomicAdd(&nvalid_n, 1);
+      atomicAdd(&sum_n, (double)d_n);
+      for (int t = 0; t < T; ++t)
+        if ((double)d_n < (double)thr[t]) atomicAdd(&hits[t], 1);
+    }
+    if (auc_ok) {
+      const double dx = ex / (double)ax, dy = ey / (double)ax;
+      const float d_a = (float)sqrt(dx * dx + dy * dy);
+      for (int i = 0; i < auc_steps; ++i)
+        if ((double)d_a < (double)i / (double)auc_steps) atomicAdd(&auc_hits[i], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < T) atomicAdd(&counters[threadIdx.x], nvalid_n > 0 ? (double)hits[threadIdx.x] / (double)nvalid_n : 0.0);
+  if (threadIdx.x == 0) {
+    atomicAdd(&counters[T], sum_n / (double)max(1, nvalid_n));
+    double auc = 0.0;
+    if (auc_ok && nvalid > 0)
+      for (int i = 0; i < auc_steps; ++i) auc += (1.0 / auc_steps) * ((double)auc_hits[i] / (double)nvalid);
+    atomicAdd(&counters[T + 1], auc);
+    atomicAdd(&counters[T + 2], sum_e / (double)max(1, nvalid));
+    atomicAdd(&counters[T + 3], 1.0);
+  }
+}
+
 // preds[b,k,:] = (transform_preds(points[b,k] * [W,H], center[b], scale[b], [W,H]), 1): the heat-map-space ->
 // image-space affine of TwoStageHead.decode, cs = [cx, cy, sx, sy] per sample
 __global__ void decode_preds_kernel(const float* __restrict__ points, const float* __restrict__ cs,
@@ -245,4 +307,14 @@ extern "C" int ec_pck_accumulate(const float* pred, const float* gt, const uint8
   if (B == 0) return EC_OK;
   pck_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(pred, gt, valid, norm, thr, T, counters, K);
   return check_launch("ec_pck_accumulate");
+}
+
+extern "C" int ec_metrics_accumulate(const float* pred, const float* gt, const uint8_t* valid, const float* norm,
+                                     const float* thr, int T, int auc_steps, double* counters, int B, int K,
+                                     void* stream) {
+  EC_REQUIRE(pred && gt && valid && norm && thr && counters, "ec_metrics_accumulate: null pointer");
+  EC_REQUIRE(T >= 1 && T <= 16 && auc_steps >= 1 && auc_steps <= 64, "ec_metrics_accumulate: 1..16 thresholds, 1..64 AUC steps");
+  if (B == 0) return EC_OK;
+  metrics_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(pred, gt, valid, norm, thr, T, auc_steps, counters, K);
+  return check_launch("ec_metrics_accumulate");
 }

@@ -619,6 +619,18 @@ def write_cls_(tokens, cls, pos0):
     return tokens
 
 
+def metrics_accumulate_(counters, pred, gt, valid, norm, thr, auc_steps=20):
+    """counters (fp64, >= T+4) += [per-sample PCK@thr..., NME, AUC, EPE, 1] for every sample of the batch."""
+    _chk(pred, "pred"); _chk(gt, "gt"); _chk(valid, "valid", torch.uint8); _chk(norm, "norm"); _chk(thr, "thr")
+    _chk(counters, "counters", torch.float64)
+    B, K, _ = pred.shape
+    assert pred.is_contiguous() and gt.is_contiguous() and valid.is_contiguous() and norm.is_contiguous()
+    assert counters.numel() >= thr.numel() + 4
+    _lib.call("ec_metrics_accumulate", _p(pred), _p(gt), _p(valid), _p(norm), _p(thr), thr.numel(), int(auc_steps),
+              _p(counters), B, K, _stream())
+    return counters
+
+
 def pck_accumulate_(counters, pred, gt, valid, norm, thr):
     _chk(pred, "pred"); _chk(gt, "gt"); _chk(valid, "valid", torch.uint8); _chk(norm, "norm"); _chk(thr, "thr")
     _chk(counters, "counters", torch.float64)

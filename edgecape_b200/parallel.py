@@ -39,3 +39,19 @@ def summarize_pck(counters, thresholds=PCK_THRESHOLDS):
     out["mPCK"] = sum(out.values()) / len(thresholds)
     out["samples"] = int(c[len(thresholds)])
     return out
+
+
+def new_metric_counters(device, n_thresholds=len(PCK_THRESHOLDS)):
+    """[sum PCK@t ..., sum NME, sum AUC, sum EPE, n_samples] in fp64 (ec_metrics_accumulate's layout)."""
+    return torch.zeros(n_thresholds + 4, dtype=torch.float64, device=device)
+
+
+def summarize_metrics(counters, thresholds=PCK_THRESHOLDS):
+    """`_report_metric`'s means (test_base_dataset.py:119-154) from the all-reduced counter vector."""
+    c = counters.detach().cpu().tolist()
+    T = len(thresholds)
+    n = max(c[T + 3], 1.0)
+    out = {f"PCK@{t}": c[i] / n for i, t in enumerate(thresholds)}
+    out["mPCK"] = sum(out.values()) / T
+    out.update(NME=c[T] / n, AUC=c[T + 1] / n, EPE=c[T + 2] / n, samples=int(c[T + 3]))
+    return out

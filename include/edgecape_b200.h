@@ -267,6 +267,13 @@ int ec_write_cls(const float* cls, const float* pos0, float* tokens, int B, long
  * PCK@thr[t]; counters[T] += number of samples.  Accumulated in fp64 for one ncclAllReduce. */
 int ec_pck_accumulate(const float* pred, const float* gt, const uint8_t* valid, const float* norm,
                       const float* thr, int T, double* counters, int B, int K, void* stream);
+/* every metric of `_report_metric` (test_base_dataset.py:119-154; mmpose 0.29 keypoint_pck_accuracy / keypoint_nme /
+ * keypoint_auc / keypoint_epe, one sample at a time): counters[0..T-1] += PCK@thr[t]; counters[T] += NME;
+ * counters[T+1] += AUC over auc_steps thresholds i/auc_steps (mmpose: 20) normalised by norm[b,0];
+ * counters[T+2] += EPE (pixels); counters[T+3] += 1.  One fp64 vector for the final all-reduce. */
+int ec_metrics_accumulate(const float* pred, const float* gt, const uint8_t* valid, const float* norm,
+                          const float* thr, int T, int auc_steps, double* counters, int B, int K,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -457,6 +457,21 @@ def ec_pck_accumulate(pred, gt, valid, norm, thr, Tn, counters, B, K, stream):
         c[Tn] += 1
 
 
+def ec_metrics_accumulate(pred, gt, valid, norm, thr, Tn, auc_steps, counters, B, K, stream):
+    from oracle import metrics_oracle as mo
+    p, g = arr(pred, (B, K, 2)).astype(np.float64), arr(gt, (B, K, 2)).astype(np.float64)
+    v, n, th = arr(valid, (B, K), dtype=np.uint8).astype(bool), arr(norm, (B, 2)), arr(thr, (Tn,))
+    c = arr(counters, (Tn + 4,), dtype=np.float64)
+    for b in range(B):
+        p1, g1, m1, nb = p[b:b + 1], g[b:b + 1], v[b:b + 1], n[b:b + 1].astype(np.float64)
+        for t in range(Tn):
+            c[t] += mo.keypoint_pck_accuracy(p1, g1, m1, float(th[t]), nb)[1]
+        c[Tn] += mo.keypoint_nme(p1, g1, m1, nb)
+        c[Tn + 1] += mo.keypoint_auc(p1, g1, m1, float(nb[0, 0]), auc_steps)
+        c[Tn + 2] += mo.keypoint_epe(p1, g1, m1)
+        c[Tn + 3] += 1
+
+
 FUNCS = {k: v for k, v in list(globals().items()) if k.startswith("ec_")}
 
 

@@ -351,6 +351,35 @@ def test_pck_counters():
     assert torch.allclose(c.cpu(), want, atol=1e-9)
 
 
+def test_metric_counters_match_report_metric_oracle():
+    """ec_metrics_accumulate vs the restated mmpose metrics + the reference's per-sample reduction, including a sample
+    without valid keypoints, a zero normaliser and a negative one."""
+    from oracle import metrics_oracle as mo
+    from edgecape_b200.parallel import PCK_THRESHOLDS, new_metric_counters, summarize_metrics
+    B, K = 7, 33
+    g = torch.Generator().manual_seed(1)
+    gt = torch.rand(B, K, 2, generator=g) * 200
+    pred = gt + torch.randn(B, K, 2, generator=g) * 25
+    valid = torch.rand(B, K, generator=g) > 0.3
+    valid[4] = False
+    bbox = torch.tensor([200.0, 150.0, 80.0, 300.0, 120.0, 0.0, -5.0])
+    norm = torch.stack((bbox, bbox), dim=1)
+    want = mo.report_metric(list(pred.double().numpy()), list(gt.double().numpy()), list(valid.numpy()),
+                            list(bbox.double().numpy()), PCK_THRESHOLDS)
+    D = dev()
+    c = new_metric_counters(D)
+    thr = torch.tensor(PCK_THRESHOLDS, dtype=torch.float32)
+    for lo in (0, 4):                       # two calls accumulate into the same vector
+        hi = 4 if lo == 0 else B
+        ops.metrics_accumulate_(c, pred[lo:hi].contiguous().to(D), gt[lo:hi].contiguous().to(D),
+                                valid[lo:hi].to(torch.uint8).contiguous().to(D), norm[lo:hi].contiguous().to(D), thr.to(D))
+    assert np.allclose(c.cpu().numpy(), np.array(want["sums"]), rtol=1e-6, atol=1e-9), (c.cpu().numpy(), want["sums"])
+    got = summarize_metrics(c)
+    for k in ("PCK@0.05", "PCK@0.2", "mPCK", "NME", "AUC", "EPE"):
+        assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, got[k], want[k])
+    assert got["samples"] == B
+
+
 # ------------------------------------------------------------- tensor-core (tcgen05) GEMM
 def test_split_f16_reconstructs_fp32():
     x = rnd(300, 588, seed=1, scale=2.0)
