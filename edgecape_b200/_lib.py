@@ -66,6 +66,8 @@ SIGNATURES = {
     "ec_im2col_patches": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_int, c_fp]),
     "ec_interp_pos_embed": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_d, c_fp]),
     "ec_write_cls": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_fp]),
+    "ec_warp_affine_normalize_u8": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_fp, c_int, c_int, c_fp, c_fp, c_fp]),
+    "ec_msra_targets": (c_int, [c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_fp]),
     "ec_pck_accumulate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_fp]),
     "ec_metrics_accumulate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp, c_int, c_int, c_fp]),
 }

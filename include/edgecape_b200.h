@@ -261,6 +261,20 @@ int ec_interp_pos_embed(const float* pos_embed, float* pos_out, int Mgrid, int h
 int ec_write_cls(const float* cls, const float* pos0, float* tokens, int B, long long stride, int C,
                  void* stream);
 
+/* -------------------------------------------------------------------------- input stage
+ * TopDownAffineFewShot + ToTensor + NormalizeTensor (datasets/pipelines/top_down_transform.py:35-67, configs/test/
+ * 1shot_split1.py:101-108): src = uint8 HxWx3 image in device memory (row_stride bytes per row), M = the 2x3 double matrix
+ * of get_affine_transform (HOST pointer, source -> crop), out = fp32 [3,H,W] = (warpAffine(src)/255 - mean) / std.
+ * The crop reproduces cv2.warpAffine(INTER_LINEAR) on uint8 bit for bit (fixed-point coordinates and weights).
+ * mean / stdv: 3 floats each, HOST pointers. */
+int ec_warp_affine_normalize_u8(const uint8_t* src, int Hs, int Ws, long long row_stride, const double* M,
+                                float* out, int H, int W, const float* mean, const float* stdv, void* stream);
+/* TopDownGenerateTargetFewShot._msra_generate_target (top_down_transform.py:113-199, unbiased_encoding=False):
+ * joints [n, ldj] (x, y in crop pixels), visible [n, ldv] -> target [n,H,W] un-normalised Gaussian patches (sigma an
+ * integer), weight [n] (visibility, 0 when the patch falls outside the map). */
+int ec_msra_targets(const float* joints, int ldj, const float* visible, int ldv, float* target, float* weight,
+                    int n, int img_w, int img_h, int W, int H, float sigma, void* stream);
+
 /* -------------------------------------------------------------------------- evaluation
  * per-sample PCK (mmpose keypoint_pck_accuracy semantics, datasets/.../test_base_dataset.py:
  * 104-133): pred/gt [B,K,2], valid uint8 [B,K], norm [B,2]; counters[0..T-1] += per-sample

@@ -457,6 +457,23 @@ def ec_pck_accumulate(pred, gt, valid, norm, thr, Tn, counters, B, K, stream):
         c[Tn] += 1
 
 
+def ec_warp_affine_normalize_u8(src, Hs, Ws, row_stride, M, out, H, W, mean, stdv, stream):
+    import ctypes
+    from oracle import input_oracle as io
+    img = arr(src, (Hs, Ws, 3), (row_stride, 3, 1), dtype=np.uint8)
+    Mh = np.ctypeslib.as_array((ctypes.c_double * 6).from_address(M)).reshape(2, 3)
+    mh = np.ctypeslib.as_array((ctypes.c_float * 3).from_address(mean))
+    sh = np.ctypeslib.as_array((ctypes.c_float * 3).from_address(stdv))
+    arr(out, (3, H, W))[...] = io.to_tensor_normalize(io.warp_affine_u8(img, Mh, W, H), mh, sh)
+
+
+def ec_msra_targets(joints, ldj, visible, ldv, target, weight, n, img_w, img_h, W, H, sigma, stream):
+    from oracle import input_oracle as io
+    t, w = io.msra_targets(arr(joints, (n, ldj)), arr(visible, (n, ldv)), (img_w, img_h), (W, H), int(sigma))
+    arr(target, (n, H, W))[...] = t
+    arr(weight, (n,))[...] = w[:, 0]
+
+
 def ec_metrics_accumulate(pred, gt, valid, norm, thr, Tn, auc_steps, counters, B, K, stream):
     from oracle import metrics_oracle as mo
     p, g = arr(pred, (B, K, 2)).astype(np.float64), arr(gt, (B, K, 2)).astype(np.float64)

@@ -1,0 +1,37 @@
+"""CPU: the input-stage oracle (oracle/input_oracle.py) against the golden vectors the UNMODIFIED reference pipeline +
+OpenCV produced (tests/golden/input_stage.npz, oracle/gen_golden_input.py)."""
+import os
+
+import numpy as np
+
+from oracle import input_oracle as io
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "input_stage.npz"))
+R, HM = 256, 64
+
+
+def test_affine_matrix_matches_cv2():
+    for i in range(int(G["n"])):
+        M = io.get_affine_transform(G[f"center{i}"], G[f"scale{i}"], 0, (R, R))
+        assert np.allclose(M, G[f"trans{i}"], rtol=0, atol=1e-9), i
+
+
+def test_warp_is_bit_exact_with_cv2():
+    for i in range(int(G["n"])):
+        got = io.warp_affine_u8(G[f"img{i}"], G[f"trans{i}"], R, R)
+        assert np.array_equal(got, G[f"warped{i}"]), (i, np.abs(got.astype(int) - G[f"warped{i}"].astype(int)).max())
+        # and with the oracle's own matrix (the solver differs from OpenCV's in the last bits)
+        got2 = io.warp_affine_u8(G[f"img{i}"], io.get_affine_transform(G[f"center{i}"], G[f"scale{i}"], 0, (R, R)), R, R)
+        assert (got2 != G[f"warped{i}"]).mean() < 1e-3
+
+
+def test_tensor_and_joints_and_targets():
+    for i in range(int(G["n"])):
+        t = io.to_tensor_normalize(G[f"warped{i}"], G["mean"], G["std"])
+        assert np.array_equal(t[:, :4, :4], G[f"tensor_corner{i}"])
+        assert abs(float(t.astype(np.float64).sum()) - float(G[f"tensor_sum{i}"])) < 1e-6 * abs(float(G[f"tensor_sum{i}"])) + 1e-3
+        jt = io.affine_transform_joints(G[f"joints{i}"], G[f"vis{i}"], G[f"trans{i}"])
+        assert np.allclose(jt, G[f"joints_t{i}"], atol=1e-4)
+        target, weight = io.msra_targets(G[f"joints_t{i}"], G[f"vis{i}"], (R, R), (HM, HM), 1)
+        assert np.array_equal(weight, G[f"weight{i}"])
+        assert np.array_equal(target, G[f"target{i}"])
