@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="queries per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--backbone", default="dinov2_vitb14")
+    ap.add_argument("--dedup-demo", action="store_true",
+                    help="also time episodes whose queries share their support sample, with and without de-duplication")
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--kpts", type=int, default=100)
     ap.add_argument("--shots", type=int, default=1)
@@ -51,6 +53,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
+
+
+def q_per_step_local(B, world):
+    return B * world
 
 
 def model_cfg(backbone):
@@ -299,6 +305,23 @@ def run_ours(args):
         ms_eager, launches = timed(run_resident, args.steps, 2, gt_timer)
         model.use_cuda_graph = not args.no_graph
         roof = gt_timer.summary()
+    # informational (NOT the headline: SURVEY 8d counts (1+shots) backbone passes per query): the same loop on episodes
+    # whose 16 queries share one support sample, as MP-100 test episodes do, with support de-duplication on
+    dedup = None
+    if not args.no_graph and args.dedup_demo:
+        shared = [make_episode(batch=B, image_size=R, num_kpts=K, shots=args.shots, seed=4321 + 97 * rank + i,
+                               pin_memory=True, shared_support=B) for i in range(NB)]
+        def run_shared(start, n):
+            for res in iter_results(model, (shared[i % NB] for i in range(start, start + n))):
+                pass
+        ms_plain, _ = timed(run_shared, args.steps, W)
+        model.test_cfg = dict(model.test_cfg, dedup_supports=True)
+        ms_dedup, _ = timed(run_shared, args.steps, W)
+        model.test_cfg = dict(model.test_cfg, dedup_supports=False)
+        dedup = {"episodes": f"{B} queries share 1 support sample per batch",
+                 "e2e_value_reference_batching": q_per_step_local(B, world) * args.steps / (ms_plain / 1e3),
+                 "e2e_value_dedup_supports": q_per_step_local(B, world) * args.steps / (ms_dedup / 1e3),
+                 "unit": "query images/s"}
     from edgecape_b200.parallel import allreduce_counters, summarize_pck
     allreduce_counters(counters)           # the single collective of the path: fp64 PCK counters (NCCL all-reduce)
     torch.cuda.synchronize()
@@ -339,6 +362,8 @@ def run_ours(args):
         "pck_vs_random_gt": summarize_pck(counters[:6]),
         "algorithmic_gflop_per_query": flops_per_query(cfg, R, K, args.shots) / 1e9,
     }
+    if dedup is not None:
+        line["support_dedup_demo"] = dedup
     traffic = None
     try:
         traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))["traffic_bytes_per_launch"]

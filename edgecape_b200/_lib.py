@@ -39,6 +39,7 @@ SIGNATURES = {
                              c_int, c_int, c_fp, c_int, c_fp]),
     "ec_add_rows": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "ec_copy_rows": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_int, c_ll, c_int, c_int, c_int, c_fp]),
+    "ec_gather_blocks": (c_int, [c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_ll, c_fp]),
     "ec_axpby": (c_int, [c_fp, c_fp, c_fp, c_f, c_f, c_f, c_ll, c_fp]),
     "ec_attention": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_ll, c_ll, c_ll, c_ll, c_f, c_fp, c_fp, c_fp, c_int, c_fp]),

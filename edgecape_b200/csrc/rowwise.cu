@@ -142,6 +142,23 @@ __global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__
   X[(b * T + s) * C + c] += P[(long long)s * C + c];
 }
 
+// dst block r = src block idx[r]  (blocks of `n` contiguous floats; support de-duplication expands the features of the
+// unique support images back to one block per batch row)
+__global__ void gather_blocks_kernel(const float* __restrict__ src, long long src_stride, const int* __restrict__ idx,
+                                     float* __restrict__ dst, long long dst_stride, long long n, int vec) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.y;
+  const float* s = src + (long long)idx[r] * src_stride;
+  float* d = dst + (long long)r * dst_stride;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    if (i * 4 < n) reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
+  } else if (i < n) {
+    d[i] = s[i];
+  }
+}
+
 __global__ void copy_rows_kernel(const float* __restrict__ X, int ldx, int segx, long long sstridex,
                                  float* __restrict__ Y, int ldy, int segy, long long sstridey, int C,
                                  int bcast_rows, long long total) {
@@ -288,6 +305,19 @@ extern "C" int ec_copy_rows(const float* X, int ldx, int seg_x, long long seg_st
   launch_pdl(copy_rows_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, X, ldx, seg_x, seg_stride_x, Y, ldy, seg_y,
                                                                        seg_stride_y, C, bcast_rows, total);
   return check_launch("ec_copy_rows");
+}
+
+extern "C" int ec_gather_blocks(const float* src, long long src_stride, const int32_t* idx, float* dst,
+                                long long dst_stride, int n_out, long long block_elems, void* stream) {
+  EC_REQUIRE(src && idx && dst && block_elems > 0 && n_out >= 0, "ec_gather_blocks: bad arguments");
+  if (n_out == 0) return EC_OK;
+  const int vec = (block_elems % 4 == 0 && src_stride % 4 == 0 && dst_stride % 4 == 0 && (((uintptr_t)src) & 15) == 0 &&
+                   (((uintptr_t)dst) & 15) == 0) ? 1 : 0;
+  const long long work = vec ? block_elems / 4 : block_elems;
+  dim3 grid((unsigned)cdiv(work, 256), n_out);
+  launch_pdl(gather_blocks_kernel, grid, dim3(256), (size_t)0, (cudaStream_t)stream, src, src_stride, (const int*)idx, dst,
+             dst_stride, block_elems, vec);
+  return check_launch("ec_gather_blocks");
 }
 
 extern "C" int ec_l2_normalize(const float* X, float* Y, int M, int C, float eps, void* stream) {

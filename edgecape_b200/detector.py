@@ -66,8 +66,11 @@ class _GraphedForward:
     its neighbours; the buffers of a slot are recycled under events (A(i) waits for B(i-depth), the copies wait for
     the graph that last read the buffer)."""
 
-    def __init__(self, model, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev, img_hw, depth=2):
+    def __init__(self, model, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev, img_hw, depth=2, groups=None):
         self.model = model
+        # support de-duplication: `groups` = (first, inv); the ViT sees only the n_u unique support rows `first`, and
+        # the features are expanded back to one block per batch row with the index vector `inv`
+        self.n_u = None if groups is None else len(groups[0])
         self.dev = dev
         self.depth = depth
         self.B = B = img_q.shape[0]
@@ -83,7 +86,9 @@ class _GraphedForward:
         for _ in range(depth):
             s = _Slot()
             s.img_q = mk(img_q)
-            s.img_s = [mk(t) for t in img_s]
+            s.img_s = [mk(t) if self.n_u is None else mk(t[:self.n_u]) for t in img_s]
+            s.inv = None if self.n_u is None else torch.zeros(B, dtype=torch.int32, device=dev)
+            s.host_inv = None if self.n_u is None else torch.zeros(B, dtype=torch.int32).pin_memory()
             s.target_s = [mk(t) for t in target_s]
             s.tw_s = [mk(t) for t in target_weight_s]
             s.edges = torch.zeros(self.edge_capacity, 2, dtype=torch.int32, device=dev)
@@ -97,9 +102,9 @@ class _GraphedForward:
             self.slots.append(s)
         # warm-up on a side stream (packs weights, fills caches, sets kernel attributes), then capture per slot
         s0 = self.slots[0]
-        for d, t in zip([s0.img_q] + s0.img_s + s0.target_s + s0.tw_s,
-                        [img_q] + list(img_s) + list(target_s) + list(target_weight_s)):
+        for d, t in zip([s0.img_q] + s0.target_s + s0.tw_s, [img_q] + list(target_s) + list(target_weight_s)):
             d.copy_(t, non_blocking=True)
+        self._copy_supports(s0, img_s, groups)
         ne, no = e_np.shape[0], o_np.shape[0]
         s0.offsets.copy_(torch.from_numpy(o_np))
         if ne:
@@ -108,19 +113,32 @@ class _GraphedForward:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._head(s0, *model.extract_features(s0.img_s, s0.img_q))
+                self._head(s0, *model.extract_features(s0.img_s, s0.img_q, s0.inv))
         main.wait_stream(side)
         torch.cuda.synchronize(dev)
         for s in self.slots:
             s.graph_vit = torch.cuda.CUDAGraph()
             with torch.cuda.graph(s.graph_vit):
-                s.feat_q, s.feats_s = model.extract_features(s.img_s, s.img_q)
+                s.feat_q, s.feats_s = model.extract_features(s.img_s, s.img_q, s.inv)
             s.graph_head = torch.cuda.CUDAGraph()
             with torch.cuda.graph(s.graph_head, pool=s.graph_vit.pool()):
                 s.out, s.preds = self._head(s, s.feat_q, s.feats_s)
             L, _, K, _ = s.out[0].shape
             s.host_out = tuple(t.pin_memory() for t in (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K),
                                                         torch.empty(B, K, 3)))
+
+    def _copy_supports(self, s, img_s, groups):
+        if self.n_u is None:
+            for d, t in zip(s.img_s, img_s):
+                d.copy_(t, non_blocking=True)
+            return
+        first, inv = groups
+        assert len(first) == self.n_u
+        s.host_inv.copy_(torch.as_tensor(inv, dtype=torch.int32))
+        s.inv.copy_(s.host_inv, non_blocking=True)
+        for d, t in zip(s.img_s, img_s):
+            for u, row in enumerate(first):          # only the unique support rows cross PCIe
+                d[u].copy_(t[row], non_blocking=True)
 
     def _head(self, s, feat_q, feats_s):
         """mask + head + decode to image coordinates (TwoStageHead.decode arithmetic on the device)."""
@@ -131,7 +149,7 @@ class _GraphedForward:
                                  use_udp=model.keypoint_head_module.test_cfg.get("use_udp", False))
         return out, preds
 
-    def submit(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, img_metas, want_host=True):
+    def submit(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, img_metas, want_host=True, groups=None):
         dev = self.dev
         s = self.slots[self.count % self.depth]
         self.count += 1
@@ -157,8 +175,7 @@ class _GraphedForward:
             if s.used:
                 cp.wait_event(s.ev_vit)    # A(i - depth) has read the image buffers
             s.img_q.copy_(img_q, non_blocking=True)
-            for d, t in zip(s.img_s, img_s):
-                d.copy_(t, non_blocking=True)
+            self._copy_supports(s, img_s, groups)
             s.ev_img.record(cp)
             if s.used:
                 cp.wait_event(s.ev_head)   # B(i - depth) has read the head inputs
@@ -317,10 +334,14 @@ class EdgeCape(nn.Module):
             return self._predict_graphed(img_s, target_s, target_weight_s, img_q, img_metas)
         up = lambda t: t.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         edges, offsets = edges_to_csr(skeleton_lst, dev)
+        groups, inv = self._support_groups(img_metas), None
+        if groups is not None:
+            img_s = [torch.stack([t[i] for i in groups[0]]) for t in img_s]
+            inv = torch.as_tensor(groups[1], dtype=torch.int32).to(dev)
         return self._forward_device(up(img_q), [up(t) for t in img_s], [up(t) for t in target_s],
-                                    [up(t) for t in target_weight_s], (edges, offsets), return_intermediates)
+                                    [up(t) for t in target_weight_s], (edges, offsets), return_intermediates, inv=inv)
 
-    def _forward_device(self, img_q, img_s, target_s, target_weight_s, skeleton, return_intermediates=False):
+    def _forward_device(self, img_q, img_s, target_s, target_weight_s, skeleton, return_intermediates=False, inv=None):
         """Device-resident forward: every argument is a CUDA tensor, `skeleton` = (edges, offsets) CSR."""
         dev = img_q.device
         B, K = target_weight_s[0].shape[:2]
@@ -329,7 +350,7 @@ class EdgeCape(nn.Module):
         ops.mask_accumulate_(target_weight_s[0].reshape(B, K), mask_s, first=True)
         for tw in target_weight_s[1:]:
             ops.mask_accumulate_(tw.reshape(B, K), mask_s, first=False)
-        feat_q, feats_s = self.extract_features(img_s, img_q)
+        feat_q, feats_s = self.extract_features(img_s, img_q, inv)
         return self.keypoint_head_module.forward_tokens(feat_q, feats_s, target_s, mask_s, skeleton,
                                                         return_intermediates=return_intermediates)
 
@@ -348,18 +369,40 @@ class EdgeCape(nn.Module):
         dev = self.device
         skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
         e_np, o_np = edges_to_csr_host(skeleton_lst)
-        key = (tuple(img_q.shape), len(img_s), tuple(target_s[0].shape), ops.TENSOR_CORES)
+        groups = self._support_groups(img_metas)
+        key = (tuple(img_q.shape), len(img_s), tuple(target_s[0].shape), ops.TENSOR_CORES,
+               None if groups is None else len(groups[0]))
         g = self._graphs.get(key)
         if g is None or g.edge_capacity < e_np.shape[0]:
             if g is not None:
                 torch.cuda.synchronize(dev)          # batches in flight on the engine being replaced
             g = _GraphedForward(self, img_q, img_s, target_s, target_weight_s, e_np, o_np, dev,
-                                (img_q.shape[-1], img_q.shape[-2]), depth=int(self.test_cfg.get("pipeline_depth", 2)))
+                                (img_q.shape[-1], img_q.shape[-2]), depth=int(self.test_cfg.get("pipeline_depth", 2)),
+                                groups=groups)
             if len(self._graphs) >= 8:
                 torch.cuda.synchronize(dev)
                 self._graphs.clear()
             self._graphs[key] = g
-        return g.submit(img_q, img_s, target_s, target_weight_s, e_np, o_np, img_metas, want_host=want_host)
+        return g.submit(img_q, img_s, target_s, target_weight_s, e_np, o_np, img_metas, want_host=want_host,
+                        groups=groups)
+
+    def _support_groups(self, img_metas):
+        """Support de-duplication (test_cfg['dedup_supports'], default off = the reference's behaviour of running the
+        backbone on every row's copy): rows whose `sample_image_file` lists are equal carry the same support sample
+        (the queries of an MP-100 test episode, test_dataset.py:93-97).  Returns (first, inv): the rows holding the
+        first copy of each distinct support, and for every row the index of its support among them -- or None when
+        the option is off or nothing repeats."""
+        if not self.test_cfg.get("dedup_supports", False) or img_metas is None:
+            return None
+        seen, first, inv = {}, [], []
+        for i, m in enumerate(img_metas):
+            names = m.get("sample_image_file")
+            k = tuple(names) if names else ("__row__", i)
+            if k not in seen:
+                seen[k] = len(first)
+                first.append(i)
+            inv.append(seen[k])
+        return None if len(first) == len(inv) else (first, inv)
 
     def _predict_graphed(self, img_s, target_s, target_weight_s, img_q, img_metas):
         """Synchronous-on-the-current-stream form: the outputs are ordered after everything the caller enqueues next."""
@@ -367,13 +410,19 @@ class EdgeCape(nn.Module):
         return h.wait_on(torch.cuda.current_stream(self.device))
 
     @torch.no_grad()
-    def extract_features(self, img_s, img_q):
+    def extract_features(self, img_s, img_q, inv=None):
         """(:186-191) one batched ViT pass over [query; support shots]; returns token-major views
-        feat_q [B,S,C] and a list of feats_s [B,S,C] (cls row dropped by striding, no copy)."""
+        feat_q [B,S,C] and a list of feats_s [B,S,C] (cls row dropped by striding, no copy).
+        With `inv` (int32 [B], support de-duplication) every img_s[j] holds only the n_u distinct support images and
+        row b of feats_s[j] is the feature block of image inv[b]."""
         tok, _ = self.encoder_query.forward_tokens([img_q] + list(img_s))
         B = img_q.shape[0]
         feat_q = tok[:B, 1:, :]
-        feats_s = [tok[(i + 1) * B:(i + 2) * B, 1:, :] for i in range(len(img_s))]
+        if inv is None:
+            feats_s = [tok[(i + 1) * B:(i + 2) * B, 1:, :] for i in range(len(img_s))]
+        else:
+            n_u = img_s[0].shape[0]
+            feats_s = [ops.gather_blocks(tok[B + i * n_u:B + (i + 1) * n_u, 1:, :], inv) for i in range(len(img_s))]
         return feat_q, feats_s
 
     def forward_train(self, *args, **kwargs):

@@ -388,6 +388,22 @@ def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only
                            key_mask=key_mask, bias=bias, out=out, split=split)
 
 
+def gather_blocks(src, idx, out=None):
+    """out[r] = src[idx[r]] over the leading dimension; src [n, ...] may be strided in dim 0 (inner dims contiguous),
+    idx int32 [B] on the device."""
+    _chk(src, "src"); _chk(idx, "idx", torch.int32)
+    inner = 1
+    for d in src.shape[1:]:
+        inner *= d
+    assert src[0].is_contiguous() and idx.is_contiguous()
+    B = idx.numel()
+    if out is None:
+        out = empty(B, *src.shape[1:], device=src.device)
+    assert out.is_contiguous()
+    _lib.call("ec_gather_blocks", _p(src), src.stride(0), _p(idx), _p(out), inner, B, inner, _stream())
+    return out
+
+
 def hop_bias(attn_adj, w0, b0, w1, b1, out=None):
     """attn_adj [n_hops,B,K,K] -> bias [B,H,K,K] through Linear(n_hops,hidden)-ReLU-Linear(hidden,H)."""
     _chk(attn_adj, "attn_adj")

@@ -113,11 +113,13 @@ def random_skeleton(rng, K, n_valid=None, kind="tree+extra"):
 
 
 def make_episode(batch, image_size=256, num_kpts=100, shots=1, seed=1234, masked_tail=0.0,
-                 skeleton="tree+extra", heatmap_size=64, pin_memory=False):
+                 skeleton="tree+extra", heatmap_size=64, pin_memory=False, shared_support=1):
     """One batch of the reference's forward() kwargs (CPU tensors).
 
     masked_tail: fraction of trailing keypoints marked invisible (MP-100 pads categories to
-    100 keypoints, datasets/datasets/mp100/test_dataset.py:187-197)."""
+    100 keypoints, datasets/datasets/mp100/test_dataset.py:187-197).
+    shared_support: runs of this many consecutive rows share their support sample -- image(s), heat-maps, skeleton and
+    `sample_image_file` -- as the queries of one MP-100 test episode do (test_dataset.py:93-97: 15 queries per support)."""
     rng = np.random.default_rng([int(seed), 77])
     B, K, R = batch, num_kpts, image_size
     n_valid = K - int(round(masked_tail * K))
@@ -133,15 +135,23 @@ def make_episode(batch, image_size=256, num_kpts=100, shots=1, seed=1234, masked
         target_s.append(t)
         weight_s.append(w)
         kpts_s.append(xy)
+    g_of = [b - b % max(1, int(shared_support)) for b in range(B)]     # first row of each row's support group
+    if shared_support > 1:
+        for j in range(shots):
+            for arr_ in (img_s[j], target_s[j], weight_s[j], kpts_s[j]):
+                arr_[:] = arr_[g_of]
     img_metas = []
+    group_edges = {}
     for b in range(B):
-        edges = random_skeleton(rng, K, n_valid, skeleton)
+        if g_of[b] not in group_edges:
+            group_edges[g_of[b]] = random_skeleton(rng, K, n_valid, skeleton)
+        edges = group_edges[g_of[b]]
         img_metas.append(dict(
             sample_skeleton=[edges], query_skeleton=edges,
             query_center=np.array([R / 2.0, R / 2.0], dtype=np.float32),
             query_scale=np.array([R / 200.0, R / 200.0], dtype=np.float32),
             query_image_file=f"synthetic_q_{seed}_{b}.png",
-            sample_image_file=[f"synthetic_s_{seed}_{b}.png"],
+            sample_image_file=[f"synthetic_s_{seed}_{g_of[b]}_{j}.png" for j in range(shots)],
             query_bbox_score=1.0, bbox_id=b,
             sample_joints_3d=[kpts_s[j][b] for j in range(shots)],
         ))

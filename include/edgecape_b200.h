@@ -123,6 +123,11 @@ int ec_add_rows(float* X, const float* P, int batch, int T, int S, int C, void* 
  * helper (torch.cat at encoder_decoder.py:198-203,620-622; the token split at :307-308). */
 int ec_copy_rows(const float* X, int ldx, int seg_x, long long seg_stride_x, float* Y, int ldy,
                  int seg_y, long long seg_stride_y, int M, int C, int bcast_rows, void* stream);
+/* dst[r, 0:block_elems] = src[idx[r], 0:block_elems] for r < n_out (strides in floats between blocks).  Expands the ViT
+ * features of de-duplicated support images to one block per batch row (test_dataset.py:93-97: the queries of an episode
+ * share their support sample; the reference runs the backbone on every copy). */
+int ec_gather_blocks(const float* src, long long src_stride, const int32_t* idx, float* dst, long long dst_stride,
+                     int n_out, long long block_elems, void* stream);
 
 /* out = (a*x + b*y) / div elementwise: the mean over shots (head.py:186, skeleton.py:113). */
 int ec_axpby(const float* x, const float* y, float* out, float a, float b, float div, long long n,

@@ -457,6 +457,13 @@ def ec_pck_accumulate(pred, gt, valid, norm, thr, Tn, counters, B, K, stream):
         c[Tn] += 1
 
 
+def ec_gather_blocks(src, src_stride, idx, dst, dst_stride, n_out, block_elems, stream):
+    ix = arr(idx, (n_out,), dtype=np.int32)
+    d = arr(dst, (n_out, block_elems), (dst_stride, 1))
+    for r in range(n_out):
+        d[r] = arr(src + 4 * int(ix[r]) * src_stride, (block_elems,))
+
+
 def ec_warp_affine_normalize_u8(src, Hs, Ws, row_stride, M, out, H, W, mean, stdv, stream):
     import ctypes
     from oracle import input_oracle as io

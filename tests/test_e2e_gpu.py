@@ -158,3 +158,22 @@ def test_pipelined_test_loop_equals_one_call_per_batch():
     assert torch.equal(h0.out[0], out0)
     assert np.array_equal(h0.out[0][-1].cpu().numpy(), want[0]["points"][-1])
     assert np.array_equal(h1.out[0][-1].cpu().numpy(), want[1]["points"][-1])
+
+
+def test_support_deduplication_on_gpu_matches_full_backbone_batch():
+    """CUDA-graph engine with test_cfg['dedup_supports']: 16 queries sharing 2 supports -> the ViT runs 16 + 2 images;
+    the results equal the run that sends all 32 through (same per-row arithmetic)."""
+    from edgecape_b200.apis import single_gpu_test
+    from edgecape_b200.config import default_model_cfg
+    cfg = default_model_cfg("dinov2_vits14")
+    model = _build(cfg, 3)
+    batches = [make_episode(batch=16, image_size=224, num_kpts=17, shots=1, seed=70 + i, pin_memory=True,
+                            shared_support=8 if i != 1 else 5) for i in range(3)]
+    want = single_gpu_test(model, batches)
+    model.test_cfg = dict(model.test_cfg, dedup_supports=True)
+    got = single_gpu_test(model, batches)
+    assert sorted(k[-1] for k in model._graphs) == [None, 2, 4] or len(model._graphs) >= 2
+    for g, w in zip(got, want):
+        for k in ("preds", "points", "skeleton"):
+            a, b = np.asarray(g[k]), np.asarray(w[k])
+            assert np.abs(a - b).max() <= 1e-5 * (np.abs(b).max() + 1e-12), k

@@ -54,3 +54,29 @@ def test_host_orchestration_against_golden(name, tensor_cores, golden_dir, monke
         assert err < 2e-4, f"{name}:{k} rel err {err:.3e}"
     assert res["image_paths"] == [m["query_image_file"] for m in data["img_metas"]]
     assert res["bbox_ids"] == [m["bbox_id"] for m in data["img_metas"]]
+
+
+def test_support_deduplication_changes_nothing_but_the_backbone_batch(monkeypatch):
+    """test_cfg['dedup_supports']: rows sharing `sample_image_file` run the backbone once per distinct support; the
+    result dict must equal the reference behaviour (every row's own copy through the ViT)."""
+    from edgecape_b200 import ops
+    from edgecape_b200.synthetic import make_episode
+    from oracle.gen_golden import TINY_VIT, model_cfg_for
+    cpu_emulator.install(monkeypatch)
+    monkeypatch.setattr(ops, "TENSOR_CORES", False)
+    cfg = model_cfg_for(TINY_VIT)
+    data = make_episode(batch=5, image_size=64, num_kpts=7, shots=2, seed=11, shared_support=3)
+    model = E.build_model(dict(model=cfg))
+    model.load_state_dict(make_state_dict(state_dict_shapes(cfg), 5), strict=True)
+    model.eval()
+    want = model(return_loss=False, **data)
+    calls = []
+    orig = model.encoder_query.forward_tokens
+    monkeypatch.setattr(model.encoder_query, "forward_tokens",
+                        lambda images: (calls.append([int(t.shape[0]) for t in images]), orig(images))[1])
+    model.test_cfg = dict(model.test_cfg, dedup_supports=True)
+    assert model._support_groups(data["img_metas"]) == ([0, 3], [0, 0, 0, 1, 1])
+    got = model(return_loss=False, **data)
+    assert calls == [[5, 2, 2]]                      # 5 queries + 2 distinct supports per shot instead of 5 + 5 + 5
+    for k in ("preds", "points", "skeleton", "boxes"):
+        assert np.allclose(np.asarray(got[k]), np.asarray(want[k]), rtol=0, atol=1e-6), k
