@@ -172,7 +172,7 @@ def test_support_deduplication_on_gpu_matches_full_backbone_batch():
     want = single_gpu_test(model, batches)
     model.test_cfg = dict(model.test_cfg, dedup_supports=True)
     got = single_gpu_test(model, batches)
-    assert sorted(k[-1] for k in model._graphs) == [None, 2, 4] or len(model._graphs) >= 2
+    assert {k[-1] for k in model._graphs} == {None, 2, 4}      # one engine per backbone batch size
     for g, w in zip(got, want):
         for k in ("preds", "points", "skeleton"):
             a, b = np.asarray(g[k]), np.asarray(w[k])
