@@ -31,6 +31,7 @@ SIGNATURES = {
                               c_int, c_int, c_fp, c_int, c_f, c_fp]),
     "ec_tc_set_tile_n": (c_int, [c_int]),
     "ec_tc_set_cta_limit": (c_int, [c_int]),
+    "ec_tc_set_dynamic": (c_int, [c_int]),
     "ec_set_pdl": (c_int, [c_int]),
     "ec_tc_set_debug": (c_int, [c_int]),
     "ec_attention_tc_set_trace": (c_int, [c_fp, c_int]),

@@ -15,6 +15,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ec {
@@ -126,6 +128,7 @@ struct TcParams {
   __half* split_out;   // optional [M, 2*split_kp] = [hi | lo] of the result (next GEMM's A operand)
   int split_kp;
   float split_scale;
+  int* sched;          // dynamic tile scheduler: {next tile, finished workers} of this launch (zero on entry), or NULL
 };
 
 // ---- cluster / 2-CTA helpers (cta_group::2: one UMMA spans the tensor cores and shared memory of an SM pair)
@@ -143,6 +146,21 @@ __device__ __forceinline__ void cluster_sync() {
   __syncwarp();   // .aligned: the whole warp must arrive together (role lanes re-converge here)
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquires the peer CTA's writes
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void st_shared_cluster(uint32_t cluster_addr, int v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -192,6 +210,15 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
+  // tile ring: the TMA thread of the (leader) CTA draws tile indices -- from a global counter when p.sched is set, so a
+  // CTA that starts late (its SM was busy with another stream's kernel) simply takes fewer tiles -- and hands them to
+  // the MMA thread, the epilogue warps and the peer CTA through RING slots: ring_full (1 producer arrival) /
+  // ring_empty on the leader (every consumer of both CTAs arrives once it has read the slot).  -1 ends the kernel.
+  constexpr int RING = 4;
+  auto ring_full = [&](int r) { return bar_base + 96u + 8u * r; };
+  auto ring_empty = [&](int r) { return bar_base + 128u + 8u * r; };
+  const uint32_t ring_tile = bar_base + 160u;                       // RING x int32
+  volatile int* ring_tile_ptr = reinterpret_cast<volatile int*>(smem_raw + (ring_tile - smem_u32(smem_raw)));
   const uint32_t epi_base = bar_base + 256u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -205,6 +232,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 16 : 8); }
+    for (int r = 0; r < RING; ++r) { mbar_init(ring_full(r), 1); mbar_init(ring_empty(r), TWO ? 18 : 9); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -223,12 +251,43 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_launch_dependents();     // TMEM is ours: the next kernel in the stream may start its prologue
   pdl_wait();                  // ... and ours ends here: operands written by the previous kernel are visible
 
+  // consumer side of the tile ring: j-th tile of this CTA (pair); one arrival per consumer on the leader's ring_empty
+  auto ring_get = [&](int j) -> int {
+    const int r = j % RING;
+    const uint32_t ph = (uint32_t)(j / RING) & 1u;
+    if (TWO && rank == 1) mbar_wait_cluster(ring_full(r), ph); else mbar_wait(ring_full(r), ph);
+    return ring_tile_ptr[r];
+  };
+  auto ring_release = [&](int j) {
+    const int r = j % RING;
+    if (TWO && rank == 1) mbar_arrive_remote(mapa(ring_empty(r), 0)); else mbar_arrive(ring_empty(r));
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int j = 0;; ++j) {
+        int tile;
+        if (rank == 0) {
+          // tile scheduler (leader): draw the next tile, publish it to this CTA and to the peer
+          const int r = j % RING;
+          if (j >= RING) {
+            const uint32_t ph = (uint32_t)(j / RING - 1) & 1u;
+            if (TWO) mbar_wait_cluster(ring_empty(r), ph); else mbar_wait(ring_empty(r), ph);
+          }
+          tile = p.sched ? atomicAdd(p.sched, 1) : worker + j * num_workers;
+          if (tile >= num_tiles) tile = -1;
+          ring_tile_ptr[r] = tile;
+          if (TWO) st_shared_cluster(mapa(ring_tile + 4u * r, 1), tile);
+          mbar_arrive(ring_full(r));
+          if (TWO) mbar_arrive_remote(mapa(ring_full(r), 1));
+        } else {
+          tile = ring_get(j);
+          ring_release(j);
+        }
+        if (tile < 0) break;
         const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
         const int m0 = tm * TM + rank * BM, n0 = tn * BN + rank * B_ROWS;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -263,8 +322,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      int t = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
+      for (int t = 0;; ++t) {
+        const int tile = ring_get(t);
+        ring_release(t);
+        if (tile < 0) break;
         const int acc = t & 1;
         mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -316,7 +377,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int NSUB = BN / 16;
     int t = 0;
     const uint32_t tempty_leader0 = TWO ? mapa(tempty_bar(0), 0) : 0u, tempty_leader1 = TWO ? mapa(tempty_bar(1), 0) : 0u;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
+    for (;; ++t) {
+      const int tile = ring_get(t);
+      __syncwarp();                                  // every lane has read the slot
+      if (lane == 0) ring_release(t);
+      if (tile < 0) break;
       const int acc = t & 1;
       const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
       const int m0 = tm * TM + rank * BM, n0 = tn * BN;
@@ -445,6 +510,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   if (TWO) cluster_sync(); else __syncthreads();   // the peer's shared memory / barriers stay alive until both are done
+  if (p.sched && rank == 0 && threadIdx.x == 0) {
+    // the last worker to finish re-arms the counters for the next use of this slot (every worker has drawn its -1)
+    if (atomicAdd(p.sched + 1, 1) == num_workers - 1) {
+      atomicExch(p.sched, 0);
+      atomicExch(p.sched + 1, 0);
+    }
+  }
   if (warp == 1) {
     if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -544,6 +616,11 @@ extern "C" int ec_tc_set_debug(int flags) {   // bring-up / profiling experiment
   ec_tc_debug = flags;
   return EC_OK;
 }
+static int ec_tc_dynamic = -1;   // dynamic tile scheduling (default on; EDGECAPE_GEMM_DYNAMIC=0 / ec_tc_set_dynamic(0) = static)
+extern "C" int ec_tc_set_dynamic(int on) {
+  ec_tc_dynamic = on ? 1 : 0;
+  return EC_OK;
+}
 static int ec_tc_cta_limit = 0;  // 0 = every SM; else the persistent grids use at most this many CTAs
 extern "C" int ec_tc_set_cta_limit(int ctas) {
   EC_REQUIRE(ctas >= 0, "ec_tc_set_cta_limit: negative");
@@ -616,6 +693,22 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
   p.res_mode = res_mode; p.res_rows = res_rows; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
   p.dbg = ec_tc_debug;
+  // one {next tile, finished workers} pair per launch, self re-arming; a launch keeps its slot inside a captured graph
+  constexpr int SCHED_SLOTS = 8192;
+  static int* sched_base = nullptr;
+  static unsigned sched_seq = 0;
+  if (ec_tc_dynamic < 0) {
+    const char* e = getenv("EDGECAPE_GEMM_DYNAMIC");
+    ec_tc_dynamic = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.sched = nullptr;
+  if (ec_tc_dynamic) {
+    if (!sched_base) {
+      EC_CUDA(cudaMalloc(&sched_base, SCHED_SLOTS * 2 * sizeof(int)));
+      EC_CUDA(cudaMemset(sched_base, 0, SCHED_SLOTS * 2 * sizeof(int)));
+    }
+    p.sched = sched_base + 2 * (sched_seq++ % SCHED_SLOTS);
+  }
   // with few N tiles the A operand (activations, up to 128 MB > L2) would be swept once per N tile: walk N first
   p.n_fastest = (cdiv(N, BN) <= 4 && (long long)M * Kp * 4 > (64LL << 20)) ? 1 : 0;   // A (hi+lo) beyond ~half of L2
   cudaStream_t st = (cudaStream_t)stream;

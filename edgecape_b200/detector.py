@@ -7,6 +7,8 @@ hub code); it is bound to both `encoder_sample` and `encoder_query` exactly like
 (one module, two state-dict prefixes, :36).  Query and support images go through the ViT as ONE
 batch, and every op runs in the CUDA library.  Training (`forward_train`, :82-129) is out of scope.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -75,9 +77,14 @@ class _GraphedForward:
         self.depth = depth
         self.B = B = img_q.shape[0]
         self.edge_capacity = max(1024, 2 * int(e_np.shape[0]))
+        # the head's ~300 small kernels get the higher stream priority: at every kernel boundary of the backbone they
+        # are placed first, and the backbone's persistent GEMM CTAs -- which draw their tiles dynamically -- absorb
+        # the SMs they occupy instead of stalling (priorities are recorded per kernel node at capture)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.vit_stream = torch.cuda.Stream(device=dev)
-        self.head_stream = torch.cuda.Stream(device=dev)
+        self.head_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._capture_lo = torch.cuda.Stream(device=dev)
+        self._capture_hi = torch.cuda.Stream(device=dev, priority=-1)
         self.img_hw = img_hw
         self.count = 0
         mk = lambda t: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
@@ -116,16 +123,26 @@ class _GraphedForward:
                 self._head(s0, *model.extract_features(s0.img_s, s0.img_q, s0.inv))
         main.wait_stream(side)
         torch.cuda.synchronize(dev)
+        # programmatic dependent launch is recorded per kernel node at capture.  Inside graphs it buys nothing for a
+        # graph running alone (scripts/overlap_probe.py: backbone 6.05 / head 2.75 ms either way) and it HURTS the
+        # pipeline: pre-launched dependents sit on SMs (a GEMM CTA holds 213 KB of shared memory) while they wait, which
+        # keeps the other stream's kernels out -- both graphs concurrently: 7.98 ms with PDL in the head graph, 7.25 ms
+        # without.  test_cfg['pdl'] = 'none' (default) | 'head' | 'all'; EDGECAPE_PDL=0 forces none.
+        pdl = str(model.test_cfg.get("pdl", "none"))
+        env_off = os.environ.get("EDGECAPE_PDL", "1") == "0"
         for s in self.slots:
+            _lib.call("ec_set_pdl", int(pdl == "all" and not env_off))
             s.graph_vit = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(s.graph_vit):
+            with torch.cuda.graph(s.graph_vit, stream=self._capture_lo):
                 s.feat_q, s.feats_s = model.extract_features(s.img_s, s.img_q, s.inv)
+            _lib.call("ec_set_pdl", int(pdl in ("all", "head") and not env_off))
             s.graph_head = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(s.graph_head, pool=s.graph_vit.pool()):
+            with torch.cuda.graph(s.graph_head, pool=s.graph_vit.pool(), stream=self._capture_hi):
                 s.out, s.preds = self._head(s, s.feat_q, s.feats_s)
             L, _, K, _ = s.out[0].shape
             s.host_out = tuple(t.pin_memory() for t in (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K),
                                                         torch.empty(B, K, 3)))
+        _lib.call("ec_set_pdl", int(not env_off))
 
     def _copy_supports(self, s, img_s, groups):
         if self.n_u is None:

@@ -143,8 +143,8 @@ class TwoStageHead(PackedMixin, nn.Module):
         main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
         sk = {}
         if main is not None and self.concurrent_skeleton:
-            if self._side is None or self._side.device != dev:
-                self._side = torch.cuda.Stream(device=dev)
+            if self._side is None or self._side.device != dev or self._side.priority != main.priority:
+                self._side = torch.cuda.Stream(device=dev, priority=main.priority)   # same priority as its parent
             side = self._side
             side.wait_stream(main)
             with torch.cuda.stream(side):

@@ -88,6 +88,10 @@ int ec_tc_set_tile_n(int bn);
 /* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
  * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
 int ec_tc_set_cta_limit(int ctas);
+/* tile scheduling of ec_gemm_f16x3's persistent CTAs: 1 (default) = tiles drawn from a per-launch global counter, so a
+ * CTA whose SM is busy with another stream's kernel takes fewer tiles instead of stalling the launch; 0 = static
+ * round-robin.  EDGECAPE_GEMM_DYNAMIC=0 selects static at start-up. */
+int ec_tc_set_dynamic(int on);
 /* programmatic dependent launch of the library's kernels (default on; EDGECAPE_PDL=0 or ec_set_pdl(0) = plain
  * stream-ordered launches, for A/B measurements) */
 int ec_set_pdl(int on);
