@@ -17,6 +17,8 @@
 
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ec {
@@ -693,24 +695,34 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
   p.res_mode = res_mode; p.res_rows = res_rows; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
   p.dbg = ec_tc_debug;
-  // one {next tile, finished workers} pair per launch, self re-arming; a launch keeps its slot inside a captured graph
-  constexpr int SCHED_SLOTS = 8192;
+  // one {next tile, finished workers} pair per launch, re-armed by the launch's last worker.  Eager launches cycle
+  // through a ring of slots (a slot is reused 4096 launches later); launches recorded into a CUDA graph keep their slot
+  // for the life of the process (the node replays with it, possibly concurrently with eager work on another stream), so
+  // they come from a separate pool that never wraps -- when it runs out, further captured launches use static tiles.
+  constexpr unsigned EAGER_SLOTS = 4096, GRAPH_SLOTS = 61440;
   static int* sched_base = nullptr;
-  static unsigned sched_seq = 0;
+  static std::atomic<unsigned> eager_seq{0}, graph_seq{0};
   if (ec_tc_dynamic < 0) {
     const char* e = getenv("EDGECAPE_GEMM_DYNAMIC");
     ec_tc_dynamic = (e && e[0] == '0') ? 0 : 1;
   }
   p.sched = nullptr;
   if (ec_tc_dynamic) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    EC_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
     if (!sched_base) {
-      EC_CUDA(cudaMalloc(&sched_base, SCHED_SLOTS * 2 * sizeof(int)));
-      EC_CUDA(cudaMemset(sched_base, 0, SCHED_SLOTS * 2 * sizeof(int)));
+      EC_REQUIRE(cap == cudaStreamCaptureStatusNone,
+                 "ec_gemm_f16x3: the first call must not be inside a stream capture (it allocates the tile counters)");
+      EC_CUDA(cudaMalloc(&sched_base, (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int)));
+      EC_CUDA(cudaMemset(sched_base, 0, (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int)));
     }
-    p.sched = sched_base + 2 * (sched_seq++ % SCHED_SLOTS);
+    if (cap == cudaStreamCaptureStatusNone) {
+      p.sched = sched_base + 2 * (eager_seq.fetch_add(1) % EAGER_SLOTS);
+    } else {
+      const unsigned g = graph_seq.fetch_add(1);
+      if (g < GRAPH_SLOTS) p.sched = sched_base + 2 * (EAGER_SLOTS + g);
+    }
   }
-  // with few N tiles the A operand (activations, up to 128 MB > L2) would be swept once per N tile: walk N first
-  p.n_fastest = (cdiv(N, BN) <= 4 && (long long)M * Kp * 4 > (64LL << 20)) ? 1 : 0;   // A (hi+lo) beyond ~half of L2
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 512) {
     const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
