@@ -36,6 +36,18 @@ METRIC = "query images/sec (1-shot, 256x256, ViT-B/14, 100 kpts)"
 WORKLOAD = "configs[1]: 1-shot synthetic 256x256, DINOv2-B/14, 100-kpt random skeleton, batch 16 per GPU"
 
 
+def describe(args):
+    """(metric, workload) strings: BASELINE.json's wording for the default arguments (configs[1]), an explicit
+    description otherwise so that a non-default run can never be mistaken for the headline."""
+    default = (args.backbone == "dinov2_vitb14" and args.image_size == 256 and args.kpts == 100 and args.shots == 1 and
+               args.batch == 16)
+    if default:
+        return METRIC, WORKLOAD
+    return (f"query images/sec ({args.shots}-shot, {args.image_size}x{args.image_size}, {args.backbone}, {args.kpts} kpts)",
+            f"NON-DEFAULT: {args.shots}-shot synthetic {args.image_size}x{args.image_size}, {args.backbone}, "
+            f"{args.kpts}-kpt random skeleton, batch {args.batch} per GPU")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -109,10 +121,10 @@ def run_reference(args):
     steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 10))
     cb, ms = cpu_reference_rate(args, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "query images/s",
+        "impl": "reference", "metric": describe(args)[0], "value": cb["value"], "unit": "query images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_queries_per_step": max(1, args.cpu_sample),
+        "config": {"workload": describe(args)[1], "sample_queries_per_step": max(1, args.cpu_sample),
                    "note": "reference's PyTorch-CPU forward_test restated in oracle/ (the reference itself cannot "
                            "travel to the GPU box: mmcv/mmpose/hub DINOv2 are absent)"},
         "cpu_baseline": cb,
@@ -341,10 +353,10 @@ def run_ours(args):
     L = cfg["keypoint_head"]["num_decoder_layer"]
     d2h = (B * K * 2 + (1 + L) * B * K * 2 + 2 * K * K) * 4
     line = {
-        "metric": METRIC, "value": value, "unit": "query images/s", "n_gpus": world, "steps": args.steps,
+        "metric": describe(args)[0], "value": value, "unit": "query images/s", "n_gpus": world, "steps": args.steps,
         "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": q_per_step, "image_size": R,
+        "config": {"workload": describe(args)[1], "per_gpu_batch": B, "global_batch": q_per_step, "image_size": R,
                    "keypoints": K, "shots": args.shots, "backbone": args.backbone,
                    "l2": "no explicit flush: weights (0.41 GB) + per-step activations exceed the 126 MB L2 and "
                          f"inputs rotate over {NB} distinct batches"},
