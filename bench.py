@@ -12,8 +12,11 @@ Queries shard over GPUs with no data-path collective (weak scaling: per-GPU batc
 all-reduce of the fp64 PCK counters closes the run.
 
 One JSON line is printed by rank 0; see the task contract for the keys.  `value` is measured with
-inputs resident in HBM; `e2e` goes through the reference-facing call `model(return_loss=False,
-**data)` with pinned host tensors (H2D + D2H inside the timed region).  `roofline` covers the
+inputs resident in HBM (`model.predict_async`, the library's two-deep pipeline over consecutive
+steps: every one of the K steps starts and completes inside the timed region); `e2e` goes through
+the reference-facing test loop `edgecape_b200.apis.iter_results` (= `single_gpu_test`, one
+`model.forward_test_async(**data)` per batch, result dicts consumed in order) with pinned host
+tensors, every H2D and D2H copy inside the timed region.  `roofline` covers the
 dominant kernel (the ViT/head GEMM), timed live with CUDA events on the launching stream.
 `cpu_baseline` / `--impl reference` time the CPU restatement of the reference (oracle/, pinned
 against the unmodified reference by tests/golden) on the host cores.
