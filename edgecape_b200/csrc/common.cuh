@@ -12,13 +12,14 @@ namespace ec {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
-// Programmatic dependent launch.  The path is a chain of ~360 dependent launches per step, most of them far
-// from filling the GPU, so launch latency and per-kernel prologues (barrier init, TMEM allocation, tensor-map
-// fetch) are a sizeable share of the step.  Kernels launched through launch_pdl() may start while their
-// predecessor in the stream is still running; each of them calls pdl_wait() -- which returns once the
-// predecessor grid has completed and its writes are visible -- BEFORE its first global-memory access (read or
-// write), and pdl_launch_dependents() as early as it safely can (after TMEM allocation in the kernels that
-// allocate TMEM: a dependent CTA that grabbed TMEM first would wait for us while we wait for TMEM).
+// Programmatic dependent launch.  Kernels launched through launch_pdl() may start while their predecessor in the
+// stream is still running; each of them calls pdl_wait() -- which returns once the predecessor grid has completed
+// and its writes are visible -- BEFORE its first global-memory access (read or write), and
+// pdl_launch_dependents() as early as it safely can (after TMEM allocation in the kernels that allocate TMEM: a
+// dependent CTA that grabbed TMEM first would wait for us while we wait for TMEM).
+// Measured (profiles/r01_n_attention_and_issue.md): it shortens eager launch chains slightly, does nothing for a
+// CUDA graph running alone, and costs ~0.7 ms per step when two graphs share the GPU (pre-launched dependents sit
+// on SMs while they wait), so the detector records its graphs with it switched off (detector.py, test_cfg['pdl']).
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

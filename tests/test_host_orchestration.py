@@ -80,3 +80,26 @@ def test_support_deduplication_changes_nothing_but_the_backbone_batch(monkeypatc
     assert calls == [[5, 2, 2]]                      # 5 queries + 2 distinct supports per shot instead of 5 + 5 + 5
     for k in ("preds", "points", "skeleton", "boxes"):
         assert np.allclose(np.asarray(got[k]), np.asarray(want[k]), rtol=0, atol=1e-6), k
+
+
+def test_test_loop_api_returns_results_in_order(monkeypatch):
+    """edgecape_b200.apis.single_gpu_test (the reference's apis/test.py loop): one result dict per batch, in order;
+    without CUDA graphs it degrades to one synchronous forward_test per batch."""
+    from edgecape_b200 import ops
+    from edgecape_b200.apis import iter_results, single_gpu_test
+    from edgecape_b200.synthetic import make_episode
+    from oracle.gen_golden import TINY_VIT, model_cfg_for
+    cpu_emulator.install(monkeypatch)
+    monkeypatch.setattr(ops, "TENSOR_CORES", False)
+    cfg = model_cfg_for(TINY_VIT)
+    model = E.build_model(dict(model=cfg))
+    model.load_state_dict(make_state_dict(state_dict_shapes(cfg), 5), strict=True)
+    model.eval()
+    model.use_cuda_graph = False
+    batches = [make_episode(batch=2, image_size=64, num_kpts=5, shots=1, seed=20 + i) for i in range(3)]
+    want = [model(return_loss=False, **d) for d in batches]
+    got = single_gpu_test(model, batches)
+    assert [g["image_paths"] for g in got] == [w["image_paths"] for w in want]
+    for g, w in zip(got, want):
+        assert np.array_equal(g["preds"], w["preds"])
+    assert len(list(iter_results(model, iter(batches[:1]), depth=4))) == 1
