@@ -126,6 +126,37 @@ if __name__ == "__main__":
     if st == "tmabench":          # the ViT-B block attention alone (ncu target)
         bench_tma(32, 12, 325, iters=5)
         sys.exit(0)
+    if st == "trace32":           # encoder self-attention of the head: 424 tokens, 8 heads x 32, key mask
+        from edgecape_b200 import _lib
+        D = torch.device("cuda")
+        B, H, N, Dh = 16, 8, 424, 32
+        qkv2 = ops.split_f16(torch.randn(B * N, 3 * H * Dh, device=D))
+        mask = torch.zeros(B, N, dtype=torch.uint8, device=D)
+        mask[:, 400:] = 1
+        for masked in (True, False):
+            km = mask if masked else None
+            for _ in range(3):
+                ops.attention_packed_split(qkv2, B, N, H, key_mask=km)
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(20):
+                ops.attention_packed_split(qkv2, B, N, H, key_mask=km)
+            e_.record()
+            torch.cuda.synchronize()
+            print(f"encoder-shaped attention masked={masked}: {s_.elapsed_time(e_) / 20 * 1e3:.1f} us")
+            buf = torch.zeros(512, 10, dtype=torch.int64, device=D)
+            _lib.call("ec_attention_tc_set_trace", buf.data_ptr(), 512)
+            ops.attention_packed_split(qkv2, B, N, H, key_mask=km)
+            torch.cuda.synchronize()
+            _lib.call("ec_attention_tc_set_trace", None, 0)
+            t = buf.cpu().double()
+            d = t[:, 1:] - t[:, :-1]
+            names = ["setup+tmem_alloc", "Q/K TMA + S mma", "row max", "P chunk 0", "P chunks (rest)", "drain PV",
+                     "epilogue", "final sync", "dealloc"]
+            print(f"  CTA total mean {(t[:, 9] - t[:, 0]).mean():.0f} clk")
+            for i, nm in enumerate(names):
+                print(f"  {nm:28s} mean {d[:, i].mean():8.0f}  min {d[:, i].min():8.0f}  max {d[:, i].max():8.0f}")
+        sys.exit(0)
     if st == "trace":
         trace_tma(32, 12, 325)
         trace_tma(8, 16, 730)
