@@ -755,7 +755,10 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                  tmem_slot = misc + 40, bar_pr = misc + 48;            // bar_pr: MAX_CHUNKS barriers, one per chunk
   float* xmax = reinterpret_cast<float*>(gbase + data_bytes + 128);   // [NPART][BM]
   float* xsum = xmax + NPART * BM;
-  uint8_t* msk = reinterpret_cast<uint8_t*>(xsum + NPART * BM);       // [<= 448] key-padding mask of this batch row
+  // key-padding mask of this batch row as a bit per key (1 = ignore; keys >= Lk are set too): one shared-memory word
+  // per 32 keys, tested with shifts.  (A byte per key read inside the softmax loops cost a dependent generic load
+  // and a branch per element: 19K clk for the row max of 424 keys instead of 1.3K.)
+  uint32_t* mskw = reinterpret_cast<uint32_t*>(xsum + NPART * BM);    // [16] words = 512 keys
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, part = (warp >> 2) & 3;
@@ -893,7 +896,10 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float* bias_row = (p.bias && q0 + row < p.Lq)
                                 ? p.bias + (((long long)b * p.H + h) * p.Lq + (q0 + row)) * p.Lk : nullptr;
     if (gen) {
-      for (int j = tid; j < p.LB; j += THREADS) msk[j] = (j < p.Lk && p.key_mask) ? p.key_mask[(long long)b * p.Lk + j] : 0;
+      const int key = tid;                              // 16 warps x 32 lanes cover 512 keys >= LB
+      const bool ignore = key >= p.Lk || (p.key_mask && p.key_mask[(long long)b * p.Lk + key] != 0);
+      const uint32_t word = __ballot_sync(0xffffffffu, ignore);
+      if (lane == 0) mskw[warp] = word;
       softmax_sync();
     }
     for (int blk = 0; blk < p.NB; ++blk) {
@@ -910,11 +916,20 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         float s[32];
         tmem_ld32(t_row + j * 32, s);
         if (gen) {
+          const uint32_t mw = mskw[j];
+          if (bias_row) {
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const int key = j * 32 + u;
-            if (key < nkeys && !msk[key])
-              mymax = fmaxf(mymax, bias_row ? fmaf(s[u], p.scale, __ldg(bias_row + key)) : s[u] * p.scale);
+            for (int g8 = 0; g8 < 32; g8 += 8) {          // 8 bias loads in flight at a time (register budget)
+#pragma unroll
+              for (int u = g8; u < g8 + 8; ++u) {
+                const float x = fmaf(s[u], p.scale, (mw >> u) & 1u ? 0.f : __ldg(bias_row + j * 32 + u));
+                mymax = (mw >> u) & 1u ? mymax : fmaxf(mymax, x);
+              }
+              asm volatile("" ::: "memory");
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) mymax = (mw >> u) & 1u ? mymax : fmaxf(mymax, s[u] * p.scale);
           }
         } else if (j * 32 + 32 <= nkeys) {
 #pragma unroll
@@ -943,12 +958,13 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_ld16(t_row + kbase, s);
         if (gen) {
           const float L2E = 1.4426950408889634f;
+          const uint32_t mw = mskw[kbase >> 5] >> (kbase & 31);        // PW = 16 keys: half a word
+          const float nbg = -rmax * L2E;
 #pragma unroll
           for (int u = 0; u < PW; ++u) {
-            const int key = kbase + u;
-            const bool ok = key < nkeys && !msk[key];
-            const float x = (ok && bias_row) ? fmaf(s[u], p.scale, __ldg(bias_row + key)) : s[u] * p.scale;
-            s[u] = ok ? ex2((x - rmax) * L2E) : 0.f;
+            const bool ok = !((mw >> u) & 1u);
+            const float x = (ok && bias_row) ? fmaf(s[u], p.scale, __ldg(bias_row + kbase + u)) : s[u] * p.scale;
+            s[u] = ok ? ex2(fmaf(x, L2E, nbg)) : 0.f;
             rsum += s[u];
           }
         } else if (kbase + PW <= nkeys) {
