@@ -7,7 +7,7 @@
 namespace ec {
 
 // One CTA per batch element.  `binary` (global, [K,K]) doubles as the scatter target.
-__global__ void __launch_bounds__(256) adj_from_edges_kernel(const int32_t* __restrict__ edges,
+__global__ void __launch_bounds__(1024) adj_from_edges_kernel(const int32_t* __restrict__ edges,
                                                              const int32_t* __restrict__ offsets,
                                                              const uint8_t* __restrict__ kp_mask,
                                                              float* __restrict__ adj, float* __restrict__ binary,
@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(256) soft_normalize_kernel(const float* __rest
   const uint8_t* mk = kp_mask + (long long)b * K;
   float* a0 = adj + (long long)b * 2 * KK;
   float* a1 = a0 + KK;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // rows are independent: gridDim.y CTAs share the rows of a sample, one warp per row at a time
+  const int lane = threadIdx.x & 31, nw = (blockDim.x >> 5) * gridDim.y;
+  const int warp = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (int i = warp; i < K; i += nw) {
     const float vi = mk[i] ? 0.f : 1.f;
     float s = 0.f;
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(256) edge_weights_kernel(const float* __restri
   float* un = unnorm ? unnorm + (long long)b * KK : nullptr;
   float* h0 = hop0 ? hop0 + (long long)b * KK : nullptr;
   float* h1 = hop1 ? hop1 + (long long)b * KK : nullptr;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, nw = (blockDim.x >> 5) * gridDim.y;
+  const int warp = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (int i = warp; i < K; i += nw) {
     const float vi = mk[i] ? 0.f : 1.f;
     auto value = [&](int j) {
@@ -250,7 +253,8 @@ extern "C" int ec_adj_from_edges(const int32_t* edges, const int32_t* offsets, c
                                  float* adj, float* binary, int B, int K, void* stream) {
   EC_REQUIRE(offsets && kp_mask && adj && binary, "ec_adj_from_edges: null pointer");
   if (B == 0) return EC_OK;
-  launch_pdl(adj_from_edges_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, edges, offsets, kp_mask, adj, binary, K);
+  // one CTA per sample (the scatter needs the whole matrix), 32 warps: the row passes are latency chains
+  launch_pdl(adj_from_edges_kernel, dim3(B), dim3(1024), (size_t)(0), (cudaStream_t)stream, edges, offsets, kp_mask, adj, binary, K);
   return check_launch("ec_adj_from_edges");
 }
 
@@ -258,7 +262,7 @@ extern "C" int ec_soft_normalize_adj(const float* U, const uint8_t* kp_mask, flo
                                      void* stream) {
   EC_REQUIRE(U && kp_mask && adj, "ec_soft_normalize_adj: null pointer");
   if (B == 0) return EC_OK;
-  launch_pdl(soft_normalize_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, U, kp_mask, adj, K);
+  launch_pdl(soft_normalize_kernel, dim3(B, cdiv(K, 8)), dim3(256), (size_t)(0), (cudaStream_t)stream, U, kp_mask, adj, K);
   return check_launch("ec_soft_normalize_adj");
 }
 
@@ -267,7 +271,7 @@ extern "C" int ec_edge_weights(const float* S, const float* binary, const uint8_
                                float* hop1, int B, int K, void* stream) {
   EC_REQUIRE(S && binary && kp_mask && adj, "ec_edge_weights: null pointer");
   if (B == 0) return EC_OK;
-  launch_pdl(edge_weights_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, S, binary, kp_mask, zc_w, zc_b, use_zero_conv, adj,
+  launch_pdl(edge_weights_kernel, dim3(B, cdiv(K, 8)), dim3(256), (size_t)(0), (cudaStream_t)stream, S, binary, kp_mask, zc_w, zc_b, use_zero_conv, adj,
                                                            unnorm, hop0, hop1, K);
   return check_launch("ec_edge_weights");
 }
