@@ -330,6 +330,7 @@ extern "C" int ec_pck_accumulate(const float* pred, const float* gt, const uint8
 extern "C" int ec_metrics_accumulate(const float* pred, const float* gt, const uint8_t* valid, const float* norm,
                                      const float* thr, int T, int auc_steps, double* counters, int B, int K,
                                      void* stream) {
+  if (B == 0) return EC_OK;                       // an empty shard: nothing to add (its tensors may be null)
   EC_REQUIRE(pred && gt && valid && norm && thr && counters, "ec_metrics_accumulate: null pointer");
   EC_REQUIRE(T >= 1 && T <= 16 && auc_steps >= 1 && auc_steps <= 64, "ec_metrics_accumulate: 1..16 thresholds, 1..64 AUC steps");
   if (B == 0) return EC_OK;

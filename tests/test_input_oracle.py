@@ -35,3 +35,21 @@ def test_tensor_and_joints_and_targets():
         target, weight = io.msra_targets(G[f"joints_t{i}"], G[f"vis{i}"], (R, R), (HM, HM), 1)
         assert np.array_equal(weight, G[f"weight{i}"])
         assert np.array_equal(target, G[f"target{i}"])
+
+
+def test_warp_matches_cv2_for_rotations_and_scalings_when_cv2_is_here():
+    """Beyond the committed goldens (rotation 0): random rotations / anisotropic scalings against the OpenCV installed in
+    this environment (skipped where cv2 is absent, e.g. on a bare GPU box)."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        Hs, Ws = int(rng.integers(40, 200)), int(rng.integers(40, 200))
+        img = rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8)
+        ang = np.deg2rad(rng.uniform(-60, 60))
+        sx, sy = rng.uniform(0.3, 2.5, 2)
+        M = np.array([[sx * np.cos(ang), -sy * np.sin(ang), rng.uniform(-30, 30)],
+                      [sx * np.sin(ang), sy * np.cos(ang), rng.uniform(-30, 30)]])
+        W, H = int(rng.integers(16, 96)), int(rng.integers(16, 96))
+        want = cv2.warpAffine(img, M, (W, H), flags=cv2.INTER_LINEAR)
+        got = io.warp_affine_u8(img, M, W, H)
+        assert np.array_equal(got, want), np.abs(got.astype(int) - want.astype(int)).max()

@@ -56,3 +56,42 @@ def test_input_stage_host_orchestration(monkeypatch):
 @pytest.mark.gpu
 def test_input_stage_kernels_bit_exact_crop():
     _run(torch.device("cuda"))
+
+
+@pytest.mark.gpu
+def test_crop_kernel_matches_oracle_for_rotated_transforms():
+    """The oracle's fixed-point warp is pinned against OpenCV (tests/test_input_oracle.py); here the kernel is compared
+    with the oracle on rotated / anisotropic transforms and odd image sizes."""
+    from oracle import input_oracle as io
+    rng = np.random.default_rng(9)
+    dev = torch.device("cuda")
+    for _ in range(5):
+        Hs, Ws = int(rng.integers(30, 300)), int(rng.integers(30, 300))
+        img = rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8)
+        ang = np.deg2rad(rng.uniform(-90, 90))
+        sx, sy = rng.uniform(0.2, 3.0, 2)
+        M = np.array([[sx * np.cos(ang), -sy * np.sin(ang), rng.uniform(-50, 50)],
+                      [sx * np.sin(ang), sy * np.cos(ang), rng.uniform(-50, 50)]])
+        W, H = int(rng.integers(8, 130)), int(rng.integers(8, 130))
+        stage = inputs.InputStage((W, H), (HM, HM), 1, G["mean"], G["std"])
+        got = stage.crop_normalize(torch.from_numpy(img).to(dev), M).cpu().numpy()
+        want = io.to_tensor_normalize(io.warp_affine_u8(img, M, W, H), G["mean"], G["std"])
+        assert np.array_equal(got, want), float(np.abs(got - want).max())
+
+
+@pytest.mark.gpu
+def test_gather_blocks_and_empty_batches():
+    from edgecape_b200 import ops
+    from edgecape_b200.parallel import new_metric_counters
+    dev = torch.device("cuda")
+    src = torch.randn(5, 7, 12, device=dev)
+    idx = torch.tensor([4, 0, 0, 3, 1, 4], dtype=torch.int32, device=dev)
+    assert torch.equal(ops.gather_blocks(src, idx), src[idx.long()])
+    tok = torch.randn(4, 9, 10, device=dev)                       # strided view (cls row dropped), odd sizes -> scalar path
+    idx2 = torch.tensor([3, 0, 2], dtype=torch.int32, device=dev)
+    assert torch.equal(ops.gather_blocks(tok[:, 1:, :], idx2), tok[:, 1:, :][idx2.long()])
+    c = new_metric_counters(dev)
+    z = torch.zeros(0, 5, 2, device=dev)
+    ops.metrics_accumulate_(c, z, z, torch.zeros(0, 5, dtype=torch.uint8, device=dev), torch.zeros(0, 2, device=dev),
+                            torch.tensor([0.2], device=dev))
+    assert float(c.sum()) == 0.0
