@@ -42,3 +42,27 @@ class _Done:
 def single_gpu_test(model, data_loader, pck=False, depth=None):
     """apis/test.py:33-50: run the model over the loader, return the list of per-batch result dicts."""
     return list(iter_results(model, data_loader, depth=depth))
+
+
+def multi_gpu_test(model, data_loader, tmpdir=None, gpu_collect=True, pck=False, depth=None, size=None):
+    """apis/test.py:53-90 (`multi_gpu_test`): every rank runs the pipelined loop over its own loader, then the
+    per-batch result dicts are gathered on rank 0 and re-interleaved exactly like `collect_results_gpu` /
+    `collect_results_cpu` (:93-198: `zip(*parts)`, truncated to the dataset size because the distributed sampler pads).
+    Returns the ordered list on rank 0 and None elsewhere.  `tmpdir` / `gpu_collect` are accepted for signature
+    compatibility; the exchange is one `all_gather_object`.  (For metrics only, prefer the device-side counters +
+    one all-reduce: parallel.new_metric_counters / allreduce_counters.)"""
+    import torch.distributed as dist
+    part = list(iter_results(model, data_loader, depth=depth))
+    if size is None:
+        ds = getattr(data_loader, "dataset", None)
+        size = len(ds) if ds is not None else None
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return part if size is None else part[:size]
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, part)
+    if dist.get_rank() != 0:
+        return None
+    ordered = []
+    for res in zip(*parts):
+        ordered.extend(list(res))
+    return ordered if size is None else ordered[:size]

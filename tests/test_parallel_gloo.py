@@ -78,3 +78,53 @@ def test_two_rank_counters_equal_single_process():
     s_ = summarize_pck(torch.tensor(got, dtype=torch.float64))
     assert s_["samples"] == 37 and abs(s_["PCK@0.2"] - want[3] / 37) < 1e-12
     assert abs(s_["mPCK"] - want[:5].sum() / 37 / 5) < 1e-12
+
+
+class _FakeModel:
+    """Stands in for the detector: result = the batch's ids (the collection logic is what is under test)."""
+    test_cfg = {}
+    use_cuda_graph = False
+
+    def eval(self):
+        return self
+
+    def forward_test(self, ids=None, **kw):
+        return dict(bbox_ids=list(ids), preds=np.asarray(ids, dtype=np.float32)[:, None])
+
+
+class _Loader(list):
+    dataset = None
+
+
+def _collect_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from edgecape_b200.apis import multi_gpu_test
+    # DistributedSampler semantics: rank r sees samples r, r + world, ... (padded by wrapping); batch size 1
+    n = 5
+    idx = list(range(n)) + [0] * ((-n) % world)
+    loader = _Loader([dict(ids=[i]) for i in idx[rank::world]])
+    loader.dataset = list(range(n))
+    out = multi_gpu_test(_FakeModel(), loader)
+    if rank == 0:
+        q.put([r["bbox_ids"][0] for r in out])
+    else:
+        assert out is None
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_test_interleaves_and_truncates_like_the_reference():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_collect_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [0, 1, 2, 3, 4]          # zip(*parts) re-interleaving, padding sample dropped
