@@ -60,6 +60,8 @@ SIGNATURES = {
     "ec_gcn": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp, c_sz, c_fp]),
     "ec_gcn_aggregate_split": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "ec_workspace_bytes_gcn": (c_sz, [c_int, c_int, c_int, c_int]),
+    "ec_gcn_fused_slice": (c_int, [c_int, c_int, c_int]),
+    "ec_gcn_fused": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_support_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),
     "ec_proposal": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),

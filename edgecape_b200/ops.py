@@ -491,6 +491,14 @@ def gcn_tc_ok(B, K):
     return TENSOR_CORES and B * K >= TC_MIN_M and ((K + 3) // 4 * 4) * 32 <= 48 * 1024
 
 
+# one-kernel GCN (csrc/gcn_fused_tcgen05.cu); EDGECAPE_GCN_FUSED=0 keeps the aggregate kernel + GEMM pair
+GCN_FUSED = os.environ.get("EDGECAPE_GCN_FUSED", "0") != "0"
+
+
+def gcn_fused_ok(B, K, d, dff):
+    return bool(GCN_FUSED and gcn_tc_ok(B, K) and _lib.load().ec_gcn_fused_slice(K, d, dff) > 0)
+
+
 def gcn(x, adj, Wp, out=None, split="no"):
     """x [B,K,d], adj [B,2,K,K] (plane 0 diagonal), packed weights -> relu(GCN) [B,K,dff].
     Tensor-core mode: fused aggregate -> split-fp16 Z, then the tcgen05 GEMM with a ReLU epilogue; split="only"
@@ -500,6 +508,20 @@ def gcn(x, adj, Wp, out=None, split="no"):
     B, K, d = x.shape
     dff = Wp.shape[0]
     assert Wp.shape[1] == 2 * d + 4
+    if gcn_fused_ok(B, K, d, dff):
+        w2 = split_weight(Wp)
+        so, so_ptr = None, None
+        if split != "no":
+            so = SplitOperand(empty(B * K, 2 * dff, dtype=torch.float16, device=x.device), B * K, dff, dff, 1.0)
+            so_ptr = so.data.data_ptr()
+        if split == "only":
+            out = None
+        elif out is None:
+            out = empty(B, K, dff, device=x.device)
+        assert out is None or out.is_contiguous()
+        _lib.call("ec_gcn_fused", _p(x), _p(adj), _p(Wp), w2.data.data_ptr(), w2.Kp, float(w2.scale), _p(out), so_ptr,
+                  dff, B, K, d, dff, _stream())
+        return so if split == "only" else ((out, so) if split == "also" else out)
     if gcn_tc_ok(B, K):
         Kp = _kp(2 * d + 4)
         z2 = SplitOperand(empty(B * K, 2 * Kp, dtype=torch.float16, device=x.device), B * K, 2 * d + 4, Kp, 1.0)

@@ -226,6 +226,16 @@ size_t ec_workspace_bytes_gcn(int B, int K, int d, int dff);
  * Z2 [B*K, 2*Kp] (Kp = 2d+4 rounded up to 64), then ec_gemm_f16x3(Z2, split(Wp), act = ReLU) finishes it. */
 int ec_gcn_aggregate_split(const float* X, const float* adj, void* Z2, int B, int K, int d, int Kp,
                            void* stream);
+/* The same layer as ONE kernel (csrc/gcn_fused_tcgen05.cu): per (sample, slice of output channels) CTA the
+ * aggregate A1 X and both weight products run on the tensor cores out of shared memory / TMEM; nothing but X,
+ * adj and the weights is read and nothing but the result is written.  W2 [dff, 2*Kp] is the split-fp16 form of
+ * Wp * w_scale (ec_split_f16; Kp = 2d+4 rounded up to 64, w_scale a power of two); the bias columns are taken
+ * from the fp32 Wp.  Y [B,K,dff] and / or split_out [B*K, 2*split_kp] (hi | lo of Y) are written.
+ * ec_gcn_fused_slice returns the channel-slice width the kernel would use, or 0 when it cannot take the shape
+ * (it needs K <= 128, d a multiple of 64 up to 256, dff a multiple of 64, and the tiles to fit 227 KB). */
+int ec_gcn_fused_slice(int K, int d, int dff);
+int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* W2, int Kp, float w_scale,
+                 float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);
 
 /* ----------------------------------------------------------------------------- head ops
  * support-keypoint pooling weights (head.py:175-184, exact by linearity):

@@ -8,9 +8,12 @@ sys.path.insert(0, ".")
 from edgecape_b200 import ops  # noqa: E402
 
 
-def run(B, K, d, dff, tc, iters=50):
+def run(B, K, d, dff, tc, iters=50, fused=False):
     D = torch.device("cuda")
     ops.TENSOR_CORES = tc
+    ops.GCN_FUSED = fused
+    if fused and not ops.gcn_fused_ok(B, K, d, dff):
+        return
     x = torch.randn(B, K, d, device=D)
     U = torch.rand(B, K, K, device=D)
     mask = torch.zeros(B, K, dtype=torch.uint8, device=D)
@@ -36,12 +39,15 @@ def run(B, K, d, dff, tc, iters=50):
     flops = 2.0 * B * K * d * 2 * dff + 2.0 * B * K * K * d
     peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if __import__("os").path.exists("MEASURED_PEAKS.json") else 6650.0
     gbs = bytes_alg / us / 1e3
-    print(json.dumps(dict(op="gcn", B=B, K=K, d=d, dff=dff, path="tcgen05" if tc else "simt_fp32", us=round(us, 2),
+    print(json.dumps(dict(op="gcn", B=B, K=K, d=d, dff=dff, path=("fused_tcgen05" if fused else "tcgen05") if tc else "simt_fp32", us=round(us, 2),
                           algorithmic_MB=round(bytes_alg / 1e6, 2), achieved_GBs=round(gbs, 1), hbm_peak_GBs=peak,
                           frac_hbm=round(gbs / peak, 4), algorithmic_TFLOPs=round(flops / us / 1e6, 1))), flush=True)
 
 
 if __name__ == "__main__":
+    for B in (64, 16, 148, 2048):
+        run(B, 100, 256, 384, True, iters=50 if B < 1000 else 5, fused=True)
+    run(64, 100, 256, 768, True, fused=True)
     for tc in (True, False):
         run(64, 100, 256, 384, tc)
         run(64, 100, 256, 768, tc)

@@ -362,6 +362,27 @@ def ec_gcn_aggregate_split(X, adj, Z2, B, K, d, Kp, stream):
     _write_split(Z2, Kp, z.reshape(B * K, Kp))
 
 
+def ec_gcn_fused(X, adj, Wp, W2, Kp, w_scale, Y, split_out, split_kp, B, K, d, dff, stream):
+    """One-kernel GCN: split-fp16 products of the aggregate-first form, biases added in fp32 (gcn_fused_tcgen05.cu)."""
+    x, a = arr(X, (B, K, d)), arr(adj, (B, 2, K, K))
+    wp = arr(Wp, (dff, 2 * d + 4))
+    w2 = arr(W2, (dff, 2 * Kp), dtype=np.float16).astype(np.float32)
+    wh, wl = w2[:, :2 * d], w2[:, Kp:Kp + 2 * d]
+    a0 = np.stack([np.diag(a[b, 0]) for b in range(B)])                      # [B,K]
+    a1h, a1l = _h2(a[:, 1])
+    xh, xl = _h2(x)
+    agg = a1l @ xh + a1h @ xl + a1h @ xh                                       # GEMM 1 (fp32 accumulate)
+    z = np.concatenate([a0[:, :, None] * (xh + xl), agg], axis=-1).astype(np.float32).reshape(B * K, 2 * d)
+    zh, zl = _h2(z)
+    acc = zl @ wh.T + zh @ wl.T + zh @ wh.T
+    y = acc / np.float32(w_scale) + a0.reshape(-1, 1) * wp[None, :, 2 * d] + a[:, 1].sum(-1).reshape(-1, 1) * wp[None, :, 2 * d + 1]
+    y = np.maximum(y, 0).astype(np.float32)
+    if Y:
+        arr(Y, (B * K, dff))[...] = y
+    if split_out:
+        _write_split(split_out, split_kp, y)
+
+
 def ec_support_weights(target, rowscale, Tw, ldtw, BK, hm_h, hm_w, h, w, stream):
     t = T(arr(target, (BK, hm_h * hm_w)))
     # U[p, s]: bilinear interpolation matrix = upsampled one-hot basis images

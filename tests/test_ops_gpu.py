@@ -189,9 +189,14 @@ def test_adjacency_from_edges_and_soft_normalize(K):
 
 
 @pytest.mark.parametrize("B,K,d,dff", [(4, 100, 256, 384), (2, 17, 256, 64), (2, 200, 256, 384), (3, 100, 256, 768)])
-@pytest.mark.parametrize("tensor_cores", [True, False], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("tensor_cores", [True, False, "fused"], ids=["tcgen05", "simt", "fused"])
 def test_gcn_matches_oracle(B, K, d, dff, tensor_cores, monkeypatch):
+    fused = tensor_cores == "fused"
+    tensor_cores = bool(tensor_cores)
     monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
+    monkeypatch.setattr(ops, "GCN_FUSED", fused)
+    if fused and not ops.gcn_fused_ok(B, K, d, dff):
+        pytest.skip("shape outside the fused kernel (falls back to the two-kernel path)")
     x = rnd(B, K, d, seed=1)
     W, b = rnd(2 * dff, d, 1, seed=2, scale=d ** -0.5), 0.1 * rnd(2 * dff, seed=3)
     mask = torch.zeros(B, K, dtype=torch.bool)
@@ -206,6 +211,38 @@ def test_gcn_matches_oracle(B, K, d, dff, tensor_cores, monkeypatch):
     if tensor_cores and B * K >= ops.TC_MIN_M:
         so = ops.gcn(x.to(D), adj.to(D).contiguous(), Wp, split="only")
         close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), what="gcn split")
+
+
+@pytest.mark.parametrize("B,K,d,dff", [(64, 100, 256, 384), (5, 97, 128, 192), (3, 112, 256, 768), (2, 64, 64, 64)])
+def test_gcn_fused_kernel(B, K, d, dff, monkeypatch):
+    """One-kernel GCN (gcn_fused_tcgen05.cu) vs the fp64 oracle and vs the two-kernel tensor-core path: general
+    (non 0/1) diagonal plane, masked rows, fp32 and split outputs."""
+    monkeypatch.setattr(ops, "TENSOR_CORES", True)
+    monkeypatch.setattr(ops, "GCN_FUSED", True)
+    assert ops.gcn_fused_ok(B, K, d, dff)
+    x = rnd(B, K, d, seed=11)
+    W, b = rnd(2 * dff, d, 1, seed=12, scale=d ** -0.5), 0.1 * rnd(2 * dff, seed=13)
+    mask = torch.zeros(B, K, dtype=torch.bool)
+    mask[0, K - K // 5:] = True
+    mask[B - 1, ::3] = True
+    U = torch.rand(B, K, K, generator=torch.Generator().manual_seed(14))
+    adj = O.soft_normalize_adj(U, mask)
+    if B > 2:   # a diagonal plane that is not 0/1 exercises the in-place rescale of the X tiles
+        adj[1, 0] = torch.diag_embed(torch.rand(K, generator=torch.Generator().manual_seed(15)) * 2 - 0.5)
+    want = O.gcn(x.double(), adj.double(), W.double(), b.double()).float()
+    D = dev()
+    Wp = ops.gcn_pack_weights(W.to(D), b.to(D))
+    xd, ad = x.to(D), adj.to(D).contiguous()
+    got = ops.gcn(xd, ad, Wp)
+    close(got, want, tol=2e-5, what="gcn fused")
+    y2, so = ops.gcn(xd, ad, Wp, split="also")
+    assert torch.equal(y2, got)
+    close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), tol=2e-5,
+          what="gcn fused split")
+    so2 = ops.gcn(xd, ad, Wp, split="only")
+    assert torch.equal(so2.data, so.data)
+    monkeypatch.setattr(ops, "GCN_FUSED", False)
+    close(got, ops.gcn(xd, ad, Wp), tol=2e-5, what="fused vs two-kernel")
 
 
 def test_edge_weights_and_markov_match_oracle():
