@@ -29,7 +29,8 @@ int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap*
 }
 namespace gf {
 
-constexpr int WORKERS = 256;             // 8 worker warps
+constexpr int WORKERS = 512;             // 16 worker warps (4 per TMEM lane quarter)
+constexpr int EPI_LD = 20;               // epilogue staging row stride (floats): conflict-free float4 writes
 constexpr int THREADS = WORKERS + 64;    // + MMA warp + TMA warp
 constexpr int ACC_COL = 256;             // TMEM: D1 in columns [0, d), the output accumulator in [256, 256 + NS)
 constexpr int MAX_G = 4;                 // d <= 256: at most four 64-column groups
@@ -104,6 +105,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* r) {   // caller issues tcgen05.wait::ld
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+}
+
 // byte offset of the 16-byte chunk `c` (8 fp16) of row `row` inside a 128B-swizzled tile
 __device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)); }
 
@@ -124,6 +146,8 @@ struct Params {
   int split_kp;
   int K, d, dff, NS, k16, Kp;
   float out_scale;     // 1 / (power-of-two scale of the split weights)
+  long long* trace;    // optional [trace_n][32] clock64 stamps of CTA phases (ec_gcn_fused_set_trace)
+  int trace_n;
 };
 
 // barrier indices (8 bytes each)
@@ -140,6 +164,8 @@ __host__ __device__ inline Layout make_layout(int k16, int d, int NS) {
   L.wst = (uint32_t)NS * 256u;                    // hi + lo tiles of NS rows x 128 B
   const uint32_t a1 = 2u * kbs * L.ts;
   L.a1_bytes = a1 > L.wst ? a1 : L.wst;            // the A1 region is recycled as W stage 1
+  const uint32_t epi = (WORKERS / 32) * 32 * EPI_LD * 4;   // the epilogue staging tiles reuse the operand regions
+  if (L.xb_bytes + L.a1_bytes + L.wst < epi) L.a1_bytes = epi - L.xb_bytes - L.wst;
   // + barriers / TMEM slot (256 B) + rs, a0 (128 floats each) + b0, b1 (256 floats each)
   L.total = L.xb_bytes + L.a1_bytes + L.wst + 256u + (128u + 128u + 256u + 256u) * 4u;
   return L;
@@ -156,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
   const uint32_t xb = base, a1 = xb + L.xb_bytes, w0 = a1 + L.a1_bytes, misc = w0 + L.wst;
   auto bar = [&](int i) { return misc + 8u * i; };
   const uint32_t tmem_slot = misc + 8u * NUM_BARS;
+  int* flag = reinterpret_cast<int*>(gbase + (tmem_slot - base) + 8);     // "some a0 != 1": the rescale pass is needed
   float* rs = reinterpret_cast<float*>(gbase + (misc - base) + 256);
   float* a0s = rs + 128;
   float* b0s = a0s + 128;
@@ -163,8 +190,13 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, n0 = blockIdx.x * NS;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  auto stamp = [&](int i) {
+    if (p.trace && cta < p.trace_n) p.trace[cta * 32 + i] = clock64();
+  };
 
   if (threadIdx.x == 0) {
+    *flag = 0;
     mbar_init(bar(W_FULL + 0), 1); mbar_init(bar(W_FULL + 1), 1);
     mbar_init(bar(W_EMPTY + 0), 1); mbar_init(bar(W_EMPTY + 1), 1);
     mbar_init(bar(B_FILL), WORKERS / 32);
@@ -174,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
     mbar_init(bar(B_ACC), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == WORKERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -185,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == 9) {
+  if (warp == WORKERS / 32 + 1) {
     // ------------------------------------------------------------------ TMA producer: the W ring
     if (elect_one()) {
       const int nkb = 2 * ng;
@@ -199,11 +231,12 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
         tma_load_2d(dst + (uint32_t)NS * 128u, &tmW, bar(W_FULL + s), p.Kp + kb * 64, n0);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == WORKERS / 32) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       mbar_wait(bar(B_FILL), 0);
       tc_fence_after();
+      stamp(12);
       {
         // GEMM 1: D1[128 x d] = A1 (K-major, k16 deep) . X (MN-major rows v, d columns in ng tiles TS apart)
         const uint32_t idesc1 = make_idesc(d) | (1u << 16);
@@ -216,8 +249,10 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
           umma(tmem_base, make_desc(a1 + (uint32_t)(k >> 2) * TS) + 2 * (k & 3), x_hi + 128 * k, idesc1, 1u);
         umma_commit(bar(B_D1));
       }
+      stamp(13);
       mbar_wait(bar(B_ZA), 0);
       tc_fence_after();
+      stamp(14);
       const uint32_t idesc2 = make_idesc(NS);
       const int nkb = 2 * ng;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -225,6 +260,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
         mbar_wait(bar(W_FULL + s), (uint32_t)(kb >> 1) & 1u);
         if (kb >= ng) mbar_wait(bar(B_ZB + g), 0);
         tc_fence_after();
+        stamp(15 + 2 * kb);
         const uint64_t a_hi = make_desc(xb + (uint32_t)g * TS), a_lo = make_desc(xb + (uint32_t)(ng + g) * TS);
         const uint32_t wb = s ? a1 : w0;
         const uint64_t b_hi = make_desc(wb), b_lo = make_desc(wb + (uint32_t)NS * 128u);
@@ -236,136 +272,171 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
         for (int k = 0; k < 4; ++k) umma(tmem_base + ACC_COL, a_hi + 2 * k, b_hi + 2 * k, idesc2, 1u);
         umma_commit(bar(W_EMPTY + s));
         if (kb < ng) umma_commit(bar(B_G2A + g));          // X tile g may be overwritten by (A1 X) tile g
+        stamp(16 + 2 * kb);
       }
       umma_commit(bar(B_ACC));
     }
   } else {
-    // ------------------------------------------------------------------ workers (8 warps)
+    // ------------------------------------------------------------------ workers (16 warps)
     const int tid = threadIdx.x;
     const long long KK = (long long)K * K;
     const float* a0p = p.adj + (long long)b * 2 * KK;
     const float* a1p = a0p + KK;
     const float* Xb = p.X + (long long)b * K * d;
     const int ldw = 2 * d + 4;
-    for (int i = tid; i < NS; i += WORKERS) {
-      b0s[i] = __ldg(p.Wp + (long long)(n0 + i) * ldw + 2 * d);
-      b1s[i] = __ldg(p.Wp + (long long)(n0 + i) * ldw + 2 * d + 1);
-    }
-    // row sums of A1 (fp32, same lane order as the unfused kernel) and the diagonal of plane 0
-    for (int w = warp; w < K; w += WORKERS / 32) {
-      float sacc = 0.f;
-      for (int v = lane; v < K; v += 32) sacc += __ldg(a1p + (long long)w * K + v);
-      sacc = warp_sum(sacc);
-      if (lane == 0) {
-        rs[w] = sacc;
-        a0s[w] = __ldg(a0p + (long long)w * K + w);
+    if (tid == 0) stamp(0);
+    const int ncx = d / 8;
+    constexpr int X_IT = 8;                                         // 128 rows x 32 chunks / 512 threads
+    float4 q[X_IT][2];
+    auto load_x = [&](int u0, int u1) {
+      const int items = k16 * ncx;
+#pragma unroll
+      for (int u = u0; u < u1; ++u) {
+        const int it = tid + u * WORKERS;
+        q[u][0] = q[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < items) {
+          const int v = it / ncx, c = it - v * ncx;
+          if (v < K) {
+            const float4* src = reinterpret_cast<const float4*>(Xb + (long long)v * d + c * 8);
+            q[u][0] = __ldg(src);
+            q[u][1] = __ldg(src + 1);
+          }
+        }
       }
-    }
-    // A1 -> K-major tiles (hi tiles [0, kbs), lo tiles [kbs, 2 kbs)), columns >= K zero
+    };
+    // A1 -> K-major tiles (hi tiles [0, kbs), lo tiles [kbs, 2 kbs)), columns >= K zero.  16 lanes per row (one
+    // 8-column chunk each; every load of the thread is issued before the first use), row sums by shuffles.
     {
       const int nc = k16 / 8;
       const bool vec = (K & 3) == 0;
-      for (int it = tid; it < K * nc; it += WORKERS) {
-        const int w = it / nc, c = it - w * nc;
-        float v[8];
-        const float* src = a1p + (long long)w * K + c * 8;
-        if (vec) {
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 q0 = (c * 8 < K) ? __ldg(reinterpret_cast<const float4*>(src)) : z;
-          const float4 q1 = (c * 8 + 4 < K) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : z;
-          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-        } else {
+      const int c = tid & 15;
+      constexpr int A1_IT = (128 * 16 + WORKERS - 1) / WORKERS;   // K <= 128
+      float v[A1_IT][8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = (c * 8 + u < K) ? __ldg(src + u) : 0.f;
-        }
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        const uint32_t off = (uint32_t)(c >> 3) * TS + swz(w, c & 7);
-        *reinterpret_cast<uint4*>(gbase + (a1 - base) + off) = hi;
-        *reinterpret_cast<uint4*>(gbase + (a1 - base) + (uint32_t)kbs * TS + off) = lo;
-      }
-    }
-    // X -> [v][64-column] tiles (hi tiles [0, ng), lo tiles [ng, 2 ng)), rows [K, k16) zero; 4 items in flight
-    const int ncx = d / 8;
-    {
-      const int items = k16 * ncx;
-      for (int it0 = tid; it0 < items; it0 += 4 * WORKERS) {
-        float4 q[4][2];
+      for (int i = 0; i < A1_IT; ++i) {
+        const int w = (tid + i * WORKERS) >> 4;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + u * WORKERS;
-          q[u][0] = q[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (it < items) {
-            const int v = it / ncx, c = it - v * ncx;
-            if (v < K) {
-              const float4* src = reinterpret_cast<const float4*>(Xb + (long long)v * d + c * 8);
-              q[u][0] = __ldg(src);
-              q[u][1] = __ldg(src + 1);
+        for (int u = 0; u < 8; ++u) v[i][u] = 0.f;
+        if (w < K) {
+          const float* src = a1p + (long long)w * K + c * 8;
+          if (vec) {
+            if (c * 8 < K) {
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
+              v[i][0] = q0.x; v[i][1] = q0.y; v[i][2] = q0.z; v[i][3] = q0.w;
             }
+            if (c * 8 + 4 < K) {
+              const float4 q1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+              v[i][4] = q1.x; v[i][5] = q1.y; v[i][6] = q1.z; v[i][7] = q1.w;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (c * 8 + u < K) v[i][u] = __ldg(src + u);
           }
         }
+      }
+      // the first half of the X loads is issued here, behind the A1 loads and ahead of any use
+      load_x(0, X_IT / 2);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + u * WORKERS;
-          if (it >= items) continue;
-          const int v = it / ncx, c = it - v * ncx;
-          const float f[8] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w, q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w};
-          uint4 hi, lo;
-          split8(f, hi, lo);
-          const uint32_t off = (uint32_t)(c >> 3) * TS + swz(v, c & 7);
-          *reinterpret_cast<uint4*>(gbase + (xb - base) + off) = hi;
-          *reinterpret_cast<uint4*>(gbase + (xb - base) + (uint32_t)ng * TS + off) = lo;
+      for (int i = 0; i < A1_IT; ++i) {
+        const int w = (tid + i * WORKERS) >> 4;
+        float sacc = ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (w < K) {
+          if (c == 0) rs[w] = sacc;
+          if (c < nc) {
+            uint4 hi, lo;
+            split8(v[i], hi, lo);
+            const uint32_t off = (uint32_t)(c >> 3) * TS + swz(w, c & 7);
+            *reinterpret_cast<uint4*>(gbase + (a1 - base) + off) = hi;
+            *reinterpret_cast<uint4*>(gbase + (a1 - base) + (uint32_t)kbs * TS + off) = lo;
+          }
         }
+      }
+    }
+    if (tid == 0) stamp(2);
+    // X -> [v][64-column] tiles (hi tiles [0, ng), lo tiles [ng, 2 ng)), rows [K, k16) zero; up to 8 items (one
+    // 8-column chunk of one row each) per thread, all loads in flight before the first conversion
+    load_x(X_IT / 2, X_IT);                     // second half: in flight while the first half is converted
+    {
+      const int items = k16 * ncx;
+#pragma unroll
+      for (int u = 0; u < X_IT; ++u) {
+        const int it = tid + u * WORKERS;
+        if (it >= items) continue;
+        const int v = it / ncx, c = it - v * ncx;
+        const float f[8] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w, q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w};
+        uint4 hi, lo;
+        split8(f, hi, lo);
+        const uint32_t off = (uint32_t)(c >> 3) * TS + swz(v, c & 7);
+        *reinterpret_cast<uint4*>(gbase + (xb - base) + off) = hi;
+        *reinterpret_cast<uint4*>(gbase + (xb - base) + (uint32_t)ng * TS + off) = lo;
       }
     }
     proxy_fence();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar(B_FILL));
+    if (tid == 0) stamp(3);
+    // strided gathers (bias columns of Wp, diagonal of plane 0): their latency hides behind GEMM 1
+    for (int i = tid; i < NS; i += WORKERS) {
+      b0s[i] = __ldg(p.Wp + (long long)(n0 + i) * ldw + 2 * d);
+      b1s[i] = __ldg(p.Wp + (long long)(n0 + i) * ldw + 2 * d + 1);
+    }
+    if (tid < K) {                                   // does any row need the rescale pass?
+      const float a = __ldg(a0p + (long long)tid * K + tid);
+      a0s[tid] = a;
+      if (a != 1.0f) atomicOr(flag, 1);
+    }
 
-    // ---- GEMM 1 done: rescale the X tiles by a0[w] in place (rows with a0 == 1 are left alone)
+    // ---- GEMM 1 done: rescale the X tiles by a0[w] in place (skipped when every a0 is 1, the usual case)
     mbar_wait(bar(B_D1), 0);
     tc_fence_after();
-    asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");     // rs / a0s of every warp are visible
-    for (int it = tid; it < K * ncx; it += WORKERS) {
-      const int v = it / ncx, c = it - v * ncx;
-      const float a0v = a0s[v];
-      if (a0v == 1.0f) continue;
-      const uint32_t off = (uint32_t)(c >> 3) * TS + swz(v, c & 7);
-      uint4* ph = reinterpret_cast<uint4*>(gbase + (xb - base) + off);
-      uint4* pl = reinterpret_cast<uint4*>(gbase + (xb - base) + (uint32_t)ng * TS + off);
-      const uint4 h = *ph, l = *pl;
-      const __half2* hh = reinterpret_cast<const __half2*>(&h);
-      const __half2* ll = reinterpret_cast<const __half2*>(&l);
-      float f[8];
+    if (tid == 0) stamp(4);
+    asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");     // rs / a0s / flag of every warp are visible
+    if (*reinterpret_cast<volatile int*>(flag)) {
+      for (int it = tid; it < K * ncx; it += WORKERS) {
+        const int v = it / ncx, c = it - v * ncx;
+        const float a0v = a0s[v];
+        if (a0v == 1.0f) continue;
+        const uint32_t off = (uint32_t)(c >> 3) * TS + swz(v, c & 7);
+        uint4* ph = reinterpret_cast<uint4*>(gbase + (xb - base) + off);
+        uint4* pl = reinterpret_cast<uint4*>(gbase + (xb - base) + (uint32_t)ng * TS + off);
+        const uint4 h = *ph, l = *pl;
+        const __half2* hh = reinterpret_cast<const __half2*>(&h);
+        const __half2* ll = reinterpret_cast<const __half2*>(&l);
+        float f[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 fh = __half22float2(hh[u]), fl = __half22float2(ll[u]);
-        f[2 * u] = a0v * (fh.x + fl.x);
-        f[2 * u + 1] = a0v * (fh.y + fl.y);
+        for (int u = 0; u < 4; ++u) {
+          const float2 fh = __half22float2(hh[u]), fl = __half22float2(ll[u]);
+          f[2 * u] = a0v * (fh.x + fl.x);
+          f[2 * u + 1] = a0v * (fh.y + fl.y);
+        }
+        uint4 hi, lo;
+        split8(f, hi, lo);
+        *ph = hi;
+        *pl = lo;
       }
-      uint4 hi, lo;
-      split8(f, hi, lo);
-      *ph = hi;
-      *pl = lo;
+      proxy_fence();
     }
-    proxy_fence();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar(B_ZA));
+    if (tid == 0) stamp(5);
 
     // ---- drain D1 = A1 X group by group into the X tile whose k-block of GEMM 2 has retired
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, part = warp >> 2;                 // TMEM lane quarter; 16-column part of a group
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int g = 0; g < ng; ++g) {
-      float r[32];
-      tmem_ld32(t_row + (uint32_t)(g * 64 + half * 32), r);
+      float r[16];
+      tmem_ld16(t_row + (uint32_t)(g * 64 + part * 16), r);
       mbar_wait(bar(B_G2A + g), 0);
       if (row < K) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           uint4 hi, lo;
           split8(r + 8 * i, hi, lo);
-          const uint32_t off = (uint32_t)g * TS + swz(row, half * 4 + i);
+          const uint32_t off = (uint32_t)g * TS + swz(row, part * 2 + i);
           *reinterpret_cast<uint4*>(gbase + (xb - base) + off) = hi;
           *reinterpret_cast<uint4*>(gbase + (xb - base) + (uint32_t)ng * TS + off) = lo;
         }
@@ -373,43 +444,69 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
       proxy_fence();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_ZB + g));
+      if (tid == 0) stamp(6 + g);
     }
 
-    // ---- epilogue: this warp owns rows [32 quarter, +32) and columns [half NS/2, +NS/2) of the slice
+    // ---- epilogue: this warp owns rows [32 quarter, +32) and columns [part NS/4, +NS/4) of the slice.  Each
+    // 16-column sub-chunk is transposed through a per-warp staging tile (the X tiles are dead by now) so that the
+    // global stores are row-contiguous: 4 lanes cover a 64 B row segment, a warp 8 rows per instruction.
     mbar_wait(bar(B_ACC), 0);
     tc_fence_after();
-    const float a0v = row < K ? a0s[row] : 0.f, rsv = row < K ? rs[row] : 0.f;
-    const int hw = NS / 2;
-    for (int ch = 0; ch < hw / 32; ++ch) {
-      const int col0 = half * hw + ch * 32;
-      float r[32];
-      tmem_ld32(t_row + (uint32_t)(ACC_COL + col0), r);
-      if (row < K) {
+    if (tid == 0) stamp(10);
+    float* stg = reinterpret_cast<float*>(gbase + (xb - base)) + warp * (32 * EPI_LD);
+    const int sub_row = lane >> 2, c4 = (lane & 3) * 4;
+    const int cw = NS / 4, nsub = cw / 16;           // nsub <= 3 (NS <= 192)
+    float r[3][16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          r[j] = fmaxf(fmaf(r[j], p.out_scale, fmaf(a0v, b0s[col0 + j], rsv * b1s[col0 + j])), 0.f);
-        const long long grow = (long long)b * K + row;
-        if (p.Y) {
-          float4* yp = reinterpret_cast<float4*>(p.Y + grow * p.dff + n0 + col0);
+    for (int sc = 0; sc < 3; ++sc)
+      if (sc < nsub) tmem_ld16_nowait(t_row + (uint32_t)(ACC_COL + part * cw + sc * 16), r[sc]);
+    float a0r[4], rsr[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) yp[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        }
+    for (int i = 0; i < 4; ++i) {
+      const int orow = quarter * 32 + i * 8 + sub_row;
+      a0r[i] = orow < K ? a0s[orow] : 0.f;
+      rsr[i] = orow < K ? rs[orow] : 0.f;
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int sc = 0; sc < 3; ++sc) {
+      if (sc >= nsub) break;
+      const int col0 = part * cw + sc * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(r[sc][j], r[sc][j + 1], r[sc][j + 2], r[sc][j + 3]);
+      __syncwarp();
+      const int gcol = col0 + c4;
+      const float4 bb0 = *reinterpret_cast<const float4*>(b0s + gcol), bb1 = *reinterpret_cast<const float4*>(b1s + gcol);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + sub_row, orow = quarter * 32 + rr;
+        if (orow >= K) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + c4);
+        const float a0v = a0r[i], rsv = rsr[i];
+        float y[4];
+        y[0] = fmaxf(fmaf(a4.x, p.out_scale, fmaf(a0v, bb0.x, rsv * bb1.x)), 0.f);
+        y[1] = fmaxf(fmaf(a4.y, p.out_scale, fmaf(a0v, bb0.y, rsv * bb1.y)), 0.f);
+        y[2] = fmaxf(fmaf(a4.z, p.out_scale, fmaf(a0v, bb0.z, rsv * bb1.z)), 0.f);
+        y[3] = fmaxf(fmaf(a4.w, p.out_scale, fmaf(a0v, bb0.w, rsv * bb1.w)), 0.f);
+        const long long grow = (long long)b * K + orow;
+        if (p.Y) *reinterpret_cast<float4*>(p.Y + grow * p.dff + n0 + gcol) = make_float4(y[0], y[1], y[2], y[3]);
         if (p.split_out) {
-          __half* sp = p.split_out + grow * (2LL * p.split_kp) + n0 + col0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 hi, lo;
-            split8(r + 8 * j, hi, lo);
-            *reinterpret_cast<uint4*>(sp + 8 * j) = hi;
-            *reinterpret_cast<uint4*>(sp + p.split_kp + 8 * j) = lo;
-          }
+          uint32_t h01, l01, h23, l23;
+          split_pair(y[0], y[1], h01, l01);
+          split_pair(y[2], y[3], h23, l23);
+          __half* sp = p.split_out + grow * (2LL * p.split_kp) + n0 + gcol;
+          *reinterpret_cast<uint2*>(sp) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(sp + p.split_kp) = make_uint2(l01, l23);
         }
       }
+      __syncwarp();
     }
   }
+  if (threadIdx.x == 0) stamp(11);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  if (warp == WORKERS / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 constexpr uint32_t SMEM_LIMIT = 227u * 1024u;
@@ -431,6 +528,14 @@ inline int pick_slice(int K, int d, int dff) {
 }  // namespace ec
 
 using namespace ec;
+
+static long long* gf_trace = nullptr;
+static int gf_trace_n = 0;
+extern "C" int ec_gcn_fused_set_trace(void* buf, int n_ctas) {   // profiling hook: [n_ctas][32] int64 device buffer, or NULL
+  gf_trace = (long long*)buf;
+  gf_trace_n = buf ? n_ctas : 0;
+  return EC_OK;
+}
 
 extern "C" int ec_gcn_fused_slice(int K, int d, int dff) { return gf::pick_slice(K, d, dff); }
 
@@ -458,6 +563,7 @@ extern "C" int ec_gcn_fused(const float* X, const float* adj, const float* Wp, c
   gf::Params p;
   p.X = X; p.adj = adj; p.Wp = Wp; p.Y = Y; p.split_out = (__half*)split_out; p.split_kp = split_kp;
   p.K = K; p.d = d; p.dff = dff; p.NS = NS; p.k16 = k16; p.Kp = Kp; p.out_scale = 1.0f / w_scale;
+  p.trace = gf_trace; p.trace_n = gf_trace_n;
   launch_pdl(gf::gcn_fused_kernel, dim3(dff / NS, B), dim3(gf::THREADS), (size_t)smem, (cudaStream_t)stream, tmW, p);
   return check_launch("ec_gcn_fused");
 }
