@@ -217,6 +217,57 @@ class GemmTimer:
                     tensor_core_launches=tc)
 
 
+def north_star_kernels(peaks):
+    """The two kernels the north-star names, timed alone at its shapes (CUDA-graph replay of 20 launches between
+    CUDA events, warm; inputs of one launch are far smaller than L2, so these are L2-resident figures):
+    the skeleton-GCN feed-forward at batch 64 against the HBM roofline (SURVEY 8d bytes) and the ViT patch attention
+    of one bench step against the tensor-pipe roofline (algorithmic 4 N^2 D per head; 3 fp16 products issued per
+    algorithmic product)."""
+    import torch
+    from edgecape_b200 import ops
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf = float(peaks.get("bf16_tflops", 1650.0))          # a kernel timed alone: the burst figure
+
+    def graph_time(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) * 1e3 / iters          # us per launch
+
+    out = {}
+    B, K, d, dff = 64, 100, 256, 384
+    x = torch.randn(B, K, d, device=dev)
+    adj = ops.soft_normalize_adj(torch.rand(B, K, K, device=dev), torch.zeros(B, K, dtype=torch.uint8, device=dev))
+    Wp = ops.gcn_pack_weights(torch.randn(2 * dff, d, device=dev) * d ** -0.5, torch.randn(2 * dff, device=dev) * 0.1)
+    y = torch.empty(B, K, dff, device=dev)
+    us = graph_time(lambda: ops.gcn(x, adj, Wp, out=y))
+    nbytes = B * K * d * 4 + B * K * K * 4 + B * K + (2 * dff * d + 2 * dff) * 4 + B * K * dff * 4
+    out["gcn"] = {"shape": f"B={B} K={K} d={d} dff={dff}", "us": us, "bound": "hbm", "achieved": nbytes / us / 1e3,
+                  "peak": hbm, "unit": "GB/s", "frac": nbytes / us / 1e3 / hbm,
+                  "kernel": "ec::gf::gcn_fused_kernel" if ops.gcn_fused_ok(B, K, d, dff) else "gcn_aggregate_split + gemm_f16x3",
+                  "note": "3.0 algorithmic GFLOP (9.0 issued as split fp16): the tensor time alone is ~6.5 us, the byte roofline 3.0 us"}
+    Bi, H, N, D = 32, 12, 325, 64
+    if ops.attention_split_ok(D, N):
+        qkv2 = ops.split_f16(torch.randn(Bi * N, 3 * H * D, device=dev))
+        us = graph_time(lambda: ops.attention_packed_split(qkv2, Bi, N, H))
+        fl = 4.0 * N * N * D * H * Bi
+        out["vit_attention"] = {"shape": f"{Bi} images x {H} heads x {N} tokens x {D}", "us": us, "bound": "tensor",
+                                "achieved": fl / us / 1e6, "peak": tf, "unit": "TFLOP/s", "frac": fl / us / 1e6 / tf,
+                                "issued_frac": 3 * fl / us / 1e6 / tf, "kernel": "ec::atc::attention_tc_ts_kernel"}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from edgecape_b200 import _lib, ops, build_model
@@ -393,6 +444,8 @@ def run_ours(args):
                             else "ec::gemm_simt_kernel<128,128> (fp32 FFMA)",
                             "launches_timed": roof["launches"], "kernel_ms_per_step": roof["ms"] / args.steps,
                             "all_gemm_ms_per_step": roof["all_ms"] / args.steps, "peak_source": peak_src}
+    if rank == 0 and world == 1:
+        line["north_star_kernels"] = north_star_kernels(peaks)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_reference_rate(args, 3, 1)

@@ -492,7 +492,7 @@ def gcn_tc_ok(B, K):
 
 
 # one-kernel GCN (csrc/gcn_fused_tcgen05.cu); EDGECAPE_GCN_FUSED=0 keeps the aggregate kernel + GEMM pair
-GCN_FUSED = os.environ.get("EDGECAPE_GCN_FUSED", "0") != "0"
+GCN_FUSED = os.environ.get("EDGECAPE_GCN_FUSED", "1") != "0"
 
 
 def gcn_fused_ok(B, K, d, dff):
