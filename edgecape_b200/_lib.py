@@ -62,6 +62,7 @@ SIGNATURES = {
     "ec_workspace_bytes_gcn": (c_sz, [c_int, c_int, c_int, c_int]),
     "ec_gcn_fused_slice": (c_int, [c_int, c_int, c_int]),
     "ec_gcn_fused_set_trace": (c_int, [c_fp, c_int]),
+    "ec_gcn_fused_set_debug": (c_int, [c_int]),
     "ec_gcn_fused": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_support_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),

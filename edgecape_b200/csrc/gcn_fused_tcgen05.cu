@@ -148,6 +148,7 @@ struct Params {
   float out_scale;     // 1 / (power-of-two scale of the split weights)
   long long* trace;    // optional [trace_n][32] clock64 stamps of CTA phases (ec_gcn_fused_set_trace)
   int trace_n;
+  int dbg;             // experiments (ec_gcn_fused_set_debug; results are wrong when != 0): 1 = no global loads of A1 / X, 2 = no stores
 };
 
 // barrier indices (8 bytes each)
@@ -285,22 +286,23 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
     const float* Xb = p.X + (long long)b * K * d;
     const int ldw = 2 * d + 4;
     if (tid == 0) stamp(0);
-    const int ncx = d / 8;
-    constexpr int X_IT = 8;                                         // 128 rows x 32 chunks / 512 threads
+    // Work items are (row, 8-column chunk) pairs.  A thread keeps its chunk and steps over rows by a multiple of 8,
+    // so the swizzle term (row & 7) is loop invariant: one base address per thread, constant strides after that.
+    const int ncx = d / 8;                                           // chunks per X row: 8, 16 or 32
+    const int xs = 31 - __clz(ncx);
+    const int xv0 = tid >> xs, xc = tid & (ncx - 1), xstep = WORKERS >> xs;   // first row, chunk, rows per step
+    constexpr int X_IT = 8;                                          // 128 rows x 32 chunks / 512 threads
+    const float* xsrc = Xb + (long long)xv0 * d + xc * 8;
+    const long long xstride = (long long)xstep * d;
     float4 q[X_IT][2];
     auto load_x = [&](int u0, int u1) {
-      const int items = k16 * ncx;
 #pragma unroll
       for (int u = u0; u < u1; ++u) {
-        const int it = tid + u * WORKERS;
         q[u][0] = q[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (it < items) {
-          const int v = it / ncx, c = it - v * ncx;
-          if (v < K) {
-            const float4* src = reinterpret_cast<const float4*>(Xb + (long long)v * d + c * 8);
-            q[u][0] = __ldg(src);
-            q[u][1] = __ldg(src + 1);
-          }
+        if (xv0 + u * xstep < K && !(p.dbg & 1)) {
+          const float4* src = reinterpret_cast<const float4*>(xsrc + u * xstride);
+          q[u][0] = __ldg(src);
+          q[u][1] = __ldg(src + 1);
         }
       }
     };
@@ -309,16 +311,16 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
     {
       const int nc = k16 / 8;
       const bool vec = (K & 3) == 0;
-      const int c = tid & 15;
-      constexpr int A1_IT = (128 * 16 + WORKERS - 1) / WORKERS;   // K <= 128
+      const int c = tid & 15, w0 = tid >> 4;
+      constexpr int A1_IT = (128 * 16 + WORKERS - 1) / WORKERS;   // K <= 128; 32 rows per step
+      const float* asrc = a1p + (long long)w0 * K + c * 8;
       float v[A1_IT][8];
 #pragma unroll
       for (int i = 0; i < A1_IT; ++i) {
-        const int w = (tid + i * WORKERS) >> 4;
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[i][u] = 0.f;
-        if (w < K) {
-          const float* src = a1p + (long long)w * K + c * 8;
+        if (w0 + 32 * i < K && !(p.dbg & 1)) {
+          const float* src = asrc + (long long)(32 * i) * K;
           if (vec) {
             if (c * 8 < K) {
               const float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
@@ -337,9 +339,10 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
       }
       // the first half of the X loads is issued here, behind the A1 loads and ahead of any use
       load_x(0, X_IT / 2);
+      uint8_t* adst = gbase + (a1 - base) + (uint32_t)(c >> 3) * TS + swz(w0, c & 7);
 #pragma unroll
       for (int i = 0; i < A1_IT; ++i) {
-        const int w = (tid + i * WORKERS) >> 4;
+        const int w = w0 + 32 * i;
         float sacc = ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
@@ -348,30 +351,27 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
           if (c < nc) {
             uint4 hi, lo;
             split8(v[i], hi, lo);
-            const uint32_t off = (uint32_t)(c >> 3) * TS + swz(w, c & 7);
-            *reinterpret_cast<uint4*>(gbase + (a1 - base) + off) = hi;
-            *reinterpret_cast<uint4*>(gbase + (a1 - base) + (uint32_t)kbs * TS + off) = lo;
+            *reinterpret_cast<uint4*>(adst + i * (32 * 128)) = hi;
+            *reinterpret_cast<uint4*>(adst + i * (32 * 128) + (uint32_t)kbs * TS) = lo;
           }
         }
       }
     }
     if (tid == 0) stamp(2);
-    // X -> [v][64-column] tiles (hi tiles [0, ng), lo tiles [ng, 2 ng)), rows [K, k16) zero; up to 8 items (one
-    // 8-column chunk of one row each) per thread, all loads in flight before the first conversion
-    load_x(X_IT / 2, X_IT);                     // second half: in flight while the first half is converted
+    // X -> [v][64-column] tiles (hi tiles [0, ng), lo tiles [ng, 2 ng)), rows [K, k16) zero; up to 8 items per
+    // thread, the second half of the loads in flight while the first half is converted
+    load_x(X_IT / 2, X_IT);
     {
-      const int items = k16 * ncx;
+      uint8_t* xdst = gbase + (xb - base) + (uint32_t)(xc >> 3) * TS + swz(xv0, xc & 7);
+      const uint32_t lo_off = (uint32_t)ng * TS;
 #pragma unroll
       for (int u = 0; u < X_IT; ++u) {
-        const int it = tid + u * WORKERS;
-        if (it >= items) continue;
-        const int v = it / ncx, c = it - v * ncx;
+        if (xv0 + u * xstep >= k16) continue;
         const float f[8] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w, q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w};
         uint4 hi, lo;
         split8(f, hi, lo);
-        const uint32_t off = (uint32_t)(c >> 3) * TS + swz(v, c & 7);
-        *reinterpret_cast<uint4*>(gbase + (xb - base) + off) = hi;
-        *reinterpret_cast<uint4*>(gbase + (xb - base) + (uint32_t)ng * TS + off) = lo;
+        *reinterpret_cast<uint4*>(xdst + (uint32_t)(u * xstep) * 128u) = hi;
+        *reinterpret_cast<uint4*>(xdst + (uint32_t)(u * xstep) * 128u + lo_off) = lo;
       }
     }
     proxy_fence();
@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
         y[2] = fmaxf(fmaf(a4.z, p.out_scale, fmaf(a0v, bb0.z, rsv * bb1.z)), 0.f);
         y[3] = fmaxf(fmaf(a4.w, p.out_scale, fmaf(a0v, bb0.w, rsv * bb1.w)), 0.f);
         const long long grow = (long long)b * K + orow;
+        if (p.dbg & 2) continue;
         if (p.Y) *reinterpret_cast<float4*>(p.Y + grow * p.dff + n0 + gcol) = make_float4(y[0], y[1], y[2], y[3]);
         if (p.split_out) {
           uint32_t h01, l01, h23, l23;
@@ -513,7 +514,7 @@ constexpr uint32_t SMEM_LIMIT = 227u * 1024u;
 
 // slice width for (K, d, dff), or 0 when the fused kernel cannot take the shape
 inline int pick_slice(int K, int d, int dff) {
-  if (K < 1 || K > 128 || d < 64 || d > 256 || d % 64 || dff % 64) return 0;
+  if (K < 1 || K > 128 || (d != 64 && d != 128 && d != 256) || dff % 64) return 0;
   const int k16 = (K + 15) / 16 * 16;
   const int cand[3] = {192, 128, 64};
   for (int i = 0; i < 3; ++i) {
@@ -537,13 +538,19 @@ extern "C" int ec_gcn_fused_set_trace(void* buf, int n_ctas) {   // profiling ho
   return EC_OK;
 }
 
+static int gf_debug = 0;
+extern "C" int ec_gcn_fused_set_debug(int flags) {   // bring-up / profiling experiments only (results are wrong when != 0)
+  gf_debug = flags;
+  return EC_OK;
+}
+
 extern "C" int ec_gcn_fused_slice(int K, int d, int dff) { return gf::pick_slice(K, d, dff); }
 
 extern "C" int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* W2, int Kp, float w_scale,
                             float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream) {
   EC_REQUIRE(X && adj && Wp && W2 && (Y || split_out), "ec_gcn_fused: null pointer");
   const int NS = gf::pick_slice(K, d, dff);
-  EC_REQUIRE(NS > 0, "ec_gcn_fused: unsupported shape (K <= 128, d in {64,128,192,256}, dff %% 64 == 0, shared memory)");
+  EC_REQUIRE(NS > 0, "ec_gcn_fused: unsupported shape (K <= 128, d in {64,128,256}, dff %% 64 == 0, shared memory)");
   EC_REQUIRE(Kp % 64 == 0 && Kp >= 2 * d, "ec_gcn_fused: Kp must be a multiple of 64 and >= 2d");
   EC_REQUIRE(w_scale > 0.f, "ec_gcn_fused: bad weight scale");
   EC_REQUIRE(aligned16(X) && aligned16(adj) && aligned16(W2) && (!Y || aligned16(Y)) && (!split_out || aligned16(split_out)),
@@ -563,7 +570,7 @@ extern "C" int ec_gcn_fused(const float* X, const float* adj, const float* Wp, c
   gf::Params p;
   p.X = X; p.adj = adj; p.Wp = Wp; p.Y = Y; p.split_out = (__half*)split_out; p.split_kp = split_kp;
   p.K = K; p.d = d; p.dff = dff; p.NS = NS; p.k16 = k16; p.Kp = Kp; p.out_scale = 1.0f / w_scale;
-  p.trace = gf_trace; p.trace_n = gf_trace_n;
+  p.trace = gf_trace; p.trace_n = gf_trace_n; p.dbg = gf_debug;
   launch_pdl(gf::gcn_fused_kernel, dim3(dff / NS, B), dim3(gf::THREADS), (size_t)smem, (cudaStream_t)stream, tmW, p);
   return check_launch("ec_gcn_fused");
 }

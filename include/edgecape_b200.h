@@ -232,8 +232,9 @@ int ec_gcn_aggregate_split(const float* X, const float* adj, void* Z2, int B, in
  * Wp * w_scale (ec_split_f16; Kp = 2d+4 rounded up to 64, w_scale a power of two); the bias columns are taken
  * from the fp32 Wp.  Y [B,K,dff] and / or split_out [B*K, 2*split_kp] (hi | lo of Y) are written.
  * ec_gcn_fused_slice returns the channel-slice width the kernel would use, or 0 when it cannot take the shape
- * (it needs K <= 128, d a multiple of 64 up to 256, dff a multiple of 64, and the tiles to fit 227 KB). */
+ * (it needs K <= 128, d in {64, 128, 256}, dff a multiple of 64, and the tiles to fit 227 KB). */
 int ec_gcn_fused_slice(int K, int d, int dff);
+int ec_gcn_fused_set_debug(int flags);               /* profiling experiments only: 1 = skip the A1 / X loads, 2 = skip the stores */
 int ec_gcn_fused_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] int64 clock stamps per CTA, NULL = off */
 int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* W2, int Kp, float w_scale,
                  float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);

@@ -41,4 +41,10 @@ def main(B=64, K=100, d=256, dff=384):
 
 if __name__ == "__main__":
     main()
+    if "--experiments" in sys.argv:
+        for flags, what in ((1, "no global loads of A1 / X"), (2, "no epilogue stores"), (3, "neither")):
+            print(f"--- experiment: {what}")
+            _lib.call("ec_gcn_fused_set_debug", flags)
+            main()
+        _lib.call("ec_gcn_fused_set_debug", 0)
     main(B=16)
