@@ -25,6 +25,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.ec_version() >= 100
 
 
+def test_fused_gcn_shape_gate():
+    """Host-side shape gate of the one-kernel GCN (no kernel is launched): slice width per (K, d, dff), 0 = the
+    two-launch path takes the shape."""
+    lib = _lib.load()
+    assert lib.ec_gcn_fused_slice(100, 256, 384) == 192       # configs[1] decoder layers
+    assert lib.ec_gcn_fused_slice(100, 256, 768) == 192       # skeleton layers at ViT-B (dff = C)
+    assert lib.ec_gcn_fused_slice(100, 256, 1024) == 128      # ... at ViT-L
+    assert lib.ec_gcn_fused_slice(64, 64, 64) == 64
+    assert lib.ec_gcn_fused_slice(112, 256, 384) == 192
+    assert lib.ec_gcn_fused_slice(128, 256, 384) == 64        # 16 KB tiles: only the narrow slice fits 227 KB
+    assert lib.ec_gcn_fused_slice(200, 256, 384) == 0         # configs[4]: K > 128
+    assert lib.ec_gcn_fused_slice(100, 192, 384) == 0         # d must be 64, 128 or 256
+    assert lib.ec_gcn_fused_slice(100, 256, 100) == 0
+
+
 def test_registries_hold_the_reference_names():
     assert "EdgeCape" in registry.POSENETS
     assert "TwoStageHead" in registry.HEADS and "SkeletonPredictor" in registry.HEADS

@@ -213,7 +213,8 @@ def test_gcn_matches_oracle(B, K, d, dff, tensor_cores, monkeypatch):
         close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), what="gcn split")
 
 
-@pytest.mark.parametrize("B,K,d,dff", [(64, 100, 256, 384), (5, 97, 128, 192), (3, 112, 256, 768), (2, 64, 64, 64)])
+@pytest.mark.parametrize("B,K,d,dff", [(64, 100, 256, 384), (5, 97, 128, 192), (3, 112, 256, 768), (2, 64, 64, 64),
+                                      (3, 128, 256, 384), (4, 16, 256, 384), (70, 1, 64, 128)])
 def test_gcn_fused_kernel(B, K, d, dff, monkeypatch):
     """One-kernel GCN (gcn_fused_tcgen05.cu) vs the fp64 oracle and vs the two-kernel tensor-core path: general
     (non 0/1) diagonal plane, masked rows, fp32 and split outputs."""
