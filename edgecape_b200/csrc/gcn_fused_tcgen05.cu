@@ -211,12 +211,72 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // ---- workers: every global load of the fill is issued BEFORE the CTA-wide setup barrier, so the first-touch
+  // latency overlaps the TMEM allocation and the barrier (values are consumed in the worker branch below)
+  const int tid = threadIdx.x;
+  const bool worker = warp < WORKERS / 32;
+  const long long KK = (long long)K * K;
+  const float* a0p = p.adj + (long long)b * 2 * KK;
+  const float* a1p = a0p + KK;
+  const float* Xb = p.X + (long long)b * K * d;
+  // Work items are (row, 8-column chunk) pairs.  A thread keeps its chunk and steps over rows by a multiple of 8,
+  // so the swizzle term (row & 7) is loop invariant: one base address per thread, constant strides after that.
+  const int ncx = d / 8;                                           // chunks per X row: 8, 16 or 32
+  const int xs = 31 - __clz(ncx);
+  const int xv0 = tid >> xs, xc = tid & (ncx - 1), xstep = WORKERS >> xs;   // first row, chunk, rows per step
+  constexpr int X_IT = 8;                                          // 128 rows x 32 chunks / 512 threads
+  const float* xsrc = Xb + (long long)xv0 * d + xc * 8;
+  const long long xstride = (long long)xstep * d;
+  float4 q[X_IT][2];
+  auto load_x = [&](int u0, int u1) {
+#pragma unroll
+    for (int u = u0; u < u1; ++u) {
+      q[u][0] = q[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (xv0 + u * xstep < K && !(p.dbg & 1)) {
+        const float4* src = reinterpret_cast<const float4*>(xsrc + u * xstride);
+        q[u][0] = __ldg(src);
+        q[u][1] = __ldg(src + 1);
+      }
+    }
+  };
+  // A1: 16 lanes per row (one 8-column chunk each), 32 rows per step
+  const int ac = tid & 15, aw0 = tid >> 4;
+  constexpr int A1_IT = (128 * 16 + WORKERS - 1) / WORKERS;       // K <= 128
+  float av[A1_IT][8];
+  if (worker) {
+    pdl_wait();
+    const bool vec = (K & 3) == 0;
+    const float* asrc = a1p + (long long)aw0 * K + ac * 8;
+#pragma unroll
+    for (int i = 0; i < A1_IT; ++i) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) av[i][u] = 0.f;
+      if (aw0 + 32 * i < K && !(p.dbg & 1)) {
+        const float* src = asrc + (long long)(32 * i) * K;
+        if (vec) {
+          if (ac * 8 < K) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
+            av[i][0] = q0.x; av[i][1] = q0.y; av[i][2] = q0.z; av[i][3] = q0.w;
+          }
+          if (ac * 8 + 4 < K) {
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            av[i][4] = q1.x; av[i][5] = q1.y; av[i][6] = q1.z; av[i][7] = q1.w;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (ac * 8 + u < K) av[i][u] = __ldg(src + u);
+        }
+      }
+    }
+    load_x(0, X_IT / 2);          // first half of the X loads, behind the A1 loads and ahead of any use
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
   pdl_launch_dependents();
-  pdl_wait();
+  if (!worker) pdl_wait();
 
   if (warp == WORKERS / 32 + 1) {
     // ------------------------------------------------------------------ TMA producer: the W ring
@@ -279,66 +339,13 @@ __global__ void __launch_bounds__(THREADS, 1) gcn_fused_kernel(const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ workers (16 warps)
-    const int tid = threadIdx.x;
-    const long long KK = (long long)K * K;
-    const float* a0p = p.adj + (long long)b * 2 * KK;
-    const float* a1p = a0p + KK;
-    const float* Xb = p.X + (long long)b * K * d;
     const int ldw = 2 * d + 4;
     if (tid == 0) stamp(0);
-    // Work items are (row, 8-column chunk) pairs.  A thread keeps its chunk and steps over rows by a multiple of 8,
-    // so the swizzle term (row & 7) is loop invariant: one base address per thread, constant strides after that.
-    const int ncx = d / 8;                                           // chunks per X row: 8, 16 or 32
-    const int xs = 31 - __clz(ncx);
-    const int xv0 = tid >> xs, xc = tid & (ncx - 1), xstep = WORKERS >> xs;   // first row, chunk, rows per step
-    constexpr int X_IT = 8;                                          // 128 rows x 32 chunks / 512 threads
-    const float* xsrc = Xb + (long long)xv0 * d + xc * 8;
-    const long long xstride = (long long)xstep * d;
-    float4 q[X_IT][2];
-    auto load_x = [&](int u0, int u1) {
-#pragma unroll
-      for (int u = u0; u < u1; ++u) {
-        q[u][0] = q[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xv0 + u * xstep < K && !(p.dbg & 1)) {
-          const float4* src = reinterpret_cast<const float4*>(xsrc + u * xstride);
-          q[u][0] = __ldg(src);
-          q[u][1] = __ldg(src + 1);
-        }
-      }
-    };
-    // A1 -> K-major tiles (hi tiles [0, kbs), lo tiles [kbs, 2 kbs)), columns >= K zero.  16 lanes per row (one
-    // 8-column chunk each; every load of the thread is issued before the first use), row sums by shuffles.
+    // A1 -> K-major tiles (hi tiles [0, kbs), lo tiles [kbs, 2 kbs)), columns >= K zero; row sums by shuffles
     {
       const int nc = k16 / 8;
-      const bool vec = (K & 3) == 0;
-      const int c = tid & 15, w0 = tid >> 4;
-      constexpr int A1_IT = (128 * 16 + WORKERS - 1) / WORKERS;   // K <= 128; 32 rows per step
-      const float* asrc = a1p + (long long)w0 * K + c * 8;
-      float v[A1_IT][8];
-#pragma unroll
-      for (int i = 0; i < A1_IT; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[i][u] = 0.f;
-        if (w0 + 32 * i < K && !(p.dbg & 1)) {
-          const float* src = asrc + (long long)(32 * i) * K;
-          if (vec) {
-            if (c * 8 < K) {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
-              v[i][0] = q0.x; v[i][1] = q0.y; v[i][2] = q0.z; v[i][3] = q0.w;
-            }
-            if (c * 8 + 4 < K) {
-              const float4 q1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-              v[i][4] = q1.x; v[i][5] = q1.y; v[i][6] = q1.z; v[i][7] = q1.w;
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (c * 8 + u < K) v[i][u] = __ldg(src + u);
-          }
-        }
-      }
-      // the first half of the X loads is issued here, behind the A1 loads and ahead of any use
-      load_x(0, X_IT / 2);
+      const int c = ac, w0 = aw0;
+      float (&v)[A1_IT][8] = av;
       uint8_t* adst = gbase + (a1 - base) + (uint32_t)(c >> 3) * TS + swz(w0, c & 7);
 #pragma unroll
       for (int i = 0; i < A1_IT; ++i) {
