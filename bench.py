@@ -442,6 +442,7 @@ def run_ours(args):
                             "kernel": ("ec::tc::gemm_f16x3_kernel (tcgen05 kind::f16, 3-product split-fp16, fp32 TMEM accumulate; "
                                        "algorithmic FLOPs = 1/3 of the tensor-pipe FLOPs issued)") if roof["tensor_core_launches"]
                             else "ec::gemm_simt_kernel<128,128> (fp32 FFMA)",
+                            "issued_frac": (3 * ach / peak_tf) if roof["tensor_core_launches"] else None,
                             "launches_timed": roof["launches"], "kernel_ms_per_step": roof["ms"] / args.steps,
                             "all_gemm_ms_per_step": roof["all_ms"] / args.steps, "peak_source": peak_src}
     if rank == 0 and world == 1:
