@@ -4,16 +4,19 @@
 //
 // CTA = (sample b, slice of NS output channels).  Everything runs on the tensor cores at fp32-grade accuracy
 // (three fp16 products per fp32 product, see gemm_tcgen05.cu):
-//   fill    8 worker warps read A1[b] and X[b] once (coalesced float4), split them into fp16 hi | lo and write
-//           128B-swizzled shared-memory tiles: A1 as a K-major A operand, X as [v][64 columns] row tiles.
+//   fill    16 worker warps read A1[b] and X[b] once (coalesced float4, every load issued ahead of the CTA setup
+//           barrier), split them into fp16 hi | lo and write 128B-swizzled shared-memory tiles: A1 as a K-major
+//           A operand, X as [v][64 columns] row tiles; row sums of A1 by 16-lane shuffles on the way.
 //   GEMM 1  D1[128 x d] = A1 . X in TMEM; the X tiles are consumed as an MN-major B operand (N = d in one UMMA).
 //   scale   X tiles are rescaled in place by a0[w] (a no-op for the usual a0 = 1): the very same bytes are now
 //           the K-major A operand a0*X of GEMM 2 (an MN-major [v][c] tile and a K-major [w][c] tile coincide).
 //   GEMM 2  acc[128 x NS] = (a0 X) . W0^T  (k-blocks 0..d/64-1)  +  (A1 X) . W1^T  (k-blocks d/64..2d/64-1);
 //           W streams through a two-stage TMA ring from the pre-split packed weights; while the first half runs
 //           the workers drain D1 (tcgen05.ld), split it and write it over the X tile whose k-block has retired.
-//   epilogue  relu(acc / w_scale + a0[w] b0[n] + rowsum(A1[w,:]) b1[n]) in fp32, written as fp32 rows and / or
-//           as the split-fp16 A operand of the ffn2 GEMM that follows.
+//   epilogue  relu(acc / w_scale + a0[w] b0[n] + rowsum(A1[w,:]) b1[n]) in fp32 through a per-warp staging tile
+//           (64 B row segments), written as fp32 rows and / or as the split-fp16 A operand of the ffn2 GEMM.
+// Measured (profiles/r01_ah_gcn_fused.md): 15.5 us at B = 64, K = 100, d = 256, dff = 384 (two-launch path 52.8 us);
+// tensor pipe 13.3 K of the 24 K clocks of a CTA, then L2 write ingest (epilogue) and the fill.
 // Shared memory (K = 100, d = 256, NS = 192): X tiles 8 x 14 KB, A1 tiles 4 x 14 KB (recycled as W stage 1 once
 // GEMM 1 has retired), W stage 0 48 KB.  Tiles are k16 = ceil16(K) rows tall; an A operand always spans 128 rows,
 // so the MMA reads past a tile into its neighbour: that only produces garbage in accumulator rows >= K, which
