@@ -63,6 +63,8 @@ SIGNATURES = {
     "ec_gcn_fused_slice": (c_int, [c_int, c_int, c_int]),
     "ec_gcn_fused_set_trace": (c_int, [c_fp, c_int]),
     "ec_gcn_fused_set_debug": (c_int, [c_int]),
+    "ec_split_f16f8": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_int, c_fp]),
+    "ec_gemm_f16f8": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_fp, c_int, c_fp]),
     "ec_gcn_fused": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_support_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),

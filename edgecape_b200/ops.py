@@ -168,6 +168,36 @@ def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=N
     return (out, so) if split_out else out
 
 
+# ---- EXPERIMENTAL (not on the default path, not yet validated on hardware): cross terms on e4m3 tensor cores
+def split_f16f8(x, scale=1.0, role=0):
+    """fp32 [M,K] rows -> uint8 [M, 4*Kp] = [hi16 | hi8 | lo8] planes (csrc/gemm_f16f8_tcgen05.cu); role 0 = A, 1 = B."""
+    _chk(x, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, K = x.shape
+    Kp = _kp(K)
+    out = empty(M, 4 * Kp, dtype=torch.uint8, device=x.device)
+    _lib.call("ec_split_f16f8", _p(x), _p(out), M, K, x.stride(0), Kp, float(scale), int(role), _stream())
+    return out, Kp
+
+
+def gemm_f16f8(x, w, bias=None, act=ACT_NONE, out=None):
+    """out = act(x @ w^T + bias) with a_hi.b_hi on fp16 and both cross terms on e4m3 UMMAs (experimental)."""
+    _chk(x, "x"); _chk(w, "w"); _chk(bias, "bias")
+    amax = float(w.detach().abs().max())
+    scale = 1.0
+    if amax > 0 and math.isfinite(amax):
+        scale = 2.0 ** max(-8, min(14, math.floor(math.log2(16384.0 / amax))))
+    a3, Kp = split_f16f8(x, 1.0, 0)
+    b3, Kpb = split_f16f8(w, scale, 1)
+    assert Kp == Kpb
+    M, N = x.shape[0], w.shape[0]
+    if out is None:
+        out = empty(M, N, device=x.device)
+    assert out.stride(1) == 1
+    _lib.call("ec_gemm_f16f8", _p(a3), _p(b3), _p(out), M, N, Kp, out.stride(0), 1.0 / scale, _p(bias), act, _stream())
+    return out
+
+
 def _tc_ok(x, w, residual):
     if not TENSOR_CORES:
         return False

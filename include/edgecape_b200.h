@@ -239,6 +239,15 @@ int ec_gcn_fused_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] 
 int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* W2, int Kp, float w_scale,
                  float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);
 
+/* EXPERIMENTAL (opt-in; compiled for sm_100a but not yet validated on hardware -- DESIGN.md section 9 item 1):
+ * fp32-grade GEMM with the two cross terms on e4m3 tensor cores (2 instead of 3 units of tensor time).
+ * ec_split_f16f8 writes rows [hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp bytes] (4*Kp bytes) of X*scale;
+ * role 0 = A operand (activations; pass scale 1), role 1 = B operand (weights; scale = the power-of-two weight
+ * scale).  ec_gemm_f16f8: C[M,N] = act(out_scale * A.B^T + bias), out_scale = 1 / weight scale. */
+int ec_split_f16f8(const float* X, void* out, int M, int K, int ldx, int Kp, float scale, int role, void* stream);
+int ec_gemm_f16f8(const void* A3, const void* B3, float* C, int M, int N, int Kp, int ldc, float out_scale,
+                  const float* bias, int act, void* stream);
+
 /* ----------------------------------------------------------------------------- head ops
  * support-keypoint pooling weights (head.py:175-184, exact by linearity):
  * Tw[b,k,s] = scale[b,k] / (sum(t[b,k]) + 1e-8) * sum_p t[b,k,p] U[p,s], U = bilinear

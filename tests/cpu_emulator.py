@@ -383,6 +383,38 @@ def ec_gcn_fused(X, adj, Wp, W2, Kp, w_scale, Y, split_out, split_kp, B, K, d, d
         _write_split(split_out, split_kp, y)
 
 
+def _e4m3(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).to(torch.float32).numpy()
+
+
+def ec_split_f16f8(X, out, M, K, ldx, Kp, scale, role, stream):
+    """[hi16 | hi8 | lo8] planes (gemm_f16f8_tcgen05.cu): role 0 = activations, 1 = weights."""
+    x = arr(X, (M, K), (ldx, 1)) * np.float32(scale)
+    hi = x.astype(np.float16)
+    lo = x - hi.astype(np.float32)
+    s_hi, s_lo = (2.0 ** -11, 1.0) if role else (1.0, 2.0 ** 11)
+    o = arr(out, (M, 4 * Kp), dtype=np.uint8)
+    o[...] = 0
+    o[:, :2 * Kp].view(np.float16)[:, :K] = hi
+    f8 = lambda a: torch.from_numpy(_e4m3(a)).to(torch.float8_e4m3fn).view(torch.uint8).numpy()
+    o[:, 2 * Kp:2 * Kp + K] = f8(hi.astype(np.float32) * np.float32(s_hi))
+    o[:, 3 * Kp:3 * Kp + K] = f8(lo * np.float32(s_lo))
+
+
+def ec_gemm_f16f8(A3, B3, C, M, N, Kp, ldc, out_scale, bias, act, stream):
+    def planes(ptr, rows):
+        o = arr(ptr, (rows, 4 * Kp), dtype=np.uint8)
+        h16 = o[:, :2 * Kp].view(np.float16).astype(np.float32)
+        f = lambda b: torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).to(torch.float32).numpy()
+        return h16, f(o[:, 2 * Kp:3 * Kp]), f(o[:, 3 * Kp:])
+    a16, ah8, al8 = planes(A3, M)
+    b16, bh8, bl8 = planes(B3, N)
+    y = T((al8 @ bh8.T + ah8 @ bl8.T + a16 @ b16.T) * np.float32(out_scale))
+    if bias:
+        y = y + T(arr(bias, (N,)))
+    arr(C, (M, N), (ldc, 1))[...] = _act(y, act).numpy()
+
+
 def ec_support_weights(target, rowscale, Tw, ldtw, BK, hm_h, hm_w, h, w, stream):
     t = T(arr(target, (BK, hm_h * hm_w)))
     # U[p, s]: bilinear interpolation matrix = upsampled one-hot basis images
