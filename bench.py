@@ -38,17 +38,44 @@ sys.path.insert(0, REPO)
 METRIC = "query images/sec (1-shot, 256x256, ViT-B/14, 100 kpts)"
 WORKLOAD = "configs[1]: 1-shot synthetic 256x256, DINOv2-B/14, 100-kpt random skeleton, batch 16 per GPU"
 
+# --config presets: BASELINE.json configs[1..4] as per-GPU slices (the driver's default run is c2 = configs[1]; the
+# others are parity-test cases whose per-GPU throughput is recorded under profiles/, not bench lines of the round)
+PRESETS = {
+    "c2": dict(backbone="dinov2_vitb14", image_size=256, kpts=100, shots=1, batch=16, skeleton="tree+extra",
+               workload=WORKLOAD, metric=METRIC),
+    "c3": dict(backbone="dinov2_vitb14", image_size=256, kpts=100, shots=1, batch=16, skeleton="tree+extra",
+               workload="configs[2]: 1-shot synthetic 256x256, DINOv2-B/14, random 100-kpt skeleton, batch 128 sharded "
+                        "over 8 GPUs = 16 per GPU"),
+    "c4": dict(backbone="dinov2_vitb14", image_size=256, kpts=100, shots=5, batch=8, skeleton="tree+extra",
+               workload="configs[3]: 5-shot synthetic 256x256, DINOv2-B/14, 100 kpts, batch 64 over 8 GPUs = 8 per GPU"),
+    "c5": dict(backbone="dinov2_vitl14", image_size=384, kpts=200, shots=1, batch=4, skeleton="full",
+               workload="configs[4]: dense-graph stress, 1-shot synthetic 384x384, DINOv2-L/14, 200-kpt fully-connected "
+                        "skeleton (19 900 edges), batch 32 over 8 GPUs = 4 per GPU"),
+}
+
 
 def describe(args):
-    """(metric, workload) strings: BASELINE.json's wording for the default arguments (configs[1]), an explicit
-    description otherwise so that a non-default run can never be mistaken for the headline."""
+    """(metric, workload) strings: BASELINE.json's wording for the default arguments (configs[1]), the preset's
+    wording for --config, an explicit description otherwise so that a non-default run can never be mistaken for the
+    headline."""
+    generic = (f"query images/sec ({args.shots}-shot, {args.image_size}x{args.image_size}, {args.backbone}, "
+               f"{args.kpts} kpts)")
+    if args.config:
+        pr = PRESETS[args.config]
+        return pr.get("metric", generic), pr["workload"]
     default = (args.backbone == "dinov2_vitb14" and args.image_size == 256 and args.kpts == 100 and args.shots == 1 and
-               args.batch == 16)
+               args.batch == 16 and args.skeleton == "tree+extra")
     if default:
         return METRIC, WORKLOAD
-    return (f"query images/sec ({args.shots}-shot, {args.image_size}x{args.image_size}, {args.backbone}, {args.kpts} kpts)",
-            f"NON-DEFAULT: {args.shots}-shot synthetic {args.image_size}x{args.image_size}, {args.backbone}, "
-            f"{args.kpts}-kpt random skeleton, batch {args.batch} per GPU")
+    return (generic, f"NON-DEFAULT: {args.shots}-shot synthetic {args.image_size}x{args.image_size}, {args.backbone}, "
+                     f"{args.kpts}-kpt {args.skeleton} skeleton, batch {args.batch} per GPU")
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line -- identical for both arms (`--impl ours` / `--impl reference`)."""
+    return {"workload": describe(args)[1], "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "image_size": args.image_size, "keypoints": args.kpts, "shots": args.shots, "backbone": args.backbone,
+            "skeleton": args.skeleton}
 
 
 def parse():
@@ -56,6 +83,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default=None, choices=sorted(PRESETS),
+                    help="BASELINE.json configs[1..4] as per-GPU slices (overrides the shape arguments)")
     ap.add_argument("--batch", type=int, default=16, help="queries per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--backbone", default="dinov2_vitb14")
@@ -64,10 +93,21 @@ def parse():
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--kpts", type=int, default=100)
     ap.add_argument("--shots", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=8, help="queries per CPU-baseline step")
+    ap.add_argument("--skeleton", default="tree+extra", choices=["tree+extra", "chain", "full"])
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="queries per CPU-baseline step (0 = min(batch, 16), BASELINE.md section 3)")
+    ap.add_argument("--sustained-seconds", type=float, default=10.0,
+                    help="length of the extra sustained-throughput pass (clock sampler on); 0 disables it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config:
+        for k, v in PRESETS[args.config].items():
+            if k not in ("workload", "metric"):
+                setattr(args, k, v)
+    if args.cpu_sample <= 0:
+        args.cpu_sample = min(args.batch, 16)
+    return args
 
 
 def q_per_step_local(B, world):
@@ -91,45 +131,85 @@ def flops_per_query(cfg, image_size, K, shots):
 
 
 # --------------------------------------------------------------------------- CPU baseline
+def cpu_episode(args):
+    """The CPU arm's batch: min(B, 16) queries of the same workload; with the default batch
+    it is exactly rank 0's first GPU batch (same generator arguments)."""
+    from edgecape_b200.synthetic import make_episode
+    return make_episode(batch=max(1, args.cpu_sample), image_size=args.image_size, num_kpts=args.kpts,
+                        shots=args.shots, seed=1234, skeleton=args.skeleton)
+
+
 def cpu_reference_rate(args, steps, warmup):
     """Times oracle.edgecape_oracle.detector_forward_test (CPU restatement of the reference's
-    forward_test, pinned to the unmodified reference by tests/golden) on the host cores."""
+    forward_test, pinned to the unmodified reference by tests/golden) on the host cores.
+    Returns (cpu_baseline object, ms per step, the oracle's outputs on that batch)."""
     from edgecape_b200.config import state_dict_shapes
-    from edgecape_b200.synthetic import make_episode, make_state_dict
+    from edgecape_b200.synthetic import make_state_dict
     from oracle import edgecape_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = model_cfg(args.backbone)
     sd = make_state_dict(state_dict_shapes(cfg), 0)
-    b = max(1, args.cpu_sample)
-    data = make_episode(batch=b, image_size=args.image_size, num_kpts=args.kpts, shots=args.shots, seed=1234)
-    times = []
+    data = cpu_episode(args)
+    b = data["img_q"].shape[0]
+    times, out = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            edgecape_oracle.detector_forward_test(sd, cfg, data, torch.float32)
+            out = edgecape_oracle.detector_forward_test(sd, cfg, data, torch.float32)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     ms = 1e3 * float(np.mean(times))
     return dict(value=b / (ms / 1e3), unit="query images/s", cores=cores, kind="port",
                 sample=f"{b} queries/step x {steps} steps (+{warmup} warm-up) of the same workload, fp32, "
-                       f"torch CPU {cores} threads, oracle/edgecape_oracle.py"), ms
+                       f"torch CPU {cores} threads, oracle/edgecape_oracle.py"), ms, out
+
+
+def parity_against_oracle(model, args, want):
+    """The GPU path against the CPU oracle on the CPU arm's batch (= the first timed GPU batch at the default
+    arguments): relative-to-max error of the result dict through the public call (CUDA-graph engine, pinned copies),
+    and of the heat-map / proposals / per-layer coordinates through the eager path, whose arg-max keypoint indices
+    must equal the oracle's."""
+    data = cpu_episode(args)
+    res = model(return_loss=False, **data)
+    _, inter = model.predict(data["img_s"], data["target_s"], data["target_weight_s"], data["img_q"], data["img_metas"],
+                             return_intermediates=True)
+    errs = {}
+
+    def rel(a, w):
+        a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+        w = w.detach().float().cpu().numpy() if torch.is_tensor(w) else np.asarray(w)
+        return float(np.abs(a.astype(np.float64) - w).max() / (np.abs(w).max() + 1e-12))
+
+    for k in ("preds", "points", "skeleton"):
+        errs[k] = rel(res[k], want[k])
+    for k in ("similarity_map", "initial_proposals", "output", "adj"):
+        if k in inter and inter[k] is not None and k in want:
+            errs[k] = rel(inter[k], want[k])
+    am = inter["argmax"].detach().cpu().numpy().astype(np.int64)
+    wm = want["argmax"].detach().cpu().numpy().astype(np.int64)
+    return {"max_rel_err": max(errs.values()), "argmax_equal": bool(np.array_equal(am, wm)),
+            "argmax_compared": int(wm.size), "rel_err": errs, "queries": int(data["img_q"].shape[0]),
+            "bar": "1e-3 relative to the tensor's max magnitude, arg-max keypoint indices bit-exact",
+            "against": "oracle/edgecape_oracle.py fp32 on the same batch (pinned to the unmodified reference by tests/golden)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 10))
-    cb, ms = cpu_reference_rate(args, steps, warmup)
+    cb, ms, _ = cpu_reference_rate(args, steps, warmup)
     line = {
         "impl": "reference", "metric": describe(args)[0], "value": cb["value"], "unit": "query images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": describe(args)[1], "sample_queries_per_step": max(1, args.cpu_sample),
-                   "note": "reference's PyTorch-CPU forward_test restated in oracle/ (the reference itself cannot "
-                           "travel to the GPU box: mmcv/mmpose/hub DINOv2 are absent)"},
+        "config": workload_config(args, world),
+        "note": "reference's PyTorch-CPU forward_test restated in oracle/ (the reference itself cannot travel to the "
+                "GPU box: mmcv/mmpose/hub DINOv2 are absent); each step is one batch of min(per_gpu_batch, 16) queries "
+                "of the workload on all host threads",
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "query images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -295,7 +375,7 @@ def run_ours(args):
     B, R, K = args.batch, args.image_size, args.kpts
     NB = 4   # distinct input batches rotated through the timed region
     host = [make_episode(batch=B, image_size=R, num_kpts=K, shots=args.shots, seed=1234 + 97 * rank + i,
-                         pin_memory=True) for i in range(NB)]
+                         pin_memory=True, skeleton=args.skeleton) for i in range(NB)]
     devb = []
     for d in host:
         devb.append(dict(img_s=[t.to(dev) for t in d["img_s"]], img_q=d["img_q"].to(dev),
@@ -308,6 +388,7 @@ def run_ours(args):
     counters = torch.zeros(8, dtype=torch.float64, device=dev)
 
     from edgecape_b200.apis import iter_results
+    from edgecape_b200.parallel import allreduce_counters, summarize_pck
 
     def run_resident(start, n):
         """n steps on device-resident inputs.  Graph mode: the library's depth-2 pipeline (backbone of step i+1 beside
@@ -335,23 +416,31 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, timer=None):
+    def timed(fn, steps, warmup, timer=None, reduce=False):
         fn(0, warmup)
         barrier()
+        if reduce:
+            counters.zero_()
+            torch.cuda.synchronize()
         if timer is not None:
             timer.active = True
         l0 = _lib.launch_count()
-        t0 = time.perf_counter()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn(warmup, steps)
+        if reduce:
+            # the single collective of the path closes the last step INSIDE the timed region: the fp64 PCK
+            # counters of every rank, summed over NVLink by NCCL, ordered after the last step's counter kernel
+            if model.use_cuda_graph:
+                for g in model._graphs.values():
+                    torch.cuda.current_stream().wait_stream(g.head_stream)
+            allreduce_counters(counters)
         torch.cuda.synchronize()           # the pipeline's streams: every step has completed before the end event
         e.record()
         if timer is not None:
             timer.active = False
         barrier()
         ms = max(s.elapsed_time(e), 0.0)
-        wall_ms = (time.perf_counter() - t0) * 1e3
         launches = _lib.launch_count() - l0
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -363,7 +452,8 @@ def run_ours(args):
     W = max(3, args.warmup)
     with ClockSampler(local) as clocks:
         # (1) headline: the CUDA-graph replay path (what model(...) runs by default)
-        ms_total, _ = timed(run_resident, args.steps, W)
+        ms_total, _ = timed(run_resident, args.steps, W, reduce=True)
+        pck_counters = counters.clone()
         ms_e2e, _ = timed(run_e2e, args.steps, W)
         # (2) the same K steps launched eagerly, with a CUDA-event pair around every GEMM launch: per-kernel
         #     durations for the roofline, and the count of kernels one step launches (a graph replays them)
@@ -388,8 +478,16 @@ def run_ours(args):
                  "e2e_value_reference_batching": q_per_step_local(B, world) * args.steps / (ms_plain / 1e3),
                  "e2e_value_dedup_supports": q_per_step_local(B, world) * args.steps / (ms_dedup / 1e3),
                  "unit": "query images/s"}
-    from edgecape_b200.parallel import allreduce_counters, summarize_pck
-    allreduce_counters(counters)           # the single collective of the path: fp64 PCK counters (NCCL all-reduce)
+    # does the headline survive the power cap?  >= --sustained-seconds of back-to-back resident steps with the clock
+    # sampler running (a real evaluation is thousands of steps; the K-step headline region is ~0.1 s)
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(np.ceil(args.sustained_seconds * 1e3 / (ms_total / args.steps))))
+        with ClockSampler(local) as sus_clocks:
+            ms_sus, _ = timed(run_resident, n_sus, 2)
+        sc = sus_clocks.summary()
+        sustained = {"seconds": ms_sus / 1e3, "steps": n_sus, "value": B * world * n_sus / (ms_sus / 1e3),
+                     "unit": "query images/s", "ms_per_step": ms_sus / n_sus, "clocks": sc}
     torch.cuda.synchronize()
 
     peaks = {}
@@ -397,8 +495,14 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    # denominator: the per-launch GEMM timings come from a region of K eager steps -- well under a second, SM clocks at
+    # boost -- so the BURST figure is the honest peak there; the sustained figure is reported beside it
+    burst_region = ms_eager < 1000.0
+    peak_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_burst = float(peaks.get("bf16_tflops", 1590.0))
+    peak_tf = peak_burst if burst_region else peak_sus
+    which = "bf16_tflops (burst: timed region < 1 s)" if burst_region else "bf16_tflops_sustained (timed region >= 1 s)"
+    peak_src = (f"MEASURED_PEAKS.json {which} (of measured)" if peaks else f"fallback {peak_tf / 1e3:.2f} PFLOP/s, {which} (of fallback)")
     q_per_step = B * world
     value = q_per_step * args.steps / (ms_total / 1e3)
     e2e_value = q_per_step * args.steps / (ms_e2e / 1e3)
@@ -410,10 +514,9 @@ def run_ours(args):
         "metric": describe(args)[0], "value": value, "unit": "query images/s", "n_gpus": world, "steps": args.steps,
         "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": describe(args)[1], "per_gpu_batch": B, "global_batch": q_per_step, "image_size": R,
-                   "keypoints": K, "shots": args.shots, "backbone": args.backbone,
-                   "l2": "no explicit flush: weights (0.41 GB) + per-step activations exceed the 126 MB L2 and "
-                         f"inputs rotate over {NB} distinct batches"},
+        "config": workload_config(args, world),
+        "l2": "no explicit flush: weights (0.41 GB) + per-step activations exceed the 126 MB L2 and "
+              f"inputs rotate over {NB} distinct batches",
         "e2e": {"value": e2e_value, "unit": "query images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "edgecape_b200.apis.iter_results (the single_gpu_test loop): model.forward_test_async per batch, "
@@ -424,10 +527,14 @@ def run_ours(args):
                                                       "i+1 beside the head of step i"),
         "eager_ms_per_step": ms_eager / args.steps,
         "clocks": clocks.summary(),
-        "pck_counters": [float(x) for x in counters.cpu().tolist()[:6]],
-        "pck_vs_random_gt": summarize_pck(counters[:6]),
+        "collective": "one all_reduce(SUM) of the fp64 PCK counters, inside the timed region after the last step"
+                      + (" (NCCL)" if world > 1 else " (no-op at world size 1)"),
+        "pck_counters": [float(x) for x in pck_counters.cpu().tolist()[:6]],
+        "pck_vs_random_gt": summarize_pck(pck_counters[:6]),
         "algorithmic_gflop_per_query": flops_per_query(cfg, R, K, args.shots) / 1e9,
     }
+    if sustained is not None:
+        line["sustained"] = sustained
     if dedup is not None:
         line["support_dedup_demo"] = dedup
     traffic = None
@@ -443,14 +550,16 @@ def run_ours(args):
                                        "algorithmic FLOPs = 1/3 of the tensor-pipe FLOPs issued)") if roof["tensor_core_launches"]
                             else "ec::gemm_simt_kernel<128,128> (fp32 FFMA)",
                             "issued_frac": (3 * ach / peak_tf) if roof["tensor_core_launches"] else None,
+                            "frac_of_sustained_peak": ach / peak_sus, "frac_of_burst_peak": ach / peak_burst,
                             "launches_timed": roof["launches"], "kernel_ms_per_step": roof["ms"] / args.steps,
                             "all_gemm_ms_per_step": roof["all_ms"] / args.steps, "peak_source": peak_src}
     if rank == 0 and world == 1:
         line["north_star_kernels"] = north_star_kernels(peaks)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            cb, _ = cpu_reference_rate(args, 3, 1)
+            cb, _, want = cpu_reference_rate(args, 3, 1)
             line["cpu_baseline"] = cb
+            line["parity"] = parity_against_oracle(model, args, want)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -30,6 +30,7 @@ SIGNATURES = {
     "ec_gemm_f16x3": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_ll, c_f, c_fp, c_int, c_fp, c_fp, c_int,
                               c_int, c_int, c_fp, c_int, c_f, c_fp]),
     "ec_tc_set_tile_n": (c_int, [c_int]),
+    "ec_tc_mode_launches": (c_ll, [c_int]),
     "ec_tc_set_cta_limit": (c_int, [c_int]),
     "ec_tc_set_dynamic": (c_int, [c_int]),
     "ec_set_pdl": (c_int, [c_int]),

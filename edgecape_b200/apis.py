@@ -9,6 +9,8 @@ import collections
 
 import torch
 
+from .detector import unwrap_data_container
+
 _DATA_KEYS = ("img_s", "target_s", "target_weight_s", "img_q", "target_q", "target_weight_q", "img_metas")
 
 
@@ -20,7 +22,7 @@ def iter_results(model, batches, depth=None):
     pending = collections.deque()
     with torch.no_grad():
         for data in batches:
-            kw = {k: v for k, v in data.items() if k != "return_loss"}
+            kw = {k: unwrap_data_container(v) for k, v in data.items() if k != "return_loss"}
             if getattr(model, "use_cuda_graph", False):
                 pending.append(model.forward_test_async(**kw))
             else:

@@ -608,6 +608,50 @@ int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap*
   return EC_OK;
 }
 
+// Per-device state of ec_gemm_f16x3: SM count, the opt-in shared-memory attribute of the three kernel instances (a
+// per-device function attribute) and the tile counters of the dynamic scheduler.  Created under a mutex on the first
+// call made with that device current -- which therefore must not be inside a stream capture (cudaMalloc / cudaMemset).
+constexpr unsigned EAGER_SLOTS = 4096, GRAPH_SLOTS = 61440;
+struct DevState {
+  int num_sms = 0;
+  int* sched_base = nullptr;
+  std::atomic<unsigned> eager_seq{0}, graph_seq{0};
+};
+std::atomic<long long> g_mode_launches[3];   // launches per tile mode: 128x128, 128x256, CTA-pair 256x256
+
+static DevState* dev_state() {
+  constexpr int MAX_DEV = 64;
+  static DevState* states[MAX_DEV] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) {
+    set_error("ec_gemm_f16x3: no current CUDA device");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (states[dev]) return states[dev];
+  DevState* d = new DevState();
+  cudaError_t e = cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_f16x3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_f16x3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_f16x3_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  const size_t bytes = (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int);
+  if (e == cudaSuccess) e = cudaMalloc(&d->sched_base, bytes);
+  if (e == cudaSuccess) e = cudaMemset(d->sched_base, 0, bytes);
+  if (e != cudaSuccess) {
+    set_error("ec_gemm_f16x3: per-device setup failed on device %d: %s (the first call on a device allocates the tile "
+              "counters and must not be inside a stream capture)", dev, cudaGetErrorString(e));
+    cudaGetLastError();
+    delete d;
+    return nullptr;
+  }
+  states[dev] = d;
+  return d;
+}
+
 }  // namespace tc
 }  // namespace ec
 
@@ -636,6 +680,11 @@ extern "C" int ec_tc_set_tile_n(int bn) {
   return EC_OK;
 }
 
+extern "C" long long ec_tc_mode_launches(int mode) {
+  if (mode != 128 && mode != 256 && mode != 512) return -1;
+  return tc::g_mode_launches[mode == 512 ? 2 : (mode == 256 ? 1 : 0)].load(std::memory_order_relaxed);
+}
+
 extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int seg, long long seg_stride, int Kp,
                             float scale, void* stream) {
   EC_REQUIRE(X && X2, "ec_split_f16: null pointer");
@@ -659,20 +708,9 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   EC_REQUIRE((res_mode == EC_RES_NONE) == (R == nullptr), "ec_gemm_f16x3: residual pointer/mode mismatch");
   EC_REQUIRE(!split_out || (split_kp % tc::BK == 0 && split_kp >= N), "ec_gemm_f16x3: bad split_kp");
   if (M == 0 || N == 0) return EC_OK;
-  static int num_sms = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    EC_CUDA(cudaGetDevice(&dev));
-    EC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 tc::SMEM_BYTES));
-    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 tc::SMEM_BYTES));
-    EC_CUDA(cudaFuncSetAttribute(tc::gemm_f16x3_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 tc::SMEM_BYTES));
-    attr_set = true;
-  }
+  tc::DevState* ds = tc::dev_state();
+  if (!ds) return EC_ERR_CUDA;
+  const int num_sms = ds->num_sms;
   // tile selection: CTA-pair 256x256 tiles (half the operand traffic per unit of math) for problems that give every
   // SM pair >= 1.5 tiles; 128x128 single-CTA tiles otherwise.  (A waves x tile-cost model that also moved mid-size
   // problems to pair tiles measured 1.5% slower end to end -- pass L -- the cluster launch has a higher fixed cost.)
@@ -687,7 +725,10 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   if (rc) return rc;
   rc = tc::get_tensor_map(B2, N, Kp, mode == 256 ? 256 : 128, &tmB);
   if (rc) return rc;
-  tc::TcParams p;
+  tc::TcParams p{};
+  // consecutive tiles walk N first when there are few N tiles: the CTAs working at the same time then share their A
+  // row block (read from DRAM once, L2 hits for the other N tiles) and the whole of B stays in L2
+  p.n_fastest = cdiv(N, BN) <= 16 ? 1 : 0;
   p.C = C; p.M = M; p.N = N; p.num_kb = Kp / tc::BK; p.Kp = Kp; p.ldc = ldc;
   p.seg_c = seg_c; p.seg_stride_c = seg_stride_c;
   p.vec_c = C && aligned16(C) && (ldc % 4 == 0) && (seg_stride_c % 4 == 0);
@@ -699,9 +740,6 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   // through a ring of slots (a slot is reused 4096 launches later); launches recorded into a CUDA graph keep their slot
   // for the life of the process (the node replays with it, possibly concurrently with eager work on another stream), so
   // they come from a separate pool that never wraps -- when it runs out, further captured launches use static tiles.
-  constexpr unsigned EAGER_SLOTS = 4096, GRAPH_SLOTS = 61440;
-  static int* sched_base = nullptr;
-  static std::atomic<unsigned> eager_seq{0}, graph_seq{0};
   if (ec_tc_dynamic < 0) {
     const char* e = getenv("EDGECAPE_GEMM_DYNAMIC");
     ec_tc_dynamic = (e && e[0] == '0') ? 0 : 1;
@@ -710,19 +748,14 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   if (ec_tc_dynamic) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     EC_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
-    if (!sched_base) {
-      EC_REQUIRE(cap == cudaStreamCaptureStatusNone,
-                 "ec_gemm_f16x3: the first call must not be inside a stream capture (it allocates the tile counters)");
-      EC_CUDA(cudaMalloc(&sched_base, (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int)));
-      EC_CUDA(cudaMemset(sched_base, 0, (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int)));
-    }
     if (cap == cudaStreamCaptureStatusNone) {
-      p.sched = sched_base + 2 * (eager_seq.fetch_add(1) % EAGER_SLOTS);
+      p.sched = ds->sched_base + 2 * (ds->eager_seq.fetch_add(1) % tc::EAGER_SLOTS);
     } else {
-      const unsigned g = graph_seq.fetch_add(1);
-      if (g < GRAPH_SLOTS) p.sched = sched_base + 2 * (EAGER_SLOTS + g);
+      const unsigned g = ds->graph_seq.fetch_add(1);
+      if (g < tc::GRAPH_SLOTS) p.sched = ds->sched_base + 2 * (tc::EAGER_SLOTS + g);
     }
   }
+  tc::g_mode_launches[mode == 512 ? 2 : (mode == 256 ? 1 : 0)].fetch_add(1, std::memory_order_relaxed);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 512) {
     const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;

@@ -191,6 +191,11 @@ class _GraphedForward:
             # images first: the DMA engine serves copies in issue order and graph A only needs the images
             if s.used:
                 cp.wait_event(s.ev_vit)    # A(i - depth) has read the image buffers
+            # device-resident inputs are read on the copy stream after the caller may have dropped them: tell the
+            # caching allocator, or their memory could be handed out again while the copy is still pending
+            for t in [img_q] + list(img_s) + list(target_s) + list(target_weight_s):
+                if t.is_cuda:
+                    t.record_stream(cp)
             s.img_q.copy_(img_q, non_blocking=True)
             self._copy_supports(s, img_s, groups)
             s.ev_img.record(cp)
@@ -225,6 +230,28 @@ class _GraphedForward:
         h = PendingResult(self, s, img_metas, self.model)
         s.pending = h if want_host else None
         return h
+
+
+def _hashable(v):
+    """img_metas values (lists of numpy arrays / scalars) as nested tuples; None stays None."""
+    if v is None:
+        return None
+    a = np.asarray(v)
+    return (a.shape, tuple(np.round(a.astype(np.float64).reshape(-1), 6).tolist()))
+
+
+def unwrap_data_container(x):
+    """mmcv's collate wraps batches in `DataContainer`s that only `MMDataParallel.scatter` unwraps
+    (/root/reference/EdgeCape/apis/test.py:33 is always called with the wrapped model).  The drop-in is used without
+    that wrapper, so `forward` / `apis.iter_results` unwrap here: a container's `.data` is a list with one entry per
+    GPU -- entry 0 is this process's batch (a stacked tensor, or the list of meta dicts when `cpu_only`).  Lists are
+    unwrapped element-wise; everything else passes through.  Duck-typed: mmcv is not a dependency."""
+    if isinstance(x, (list, tuple)):
+        return type(x)(unwrap_data_container(v) for v in x)
+    if type(x).__name__ == "DataContainer" and hasattr(x, "data"):
+        d = x.data
+        return d[0] if isinstance(d, (list, tuple)) and len(d) >= 1 else d
+    return x
 
 
 def _require_cuda(dev):
@@ -276,6 +303,9 @@ class EdgeCape(nn.Module):
             raise NotImplementedError(
                 "edgecape_b200 accelerates the inference path only: call model(return_loss=False, **data) "
                 "(forward_train / losses are out of scope, see DESIGN.md)")
+        img_s, img_q, target_s, target_weight_s, target_q, target_weight_q, img_metas = (
+            unwrap_data_container(v) for v in (img_s, img_q, target_s, target_weight_s, target_q, target_weight_q,
+                                               img_metas))
         return self.forward_test(img_s, target_s, target_weight_s, img_q, target_q, target_weight_q, img_metas,
                                  **kwargs)
 
@@ -414,7 +444,12 @@ class EdgeCape(nn.Module):
         seen, first, inv = {}, [], []
         for i, m in enumerate(img_metas):
             names = m.get("sample_image_file")
-            k = tuple(names) if names else ("__row__", i)
+            # the same image file can hold several annotated instances (MP-100 pairs are drawn per object id,
+            # test_dataset.py:93-97): two rows only share a support when file AND crop (bbox id / centre / scale /
+            # rotation of every shot) agree; rows without that information are never merged
+            crop = tuple(_hashable(m.get(f)) for f in ("sample_bbox_id", "sample_center", "sample_scale",
+                                                        "sample_rotation"))
+            k = (tuple(names), crop) if names and any(c is not None for c in crop) else ("__row__", i)
             if k not in seen:
                 seen[k] = len(first)
                 first.append(i)

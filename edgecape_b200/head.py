@@ -220,35 +220,14 @@ class TwoStageHead(PackedMixin, nn.Module):
                     bbox_ids=bbox_ids)
 
     def decode(self, img_metas, output, img_size, **kwargs):
-        """head.py:324-387: scale to pixels, undo the top-down crop, assemble preds / boxes."""
-        batch_size = len(img_metas)
+        """head.py:324-387 for host arrays (the default path decodes on the device, ec_decode_preds): scale the
+        normalised coordinates to pixels, undo the top-down crop for the whole batch at once (transform_preds
+        broadcast over the rows), then the same bookkeeping as assemble_result."""
         W, H = img_size
-        output = output * np.array([W, H])[None, None, :]
-        bbox_ids = []        # the reference's `if 'bbox_id' or ...` is always true (head.py:341)
-        c = np.zeros((batch_size, 2), dtype=np.float32)
-        s = np.zeros((batch_size, 2), dtype=np.float32)
-        image_paths = []
-        score = np.ones(batch_size)
-        for i in range(batch_size):
-            c[i, :] = img_metas[i]["query_center"]
-            s[i, :] = img_metas[i]["query_scale"]
-            image_paths.append(img_metas[i]["query_image_file"])
-            if "query_bbox_score" in img_metas[i]:
-                score[i] = np.array(img_metas[i]["query_bbox_score"]).reshape(-1)[0]
-            if "bbox_id" in img_metas[i]:
-                bbox_ids.append(img_metas[i]["bbox_id"])
-            elif "query_bbox_id" in img_metas[i]:
-                bbox_ids.append(img_metas[i]["query_bbox_id"])
-        preds = np.zeros(output.shape)
-        for idx in range(output.shape[0]):
-            preds[idx] = transform_preds(output[idx], c[idx], s[idx], [W, H],
-                                         use_udp=self.test_cfg.get("use_udp", False))
-        all_preds = np.zeros((batch_size, preds.shape[1], 3), dtype=np.float32)
-        all_boxes = np.zeros((batch_size, 6), dtype=np.float32)
-        all_preds[:, :, 0:2] = preds[:, :, 0:2]
-        all_preds[:, :, 2:3] = 1.0
-        all_boxes[:, 0:2] = c[:, 0:2]
-        all_boxes[:, 2:4] = s[:, 0:2]
-        all_boxes[:, 4] = np.prod(s * 200.0, axis=1)
-        all_boxes[:, 5] = score
-        return dict(preds=all_preds, boxes=all_boxes, image_paths=image_paths, bbox_ids=bbox_ids)
+        px = np.asarray(output, dtype=np.float64) * np.array([W, H])[None, None, :]
+        c = np.stack([np.asarray(m["query_center"], dtype=np.float32).reshape(-1)[:2] for m in img_metas])
+        s = np.stack([np.asarray(m["query_scale"], dtype=np.float32).reshape(-1)[:2] for m in img_metas]) * 200.0
+        denom = np.array([W, H], dtype=np.float64) - (1.0 if self.test_cfg.get("use_udp", False) else 0.0)
+        preds = np.ones(px.shape[:2] + (3,), dtype=np.float32)
+        preds[:, :, 0:2] = px[:, :, 0:2] * (s / denom)[:, None, :] + (c - 0.5 * s)[:, None, :]
+        return self.assemble_result(img_metas, preds)

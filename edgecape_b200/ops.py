@@ -33,6 +33,12 @@ def _chk(t, name, dtype=torch.float32):
             f"{name} is on {t.device}: edgecape_b200 has no CPU path (the CUDA library is the product)")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's current stream (_stream); a tensor living elsewhere would be
+        # dereferenced on the wrong GPU
+        raise _lib.EdgeCapeLibraryError(
+            f"{name} lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: "
+            f"call torch.cuda.set_device({t.device.index}) (one device per process is the supported layout)")
 
 
 def _rows(t, name):

@@ -153,6 +153,10 @@ def make_episode(batch, image_size=256, num_kpts=100, shots=1, seed=1234, masked
             query_image_file=f"synthetic_q_{seed}_{b}.png",
             sample_image_file=[f"synthetic_s_{seed}_{g_of[b]}_{j}.png" for j in range(shots)],
             query_bbox_score=1.0, bbox_id=b,
+            # the support crop (the pipeline's Collect meta_keys center / scale / rotation, configs/test/1shot_split1.py:129)
+            sample_center=[np.array([R / 2.0, R / 2.0], dtype=np.float32) for _ in range(shots)],
+            sample_scale=[np.array([R / 200.0, R / 200.0], dtype=np.float32) for _ in range(shots)],
+            sample_rotation=[0 for _ in range(shots)],
             sample_joints_3d=[kpts_s[j][b] for j in range(shots)],
         ))
 

@@ -15,7 +15,9 @@
  *     (a cudaStream_t passed as void*); the caller owns buffers and synchronisation.
  *   - all tensors are device pointers to dense row-major fp32 unless stated; `ld*` are row
  *     strides in elements.  Masks are uint8 (1 = masked / padded), indices int32/int64.
- *   - the device is the caller's current CUDA device.
+ *   - the device is the caller's current CUDA device; per-device state (tile counters, function
+ *     attributes) is created under a mutex on the first call made with a device current, so
+ *     several devices per process and concurrent host threads are fine.
  */
 #ifndef EDGECAPE_B200_H
 #define EDGECAPE_B200_H
@@ -85,6 +87,10 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
 /* tuning knob for ec_gemm_f16x3: 0 = pick the tile width per shape (128x256 tiles for wide, large
  * problems, 128x128 otherwise), 128 / 256 = force it. */
 int ec_tc_set_tile_n(int bn);
+/* number of ec_gemm_f16x3 launches so far in this process that took the tile mode `mode`: 128 (128x128, one CTA),
+ * 256 (128x256, one CTA) or 512 (256x256 on a CTA pair, cta_group::2); -1 for any other argument.  Tests use the
+ * deltas to prove which kernel instance a given configuration runs. */
+long long ec_tc_mode_launches(int mode);
 /* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
  * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
 int ec_tc_set_cta_limit(int ctas);

@@ -53,7 +53,20 @@ CASES = {
     "c2_vitb_256_k100": dict(pretrained="dinov2_vitb14",
                              episode=dict(batch=2, image_size=256, num_kpts=100, shots=1, seed=21,
                                           masked_tail=0.25), wseed=3),
-    # reference-native config: ViT-S/14 at 224^2, 5-shot (configs[3] shape at reduced batch)
+    # BASELINE.json configs[1] at the batch bench.py times (16 queries = 32 ViT images, M = 10400 GEMM rows: the
+    # CTA-pair 256x256 tile mode, dynamic tile scheduler, graphs, two batches in flight); only the tensors in
+    # `keep` are frozen so the file stays small
+    "c2_vitb_256_k100_b16": dict(pretrained="dinov2_vitb14",
+                                 episode=dict(batch=16, image_size=256, num_kpts=100, shots=1, seed=22,
+                                              masked_tail=0.25), wseed=3,
+                                 keep=("feature_q", "support_keypoints", "skeleton_kp_features", "adj",
+                                       "similarity_map", "initial_proposals", "argmax", "out_points", "output",
+                                       "preds", "boxes", "points", "skeleton")),
+    # BASELINE.json configs[3] at its real shape (reduced batch): ViT-B/14, 256^2, 5-shot, K=100
+    "c4_vitb_256_5shot": dict(pretrained="dinov2_vitb14",
+                              episode=dict(batch=2, image_size=256, num_kpts=100, shots=5, seed=42,
+                                           masked_tail=0.4), wseed=6),
+    # reference-native config: ViT-S/14 at 224^2, 5-shot (configs[3] at another backbone / resolution)
     "c4_vits_224_5shot": dict(pretrained="dinov2_vits14",
                               episode=dict(batch=2, image_size=224, num_kpts=100, shots=5, seed=41,
                                            masked_tail=0.4), wseed=4),
@@ -198,6 +211,8 @@ def main(argv):
         # keep files small: feature_q only for batch row 0
         g["feature_q"] = g["feature_q"][:1]
         g["encoder_image"] = g["encoder_image"][:1]
+        if "keep" in CASES[name]:
+            g = {k: v for k, v in g.items() if k in CASES[name]["keep"]}
         np.savez_compressed(os.path.join(REPO, "tests/golden", name + ".npz"), **g)
         summary[name] = dict(oracle_fp32_vs_ref=worst32, oracle_fp64_vs_ref=worst64,
                              ref_seconds=round(dt, 2))

@@ -41,10 +41,14 @@ def main():
         run8()
         err = lambda y: ((y.double() - want).abs().max() / want.abs().max()).item()
         t3 = timeit(lambda: ops.gemm_tc(a2, b2, out=y3))
+        _lib.call("ec_tc_set_tile_n", 256)          # the same 128x256 single-CTA tile the f16f8 kernel uses
+        t3s = timeit(lambda: ops.gemm_tc(a2, b2, out=y3))
+        _lib.call("ec_tc_set_tile_n", 0)
         t8 = timeit(run8)
         fl = 2.0 * M * N * K
-        print(f"{name:5s} M={M} N={N} K={K}: 3xfp16 {t3 * 1e3:7.1f} us {fl / t3 / 1e9:6.0f} TF/s err {err(y3):.1e} | "
-              f"fp16+2xfp8 {t8 * 1e3:7.1f} us {fl / t8 / 1e9:6.0f} TF/s err {err(y8):.1e}", flush=True)
+        print(f"{name:5s} M={M} N={N} K={K}: 3xfp16 auto {t3 * 1e3:7.1f} us {fl / t3 / 1e9:6.0f} TF/s err {err(y3):.1e} | "
+              f"3xfp16 128x256 {t3s * 1e3:7.1f} us {fl / t3s / 1e9:6.0f} TF/s | "
+              f"fp16+2xfp8 128x256 {t8 * 1e3:7.1f} us {fl / t8 / 1e9:6.0f} TF/s err {err(y8):.1e}", flush=True)
 
 
 if __name__ == "__main__":

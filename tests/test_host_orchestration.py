@@ -105,3 +105,81 @@ def test_test_loop_api_returns_results_in_order(monkeypatch):
     for g, w in zip(got, want):
         assert np.array_equal(g["preds"], w["preds"])
     assert len(list(iter_results(model, iter(batches[:1]), depth=4))) == 1
+
+
+class DataContainer:
+    """Shape of mmcv.parallel.DataContainer after `collate` (mmcv is absent offline): `.data` is a list with one
+    entry per GPU; stacked tensors for `stack=True` fields, the list of meta dicts for `cpu_only=True`."""
+
+    def __init__(self, data, stack=False, cpu_only=False):
+        self.data, self.stack, self.cpu_only = data, stack, cpu_only
+
+
+def test_data_container_batches_are_unwrapped(monkeypatch):
+    """The reference's loop hands the model what mmcv's collate produced; only MMDataParallel.scatter unwraps the
+    DataContainers (apis/test.py:33).  INTEGRATION.md drops that wrapper, so forward() and apis.iter_results must
+    accept the wrapped batch themselves."""
+    from edgecape_b200 import ops
+    from edgecape_b200.apis import single_gpu_test
+    from edgecape_b200.synthetic import make_episode
+    from oracle.gen_golden import TINY_VIT, model_cfg_for
+    cpu_emulator.install(monkeypatch)
+    monkeypatch.setattr(ops, "TENSOR_CORES", False)
+    cfg = model_cfg_for(TINY_VIT)
+    model = E.build_model(dict(model=cfg))
+    model.load_state_dict(make_state_dict(state_dict_shapes(cfg), 5), strict=True)
+    model.eval()
+    model.use_cuda_graph = False
+    data = make_episode(batch=2, image_size=64, num_kpts=5, shots=2, seed=31)
+    want = model(return_loss=False, **data)
+    wrapped = dict(data)
+    wrapped["img_metas"] = DataContainer([data["img_metas"]], cpu_only=True)
+    wrapped["img_q"] = DataContainer([data["img_q"]], stack=True)
+    wrapped["img_s"] = [DataContainer([t], stack=True) for t in data["img_s"]]
+    for got in (model(return_loss=False, **wrapped), single_gpu_test(model, [wrapped])[0]):
+        assert got["image_paths"] == want["image_paths"]
+        for k in ("preds", "points", "skeleton", "boxes"):
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+
+
+def test_support_deduplication_key_includes_the_crop():
+    """Two rows with the same support image FILE but different annotated instances (another bbox / crop) must not
+    share backbone features (MP-100 pairs are drawn per object id, test_dataset.py:93-97)."""
+    from edgecape_b200.synthetic import make_episode
+    from oracle.gen_golden import TINY_VIT, model_cfg_for
+    model = E.build_model(dict(model=model_cfg_for(TINY_VIT)))
+    model.test_cfg = dict(model.test_cfg, dedup_supports=True)
+    metas = make_episode(batch=4, image_size=64, num_kpts=5, shots=1, seed=3, shared_support=4)["img_metas"]
+    assert model._support_groups(metas) == ([0], [0, 0, 0, 0])
+    metas[2]["sample_center"] = [np.array([10.0, 12.0], dtype=np.float32)]        # same file, another instance
+    assert model._support_groups(metas) == ([0, 2], [0, 0, 1, 0])
+    for m in metas:                                                             # no crop information: never merged
+        for k in ("sample_center", "sample_scale", "sample_rotation"):
+            m.pop(k)
+    assert model._support_groups(metas) is None
+
+
+def test_host_decode_equals_per_sample_transform_preds():
+    """TwoStageHead.decode (head.py:324-387) on host arrays: the batched form equals transform_preds row by row."""
+    from edgecape_b200.head import transform_preds
+    from edgecape_b200.synthetic import make_episode
+    from oracle.gen_golden import TINY_VIT, model_cfg_for
+    model = E.build_model(dict(model=model_cfg_for(TINY_VIT)))
+    head = model.keypoint_head_module
+    metas = make_episode(batch=3, image_size=64, num_kpts=6, shots=1, seed=4)["img_metas"]
+    rng = np.random.default_rng(0)
+    for i, m in enumerate(metas):
+        m["query_center"] = rng.uniform(20, 200, 2).astype(np.float32)
+        m["query_scale"] = rng.uniform(0.3, 2.0, 2).astype(np.float32)
+        m["query_bbox_score"] = 0.5 + 0.1 * i
+    out = rng.uniform(0, 1, (3, 6, 2))
+    for udp in (False, True):
+        head.test_cfg = dict(head.test_cfg or {}, use_udp=udp)
+        res = head.decode(metas, out, (64, 48))
+        for b, m in enumerate(metas):
+            want = transform_preds(out[b] * np.array([64, 48]), m["query_center"], m["query_scale"], [64, 48], use_udp=udp)
+            assert np.allclose(res["preds"][b, :, :2], want, rtol=1e-6, atol=1e-4)
+            assert np.all(res["preds"][b, :, 2] == 1.0)
+            assert np.allclose(res["boxes"][b], [*m["query_center"], *m["query_scale"],
+                                                 np.prod(m["query_scale"] * 200.0), 0.5 + 0.1 * b], rtol=1e-6)
+    assert res["bbox_ids"] == [0, 1, 2] and res["image_paths"] == [m["query_image_file"] for m in metas]

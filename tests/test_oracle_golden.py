@@ -12,7 +12,7 @@ from edgecape_b200.synthetic import make_state_dict
 from edgecape_b200.config import state_dict_shapes
 
 FAST = ["c1_tiny", "tiny_k100_2shot_masked", "tiny_allmasked", "c2_vitb_256_k100"]
-SLOW = ["c4_vits_224_5shot", "c5_vitl_384_k200_full"]
+SLOW = ["c4_vits_224_5shot", "c5_vitl_384_k200_full", "c2_vitb_256_k100_b16", "c4_vitb_256_5shot"]
 
 
 def _check(name, golden_dir, dtype, tol):
