@@ -270,7 +270,7 @@ class GemmTimer:
         timer = self
 
         def call(name, *a):
-            if timer.active and name in ("ec_gemm", "ec_gemm_f16x3"):
+            if timer.active and name in ("ec_gemm", "ec_gemm_f16x3", "ec_gemm_f16f8"):
                 M, N, K = a[3], a[4], a[5]
                 batch = a[10] if name == "ec_gemm" else 1
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,9 +292,13 @@ class GemmTimer:
         dom = [r for r in big if r[0] >= 1e9] or big
         fl = sum(r[0] for r in dom)
         ms = sum(r[2] for r in dom)
-        tc = sum(1 for r in dom if r[1][0] == "ec_gemm_f16x3")
+        tc = sum(1 for r in dom if r[1][0] in ("ec_gemm_f16x3", "ec_gemm_f16f8"))
+        f8 = sum(1 for r in dom if r[1][0] == "ec_gemm_f16f8")
+        # tensor-pipe time issued, in units of one fp16 product: 3 for three fp16 products, 2 for fp16 + two e4m3
+        # cross terms (an e4m3 UMMA covers twice the contraction depth per clock)
+        units = sum(r[0] * (2.0 if r[1][0] == "ec_gemm_f16f8" else 3.0) for r in dom if r[1][0] != "ec_gemm")
         return dict(flops=fl, ms=ms, launches=len(dom), all_ms=sum(r[2] for r in big), all_launches=len(big),
-                    tensor_core_launches=tc)
+                    tensor_core_launches=tc, f8_launches=f8, issued_units=units)
 
 
 def north_star_kernels(peaks):
@@ -546,10 +550,13 @@ def run_ours(args):
         ach = roof["flops"] / (roof["ms"] / 1e3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                             "frac": ach / peak_tf, "traffic": traffic,
-                            "kernel": ("ec::tc::gemm_f16x3_kernel (tcgen05 kind::f16, 3-product split-fp16, fp32 TMEM accumulate; "
-                                       "algorithmic FLOPs = 1/3 of the tensor-pipe FLOPs issued)") if roof["tensor_core_launches"]
-                            else "ec::gemm_simt_kernel<128,128> (fp32 FFMA)",
-                            "issued_frac": (3 * ach / peak_tf) if roof["tensor_core_launches"] else None,
+                            "kernel": ("ec::tc::gemm_f16x3_kernel (tcgen05, fp32 TMEM accumulate, fp32-grade split operands: "
+                                       f"{roof['f8_launches']} of the {roof['launches']} timed launches run a_hi.b_hi on "
+                                       "kind::f16 + both cross terms on kind::f8f6f4 e4m3 = 2 units of tensor time per "
+                                       "algorithmic product, the others three kind::f16 products = 3 units)")
+                            if roof["tensor_core_launches"] else "ec::gemm_simt_kernel<128,128> (fp32 FFMA)",
+                            "issued_frac": (roof["issued_units"] / (roof["ms"] / 1e3) / 1e12 / peak_tf)
+                            if roof["tensor_core_launches"] else None,
                             "frac_of_sustained_peak": ach / peak_sus, "frac_of_burst_peak": ach / peak_burst,
                             "launches_timed": roof["launches"], "kernel_ms_per_step": roof["ms"] / args.steps,
                             "all_gemm_ms_per_step": roof["all_ms"] / args.steps, "peak_source": peak_src}

@@ -38,7 +38,7 @@ SIGNATURES = {
     "ec_attention_tc_set_trace": (c_int, [c_fp, c_int]),
     "ec_attention_tc_set_variant": (c_int, [c_int]),
     "ec_layernorm": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_f,
-                             c_int, c_int, c_fp, c_int, c_fp]),
+                             c_int, c_int, c_fp, c_int, c_int, c_fp]),
     "ec_add_rows": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "ec_copy_rows": (c_int, [c_fp, c_int, c_int, c_ll, c_fp, c_int, c_int, c_ll, c_int, c_int, c_int, c_fp]),
     "ec_gather_blocks": (c_int, [c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_ll, c_fp]),
@@ -64,8 +64,10 @@ SIGNATURES = {
     "ec_gcn_fused_slice": (c_int, [c_int, c_int, c_int]),
     "ec_gcn_fused_set_trace": (c_int, [c_fp, c_int]),
     "ec_gcn_fused_set_debug": (c_int, [c_int]),
-    "ec_split_f16f8": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_int, c_fp]),
-    "ec_gemm_f16f8": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_fp, c_int, c_fp]),
+    "ec_split_f16f8": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_ll, c_int, c_f, c_int, c_fp]),
+    "ec_gemm_f16f8": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_ll, c_f, c_fp, c_int, c_fp, c_fp, c_int,
+                              c_int, c_int, c_fp, c_int, c_f, c_int, c_fp]),
+    "ec_overflow_count": (c_int, [c_fp, c_int]),
     "ec_gcn_fused": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_support_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),

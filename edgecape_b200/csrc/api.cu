@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -30,7 +31,42 @@ bool pdl_enabled() {
   return g_pdl != 0;
 }
 
+unsigned long long* overflow_counters() {
+  constexpr int MAX_DEV = 64;
+  static unsigned long long* ptrs[MAX_DEV] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) {
+    set_error("overflow counters: no current CUDA device");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ptrs[dev]) {
+    unsigned long long* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+      set_error("overflow counters: allocation failed on device %d: %s (the first F16F8 producer call on a device must "
+                "be outside a stream capture)", dev, cudaGetErrorString(e));
+      cudaGetLastError();
+      return nullptr;
+    }
+    ptrs[dev] = p;
+  }
+  return ptrs[dev];
+}
+
 }  // namespace ec
+
+extern "C" int ec_overflow_count(unsigned long long* out2, int reset) {
+  EC_REQUIRE(out2, "ec_overflow_count: null output");
+  unsigned long long* p = ec::overflow_counters();
+  if (!p) return EC_ERR_CUDA;
+  EC_CUDA(cudaDeviceSynchronize());
+  EC_CUDA(cudaMemcpy(out2, p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) EC_CUDA(cudaMemset(p, 0, 2 * sizeof(unsigned long long)));
+  return EC_OK;
+}
 
 extern "C" int ec_version(void) { return 100; }
 extern "C" const char* ec_last_error_string(void) { return ec::g_err; }

@@ -1,6 +1,7 @@
 // Shared helpers for the edgecape_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -11,6 +12,9 @@ namespace ec {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// device counters {values beyond the e4m3 range, values beyond the fp16 range} seen by F16F8 split producers on the
+// current device; allocated on first use (which must be outside a stream capture).  nullptr + error on failure.
+unsigned long long* overflow_counters();
 
 // Programmatic dependent launch.  Kernels launched through launch_pdl() may start while their predecessor in the
 // stream is still running; each of them calls pdl_wait() -- which returns once the predecessor grid has completed
@@ -85,6 +89,45 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   split_pair(a, b, h, l);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---- split operand rows.  A matrix [rows, K] feeds the tensor-core GEMMs as rows of 4*Kp bytes in one of two formats
+// (Kp = K rounded up to 64, zero padded; `fmt` = EC_SPLIT_F16X2 / EC_SPLIT_F16F8, include/edgecape_b200.h):
+//   F16X2: [ hi16 : Kp halves | lo16 : Kp halves ]                 three fp16 products (ec_gemm_f16x3)
+//   F16F8: [ hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp bytes ]  fp16 hi.hi + two e4m3 cross terms (ec_gemm_f16f8)
+// F16F8 plane scales are static powers of two, so every product carries the same scale and all three accumulate into
+// one fp32 accumulator:  A role (activations): hi8 = e4m3(hi16), lo8 = e4m3((a - hi16) 2^11);
+//                        B role (weights, pre-scaled by s_w): hi8 = e4m3(hi16 2^-11), lo8 = e4m3(b s_w - hi16).
+// e4m3 saturates at 448: an activation beyond that only degrades ITS cross terms to plain-fp16 accuracy (the hi16 plane
+// carries the value); beyond 65504 hi16 itself overflows.  Both events are counted (ec_overflow_count).
+__device__ __forceinline__ uint32_t e4m3x2(float a, float b) {
+  return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);   // a in the low byte
+}
+// four consecutive elements (column c, a multiple of 4) of an A-role row; `row` = the row's first byte
+__device__ __forceinline__ void store_split4(uint8_t* row, int kp, int c, float v0, float v1, float v2, float v3,
+                                             int fmt, uint32_t& flags) {
+  __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  *reinterpret_cast<uint2*>(row + 2 * c) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  if (fmt == EC_SPLIT_F16X2) {
+    __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+    *reinterpret_cast<uint2*>(row + 2 * kp + 2 * c) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+  } else {
+    *reinterpret_cast<uint32_t*>(row + 2 * kp + c) = e4m3x2(f01.x, f01.y) | (e4m3x2(f23.x, f23.y) << 16);
+    *reinterpret_cast<uint32_t*>(row + 3 * kp + c) =
+        e4m3x2((v0 - f01.x) * 2048.f, (v1 - f01.y) * 2048.f) | (e4m3x2((v2 - f23.x) * 2048.f, (v3 - f23.y) * 2048.f) << 16);
+    const float m = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
+    flags |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
+  }
+}
+// end of a thread's stores: one atomic per event class at most (flags is zero on every healthy run)
+__device__ __forceinline__ void report_overflow(unsigned long long* counters, uint32_t flags) {
+  if (flags && counters) {
+    if (flags & 1u) atomicAdd(counters, 1ULL);
+    if (flags & 2u) atomicAdd(counters + 1, 1ULL);
+  }
 }
 
 // One lane of a converged warp.  Code that issues tcgen05.mma / TMA / tcgen05.commit must be guarded by this

@@ -77,6 +77,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
+// K-major, 64B-swizzled tile of e4m3 bytes: rows of 64 B, 8-row atoms of 512 B, layout type 4 (SWIZZLE_64B).
+// Hardware facts behind it: scripts/probes/f8_mma_probe.cu, profiles/r01_ao_f8_mma_probe.log.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
 // kind::f16 instruction descriptor (Cfg<BN>::IDESC): D = f32, A = B = f16, both K-major, M = 128, N = BN.
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -85,6 +90,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f8f6f4 with the same instruction descriptor: a / b format 0 = E4M3, fp32 accumulate, K = 32 per instruction
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -127,9 +142,11 @@ struct TcParams {
   const float* R;
   int ldr, act, res_mode;
   int res_rows;        // > 0: residual row = row % res_rows (broadcast over a batch of res_rows-row blocks)
-  __half* split_out;   // optional [M, 2*split_kp] = [hi | lo] of the result (next GEMM's A operand)
+  __half* split_out;   // optional [M, 2*split_kp] halves = the split rows of the result (next GEMM's A operand)
   int split_kp;
+  int split_fmt;       // EC_SPLIT_F16X2 = [hi16 | lo16], EC_SPLIT_F16F8 = [hi16 | hi8 | lo8] (common.cuh)
   float split_scale;
+  unsigned long long* overflow;   // F16F8 producers: {beyond e4m3, beyond fp16} event counters
   int* sched;          // dynamic tile scheduler: {next tile, finished workers} of this launch (zero on entry), or NULL
 };
 
@@ -182,6 +199,15 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on `bar` of BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3)
@@ -192,9 +218,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on 
 // TWO = true : a cluster of two CTAs per 256 x 256 tile (cta_group::2, BN must be 256): each CTA stages its own
 //              128 rows of A and 128 rows of B (64 KB per k-block, 3 stages), the leader issues M = 256 UMMAs that
 //              read both CTAs' shared memory, so every staged byte feeds twice the math of the single-CTA tile.
-template <int BN, bool TWO>
+// F8 = false: operands in F16X2 rows, three kind::f16 products per k-block (12 UMMAs of K = 16).
+// F8 = true : operands in F16F8 rows; a stage holds {A.hi16, A.hi8, A.lo8, B.hi16, B.hi8, B.lo8} (the same bytes), the
+//             fp16 tiles in 128B swizzle and the e4m3 tiles in 64B swizzle (64-byte rows, loaded through the byte
+//             view tmA8 / tmB8 of the same buffers); a k-block is 2 + 2 kind::f8f6f4 UMMAs (K = 32) for the cross terms
+//             a_lo.b_hi + a_hi.b_lo and 4 kind::f16 UMMAs for a_hi.b_hi: 2 instead of 3 units of tensor time.
+template <int BN, bool TWO, bool F8>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, TcParams p) {
   constexpr int B_ROWS = TWO ? BN / 2 : BN;                      // B rows staged by one CTA
   constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
   constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;
@@ -300,20 +332,36 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
+          // stage: [A.hi16 16 KB | A second plane(s) 16 KB | B.hi16 | B second plane(s)]; the second plane is lo16
+          // (one box of halves) or hi8 | lo8 (two boxes of bytes at byte columns 2 Kp / 3 Kp of the same rows)
           if (TWO) {
             // both CTAs' bytes are accounted on the leader's barrier: it expects 2 x STAGE_BYTES
             const uint32_t lbar = mapa(full_bar(stage), 0);
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             tma_load_2d_2sm(sb + 0 * TILE_BYTES, &tmA, lbar, kb * BK, m0);
-            tma_load_2d_2sm(sb + 1 * TILE_BYTES, &tmA, lbar, p.Kp + kb * BK, m0);
             tma_load_2d_2sm(sb + 2 * TILE_BYTES, &tmB, lbar, kb * BK, n0);
-            tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, lbar, p.Kp + kb * BK, n0);
+            if (F8) {
+              tma_load_2d_2sm(sb + TILE_BYTES, &tmA8, lbar, 2 * p.Kp + kb * BK, m0);
+              tma_load_2d_2sm(sb + TILE_BYTES + TILE_BYTES / 2, &tmA8, lbar, 3 * p.Kp + kb * BK, m0);
+              tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB8, lbar, 2 * p.Kp + kb * BK, n0);
+              tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2, &tmB8, lbar, 3 * p.Kp + kb * BK, n0);
+            } else {
+              tma_load_2d_2sm(sb + 1 * TILE_BYTES, &tmA, lbar, p.Kp + kb * BK, m0);
+              tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, lbar, p.Kp + kb * BK, n0);
+            }
           } else {
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(sb + 0 * TILE_BYTES, &tmA, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
             tma_load_2d(sb + 2 * TILE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
-            tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
+            if (F8) {
+              tma_load_2d(sb + TILE_BYTES, &tmA8, full_bar(stage), 2 * p.Kp + kb * BK, m0);
+              tma_load_2d(sb + TILE_BYTES + TILE_BYTES / 2, &tmA8, full_bar(stage), 3 * p.Kp + kb * BK, m0);
+              tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB8, full_bar(stage), 2 * p.Kp + kb * BK, n0);
+              tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2, &tmB8, full_bar(stage), 3 * p.Kp + kb * BK, n0);
+            } else {
+              tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
+              tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -336,8 +384,31 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sb = base + stage * STAGE_BYTES;
-          const uint64_t a_hi = make_smem_desc(sb + 0 * TILE_BYTES), a_lo = make_smem_desc(sb + 1 * TILE_BYTES);
-          const uint64_t b_hi = make_smem_desc(sb + 2 * TILE_BYTES);
+          const uint64_t a_hi = make_smem_desc(sb + 0 * TILE_BYTES), b_hi = make_smem_desc(sb + 2 * TILE_BYTES);
+          if (F8) {
+            // cross terms first (e4m3, K = 32 per UMMA, descriptors advance 32 B), then hi16 . hi16
+            const uint64_t a_h8 = make_smem_desc_sw64(sb + TILE_BYTES), a_l8 = make_smem_desc_sw64(sb + TILE_BYTES + TILE_BYTES / 2);
+            const uint64_t b_h8 = make_smem_desc_sw64(sb + 2 * TILE_BYTES + B_TILE_BYTES);
+            const uint64_t b_l8 = make_smem_desc_sw64(sb + 2 * TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2);
+            if (TWO) {
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) umma_f8_2sm(tmem_d, a_l8 + 2 * k, b_h8 + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) umma_f8_2sm(tmem_d, a_h8 + 2 * k, b_l8 + 2 * k, IDESC, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, 1u);
+              umma_commit_2sm(empty_bar(stage));
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) umma_f8(tmem_d, a_l8 + 2 * k, b_h8 + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) umma_f8(tmem_d, a_h8 + 2 * k, b_l8 + 2 * k, IDESC, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, 1u);
+              umma_commit(empty_bar(stage));
+            }
+          } else {
+          const uint64_t a_lo = make_smem_desc(sb + 1 * TILE_BYTES);
           const uint64_t b_lo = make_smem_desc(sb + 2 * TILE_BYTES + B_TILE_BYTES);
           // small terms first, then hi*hi
           if (TWO) {
@@ -360,6 +431,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               umma_f16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, IDESC, ((p.dbg & 2) && !(kb | k)) ? 0u : 1u);
             umma_commit(empty_bar(stage));           // frees the smem stage when these MMAs retire
           }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (TWO) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
@@ -378,6 +450,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int sub_row = lane >> 2, c4 = (lane & 3) * 4;
     constexpr int NSUB = BN / 16;
     int t = 0;
+    uint32_t ovf = 0;                              // F16F8 split_out: values beyond the e4m3 / fp16 range seen by this thread
     const uint32_t tempty_leader0 = TWO ? mapa(tempty_bar(0), 0) : 0u, tempty_leader1 = TWO ? mapa(tempty_bar(1), 0) : 0u;
     for (;; ++t) {
       const int tile = ring_get(t);
@@ -493,12 +566,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               float sc_[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) sc_[u] = (gcol + u < p.N) ? y[i][u] * p.split_scale : 0.f;
-              uint32_t h01, l01, h23, l23;
-              split_pair(sc_[0], sc_[1], h01, l01);
-              split_pair(sc_[2], sc_[3], h23, l23);
-              __half* sp = p.split_out + (long long)row * (2 * p.split_kp) + gcol;   // gcol % 4 == 0: 8 B aligned
-              *reinterpret_cast<uint2*>(sp) = make_uint2(h01, h23);
-              *reinterpret_cast<uint2*>(sp + p.split_kp) = make_uint2(l01, l23);
+              // gcol % 4 == 0: 8-byte aligned hi16 / lo16 stores, 4-byte aligned e4m3 stores
+              store_split4(reinterpret_cast<uint8_t*>(p.split_out) + (long long)row * (4 * p.split_kp), p.split_kp, gcol,
+                           sc_[0], sc_[1], sc_[2], sc_[3], p.split_fmt, ovf);
             }
           }
         }
@@ -509,6 +579,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    report_overflow(p.overflow, ovf);
   }
   tc_fence_before();
   if (TWO) cluster_sync(); else __syncthreads();   // the peer's shared memory / barriers stay alive until both are done
@@ -545,6 +616,37 @@ __global__ void split_f16_kernel(const float* __restrict__ X, __half* __restrict
   row[(Kp + k) >> 1] = lo;
 }
 
+// X [M, K] fp32 -> F16F8 rows [hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp bytes] of X*scale, zero padded to Kp.
+// role 0 = A operand (activations), 1 = B operand (weights): the plane scales at the top of common.cuh's split section.
+__global__ void split_f16f8_kernel(const float* __restrict__ X, uint8_t* __restrict__ out, int M, int K, int ldx, int seg,
+                                   long long seg_stride, int Kp, float scale, int role, unsigned long long* overflow) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 elements
+  const int quarter_kp = Kp >> 2;
+  if (i >= (long long)M * quarter_kp) return;
+  const int m = (int)(i / quarter_kp), k = (int)(i % quarter_kp) * 4;
+  const float* x = seg > 0 ? X + (long long)(m / seg) * seg_stride + (long long)(m % seg) * ldx : X + (long long)m * ldx;
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = (k + u < K) ? x[k + u] * scale : 0.f;
+  uint8_t* row = out + (long long)m * 4 * Kp;
+  if (role == 0) {
+    uint32_t flags = 0;
+    store_split4(row, Kp, k, v[0], v[1], v[2], v[3], EC_SPLIT_F16F8, flags);
+    report_overflow(overflow, flags);
+  } else {
+    const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const float s = 0.00048828125f;                     // 2^-11
+    *reinterpret_cast<uint2*>(row + 2 * k) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint32_t*>(row + 2 * Kp + k) = e4m3x2(f01.x * s, f01.y * s) | (e4m3x2(f23.x * s, f23.y * s) << 16);
+    *reinterpret_cast<uint32_t*>(row + 3 * Kp + k) =
+        e4m3x2(v[0] - f01.x, v[1] - f01.y) | (e4m3x2(v[2] - f23.x, v[3] - f23.y) << 16);
+  }
+}
+
 // ------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -565,7 +667,7 @@ static EncodeTiledFn get_encode() {
 
 struct MapKey {
   const void* ptr;
-  int rows, kp, box_rows;
+  int rows, kp, box_rows;   // box_rows < 0: the byte view of an F16F8 operand (64-byte boxes, 64B swizzle)
   bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kp == o.kp && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
@@ -575,11 +677,14 @@ struct MapKeyHash {
   }
 };
 
-int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {
+// halves view (bytes == false): dims {2 Kp halves, rows}, 64-half x box_rows boxes, 128B swizzle -- the hi16 | lo16 planes.
+// byte view (bytes == true): dims {4 Kp bytes, rows}, 64-byte x box_rows boxes, 64B swizzle -- the hi8 | lo8 planes of an
+// F16F8 operand, at byte columns 2 Kp and 3 Kp of the same rows.
+static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out, bool bytes) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   std::lock_guard<std::mutex> lock(mu);
-  MapKey key{ptr, rows, kp, box_rows};
+  MapKey key{ptr, rows, kp, bytes ? -box_rows : box_rows};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -590,13 +695,14 @@ int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap*
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return EC_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)(2 * kp), (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)(2 * kp) * 2};
+  cuuint64_t dims[2] = {(cuuint64_t)(bytes ? 4 * kp : 2 * kp), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(4 * kp)};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(&m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %d kp %d)", (int)r, ptr, rows, kp);
@@ -617,7 +723,7 @@ struct DevState {
   int* sched_base = nullptr;
   std::atomic<unsigned> eager_seq{0}, graph_seq{0};
 };
-std::atomic<long long> g_mode_launches[3];   // launches per tile mode: 128x128, 128x256, CTA-pair 256x256
+std::atomic<long long> g_mode_launches[6];   // launches per tile mode: 128x128, 128x256, CTA-pair 256x256; [3..5] = the F16F8 kernels
 
 static DevState* dev_state() {
   constexpr int MAX_DEV = 64;
@@ -632,12 +738,11 @@ static DevState* dev_state() {
   if (states[dev]) return states[dev];
   DevState* d = new DevState();
   cudaError_t e = cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gemm_f16x3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gemm_f16x3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gemm_f16x3_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  const void* kernels[6] = {(const void*)gemm_f16x3_kernel<128, false, false>, (const void*)gemm_f16x3_kernel<256, false, false>,
+                            (const void*)gemm_f16x3_kernel<256, true, false>,  (const void*)gemm_f16x3_kernel<128, false, true>,
+                            (const void*)gemm_f16x3_kernel<256, false, true>,  (const void*)gemm_f16x3_kernel<256, true, true>};
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+    e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const size_t bytes = (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int);
   if (e == cudaSuccess) e = cudaMalloc(&d->sched_base, bytes);
   if (e == cudaSuccess) e = cudaMemset(d->sched_base, 0, bytes);
@@ -650,6 +755,10 @@ static DevState* dev_state() {
   }
   states[dev] = d;
   return d;
+}
+
+int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {   // also used by other kernels
+  return get_tensor_map_any(ptr, rows, kp, box_rows, out, false);
 }
 
 }  // namespace tc
@@ -680,9 +789,10 @@ extern "C" int ec_tc_set_tile_n(int bn) {
   return EC_OK;
 }
 
-extern "C" long long ec_tc_mode_launches(int mode) {
-  if (mode != 128 && mode != 256 && mode != 512) return -1;
-  return tc::g_mode_launches[mode == 512 ? 2 : (mode == 256 ? 1 : 0)].load(std::memory_order_relaxed);
+extern "C" long long ec_tc_mode_launches(int mode) {   // mode + 1: the same tile mode on the F16F8 kernels
+  const int f8 = mode & 1, m = mode & ~1;
+  if (m != 128 && m != 256 && m != 512) return -1;
+  return tc::g_mode_launches[3 * f8 + (m == 512 ? 2 : (m == 256 ? 1 : 0))].load(std::memory_order_relaxed);
 }
 
 extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int seg, long long seg_stride, int Kp,
@@ -696,17 +806,32 @@ extern "C" int ec_split_f16(const float* X, void* X2, int M, int K, int ldx, int
   return check_launch("ec_split_f16");
 }
 
-extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp, int ldc, int seg_c,
-                             long long seg_stride_c, float out_scale,
-                             const float* bias, int act, const float* colscale, const float* R, int ldr,
-                             int res_mode, int res_rows, void* split_out, int split_kp, float split_scale,
-                             void* stream) {
-  EC_REQUIRE(A2 && B2 && (C || split_out), "ec_gemm_f16x3: null operand");
-  EC_REQUIRE(Kp > 0 && Kp % tc::BK == 0, "ec_gemm_f16x3: Kp must be a positive multiple of 64");
-  EC_REQUIRE(aligned16(A2) && aligned16(B2), "ec_gemm_f16x3: split operands must be 16-byte aligned");
-  EC_REQUIRE(!split_out || (((uintptr_t)split_out & 7) == 0), "ec_gemm_f16x3: split_out must be 8-byte aligned");
-  EC_REQUIRE((res_mode == EC_RES_NONE) == (R == nullptr), "ec_gemm_f16x3: residual pointer/mode mismatch");
-  EC_REQUIRE(!split_out || (split_kp % tc::BK == 0 && split_kp >= N), "ec_gemm_f16x3: bad split_kp");
+extern "C" int ec_split_f16f8(const float* X, void* out, int M, int K, int ldx, int seg, long long seg_stride, int Kp,
+                              float scale, int role, void* stream) {
+  EC_REQUIRE(X && out, "ec_split_f16f8: null pointer");
+  EC_REQUIRE(Kp % tc::BK == 0 && Kp >= K && K > 0, "ec_split_f16f8: Kp must be a multiple of 64 and >= K");
+  EC_REQUIRE(role == 0 || role == 1, "ec_split_f16f8: role is 0 (A operand) or 1 (B operand)");
+  EC_REQUIRE(aligned16(out), "ec_split_f16f8: the operand buffer must be 16-byte aligned");
+  if (M == 0) return EC_OK;
+  unsigned long long* ovf = overflow_counters();
+  if (!ovf) return EC_ERR_CUDA;
+  const long long total = (long long)M * (Kp / 4);
+  launch_pdl(tc::split_f16f8_kernel, dim3(cdiv(total, 256)), dim3(256), 0, (cudaStream_t)stream, X, (uint8_t*)out, M, K,
+             ldx, seg, seg_stride, Kp, scale, role, ovf);
+  return check_launch("ec_split_f16f8");
+}
+
+static int gemm_split_launch(const char* what, bool f8, const void* A2, const void* B2, float* C, int M, int N, int Kp,
+                             int ldc, int seg_c, long long seg_stride_c, float out_scale, const float* bias, int act,
+                             const float* colscale, const float* R, int ldr, int res_mode, int res_rows,
+                             void* split_out, int split_kp, float split_scale, int split_fmt, void* stream) {
+  EC_REQUIRE(A2 && B2 && (C || split_out), "%s: null operand", what);
+  EC_REQUIRE(Kp > 0 && Kp % tc::BK == 0, "%s: Kp must be a positive multiple of 64", what);
+  EC_REQUIRE(aligned16(A2) && aligned16(B2), "%s: split operands must be 16-byte aligned", what);
+  EC_REQUIRE(!split_out || (((uintptr_t)split_out & 7) == 0), "%s: split_out must be 8-byte aligned", what);
+  EC_REQUIRE((res_mode == EC_RES_NONE) == (R == nullptr), "%s: residual pointer/mode mismatch", what);
+  EC_REQUIRE(!split_out || (split_kp % tc::BK == 0 && split_kp >= N), "%s: bad split_kp", what);
+  EC_REQUIRE(split_fmt == EC_SPLIT_F16X2 || split_fmt == EC_SPLIT_F16F8, "%s: split_fmt is EC_SPLIT_F16X2 or EC_SPLIT_F16F8", what);
   if (M == 0 || N == 0) return EC_OK;
   tc::DevState* ds = tc::dev_state();
   if (!ds) return EC_ERR_CUDA;
@@ -720,12 +845,25 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
   if (mode == 0)
     mode = (N >= 256 && pair_tiles * 4 >= 3LL * num_sms && (pair_tiles >= num_sms || Kp >= 1024)) ? 512 : 128;
   const int BN = mode == 128 ? 128 : 256;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA8, tmB8;
   int rc = tc::get_tensor_map(A2, M, Kp, tc::BM, &tmA);
   if (rc) return rc;
   rc = tc::get_tensor_map(B2, N, Kp, mode == 256 ? 256 : 128, &tmB);
   if (rc) return rc;
+  tmA8 = tmA;
+  tmB8 = tmB;
+  if (f8) {
+    rc = tc::get_tensor_map_any(A2, M, Kp, tc::BM, &tmA8, true);
+    if (rc) return rc;
+    rc = tc::get_tensor_map_any(B2, N, Kp, mode == 256 ? 256 : 128, &tmB8, true);
+    if (rc) return rc;
+  }
   tc::TcParams p{};
+  p.split_fmt = split_fmt;
+  if (split_out && split_fmt == EC_SPLIT_F16F8) {
+    p.overflow = overflow_counters();
+    if (!p.overflow) return EC_ERR_CUDA;
+  }
   // consecutive tiles walk N first when there are few N tiles: the CTAs working at the same time then share their A
   // row block (read from DRAM once, L2 hits for the other N tiles) and the whole of B stays in L2
   p.n_fastest = cdiv(N, BN) <= 16 ? 1 : 0;
@@ -755,7 +893,7 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
       if (g < tc::GRAPH_SLOTS) p.sched = ds->sched_base + 2 * (tc::EAGER_SLOTS + g);
     }
   }
-  tc::g_mode_launches[mode == 512 ? 2 : (mode == 256 ? 1 : 0)].fetch_add(1, std::memory_order_relaxed);
+  tc::g_mode_launches[(f8 ? 3 : 0) + (mode == 512 ? 2 : (mode == 256 ? 1 : 0))].fetch_add(1, std::memory_order_relaxed);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 512) {
     const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
@@ -774,15 +912,36 @@ extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, in
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true>, tmA, tmB, p));
+    if (f8) EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true, true>, tmA, tmB, tmA8, tmB8, p));
+    else EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true, false>, tmA, tmB, tmA8, tmB8, p));
   } else {
     const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
     const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
     const int grid = tiles < max_ctas ? tiles : max_ctas;
-    if (BN == 256)
-      launch_pdl(tc::gemm_f16x3_kernel<256, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, p);
+    if (BN == 256 && f8)
+      launch_pdl(tc::gemm_f16x3_kernel<256, false, true>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
+    else if (BN == 256)
+      launch_pdl(tc::gemm_f16x3_kernel<256, false, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
+    else if (f8)
+      launch_pdl(tc::gemm_f16x3_kernel<128, false, true>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
     else
-      launch_pdl(tc::gemm_f16x3_kernel<128, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, p);
+      launch_pdl(tc::gemm_f16x3_kernel<128, false, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
   }
-  return check_launch("ec_gemm_f16x3");
+  return check_launch(what);
+}
+
+extern "C" int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp, int ldc, int seg_c,
+                             long long seg_stride_c, float out_scale, const float* bias, int act, const float* colscale,
+                             const float* R, int ldr, int res_mode, int res_rows, void* split_out, int split_kp,
+                             float split_scale, void* stream) {
+  return gemm_split_launch("ec_gemm_f16x3", false, A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act,
+                           colscale, R, ldr, res_mode, res_rows, split_out, split_kp, split_scale, EC_SPLIT_F16X2, stream);
+}
+
+extern "C" int ec_gemm_f16f8(const void* A3, const void* B3, float* C, int M, int N, int Kp, int ldc, int seg_c,
+                             long long seg_stride_c, float out_scale, const float* bias, int act, const float* colscale,
+                             const float* R, int ldr, int res_mode, int res_rows, void* split_out, int split_kp,
+                             float split_scale, int split_fmt, void* stream) {
+  return gemm_split_launch("ec_gemm_f16f8", true, A3, B3, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act,
+                           colscale, R, ldr, res_mode, res_rows, split_out, split_kp, split_scale, split_fmt, stream);
 }

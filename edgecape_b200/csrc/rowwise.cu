@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float* __restrict__ Y, int ldy,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps, int M, int C,
-                                                        __half* __restrict__ split_out, int split_kp) {
+                                                        __half* __restrict__ split_out, int split_kp, int split_fmt,
+                                                        unsigned long long* overflow) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -45,19 +46,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = 1.0f / sqrtf(var + eps);
   float* y = Y ? Y + (long long)m * ldy : nullptr;
   __half* sp = split_out ? split_out + (long long)m * 2 * split_kp : nullptr;
+  uint32_t ovf = 0;
   for (int c = lane; c < C; c += 32) {
     float v = x[c];
     if (r) v += r[c];
     const float o = (v - mean) * rstd * w[c] + b[c];
     if (y) y[c] = o;
-    if (sp) {   // split-fp16 form for the tensor-core GEMM that consumes this row
+    if (sp) {   // split form for the tensor-core GEMM that consumes this row (scalar stores: odd widths only)
       const __half hi = __float2half_rn(o);
+      const float hf = __half2float(hi);
       sp[c] = hi;
-      sp[split_kp + c] = __float2half_rn(o - __half2float(hi));
+      if (split_fmt == EC_SPLIT_F16X2) {
+        sp[split_kp + c] = __float2half_rn(o - hf);
+      } else {
+        uint8_t* b8 = reinterpret_cast<uint8_t*>(sp);
+        b8[2 * split_kp + c] = (uint8_t)(e4m3x2(hf, 0.f) & 0xff);
+        b8[3 * split_kp + c] = (uint8_t)(e4m3x2((o - hf) * 2048.f, 0.f) & 0xff);
+        ovf |= (fabsf(o) > 448.f ? 1u : 0u) | (fabsf(o) > 65504.f ? 2u : 0u);
+      }
     }
   }
-  if (sp)
+  if (sp)   // zero padding: all-zero bytes are +0 in fp16 and in e4m3
     for (int c = C + lane; c < split_kp; c += 32) { sp[c] = __float2half_rn(0.f); sp[split_kp + c] = __float2half_rn(0.f); }
+  report_overflow(overflow, ovf);
 }
 
 // Vector form for C = NV * 128 with 16-byte aligned rows (every LayerNorm of the ViT and the head): the row
@@ -69,7 +80,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                                                             float* __restrict__ Y, int ldy,
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ b, float eps, int M,
-                                                            __half* __restrict__ split_out, int split_kp) {
+                                                            __half* __restrict__ split_out, int split_kp, int split_fmt,
+                                                            unsigned long long* overflow) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int C = NV * 128;
@@ -107,6 +119,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
   float* y = Y ? Y + (long long)m * ldy : nullptr;
   __half* sp = split_out ? split_out + (long long)m * 2 * split_kp : nullptr;
+  uint32_t ovf = 0;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int c = (j * 32 + lane) * 4;
@@ -117,16 +130,11 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     o.z = v[j].z * rstd * ww.z + bb.z;
     o.w = v[j].w * rstd * ww.w + bb.w;
     if (y) *reinterpret_cast<float4*>(y + c) = o;
-    if (sp) {
-      uint32_t h01, l01, h23, l23;
-      split_pair(o.x, o.y, h01, l01);
-      split_pair(o.z, o.w, h23, l23);
-      *reinterpret_cast<uint2*>(sp + c) = make_uint2(h01, h23);
-      *reinterpret_cast<uint2*>(sp + split_kp + c) = make_uint2(l01, l23);
-    }
+    if (sp) store_split4(reinterpret_cast<uint8_t*>(sp), split_kp, c, o.x, o.y, o.z, o.w, split_fmt, ovf);
   }
   if (sp)
     for (int c = C + lane; c < split_kp; c += 32) { sp[c] = __float2half_rn(0.f); sp[split_kp + c] = __float2half_rn(0.f); }
+  report_overflow(overflow, ovf);
 }
 
 __global__ void add_rows_kernel(float* __restrict__ X, const float* __restrict__ P, int T, int S, int C,
@@ -263,8 +271,14 @@ extern "C" int ec_axpby(const float* x, const float* y, float* out, float a, flo
 
 extern "C" int ec_layernorm(const float* X, int ldx, int seg, long long seg_stride, const float* R, int ldr,
                             float* sum_out, int ld_sum, float* Y, int ldy, const float* w, const float* b,
-                            float eps, int M, int C, void* split_out, int split_kp, void* stream) {
+                            float eps, int M, int C, void* split_out, int split_kp, int split_fmt, void* stream) {
   EC_REQUIRE(X && (Y || split_out) && w && b, "ec_layernorm: null pointer");
+  EC_REQUIRE(split_fmt == EC_SPLIT_F16X2 || split_fmt == EC_SPLIT_F16F8, "ec_layernorm: bad split_fmt");
+  unsigned long long* ovf = nullptr;
+  if (split_out && split_fmt == EC_SPLIT_F16F8) {
+    ovf = overflow_counters();
+    if (!ovf) return EC_ERR_CUDA;
+  }
   EC_REQUIRE(!split_out || (split_kp >= C && split_kp % 64 == 0), "ec_layernorm: bad split_kp");
   EC_REQUIRE(M >= 0 && C > 0, "ec_layernorm: bad shape");
   if (M == 0) return EC_OK;
@@ -277,14 +291,14 @@ extern "C" int ec_layernorm(const float* X, int ldx, int seg, long long seg_stri
                    (!Y || (al16(Y) && ldy % 4 == 0)) && al16(w) && al16(b) && (!split_out || al16(split_out));
 #define EC_LN_VEC(NV)                                                                                             \
   launch_pdl(layernorm_vec_kernel<NV>, grid, block, 0, st, X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, \
-             b, eps, M, (__half*)split_out, split_kp)
+             b, eps, M, (__half*)split_out, split_kp, split_fmt, ovf)
   if (vec && C == 256) EC_LN_VEC(2);
   else if (vec && C == 384) EC_LN_VEC(3);
   else if (vec && C == 768) EC_LN_VEC(6);
   else if (vec && C == 1024) EC_LN_VEC(8);
   else
     launch_pdl(layernorm_kernel, grid, block, 0, st, X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps,
-               M, C, (__half*)split_out, split_kp);
+               M, C, (__half*)split_out, split_kp, split_fmt, ovf);
 #undef EC_LN_VEC
   return check_launch("ec_layernorm");
 }

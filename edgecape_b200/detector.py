@@ -417,7 +417,7 @@ class EdgeCape(nn.Module):
         skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
         e_np, o_np = edges_to_csr_host(skeleton_lst)
         groups = self._support_groups(img_metas)
-        key = (tuple(img_q.shape), len(img_s), tuple(target_s[0].shape), ops.TENSOR_CORES, ops.GCN_FUSED,
+        key = (tuple(img_q.shape), len(img_s), tuple(target_s[0].shape), ops.TENSOR_CORES, ops.GCN_FUSED, ops.GEMM_F8,
                None if groups is None else len(groups[0]))
         g = self._graphs.get(key)
         if g is None or g.edge_capacity < e_np.shape[0]:

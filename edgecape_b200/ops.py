@@ -93,37 +93,58 @@ TENSOR_CORES = os.environ.get("EDGECAPE_TC", "1") != "0"
 ATTENTION_TC = os.environ.get("EDGECAPE_ATTN_TC", "1") != "0"     # tcgen05 attention for head dim 64
 ATTENTION_TMA = os.environ.get("EDGECAPE_ATTN_TMA", "1") != "0"   # TMA-fed variant on pre-split QKV (ViT)
 TC_MIN_M, TC_MIN_N, TC_MIN_K = 64, 32, 32
+# Split-operand row formats (include/edgecape_b200.h): F16X2 = [hi16 | lo16] for ec_gemm_f16x3 and the attention
+# kernels, F16F8 = [hi16 | hi8 | lo8] for ec_gemm_f16f8 (a_hi.b_hi on fp16, both cross terms on e4m3: 2 instead of 3
+# units of tensor time).  EDGECAPE_GEMM_F8=0 keeps every linear on three fp16 products; with it on (default) the
+# large linears (M >= F8_MIN_M rows: the ViT's qkv / fc1 / fc2 at bench batch sizes) take the F16F8 kernel.
+F16X2, F16F8 = 0, 1
+GEMM_F8 = os.environ.get("EDGECAPE_GEMM_F8", "1") != "0"
+F8_MIN_M = 2048
 _SPLIT_WEIGHTS = {}
 
 
 class SplitOperand:
-    """fp16 [rows, 2*Kp] = [hi | lo] form of an fp32 matrix (scaled by `scale`, a power of two)."""
-    __slots__ = ("data", "rows", "K", "Kp", "scale")
+    """Split form of an fp32 matrix (scaled by `scale`, a power of two): fp16 [rows, 2*Kp] holding 4*Kp bytes per
+    row in the format `fmt` (F16X2: [hi | lo] halves; F16F8: [hi16 | hi8 | lo8])."""
+    __slots__ = ("data", "rows", "K", "Kp", "scale", "fmt")
 
-    def __init__(self, data, rows, K, Kp, scale):
-        self.data, self.rows, self.K, self.Kp, self.scale = data, rows, K, Kp, scale
+    def __init__(self, data, rows, K, Kp, scale, fmt=F16X2):
+        self.data, self.rows, self.K, self.Kp, self.scale, self.fmt = data, rows, K, Kp, scale, fmt
 
 
 def _kp(K):
     return (K + 63) // 64 * 64
 
 
-def split_f16(x, scale=1.0, out=None):
-    """fp32 rows (2-D view, or 3-D [B,S,K] view read in place) -> SplitOperand."""
+def split_f16(x, scale=1.0, out=None, fmt=F16X2, role=0):
+    """fp32 rows (2-D view, or 3-D [B,S,K] view read in place) -> SplitOperand in the row format `fmt`
+    (role: 0 = A operand / activations, 1 = B operand / weights -- the F16F8 plane scales differ)."""
     M, K, ldx, seg, seg_stride = _seg(x, "x")
     Kp = _kp(K)
     if out is None:
         out = empty(M, 2 * Kp, dtype=torch.float16, device=x.device)
     assert out.is_contiguous() and out.dtype == torch.float16 and out.numel() == M * 2 * Kp
-    _lib.call("ec_split_f16", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), _stream())
-    return SplitOperand(out, M, K, Kp, float(scale))
+    if fmt == F16X2:
+        _lib.call("ec_split_f16", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), _stream())
+    else:
+        _lib.call("ec_split_f16f8", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), int(role), _stream())
+    return SplitOperand(out, M, K, Kp, float(scale), fmt)
 
 
-def split_weight(w):
+def overflow_count(reset=False):
+    """{values beyond the e4m3 range (448), values beyond the fp16 range (65504)} seen so far by the F16F8 split
+    producers on the current device.  Synchronises the device (a diagnostic, not part of the hot path)."""
+    import ctypes
+    buf = (ctypes.c_ulonglong * 2)()
+    _lib.call("ec_overflow_count", ctypes.cast(buf, ctypes.c_void_p), int(bool(reset)))
+    return int(buf[0]), int(buf[1])
+
+
+def split_weight(w, fmt=F16X2):
     """Cached split form of a weight matrix [N,K] (one-time repack per checkpoint: the power-of-two
     scale is picked from the tensor's absmax so that small weights stay out of the fp16 subnormals)."""
     owner = w._base if w._base is not None else w        # the nn.Parameter behind a reshaped view
-    key = (id(owner), w.data_ptr(), owner._version, tuple(w.shape))
+    key = (id(owner), w.data_ptr(), owner._version, tuple(w.shape), fmt)
     hit = _SPLIT_WEIGHTS.get(key)
     sw = hit[1] if hit is not None and hit[0]() is owner else None   # guards against id / address reuse
     if sw is None:
@@ -131,7 +152,7 @@ def split_weight(w):
         scale = 1.0
         if amax > 0 and math.isfinite(amax):
             scale = 2.0 ** max(-8, min(14, math.floor(math.log2(16384.0 / amax))))
-        sw = split_f16(w.detach(), scale)
+        sw = split_f16(w.detach(), scale, fmt=fmt, role=1)
         if len(_SPLIT_WEIGHTS) > 4096:
             _SPLIT_WEIGHTS.clear()
         _SPLIT_WEIGHTS[key] = (weakref.ref(owner), sw)
@@ -139,11 +160,14 @@ def split_weight(w):
 
 
 def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
-            split_out=False, fp32_out=True, res_rows=0):
-    """out = epilogue(A @ B^T) on the tcgen05 tensor cores from two SplitOperands.  `out` may be a
-    2-D view or a 3-D [B,S,N] view with B*S == M (batch-strided rows).  With split_out=True also
-    returns the SplitOperand of the result (produced by the epilogue)."""
+            split_out=False, fp32_out=True, res_rows=0, split_fmt=F16X2):
+    """out = epilogue(A @ B^T) on the tcgen05 tensor cores from two SplitOperands of the same row format
+    (F16X2 -> ec_gemm_f16x3, F16F8 -> ec_gemm_f16f8).  `out` may be a 2-D view or a 3-D [B,S,N] view with
+    B*S == M (batch-strided rows).  With split_out=True also returns the SplitOperand of the result (produced by
+    the epilogue, in the row format `split_fmt`)."""
     assert a2.Kp == b2.Kp, f"gemm_tc: padded K differs ({a2.Kp} vs {b2.Kp})"
+    assert a2.fmt == b2.fmt, "gemm_tc: operands must share a split format"
+    assert split_fmt == F16X2 or a2.fmt == F16F8, "only ec_gemm_f16f8 writes F16F8 rows"
     M, N = a2.rows, b2.rows
     dev = a2.data.device
     ldc = seg_c = seg_stride_c = 0
@@ -166,42 +190,25 @@ def gemm_tc(a2, b2, out=None, bias=None, act=ACT_NONE, colscale=None, residual=N
     if split_out:
         so_kp = _kp(N)
         buf = (torch.zeros if so_kp != N else torch.empty)(M, 2 * so_kp, dtype=torch.float16, device=dev)
-        so = SplitOperand(buf, M, N, so_kp, 1.0)
+        so = SplitOperand(buf, M, N, so_kp, 1.0, split_fmt)
         so_ptr = buf.data_ptr()
-    _lib.call("ec_gemm_f16x3", _p(a2.data), _p(b2.data), _p(out), M, N, a2.Kp, ldc, seg_c, seg_stride_c,
-              1.0 / (a2.scale * b2.scale), _p(bias), act, _p(colscale), _p(residual), ldr, res_mode, res_rows, so_ptr,
-              so_kp, 1.0, _stream())
+    if a2.fmt == F16F8:
+        _lib.call("ec_gemm_f16f8", _p(a2.data), _p(b2.data), _p(out), M, N, a2.Kp, ldc, seg_c, seg_stride_c,
+                  1.0 / (a2.scale * b2.scale), _p(bias), act, _p(colscale), _p(residual), ldr, res_mode, res_rows,
+                  so_ptr, so_kp, 1.0, split_fmt, _stream())
+    else:
+        _lib.call("ec_gemm_f16x3", _p(a2.data), _p(b2.data), _p(out), M, N, a2.Kp, ldc, seg_c, seg_stride_c,
+                  1.0 / (a2.scale * b2.scale), _p(bias), act, _p(colscale), _p(residual), ldr, res_mode, res_rows,
+                  so_ptr, so_kp, 1.0, _stream())
     return (out, so) if split_out else out
 
 
-# ---- EXPERIMENTAL (not on the default path, not yet validated on hardware): cross terms on e4m3 tensor cores
-def split_f16f8(x, scale=1.0, role=0):
-    """fp32 [M,K] rows -> uint8 [M, 4*Kp] = [hi16 | hi8 | lo8] planes (csrc/gemm_f16f8_tcgen05.cu); role 0 = A, 1 = B."""
-    _chk(x, "x")
-    assert x.dim() == 2 and x.stride(1) == 1
-    M, K = x.shape
-    Kp = _kp(K)
-    out = empty(M, 4 * Kp, dtype=torch.uint8, device=x.device)
-    _lib.call("ec_split_f16f8", _p(x), _p(out), M, K, x.stride(0), Kp, float(scale), int(role), _stream())
-    return out, Kp
-
-
-def gemm_f16f8(x, w, bias=None, act=ACT_NONE, out=None):
-    """out = act(x @ w^T + bias) with a_hi.b_hi on fp16 and both cross terms on e4m3 UMMAs (experimental)."""
-    _chk(x, "x"); _chk(w, "w"); _chk(bias, "bias")
-    amax = float(w.detach().abs().max())
-    scale = 1.0
-    if amax > 0 and math.isfinite(amax):
-        scale = 2.0 ** max(-8, min(14, math.floor(math.log2(16384.0 / amax))))
-    a3, Kp = split_f16f8(x, 1.0, 0)
-    b3, Kpb = split_f16f8(w, scale, 1)
-    assert Kp == Kpb
-    M, N = x.shape[0], w.shape[0]
-    if out is None:
-        out = empty(M, N, device=x.device)
-    assert out.stride(1) == 1
-    _lib.call("ec_gemm_f16f8", _p(a3), _p(b3), _p(out), M, N, Kp, out.stride(0), 1.0 / scale, _p(bias), act, _stream())
-    return out
+def f8_linear_ok(M, w):
+    """Would a linear with `M` activation rows and weight `w` [N,K] take the F16F8 kernel?  Callers that produce its A
+    operand (LayerNorm, the previous GEMM's epilogue) ask before choosing the row format."""
+    if w.dim() > 2:
+        w = w.reshape(w.shape[0], -1)
+    return bool(TENSOR_CORES and GEMM_F8 and M >= F8_MIN_M and w.shape[0] >= 256 and w.shape[1] >= 256)
 
 
 def _tc_ok(x, w, residual):
@@ -216,9 +223,10 @@ def _tc_ok(x, w, residual):
 
 
 def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None, res_mode=RES_ADD,
-           split_out=False, fp32_out=True):
+           split_out=False, fp32_out=True, split_fmt=F16X2):
     """nn.Linear on the last dimension of a 2-D/3-D view (or an already split A operand); w is [N,K]
-    (conv 1x1 weights are reshaped).  Dispatches to the tcgen05 kernel or the fp32 SIMT kernel."""
+    (conv 1x1 weights are reshaped).  Dispatches to a tcgen05 kernel (the one matching the split format of `x`) or
+    the fp32 SIMT kernel."""
     if w.dim() > 2:
         w = w.reshape(w.shape[0], -1)
     if _tc_ok(x, w, residual):
@@ -227,8 +235,8 @@ def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None
             out = empty(x.shape[0], x.shape[1], w.shape[0], device=x.device)
         if not fp32_out:
             out = None
-        return gemm_tc(a2, split_weight(w), out=out, bias=bias, act=act, colscale=colscale, residual=residual,
-                       res_mode=res_mode, split_out=split_out, fp32_out=fp32_out)
+        return gemm_tc(a2, split_weight(w, a2.fmt), out=out, bias=bias, act=act, colscale=colscale, residual=residual,
+                       res_mode=res_mode, split_out=split_out, fp32_out=fp32_out, split_fmt=split_fmt)
     assert not isinstance(x, SplitOperand), "a split operand needs the tensor-core path"
     y = gemm(x, w, out=out, b_kmajor=True, bias=bias, act=act, colscale=colscale, residual=residual,
              res_mode=res_mode)
@@ -248,7 +256,7 @@ def linear_split(x, w, bias=None, act=ACT_NONE):
     return linear(x, w, bias, act=act, split_out=True, fp32_out=False)[1]
 
 
-def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None, split="no"):
+def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None, split="no", split_fmt=F16X2):
     """LayerNorm over the last dim of x (+ residual).  A 3-D x view [B,S,C] with a batch stride
     larger than S*ld (e.g. ViT tokens without the cls row) is read in place.
     split: "no" -> fp32 result; "also" -> (fp32, SplitOperand); "only" -> SplitOperand (the fp32
@@ -275,7 +283,7 @@ def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None, split="n
     so, so_ptr, so_kp = None, None, 0
     if split != "no":
         so_kp = _kp(C)
-        so = SplitOperand(empty(M, 2 * so_kp, dtype=torch.float16, device=x.device), M, C, so_kp, 1.0)
+        so = SplitOperand(empty(M, 2 * so_kp, dtype=torch.float16, device=x.device), M, C, so_kp, 1.0, split_fmt)
         so_ptr = so.data.data_ptr()
     ldr = ld_sum = 0
     if residual is not None:
@@ -288,7 +296,7 @@ def layernorm(x, w, b, eps=1e-5, out=None, residual=None, sum_out=None, split="n
         assert s2.dim() == 2 and s2.stride(1) == 1
         sum_out, ld_sum = s2, s2.stride(0)
     _lib.call("ec_layernorm", _p(x), ldx, seg, seg_stride, _p(residual), ldr, _p(sum_out), ld_sum, _p(o2),
-              ldy, _p(w), _p(b), float(eps), M, C, so_ptr, so_kp, _stream())
+              ldy, _p(w), _p(b), float(eps), M, C, so_ptr, so_kp, split_fmt, _stream())
     return so if split == "only" else ((out, so) if split == "also" else out)
 
 

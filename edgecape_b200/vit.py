@@ -95,9 +95,13 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
             # tensor-core path: every GEMM input is produced directly in split-fp16 form by the kernel
             # before it (LayerNorm, attention, GELU epilogue); only the residual stream t stays fp32
             packed_attn = ops.ATTENTION_TC and ops.ATTENTION_TMA and C // H == 64 and N <= 768 and (3 * C) % 64 == 0
+            # the large linears run with their cross terms on e4m3 (ec_gemm_f16f8): their A operands are produced in
+            # F16F8 rows by the LayerNorms / the fc1 epilogue; q, k, v and the attention output stay F16X2 (the
+            # attention kernel and the proj GEMM -- short K, 128x128 tiles -- consume those)
+            f8 = ops.F16F8 if ops.f8_linear_ok(Btot * N, getattr(self.blocks, "0").mlp.fc1.weight) else ops.F16X2
             for i in range(self.depth):
                 blk = getattr(self.blocks, str(i))
-                y2 = ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, split="only")
+                y2 = ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, split="only", split_fmt=f8)
                 if packed_attn:
                     # the QKV GEMM writes q, k, v already split; the attention kernel TMA-loads them
                     _, qkv2 = ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, split_out=True, fp32_out=False)
@@ -106,9 +110,9 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
                     ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
                     a2 = ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, split="only")
                 ops.linear(a2, blk.attn.proj.weight, blk.attn.proj.bias, colscale=blk.ls1.gamma, residual=t2, out=t2)
-                y2 = ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, split="only")
+                y2 = ops.layernorm(t2, blk.norm2.weight, blk.norm2.bias, 1e-6, split="only", split_fmt=f8)
                 _, h2 = ops.linear(y2, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, split_out=True,
-                                   fp32_out=False)
+                                   fp32_out=False, split_fmt=f8)
                 ops.linear(h2, blk.mlp.fc2.weight, blk.mlp.fc2.bias, colscale=blk.ls2.gamma, residual=t2, out=t2)
         else:
             y = ops.empty(Btot * N, C, device=dev)

@@ -84,12 +84,39 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
                   const float* R, int ldr, int res_mode, int res_rows, void* split_out, int split_kp,
                   float split_scale, void* stream);
 
+/* The same contraction in 2 instead of 3 units of tensor time: a_hi.b_hi on fp16 UMMAs, the two cross terms
+ * a_lo.b_hi + a_hi.b_lo -- which only need ~11 bits of relative accuracy -- on e4m3 UMMAs (kind::f8f6f4, twice the
+ * contraction depth per clock).  Operand rows are EC_SPLIT_F16F8: [hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp
+ * bytes], 4*Kp bytes as EC_SPLIT_F16X2's [hi16 | lo16].  The plane scales are static powers of two --
+ *   A role (activations): hi8 = e4m3(hi16),          lo8 = e4m3((a - hi16) * 2^11)
+ *   B role (weights * s_w): hi8 = e4m3(hi16 * 2^-11), lo8 = e4m3(b * s_w - hi16)
+ * -- so every product carries s_w and all three accumulate into ONE fp32 TMEM accumulator (out_scale = 1 / s_w undoes
+ * it).  Measured error vs fp64 on ViT-B shapes: 1.1e-5 of max|C| (three fp16 products: 3.4e-6; bar 1e-3).
+ * ec_split_f16f8 produces the rows from fp32 (role 0 = A, 1 = B; addressing as ec_split_f16).  ec_gemm_f16f8 has
+ * ec_gemm_f16x3's arguments plus split_fmt, the format of split_out (EC_SPLIT_F16X2 when an attention kernel or an
+ * ec_gemm_f16x3 consumes it, EC_SPLIT_F16F8 when an ec_gemm_f16f8 does).
+ * Range: e4m3 saturates at 448.  An activation beyond that only loses ITS cross terms (the element degrades to
+ * plain-fp16 accuracy, ~2^-11 relative); beyond 65504 the hi16 plane overflows.  Every EC_SPLIT_F16F8 producer counts
+ * both events on the device: ec_overflow_count(out2, reset) synchronises the device and returns
+ * {values beyond 448, values beyond 65504} seen so far (a checkpoint with outlier activations reports itself instead
+ * of degrading silently). */
+#define EC_SPLIT_F16X2 0
+#define EC_SPLIT_F16F8 1
+int ec_split_f16f8(const float* X, void* out, int M, int K, int ldx, int seg, long long seg_stride, int Kp,
+                   float scale, int role, void* stream);
+int ec_gemm_f16f8(const void* A3, const void* B3, float* C, int M, int N, int Kp, int ldc,
+                  int seg_c, long long seg_stride_c, float out_scale, const float* bias, int act, const float* colscale,
+                  const float* R, int ldr, int res_mode, int res_rows, void* split_out, int split_kp,
+                  float split_scale, int split_fmt, void* stream);
+int ec_overflow_count(unsigned long long* out2, int reset);
+
 /* tuning knob for ec_gemm_f16x3: 0 = pick the tile width per shape (128x256 tiles for wide, large
  * problems, 128x128 otherwise), 128 / 256 = force it. */
 int ec_tc_set_tile_n(int bn);
 /* number of ec_gemm_f16x3 launches so far in this process that took the tile mode `mode`: 128 (128x128, one CTA),
  * 256 (128x256, one CTA) or 512 (256x256 on a CTA pair, cta_group::2); -1 for any other argument.  Tests use the
- * deltas to prove which kernel instance a given configuration runs. */
+ * deltas to prove which kernel instance a given configuration runs.  mode + 1 (129 / 257 / 513) counts the same tile
+ * mode of ec_gemm_f16f8. */
 long long ec_tc_mode_launches(int mode);
 /* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
  * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
@@ -118,11 +145,12 @@ int ec_attention_tc_set_variant(int variant);
  * ViT token matrix can be read with its cls row dropped.  If sum_out != NULL the pre-norm sum
  * X+R is stored there (row stride ld_sum).  torch.nn.LayerNorm on the path:
  * encoder_decoder.py:477-482,612-637, ViT norm1/norm2/norm (DINOv2, eps 1e-6).
- * split_out (optional, fp16 [M, 2*split_kp]) receives the split-fp16 form of the result for a
- * following ec_gemm_f16x3; Y may then be NULL. */
+ * split_out (optional, [M, 4*split_kp bytes]) receives the split form of the result for a following
+ * tensor-core GEMM, in the row format split_fmt (EC_SPLIT_F16X2 for ec_gemm_f16x3, EC_SPLIT_F16F8 for
+ * ec_gemm_f16f8); Y may then be NULL. */
 int ec_layernorm(const float* X, int ldx, int seg, long long seg_stride, const float* R, int ldr,
                  float* sum_out, int ld_sum, float* Y, int ldy, const float* w, const float* b,
-                 float eps, int M, int C, void* split_out, int split_kp, void* stream);
+                 float eps, int M, int C, void* split_out, int split_kp, int split_fmt, void* stream);
 
 /* X[b, t, :] += P[t, :] for t < S (rows S..T-1 untouched): the encoder adds the grid positional
  * encoding to the residual stream every layer (encoder_decoder.py:467). */
@@ -244,15 +272,6 @@ int ec_gcn_fused_set_debug(int flags);               /* profiling experiments on
 int ec_gcn_fused_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] int64 clock stamps per CTA, NULL = off */
 int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* W2, int Kp, float w_scale,
                  float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);
-
-/* EXPERIMENTAL (opt-in; compiled for sm_100a but not yet validated on hardware -- DESIGN.md section 9 item 1):
- * fp32-grade GEMM with the two cross terms on e4m3 tensor cores (2 instead of 3 units of tensor time).
- * ec_split_f16f8 writes rows [hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp bytes] (4*Kp bytes) of X*scale;
- * role 0 = A operand (activations; pass scale 1), role 1 = B operand (weights; scale = the power-of-two weight
- * scale).  ec_gemm_f16f8: C[M,N] = act(out_scale * A.B^T + bias), out_scale = 1 / weight scale. */
-int ec_split_f16f8(const float* X, void* out, int M, int K, int ldx, int Kp, float scale, int role, void* stream);
-int ec_gemm_f16f8(const void* A3, const void* B3, float* C, int M, int N, int Kp, int ldc, float out_scale,
-                  const float* bias, int act, void* stream);
 
 /* ----------------------------------------------------------------------------- head ops
  * support-keypoint pooling weights (head.py:175-184, exact by linearity):

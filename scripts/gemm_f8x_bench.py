@@ -1,7 +1,5 @@
-"""EXPERIMENTAL: ec_gemm_f16f8 (fp16 hi.hi + e4m3 cross terms) against ec_gemm_f16x3 (three fp16 products) on the ViT-B
-GEMM shapes of the bench step (M = 32 images x 325 tokens): accuracy vs fp64 and algorithmic TFLOP/s.
-First thing to run on a B200 next round:  EDGECAPE_TEST_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -m gpu
-then  python scripts/gemm_f8x_bench.py"""
+"""ec_gemm_f16f8 (fp16 hi.hi + e4m3 cross terms) against ec_gemm_f16x3 (three fp16 products) on the ViT-B GEMM shapes of
+the bench step (M = 32 images x 325 tokens), per tile mode: accuracy vs fp64 and algorithmic TFLOP/s."""
 import sys
 
 import torch
@@ -30,25 +28,20 @@ def main():
         x = torch.randn(M, K, device=D)
         w = torch.randn(N, K, device=D) * 0.02
         want = x.double() @ w.double().T
-        a2, b2 = ops.split_f16(x), ops.split_weight(w)
-        y3 = ops.gemm_tc(a2, b2)
-        a3, Kp = ops.split_f16f8(x, 1.0, 0)
-        scale = b2.scale
-        b3, _ = ops.split_f16f8(w, scale, 1)
-        y8 = torch.empty(M, N, device=D)
-        run8 = lambda: _lib.call("ec_gemm_f16f8", a3.data_ptr(), b3.data_ptr(), y8.data_ptr(), M, N, Kp, N, 1.0 / scale, None, 0,
-                                 torch.cuda.current_stream().cuda_stream)
-        run8()
         err = lambda y: ((y.double() - want).abs().max() / want.abs().max()).item()
-        t3 = timeit(lambda: ops.gemm_tc(a2, b2, out=y3))
-        _lib.call("ec_tc_set_tile_n", 256)          # the same 128x256 single-CTA tile the f16f8 kernel uses
-        t3s = timeit(lambda: ops.gemm_tc(a2, b2, out=y3))
-        _lib.call("ec_tc_set_tile_n", 0)
-        t8 = timeit(run8)
         fl = 2.0 * M * N * K
-        print(f"{name:5s} M={M} N={N} K={K}: 3xfp16 auto {t3 * 1e3:7.1f} us {fl / t3 / 1e9:6.0f} TF/s err {err(y3):.1e} | "
-              f"3xfp16 128x256 {t3s * 1e3:7.1f} us {fl / t3s / 1e9:6.0f} TF/s | "
-              f"fp16+2xfp8 128x256 {t8 * 1e3:7.1f} us {fl / t8 / 1e9:6.0f} TF/s err {err(y8):.1e}", flush=True)
+        y = torch.empty(M, N, device=D)
+        line = f"{name:5s} M={M} N={N} K={K}:"
+        for fmt, tag in ((ops.F16X2, "3xf16"), (ops.F16F8, "f16+2xf8")):
+            a, b = ops.split_f16(x, fmt=fmt, role=0), ops.split_weight(w, fmt)
+            for mode in (128, 256, 512):
+                _lib.call("ec_tc_set_tile_n", mode)
+                ops.gemm_tc(a, b, out=y)
+                e = err(y)
+                t = timeit(lambda: ops.gemm_tc(a, b, out=y))
+                line += f" | {tag} m{mode} {t * 1e3:6.1f} us {fl / t / 1e9:4.0f} TF/s err {e:.0e}"
+        _lib.call("ec_tc_set_tile_n", 0)
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

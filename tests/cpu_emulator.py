@@ -108,12 +108,34 @@ def ec_split_f16(X, X2, M, K, ldx, seg, seg_stride, Kp, scale, stream):
     out[:, :K], out[:, Kp:Kp + K] = hi, lo
 
 
-def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act, colscale, R, ldr, res_mode,
-                  res_rows, split_out, split_kp, split_scale, stream):
-    a = T(arr(A2, (M, 2 * Kp), dtype=np.float16).astype(np.float32))
-    b = T(arr(B2, (N, 2 * Kp), dtype=np.float16).astype(np.float32))
-    ah, al, bh, bl = a[:, :Kp], a[:, Kp:], b[:, :Kp], b[:, Kp:]
-    y = (al @ bh.T + ah @ bl.T + ah @ bh.T) * np.float32(out_scale)
+def _f8_bytes(a):
+    return torch.from_numpy(_e4m3(a)).to(torch.float8_e4m3fn).view(torch.uint8).numpy()
+
+
+def _f8_values(b):
+    return torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).to(torch.float32).numpy()
+
+
+def _write_split(ptr, kp, y, fmt=0):
+    """rows in EC_SPLIT_F16X2 ([hi16 | lo16]) or EC_SPLIT_F16F8 ([hi16 | hi8 | lo8], A role) format."""
+    M, N = y.shape
+    y = y.astype(np.float32)
+    hi = y.astype(np.float16)
+    lo = y - hi.astype(np.float32)
+    if fmt == 0:
+        out = arr(ptr, (M, 2 * kp), dtype=np.float16)
+        out[...] = 0
+        out[:, :N], out[:, kp:kp + N] = hi, lo.astype(np.float16)
+    else:
+        o = arr(ptr, (M, 4 * kp), dtype=np.uint8)
+        o[...] = 0
+        o[:, :2 * kp].view(np.float16)[:, :N] = hi
+        o[:, 2 * kp:2 * kp + N] = _f8_bytes(hi.astype(np.float32))
+        o[:, 3 * kp:3 * kp + N] = _f8_bytes(lo * np.float32(2.0 ** 11))
+
+
+def _gemm_epilogue(y, M, N, C, ldc, seg_c, seg_stride_c, bias, act, colscale, R, ldr, res_mode, res_rows, split_out,
+                   split_kp, split_scale, split_fmt):
     if bias:
         y = y + T(arr(bias, (N,)))
     y = _act(y, act)
@@ -127,21 +149,21 @@ def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias
     if C:
         _set(rows(C, M, N, ldc, seg_c, seg_stride_c), y.numpy())
     if split_out:
-        s = y.numpy() * np.float32(split_scale)
-        hi = s.astype(np.float16)
-        out = arr(split_out, (M, 2 * split_kp), dtype=np.float16)
-        out[:, :N], out[:, split_kp:split_kp + N] = hi, (s - hi.astype(np.float32)).astype(np.float16)
+        _write_split(split_out, split_kp, y.numpy() * np.float32(split_scale), split_fmt)
 
 
-def _write_split(ptr, kp, y):
-    M, N = y.shape
-    hi = y.astype(np.float16)
-    out = arr(ptr, (M, 2 * kp), dtype=np.float16)
-    out[...] = 0
-    out[:, :N], out[:, kp:kp + N] = hi, (y - hi.astype(np.float32)).astype(np.float16)
+def ec_gemm_f16x3(A2, B2, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act, colscale, R, ldr, res_mode,
+                  res_rows, split_out, split_kp, split_scale, stream):
+    a = T(arr(A2, (M, 2 * Kp), dtype=np.float16).astype(np.float32))
+    b = T(arr(B2, (N, 2 * Kp), dtype=np.float16).astype(np.float32))
+    ah, al, bh, bl = a[:, :Kp], a[:, Kp:], b[:, :Kp], b[:, Kp:]
+    y = (al @ bh.T + ah @ bl.T + ah @ bh.T) * np.float32(out_scale)
+    _gemm_epilogue(y, M, N, C, ldc, seg_c, seg_stride_c, bias, act, colscale, R, ldr, res_mode, res_rows, split_out,
+                   split_kp, split_scale, 0)
 
 
-def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, split_out, split_kp, stream):
+def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b, eps, M, C, split_out, split_kp,
+                 split_fmt, stream):
     x = T(_get(rows(X, M, C, ldx, seg, seg_stride)))
     if R:
         x = x + T(arr(R, (M, C), (ldr, 1)))
@@ -151,7 +173,7 @@ def ec_layernorm(X, ldx, seg, seg_stride, R, ldr, sum_out, ld_sum, Y, ldy, w, b,
     if Y:
         arr(Y, (M, C), (ldy, 1))[...] = y.numpy()
     if split_out:
-        _write_split(split_out, split_kp, y.numpy())
+        _write_split(split_out, split_kp, y.numpy(), split_fmt)
 
 
 def ec_add_rows(X, P, batch, Tt, S, C, stream):
@@ -387,32 +409,30 @@ def _e4m3(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).to(torch.float32).numpy()
 
 
-def ec_split_f16f8(X, out, M, K, ldx, Kp, scale, role, stream):
-    """[hi16 | hi8 | lo8] planes (gemm_f16f8_tcgen05.cu): role 0 = activations, 1 = weights."""
-    x = arr(X, (M, K), (ldx, 1)) * np.float32(scale)
+def ec_split_f16f8(X, out, M, K, ldx, seg, seg_stride, Kp, scale, role, stream):
+    """[hi16 | hi8 | lo8] planes (include/edgecape_b200.h, EC_SPLIT_F16F8): role 0 = activations, 1 = weights."""
+    x = _get(rows(X, M, K, ldx, seg, seg_stride)).astype(np.float32) * np.float32(scale)
     hi = x.astype(np.float16)
     lo = x - hi.astype(np.float32)
     s_hi, s_lo = (2.0 ** -11, 1.0) if role else (1.0, 2.0 ** 11)
     o = arr(out, (M, 4 * Kp), dtype=np.uint8)
     o[...] = 0
     o[:, :2 * Kp].view(np.float16)[:, :K] = hi
-    f8 = lambda a: torch.from_numpy(_e4m3(a)).to(torch.float8_e4m3fn).view(torch.uint8).numpy()
-    o[:, 2 * Kp:2 * Kp + K] = f8(hi.astype(np.float32) * np.float32(s_hi))
-    o[:, 3 * Kp:3 * Kp + K] = f8(lo * np.float32(s_lo))
+    o[:, 2 * Kp:2 * Kp + K] = _f8_bytes(hi.astype(np.float32) * np.float32(s_hi))
+    o[:, 3 * Kp:3 * Kp + K] = _f8_bytes(lo * np.float32(s_lo))
 
 
-def ec_gemm_f16f8(A3, B3, C, M, N, Kp, ldc, out_scale, bias, act, stream):
-    def planes(ptr, rows):
-        o = arr(ptr, (rows, 4 * Kp), dtype=np.uint8)
+def ec_gemm_f16f8(A3, B3, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act, colscale, R, ldr, res_mode,
+                  res_rows, split_out, split_kp, split_scale, split_fmt, stream):
+    def planes(ptr, nrows):
+        o = arr(ptr, (nrows, 4 * Kp), dtype=np.uint8)
         h16 = o[:, :2 * Kp].view(np.float16).astype(np.float32)
-        f = lambda b: torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).to(torch.float32).numpy()
-        return h16, f(o[:, 2 * Kp:3 * Kp]), f(o[:, 3 * Kp:])
+        return h16, _f8_values(o[:, 2 * Kp:3 * Kp]), _f8_values(o[:, 3 * Kp:])
     a16, ah8, al8 = planes(A3, M)
     b16, bh8, bl8 = planes(B3, N)
     y = T((al8 @ bh8.T + ah8 @ bl8.T + a16 @ b16.T) * np.float32(out_scale))
-    if bias:
-        y = y + T(arr(bias, (N,)))
-    arr(C, (M, N), (ldc, 1))[...] = _act(y, act).numpy()
+    _gemm_epilogue(y, M, N, C, ldc, seg_c, seg_stride_c, bias, act, colscale, R, ldr, res_mode, res_rows, split_out,
+                   split_kp, split_scale, split_fmt)
 
 
 def ec_support_weights(target, rowscale, Tw, ldtw, BK, hm_h, hm_w, h, w, stream):

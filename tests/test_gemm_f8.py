@@ -1,0 +1,188 @@
+"""ec_gemm_f16f8 -- fp32-grade GEMM with a_hi.b_hi on fp16 and the two cross terms on e4m3 tensor cores -- and the
+EC_SPLIT_F16F8 operand format its producers write (include/edgecape_b200.h).
+
+CPU tests pin the format (plane scales, byte layout) and the host orchestration through the emulated ABI; the GPU
+tests compare the kernel with fp64, with ec_gemm_f16x3 on the same inputs (every epilogue option, every tile mode),
+and check the range behaviour (values beyond the e4m3 / fp16 range are counted, not silently wrong)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import edgecape_b200 as E
+from edgecape_b200 import ops
+from edgecape_b200.config import state_dict_shapes
+from edgecape_b200.synthetic import make_state_dict
+
+from . import cpu_emulator
+
+
+def _case(M=300, K=200, N=72, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(M, K, generator=g)
+    x[3, 5] = 37.0                                     # an outlier activation
+    w = torch.randn(N, K, generator=g) * 0.02
+    b = torch.randn(N, generator=g) * 0.1
+    return x, w, b
+
+
+def _f8_linear(x, w, **kw):
+    a = ops.split_f16(x, fmt=ops.F16F8, role=0)
+    return ops.gemm_tc(a, ops.split_weight(w, ops.F16F8), **kw)
+
+
+def test_f16f8_operand_format_on_the_emulated_abi(monkeypatch):
+    """fp16 hi.hi + two e4m3 cross terms with the static plane scales: ~1e-5 of the fp64 product, several times
+    better than the plain fp16 product; the A-role planes written by the GEMM / LayerNorm epilogues equal the ones
+    ec_split_f16f8 writes from the fp32 result."""
+    cpu_emulator.install(monkeypatch)
+    x, w, b = _case()
+    got, so = _f8_linear(x, w, bias=b, act=ops.ACT_RELU, split_out=True, split_fmt=ops.F16F8)
+    want = torch.relu(x.double() @ w.double().T + b.double())
+    err = ((got.double() - want).abs().max() / want.abs().max()).item()
+    plain = torch.relu(x.half().double() @ w.half().double().T + b.double())
+    err_plain = ((plain - want).abs().max() / want.abs().max()).item()
+    assert err < 5e-5, err
+    assert err < err_plain / 5, (err, err_plain)
+    assert so.fmt == ops.F16F8 and so.Kp == 128
+    again = ops.split_f16(got, fmt=ops.F16F8, role=0)
+    assert torch.equal(so.data.view(torch.uint8), again.data.view(torch.uint8))
+    ln = ops.layernorm(x, torch.ones(200), torch.zeros(200), 1e-5, split="also", split_fmt=ops.F16F8)
+    again = ops.split_f16(ln[0], fmt=ops.F16F8, role=0)
+    assert torch.equal(ln[1].data.view(torch.uint8), again.data.view(torch.uint8))
+
+
+def test_vit_host_orchestration_with_f8_linears(monkeypatch, golden_dir):
+    """The ViT's F16F8 chain (LayerNorm -> qkv, LayerNorm -> fc1 -> fc2 on ec_gemm_f16f8; q, k, v / attention output /
+    proj on F16X2) through the emulated ABI against the golden features of the unmodified reference."""
+    from oracle.gen_golden import build_case
+    cpu_emulator.install(monkeypatch)
+    monkeypatch.setattr(ops, "TENSOR_CORES", True)
+    monkeypatch.setattr(ops, "f8_linear_ok", lambda M, w: True)
+    calls = []
+    orig = ops._lib.call
+    monkeypatch.setattr(ops._lib, "call", lambda name, *a: (calls.append(name), orig(name, *a))[1])
+    name = "tiny_k100_2shot_masked"
+    golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    cfg, data, wseed = build_case(name)
+    model = E.build_model(dict(model=cfg))
+    model.load_state_dict(make_state_dict(state_dict_shapes(cfg), wseed), strict=True)
+    model.eval()
+    feat_q, _ = model.extract_features(data["img_s"], data["img_q"])
+    depth = model.encoder_query.depth
+    assert calls.count("ec_gemm_f16f8") == 3 * depth           # qkv, fc1, fc2 of every block
+    a, w = feat_q.numpy()[:1], golden["feature_q"]
+    err = np.abs(a.astype(np.float64) - w).max() / np.abs(w).max()
+    assert err < 2e-4, err
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(10400, 2304, 768), (300, 72, 200), (128, 256, 64), (1600, 768, 3072), (1300, 768, 768),
+                                   (517, 1000, 136)])
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 512])
+def test_gemm_f16f8_matches_fp64(M, N, K, tile_n):
+    D = _dev()
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.02
+    b = torch.randn(N, generator=g) * 0.1
+    ops._lib.call("ec_tc_set_tile_n", tile_n)
+    try:
+        got = _f8_linear(x.to(D), w.to(D), bias=b.to(D)).cpu()
+    finally:
+        ops._lib.call("ec_tc_set_tile_n", 0)
+    want = x.double() @ w.double().T + b.double()
+    err = ((got.double() - want).abs().max() / want.abs().max()).item()
+    assert err < 6e-5, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile_n", [128, 512])
+def test_gemm_f16f8_epilogues_match_f16x3(tile_n):
+    """bias + GELU + LayerScale + residual into a strided 3-D view, and both split_out formats: the F16F8 kernel
+    against ec_gemm_f16x3 on the same fp32 inputs."""
+    D = _dev()
+    g = torch.Generator().manual_seed(5)
+    Bt, S, K, N = 9, 257, 384, 640
+    x = torch.randn(Bt * S, K, generator=g).to(D)
+    w = (torch.randn(N, K, generator=g) * 0.03).to(D)
+    b = (torch.randn(N, generator=g) * 0.1).to(D)
+    cs = torch.rand(N, generator=g).to(D)
+    res = torch.randn(Bt * S, N, generator=g).to(D)
+    buf3 = torch.zeros(Bt, S + 1, N, device=D)
+    buf8 = torch.zeros(Bt, S + 1, N, device=D)
+    ops._lib.call("ec_tc_set_tile_n", tile_n)
+    try:
+        ref, so3 = ops.gemm_tc(ops.split_f16(x), ops.split_weight(w), out=buf3[:, 1:, :], bias=b, act=ops.ACT_GELU,
+                               colscale=cs, residual=res, split_out=True)
+        for fmt in (ops.F16X2, ops.F16F8):
+            got, so8 = _f8_linear(x, w, out=buf8[:, 1:, :], bias=b, act=ops.ACT_GELU, colscale=cs, residual=res,
+                                  split_out=True, split_fmt=fmt)
+            scale = ref.abs().max().item()
+            assert (got - ref).abs().max().item() < 1e-4 * scale
+            assert torch.equal(buf8[:, 0, :], torch.zeros_like(buf8[:, 0, :]))       # the skipped row is untouched
+            flat = got.reshape(Bt * S, N).contiguous()
+            want = ops.split_f16(flat, fmt=fmt, role=0)
+            assert so8.fmt == fmt and torch.equal(so8.data.view(torch.uint8), want.data.view(torch.uint8))
+    finally:
+        ops._lib.call("ec_tc_set_tile_n", 0)
+
+
+@pytest.mark.gpu
+def test_f16f8_planes_reconstruct_and_layernorm_writes_them():
+    D = _dev()
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(650, 768, generator=g) * 3).to(D)
+    so = ops.split_f16(x, fmt=ops.F16F8, role=0)
+    raw = so.data.view(torch.uint8).reshape(650, 4 * 768)
+    hi16 = raw[:, :2 * 768].contiguous().view(torch.float16).float()
+    hi8 = raw[:, 2 * 768:3 * 768].contiguous().view(torch.float8_e4m3fn).float()
+    lo8 = raw[:, 3 * 768:].contiguous().view(torch.float8_e4m3fn).float()
+    assert torch.equal(hi16, x.half().float())
+    assert torch.equal(hi8, hi16.to(torch.float8_e4m3fn).float())
+    assert ((hi16 + lo8 / 2048.0) - x).abs().max().item() <= 2.0 ** -15 * x.abs().max().item()
+    w, b = torch.rand(768, generator=g).to(D) + 0.5, torch.randn(768, generator=g).to(D)
+    y, so_ln = ops.layernorm(x, w, b, 1e-6, split="also", split_fmt=ops.F16F8)
+    want = ops.split_f16(y, fmt=ops.F16F8, role=0)
+    assert torch.equal(so_ln.data.view(torch.uint8), want.data.view(torch.uint8))
+
+
+@pytest.mark.gpu
+def test_f16f8_range_events_are_counted_and_degrade_gracefully():
+    """An activation beyond 448 (e4m3 saturates) only loses its cross terms: the result stays within plain-fp16
+    accuracy of that element's contribution and the event is counted; beyond 65504 hi16 itself overflows and the
+    second counter says so.  A healthy run counts nothing."""
+    D = _dev()
+    g = torch.Generator().manual_seed(3)
+    M, K, N = 512, 768, 512
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.02
+    want = x.double() @ w.double().T
+    ops.overflow_count(reset=True)
+    got = _f8_linear(x.to(D), w.to(D)).cpu()
+    assert ops.overflow_count() == (0, 0)
+    assert ((got.double() - want).abs().max() / want.abs().max()).item() < 6e-5
+    x2 = x.clone()
+    x2[7, 11], x2[100, 5] = 500.0, -3000.0             # outlier channels of a real checkpoint's residual stream
+    want2 = x2.double() @ w.double().T
+    got2 = _f8_linear(x2.to(D), w.to(D)).cpu()
+    n448, n65504 = ops.overflow_count()
+    assert n448 >= 2 and n65504 == 0
+    # the two rows with an outlier: error bounded by the outlier's lost cross terms (~2^-11 of its contribution)
+    err_rows = (got2.double() - want2).abs().max(dim=1).values
+    bound = 3000.0 * w.abs().max().item() * 2.0 ** -10
+    assert err_rows.max().item() < bound
+    clean = torch.ones(M, dtype=torch.bool)
+    clean[[7, 100]] = False
+    assert (err_rows[clean].max() / want2.abs().max()).item() < 6e-5
+    x3 = x.clone()
+    x3[1, 1] = 7e4
+    _f8_linear(x3.to(D), w.to(D))
+    assert ops.overflow_count(reset=True)[1] >= 1
+    assert ops.overflow_count() == (0, 0)
