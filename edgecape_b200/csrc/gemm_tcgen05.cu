@@ -135,7 +135,7 @@ struct TcParams {
   long long seg_stride_c;
   int vec_c, vec_r;
   int n_fastest;   // tile order: consecutive tiles walk N first (few N tiles, large A: every A tile is read once)
-  int dbg;   // experiment flags (ec_tc_set_debug): 1 = no TMA after the pipeline is primed, 2 = hi*hi only, 4 = no epilogue stores
+  int dbg;   // experiment flags (ec_tc_set_debug): 1 = no TMA after the pipeline is primed, 2 = hi*hi only (single-CTA F16X2), 4 = no epilogue stores, 8 = no epilogue
   float out_scale;
   const float* bias;
   const float* colscale;
@@ -327,8 +327,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sb = base + stage * STAGE_BYTES;
-          if (!TWO && (p.dbg & 1) && (tile != worker || kb >= STAGES)) {   // experiment: operands stay resident
-            mbar_arrive(full_bar(stage));
+          if ((p.dbg & 1) && (j > 0 || kb >= STAGES)) {   // experiment: operands stay resident after the first fill
+            if (rank == 0) mbar_arrive(full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -486,6 +486,15 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.R) load_res(group, rcur);
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
+      if (p.dbg & 8) {   // experiment: no epilogue at all (the accumulator is handed straight back)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (TWO) mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);
+          else mbar_arrive(tempty_bar(acc));
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int sc = group; sc < NSUB; sc += 2) {
         uint32_t r[16];

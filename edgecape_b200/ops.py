@@ -230,7 +230,10 @@ def linear(x, w, bias=None, out=None, act=ACT_NONE, colscale=None, residual=None
     if w.dim() > 2:
         w = w.reshape(w.shape[0], -1)
     if _tc_ok(x, w, residual):
-        a2 = x if isinstance(x, SplitOperand) else split_f16(x)
+        if isinstance(x, SplitOperand):
+            a2 = x
+        else:   # fp32 rows: split here, in the format of the kernel this shape takes
+            a2 = split_f16(x, fmt=F16F8 if f8_linear_ok(x.numel() // x.shape[-1], w) else F16X2)
         if out is None and not isinstance(x, SplitOperand) and x.dim() == 3:
             out = empty(x.shape[0], x.shape[1], w.shape[0], device=x.device)
         if not fp32_out:

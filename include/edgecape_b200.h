@@ -129,7 +129,7 @@ int ec_tc_set_dynamic(int on);
  * stream-ordered launches, for A/B measurements) */
 int ec_set_pdl(int on);
 /* profiling experiments on ec_gemm_f16x3 (results are WRONG when flags != 0): 1 = operands stay resident
- * (no TMA after the pipeline is primed), 2 = hi*hi product only, 4 = no epilogue stores. */
+ * (no TMA after the pipeline is primed), 2 = hi*hi product only, 4 = no epilogue stores, 8 = no epilogue. */
 int ec_tc_set_debug(int flags);
 /* profiling aid for ec_attention_tc_split: when buf != NULL the first n_ctas CTAs of every launch write ten
  * clock64() stamps (int64) of their phases to buf[cta][10] (device memory); NULL switches it off. */

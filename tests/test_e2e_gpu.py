@@ -53,10 +53,17 @@ def _compare(name, got, want, report):
     return worst
 
 
-@pytest.mark.parametrize("tensor_cores", [True, False], ids=["tcgen05", "simt_fp32"])
+@pytest.mark.parametrize("tensor_cores", [True, False, "f8"], ids=["tcgen05", "simt_fp32", "tcgen05_f8_everywhere"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_detector_matches_reference_golden(name, tensor_cores, golden_dir, monkeypatch):
+    """tcgen05: the default dispatch (F16F8 kernel for the large linears, three fp16 products elsewhere);
+    tcgen05_f8_everywhere: every linear the F16F8 kernel can take, whatever its size (ViT qkv / fc1 / fc2 and the
+    head's fp32-input linears with N, K >= 256); simt_fp32: the exact-fp32 FFMA path."""
     from edgecape_b200 import ops
+    if tensor_cores == "f8":
+        monkeypatch.setattr(ops, "F8_MIN_M", 64)
+        monkeypatch.setattr(ops, "GEMM_F8", True)
+        tensor_cores = True
     monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     cfg, data, wseed = build_case(name)
@@ -73,7 +80,7 @@ def test_detector_matches_reference_golden(name, tensor_cores, golden_dir, monke
                skeleton=res["skeleton"])
     rep = {}
     worst = _compare(name, got, golden, rep)
-    REPORT[name + ("[tc]" if tensor_cores else "[simt]")] = rep
+    REPORT[name + (("[tc_f8_everywhere]" if ops.F8_MIN_M == 64 else "[tc]") if tensor_cores else "[simt]")] = rep
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/e2e_parity.json", "w") as fh:
         json.dump(REPORT, fh, indent=1, sort_keys=True)
@@ -87,7 +94,7 @@ def test_benchmarked_pipeline_matches_reference_golden(golden_dir):
     counter -- which no smaller golden reaches.  The golden batch is submitted three times between other batches, so
     both pipeline slots and slot reuse are covered; every copy must match the reference (1e-3, arg-max exact) and the
     copies must agree bit for bit."""
-    from edgecape_b200 import _lib
+    from edgecape_b200 import _lib, ops
     from edgecape_b200.apis import single_gpu_test
     name = "c2_vitb_256_k100_b16"
     golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))
@@ -97,9 +104,12 @@ def test_benchmarked_pipeline_matches_reference_golden(golden_dir):
     other = [make_episode(batch=16, image_size=256, num_kpts=100, shots=1, seed=900 + i, masked_tail=0.1)
              for i in range(2)]
     lib = _lib.load()
-    pair0 = lib.ec_tc_mode_launches(512)
+    pair_count = lambda: lib.ec_tc_mode_launches(512) + lib.ec_tc_mode_launches(513)   # F16X2 + F16F8 pair kernels
+    pair0 = pair_count()
     got = single_gpu_test(model, [data, other[0], data, data, other[1]])
-    pair_launches = lib.ec_tc_mode_launches(512) - pair0
+    pair_launches = pair_count() - pair0
+    if ops.GEMM_F8:
+        assert lib.ec_tc_mode_launches(513) >= 2 * 36, "the F16F8 CTA-pair kernel (default for the ViT's large linears) did not run"
     # qkv, fc1, fc2 of 12 ViT-B blocks, recorded once per pipeline slot (graph capture) + the eager warm-up passes
     assert pair_launches >= 2 * 36, f"only {pair_launches} CTA-pair GEMM launches: the benchmarked tile mode did not run"
     rep = {}
