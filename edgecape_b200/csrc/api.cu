@@ -4,7 +4,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -29,6 +31,21 @@ bool pdl_enabled() {
     g_pdl = (e && strcmp(e, "0") == 0) ? 0 : 1;
   }
   return g_pdl != 0;
+}
+
+int ensure_dynamic_smem_impl(const void* func, int bytes) {
+  static std::map<std::pair<const void*, int>, int> done;   // (kernel, device) -> bytes already granted
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(func, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return 0;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[key] = bytes;
+  return (int)e;
 }
 
 unsigned long long* overflow_counters() {

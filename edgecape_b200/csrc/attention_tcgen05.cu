@@ -1102,12 +1102,7 @@ extern "C" int ec_attention_tc(const float* Q, const float* K, const float* V, f
   EC_REQUIRE(B <= 65535 && H <= 65535, "ec_attention_tc: grid too large");
   const int data_bytes = atc::Q_BYTES + 2 * LKP * 128 > atc::REUSE_BYTES ? atc::Q_BYTES + 2 * LKP * 128 : atc::REUSE_BYTES;
   const int smem = data_bytes + atc::MISC_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 atc::Q_BYTES + 2 * atc::MAX_LKP * 128 + atc::MISC_BYTES + 1024));
-    attr_set = true;
-  }
+  EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_kernel, atc::Q_BYTES + 2 * atc::MAX_LKP * 128 + atc::MISC_BYTES + 1024));
   atc::Params p{Q, K, V, O, B, H, Lq, Lk, LKP, ldq, ldk, ldv, ldo, sq, sk, sv, so, scale, (__half*)split_out, split_kp,
                 D, key_mask, bias};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
@@ -1152,12 +1147,8 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   const int pv = 2 * atc::PBUF_BYTES + NKB * atc::VBUF_BYTES;
   const int data_bytes = kq > pv ? kq : pv;
   const int smem = data_bytes + atc::MISC_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 2 * atc::PBUF_BYTES + 7 * atc::VBUF_BYTES + atc::MISC_BYTES + 1024));
-    attr_set = true;
-  }
+  EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_tma_kernel,
+                                           2 * atc::PBUF_BYTES + 7 * atc::VBUF_BYTES + atc::MISC_BYTES + 1024));
   CUtensorMap tmQ, tmK, tmV;
   int rc = tc::get_tensor_map(Q2, q_total_rows, q_kp, 64, &tmQ);
   if (rc) return rc;
@@ -1170,12 +1161,8 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
                  (atc::g_variant != 2 && NB == 1 && LB <= 384) ? 1 : 0, dv, key_mask, bias};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
   if (atc::g_variant != 1 || general) {
-    static bool ts_attr_set = false;
-    if (!ts_attr_set) {
-      EC_CUDA(cudaFuncSetAttribute(atc::attention_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
-      ts_attr_set = true;
-    }
+    EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_ts_kernel,
+                                             atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
     launch_pdl(atc::attention_tc_ts_kernel, grid, dim3(atc::THREADS_TS), (size_t)(kq + atc::MISC_BYTES + 1024),
                (cudaStream_t)stream, tmQ, tmK, tmV, p);
   } else {

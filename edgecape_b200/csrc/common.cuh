@@ -15,6 +15,11 @@ void count_launch(int n = 1);
 // device counters {values beyond the e4m3 range, values beyond the fp16 range} seen by F16F8 split producers on the
 // current device; allocated on first use (which must be outside a stream capture).  nullptr + error on failure.
 unsigned long long* overflow_counters();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: raises it to `bytes` for `func` on the current
+// device the first time (and whenever a larger value is asked for), under a mutex.  Returns a cudaError_t as int.
+int ensure_dynamic_smem_impl(const void* func, int bytes);
+template <typename F>
+inline int ensure_dynamic_smem(F* func, int bytes) { return ensure_dynamic_smem_impl((const void*)func, bytes); }
 
 // Programmatic dependent launch.  Kernels launched through launch_pdl() may start while their predecessor in the
 // stream is still running; each of them calls pdl_wait() -- which returns once the predecessor grid has completed

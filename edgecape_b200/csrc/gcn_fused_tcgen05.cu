@@ -569,11 +569,7 @@ extern "C" int ec_gcn_fused(const float* X, const float* adj, const float* Wp, c
   if (B == 0) return EC_OK;
   const int k16 = (K + 15) / 16 * 16;
   const uint32_t smem = gf::make_layout(k16, d, NS).total + 1024u;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EC_CUDA(cudaFuncSetAttribute(gf::gcn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM_LIMIT));
-    attr_set = true;
-  }
+  EC_CUDA((cudaError_t)ensure_dynamic_smem(gf::gcn_fused_kernel, (int)gf::SMEM_LIMIT));
   CUtensorMap tmW;
   int rc = tc::get_tensor_map(W2, dff, Kp, NS, &tmW);
   if (rc) return rc;

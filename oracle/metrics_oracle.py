@@ -7,8 +7,12 @@ Path: /root/reference/EdgeCape/datasets/datasets/mp100/test_base_dataset.py:71-1
 here from their published algorithm; `report_metric` is the reference's reduction.  Only tests/, smoke() and bench.py's
 CPU legs may import this module.
 
-Parity unpinned against mmpose itself (the package is absent offline); `_keypoint_pck_accuracy` in oracle/ref_shims.py is
-the same restatement the shimmed reference runs with.
+Pinning: mmpose itself is absent offline, so this module cannot be executed against it.  It is pinned to the
+known-answer vectors of mmpose 0.29's own unit tests for these functions (test_keypoint_pck_accuracy: acc = [1, 0.5,
+-1, 1, 1], mean 0.875, 4 valid channels; test_keypoint_auc: 0.375), restated in
+tests/test_metrics_oracle.py::test_known_answer_vectors_of_mmpose_unit_tests together with hand-derived EPE / NME
+values for the same sample -- "partially pinned": known answers, not outputs of mmpose run here.
+`_keypoint_pck_accuracy` in oracle/ref_shims.py is the same restatement the shimmed reference runs with.
 """
 import numpy as np
 

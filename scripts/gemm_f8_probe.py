@@ -43,10 +43,10 @@ def main():
         for n, fn in cases.items():
             K = 4 * C if n == "fc2" else C
             line = f"[{tag} pair] {n}:"
-            for flags in (0, 4, 8, 1, 9):
-                lib.ec_tc_set_debug(flags)
-                us = timeit(fn)
-                line += f"  dbg{flags} {us:6.1f} us ({2.0 * M * ws[n].rows * K / us / 1e6:4.0f} TF/s)"
+            flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # one flag per process: a wrong experiment can hang
+            lib.ec_tc_set_debug(flags)
+            us = timeit(fn)
+            line += f"  dbg{flags} {us:6.1f} us ({2.0 * M * ws[n].rows * K / us / 1e6:4.0f} TF/s)"
             lib.ec_tc_set_debug(0)
             print(line, flush=True)
     lib.ec_tc_set_tile_n(0)

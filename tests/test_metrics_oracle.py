@@ -44,3 +44,36 @@ def test_emulated_metrics_kernel_and_summary(monkeypatch):
     got = summarize_metrics(c)
     for k in ("PCK@0.1", "mPCK", "NME", "AUC", "EPE"):
         assert abs(got[k] - want[k]) < 1e-6 * max(1.0, abs(want[k])), k
+
+
+def test_known_answer_vectors_of_mmpose_unit_tests():
+    """Known-answer vectors of mmpose 0.29's own unit tests for these functions
+    (tests/test_evaluation/test_top_down_eval.py: test_keypoint_pck_accuracy, test_keypoint_auc), restated here because
+    mmpose is absent offline; every expected value is also derivable by hand from the documented definitions
+    (PCK = share of valid keypoints whose normalised distance is < thr, per keypoint channel, -1 for a channel with no
+    valid sample; AUC = mean PCK over thr = i / num_step).  They pin oracle/metrics_oracle.py -- and through it
+    ec_metrics_accumulate (tests/test_ops_gpu.py) -- to mmpose's published behaviour, not merely to itself."""
+    # --- test_keypoint_pck_accuracy: 2 samples x 5 keypoints, normaliser 10, thr 0.5
+    output, target = np.zeros((2, 5, 2)), np.zeros((2, 5, 2))
+    mask = np.array([[True, True, False, True, True], [True, True, False, True, True]])
+    thr = np.full((2, 2), 10, dtype=np.float32)
+    output[0, 0], target[0, 0] = [10, 0], [10, 0]
+    output[0, 1], target[0, 1] = [20, 20], [10, 10]      # distance sqrt(2) > 0.5: miss; sample 1 (zeros) hits -> 0.5
+    output[0, 2], target[0, 2] = [0, 0], [-1, 0]         # masked channel -> -1
+    output[0, 3], target[0, 3] = [30, 30], [30, 30]
+    output[0, 4], target[0, 4] = [0, 10], [0, 10]
+    acc, avg_acc, cnt = mo.keypoint_pck_accuracy(output, target, mask, 0.5, thr)
+    np.testing.assert_array_almost_equal(acc, np.array([1, 0.5, -1, 1, 1]), decimal=4)
+    assert abs(avg_acc - 0.875) < 1e-4 and cnt == 4
+    # --- test_keypoint_auc: 1 sample, normaliser 20, 4 steps -> thresholds 0, .25, .5, .75
+    output, target = np.zeros((1, 5, 2)), np.zeros((1, 5, 2))
+    mask = np.array([[True, True, False, True, True]])
+    output[0, 0], target[0, 0] = [10, 4], [10, 5]        # 1 / 20  = 0.05
+    output[0, 1], target[0, 1] = [10, 18], [10, 10]      # 8 / 20  = 0.40
+    output[0, 2], target[0, 2] = [0, 0], [0, -1]
+    output[0, 3], target[0, 3] = [40, 40], [30, 30]      # 14.14 / 20 = 0.707
+    output[0, 4], target[0, 4] = [20, 10], [0, 10]       # 20 / 20 = 1.0
+    assert abs(mo.keypoint_auc(output, target, mask, 20, 4) - 0.375) < 1e-4      # (0 + 1/4 + 2/4 + 3/4) / 4
+    # EPE and NME of the same sample, by hand: mean of (1, 8, 14.1421, 20) and of those / 20
+    assert abs(mo.keypoint_epe(output, target, mask) - (1 + 8 + 200 ** 0.5 + 20) / 4) < 1e-4
+    assert abs(mo.keypoint_nme(output, target, mask, np.full((1, 2), 20.0)) - (1 + 8 + 200 ** 0.5 + 20) / 80) < 1e-5
