@@ -6,8 +6,8 @@
 // and feeds 3 x 4 UMMA 128x128x16 instructions, i.e. 4 tile loads per 3 products instead of 6.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..9 = epilogue (TMEM -> registers -> bias/activation/LayerScale/residual -> global, and
-// optionally the split-fp16 form of the result for the next GEMM).  Two TMEM accumulator stages overlap
+// lane), warps 2..17 = epilogue (TMEM -> registers -> bias/activation/LayerScale/residual -> global, and
+// optionally the split form of the result for the next GEMM).  Two TMEM accumulator stages overlap
 // the epilogue of tile i with the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -30,9 +30,10 @@ constexpr int TILE_BYTES = BM * BK * 2;               // one 128-row operand til
 // (cta_group::2, 3 stages of 64 KB per CTA).  The main loop is bound by how many operand bytes can be in flight
 // in shared memory per unit of math (profiles/r01_d): the pair tile feeds twice the math per staged byte.
 constexpr int NUM_ACC = 2;
-constexpr int THREADS = 320;                         // TMA warp + MMA warp + 8 epilogue warps
-constexpr int EPI_LD = 20;                           // staging row stride (floats)
-constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;       // one 32 x 16 staging tile per epilogue warp
+constexpr int EPI_WARPS = 16;                        // four per TMEM lane quarter (see the epilogue)
+constexpr int THREADS = 64 + 32 * EPI_WARPS;         // TMA warp + MMA warp + the epilogue warps
+constexpr int EPI_TILE = 32 * 16;                    // floats of one 32 x 16 staging tile (rows of 64 B, chunks XOR-swizzled)
+constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE * 4;  // one staging tile per epilogue warp: 32 KB
 constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;   // all variants
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -265,8 +266,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 16 : 8); }
-    for (int r = 0; r < RING; ++r) { mbar_init(ring_full(r), 1); mbar_init(ring_empty(r), TWO ? 18 : 9); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (TWO ? 2 : 1) * EPI_WARPS); }
+    // ring consumers: the epilogue warps and the MMA thread of every CTA, plus the peer's TMA thread
+    for (int r = 0; r < RING; ++r) { mbar_init(ring_full(r), 1); mbar_init(ring_empty(r), TWO ? 2 * EPI_WARPS + 2 : EPI_WARPS + 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -438,16 +440,22 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ---------------------------------------------------------------------- epilogue (8 warps)
-    // TMEM gives each lane one accumulator row.  Two warps share a lane quarter and alternate over 16-column
-    // sub-chunks; each sub-chunk is transposed through a per-warp shared-memory tile (row stride 20 floats:
-    // conflict-free float4 writes) so that global traffic is row-contiguous: 4 lanes cover one 16-column
-    // row segment (64 B), a warp covers 8 rows per step.  Eight warps (two per scheduler) hide the latency
-    // of the residual loads and of erf / tanh, which four could not (profiles/r01_f).
+    // ---------------------------------------------------------------------- epilogue (16 warps)
+    // TMEM gives each lane one accumulator row.  Four warps share a lane quarter and take every fourth 16-column
+    // sub-chunk; each sub-chunk is transposed through a per-warp shared-memory tile (32 rows of 64 B, the 16-byte
+    // chunk c of row r stored at chunk c ^ ((r >> 1) & 3): conflict-free float4 writes by row and reads by
+    // (8 rows x 4 chunks)) so that global traffic is row-contiguous: 4 lanes cover one 16-column row segment
+    // (64 B), a warp covers 8 rows per step.  With the cross terms on e4m3 the main loop of a K = 768 tile is
+    // ~15 K clk and the epilogue -- a chain of TMEM / shared / global latencies per sub-chunk, ~60 instructions
+    // per element with erf -- had become the bound of the qkv and fc1 GEMMs with 8 warps (fc1: 132 us against
+    // 68 us with the epilogue switched off, profiles/r02_d_gemm_f16f8_experiment_flags.log): 16 warps halve the
+    // chain every warp walks per tile and give each scheduler four warps to overlap.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int group = (warp - 2) >> 2;             // which of the two warps of the quarter
-    float* stage = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * EPI_LD);
+    const int group = (warp - 2) >> 2;             // which of the four warps of the quarter
+    constexpr int NGROUP = EPI_WARPS / 4;
+    float* stage = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * EPI_TILE;
     const int sub_row = lane >> 2, c4 = (lane & 3) * 4;
+    const int st_swz = (lane >> 1) & 3;            // this lane's row as a writer: chunk j -> j ^ st_swz
     constexpr int NSUB = BN / 16;
     int t = 0;
     uint32_t ovf = 0;                              // F16F8 split_out: values beyond the e4m3 / fp16 range seen by this thread
@@ -496,11 +504,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         continue;
       }
 #pragma unroll 1
-      for (int sc = group; sc < NSUB; sc += 2) {
+      for (int sc = group; sc < NSUB; sc += NGROUP) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + sc * 16), r);
-        if (p.R) load_res(sc + 2, rnext);
-        if (sc + 2 >= NSUB) {
+        if (p.R) load_res(sc + NGROUP, rnext);
+        if (sc + NGROUP >= NSUB) {
           // this warp has drained its share of the accumulator: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
@@ -510,10 +518,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) =
-              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                          __uint_as_float(r[j + 3]));
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stage + lane * 16 + ((j ^ st_swz) << 2)) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
         __syncwarp();
         const int gcol = n0 + sc * 16 + c4;
         if (gcol < p.N) {
@@ -529,7 +537,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // accumulator * out_scale + bias, activation (transcendental ones in a rolled loop: code size)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 a4 = *reinterpret_cast<const float4*>(stage + (i * 8 + sub_row) * EPI_LD + c4);
+            const int rr = i * 8 + sub_row;
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + rr * 16 + (((c4 >> 2) ^ ((rr >> 1) & 3)) << 2));
             y[i][0] = fmaf(a4.x, p.out_scale, bv[0]); y[i][1] = fmaf(a4.y, p.out_scale, bv[1]);
             y[i][2] = fmaf(a4.z, p.out_scale, bv[2]); y[i][3] = fmaf(a4.w, p.out_scale, bv[3]);
           }
@@ -542,7 +551,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-              for (int u = 0; u < 4; ++u) y[i][u] = gelu_erf(y[i][u]);
+              for (int u = 0; u < 4; ++u) y[i][u] = gelu_fast(y[i][u]);
           } else if (p.act == EC_ACT_TANH) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -553,8 +562,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int i = 0; i < 4; ++i) {
             const int row = m0 + quarter * 32 + i * 8 + sub_row;
             if (row >= p.M) continue;
+            if (p.colscale) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) y[i][u] *= sv[u];
+              for (int u = 0; u < 4; ++u) y[i][u] *= sv[u];
+            }
             if (p.R) {
               const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
 #pragma unroll
