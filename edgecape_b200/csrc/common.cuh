@@ -127,6 +127,40 @@ __device__ __forceinline__ void store_split4(uint8_t* row, int kp, int c, float 
     flags |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
   }
 }
+// eight consecutive elements (column c, a multiple of 8): 16-byte hi16 store, 16-byte lo16 store or two 8-byte e4m3
+// stores -- with four lanes per row every 32-byte sector of the row is written whole by one instruction
+__device__ __forceinline__ void store_split8(uint8_t* row, int kp, int c, const float* v, int fmt, uint32_t& flags) {
+  uint32_t h[4];
+  float2 f[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    f[i] = __half22float2(hh);
+  }
+  *reinterpret_cast<uint4*>(row + 2 * c) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (fmt == EC_SPLIT_F16X2) {
+    uint32_t l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 ll = __floats2half2_rn(v[2 * i] - f[i].x, v[2 * i + 1] - f[i].y);
+      l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(row + 2 * kp + 2 * c) = make_uint4(l[0], l[1], l[2], l[3]);
+  } else {
+    *reinterpret_cast<uint2*>(row + 2 * kp + c) =
+        make_uint2(e4m3x2(f[0].x, f[0].y) | (e4m3x2(f[1].x, f[1].y) << 16), e4m3x2(f[2].x, f[2].y) | (e4m3x2(f[3].x, f[3].y) << 16));
+    uint32_t l8[4];
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      l8[i] = e4m3x2((v[2 * i] - f[i].x) * 2048.f, (v[2 * i + 1] - f[i].y) * 2048.f);
+      m = fmaxf(m, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));
+    }
+    *reinterpret_cast<uint2*>(row + 3 * kp + c) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
+    flags |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
+  }
+}
 // end of a thread's stores: one atomic per event class at most (flags is zero on every healthy run)
 __device__ __forceinline__ void report_overflow(unsigned long long* counters, uint32_t flags) {
   if (flags && counters) {

@@ -65,6 +65,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA store of one box from shared memory (bulk async-group form) and its group bookkeeping
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * 16) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -136,7 +147,7 @@ struct TcParams {
   long long seg_stride_c;
   int vec_c, vec_r;
   int n_fastest;   // tile order: consecutive tiles walk N first (few N tiles, large A: every A tile is read once)
-  int dbg;   // experiment flags (ec_tc_set_debug): 1 = no TMA after the pipeline is primed, 2 = hi*hi only (single-CTA F16X2), 4 = no epilogue stores, 8 = no epilogue
+  int dbg;   // experiment flags (ec_tc_set_debug): 1 = no TMA after the pipeline is primed, 2 = hi*hi only (single-CTA F16X2), 4 = no epilogue stores, 8 = no epilogue, 16 = no split_out stores, 32 = no GELU
   float out_scale;
   const float* bias;
   const float* colscale;
@@ -148,6 +159,7 @@ struct TcParams {
   int split_fmt;       // EC_SPLIT_F16X2 = [hi16 | lo16], EC_SPLIT_F16F8 = [hi16 | hi8 | lo8] (common.cuh)
   float split_scale;
   unsigned long long* overflow;   // F16F8 producers: {beyond e4m3, beyond fp16} event counters
+  int split_tma;       // split_out is the only output: the epilogue assembles 128 x 64 blocks in shared memory and TMA-stores them
   int* sched;          // dynamic tile scheduler: {next tile, finished workers} of this launch (zero on entry), or NULL
 };
 
@@ -184,6 +196,20 @@ __device__ __forceinline__ void st_shared_cluster(uint32_t cluster_addr, int v) 
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Relaxed form for hand-backs that publish no memory: "this warp has finished READING" a TMEM accumulator
+// (tcgen05.wait::ld has completed the loads) or a ring slot.  The release form above compiles to MEMBAR.ALL.GPU +
+// ERRBAR in front of the arrive, i.e. it waits for every global store the warp has in flight -- once per tile and
+// epilogue warp, exactly where the epilogue is the bound.  `dep` is a value the arrive must not overtake (the word
+// read from the ring slot): it is folded into the address so the instruction cannot issue before the load returns.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr, int dep = 0) {
+  asm volatile(
+      "{\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, 0;\n\t"
+      "add.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [t];\n\t}"
+      ::"r"(cluster_addr), "r"(dep)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
@@ -227,7 +253,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on 
 template <int BN, bool TWO, bool F8>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, TcParams p) {
+                  const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
+                  const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmO8, TcParams p) {
   constexpr int B_ROWS = TWO ? BN / 2 : BN;                      // B rows staged by one CTA
   constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
   constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;
@@ -238,7 +265,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   static_assert(!TWO || BN == 256, "the 2-CTA kernel uses 256 x 256 tiles");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  // after the pipeline stages: the epilogue staging area (1024-byte aligned: the split-only epilogue builds 128B- /
+  // 64B-swizzled tiles in it for TMA stores), then the barriers
+  const uint32_t epi_base = base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = epi_base + EPI_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[NUM_ACC], tmem_empty[NUM_ACC]; then the TMEM address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -254,7 +284,6 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto ring_empty = [&](int r) { return bar_base + 128u + 8u * r; };
   const uint32_t ring_tile = bar_base + 160u;                       // RING x int32
   volatile int* ring_tile_ptr = reinterpret_cast<volatile int*>(smem_raw + (ring_tile - smem_u32(smem_raw)));
-  const uint32_t epi_base = bar_base + 256u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,9 +323,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (TWO && rank == 1) mbar_wait_cluster(ring_full(r), ph); else mbar_wait(ring_full(r), ph);
     return ring_tile_ptr[r];
   };
-  auto ring_release = [&](int j) {
+  auto ring_release = [&](int j, int tile_read) {   // tile_read: the slot's value (the arrive must follow the read)
     const int r = j % RING;
-    if (TWO && rank == 1) mbar_arrive_remote(mapa(ring_empty(r), 0)); else mbar_arrive(ring_empty(r));
+    if (TWO && rank == 1) mbar_arrive_remote_relaxed(mapa(ring_empty(r), 0), tile_read); else mbar_arrive(ring_empty(r));
   };
 
   if (warp == 0) {
@@ -321,7 +350,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (TWO) mbar_arrive_remote(mapa(ring_full(r), 1));
         } else {
           tile = ring_get(j);
-          ring_release(j);
+          ring_release(j, tile);
         }
         if (tile < 0) break;
         const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
@@ -376,7 +405,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       for (int t = 0;; ++t) {
         const int tile = ring_get(t);
-        ring_release(t);
+        ring_release(t, tile);
         if (tile < 0) break;
         const int acc = t & 1;
         mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
@@ -463,11 +492,132 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (;; ++t) {
       const int tile = ring_get(t);
       __syncwarp();                                  // every lane has read the slot
-      if (lane == 0) ring_release(t);
+      if (lane == 0) ring_release(t, tile);
       if (tile < 0) break;
       const int acc = t & 1;
       const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
       const int m0 = tm * TM + rank * BM, n0 = tn * BN;
+      if (p.split_tma) {
+        // ------------------------------------------------------------ split-only output through TMA stores
+        // The qkv / fc1 GEMMs write nothing but the split form of their result.  Scattered from the lanes (8- and
+        // 4-byte pieces, eight rows per store instruction) those stores were 32 of fc1's 110 us against 69 us with
+        // no epilogue (profiles/r02_f_gemm_epilogue_decomposition.log).  Here the 16 warps assemble the rows of a
+        // 128-row x 64-column block in shared memory in the layout TMA expects -- the very layout the consumer's
+        // A-operand tiles have: hi16 rows of 128 B in 128B swizzle, lo16 likewise, e4m3 planes rows of 64 B in 64B
+        // swizzle -- each lane converting the 16 columns of its own accumulator row (no transposition: the tile IS
+        // the transposition, and consecutive rows hit distinct bank groups by construction of the swizzle), and
+        // one thread stores the block with two or three bulk tensor copies (whole 128-byte lines; rows >= M are
+        // clipped by the tensor map, columns >= N inside the padded width are the zero padding of the operand).
+        uint8_t* blk = smem_raw + (epi_base - smem_u32(smem_raw));      // [hi16 16 KB | lo16 16 KB] or [hi16 | hi8 8 KB | lo8 8 KB]
+        const uint32_t blk_u32 = epi_base;
+        const int row_l = quarter * 32 + lane;                          // row of the 128-row block = TMEM lane
+        mbar_wait(tfull_bar(acc), (t >> 1) & 1);
+        tc_fence_after();
+        if (p.dbg & 8) {   // experiment: no epilogue at all (the accumulator is handed straight back)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (TWO && rank == 1) mbar_arrive_remote_relaxed(acc ? tempty_leader1 : tempty_leader0);
+            else mbar_arrive(tempty_bar(acc));
+          }
+          continue;
+        }
+        constexpr int NBLK = BN / 64;
+#pragma unroll 1
+        for (int cb = 0; cb < NBLK; ++cb) {
+          const int col0 = n0 + cb * 64;                                // first column of the block
+          if (col0 >= p.split_kp) break;                                // warp-uniform: nothing of the operand lies here
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cb * 64 + group * 16), r);
+          if (cb + 1 == NBLK || col0 + 64 >= p.split_kp) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (TWO && rank == 1) mbar_arrive_remote_relaxed(acc ? tempty_leader1 : tempty_leader0);
+              else mbar_arrive(tempty_bar(acc));
+            }
+          }
+          const int gcol = col0 + group * 16;
+          float y[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float bias = (p.bias && gcol + u < p.N) ? __ldg(p.bias + gcol + u) : 0.f;
+            y[u] = fmaf(__uint_as_float(r[u]), p.out_scale, bias);
+          }
+          if (p.act == EC_ACT_RELU) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) y[u] = fmaxf(y[u], 0.f);
+          } else if (p.act == EC_ACT_GELU && !(p.dbg & 32)) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) y[u] = gelu_fast(y[u]);
+          } else if (p.act == EC_ACT_TANH) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) y[u] = tanhf(y[u]);
+          }
+          if (p.colscale) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) y[u] *= (gcol + u < p.N) ? __ldg(p.colscale + gcol + u) : 1.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) y[u] = (gcol + u < p.N) ? y[u] * p.split_scale : 0.f;
+          uint32_t h[8];
+          float2 f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+            h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            f[i] = __half22float2(hh);
+          }
+          if (cb > 0 || t > 0) epi_bar_sync();                          // the previous block has been read out of shared memory
+          // hi16: 16 columns = two 16-byte chunks (2 group, 2 group + 1) of the row's 128 bytes
+          uint8_t* hrow = blk + row_l * 128;
+          *reinterpret_cast<uint4*>(hrow + (((2 * group) ^ (row_l & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(hrow + (((2 * group + 1) ^ (row_l & 7)) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+          if (p.split_fmt == EC_SPLIT_F16X2) {
+            uint32_t l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __half2 ll = __floats2half2_rn(y[2 * i] - f[i].x, y[2 * i + 1] - f[i].y);
+              l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            uint8_t* lrow = blk + 16384 + row_l * 128;
+            *reinterpret_cast<uint4*>(lrow + (((2 * group) ^ (row_l & 7)) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(lrow + (((2 * group + 1) ^ (row_l & 7)) << 4)) = make_uint4(l[4], l[5], l[6], l[7]);
+          } else {
+            uint32_t h8[4], l8[4];
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              h8[i] = e4m3x2(f[2 * i].x, f[2 * i].y) | (e4m3x2(f[2 * i + 1].x, f[2 * i + 1].y) << 16);
+              l8[i] = e4m3x2((y[4 * i] - f[2 * i].x) * 2048.f, (y[4 * i + 1] - f[2 * i].y) * 2048.f) |
+                      (e4m3x2((y[4 * i + 2] - f[2 * i + 1].x) * 2048.f, (y[4 * i + 3] - f[2 * i + 1].y) * 2048.f) << 16);
+              m = fmaxf(m, fmaxf(fmaxf(fabsf(y[4 * i]), fabsf(y[4 * i + 1])), fmaxf(fabsf(y[4 * i + 2]), fabsf(y[4 * i + 3]))));
+            }
+            ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
+            // e4m3 planes: 16 columns = the 16-byte chunk `group` of the row's 64 bytes (64B swizzle)
+            const uint32_t off8 = (uint32_t)(row_l * 64 + ((group ^ ((row_l >> 1) & 3)) << 4));
+            *reinterpret_cast<uint4*>(blk + 16384 + off8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+            *reinterpret_cast<uint4*>(blk + 24576 + off8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+          }
+          fence_proxy_async_smem();                                     // generic-proxy writes -> visible to the TMA engine
+          epi_bar_sync();                                               // the block is complete
+          if (warp == 2 && elect_one()) {
+            if (!(p.dbg & 16)) {
+              tma_store_2d(&tmO16, blk_u32, col0, m0);
+              if (p.split_fmt == EC_SPLIT_F16X2) {
+                tma_store_2d(&tmO16, blk_u32 + 16384, p.split_kp + col0, m0);
+              } else {
+                tma_store_2d(&tmO8, blk_u32 + 16384, 2 * p.split_kp + col0, m0);
+                tma_store_2d(&tmO8, blk_u32 + 24576, 3 * p.split_kp + col0, m0);
+              }
+              tma_store_commit();
+              tma_store_wait_read();                                    // shared memory may be overwritten; the global writes complete on their own
+            }
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       // residual rows of one sub-chunk (4 rows x 4 columns per lane).  They do not depend on the accumulator, so
       // the first sub-chunk's are requested before waiting for the MMAs and every later one a sub-chunk ahead:
       // loaded at the point of use, the four dependent L2 round trips per sub-chunk (the in-place store to C
@@ -498,7 +648,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (TWO) mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);
+          if (TWO && rank == 1) mbar_arrive_remote_relaxed(acc ? tempty_leader1 : tempty_leader0);
           else mbar_arrive(tempty_bar(acc));
         }
         continue;
@@ -512,8 +662,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // this warp has drained its share of the accumulator: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            if (TWO) mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);   // the leader's MMA thread waits for 16 warps
+          if (lane == 0) {   // the leader's MMA thread waits for every epilogue warp of the pair
+            if (TWO && rank == 1) mbar_arrive_remote_relaxed(acc ? tempty_leader1 : tempty_leader0);
             else mbar_arrive(tempty_bar(acc));
           }
         }
@@ -547,7 +697,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int i = 0; i < 4; ++i)
 #pragma unroll
               for (int u = 0; u < 4; ++u) y[i][u] = fmaxf(y[i][u], 0.f);
-          } else if (p.act == EC_ACT_GELU) {
+          } else if (p.act == EC_ACT_GELU && !(p.dbg & 32)) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -582,7 +732,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   if (gcol + u < p.N) cp[u] = y[i][u];
               }
             }
-            if (p.split_out) {
+            if (p.split_out && !(p.dbg & 16)) {
               float sc_[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) sc_[u] = (gcol + u < p.N) ? y[i][u] * p.split_scale : 0.f;
@@ -600,6 +750,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     report_overflow(p.overflow, ovf);
+    if (p.split_tma && warp == 2) tma_store_wait_all();   // the issuing thread's bulk stores have been written
   }
   tc_fence_before();
   if (TWO) cluster_sync(); else __syncthreads();   // the peer's shared memory / barriers stay alive until both are done
@@ -802,6 +953,11 @@ extern "C" int ec_tc_set_cta_limit(int ctas) {
   ec_tc_cta_limit = ctas & ~1;
   return EC_OK;
 }
+static int ec_tc_split_tma = 1;  // split-only epilogues through TMA stores (0: scattered stores, for A/B measurements)
+extern "C" int ec_tc_set_split_tma(int on) {
+  ec_tc_split_tma = on ? 1 : 0;
+  return EC_OK;
+}
 static int ec_tc_force_bn = 0;   // 0 = heuristic; 128 / 256 force a tile width (tuning / tests)
 extern "C" int ec_tc_set_tile_n(int bn) {
   EC_REQUIRE(bn == 0 || bn == 128 || bn == 256 || bn == 512, "ec_tc_set_tile_n: 0, 128, 256 or 512 (CTA pair)");
@@ -878,7 +1034,19 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
     rc = tc::get_tensor_map_any(B2, N, Kp, mode == 256 ? 256 : 128, &tmB8, true);
     if (rc) return rc;
   }
+  // split-only outputs leave through TMA stores (128-row x 64-column blocks in the layout of the consumer's A tiles)
+  CUtensorMap tmO16 = tmA, tmO8 = tmA;
+  const bool split_tma = split_out && !C && aligned16(split_out) && ec_tc_split_tma;
+  if (split_tma) {
+    rc = tc::get_tensor_map_any(split_out, M, split_kp, tc::BM, &tmO16, false);
+    if (rc) return rc;
+    if (split_fmt == EC_SPLIT_F16F8) {
+      rc = tc::get_tensor_map_any(split_out, M, split_kp, tc::BM, &tmO8, true);
+      if (rc) return rc;
+    }
+  }
   tc::TcParams p{};
+  p.split_tma = split_tma ? 1 : 0;
   p.split_fmt = split_fmt;
   if (split_out && split_fmt == EC_SPLIT_F16F8) {
     p.overflow = overflow_counters();
@@ -932,20 +1100,20 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (f8) EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true, true>, tmA, tmB, tmA8, tmB8, p));
-    else EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true, false>, tmA, tmB, tmA8, tmB8, p));
+    if (f8) EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true, true>, tmA, tmB, tmA8, tmB8, tmO16, tmO8, p));
+    else EC_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_f16x3_kernel<256, true, false>, tmA, tmB, tmA8, tmB8, tmO16, tmO8, p));
   } else {
     const int tiles = cdiv(M, tc::BM) * cdiv(N, BN);
     const int max_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
     const int grid = tiles < max_ctas ? tiles : max_ctas;
     if (BN == 256 && f8)
-      launch_pdl(tc::gemm_f16x3_kernel<256, false, true>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
+      launch_pdl(tc::gemm_f16x3_kernel<256, false, true>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, tmO16, tmO8, p);
     else if (BN == 256)
-      launch_pdl(tc::gemm_f16x3_kernel<256, false, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
+      launch_pdl(tc::gemm_f16x3_kernel<256, false, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, tmO16, tmO8, p);
     else if (f8)
-      launch_pdl(tc::gemm_f16x3_kernel<128, false, true>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
+      launch_pdl(tc::gemm_f16x3_kernel<128, false, true>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, tmO16, tmO8, p);
     else
-      launch_pdl(tc::gemm_f16x3_kernel<128, false, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, p);
+      launch_pdl(tc::gemm_f16x3_kernel<128, false, false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, tmA, tmB, tmA8, tmB8, tmO16, tmO8, p);
   }
   return check_launch(what);
 }

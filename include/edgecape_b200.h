@@ -118,6 +118,10 @@ int ec_tc_set_tile_n(int bn);
  * deltas to prove which kernel instance a given configuration runs.  mode + 1 (129 / 257 / 513) counts the same tile
  * mode of ec_gemm_f16f8. */
 long long ec_tc_mode_launches(int mode);
+/* epilogue of the GEMMs whose only output is split_out (default 1): 1 = the CTA assembles 128-row x 64-column blocks of
+ * the split rows in shared memory and writes them with TMA bulk tensor stores; 0 = every lane stores its own pieces
+ * (kept for A/B measurements). */
+int ec_tc_set_split_tma(int on);
 /* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
  * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
 int ec_tc_set_cta_limit(int ctas);
@@ -129,7 +133,8 @@ int ec_tc_set_dynamic(int on);
  * stream-ordered launches, for A/B measurements) */
 int ec_set_pdl(int on);
 /* profiling experiments on ec_gemm_f16x3 (results are WRONG when flags != 0): 1 = operands stay resident
- * (no TMA after the pipeline is primed), 2 = hi*hi product only, 4 = no epilogue stores, 8 = no epilogue. */
+ * (no TMA after the pipeline is primed), 2 = hi*hi product only, 4 = no epilogue stores, 8 = no epilogue,
+ * 16 = no split_out stores, 32 = no GELU. */
 int ec_tc_set_debug(int flags);
 /* profiling aid for ec_attention_tc_split: when buf != NULL the first n_ctas CTAs of every launch write ten
  * clock64() stamps (int64) of their phases to buf[cta][10] (device memory); NULL switches it off. */

@@ -186,3 +186,34 @@ def test_f16f8_range_events_are_counted_and_degrade_gracefully():
     _f8_linear(x3.to(D), w.to(D))
     assert ops.overflow_count(reset=True)[1] >= 1
     assert ops.overflow_count() == (0, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile_n", [128, 256, 512])
+@pytest.mark.parametrize("fmt_in", [0, 1], ids=["f16x3", "f16f8"])
+@pytest.mark.parametrize("M,N,K", [(10400, 2304, 768), (1300, 1000, 320), (517, 136, 200), (128, 64, 64)])
+def test_split_only_epilogue_through_tma_stores(M, N, K, fmt_in, tile_n):
+    """GEMMs whose only output is split_out (qkv, fc1) assemble 128 x 64 blocks of the split rows in shared memory and
+    TMA-store them.  The rows must equal -- bit for bit -- the split form of the fp32 result of the same GEMM, in both
+    output formats, including the M tail (rows clipped by the tensor map) and the zero padding of columns >= N."""
+    D = _dev()
+    g = torch.Generator().manual_seed(M + N + K + tile_n)
+    x = torch.randn(M, K, generator=g).to(D)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(D)
+    b = (torch.randn(N, generator=g) * 0.1).to(D)
+    a2 = ops.split_f16(x, fmt=fmt_in, role=0)
+    b2 = ops.split_weight(w, fmt_in)
+    ops._lib.call("ec_tc_set_tile_n", tile_n)
+    try:
+        ref = ops.gemm_tc(a2, b2, bias=b, act=ops.ACT_GELU)
+        for fmt_out in ([ops.F16X2, ops.F16F8] if fmt_in == ops.F16F8 else [ops.F16X2]):
+            so = ops.gemm_tc(a2, b2, bias=b, act=ops.ACT_GELU, split_out=True, fp32_out=False, split_fmt=fmt_out)[1]
+            want = ops.split_f16(ref, fmt=fmt_out, role=0)
+            assert so.Kp == want.Kp and torch.equal(so.data.view(torch.uint8), want.data.view(torch.uint8)), fmt_out
+            ops._lib.call("ec_tc_set_split_tma", 0)                 # the scattered-store form gives the same bytes
+            so0 = ops.gemm_tc(a2, b2, bias=b, act=ops.ACT_GELU, split_out=True, fp32_out=False, split_fmt=fmt_out)[1]
+            ops._lib.call("ec_tc_set_split_tma", 1)
+            assert torch.equal(so0.data.view(torch.uint8), want.data.view(torch.uint8))
+    finally:
+        ops._lib.call("ec_tc_set_split_tma", 1)
+        ops._lib.call("ec_tc_set_tile_n", 0)
