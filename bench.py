@@ -348,7 +348,8 @@ def north_star_kernels(peaks):
         fl = 4.0 * N * N * D * H * Bi
         out["vit_attention"] = {"shape": f"{Bi} images x {H} heads x {N} tokens x {D}", "us": us, "bound": "tensor",
                                 "achieved": fl / us / 1e6, "peak": tf, "unit": "TFLOP/s", "frac": fl / us / 1e6 / tf,
-                                "issued_frac": 3 * fl / us / 1e6 / tf, "kernel": "ec::atc::attention_tc_ts_kernel"}
+                                "issued_frac": 3 * fl / us / 1e6 / tf,
+                                "kernel": "ec::atc::attention_tc_ps_kernel (persistent, software-pipelined over tiles)"}
     return out
 
 

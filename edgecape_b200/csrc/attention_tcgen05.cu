@@ -1072,7 +1072,308 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   stamp(9);
 }
 
-static int g_variant = 0;   // 0: P in TMEM + wide P V MMAs, 2: P in TMEM, three N = 64 MMAs per k-step, 1: P through shared memory
+// ---------------------------------------------------------------------------------------------------------
+// Persistent, software-pipelined form of the P-in-TMEM kernel for the ViT block attention (head dim 64, no mask,
+// no bias, one key block of <= 368 keys).  In the kernel above a CTA lives for one (image, head, 128-query) tile
+// and its phases are strictly serial: setup + TMEM allocation, Q / K loads + S MMAs (7.0 K of 17.0 K clk in the
+// pass-E trace, profiles/r02_e_attention_trace.log), row max, exponentials under the P V MMAs, epilogue.  Here a CTA
+// walks a list of tiles and keeps separate shared-memory regions for Q, K and V, so that
+//   * the Q / K tiles of tile t+1 are loaded while tile t is in its exponentials (issued as soon as S(t) is complete),
+//   * S(t+1) = Q K^T is issued as soon as the P V MMAs of tile t have retired, i.e. it runs under the epilogue of
+//     tile t (S lives in TMEM columns [0, 384), O in [384, 512): disjoint),
+//   * V(t+1) is loaded under the row max of tile t+1 (its region doubles as the epilogue's staging tile),
+//   * barrier set-up and the TMEM allocation happen once per CTA.
+// What stays on the softmax warps' critical path per tile is the row max, the exponentials and the epilogue.
+// K is loaded with a partial last box (16-row granularity, second tensor map) so that Q + K + V fit 227 KB.
+// Hand-offs (phase = tile parity): bar_qk, bar_s, bar_v, bar_pr[i], bar_o as above, plus
+//   bar_oe  softmax -> control   the epilogue of the tile has read O out of TMEM and drained its staging tile
+//                                (16 warp arrivals): the next tile's P V MMAs / V loads may start.
+struct ParamsP {
+  ParamsT t;
+  int rows_k;        // key rows staged per tile: 64 nfull + r16 (= the S columns used)
+  int nfull, r16;    // full 64-key boxes and the 16-row-granular remainder box
+  int QT;            // query tiles per (image, head)
+  int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS_TS, 1)
+attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKp,
+                       const __grid_constant__ CUtensorMap tmVp, ParamsP pp) {
+  const ParamsT& p = pp.t;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int nchunks = pp.nfull + (pp.r16 ? 1 : 0);
+  const uint32_t q_hi = base, q_lo = base + BM * 128;
+  const uint32_t k_hi = base + Q_BYTES, k_lo = k_hi + pp.rows_k * 128;
+  const uint32_t v_base = (k_lo + pp.rows_k * 128 + 1023u) & ~1023u;           // nchunks x [hi 8 KB | lo 8 KB]
+  uint8_t* stg = gbase + (v_base - base);                                      // epilogue staging tile (32 KB) = start of V
+  const uint32_t misc = v_base + max(nchunks * VBUF_BYTES, 2 * BM * 128);     // the staging tile needs 32 KB whatever Lk
+  const uint32_t bar_qk = misc, bar_s = misc + 8, bar_v = misc + 16, bar_o = misc + 24, bar_oe = misc + 32,
+                 tmem_slot = misc + 40, bar_pr = misc + 48;                    // bar_pr: MAX_CHUNKS barriers
+  float* xmax = reinterpret_cast<float*>(gbase + (misc - base) + 128);         // [NPART][BM]
+  float* xsum = xmax + NPART * BM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, part = (warp >> 2) & 3;
+  long long* trace = (p.trace && tid == 0 && (int)blockIdx.x < p.trace_n) ? p.trace + 10 * blockIdx.x : nullptr;
+  auto stamp = [&](int i) {
+    if (trace) trace[i] = clock64();
+  };
+  stamp(0);
+  const int n_it = ((int)blockIdx.x < pp.n_tiles) ? (pp.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto tile_of = [&](int it, int& b, int& h, int& q0) {
+    const int w = (int)blockIdx.x + it * (int)gridDim.x;
+    const int qt = w % pp.QT, bh = w / pp.QT;
+    q0 = qt * BM;
+    h = bh % p.H;
+    b = bh / p.H;
+  };
+
+  if (warp == THREADS / 32 && elect_one()) {
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 2); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_oe, THREADS / 32);
+    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(bar_pr + 8 * i, THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  pdl_launch_dependents();
+  pdl_wait();
+  stamp(1);
+
+  const int lkp = pp.rows_k;                            // S columns: a multiple of 16
+  auto issue_s = [&](int half) {                        // two warps issue the two halves of the key range
+    const int n0 = ((lkp / 2 + 15) / 16) * 16;
+    const int noff = half ? n0 : 0, n = half ? lkp - n0 : n0;
+    if (n > 0) {
+      const uint32_t idesc = make_idesc(n);
+      const uint64_t aq_hi = make_desc(q_hi), aq_lo = make_desc(q_lo);
+      const uint64_t bk_hi = make_desc(k_hi + noff * 128), bk_lo = make_desc(k_lo + noff * 128);
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_lo + 2 * k, bk_hi + 2 * k, idesc, k ? 1u : 0u);
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_lo + 2 * k, idesc, 1u);
+      for (int k = 0; k < D / 16; ++k) umma(tmem_base + noff, aq_hi + 2 * k, bk_hi + 2 * k, idesc, 1u);
+    }
+    umma_commit(bar_s);
+  };
+
+  if (warp == THREADS / 32 + 1) {
+    // ================================================================== second S-issuing warp
+    if (elect_one()) {
+      for (int it = 0; it < n_it; ++it) {
+        mbar_wait(bar_qk, it & 1);
+        if (it > 0) mbar_wait(bar_o, (it - 1) & 1);     // the P V MMAs of the previous tile have consumed P (= the S columns)
+        tc_fence_after();
+        issue_s(1);
+      }
+    }
+    __syncwarp();
+  } else if (warp == THREADS / 32) {
+    // ================================================================== control warp: TMA + MMA issue
+    if (elect_one()) {
+      const uint32_t idesc_o = make_idesc_bmn(D), idesc_w = make_idesc_bmn(2 * D);
+      auto load_qk = [&](int it) {
+        int b, h, q0;
+        tile_of(it, b, h, q0);
+        const int qrow = b * p.q_rows + q0, krow = b * p.k_rows;
+        mbar_expect_tx(bar_qk, (uint32_t)(Q_BYTES + 2 * pp.rows_k * 128));
+        for (int j = 0; j < 2; ++j) {
+          tma_load_2d(q_hi + j * BOX_BYTES, &tmQ, bar_qk, p.q_col + h * D, qrow + 64 * j);
+          tma_load_2d(q_lo + j * BOX_BYTES, &tmQ, bar_qk, p.q_kp + p.q_col + h * D, qrow + 64 * j);
+        }
+        for (int j = 0; j < pp.nfull; ++j) {
+          tma_load_2d(k_hi + j * BOX_BYTES, &tmK, bar_qk, p.k_col + h * D, krow + 64 * j);
+          tma_load_2d(k_lo + j * BOX_BYTES, &tmK, bar_qk, p.k_kp + p.k_col + h * D, krow + 64 * j);
+        }
+        if (pp.r16) {
+          tma_load_2d(k_hi + pp.nfull * BOX_BYTES, &tmKp, bar_qk, p.k_col + h * D, krow + 64 * pp.nfull);
+          tma_load_2d(k_lo + pp.nfull * BOX_BYTES, &tmKp, bar_qk, p.k_kp + p.k_col + h * D, krow + 64 * pp.nfull);
+        }
+      };
+      if (n_it > 0) load_qk(0);
+      for (int it = 0; it < n_it; ++it) {
+        int b, h, q0;
+        tile_of(it, b, h, q0);
+        const int krow = b * p.k_rows;
+        mbar_wait(bar_qk, it & 1);
+        if (it > 0) mbar_wait(bar_o, (it - 1) & 1);
+        tc_fence_after();
+        issue_s(0);
+        mbar_wait(bar_s, it & 1);                       // Q / K shared memory is dead: prefetch the next tile's
+        if (it + 1 < n_it) load_qk(it + 1);
+        if (it > 0) {                                   // staging tile (in the V region) drained, O read out of TMEM
+          mbar_wait(bar_oe, (it - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_expect_tx(bar_v, (uint32_t)(pp.nfull * 2 * BOX_BYTES + 2 * pp.r16 * 128));
+        for (int i = 0; i < pp.nfull; ++i) {
+          const uint32_t v_hi = v_base + i * VBUF_BYTES;
+          tma_load_2d(v_hi, &tmV, bar_v, p.v_col + h * D, krow + i * KC);
+          tma_load_2d(v_hi + BOX_BYTES, &tmV, bar_v, p.v_kp + p.v_col + h * D, krow + i * KC);
+        }
+        if (pp.r16) {
+          const uint32_t v_hi = v_base + pp.nfull * VBUF_BYTES;
+          tma_load_2d(v_hi, &tmVp, bar_v, p.v_col + h * D, krow + pp.nfull * KC);
+          tma_load_2d(v_hi + BOX_BYTES, &tmVp, bar_v, p.v_kp + p.v_col + h * D, krow + pp.nfull * KC);
+        }
+        mbar_wait(bar_v, it & 1);
+        for (int i = 0; i < nchunks; ++i) {
+          const uint32_t v_hi = v_base + i * VBUF_BYTES;
+          mbar_wait(bar_pr + 8 * i, it & 1);
+          tc_fence_after();
+          const int valid = min(KC, p.Lk - i * KC);
+          const int ksteps = (valid + 15) / 16;
+          const uint64_t bv_hi = make_desc_mn(v_hi);
+          const uint32_t a0 = tmem_base + i * KC;       // P of keys [16k, 16k+16): hi at +16k, lo at +16k+8
+          // one N = 128 MMA yields P_hi V_hi (columns 384..447) and P_hi V_lo (448..511): V_lo sits 8 KB after V_hi,
+          // the MN-atom stride of the descriptor; the epilogue adds the halves
+          for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + 384, a0 + 16 * k, bv_hi + 128 * k, idesc_w, (i | k) ? 1u : 0u);
+          for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + 384, a0 + 16 * k + 8, bv_hi + 128 * k, idesc_o, 1u);
+        }
+        umma_commit(bar_o);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== softmax warps
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int nkeys = p.Lk;
+    for (int it = 0; it < n_it; ++it) {
+      int b, h, q0;
+      tile_of(it, b, h, q0);
+      mbar_wait(bar_s, it & 1);
+      tc_fence_after();
+      if (it == 0) stamp(2);
+      // -------------------------------------------------------------- row max
+      const int nchunk32 = (nkeys + 31) / 32;
+      float mymax = -INFINITY;
+      for (int j = part; j < nchunk32; j += NPART) {
+        float s[32];
+        if (j * 32 + 32 <= lkp) {
+          tmem_ld32(t_row + j * 32, s);
+        } else {                                        // the last 16 columns of S (lkp is a multiple of 16, not of 32)
+          tmem_ld16(t_row + j * 32, s);
+#pragma unroll
+          for (int u = 16; u < 32; ++u) s[u] = -INFINITY;
+        }
+        if (j * 32 + 32 <= nkeys) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) mymax = fmaxf(mymax, s[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (j * 32 + u < nkeys) mymax = fmaxf(mymax, s[u]);
+        }
+      }
+      xmax[part * BM + row] = mymax;
+      softmax_sync();
+      float rmax = xmax[row];
+#pragma unroll
+      for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
+      if (it == 0) stamp(3);
+      // -------------------------------------------------------------- P = exp(S - max), in place in TMEM
+      const float nb = -rmax * sl2;
+      float rsum = 0.f;
+      for (int i = 0; i < nchunks; ++i) {
+        const int kbase = i * KC + PW * part;
+        if (kbase < lkp) {                               // warp-uniform: the partial chunk has fewer 16-key slices
+          float s[PW];
+          tmem_ld16(t_row + kbase, s);
+          if (kbase + PW <= nkeys) {
+#pragma unroll
+            for (int u = 0; u < PW; ++u) {
+              s[u] = ex2(fmaf(s[u], sl2, nb));
+              rsum += s[u];
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < PW; ++u) {
+              s[u] = (kbase + u < nkeys) ? ex2(fmaf(s[u], sl2, nb)) : 0.f;
+              rsum += s[u];
+            }
+          }
+          uint32_t pk[PW];
+#pragma unroll
+          for (int j = 0; j < PW / 2; ++j) split_pair(s[2 * j], s[2 * j + 1], pk[j], pk[PW / 2 + j]);
+          tmem_st16(t_row + kbase, pk);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pr + 8 * i);
+        if (it == 0 && i == 0) stamp(4);
+      }
+      if (it == 0) stamp(5);
+      xsum[part * BM + row] = rsum;
+      softmax_sync();                                   // (also: every warp has read xmax of this tile)
+      float tot = 0.f;
+#pragma unroll
+      for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
+      const float inv = tot > 0.f ? 1.0f / tot : 0.f;
+      mbar_wait(bar_o, it & 1);                         // every P V MMA of the tile is complete
+      tc_fence_after();
+      if (it == 0) stamp(6);
+      // -------------------------------------------------------------- normalise, store
+      constexpr int OW = D / NPART;
+      float o[OW], o1[OW];
+      tmem_ld16(t_row + 384 + OW * part, o);
+      tmem_ld16(t_row + 448 + OW * part, o1);
+#pragma unroll
+      for (int u = 0; u < OW; ++u) o[u] = (o[u] + o1[u]) * inv;
+      const int grow = q0 + row;
+      if (grow < p.Lq && p.O) {
+        float4* dst = reinterpret_cast<float4*>(p.O + (long long)b * p.so + (long long)grow * p.ldo + h * D + OW * part);
+#pragma unroll
+        for (int u = 0; u < OW / 4; ++u) dst[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+      }
+      if (p.split_out) {
+        // through the staging tile (the V region: every MMA reading V has retired) as [row][hi 128 B | lo 128 B],
+        // 16-byte chunks XOR-swizzled by the row, written out as whole 128-byte lines: 16 lanes per row
+#pragma unroll
+        for (int j = 0; j < OW / 8; ++j) {
+          uint4 hi, lo;
+          split8(o + 8 * j, hi, lo);
+          const int c = (OW / 8) * part + j;
+          *reinterpret_cast<uint4*>(stg + row * 256 + ((c ^ (row & 15)) << 4)) = hi;
+          *reinterpret_cast<uint4*>(stg + row * 256 + (((8 + c) ^ (row & 15)) << 4)) = lo;
+        }
+        softmax_sync();
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int r = 8 * warp + 2 * k4 + (lane >> 4), c = lane & 15;
+          if (q0 + r < p.Lq) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 256 + ((c ^ (r & 15)) << 4));
+            __half* sp = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp) + h * D +
+                         (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
+            *reinterpret_cast<uint4*>(sp) = v;
+          }
+        }
+      }
+      // O has been read out of TMEM and this warp is done with the staging tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_oe);
+      if (it == 0) stamp(7);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  stamp(8);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+  stamp(9);
+}
+
+static int g_variant = 0;   // 0: persistent pipelined kernel where it applies, else P in TMEM + wide P V MMAs; 3: never the persistent kernel; 2: P in TMEM, three N = 64 MMAs per k-step; 1: P through shared memory
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
 
@@ -1160,6 +1461,36 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
                  q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n,
                  (atc::g_variant != 2 && NB == 1 && LB <= 384) ? 1 : 0, dv, key_mask, bias};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
+  // the persistent, pipelined kernel takes the plain head-dim-64 attentions whose Q + K + V tiles fit shared memory
+  // together (the ViT blocks up to 368 tokens; variant 3 = force off for A/B measurements)
+  {
+    const int nfull = Lk / 64, r16 = ((Lk % 64) + 15) / 16 * 16, rows_k = nfull * 64 + r16;
+    const int nchunks = nfull + (r16 ? 1 : 0);
+    const size_t v_bytes = (size_t)nchunks * atc::VBUF_BYTES > 2 * atc::BM * 128 ? (size_t)nchunks * atc::VBUF_BYTES : 2 * atc::BM * 128;
+    const size_t ps_smem = (size_t)atc::Q_BYTES + 2 * (size_t)rows_k * 128 + 1024 + v_bytes + atc::MISC_BYTES + 1024;
+    if (atc::g_variant == 0 && !general && NB == 1 && rows_k <= 384 && nchunks <= atc::MAX_CHUNKS && ps_smem <= 232448) {
+      static int num_sms_dev[64] = {};
+      int dev = 0;
+      EC_CUDA(cudaGetDevice(&dev));
+      if (dev >= 0 && dev < 64 && !num_sms_dev[dev])
+        EC_CUDA(cudaDeviceGetAttribute(&num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+      const int num_sms = (dev >= 0 && dev < 64) ? num_sms_dev[dev] : 148;
+      EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_ps_kernel, 232448));
+      CUtensorMap tmKp = tmK, tmVp = tmV;
+      if (r16) {
+        rc = tc::get_tensor_map(K2, k_total_rows, k_kp, r16, &tmKp);
+        if (rc) return rc;
+        rc = tc::get_tensor_map(V2, v_total_rows, v_kp, r16, &tmVp);
+        if (rc) return rc;
+      }
+      atc::ParamsP pp{p, rows_k, nfull, r16, cdiv(Lq, atc::BM), cdiv(Lq, atc::BM) * H * B};
+      pp.t.wide = 1;
+      const int ctas = pp.n_tiles < num_sms ? pp.n_tiles : num_sms;
+      launch_pdl(atc::attention_tc_ps_kernel, dim3(ctas), dim3(atc::THREADS_TS), ps_smem, (cudaStream_t)stream, tmQ, tmK,
+                 tmV, tmKp, tmVp, pp);
+      return check_launch("ec_attention_tc_split");
+    }
+  }
   if (atc::g_variant != 1 || general) {
     EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_ts_kernel,
                                              atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
@@ -1178,7 +1509,7 @@ extern "C" int ec_attention_tc_set_trace(void* buf, int n_ctas) {
 }
 
 extern "C" int ec_attention_tc_set_variant(int variant) {
-  EC_REQUIRE(variant >= 0 && variant <= 2, "ec_attention_tc_set_variant: 0, 1 or 2");
+  EC_REQUIRE(variant >= 0 && variant <= 3, "ec_attention_tc_set_variant: 0 .. 3");
   atc::g_variant = variant;
   return EC_OK;
 }
