@@ -172,7 +172,8 @@ class TwoStageHead(PackedMixin, nn.Module):
         L = tr["hs"].shape[0]
         output = ops.empty(L, B, K, 2, device=dev)
         for i in range(L):
-            delta = token_decode_mlp(tr["hs"][i].view(B * K, d), self.kpt_branch[i])
+            hs_i = tr["hs_split"][i] if tr["hs_split"][i] is not None else tr["hs"][i].view(B * K, d)
+            delta = token_decode_mlp(hs_i, self.kpt_branch[i])
             ops.point_update(tr["out_points"][i], delta, out=output[i])
         res = (output, tr["proposal_for_loss"], tr["similarity_map"], None, adj)
         if not return_intermediates:

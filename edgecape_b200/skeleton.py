@@ -117,11 +117,11 @@ class SkeletonPredictor(PackedMixin, nn.Module):
             ops.linear(feat, self.image_project.weight, self.image_project.bias, out=img_cat[:, :, :d])
             ops.copy_rows(grid_pos, img_cat.view(B * S, 2 * d)[:, d:], bcast_rows=S)
             kp_cat = torch.zeros(B, K, 2 * d, dtype=torch.float32, device=dev)
-            kp = kp_feat
+            kp, kp_split = kp_feat, None
             for i in range(self.num_layers):
-                kp = decoder_layer_forward(getattr(self.skeleton_predictor, str(i)), pk["layers"][i],
-                                           self.num_heads, kp, img_cat, kp_cat, kp_mask_fixed, adj_b, None,
-                                           two_way=self.two_way_attn)
+                kp, kp_split = decoder_layer_forward(getattr(self.skeleton_predictor, str(i)), pk["layers"][i],
+                                                     self.num_heads, kp, img_cat, kp_cat, kp_mask_fixed, adj_b, None,
+                                                     two_way=self.two_way_attn, kp_split=kp_split)
             acc = kp if acc is None else ops.axpby(acc, kp)
         if len(feats_s) > 1:
             acc = ops.axpby(acc, acc, 1.0, 0.0, float(len(feats_s)))         # torch.mean = sum / shots

@@ -58,7 +58,7 @@ def _split_attention_ok(x2d, w, D, Lk, masked=False):
 
 
 def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, adj, attn_adj=None, two_way=False,
-                          img_split=None, kv_split=None, kv_col=0):
+                          img_split=None, kv_split=None, kv_col=0, kp_split=None):
     """One TransformerDecoderLayer (encoder_decoder.py:584-651), batch-first.
 
     kp       [B,K,d]   keypoint tokens (contiguous)
@@ -68,8 +68,9 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
                        image tokens do not change, i.e. two_way=False)
     kv_split, kv_col   optional precomputed [k | v] projection of the image tokens (split-fp16, this layer's
                        columns start at kv_col): the main decoder projects all its layers in one GEMM
-    Returns the new keypoint tokens [B,K,d]; with two_way the image half of img_cat is updated in
-    place (norm4 output feeds the next layer, :638-649)."""
+    kp_split           optional split operand of kp (the previous layer's norm3 writes it next to the fp32 tokens)
+    Returns (new keypoint tokens [B,K,d], their split operand or None); with two_way the image half of img_cat is
+    updated in place (norm4 output feeds the next layer, :638-649)."""
     B, K, d = kp.shape
     S = img_cat.shape[1]
     dev = kp.device
@@ -79,7 +80,7 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     if attn_adj is not None and "hop" in pk:
         bias = ops.hop_bias(attn_adj, *pk["hop"])
     if _split_attention_ok(kp2d, pk["qkv_w"], d // nhead, K, masked=True):
-        qkv2 = ops.linear_split(kp2d, pk["qkv_w"], pk["qkv_b"])
+        qkv2 = ops.linear_split(kp_split if kp_split is not None else kp2d, pk["qkv_w"], pk["qkv_b"])
         a = ops.attention_packed_split(qkv2, B, K, nhead, key_mask=key_mask_fixed, bias=bias)
     else:
         qkv = ops.linear(kp2d, pk["qkv_w"], pk["qkv_b"]).view(B, K, 3 * d)
@@ -118,10 +119,19 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     else:
         g = ops.gcn(kp2.view(B, K, d), adj, pk["gcn_w"]).view(B * K, -1)
     t = ops.linear(g, node.ffn2.weight, node.ffn2.bias, residual=kp2)
+    # norm3 also writes the split operand of its consumers (the next layer's q/k/v projection, the keypoint branch)
+    want_split = ops.tc_linear_ok(kp2d, pk["qkv_w"])
     if not two_way:
-        return ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5).view(B, K, d)
+        if want_split:
+            y, ys = ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5, split="also")
+            return y.view(B, K, d), ys
+        return ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5).view(B, K, d), None
     # (iv) image tokens attend to the (un-masked!) keypoint tokens, choker, residual, norm4
-    ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5, out=kc2[:, :d])
+    kp3_split = None
+    if want_split:
+        _, kp3_split = ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5, out=kc2[:, :d], split="also")
+    else:
+        ops.layernorm(t, node.norm3.weight, node.norm3.bias, 1e-5, out=kc2[:, :d])
     kp3 = kc2[:, :d]
     ia, ip = node.cross_attn_image_to_token, pk["cross_attn_image_to_token"]
     if split_x:
@@ -142,26 +152,32 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     ops.layernorm(t, node.norm4.weight, node.norm4.bias, 1e-5, out=ic2[:, :d])
     out = ops.empty(B, K, d, device=dev)
     ops.copy_rows(kp3, out.view(B * K, d))
-    return out
+    return out, kp3_split
+
+
+def _chain(x, lins, out=None):
+    """Linear + GELU ... Linear.  On the tensor-core path the intermediate activations exist only as the split operand
+    the next GEMM consumes (written by the producing GEMM's epilogue: no fp32 round trip, no conversion launch); `x`
+    may itself be a SplitOperand."""
+    n = len(lins)
+    for i, lin in enumerate(lins):
+        if i == n - 1:
+            return ops.linear(x, lin.weight, lin.bias, out=out)
+        if ops.tc_linear_ok(x, lin.weight):
+            x = ops.linear(x, lin.weight, lin.bias, act=ops.ACT_GELU, split_out=True, fp32_out=False)[1]
+        else:
+            x = ops.linear(x, lin.weight, lin.bias, act=ops.ACT_GELU)
+    return x
 
 
 def mlp_gelu(x, node, n, out=None):
     """encoder_decoder.py:21-34 MLP (Linear+GELU ... Linear)."""
-    for i in range(n):
-        lin = getattr(node.layers, str(i))
-        last = i == n - 1
-        x = ops.linear(x, lin.weight, lin.bias, act=ops.ACT_NONE if last else ops.ACT_GELU,
-                       out=out if last else None)
-    return x
+    return _chain(x, [getattr(node.layers, str(i)) for i in range(n)], out=out)
 
 
 def token_decode_mlp(x, node):
-    """head.py:34-58 TokenDecodeMLP: 3 x (Linear + GELU) + Linear(->2); x [M,d] -> [M,2]."""
-    for i in (0, 2, 4):
-        lin = getattr(node.mlp, str(i))
-        x = ops.linear(x, lin.weight, lin.bias, act=ops.ACT_GELU)
-    lin = getattr(node.mlp, "6")
-    return ops.linear(x, lin.weight, lin.bias)
+    """head.py:34-58 TokenDecodeMLP: 3 x (Linear + GELU) + Linear(->2); x [M,d] (or its split operand) -> [M,2]."""
+    return _chain(x, [getattr(node.mlp, k) for k in ("0", "2", "4", "6")])
 
 
 @TRANSFORMER.register_module(force=True)
@@ -257,8 +273,17 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
                 a = ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], self.nhead,
                                   key_mask=key_mask).view(B * T, d)
             t = ops.linear(a, L.self_attn.out_proj.weight, L.self_attn.out_proj.bias, residual=x2)
-            ops.layernorm(t, L.norm1.weight, L.norm1.bias, 1e-5, out=x2)
-            f = ops.linear(x2, L.linear1.weight, L.linear1.bias, act=ops.ACT_RELU)
+            if ops.tc_linear_ok(x2, L.linear1.weight):
+                # norm1 also writes the split operand of linear1 (in the row format that GEMM takes), linear1 writes
+                # nothing but the split operand of linear2: two conversion launches and an fp32 round trip less
+                fmt = ops.F16F8 if ops.f8_linear_ok(B * T, L.linear1.weight) else ops.F16X2
+                _, x2s = ops.layernorm(t, L.norm1.weight, L.norm1.bias, 1e-5, out=x2, split="also", split_fmt=fmt)
+                fmt2 = ops.F16F8 if fmt == ops.F16F8 and ops.f8_linear_ok(B * T, L.linear2.weight) else ops.F16X2
+                f = ops.linear(x2s, L.linear1.weight, L.linear1.bias, act=ops.ACT_RELU, split_out=True, fp32_out=False,
+                               split_fmt=fmt2)[1]
+            else:
+                ops.layernorm(t, L.norm1.weight, L.norm1.bias, 1e-5, out=x2)
+                f = ops.linear(x2, L.linear1.weight, L.linear1.bias, act=ops.ACT_RELU)
             t = ops.linear(f, L.linear2.weight, L.linear2.bias, residual=x2)
             ops.layernorm(t, L.norm2.weight, L.norm2.bias, 1e-5, out=x2)
         return x
@@ -271,10 +296,13 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         K = kp.shape[1]
         fs = ops.linear(kp, pg.support_proj.weight, pg.support_proj.bias)               # [B,K,p]
         fq = ops.linear(img, pg.query_proj.weight, pg.query_proj.bias)                  # [B,S,p]
-        hdn = ops.linear(fs, getattr(pg.dynamic_proj, "0").weight, getattr(pg.dynamic_proj, "0").bias,
-                         act=ops.ACT_RELU)
-        fsf = ops.linear(hdn, getattr(pg.dynamic_proj, "2").weight, getattr(pg.dynamic_proj, "2").bias,
-                         act=ops.ACT_TANH, residual=fs, res_mode=ops.RES_GATE)           # (tanh(.)+1) * fs
+        d0, d2 = getattr(pg.dynamic_proj, "0"), getattr(pg.dynamic_proj, "2")
+        if ops.tc_linear_ok(fs, d0.weight):        # the hidden layer only exists as the split operand of the next GEMM
+            hdn = ops.linear(fs, d0.weight, d0.bias, act=ops.ACT_RELU, split_out=True, fp32_out=False)[1]
+        else:
+            hdn = ops.linear(fs, d0.weight, d0.bias, act=ops.ACT_RELU)
+        fsf = ops.linear(hdn, d2.weight, d2.bias, act=ops.ACT_TANH, residual=fs, res_mode=ops.RES_GATE)   # (tanh(.)+1) * fs
+        fsf = fsf.view(B, K, -1)
         sim = ops.gemm(fsf, fq, b_kmajor=True)                                           # [B,K,S] exact fp32
         pl, pr, am = ops.proposal(sim, h, w)
         return pl, sim.view(B, K, h, w), pr, am
@@ -313,6 +341,8 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
         hs = ops.empty(self.num_decoder_layers, B, K, d, device=dev)
         use_bias = self.attn_bias and attn_adj is not None
         kv_all = None
+        cur_split = None
+        hs_split = []
         for i in range(self.num_decoder_layers):
             L = getattr(self.decoder.layers, str(i))
             pe = position_embedding.forward_coordinates(bi)                               # [B,K,d]
@@ -321,15 +351,21 @@ class TwoStageSupportRefineTransformer(PackedMixin, nn.Module):
                     ops.attention_split_ok(2 * d // self.nhead, max(S, K)):
                 # image tokens are fixed over the layers: one split, one [k | v] projection GEMM for all of them
                 kv_all = ops.linear_split(ops.split_f16(img_cat.view(B * S, 2 * d)), packed["kv_w"], packed["kv_b"])
-            cur = decoder_layer_forward(L, pk[i], self.nhead, cur, img_cat, kp_cat, kp_mask_fixed, adj,
-                                        attn_adj if use_bias else None, two_way=False, kv_split=kv_all,
-                                        kv_col=i * 4 * d)
-            ops.layernorm(cur.view(B * K, d), self.decoder.norm.weight, self.decoder.norm.bias, 1e-5,
-                          out=hs[i].view(B * K, d))
-            delta = token_decode_mlp(cur.view(B * K, d), getattr(kpt_branch, str(i)))
+            cur, cur_split = decoder_layer_forward(L, pk[i], self.nhead, cur, img_cat, kp_cat, kp_mask_fixed, adj,
+                                                   attn_adj if use_bias else None, two_way=False, kv_split=kv_all,
+                                                   kv_col=i * 4 * d, kp_split=cur_split)
+            if cur_split is not None:      # the head's final decode runs the keypoint branch on hs[i]: split operand too
+                hs_split.append(ops.layernorm(cur.view(B * K, d), self.decoder.norm.weight, self.decoder.norm.bias, 1e-5,
+                                              out=hs[i].view(B * K, d), split="also")[1])
+            else:
+                hs_split.append(None)
+                ops.layernorm(cur.view(B * K, d), self.decoder.norm.weight, self.decoder.norm.bias, 1e-5,
+                              out=hs[i].view(B * K, d))
+            delta = token_decode_mlp(cur_split if cur_split is not None else cur.view(B * K, d),
+                                     getattr(kpt_branch, str(i)))
             bi = ops.point_update(bi, delta)
             points.append(bi)
-        return dict(hs=hs, out_points=points, proposal_for_loss=pl, similarity_map=sim, proposals=pr, argmax=am,
+        return dict(hs=hs, hs_split=hs_split, out_points=points, proposal_for_loss=pl, similarity_map=sim, proposals=pr, argmax=am,
                     encoder_image=img, encoder_kp=kp)
 
     def forward(self, *args, **kwargs):
