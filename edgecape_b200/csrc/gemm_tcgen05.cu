@@ -568,7 +568,12 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             h[i] = *reinterpret_cast<const uint32_t*>(&hh);
             f[i] = __half22float2(hh);
           }
-          if (cb > 0 || t > 0) epi_bar_sync();                          // the previous block has been read out of shared memory
+          // the previous block has been read out of shared memory: the issuing thread waits for its bulk stores' reads
+          // only here, after its own conversions, so the TMA engine drains the tile under everybody's arithmetic
+          if (cb > 0 || t > 0) {
+            if (warp == 2) tma_store_wait_read();
+            epi_bar_sync();
+          }
           // hi16: 16 columns = two 16-byte chunks (2 group, 2 group + 1) of the row's 128 bytes
           uint8_t* hrow = blk + row_l * 128;
           *reinterpret_cast<uint4*>(hrow + (((2 * group) ^ (row_l & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -610,8 +615,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_store_2d(&tmO8, blk_u32 + 16384, 2 * p.split_kp + col0, m0);
                 tma_store_2d(&tmO8, blk_u32 + 24576, 3 * p.split_kp + col0, m0);
               }
-              tma_store_commit();
-              tma_store_wait_read();                                    // shared memory may be overwritten; the global writes complete on their own
+              tma_store_commit();                                       // (reads awaited at the top of the next block)
             }
           }
           __syncwarp();
@@ -1071,7 +1075,13 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
     ec_tc_dynamic = (e && e[0] == '0') ? 0 : 1;
   }
   p.sched = nullptr;
-  if (ec_tc_dynamic) {
+  // dynamic tiles only pay when a CTA can take more than one: with one tile per CTA (the head's many small GEMMs) the
+  // two global atomics -- the tile and the terminator, a round trip each before the first TMA load can be issued --
+  // are pure latency, and the static assignment gives the same result
+  const long long single_tiles = (long long)cdiv(M, tc::BM) * cdiv(N, BN);
+  const int sched_ctas = (ec_tc_cta_limit > 0 && ec_tc_cta_limit < num_sms) ? ec_tc_cta_limit : num_sms;
+  const bool one_wave = mode == 512 ? pair_tiles <= sched_ctas / 2 : single_tiles <= sched_ctas;
+  if (ec_tc_dynamic && !one_wave) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     EC_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
     if (cap == cudaStreamCaptureStatusNone) {
