@@ -98,6 +98,7 @@ def parse():
                     help="queries per CPU-baseline step (0 = min(batch, 16), BASELINE.md section 3)")
     ap.add_argument("--sustained-seconds", type=float, default=10.0,
                     help="length of the extra sustained-throughput pass (clock sampler on); 0 disables it")
+    ap.add_argument("--depth", type=int, default=0, help="batches in flight in the library's pipeline (0 = its default, 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -376,6 +377,8 @@ def run_ours(args):
     model.load_state_dict(make_state_dict(state_dict_shapes(cfg), 0), strict=True)
     model = model.cuda().eval()
     model.use_cuda_graph = not args.no_graph
+    if args.depth > 0:
+        model.test_cfg = dict(model.test_cfg, pipeline_depth=args.depth)
 
     B, R, K = args.batch, args.image_size, args.kpts
     NB = 4   # distinct input batches rotated through the timed region
