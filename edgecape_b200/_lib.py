@@ -58,6 +58,7 @@ SIGNATURES = {
     "ec_soft_normalize_adj": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "ec_l2_normalize": (c_int, [c_fp, c_fp, c_int, c_int, c_f, c_fp]),
     "ec_edge_weights": (c_int, [c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
+    "ec_markov_powers": (c_int, [c_fp, c_int, c_int, c_int, c_fp]),
     "ec_gcn_pack_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "ec_gcn": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp, c_sz, c_fp]),
     "ec_gcn_aggregate_split": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),

@@ -511,6 +511,15 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t* blk = smem_raw + (epi_base - smem_u32(smem_raw));      // [hi16 16 KB | lo16 16 KB] or [hi16 | hi8 8 KB | lo8 8 KB]
         const uint32_t blk_u32 = epi_base;
         const int row_l = quarter * 32 + lane;                          // row of the 128-row block = TMEM lane
+        // bias / LayerScale of a block: ONE coalesced load per warp (lane u holds column u of the 16), fetched a block
+        // ahead of its use -- shared memory takes nearly all of the L1 carve-out, so these loads come from L2
+        // (~700 clk); read at the point of use (16 loads per lane and round) they were the largest single stall of
+        // the epilogue warps (ncu source page, profiles/r02_q_ncu_fc1_stalls.md)
+        auto load_vec = [&](const float* v, int cb, float dflt) {
+          const int c = n0 + cb * 64 + group * 16 + (lane & 15);
+          return (v && c < p.N) ? __ldg(v + c) : dflt;
+        };
+        float bias_nxt = load_vec(p.bias, 0, 0.f), cs_nxt = load_vec(p.colscale, 0, 1.f);
         mbar_wait(tfull_bar(acc), (t >> 1) & 1);
         tc_fence_after();
         if (p.dbg & 8) {   // experiment: no epilogue at all (the accumulator is handed straight back)
@@ -538,12 +547,15 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           const int gcol = col0 + group * 16;
+          const float bias_cur = bias_nxt, cs_cur = cs_nxt;
+          if (cb + 1 < NBLK) {
+            bias_nxt = load_vec(p.bias, cb + 1, 0.f);
+            cs_nxt = load_vec(p.colscale, cb + 1, 1.f);
+          }
           float y[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const float bias = (p.bias && gcol + u < p.N) ? __ldg(p.bias + gcol + u) : 0.f;
-            y[u] = fmaf(__uint_as_float(r[u]), p.out_scale, bias);
-          }
+          for (int u = 0; u < 16; ++u)
+            y[u] = fmaf(__uint_as_float(r[u]), p.out_scale, __shfl_sync(0xffffffffu, bias_cur, u));
           if (p.act == EC_ACT_RELU) {
 #pragma unroll
             for (int u = 0; u < 16; ++u) y[u] = fmaxf(y[u], 0.f);
@@ -556,7 +568,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (p.colscale) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) y[u] *= (gcol + u < p.N) ? __ldg(p.colscale + gcol + u) : 1.f;
+            for (int u = 0; u < 16; ++u) y[u] *= __shfl_sync(0xffffffffu, cs_cur, u);
           }
 #pragma unroll
           for (int u = 0; u < 16; ++u) y[u] = (gcol + u < p.N) ? y[u] * p.split_scale : 0.f;
@@ -570,6 +582,42 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           // the previous block has been read out of shared memory: the issuing thread waits for its bulk stores' reads
           // only here, after its own conversions, so the TMA engine drains the tile under everybody's arithmetic
+          if (p.split_tma == 2) {
+            // experiment / alternative: every lane stores the pieces of its own row straight from registers -- no
+            // shared-memory traffic at all (the F16F8 main loop already moves ~106 of the 128 B/clk of shared-memory
+            // bandwidth: 64 KB of TMA fill + 64 KB of UMMA operand reads per 1208-clk k-block), no CTA-wide barriers;
+            // 32 rows x 16 B per store instruction
+            const int grow = m0 + row_l;
+            if (grow < p.M && !(p.dbg & 16)) {
+              uint8_t* orow = reinterpret_cast<uint8_t*>(p.split_out) + (long long)grow * (4 * p.split_kp);
+              *reinterpret_cast<uint4*>(orow + 2 * gcol) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(orow + 2 * gcol + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+              if (p.split_fmt == EC_SPLIT_F16X2) {
+                uint32_t l[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const __half2 ll = __floats2half2_rn(y[2 * i] - f[i].x, y[2 * i + 1] - f[i].y);
+                  l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                *reinterpret_cast<uint4*>(orow + 2 * p.split_kp + 2 * gcol) = make_uint4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4*>(orow + 2 * p.split_kp + 2 * gcol + 16) = make_uint4(l[4], l[5], l[6], l[7]);
+              } else {
+                uint32_t h8[4], l8[4];
+                float m = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  h8[i] = e4m3x2(f[2 * i].x, f[2 * i].y) | (e4m3x2(f[2 * i + 1].x, f[2 * i + 1].y) << 16);
+                  l8[i] = e4m3x2((y[4 * i] - f[2 * i].x) * 2048.f, (y[4 * i + 1] - f[2 * i].y) * 2048.f) |
+                          (e4m3x2((y[4 * i + 2] - f[2 * i + 1].x) * 2048.f, (y[4 * i + 3] - f[2 * i + 1].y) * 2048.f) << 16);
+                  m = fmaxf(m, fmaxf(fmaxf(fabsf(y[4 * i]), fabsf(y[4 * i + 1])), fmaxf(fabsf(y[4 * i + 2]), fabsf(y[4 * i + 3]))));
+                }
+                ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
+                *reinterpret_cast<uint4*>(orow + 2 * p.split_kp + gcol) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                *reinterpret_cast<uint4*>(orow + 3 * p.split_kp + gcol) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+              }
+            }
+            continue;
+          }
           if (cb > 0 || t > 0) {
             if (warp == 2) tma_store_wait_read();
             epi_bar_sync();
@@ -644,7 +692,25 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       };
-      float4 rcur[4], rnext[4];
+      // bias / LayerScale of a sub-chunk (4 columns per lane), fetched a sub-chunk ahead like the residual rows: with
+      // shared memory taking the L1 carve-out these are L2 round trips (~700 clk), exposed once per sub-chunk when
+      // read at the point of use
+      auto load_bs = [&](int sc, float4& b4, float4& s4) {
+        const int gc = n0 + sc * 16 + c4;
+        float bb[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {1.f, 1.f, 1.f, 1.f};
+        if (sc < NSUB) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (gc + u < p.N) {
+              if (p.bias) bb[u] = __ldg(p.bias + gc + u);
+              if (p.colscale) ss[u] = __ldg(p.colscale + gc + u);
+            }
+        }
+        b4 = make_float4(bb[0], bb[1], bb[2], bb[3]);
+        s4 = make_float4(ss[0], ss[1], ss[2], ss[3]);
+      };
+      float4 rcur[4], rnext[4], bcur, scur, bnext, snext;
+      load_bs(group, bcur, scur);
       if (p.R) load_res(group, rcur);
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
@@ -662,6 +728,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + sc * 16), r);
         if (p.R) load_res(sc + NGROUP, rnext);
+        load_bs(sc + NGROUP, bnext, snext);
         if (sc + NGROUP >= NSUB) {
           // this warp has drained its share of the accumulator: hand it back to the MMA warp early
           tc_fence_before();
@@ -680,13 +747,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int gcol = n0 + sc * 16 + c4;
         if (gcol < p.N) {
           const bool full = gcol + 3 < p.N;
-          float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (gcol + u < p.N) {
-              if (p.bias) bv[u] = __ldg(p.bias + gcol + u);
-              if (p.colscale) sv[u] = __ldg(p.colscale + gcol + u);
-            }
+          const float bv[4] = {bcur.x, bcur.y, bcur.z, bcur.w}, sv[4] = {scur.x, scur.y, scur.z, scur.w};
           float y[4][4];
           // accumulator * out_scale + bias, activation (transcendental ones in a rolled loop: code size)
 #pragma unroll
@@ -751,6 +812,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
         }
+        bcur = bnext;
+        scur = snext;
       }
     }
     report_overflow(p.overflow, ovf);
@@ -959,7 +1022,8 @@ extern "C" int ec_tc_set_cta_limit(int ctas) {
 }
 static int ec_tc_split_tma = 1;  // split-only epilogues through TMA stores (0: scattered stores, for A/B measurements)
 extern "C" int ec_tc_set_split_tma(int on) {
-  ec_tc_split_tma = on ? 1 : 0;
+  EC_REQUIRE(on >= 0 && on <= 2, "ec_tc_set_split_tma: 0, 1 or 2");
+  ec_tc_split_tma = on;
   return EC_OK;
 }
 static int ec_tc_force_bn = 0;   // 0 = heuristic; 128 / 256 force a tile width (tuning / tests)
@@ -1050,7 +1114,7 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
     }
   }
   tc::TcParams p{};
-  p.split_tma = split_tma ? 1 : 0;
+  p.split_tma = split_tma ? ec_tc_split_tma : 0;
   p.split_fmt = split_fmt;
   if (split_out && split_fmt == EC_SPLIT_F16F8) {
     p.overflow = overflow_counters();

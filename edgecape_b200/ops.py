@@ -523,6 +523,20 @@ def edge_weights(S, binary, kp_mask, zc_w, zc_b, use_zero_conv, hops=None):
     return adj, unnorm
 
 
+def markov_powers_(hops):
+    """hops [H+1, B, K, K] with planes 0, 1 filled -> planes 2..H = P^h (skeleton.py:152-161), one launch."""
+    _chk(hops, "hops")
+    assert hops.is_contiguous() and hops.dim() == 4 and hops.shape[2] == hops.shape[3]
+    H1, B, K, _ = hops.shape
+    if H1 > 2:
+        _lib.call("ec_markov_powers", _p(hops), H1 - 1, B, K, _stream())
+    return hops
+
+
+def markov_powers_ok(K):
+    return (K * (K + 1) + 4 + 32 * K) * 4 <= 227 * 1024 and K <= 256
+
+
 def gcn_pack_weights(W, bias):
     """Conv1d(k=1) weight [2*dff, d(,1)] + bias [2*dff] -> packed [dff, 2d+4]."""
     _chk(W, "W"); _chk(bias, "bias")

@@ -130,11 +130,14 @@ class SkeletonPredictor(PackedMixin, nn.Module):
         gram = ops.gemm(fn, fn, b_kmajor=True)                                   # [B,K,K]
         hops = ops.empty(self.max_hop + 1, B, K, K, device=dev)
         adj, unnorm = ops.edge_weights(gram, binary, kp_mask, pk["zc"][0], pk["zc"][1], self.use_zero_conv, hops)
-        for hpow in range(2, self.max_hop + 1):
-            # P^h: torch.matrix_power association is irrelevant at fp32 round-off
-            left = hops[hpow // 2]
-            right = hops[hpow - hpow // 2]
-            ops.gemm(left, right, out=hops[hpow], b_kmajor=False)
+        if ops.markov_powers_ok(K):
+            ops.markov_powers_(hops)                 # P^2 .. P^max_hop in one launch (P^h = P^(h-1) P)
+        else:
+            for hpow in range(2, self.max_hop + 1):
+                # P^h: torch.matrix_power association is irrelevant at fp32 round-off
+                left = hops[hpow // 2]
+                right = hops[hpow - hpow // 2]
+                ops.gemm(left, right, out=hops[hpow], b_kmajor=False)
         return adj, hops, unnorm, acc
 
     def forward(self, skeleton, kp_features, image_features, kp_mask, query_image_pos_embed):

@@ -119,8 +119,9 @@ int ec_tc_set_tile_n(int bn);
  * mode of ec_gemm_f16f8. */
 long long ec_tc_mode_launches(int mode);
 /* epilogue of the GEMMs whose only output is split_out (default 1): 1 = the CTA assembles 128-row x 64-column blocks of
- * the split rows in shared memory and writes them with TMA bulk tensor stores; 0 = every lane stores its own pieces
- * (kept for A/B measurements). */
+ * the split rows in shared memory and writes them with TMA bulk tensor stores; 2 = every lane converts the 16 columns of
+ * its own accumulator row and stores them straight from registers (no shared-memory traffic); 0 = the transposing
+ * epilogue of the fp32 outputs (kept for A/B measurements). */
 int ec_tc_set_split_tma(int on);
 /* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
  * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
@@ -244,11 +245,16 @@ int ec_soft_normalize_adj(const float* U, const uint8_t* kp_mask, float* adj, in
  * L2-normalised refined keypoint tokens (ec_l2_normalize + ec_gemm):
  * U = relu(binary + w*(S+S^T)/2 + b); adj = soft_normalize(U); unnorm = U * valid x valid;
  * hops[0..n_hops-1] (skeleton.py:152-161) get P^0 = I and P^1 = adj1/(rowsum+1e-8); higher
- * powers are ec_gemm products. */
+ * powers: ec_markov_powers. */
 int ec_l2_normalize(const float* X, float* Y, int M, int C, float eps, void* stream);
 int ec_edge_weights(const float* S, const float* binary, const uint8_t* kp_mask, float zc_w,
                     float zc_b, int use_zero_conv, float* adj, float* unnorm, float* hop0,
                     float* hop1, int B, int K, void* stream);
+/* markov_transition_matrix's higher powers (skeleton.py:152-161: torch.matrix_power(P, h), h = 2 .. max_hop) in ONE
+ * launch: hops is [max_hop + 1, B, K, K] with planes 0 and 1 filled by ec_edge_weights; plane h = plane (h-1) . plane 1,
+ * row i of a power only needs row i of the one before, so a warp walks 8 rows through every power on its own (CTA =
+ * sample x 32 rows, P^1 resident in shared memory; K <= 224; exact fp32 FFMA). */
+int ec_markov_powers(float* hops, int max_hop, int B, int K, void* stream);
 
 /* GCN feed-forward (encoder_decoder.py:508-524), aggregate-first form:
  * Y[b,w,:] = relu( a0[b,w] * (X[b,w,:] W0^T + b0) + sum_v A1[b,w,v] (X[b,v,:] W1^T + b1) )

@@ -26,6 +26,8 @@ def main():
     D = torch.device("cuda")
     M, C = 10400, 768
     lib = _lib.load()
+    if len(sys.argv) > 2:
+        lib.ec_tc_set_split_tma(int(sys.argv[2]))      # 1 = TMA stores (default), 2 = direct stores, 0 = transposing epilogue
     for fmt, tag in ((ops.F16F8, "f16+2xf8"), (ops.F16X2, "3xf16")):
         x2 = ops.split_f16(torch.randn(M, C, device=D), fmt=fmt)
         h2 = ops.split_f16(torch.randn(M, 4 * C, device=D), fmt=fmt)

@@ -409,6 +409,12 @@ def _e4m3(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).to(torch.float32).numpy()
 
 
+def ec_markov_powers(hops, max_hop, B, K, stream):
+    h = arr(hops, (max_hop + 1, B, K, K))
+    for p in range(2, max_hop + 1):
+        h[p] = np.matmul(h[p - 1], h[1])
+
+
 def ec_split_f16f8(X, out, M, K, ldx, seg, seg_stride, Kp, scale, role, stream):
     """[hi16 | hi8 | lo8] planes (include/edgecape_b200.h, EC_SPLIT_F16F8): role 0 = activations, 1 = weights."""
     x = _get(rows(X, M, K, ldx, seg, seg_stride)).astype(np.float32) * np.float32(scale)

@@ -210,10 +210,11 @@ def test_split_only_epilogue_through_tma_stores(M, N, K, fmt_in, tile_n):
             so = ops.gemm_tc(a2, b2, bias=b, act=ops.ACT_GELU, split_out=True, fp32_out=False, split_fmt=fmt_out)[1]
             want = ops.split_f16(ref, fmt=fmt_out, role=0)
             assert so.Kp == want.Kp and torch.equal(so.data.view(torch.uint8), want.data.view(torch.uint8)), fmt_out
-            ops._lib.call("ec_tc_set_split_tma", 0)                 # the scattered-store form gives the same bytes
-            so0 = ops.gemm_tc(a2, b2, bias=b, act=ops.ACT_GELU, split_out=True, fp32_out=False, split_fmt=fmt_out)[1]
-            ops._lib.call("ec_tc_set_split_tma", 1)
-            assert torch.equal(so0.data.view(torch.uint8), want.data.view(torch.uint8))
+            for mode in (0, 2):                                     # the other two epilogue forms give the same bytes
+                ops._lib.call("ec_tc_set_split_tma", mode)
+                so0 = ops.gemm_tc(a2, b2, bias=b, act=ops.ACT_GELU, split_out=True, fp32_out=False, split_fmt=fmt_out)[1]
+                ops._lib.call("ec_tc_set_split_tma", 1)
+                assert torch.equal(so0.data.view(torch.uint8), want.data.view(torch.uint8)), mode
     finally:
         ops._lib.call("ec_tc_set_split_tma", 1)
         ops._lib.call("ec_tc_set_tile_n", 0)

@@ -646,3 +646,19 @@ def test_linear_dispatch_uses_tensor_cores_and_matches_simt(monkeypatch):
     assert names[-1] == "ec_gemm"
     close(y_tc, y_32, tol=3e-6, what="tc vs simt")
     close(y_tc, F.linear(x, w, b), tol=3e-6, what="tc vs torch")
+
+
+@pytest.mark.parametrize("B,K,H", [(16, 100, 4), (3, 17, 4), (2, 200, 4), (1, 5, 2), (4, 33, 1)])
+def test_markov_powers_one_launch(B, K, H):
+    """ec_markov_powers: planes 2..H of the hop tensor = torch.matrix_power(P, h) (skeleton.py:152-161), one launch."""
+    g = torch.Generator().manual_seed(B * 1000 + K)
+    P = torch.rand(B, K, K, generator=g)
+    P = P / P.sum(-1, keepdim=True)
+    hops = torch.zeros(H + 1, B, K, K)
+    hops[0] = torch.eye(K)
+    if H >= 1:
+        hops[1] = P
+    got = ops.markov_powers_(hops.to(dev())).cpu()
+    for h in range(H + 1):
+        want = torch.matrix_power(P.double(), h).float()
+        assert (got[h] - want).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item()), h
