@@ -277,11 +277,13 @@ extern "C" int ec_edge_weights(const float* S, const float* binary, const uint8_
 }
 
 // Markov hop matrices P^2 .. P^H (skeleton.py:152-161, torch.matrix_power).  P^h = P^(h-1) . P^1, and row i of P^h only
-// needs row i of P^(h-1): a warp owns 8 rows of one sample and walks them through every power on its own -- no
-// synchronisation between steps.  CTA = (sample, block of 32 rows): P^1 in shared memory as the right operand (rows
-// padded by one float), the warp's 8 current rows transposed in a private buffer so that one float4 pair broadcasts
-// them; 8 x 8 accumulators per lane (columns lane + 32 c), 6 shared loads per 32 .. 64 FMAs.
-constexpr int MK_ROWS = 8, MK_WARPS = 4;
+// needs row i of P^(h-1): a warp owns 4 rows of one sample and walks them through every power on its own -- no
+// synchronisation between steps.  CTA = (sample, block of 32 rows; 8 warps): P^1 in shared memory as the right operand
+// (rows padded by one float), the warp's 4 current rows transposed in a private buffer so that one float4 broadcasts
+// them; 4 x NC accumulators per lane (columns lane + 32 c; NC = ceil(K / 32) is a template parameter: no predicated
+// or branching inner loop -- with two warps per scheduler every exposed latency counts).
+constexpr int MK_ROWS = 4, MK_WARPS = 8;
+template <int NC>
 __global__ void __launch_bounds__(32 * MK_WARPS) markov_powers_kernel(float* __restrict__ hops, int H, int B, int K) {
   extern __shared__ float mk_smem[];
   pdl_launch_dependents();
@@ -289,10 +291,10 @@ __global__ void __launch_bounds__(32 * MK_WARPS) markov_powers_kernel(float* __r
   const int ldp = K + 1;
   float* P1 = mk_smem;                                         // [K][K+1]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* rowsT = P1 + (((size_t)K * ldp + 3) & ~(size_t)3) + (size_t)warp * K * MK_ROWS;   // [K][8] (16-byte aligned): value v of the warp's 8 rows
+  float* rowsT = P1 + (((size_t)K * ldp + 3) & ~(size_t)3) + (size_t)warp * K * MK_ROWS;   // [K][4] (16-byte aligned)
   const size_t plane = (size_t)B * K * K;
   const float* p1g = hops + plane + (size_t)b * K * K;
-  // 8 independent loads in flight per thread: with 128 threads a one-load-per-iteration loop is 78 serialised L2 round trips
+  // 8 independent loads in flight per thread (a one-load-per-iteration loop is a chain of L2 round trips)
   for (int base0 = 0; base0 < K * K; base0 += 8 * (int)blockDim.x) {
     float v[8];
 #pragma unroll
@@ -309,42 +311,41 @@ __global__ void __launch_bounds__(32 * MK_WARPS) markov_powers_kernel(float* __r
   __syncthreads();
   const int row0 = (blockIdx.y * MK_WARPS + warp) * MK_ROWS;
   if (row0 >= K) return;
-  const int ncol = (K + 31) / 32;                              // columns per lane (<= 8)
   for (int v = lane; v < K; v += 32)
 #pragma unroll
     for (int r = 0; r < MK_ROWS; ++r) rowsT[v * MK_ROWS + r] = (row0 + r < K) ? P1[(row0 + r) * ldp + v] : 0.f;
   __syncwarp();
+  // columns >= K of the last group read the padding / the next row of P1 (finite values) and are never stored
+  const float* pcol = P1 + lane;
   for (int h = 2; h <= H; ++h) {
-    float acc[MK_ROWS][8];
+    float acc[MK_ROWS][NC];
 #pragma unroll
     for (int r = 0; r < MK_ROWS; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
     for (int v = 0; v < K; ++v) {
-      const float4 l0 = *reinterpret_cast<const float4*>(rowsT + v * MK_ROWS);
-      const float4 l1 = *reinterpret_cast<const float4*>(rowsT + v * MK_ROWS + 4);
-      const float l[MK_ROWS] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-      const float* pr = P1 + v * ldp + lane;
+      const float4 l = *reinterpret_cast<const float4*>(rowsT + v * MK_ROWS);
+      const float* pr = pcol + v * ldp;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c < ncol) {
-          const float pv = (lane + 32 * c < K) ? pr[32 * c] : 0.f;
-#pragma unroll
-          for (int r = 0; r < MK_ROWS; ++r) acc[r][c] = fmaf(l[r], pv, acc[r][c]);
-        }
+      for (int c = 0; c < NC; ++c) {
+        const float pv = pr[32 * c];
+        acc[0][c] = fmaf(l.x, pv, acc[0][c]);
+        acc[1][c] = fmaf(l.y, pv, acc[1][c]);
+        acc[2][c] = fmaf(l.z, pv, acc[2][c]);
+        acc[3][c] = fmaf(l.w, pv, acc[3][c]);
       }
     }
     __syncwarp();                                              // every lane is done reading the rows of P^(h-1)
     float* out = hops + (size_t)h * plane + (size_t)b * K * K;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int j = lane + 32 * c;
-      if (c < ncol && j < K) {
+      if (j < K) {
 #pragma unroll
-        for (int r = 0; r < MK_ROWS; ++r) {
+        for (int r = 0; r < MK_ROWS; ++r)
           if (row0 + r < K) out[(size_t)(row0 + r) * K + j] = acc[r][c];
-          rowsT[j * MK_ROWS + r] = acc[r][c];
-        }
+        *reinterpret_cast<float4*>(rowsT + j * MK_ROWS) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
       }
     }
     __syncwarp();
@@ -355,11 +356,21 @@ extern "C" int ec_markov_powers(float* hops, int max_hop, int B, int K, void* st
   EC_REQUIRE(hops, "ec_markov_powers: null pointer");
   EC_REQUIRE(K > 0 && K <= 256, "ec_markov_powers: K must be in [1, 256]");
   if (B == 0 || max_hop < 2) return EC_OK;
-  const size_t smem = ((size_t)K * (K + 1) + 4 + (size_t)MK_WARPS * MK_ROWS * K) * sizeof(float);
+  // P1 (+ one spare row: the last column group of the last rows reads up to 31 floats past the matrix) + row buffers
+  const size_t smem = ((size_t)(K + 1) * (K + 1) + 4 + (size_t)MK_WARPS * MK_ROWS * K) * sizeof(float);
   EC_REQUIRE(smem <= 227 * 1024, "ec_markov_powers: K too large for shared memory");
-  EC_CUDA((cudaError_t)ensure_dynamic_smem(markov_powers_kernel, (int)smem));
-  launch_pdl(markov_powers_kernel, dim3(B, cdiv(K, MK_WARPS * MK_ROWS)), dim3(32 * MK_WARPS), smem, (cudaStream_t)stream, hops,
-             max_hop, B, K);
+  const dim3 grid(B, cdiv(K, MK_WARPS * MK_ROWS)), block(32 * MK_WARPS);
+  cudaStream_t st = (cudaStream_t)stream;
+#define EC_MK(NC)                                                                          \
+  case NC:                                                                                 \
+    EC_CUDA((cudaError_t)ensure_dynamic_smem(markov_powers_kernel<NC>, (int)smem));        \
+    launch_pdl(markov_powers_kernel<NC>, grid, block, smem, st, hops, max_hop, B, K);      \
+    break;
+  switch (cdiv(K, 32)) {
+    EC_MK(1) EC_MK(2) EC_MK(3) EC_MK(4) EC_MK(5) EC_MK(6) EC_MK(7) EC_MK(8)
+    default: break;
+  }
+#undef EC_MK
   return check_launch("ec_markov_powers");
 }
 

@@ -534,7 +534,7 @@ def markov_powers_(hops):
 
 
 def markov_powers_ok(K):
-    return (K * (K + 1) + 4 + 32 * K) * 4 <= 227 * 1024 and K <= 256
+    return ((K + 1) * (K + 1) + 4 + 32 * K) * 4 <= 227 * 1024 and K <= 256
 
 
 def gcn_pack_weights(W, bias):
