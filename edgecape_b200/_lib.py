@@ -33,6 +33,7 @@ SIGNATURES = {
     "ec_tc_mode_launches": (c_ll, [c_int]),
     "ec_tc_set_cta_limit": (c_int, [c_int]),
     "ec_tc_set_split_tma": (c_int, [c_int]),
+    "ec_tc_set_trace": (c_int, [c_fp]),
     "ec_tc_set_dynamic": (c_int, [c_int]),
     "ec_set_pdl": (c_int, [c_int]),
     "ec_tc_set_debug": (c_int, [c_int]),

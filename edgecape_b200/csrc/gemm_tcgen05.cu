@@ -159,6 +159,7 @@ struct TcParams {
   int split_fmt;       // EC_SPLIT_F16X2 = [hi16 | lo16], EC_SPLIT_F16F8 = [hi16 | hi8 | lo8] (common.cuh)
   float split_scale;
   unsigned long long* overflow;   // F16F8 producers: {beyond e4m3, beyond fp16} event counters
+  long long* trace;    // profiling (ec_tc_set_trace): per leader CTA {MMA thread total clk, clk waiting for an accumulator, clk waiting for operands, tiles}
   int split_tma;       // split_out is the only output: the epilogue assembles 128 x 64 blocks in shared memory and TMA-stores them
   int* sched;          // dynamic tile scheduler: {next tile, finished workers} of this launch (zero on entry), or NULL
 };
@@ -403,16 +404,24 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long tr_t0 = 0, tr_acc = 0, tr_full = 0;
+      int tr_tiles = 0;
+      if (p.trace) tr_t0 = clock64();
       for (int t = 0;; ++t) {
         const int tile = ring_get(t);
         ring_release(t, tile);
         if (tile < 0) break;
         const int acc = t & 1;
+        long long c0 = 0;
+        if (p.trace) c0 = clock64();
         mbar_wait(tempty_bar(acc), ((t >> 1) & 1) ^ 1);
+        if (p.trace) { tr_acc += clock64() - c0; ++tr_tiles; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (p.trace) c0 = clock64();
           mbar_wait(full_bar(stage), phase);
+          if (p.trace) tr_full += clock64() - c0;
           tc_fence_after();
           const uint32_t sb = base + stage * STAGE_BYTES;
           const uint64_t a_hi = make_smem_desc(sb + 0 * TILE_BYTES), b_hi = make_smem_desc(sb + 2 * TILE_BYTES);
@@ -466,6 +475,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (TWO) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
+      }
+      if (p.trace) {
+        long long* o = p.trace + 4 * worker;
+        o[0] = clock64() - tr_t0; o[1] = tr_acc; o[2] = tr_full; o[3] = tr_tiles;
       }
     }
   } else {
@@ -1026,6 +1039,11 @@ extern "C" int ec_tc_set_split_tma(int on) {
   ec_tc_split_tma = on;
   return EC_OK;
 }
+static long long* ec_tc_trace = nullptr;   // profiling: [workers][4] int64, see TcParams::trace
+extern "C" int ec_tc_set_trace(void* buf) {
+  ec_tc_trace = (long long*)buf;
+  return EC_OK;
+}
 static int ec_tc_force_bn = 0;   // 0 = heuristic; 128 / 256 force a tile width (tuning / tests)
 extern "C" int ec_tc_set_tile_n(int bn) {
   EC_REQUIRE(bn == 0 || bn == 128 || bn == 256 || bn == 512, "ec_tc_set_tile_n: 0, 128, 256 or 512 (CTA pair)");
@@ -1130,6 +1148,7 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
   p.out_scale = out_scale; p.bias = bias; p.colscale = colscale; p.R = R; p.ldr = ldr; p.act = act;
   p.res_mode = res_mode; p.res_rows = res_rows; p.split_out = (__half*)split_out; p.split_kp = split_kp; p.split_scale = split_scale;
   p.dbg = ec_tc_debug;
+  p.trace = ec_tc_trace;
   // one {next tile, finished workers} pair per launch, re-armed by the launch's last worker.  Eager launches cycle
   // through a ring of slots (a slot is reused 4096 launches later); launches recorded into a CUDA graph keep their slot
   // for the life of the process (the node replays with it, possibly concurrently with eager work on another stream), so

@@ -123,6 +123,9 @@ long long ec_tc_mode_launches(int mode);
  * its own accumulator row and stores them straight from registers (no shared-memory traffic); 0 = the transposing
  * epilogue of the fp32 outputs (kept for A/B measurements). */
 int ec_tc_set_split_tma(int on);
+/* profiling: buf = device array [148][4] of int64, or NULL (default).  Every leader CTA's MMA thread then writes {total
+ * clocks, clocks waiting for a free accumulator (= for the epilogue), clocks waiting for operands (= for TMA), tiles}. */
+int ec_tc_set_trace(void* buf);
 /* cap on the CTAs of the persistent GEMM grids (0 = one per SM).  With consecutive batches pipelined (backbone of
  * batch i+1 beside the head of batch i) a cap below the SM count leaves SMs to the other stream's small kernels. */
 int ec_tc_set_cta_limit(int ctas);

@@ -51,6 +51,17 @@ def main():
             line += f"  dbg{flags} {us:6.1f} us ({2.0 * M * ws[n].rows * K / us / 1e6:4.0f} TF/s)"
             lib.ec_tc_set_debug(0)
             print(line, flush=True)
+            if flags == 0:      # where does the MMA thread wait?  (one traced launch)
+                buf = torch.zeros(148, 4, dtype=torch.int64, device=D)
+                lib.ec_tc_set_trace(buf.data_ptr())
+                fn()
+                torch.cuda.synchronize()
+                lib.ec_tc_set_trace(None)
+                tr = buf.cpu().double()
+                tr = tr[tr[:, 3] > 0]
+                print(f"      MMA thread of {len(tr)} leader CTAs: total {tr[:, 0].mean():.0f} clk, waiting for an accumulator "
+                      f"(epilogue) {tr[:, 1].mean():.0f} ({100 * tr[:, 1].sum() / tr[:, 0].sum():.0f} %), waiting for operands (TMA) "
+                      f"{tr[:, 2].mean():.0f} ({100 * tr[:, 2].sum() / tr[:, 0].sum():.0f} %), tiles {tr[:, 3].mean():.1f}", flush=True)
     lib.ec_tc_set_tile_n(0)
 
 
