@@ -915,7 +915,13 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int j = part; j < nchunk32; j += NPART) {
         float s[32];
         tmem_ld32(t_row + j * 32, s);
-        if (gen) {
+        if (gen && !bias_row && mskw[j] == 0u) {
+          // the key mask is one word per 32 keys, the same for every lane: a word with no masked key (all but the
+          // tail of a padded keypoint list) takes the plain path -- the per-element tests doubled the cost of the
+          // encoder self-attention (424 keys, 24 of them padding)
+#pragma unroll
+          for (int u = 0; u < 32; ++u) mymax = fmaxf(mymax, s[u] * p.scale);
+        } else if (gen) {
           const uint32_t mw = mskw[j];
           if (bias_row) {
 #pragma unroll
@@ -956,7 +962,15 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         float s[PW];
         const int kbase = i * KC + PW * part;
         tmem_ld16(t_row + kbase, s);
-        if (gen) {
+        if (gen && !bias_row && ((mskw[kbase >> 5] >> (kbase & 31)) & 0xffffu) == 0u) {
+          // no masked key among these 16 (warp-uniform): x = s * scale, p = exp2(x * log2 e - max * log2 e) in one FMA
+          const float nbg = -rmax * 1.4426950408889634f;
+#pragma unroll
+          for (int u = 0; u < PW; ++u) {
+            s[u] = ex2(fmaf(s[u], sl2, nbg));
+            rsum += s[u];
+          }
+        } else if (gen) {
           const float L2E = 1.4426950408889634f;
           const uint32_t mw = mskw[kbase >> 5] >> (kbase & 31);        // PW = 16 keys: half a word
           const float nbg = -rmax * L2E;
@@ -1132,7 +1146,7 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   };
 
   if (warp == THREADS / 32 && elect_one()) {
-    mbar_init(bar_qk, 1); mbar_init(bar_s, 2); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 2); mbar_init(bar_v, 1); mbar_init(bar_o, 2);   // two P V issuing threads
     mbar_init(bar_oe, THREADS / 32);
     for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(bar_pr + 8 * i, THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1164,21 +1178,49 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     umma_commit(bar_s);
   };
 
+  // O = P V, issued by TWO threads: the control warp takes the even 64-key chunks and accumulates them in TMEM columns
+  // [384, 448), the second issuing warp the odd chunks in [448, 512); the epilogue adds the two partial sums.
+  // A tcgen05.mma costs its issuing thread ~100 clk whatever its shape, so one thread issuing the whole P V (48 MMAs in
+  // the "wide" form, started late behind the loads) was the tail of every tile: the softmax warps waited ~3 K clk for
+  // bar_o after their last chunk (profiles/r02_v_attention_trace_persistent.log).  Each accumulator has ONE issuing
+  // thread and a fixed order, so the result is bit-reproducible (both threads feeding one accumulator was 2 % faster
+  // and not: the order in which the tensor pipe retires them varies from run to run).
+  const uint32_t idesc_o = make_idesc_bmn(D);
+  auto issue_pv = [&](int first, int it) {
+    const uint32_t o_col = tmem_base + 384 + 64 * first;
+    for (int i = first; i < nchunks; i += 2) {
+      const uint32_t v_hi = v_base + i * VBUF_BYTES, v_lo = v_hi + BOX_BYTES;
+      mbar_wait(bar_pr + 8 * i, it & 1);
+      tc_fence_after();
+      const int valid = min(KC, p.Lk - i * KC);
+      const int ksteps = (valid + 15) / 16;
+      const uint64_t bv_hi = make_desc_mn(v_hi), bv_lo = make_desc_mn(v_lo);
+      const uint32_t a0 = tmem_base + i * KC;       // P of keys [16k, 16k+16): hi at +16k, lo at +16k+8
+      for (int k = 0; k < ksteps; ++k) umma_ts(o_col, a0 + 16 * k + 8, bv_hi + 128 * k, idesc_o, (i != first || k) ? 1u : 0u);
+      for (int k = 0; k < ksteps; ++k) umma_ts(o_col, a0 + 16 * k, bv_lo + 128 * k, idesc_o, 1u);
+      for (int k = 0; k < ksteps; ++k) umma_ts(o_col, a0 + 16 * k, bv_hi + 128 * k, idesc_o, 1u);
+    }
+    umma_commit(bar_o);
+  };
+
   if (warp == THREADS / 32 + 1) {
-    // ================================================================== second S-issuing warp
+    // ================================================================== second issuing warp: half of S, odd P V chunks
     if (elect_one()) {
       for (int it = 0; it < n_it; ++it) {
         mbar_wait(bar_qk, it & 1);
         if (it > 0) mbar_wait(bar_o, (it - 1) & 1);     // the P V MMAs of the previous tile have consumed P (= the S columns)
         tc_fence_after();
         issue_s(1);
+        mbar_wait(bar_oe, it & 1);                      // O read out by the epilogue of the previous tile (phase 0: start-up)
+        mbar_wait(bar_v, it & 1);
+        tc_fence_after();
+        issue_pv(1, it);
       }
     }
     __syncwarp();
   } else if (warp == THREADS / 32) {
     // ================================================================== control warp: TMA + MMA issue
     if (elect_one()) {
-      const uint32_t idesc_o = make_idesc_bmn(D), idesc_w = make_idesc_bmn(2 * D);
       auto load_qk = [&](int it) {
         int b, h, q0;
         tile_of(it, b, h, q0);
@@ -1206,12 +1248,10 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (it > 0) mbar_wait(bar_o, (it - 1) & 1);
         tc_fence_after();
         issue_s(0);
-        mbar_wait(bar_s, it & 1);                       // Q / K shared memory is dead: prefetch the next tile's
-        if (it + 1 < n_it) load_qk(it + 1);
-        if (it > 0) {                                   // staging tile (in the V region) drained, O read out of TMEM
-          mbar_wait(bar_oe, (it - 1) & 1);
-          tc_fence_after();
-        }
+        // V first (the P V MMAs of chunk 0 need it ~2 K clk from now, the next tile's Q / K much later): its region
+        // doubles as the epilogue's staging tile, free once the previous tile's epilogue has drained it
+        mbar_wait(bar_oe, it & 1);                      // staging tile drained, O read out of TMEM (phase 0: start-up)
+        tc_fence_after();
         mbar_expect_tx(bar_v, (uint32_t)(pp.nfull * 2 * BOX_BYTES + 2 * pp.r16 * 128));
         for (int i = 0; i < pp.nfull; ++i) {
           const uint32_t v_hi = v_base + i * VBUF_BYTES;
@@ -1223,21 +1263,11 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tma_load_2d(v_hi, &tmVp, bar_v, p.v_col + h * D, krow + pp.nfull * KC);
           tma_load_2d(v_hi + BOX_BYTES, &tmVp, bar_v, p.v_kp + p.v_col + h * D, krow + pp.nfull * KC);
         }
+        mbar_wait(bar_s, it & 1);                       // Q / K shared memory is dead: prefetch the next tile's
+        if (it + 1 < n_it) load_qk(it + 1);
         mbar_wait(bar_v, it & 1);
-        for (int i = 0; i < nchunks; ++i) {
-          const uint32_t v_hi = v_base + i * VBUF_BYTES;
-          mbar_wait(bar_pr + 8 * i, it & 1);
-          tc_fence_after();
-          const int valid = min(KC, p.Lk - i * KC);
-          const int ksteps = (valid + 15) / 16;
-          const uint64_t bv_hi = make_desc_mn(v_hi);
-          const uint32_t a0 = tmem_base + i * KC;       // P of keys [16k, 16k+16): hi at +16k, lo at +16k+8
-          // one N = 128 MMA yields P_hi V_hi (columns 384..447) and P_hi V_lo (448..511): V_lo sits 8 KB after V_hi,
-          // the MN-atom stride of the descriptor; the epilogue adds the halves
-          for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + 384, a0 + 16 * k, bv_hi + 128 * k, idesc_w, (i | k) ? 1u : 0u);
-          for (int k = 0; k < ksteps; ++k) umma_ts(tmem_base + 384, a0 + 16 * k + 8, bv_hi + 128 * k, idesc_o, 1u);
-        }
-        umma_commit(bar_o);
+        tc_fence_after();
+        issue_pv(0, it);
       }
     }
     __syncwarp();
@@ -1247,12 +1277,16 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;
     const int nkeys = p.Lk;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_oe);                 // phase 0 of bar_oe ("nothing to drain"); the epilogue of tile t completes phase t + 1
+    const int tr_it = n_it > 2 ? 2 : n_it - 1;        // traced tile: the third one (steady state of the pipeline)
     for (int it = 0; it < n_it; ++it) {
       int b, h, q0;
       tile_of(it, b, h, q0);
+      if (it == tr_it) stamp(1);                      // (overwrites the set-up stamp: [1] -> [2] = waiting for S of this tile)
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
-      if (it == 0) stamp(2);
+      if (it == tr_it) stamp(2);
       // -------------------------------------------------------------- row max
       const int nchunk32 = (nkeys + 31) / 32;
       float mymax = -INFINITY;
@@ -1279,7 +1313,7 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float rmax = xmax[row];
 #pragma unroll
       for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
-      if (it == 0) stamp(3);
+      if (it == tr_it) stamp(3);
       // -------------------------------------------------------------- P = exp(S - max), in place in TMEM
       const float nb = -rmax * sl2;
       float rsum = 0.f;
@@ -1309,9 +1343,9 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pr + 8 * i);
-        if (it == 0 && i == 0) stamp(4);
+        if (it == tr_it && i == 0) stamp(4);
       }
-      if (it == 0) stamp(5);
+      if (it == tr_it) stamp(5);
       xsum[part * BM + row] = rsum;
       softmax_sync();                                   // (also: every warp has read xmax of this tile)
       float tot = 0.f;
@@ -1320,12 +1354,16 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const float inv = tot > 0.f ? 1.0f / tot : 0.f;
       mbar_wait(bar_o, it & 1);                         // every P V MMA of the tile is complete
       tc_fence_after();
-      if (it == 0) stamp(6);
+      if (it == tr_it) stamp(6);
       // -------------------------------------------------------------- normalise, store
       constexpr int OW = D / NPART;
       float o[OW], o1[OW];
       tmem_ld16(t_row + 384 + OW * part, o);
       tmem_ld16(t_row + 448 + OW * part, o1);
+      if (nchunks < 2) {                                // a single chunk: the odd accumulator was never written
+#pragma unroll
+        for (int u = 0; u < OW; ++u) o1[u] = 0.f;
+      }
 #pragma unroll
       for (int u = 0; u < OW; ++u) o[u] = (o[u] + o1[u]) * inv;
       const int grow = q0 + row;
@@ -1361,7 +1399,7 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_oe);
-      if (it == 0) stamp(7);
+      if (it == tr_it) stamp(7);
     }
   }
   tc_fence_before();

@@ -106,9 +106,10 @@ def trace_tma(B, H, N, n=512):
     torch.cuda.synchronize()
     _lib.call("ec_attention_tc_set_trace", None, 0)
     t = buf.cpu().double()
+    t = t[t[:, 9] > 0]                      # the persistent kernel runs one CTA per SM: only those rows are stamped
     d = t[:, 1:] - t[:, :-1]
-    names = ["setup+tmem_alloc", "Q/K TMA + S mma", "row max", "P chunk 0", "P chunks (rest)", "drain PV",
-             "epilogue", "final sync", "dealloc"]
+    names = ["(persistent: start .. traced tile)", "Q/K TMA + S mma | persistent: wait for S", "row max", "P chunk 0",
+             "P chunks (rest)", "drain PV", "epilogue", "final sync | persistent: remaining tiles", "dealloc"]
     tot = (t[:, 9] - t[:, 0])
     print(f"trace B{B} H{H} N{N}: CTA total mean {tot.mean():.0f} clk (min {tot.min():.0f} max {tot.max():.0f})")
     for i, nm in enumerate(names):
