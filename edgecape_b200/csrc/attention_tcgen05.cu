@@ -442,6 +442,11 @@ struct ParamsT {
   int dv;                           // head dim, 32 or 64 (P-in-TMEM kernel; boxes are 64 columns wide either way)
   const uint8_t* key_mask;          // [B, Lk], 1 = ignore key, or NULL   (P-in-TMEM kernel, one key block)
   const float* bias;                // [B, H, Lq, Lk] additive, or NULL   (P-in-TMEM kernel, one key block)
+  // structural bias computed in the kernel (BiasedMultiheadAttention, utils/bias_attn.py:188-191): bias[b,h,i,j] =
+  // W1[h,:] . relu(W0 . hops[:,b,i,j] + b0) + b1[h] -- instead of a [B,H,Lq,Lk] tensor written by a kernel in front
+  const float* hops;                // [n_hops, B, Lq, Lk] Markov hop matrices, or NULL
+  const float *hw0, *hb0, *hw1, *hb1;   // Linear(n_hops, hidden), Linear(hidden, H)
+  int n_hops, hidden;
 };
 
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
@@ -738,10 +743,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* u) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+        "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]),
+        "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]),
+        "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 constexpr int MAX_CHUNKS = 8;
 
 constexpr int THREADS_TS = THREADS + 64;   // 16 softmax warps, control warp, second S-issuing warp
 
+// HOP = true: the instance that evaluates the hop-bias MLP per logit (p.hops != NULL); kept apart so that its register
+// budget does not touch the plain instance.
+template <bool HOP>
 __global__ void __launch_bounds__(THREADS_TS, 1)
 attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, ParamsT p) {
@@ -892,9 +912,18 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float bmax0 = -INFINITY, bmax1 = -INFINITY, bsum0 = 0.f, bsum1 = 0.f;
     // key mask / additive bias (the decoder and encoder attentions of the head; always one key block): the
     // logits become x = s * scale + bias over the unmasked keys
-    const bool gen = p.key_mask != nullptr || p.bias != nullptr;
+    const bool gen = p.key_mask != nullptr || p.bias != nullptr || HOP;
     const float* bias_row = (p.bias && q0 + row < p.Lq)
                                 ? p.bias + (((long long)b * p.H + h) * p.Lq + (q0 + row)) * p.Lk : nullptr;
+    // hop-MLP weights of this head behind the mask words: W0 [hidden][n_hops], b0 [hidden], W1[h] [hidden], b1[h]
+    float* hopw = reinterpret_cast<float*>(mskw + 16);
+    if (HOP) {
+      const int nw0 = p.hidden * p.n_hops;
+      for (int i = tid; i < nw0 + 2 * p.hidden + 1; i += THREADS)
+        hopw[i] = i < nw0 ? p.hw0[i]
+                          : (i < nw0 + p.hidden ? p.hb0[i - nw0]
+                                                : (i < nw0 + 2 * p.hidden ? p.hw1[h * p.hidden + (i - nw0 - p.hidden)] : p.hb1[h]));
+    }                                                   // (published by the barrier of the mask-word block below)
     if (gen) {
       const int key = tid;                              // 16 warps x 32 lanes cover 512 keys >= LB
       const bool ignore = key >= p.Lk || (p.key_mask && p.key_mask[(long long)b * p.Lk + key] != 0);
@@ -902,6 +931,38 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (lane == 0) mskw[warp] = word;
       softmax_sync();
     }
+    // x = s * scale + hop-MLP bias for 32 keys of this lane's query row, -inf where masked; written back over S so
+    // that the exponential pass (other warps of the lane quarter) reads finished logits
+    auto hop_logits = [&](float* s32, int j) {
+      const uint32_t mw = mskw[j];
+      const int qi = q0 + row;
+      const long long plane = (long long)p.B * p.Lq * p.Lk;
+      const float* hp = p.hops + ((long long)b * p.Lq + (qi < p.Lq ? qi : 0)) * p.Lk + j * 32;
+      const int nh = p.n_hops, hd = p.hidden;
+      const float* w0 = hopw;
+      const float* b0 = hopw + hd * nh;
+      const float* w1 = b0 + hd;
+      const float b1 = w1[hd];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {                     // (fully unrolled: s32 stays in registers)
+        float x = -INFINITY;
+        if (!((mw >> u) & 1u)) {                         // warp-uniform (the mask word is shared by the lanes)
+          float hv[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) hv[t] = t < nh ? __ldg(hp + t * plane + u) : 0.f;
+          float acc = b1;
+          for (int c = 0; c < hd; ++c) {
+            float a = b0[c];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              if (t < nh) a = fmaf(w0[c * nh + t], hv[t], a);
+            acc = fmaf(w1[c], fmaxf(a, 0.f), acc);
+          }
+          x = fmaf(s32[u], p.scale, acc);
+        }
+        s32[u] = x;
+      }
+    };
     for (int blk = 0; blk < p.NB; ++blk) {
       const int key0 = blk * p.LB;
       const int nkeys = min(p.LB, p.Lk - key0);        // valid keys of this block
@@ -915,7 +976,12 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int j = part; j < nchunk32; j += NPART) {
         float s[32];
         tmem_ld32(t_row + j * 32, s);
-        if (gen && !bias_row && mskw[j] == 0u) {
+        if (HOP) {
+          hop_logits(s, j);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) mymax = fmaxf(mymax, s[u]);
+          tmem_st32(t_row + j * 32, reinterpret_cast<const uint32_t*>(s));
+        } else if (gen && !bias_row && mskw[j] == 0u) {
           // the key mask is one word per 32 keys, the same for every lane: a word with no masked key (all but the
           // tail of a padded keypoint list) takes the plain path -- the per-element tests doubled the cost of the
           // encoder self-attention (424 keys, 24 of them padding)
@@ -948,7 +1014,9 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       if (blk > 0) softmax_sync();                     // xmax of the previous block has been consumed
       xmax[part * BM + row] = mymax;
+      if (HOP) tc_fence_before();                   // the logits written back over S are read by other warps below
       softmax_sync();                                  // also: every warp is done reading S for the max pass
+      if (HOP) tc_fence_after();
       float rmax = xmax[row];
 #pragma unroll
       for (int q = 1; q < NPART; ++q) rmax = fmaxf(rmax, xmax[q * BM + row]);
@@ -962,7 +1030,15 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         float s[PW];
         const int kbase = i * KC + PW * part;
         tmem_ld16(t_row + kbase, s);
-        if (gen && !bias_row && ((mskw[kbase >> 5] >> (kbase & 31)) & 0xffffu) == 0u) {
+        if (HOP) {
+          // finished logits (scale and bias applied, masked keys -inf -> probability 0)
+          const float nbg = -rmax * 1.4426950408889634f;
+#pragma unroll
+          for (int u = 0; u < PW; ++u) {                 // (columns past the last 32-key word were never rewritten)
+            s[u] = (kbase + u < nkeys) ? ex2(fmaf(s[u], 1.4426950408889634f, nbg)) : 0.f;
+            rsum += s[u];
+          }
+        } else if (gen && !bias_row && ((mskw[kbase >> 5] >> (kbase & 31)) & 0xffffu) == 0u) {
           // no masked key among these 16 (warp-uniform): x = s * scale, p = exp2(x * log2 e - max * log2 e) in one FMA
           const float nbg = -rmax * 1.4426950408889634f;
 #pragma unroll
@@ -1411,6 +1487,11 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   stamp(9);
 }
 
+struct HopArm {   // armed by ec_attention_hop_bias_next, consumed by the next ec_attention_tc_split on this thread
+  const float *hops = nullptr, *w0 = nullptr, *b0 = nullptr, *w1 = nullptr, *b1 = nullptr;
+  int n_hops = 0, hidden = 0;
+};
+static thread_local HopArm g_hop;
 static int g_variant = 0;   // 0: persistent pipelined kernel where it applies, else P in TMEM + wide P V MMAs; 3: never the persistent kernel; 2: P in TMEM, three N = 64 MMAs per k-step; 1: P through shared memory
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
@@ -1471,7 +1552,12 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
       return EC_ERR_UNSUPPORTED;
     }
   }
-  const bool general = dv != 64 || key_mask || bias;   // needs the P-in-TMEM kernel, one key block
+  const atc::HopArm hop = atc::g_hop;                  // (consumed: applies to this call only)
+  atc::g_hop = atc::HopArm();
+  EC_REQUIRE(!hop.hops || !bias, "ec_attention_tc_split: an additive bias tensor and the fused hop-bias MLP exclude each other");
+  EC_REQUIRE(!hop.hops || (hop.n_hops <= 8 && hop.hidden * (hop.n_hops + 2) + 1 <= 112),
+             "ec_attention_tc_split: hop-bias MLP too large for the fused form (n_hops <= 8, hidden * (n_hops + 2) < 112)");
+  const bool general = dv != 64 || key_mask || bias || hop.hops;   // needs the P-in-TMEM kernel, one key block
   if (general && NB != 1) {
     set_error("ec_attention_tc_split: head dim 32 / key mask / bias need <= 448 keys (got %d)", Lk);
     return EC_ERR_UNSUPPORTED;
@@ -1497,7 +1583,8 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   if (rc) return rc;
   atc::ParamsT p{O, B, H, Lq, Lk, NB, LB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
                  q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n,
-                 (atc::g_variant != 2 && NB == 1 && LB <= 384) ? 1 : 0, dv, key_mask, bias};
+                 (atc::g_variant != 2 && NB == 1 && LB <= 384) ? 1 : 0, dv, key_mask, bias,
+                 hop.hops, hop.w0, hop.b0, hop.w1, hop.b1, hop.n_hops, hop.hidden};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
   // the persistent, pipelined kernel takes the plain head-dim-64 attentions whose Q + K + V tiles fit shared memory
   // together (the ViT blocks up to 368 tokens; variant 3 = force off for A/B measurements)
@@ -1530,14 +1617,28 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
     }
   }
   if (atc::g_variant != 1 || general) {
-    EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_ts_kernel,
-                                             atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024));
-    launch_pdl(atc::attention_tc_ts_kernel, grid, dim3(atc::THREADS_TS), (size_t)(kq + atc::MISC_BYTES + 1024),
-               (cudaStream_t)stream, tmQ, tmK, tmV, p);
+    const int ts_smem_max = atc::Q_BYTES + 2 * 7 * atc::BOX_BYTES + atc::MISC_BYTES + 1024;
+    if (hop.hops) {
+      EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_ts_kernel<true>, ts_smem_max));
+      launch_pdl(atc::attention_tc_ts_kernel<true>, grid, dim3(atc::THREADS_TS), (size_t)(kq + atc::MISC_BYTES + 1024),
+                 (cudaStream_t)stream, tmQ, tmK, tmV, p);
+    } else {
+      EC_CUDA((cudaError_t)ensure_dynamic_smem(atc::attention_tc_ts_kernel<false>, ts_smem_max));
+      launch_pdl(atc::attention_tc_ts_kernel<false>, grid, dim3(atc::THREADS_TS), (size_t)(kq + atc::MISC_BYTES + 1024),
+                 (cudaStream_t)stream, tmQ, tmK, tmV, p);
+    }
   } else {
     atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   }
   return check_launch("ec_attention_tc_split");
+}
+
+extern "C" int ec_attention_hop_bias_next(const float* hops, int n_hops, int hidden, const float* w0, const float* b0,
+                                          const float* w1, const float* b1) {
+  EC_REQUIRE(hops && w0 && b0 && w1 && b1 && n_hops > 0 && hidden > 0, "ec_attention_hop_bias_next: bad arguments");
+  atc::g_hop.hops = hops; atc::g_hop.n_hops = n_hops; atc::g_hop.hidden = hidden;
+  atc::g_hop.w0 = w0; atc::g_hop.b0 = b0; atc::g_hop.w1 = w1; atc::g_hop.b1 = b1;
+  return EC_OK;
 }
 
 extern "C" int ec_attention_tc_set_trace(void* buf, int n_ctas) {

@@ -386,7 +386,7 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, s
 
 
 def attention_split(q2, q_col, q_rows, k2, k_col, v2, v_col, k_rows, B, nheads, Lq, Lk, D, scale=None,
-                    key_mask=None, bias=None, out=None, split="only"):
+                    key_mask=None, bias=None, out=None, split="only", hop=None):
     """softmax(Q K^T * scale + bias, masked) V on split-fp16 operands (the split outputs of the projections):
     head h of Q is columns q_col + D*h of each half of q2, rows b*q_rows + i; K / V likewise with k_rows rows
     per batch element.  TMA-fed tcgen05 kernel with the probabilities in TMEM.  D in (32, 64)."""
@@ -414,6 +414,15 @@ def attention_split(q2, q_col, q_rows, k2, k_col, v2, v_col, k_rows, B, nheads, 
     if bias is not None:
         _chk(bias, "bias")
         assert bias.is_contiguous() and tuple(bias.shape) == (B, nheads, Lq, Lk)
+    if hop is not None:
+        # the structural bias is computed inside the kernel from the hop tensor and the 5 -> 12 -> H MLP
+        attn_adj, w0, b0, w1, b1 = hop
+        assert bias is None and attn_adj.is_contiguous() and tuple(attn_adj.shape[1:]) == (B, Lq, Lk)
+        for t_, n_ in ((attn_adj, "attn_adj"), (w0, "w0"), (b0, "b0"), (w1, "w1"), (b1, "b1")):
+            _chk(t_, n_)
+            assert t_.is_contiguous()
+        assert w1.shape[0] == nheads
+        _lib.call("ec_attention_hop_bias_next", _p(attn_adj), attn_adj.shape[0], w0.shape[0], _p(w0), _p(b0), _p(w1), _p(b1))
     _lib.call("ec_attention_tc_split", q2.data.data_ptr(), q2.rows, q2.Kp, q_col, q_rows, k2.data.data_ptr(), k2.rows,
               k2.Kp, k_col, v2.data.data_ptr(), v2.rows, v2.Kp, v_col, k_rows, _p(out), B, nheads, Lq, Lk, ldo, so_,
               float(scale), D, _p(key_mask), _p(bias), sp_ptr, C if sp is not None else 0, _stream())
@@ -426,13 +435,25 @@ def attention_split_ok(D, Lk, masked=False):
                 and Lk <= (768 if (D == 64 and not masked) else 448))
 
 
-def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only", key_mask=None, bias=None):
+# hop-bias MLP inside the attention kernel (ec_attention_hop_bias_next).  Built, tested -- and measured
+# SLOWER than the separate ec_hop_bias kernel + bias tensor: every (batch, head) CTA re-evaluates the shared 5 -> 12
+# hidden layer per logit, 8 x the arithmetic of the separate kernel (head graph alone 2.20 vs 2.04 ms,
+# profiles/r02_w_hop_fused_overlap.log).  Opt-in: EDGECAPE_HOP_FUSED=1.
+HOP_FUSED = os.environ.get("EDGECAPE_HOP_FUSED", "0") == "1"
+
+
+def hop_fused_ok(n_hops, hidden):
+    """Can the attention kernel evaluate the hop-bias MLP itself (ec_attention_hop_bias_next)?"""
+    return n_hops <= 8 and hidden * (n_hops + 2) + 1 <= 112
+
+
+def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only", key_mask=None, bias=None, hop=None):
     """Self-attention over a packed split-fp16 QKV operand (the split output of the QKV GEMM):
     qkv2 rows = B*N tokens, columns [q | k | v] of C = nheads*D each per half."""
     C = qkv2.K // 3
     assert qkv2.rows == B * N and qkv2.Kp == qkv2.K
     return attention_split(qkv2, 0, N, qkv2, C, qkv2, 2 * C, N, B, nheads, N, N, C // nheads, scale=scale,
-                           key_mask=key_mask, bias=bias, out=out, split=split)
+                           key_mask=key_mask, bias=bias, out=out, split=split, hop=hop)
 
 
 def gather_blocks(src, idx, out=None):

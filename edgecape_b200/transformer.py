@@ -77,12 +77,19 @@ def decoder_layer_forward(node, pk, nhead, kp, img_cat, kp_cat, key_mask_fixed, 
     kp2d = kp.view(B * K, d)
     # (i) self-attention over keypoints (+ structural bias), residual, norm1
     bias = None
-    if attn_adj is not None and "hop" in pk:
-        bias = ops.hop_bias(attn_adj, *pk["hop"])
+    use_hop = attn_adj is not None and "hop" in pk
     if _split_attention_ok(kp2d, pk["qkv_w"], d // nhead, K, masked=True):
         qkv2 = ops.linear_split(kp_split if kp_split is not None else kp2d, pk["qkv_w"], pk["qkv_b"])
-        a = ops.attention_packed_split(qkv2, B, K, nhead, key_mask=key_mask_fixed, bias=bias)
+        if use_hop and ops.HOP_FUSED and ops.hop_fused_ok(attn_adj.shape[0], pk["hop"][0].shape[0]):
+            # the structural bias (utils/bias_attn.py:188-191) is evaluated inside the attention kernel, per logit
+            a = ops.attention_packed_split(qkv2, B, K, nhead, key_mask=key_mask_fixed, hop=(attn_adj,) + tuple(pk["hop"]))
+        else:
+            if use_hop:
+                bias = ops.hop_bias(attn_adj, *pk["hop"])
+            a = ops.attention_packed_split(qkv2, B, K, nhead, key_mask=key_mask_fixed, bias=bias)
     else:
+        if use_hop:
+            bias = ops.hop_bias(attn_adj, *pk["hop"])
         qkv = ops.linear(kp2d, pk["qkv_w"], pk["qkv_b"]).view(B, K, 3 * d)
         a = ops.attention(qkv[:, :, 0:d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], nhead, key_mask=key_mask_fixed,
                           bias=bias).view(B * K, d)

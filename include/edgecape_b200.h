@@ -212,6 +212,16 @@ int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, in
  * ignore) and bias ([B, H, Lq, Lk], added to the scaled logits) need Lk <= 448.  Same output contract as
  * ec_attention_tc (O fp32 and / or split_out with split_kp == H * dv).  Every attention of the path goes
  * through this entry in tensor-core mode (models/.../encoder_decoder.py:461-483, 584-651; DINOv2 blocks). */
+/* Structural attention bias computed INSIDE the attention kernel (BiasedMultiheadAttention, utils/bias_attn.py:188-191;
+ * SURVEY K11): arms the NEXT ec_attention_tc_split call made by this host thread -- and only that one -- to add
+ *   bias[b,h,i,j] = W1[h,:] . relu(W0 . hops[:,b,i,j] + b0) + b1[h]
+ * to its scaled logits, from the Markov hop tensor hops [n_hops, B, Lq, Lk] (ec_edge_weights + ec_markov_powers) and the
+ * markov_structural_mlp weights W0 [hidden, n_hops], b0 [hidden], W1 [H, hidden], b1 [H]; that call must pass
+ * bias = NULL.  The row-max pass evaluates the MLP per logit and writes the finished logits back over S in TMEM, so
+ * the [B,H,Lq,Lk] tensor ec_hop_bias writes (and the attention kernel reads back, twice) never exists.
+ * Limits: n_hops <= 8, hidden * (n_hops + 2) < 112 (else use ec_hop_bias + the bias argument). */
+int ec_attention_hop_bias_next(const float* hops, int n_hops, int hidden, const float* w0, const float* b0,
+                               const float* w1, const float* b1);
 int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
                           const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
                           int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H,

@@ -245,9 +245,18 @@ def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv,
         _write_split(split_out, split_kp, o.reshape(B * Lq, H * D))
 
 
+_HOP_NEXT = []
+
+
+def ec_attention_hop_bias_next(hops, n_hops, hidden, w0, b0, w1, b1):
+    _HOP_NEXT.append((hops, n_hops, hidden, w0, b0, w1, b1))
+
+
 def ec_attention_tc_split(Q2, q_total, q_kp, q_col, q_rows, K2, k_total, k_kp, k_col, V2, v_total, v_kp, v_col, k_rows,
                           O, B, H, Lq, Lk, ldo, so, scale, D, key_mask, bias, split_out, split_kp, stream):
-    assert D in (32, 64) and Lk <= (768 if (D == 64 and not key_mask and not bias) else 448)
+    hop = _HOP_NEXT.pop() if _HOP_NEXT else None           # armed for this call only
+    assert not _HOP_NEXT and not (hop and bias)
+    assert D in (32, 64) and Lk <= (768 if (D == 64 and not key_mask and not bias and not hop) else 448)
 
     def grab(ptr, total, kp, col, rows_per_b, L):
         a = arr(ptr, (total, 2 * kp), dtype=np.float16).astype(np.float32)
@@ -262,6 +271,12 @@ def ec_attention_tc_split(Q2, q_total, q_kp, q_col, q_rows, K2, k_total, k_kp, k
     s = (ql @ kt(kh) + qh @ kt(kl) + qh @ kt(kh)) * np.float32(scale)
     if bias:
         s = s + arr(bias, (B, H, Lq, Lk))
+    if hop:
+        hops, n_hops, hidden, w0, b0, w1, b1 = hop
+        hp = T(arr(hops, (n_hops, B, Lq, Lk))).permute(1, 2, 3, 0)
+        y = F.linear(F.relu(F.linear(hp, T(arr(w0, (hidden, n_hops))), T(arr(b0, (hidden,))))),
+                     T(arr(w1, (H, hidden))), T(arr(b1, (H,))))
+        s = s + y.permute(0, 3, 1, 2).numpy()
     keep = np.ones((B, 1, 1, Lk), dtype=bool)
     if key_mask:
         keep = arr(key_mask, (B, Lk), dtype=np.uint8)[:, None, None, :] == 0

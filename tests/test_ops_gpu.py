@@ -662,3 +662,37 @@ def test_markov_powers_one_launch(B, K, H):
     for h in range(H + 1):
         want = torch.matrix_power(P.double(), h).float()
         assert (got[h] - want).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item()), h
+
+
+@pytest.mark.parametrize("B,K,masked", [(3, 100, True), (2, 17, False), (16, 100, True), (1, 200, True)])
+def test_hop_bias_fused_into_attention(B, K, masked):
+    """ec_attention_hop_bias_next: the structural bias MLP (utils/bias_attn.py:188-191) evaluated inside the attention
+    kernel equals the separate ec_hop_bias kernel + additive bias tensor, and the fp64 statement of the biased MHA."""
+    H, Dh, n_hops, hidden = 8, 32, 5, 12
+    g = torch.Generator().manual_seed(B * 100 + K)
+    qkv = torch.randn(B * K, 3 * H * Dh, generator=g)
+    P = torch.rand(B, K, K, generator=g)
+    P = P / P.sum(-1, keepdim=True)
+    hops = torch.stack([torch.matrix_power(P, h) for h in range(n_hops)])            # [n_hops, B, K, K]
+    w0, b0 = torch.randn(hidden, n_hops, generator=g), torch.randn(hidden, generator=g) * 0.1
+    w1, b1 = torch.randn(H, hidden, generator=g), torch.randn(H, generator=g) * 0.1
+    mask = torch.zeros(B, K, dtype=torch.uint8)
+    if masked:
+        mask[:, K - K // 4:] = 1
+    D_ = dev()
+    qkv2 = ops.split_f16(qkv.to(D_))
+    hp, km = hops.contiguous().to(D_), (mask.to(D_) if masked else None)
+    ws = [t.to(D_) for t in (w0, b0, w1, b1)]
+    fused = ops.attention_packed_split(qkv2, B, K, H, key_mask=km, hop=(hp, *ws), split="no").cpu()
+    bias = ops.hop_bias(hp, *ws)
+    sep = ops.attention_packed_split(qkv2, B, K, H, key_mask=km, bias=bias, split="no").cpu()
+    # fp64 statement
+    q, k, v = (qkv[:, i * H * Dh:(i + 1) * H * Dh].double().view(B, K, H, Dh).transpose(1, 2) for i in range(3))
+    bias64 = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(hops.permute(1, 2, 3, 0).double(), w0.double(),
+                                                                               b0.double())), w1.double(), b1.double())
+    s = (q @ k.transpose(-1, -2)) * Dh ** -0.5 + bias64.permute(0, 3, 1, 2)
+    s = s.masked_fill(mask.bool()[:, None, None, :], float("-inf"))
+    want = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, K, H * Dh).float()
+    scale = want.abs().max().item()
+    assert (fused - want).abs().max().item() < 2e-5 * scale
+    assert (fused - sep).abs().max().item() < 1e-5 * scale
