@@ -408,7 +408,7 @@ def run_ours(args):
                 with torch.cuda.stream(h.stream):
                     ops.pck_accumulate_(counters, h.out[0][-1], gt[i % NB], valid[i % NB], norm, thr)
             else:
-                out, _, _, _, _ = model.predict(d["img_s"], d["target_s"], d["target_weight_s"], d["img_q"], d["img_metas"])
+                out = model.predict(d["img_s"], d["target_s"], d["target_weight_s"], d["img_q"], d["img_metas"])[0]
                 ops.pck_accumulate_(counters, out[-1], gt[i % NB], valid[i % NB], norm, thr)
 
     def run_e2e(start, n):

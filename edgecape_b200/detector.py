@@ -278,10 +278,12 @@ class EdgeCape(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._graphs = {}           # captured graphs hold the old parameter addresses
+        ops.clear_weight_cache()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
         self._graphs = {}           # repacked weight copies (split fp16, fused QKV) change
+        ops.clear_weight_cache()
         return super().load_state_dict(*a, **k)
 
     @property
@@ -318,8 +320,8 @@ class EdgeCape(nn.Module):
             return self.forward_test_async(img_s, target_s, target_weight_s, img_q, target_q, target_weight_q,
                                            img_metas, **kwargs).result()
         batch_size, _, img_height, img_width = img_q.shape
-        output, initial_proposals, similarity_map, _, adj = self.predict(img_s, target_s, target_weight_s, img_q,
-                                                                         img_metas)
+        output, initial_proposals, similarity_map, _, _, adj = self.predict(img_s, target_s, target_weight_s, img_q,
+                                                                            img_metas)
         # decode on the device (heat-map space -> image space) and ONE synchronisation for every device->host read
         # (the reference does three .cpu() calls and decodes on the host)
         L, B, K, _ = output.shape
@@ -369,24 +371,47 @@ class EdgeCape(nn.Module):
         return self._submit(img_s, target_s, target_weight_s, img_q, img_metas, want_host=False)
 
     @torch.no_grad()
-    def predict(self, img_s, target_s, target_weight_s, img_q, img_metas=None, return_intermediates=False):
-        """(:165-184).  Accepts CPU or CUDA tensors; CPU inputs are uploaded (pinned or pageable).
+    def predict(self, img_s, target_s, target_weight_s, img_q, img_metas=None, random_mask=None,
+                return_intermediates=False):
+        """(:165-184).  Returns the reference's 6-tuple `(output, initial_proposals, similarity_map, mask_s,
+        reconstructed_keypoints, adj)` (`reconstructed_keypoints` is None at inference, `random_mask` is the
+        training-only masking argument and must be None); with `return_intermediates` a `(6-tuple, dict)` pair.
+        The tensors are the caller's to keep: in CUDA-graph mode they are copies of the engine's static buffers.
+        Accepts CPU or CUDA tensors; CPU inputs are uploaded (pinned or pageable).
         With `use_cuda_graph` (default; test_cfg['cuda_graph']=False disables) the whole device-side
         forward of one input signature is captured once into a CUDA graph and replayed, which removes
         the ~300 per-launch host costs of a step; intermediates are only available eagerly."""
+        if random_mask is not None:
+            raise NotImplementedError("random_mask is the training-time masked-supervision argument (inference path only)")
         dev = self.device
         _require_cuda(dev)
         skeleton_lst = [i["sample_skeleton"][0] for i in img_metas]
-        if self.use_cuda_graph and not return_intermediates and dev.type == "cuda":
-            return self._predict_graphed(img_s, target_s, target_weight_s, img_q, img_metas)
         up = lambda t: t.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+        def with_mask(res5):
+            """head 5-tuple -> the reference's 6-tuple: mask_s = prod of the visibility weights, the first one twice
+            (:175-177), shaped like target_weight_s[0]."""
+            tw = [up(t) for t in target_weight_s]
+            B, K = tw[0].shape[:2]
+            mask_s = ops.empty(B, K, device=dev)
+            ops.mask_accumulate_(tw[0].reshape(B, K), mask_s, first=True)
+            for t in tw[1:]:
+                ops.mask_accumulate_(t.reshape(B, K), mask_s, first=False)
+            out, prop, sim, recon, adj = res5
+            return out, prop, sim, mask_s.view(tuple(tw[0].shape)), recon, adj
+
+        if self.use_cuda_graph and not return_intermediates and dev.type == "cuda":
+            res5 = self._predict_graphed(img_s, target_s, target_weight_s, img_q, img_metas)
+            # the engine's static buffers are overwritten `pipeline_depth` submissions later: hand out copies
+            return with_mask(tuple(None if t is None else t.clone() for t in res5))
         edges, offsets = edges_to_csr(skeleton_lst, dev)
         groups, inv = self._support_groups(img_metas), None
         if groups is not None:
             img_s = [torch.stack([t[i] for i in groups[0]]) for t in img_s]
             inv = torch.as_tensor(groups[1], dtype=torch.int32).to(dev)
-        return self._forward_device(up(img_q), [up(t) for t in img_s], [up(t) for t in target_s],
-                                    [up(t) for t in target_weight_s], (edges, offsets), return_intermediates, inv=inv)
+        res = self._forward_device(up(img_q), [up(t) for t in img_s], [up(t) for t in target_s],
+                                   [up(t) for t in target_weight_s], (edges, offsets), return_intermediates, inv=inv)
+        return (with_mask(res[0]), res[1]) if return_intermediates else with_mask(res)
 
     def _forward_device(self, img_q, img_s, target_s, target_weight_s, skeleton, return_intermediates=False, inv=None):
         """Device-resident forward: every argument is a CUDA tensor, `skeleton` = (edges, offsets) CSR."""

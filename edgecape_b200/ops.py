@@ -140,6 +140,13 @@ def overflow_count(reset=False):
     return int(buf[0]), int(buf[1])
 
 
+def clear_weight_cache():
+    """Drop the cached split copies of weight matrices.  The cache is keyed on the parameter's identity, address and
+    `_version`, which an in-place update through `.data` does NOT bump: the detector calls this from
+    `load_state_dict` / `.to()` / `.cuda()`, and code that writes weights through `.data` must call it too."""
+    _SPLIT_WEIGHTS.clear()
+
+
 def split_weight(w, fmt=F16X2):
     """Cached split form of a weight matrix [N,K] (one-time repack per checkpoint: the power-of-two
     scale is picked from the tensor's absmax so that small weights stay out of the fp16 subnormals)."""

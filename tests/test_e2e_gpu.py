@@ -72,8 +72,18 @@ def test_detector_matches_reference_golden(name, tensor_cores, golden_dir, monke
     res = model(return_loss=False, **data)
     assert set(res) >= {"preds", "boxes", "image_paths", "bbox_ids", "points", "sample_image_file", "skeleton"}
     # (2) the same forward with intermediates exposed
-    out5, inter = model.predict(data["img_s"], data["target_s"], data["target_weight_s"], data["img_q"],
+    out6, inter = model.predict(data["img_s"], data["target_s"], data["target_weight_s"], data["img_q"],
                                 data["img_metas"], return_intermediates=True)
+    # the reference's predict() tuple (detectors/EdgeCape.py:165-184): output, initial_proposals, similarity_map, mask_s,
+    # reconstructed_keypoints, adj
+    assert len(out6) == 6 and out6[4] is None and tuple(out6[3].shape) == tuple(data["target_weight_s"][0].shape)
+    want_mask = data["target_weight_s"][0].clone()
+    for w in data["target_weight_s"]:
+        want_mask = want_mask * w
+    assert torch.equal(out6[3].cpu(), want_mask)
+    graphed = model.predict(data["img_s"], data["target_s"], data["target_weight_s"], data["img_q"], data["img_metas"])
+    assert len(graphed) == 6 and torch.equal(graphed[3].cpu(), want_mask)
+    assert torch.equal(graphed[0], out6[0])                     # CUDA-graph replay and eager launches: the same kernels
     feat_q, _ = model.extract_features([t.cuda() for t in data["img_s"]], data["img_q"].cuda())
     got = dict(inter)
     got.update(feature_q=feat_q, preds=res["preds"], boxes=res["boxes"], points=res["points"],
