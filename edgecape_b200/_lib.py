@@ -73,6 +73,11 @@ SIGNATURES = {
                               c_int, c_int, c_fp, c_int, c_f, c_int, c_fp]),
     "ec_overflow_count": (c_int, [c_fp, c_int]),
     "ec_gcn_fused": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
+    "ec_gcn_fused2": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
+    "ec_gcn_fused2_slice": (c_int, [c_int, c_int, c_int]),
+    "ec_gcn_fused2_set_trace": (c_int, [c_fp, c_int]),
+    "ec_gcn_fused2_set_debug": (c_int, [c_int]),
+    "ec_gcn_fused2_set_cta_limit": (c_int, [c_int]),
     "ec_support_weights": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_sine_pe_coords": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_f, c_f, c_fp]),
     "ec_proposal": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),

@@ -890,6 +890,19 @@ __global__ void split_f16f8_kernel(const float* __restrict__ X, uint8_t* __restr
     const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
     const float s = 0.00048828125f;                     // 2^-11
+    if (role == 2) {
+      // role 2: all three planes interleaved per 32 columns -- 128 bytes per (row, 32-column slice j) at byte 128 j:
+      // [hi16 x 32 (64 B) | hi8 x 32 | lo8 x 32] -- so that ONE TMA box with 128-byte rows (whole L2 lines) holds a 32-deep
+      // k-slice of the operand (gcn_fused2_tcgen05.cu; 64-byte box rows move at about half the rate)
+      uint8_t* sl = row + 128 * (k >> 5);
+      const int o = k & 31;
+      *reinterpret_cast<uint2*>(sl + 2 * o) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      *reinterpret_cast<uint32_t*>(sl + 64 + o) = e4m3x2(f01.x * s, f01.y * s) | (e4m3x2(f23.x * s, f23.y * s) << 16);
+      *reinterpret_cast<uint32_t*>(sl + 96 + o) =
+          e4m3x2(v[0] - f01.x, v[1] - f01.y) | (e4m3x2(v[2] - f23.x, v[3] - f23.y) << 16);
+      return;
+    }
     *reinterpret_cast<uint2*>(row + 2 * k) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     *reinterpret_cast<uint32_t*>(row + 2 * Kp + k) = e4m3x2(f01.x * s, f01.y * s) | (e4m3x2(f23.x * s, f23.y * s) << 16);
@@ -931,11 +944,14 @@ struct MapKeyHash {
 // halves view (bytes == false): dims {2 Kp halves, rows}, 64-half x box_rows boxes, 128B swizzle -- the hi16 | lo16 planes.
 // byte view (bytes == true): dims {4 Kp bytes, rows}, 64-byte x box_rows boxes, 64B swizzle -- the hi8 | lo8 planes of an
 // F16F8 operand, at byte columns 2 Kp and 3 Kp of the same rows.
-static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out, bool bytes) {
+// slice view (kind 2): dims {4 Kp bytes, rows}, 128-byte x box_rows boxes, 128B swizzle -- one 32-deep k-slice of an operand
+// whose planes are interleaved per 32 columns (ec_split_f16f8 role 2; gcn_fused2_tcgen05.cu streams its weights so).
+static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out, int kind) {
+  const bool bytes = kind != 0;
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   std::lock_guard<std::mutex> lock(mu);
-  MapKey key{ptr, rows, kp, bytes ? -box_rows : box_rows};
+  MapKey key{ptr, rows, kp, kind == 1 ? -box_rows : (kind == 2 ? box_rows + 100000 : box_rows)};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -948,12 +964,12 @@ static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, C
   }
   cuuint64_t dims[2] = {(cuuint64_t)(bytes ? 4 * kp : 2 * kp), (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(4 * kp)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(kind == 2 ? 2 * BK : BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %d kp %d)", (int)r, ptr, rows, kp);
@@ -1009,7 +1025,58 @@ static DevState* dev_state() {
 }
 
 int get_tensor_map(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {   // also used by other kernels
-  return get_tensor_map_any(ptr, rows, kp, box_rows, out, false);
+  return get_tensor_map_any(ptr, rows, kp, box_rows, out, 0);
+}
+int get_tensor_map_slice32(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {   // 128-byte slices, planes interleaved per 32
+  return get_tensor_map_any(ptr, rows, kp, box_rows, out, 2);
+}
+// plain fp32 matrix [rows, cols] (contiguous rows), box_rows x box_cols boxes; no swizzle (raw activations that a kernel
+// converts itself) or, with box_cols = 32, 128B swizzle (result tiles a kernel assembles for TMA stores)
+int get_tensor_map_f32(const void* ptr, long long rows, int cols, int box_rows, int box_cols, bool swizzle128, CUtensorMap* out) {
+  struct Key {
+    const void* ptr; long long rows; int cols, br, bc;
+    bool operator==(const Key& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && br == o.br && bc == o.bc; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      return std::hash<const void*>()(k.ptr) ^ (std::hash<long long>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.cols) * 7919u) ^
+             (std::hash<int>()(k.br) * 104729u) ^ (std::hash<int>()(k.bc) * 15485863u);
+    }
+  };
+  static std::mutex mu;
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key{ptr, rows, cols, box_rows, swizzle128 ? -box_cols : box_cols};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EC_OK;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return EC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4u};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d (ptr %p rows %lld cols %d box %d x %d)", (int)r, ptr, rows,
+              cols, box_rows, box_cols);
+    return EC_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return EC_OK;
+}
+int get_tensor_map_bytes(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out) {   // e4m3 planes of an F16F8 operand
+  return get_tensor_map_any(ptr, rows, kp, box_rows, out, 1);
 }
 
 }  // namespace tc
@@ -1072,7 +1139,7 @@ extern "C" int ec_split_f16f8(const float* X, void* out, int M, int K, int ldx, 
                               float scale, int role, void* stream) {
   EC_REQUIRE(X && out, "ec_split_f16f8: null pointer");
   EC_REQUIRE(Kp % tc::BK == 0 && Kp >= K && K > 0, "ec_split_f16f8: Kp must be a multiple of 64 and >= K");
-  EC_REQUIRE(role == 0 || role == 1, "ec_split_f16f8: role is 0 (A operand) or 1 (B operand)");
+  EC_REQUIRE(role >= 0 && role <= 2, "ec_split_f16f8: role is 0 (A operand), 1 (B operand) or 2 (B operand, planes interleaved per 32 columns)");
   EC_REQUIRE(aligned16(out), "ec_split_f16f8: the operand buffer must be 16-byte aligned");
   if (M == 0) return EC_OK;
   unsigned long long* ovf = overflow_counters();
@@ -1115,19 +1182,19 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
   tmA8 = tmA;
   tmB8 = tmB;
   if (f8) {
-    rc = tc::get_tensor_map_any(A2, M, Kp, tc::BM, &tmA8, true);
+    rc = tc::get_tensor_map_any(A2, M, Kp, tc::BM, &tmA8, 1);
     if (rc) return rc;
-    rc = tc::get_tensor_map_any(B2, N, Kp, mode == 256 ? 256 : 128, &tmB8, true);
+    rc = tc::get_tensor_map_any(B2, N, Kp, mode == 256 ? 256 : 128, &tmB8, 1);
     if (rc) return rc;
   }
   // split-only outputs leave through TMA stores (128-row x 64-column blocks in the layout of the consumer's A tiles)
   CUtensorMap tmO16 = tmA, tmO8 = tmA;
   const bool split_tma = split_out && !C && aligned16(split_out) && ec_tc_split_tma;
   if (split_tma) {
-    rc = tc::get_tensor_map_any(split_out, M, split_kp, tc::BM, &tmO16, false);
+    rc = tc::get_tensor_map_any(split_out, M, split_kp, tc::BM, &tmO16, 0);
     if (rc) return rc;
     if (split_fmt == EC_SPLIT_F16F8) {
-      rc = tc::get_tensor_map_any(split_out, M, split_kp, tc::BM, &tmO8, true);
+      rc = tc::get_tensor_map_any(split_out, M, split_kp, tc::BM, &tmO8, 1);
       if (rc) return rc;
     }
   }

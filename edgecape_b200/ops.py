@@ -98,6 +98,8 @@ TC_MIN_M, TC_MIN_N, TC_MIN_K = 64, 32, 32
 # units of tensor time).  EDGECAPE_GEMM_F8=0 keeps every linear on three fp16 products; with it on (default) the
 # large linears (M >= F8_MIN_M rows: the ViT's qkv / fc1 / fc2 at bench batch sizes) take the F16F8 kernel.
 F16X2, F16F8 = 0, 1
+F16F8_I32 = 2      # weights only: the F16F8 B-role planes interleaved per 32 columns, [hi16 x 32 | hi8 x 32 | lo8 x 32] (the fused
+                   # GCN streams its weights in 32-deep k-slices: one TMA box with 128-byte rows then holds a whole slice)
 GEMM_F8 = os.environ.get("EDGECAPE_GEMM_F8", "1") != "0"
 F8_MIN_M = 2048
 _SPLIT_WEIGHTS = {}
@@ -126,6 +128,9 @@ def split_f16(x, scale=1.0, out=None, fmt=F16X2, role=0):
     assert out.is_contiguous() and out.dtype == torch.float16 and out.numel() == M * 2 * Kp
     if fmt == F16X2:
         _lib.call("ec_split_f16", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), _stream())
+    elif fmt == F16F8_I32:
+        assert role == 1, "the interleaved e4m3 planes are a weight (B operand) format"
+        _lib.call("ec_split_f16f8", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), 2, _stream())
     else:
         _lib.call("ec_split_f16f8", _p(x), _p(out), M, K, ldx, seg, seg_stride, Kp, float(scale), int(role), _stream())
     return SplitOperand(out, M, K, Kp, float(scale), fmt)
@@ -580,25 +585,32 @@ def gcn_tc_ok(B, K):
     return TENSOR_CORES and B * K >= TC_MIN_M and ((K + 3) // 4 * 4) * 32 <= 48 * 1024
 
 
-# one-kernel GCN (csrc/gcn_fused_tcgen05.cu); EDGECAPE_GCN_FUSED=0 keeps the aggregate kernel + GEMM pair
-GCN_FUSED = os.environ.get("EDGECAPE_GCN_FUSED", "1") != "0"
+# one-kernel GCN: EDGECAPE_GCN_FUSED=2 (default) the project-first kernel (csrc/gcn_fused2_tcgen05.cu), =1 the
+# aggregate-first kernel (csrc/gcn_fused_tcgen05.cu), =0 the aggregate kernel + GEMM pair
+GCN_FUSED = int(os.environ.get("EDGECAPE_GCN_FUSED", "2"))
 
 
 def gcn_fused_ok(B, K, d, dff):
-    return bool(GCN_FUSED and gcn_tc_ok(B, K) and _lib.load().ec_gcn_fused_slice(K, d, dff) > 0)
+    """Does gcn() run as ONE kernel for this shape (either formulation)?"""
+    if not (GCN_FUSED and gcn_tc_ok(B, K)):
+        return False
+    lib = _lib.load()
+    return bool((GCN_FUSED >= 2 and lib.ec_gcn_fused2_slice(K, d, dff) > 0) or lib.ec_gcn_fused_slice(K, d, dff) > 0)
 
 
 def gcn(x, adj, Wp, out=None, split="no"):
     """x [B,K,d], adj [B,2,K,K] (plane 0 diagonal), packed weights -> relu(GCN) [B,K,dff].
-    Tensor-core mode: fused aggregate -> split-fp16 Z, then the tcgen05 GEMM with a ReLU epilogue; split="only"
-    returns the SplitOperand of the result (the A operand of the ffn2 GEMM that follows)."""
+    Tensor-core mode: one fused kernel (or, outside its shape gate, fused aggregate -> split-fp16 Z, then the tcgen05
+    GEMM with a ReLU epilogue); split="only" returns the SplitOperand of the result (the A operand of the ffn2 GEMM
+    that follows)."""
     _chk(x, "x"); _chk(adj, "adj"); _chk(Wp, "Wp")
     assert x.is_contiguous() and adj.is_contiguous()
     B, K, d = x.shape
     dff = Wp.shape[0]
     assert Wp.shape[1] == 2 * d + 4
     if gcn_fused_ok(B, K, d, dff):
-        w2 = split_weight(Wp)
+        v2 = GCN_FUSED >= 2 and _lib.load().ec_gcn_fused2_slice(K, d, dff) > 0
+        w2 = split_weight(Wp, F16F8_I32 if v2 else F16X2)
         so, so_ptr = None, None
         if split != "no":
             so = SplitOperand(empty(B * K, 2 * dff, dtype=torch.float16, device=x.device), B * K, dff, dff, 1.0)
@@ -608,8 +620,8 @@ def gcn(x, adj, Wp, out=None, split="no"):
         elif out is None:
             out = empty(B, K, dff, device=x.device)
         assert out is None or out.is_contiguous()
-        _lib.call("ec_gcn_fused", _p(x), _p(adj), _p(Wp), w2.data.data_ptr(), w2.Kp, float(w2.scale), _p(out), so_ptr,
-                  dff, B, K, d, dff, _stream())
+        _lib.call("ec_gcn_fused2" if v2 else "ec_gcn_fused", _p(x), _p(adj), _p(Wp), w2.data.data_ptr(), w2.Kp,
+                  float(w2.scale), _p(out), so_ptr, dff, B, K, d, dff, _stream())
         return so if split == "only" else ((out, so) if split == "also" else out)
     if gcn_tc_ok(B, K):
         Kp = _kp(2 * d + 4)

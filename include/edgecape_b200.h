@@ -92,7 +92,9 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
  *   B role (weights * s_w): hi8 = e4m3(hi16 * 2^-11), lo8 = e4m3(b * s_w - hi16)
  * -- so every product carries s_w and all three accumulate into ONE fp32 TMEM accumulator (out_scale = 1 / s_w undoes
  * it).  Measured error vs fp64 on ViT-B shapes: 1.1e-5 of max|C| (three fp16 products: 3.4e-6; bar 1e-3).
- * ec_split_f16f8 produces the rows from fp32 (role 0 = A, 1 = B; addressing as ec_split_f16).  ec_gemm_f16f8 has
+ * ec_split_f16f8 produces the rows from fp32 (role 0 = A, 1 = B, 2 = B with the three planes interleaved per 32
+ * columns -- [hi16 x 32 | hi8 x 32 | lo8 x 32], 128 bytes at byte column 128 (k / 32), the weight format of ec_gcn_fused2;
+ * addressing as ec_split_f16).  ec_gemm_f16f8 has
  * ec_gemm_f16x3's arguments plus split_fmt, the format of split_out (EC_SPLIT_F16X2 when an attention kernel or an
  * ec_gemm_f16x3 consumes it, EC_SPLIT_F16F8 when an ec_gemm_f16f8 does).
  * Range: e4m3 saturates at 448.  An activation beyond that only loses ITS cross terms (the element degrades to
@@ -296,6 +298,18 @@ int ec_gcn_fused_set_debug(int flags);               /* profiling experiments on
 int ec_gcn_fused_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] int64 clock stamps per CTA, NULL = off */
 int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* W2, int Kp, float w_scale,
                  float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);
+/* Second formulation of the same layer (csrc/gcn_fused2_tcgen05.cu, the default): project first,
+ *   T0 = X W0^T, T1 = X W1^T (running while X is still being read; cross terms of the fp32-grade split on e4m3
+ *   tensor cores), D2 = A1 T1 with A1 in tensor memory, Y = relu(a0 (T0 + b0) + D2 + rowsum(A1) b1);
+ * persistent CTAs over (sample, channel slice) items.  Same arguments as ec_gcn_fused except that W3 [dff, 4*Kp bytes]
+ * is the F16F8 B-role form of Wp * w_scale with its planes interleaved per 32 columns (ec_split_f16f8 with
+ * role 2): the weights stream in 32-deep k-slices.  Same shape gate (ec_gcn_fused2_slice). */
+int ec_gcn_fused2_slice(int K, int d, int dff);
+int ec_gcn_fused2_set_debug(int flags);               /* profiling experiments only: 1 = skip the A1 / X loads, 2 = skip the stores */
+int ec_gcn_fused2_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] int64 clock stamps of each CTA's first item */
+int ec_gcn_fused2_set_cta_limit(int ctas);            /* profiling: at most this many persistent CTAs (0 = one per SM) */
+int ec_gcn_fused2(const float* X, const float* adj, const float* Wp, const void* W3, int Kp, float w_scale,
+                  float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);
 
 /* ----------------------------------------------------------------------------- head ops
  * support-keypoint pooling weights (head.py:175-184, exact by linearity):

@@ -39,15 +39,18 @@ def run(B, K, d, dff, tc, iters=50, fused=False):
     flops = 2.0 * B * K * d * 2 * dff + 2.0 * B * K * K * d
     peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if __import__("os").path.exists("MEASURED_PEAKS.json") else 6650.0
     gbs = bytes_alg / us / 1e3
-    print(json.dumps(dict(op="gcn", B=B, K=K, d=d, dff=dff, path=("fused_tcgen05" if fused else "tcgen05") if tc else "simt_fp32", us=round(us, 2),
+    print(json.dumps(dict(op="gcn", B=B, K=K, d=d, dff=dff, path=({2: "fused2_project_first", 1: "fused_aggregate_first", 0: "tcgen05_pair"}[int(fused)]) if tc else "simt_fp32", us=round(us, 2),
                           algorithmic_MB=round(bytes_alg / 1e6, 2), achieved_GBs=round(gbs, 1), hbm_peak_GBs=peak,
                           frac_hbm=round(gbs / peak, 4), algorithmic_TFLOPs=round(flops / us / 1e6, 1))), flush=True)
 
 
 if __name__ == "__main__":
-    for B in (64, 16, 148, 2048):
-        run(B, 100, 256, 384, True, iters=50 if B < 1000 else 5, fused=True)
-    run(64, 100, 256, 768, True, fused=True)
+    for fused in (2, 1):
+        for B in (64, 16, 74, 148, 2048):
+            run(B, 100, 256, 384, True, iters=50 if B < 1000 else 5, fused=fused)
+        run(64, 100, 256, 768, True, fused=fused)
+    if "--fused-only" in sys.argv:
+        sys.exit(0)
     for tc in (True, False):
         run(64, 100, 256, 384, tc)
         run(64, 100, 256, 768, tc)

@@ -23,12 +23,13 @@ def _np(t):
     return t.detach().float().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
 
 
-@pytest.mark.parametrize("tensor_cores", [True, False, "fused_gcn"], ids=["split_f16_path", "fp32_path", "fused_gcn"])
+@pytest.mark.parametrize("tensor_cores", [True, False, "fused_gcn", "fused_gcn_aggregate_first"],
+                         ids=["split_f16_path", "fp32_path", "fused_gcn", "fused_gcn_aggregate_first"])
 @pytest.mark.parametrize("name", CASES)
 def test_host_orchestration_against_golden(name, tensor_cores, golden_dir, monkeypatch):
     from edgecape_b200 import ops
     cpu_emulator.install(monkeypatch)
-    monkeypatch.setattr(ops, "GCN_FUSED", tensor_cores == "fused_gcn")
+    monkeypatch.setattr(ops, "GCN_FUSED", {"fused_gcn": 2, "fused_gcn_aggregate_first": 1}.get(tensor_cores, 0))
     tensor_cores = bool(tensor_cores)
     monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))

@@ -189,9 +189,9 @@ def test_adjacency_from_edges_and_soft_normalize(K):
 
 
 @pytest.mark.parametrize("B,K,d,dff", [(4, 100, 256, 384), (2, 17, 256, 64), (2, 200, 256, 384), (3, 100, 256, 768)])
-@pytest.mark.parametrize("tensor_cores", [True, False, "fused"], ids=["tcgen05", "simt", "fused"])
+@pytest.mark.parametrize("tensor_cores", [True, False, "fused", "fused1"], ids=["tcgen05", "simt", "fused", "fused_aggregate_first"])
 def test_gcn_matches_oracle(B, K, d, dff, tensor_cores, monkeypatch):
-    fused = tensor_cores == "fused"
+    fused = {"fused": 2, "fused1": 1}.get(tensor_cores, 0)
     tensor_cores = bool(tensor_cores)
     monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     monkeypatch.setattr(ops, "GCN_FUSED", fused)
@@ -206,21 +206,30 @@ def test_gcn_matches_oracle(B, K, d, dff, tensor_cores, monkeypatch):
     want = O.gcn(x, adj, W, b)
     D = dev()
     Wp = ops.gcn_pack_weights(W.to(D), b.to(D))
+    tol = 5e-5 if fused == 2 else 2e-5      # the project-first kernel runs its cross terms on e4m3
     got = ops.gcn(x.to(D), adj.to(D).contiguous(), Wp)
-    close(got, want, what="gcn")
+    close(got, want, tol=tol, what="gcn")
     if tensor_cores and B * K >= ops.TC_MIN_M:
         so = ops.gcn(x.to(D), adj.to(D).contiguous(), Wp, split="only")
-        close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), what="gcn split")
+        close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), tol=tol,
+              what="gcn split")
 
 
 @pytest.mark.parametrize("B,K,d,dff", [(64, 100, 256, 384), (5, 97, 128, 192), (3, 112, 256, 768), (2, 64, 64, 64),
-                                      (3, 128, 256, 384), (4, 16, 256, 384), (70, 1, 64, 128)])
-def test_gcn_fused_kernel(B, K, d, dff, monkeypatch):
-    """One-kernel GCN (gcn_fused_tcgen05.cu) vs the fp64 oracle and vs the two-kernel tensor-core path: general
-    (non 0/1) diagonal plane, masked rows, fp32 and split outputs."""
+                                      (3, 128, 256, 384), (4, 16, 256, 384), (70, 1, 64, 128), (170, 100, 256, 384),
+                                      (101, 50, 256, 576)])
+@pytest.mark.parametrize("variant", [2, 1], ids=["project_first", "aggregate_first"])
+def test_gcn_fused_kernel(B, K, d, dff, variant, monkeypatch):
+    """One-kernel GCN (gcn_fused2_tcgen05.cu: project first, e4m3 cross terms, A1 in tensor memory, persistent CTAs --
+    the last two shapes give every CTA several items, with two and with three channel slices; gcn_fused_tcgen05.cu:
+    aggregate first) vs the fp64 oracle and vs the two-kernel tensor-core path: general (non 0/1) diagonal plane,
+    masked rows, fp32 and split outputs."""
     monkeypatch.setattr(ops, "TENSOR_CORES", True)
-    monkeypatch.setattr(ops, "GCN_FUSED", True)
+    monkeypatch.setattr(ops, "GCN_FUSED", variant)
     assert ops.gcn_fused_ok(B, K, d, dff)
+    lib = ops._lib.load()
+    assert (lib.ec_gcn_fused2_slice if variant == 2 else lib.ec_gcn_fused_slice)(K, d, dff) > 0
+    tol = 5e-5 if variant == 2 else 2e-5          # e4m3 cross terms: ~1e-5 of max|Y| (three fp16 products: 3e-6)
     x = rnd(B, K, d, seed=11)
     W, b = rnd(2 * dff, d, 1, seed=12, scale=d ** -0.5), 0.1 * rnd(2 * dff, seed=13)
     mask = torch.zeros(B, K, dtype=torch.bool)
@@ -234,16 +243,19 @@ def test_gcn_fused_kernel(B, K, d, dff, monkeypatch):
     D = dev()
     Wp = ops.gcn_pack_weights(W.to(D), b.to(D))
     xd, ad = x.to(D), adj.to(D).contiguous()
+    ops.gcn(xd, ad, Wp)                            # (the first call also splits the weights)
+    launches = ops._lib.launch_count()
     got = ops.gcn(xd, ad, Wp)
-    close(got, want, tol=2e-5, what="gcn fused")
+    assert ops._lib.launch_count() - launches == 1
+    close(got, want, tol=tol, what="gcn fused")
     y2, so = ops.gcn(xd, ad, Wp, split="also")
     assert torch.equal(y2, got)
-    close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), tol=2e-5,
+    close(so.data[:, :dff].float() + so.data[:, so.Kp:so.Kp + dff].float(), want.reshape(B * K, dff), tol=tol,
           what="gcn fused split")
     so2 = ops.gcn(xd, ad, Wp, split="only")
     assert torch.equal(so2.data, so.data)
-    monkeypatch.setattr(ops, "GCN_FUSED", False)
-    close(got, ops.gcn(xd, ad, Wp), tol=2e-5, what="fused vs two-kernel")
+    monkeypatch.setattr(ops, "GCN_FUSED", 0)
+    close(got, ops.gcn(xd, ad, Wp), tol=tol, what="fused vs two-kernel")
 
 
 def test_edge_weights_and_markov_match_oracle():
