@@ -340,8 +340,11 @@ def north_star_kernels(peaks):
     nbytes = B * K * d * 4 + B * K * K * 4 + B * K + (2 * dff * d + 2 * dff) * 4 + B * K * dff * 4
     out["gcn"] = {"shape": f"B={B} K={K} d={d} dff={dff}", "us": us, "bound": "hbm", "achieved": nbytes / us / 1e3,
                   "peak": hbm, "unit": "GB/s", "frac": nbytes / us / 1e3 / hbm,
-                  "kernel": "ec::gf::gcn_fused_kernel" if ops.gcn_fused_ok(B, K, d, dff) else "gcn_aggregate_split + gemm_f16x3",
-                  "note": "3.0 algorithmic GFLOP (9.0 issued as split fp16): the tensor time alone is ~6.5 us, the byte roofline 3.0 us"}
+                  "kernel": ("ec::gf2::gcn_fused2_kernel (project first, persistent)" if ops.GCN_FUSED >= 2 else "ec::gf::gcn_fused_kernel")
+                  if ops.gcn_fused_ok(B, K, d, dff) else "gcn_aggregate_split + gemm_f16x3",
+                  "note": "3.0 algorithmic GFLOP (6.4 issued: fp16 hi.hi + two e4m3 cross terms for X W^T, three fp16 products for "
+                          "A1 T1): the tensor time alone is ~4.5 us, the byte roofline 3.0 us; at batch 64 the launch is one wave, "
+                          "i.e. the critical path of one CTA"}
     Bi, H, N, D = 32, 12, 325, 64
     if ops.attention_split_ok(D, N):
         qkv2 = ops.split_f16(torch.randn(Bi * N, 3 * H * D, device=dev))
@@ -486,6 +489,9 @@ def run_ours(args):
                  "e2e_value_reference_batching": q_per_step_local(B, world) * args.steps / (ms_plain / 1e3),
                  "e2e_value_dedup_supports": q_per_step_local(B, world) * args.steps / (ms_dedup / 1e3),
                  "unit": "query images/s"}
+    # the two kernels the north-star names, alone at its shapes -- BEFORE the sustained pass: after ten seconds under the
+    # power cap the SM clock sits ~20 % lower for a while, and a kernel timed then is not comparable with the burst peaks
+    nsk = north_star_kernels(peaks) if (rank == 0 and world == 1) else None
     # does the headline survive the power cap?  >= --sustained-seconds of back-to-back resident steps with the clock
     # sampler running (a real evaluation is thousands of steps; the K-step headline region is ~0.1 s)
     sustained = None
@@ -564,8 +570,8 @@ def run_ours(args):
                             "frac_of_sustained_peak": ach / peak_sus, "frac_of_burst_peak": ach / peak_burst,
                             "launches_timed": roof["launches"], "kernel_ms_per_step": roof["ms"] / args.steps,
                             "all_gemm_ms_per_step": roof["all_ms"] / args.steps, "peak_source": peak_src}
-    if rank == 0 and world == 1:
-        line["north_star_kernels"] = north_star_kernels(peaks)
+    if nsk is not None:
+        line["north_star_kernels"] = nsk
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cb, _, want = cpu_reference_rate(args, 3, 1)

@@ -84,10 +84,23 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 // (a, b) -> fp16 pairs hi = rn(a, b), lo = rn((a, b) - hi), so that a ~= hi.x + lo.x to 2^-22.  Uses the packed
 // conversion (cvt.rn.f16x2.f32 -> F2FP.PACK_AB, an ALU op); the scalar __float2half_rn form compiles to F2F,
 // which shares the quarter-rate unit with MUFU and was the limiter of the softmax / split epilogues.
+// (a, b) minus the fp16 pair h2, in fp32 (exact): mixed-precision adds with a negated fp16 source -- ptxas folds each into
+// ONE FHADD (`FHADD d, -h.H0/H1, a`), where converting the halves and subtracting took two instructions per element.
+__device__ __forceinline__ void sub_h2(float a, float b, uint32_t h2, float& d0, float& d1) {
+  asm("{\n\t.reg .b16 l, h, nl, nh;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "neg.f16 nl, l;\n\t"
+      "neg.f16 nh, h;\n\t"
+      "add.rn.f32.f16 %0, nl, %3;\n\t"
+      "add.rn.f32.f16 %1, nh, %4;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "r"(h2), "f"(a), "f"(b));
+}
 __device__ __forceinline__ void split_pair(float a, float b, __half2& hi, __half2& lo) {
   hi = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(hi);
-  lo = __floats2half2_rn(a - f.x, b - f.y);
+  float d0, d1;
+  sub_h2(a, b, *reinterpret_cast<const uint32_t*>(&hi), d0, d1);
+  lo = __floats2half2_rn(d0, d1);
 }
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   __half2 h, l;
@@ -108,21 +121,27 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 __device__ __forceinline__ uint32_t e4m3x2(float a, float b) {
   return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);   // a in the low byte
 }
+__device__ __forceinline__ uint32_t e4m3x2_h2(uint32_t h2) {       // the same from a packed fp16 pair (one instruction)
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+  return r;
+}
 // four consecutive elements (column c, a multiple of 4) of an A-role row; `row` = the row's first byte
 __device__ __forceinline__ void store_split4(uint8_t* row, int kp, int c, float v0, float v1, float v2, float v3,
                                              int fmt, uint32_t& flags) {
-  __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-  *reinterpret_cast<uint2*>(row + 2 * c) =
-      make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+  const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+  float d0, d1, d2, d3;                                    // the low parts v - hi16 (exact)
+  sub_h2(v0, v1, u01, d0, d1);
+  sub_h2(v2, v3, u23, d2, d3);
+  *reinterpret_cast<uint2*>(row + 2 * c) = make_uint2(u01, u23);
   if (fmt == EC_SPLIT_F16X2) {
-    __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+    const __half2 l01 = __floats2half2_rn(d0, d1), l23 = __floats2half2_rn(d2, d3);
     *reinterpret_cast<uint2*>(row + 2 * kp + 2 * c) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   } else {
-    *reinterpret_cast<uint32_t*>(row + 2 * kp + c) = e4m3x2(f01.x, f01.y) | (e4m3x2(f23.x, f23.y) << 16);
-    *reinterpret_cast<uint32_t*>(row + 3 * kp + c) =
-        e4m3x2((v0 - f01.x) * 2048.f, (v1 - f01.y) * 2048.f) | (e4m3x2((v2 - f23.x) * 2048.f, (v3 - f23.y) * 2048.f) << 16);
+    *reinterpret_cast<uint32_t*>(row + 2 * kp + c) = e4m3x2_h2(u01) | (e4m3x2_h2(u23) << 16);
+    *reinterpret_cast<uint32_t*>(row + 3 * kp + c) = e4m3x2(d0 * 2048.f, d1 * 2048.f) | (e4m3x2(d2 * 2048.f, d3 * 2048.f) << 16);
     const float m = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
     flags |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
   }
@@ -131,30 +150,30 @@ __device__ __forceinline__ void store_split4(uint8_t* row, int kp, int c, float 
 // stores -- with four lanes per row every 32-byte sector of the row is written whole by one instruction
 __device__ __forceinline__ void store_split8(uint8_t* row, int kp, int c, const float* v, int fmt, uint32_t& flags) {
   uint32_t h[4];
-  float2 f[4];
+  float dl[8];                                             // the low parts v - hi16 (exact)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    f[i] = __half22float2(hh);
+    sub_h2(v[2 * i], v[2 * i + 1], h[i], dl[2 * i], dl[2 * i + 1]);
   }
   *reinterpret_cast<uint4*>(row + 2 * c) = make_uint4(h[0], h[1], h[2], h[3]);
   if (fmt == EC_SPLIT_F16X2) {
     uint32_t l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const __half2 ll = __floats2half2_rn(v[2 * i] - f[i].x, v[2 * i + 1] - f[i].y);
+      const __half2 ll = __floats2half2_rn(dl[2 * i], dl[2 * i + 1]);
       l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     *reinterpret_cast<uint4*>(row + 2 * kp + 2 * c) = make_uint4(l[0], l[1], l[2], l[3]);
   } else {
     *reinterpret_cast<uint2*>(row + 2 * kp + c) =
-        make_uint2(e4m3x2(f[0].x, f[0].y) | (e4m3x2(f[1].x, f[1].y) << 16), e4m3x2(f[2].x, f[2].y) | (e4m3x2(f[3].x, f[3].y) << 16));
+        make_uint2(e4m3x2_h2(h[0]) | (e4m3x2_h2(h[1]) << 16), e4m3x2_h2(h[2]) | (e4m3x2_h2(h[3]) << 16));
     uint32_t l8[4];
     float m = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      l8[i] = e4m3x2((v[2 * i] - f[i].x) * 2048.f, (v[2 * i + 1] - f[i].y) * 2048.f);
+      l8[i] = e4m3x2(dl[2 * i] * 2048.f, dl[2 * i + 1] * 2048.f);
       m = fmaxf(m, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));
     }
     *reinterpret_cast<uint2*>(row + 3 * kp + c) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));

@@ -74,6 +74,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
@@ -163,7 +168,7 @@ __device__ __forceinline__ uint32_t swz64(int row, int c) { return (uint32_t)(ro
 struct Params {
   const float* X;      // [B, K, d]
   const float* adj;    // [B, 2, K, K], plane 0 diagonal
-  const float* Wp;     // packed fp32 weights [dff, 2d + 4]: the two bias columns are read from here
+  const float* bias2;  // [2][dff] fp32: b0 then b1 (the bias columns of the packed weights, contiguous)
   float* Y;            // [B, K, dff] or NULL
   __half* split_out;   // [B*K, 2*split_kp] = [hi | lo] of Y, or NULL
   int split_kp;
@@ -179,7 +184,7 @@ struct Params {
 
 // barrier indices (8 bytes each)
 constexpr int WRING = 4;                 // W ring: four slices of 32 k (see the TMA producer)
-enum { W_FULL = 0, W_EMPTY = 4, B_XRAW = 8, B_XRD = 12, B_XF = 16, B_T1 = 20, B_T1S = 21, B_ACC = 22, B_XFREE = 23, B_XRET = 24,
+enum { W_FULL = 0, W_EMPTY = 4, B_XRAW = 8, B_XRD = 12, B_XF = 16, B_T1 = 20, B_T1S = 21, B_ACC = 22, B_OFREE = 23, B_XRET = 24,
        B_A1RAW = 25, B_BIAS = 26, NUM_BARS = 32 };
 
 struct Layout {
@@ -189,10 +194,11 @@ __host__ __device__ inline Layout make_layout(int k16, int d, int NS) {
   Layout L;
   L.blk = (uint32_t)k16 * 256u;                                   // one X block: hi16 (k16 x 128 B) | hi8 | lo8 (k16 x 64 B each)
   L.x_bytes = (uint32_t)(d / 64) * L.blk;
-  // ... the region later holds the T1 tiles (NS <= d: they fit) and then the output tile (4 NS k16 bytes, likewise)
+  // ... the region later holds A1 (raw) and the T1 tiles (NS <= d: they fit); the output tiles (4 NS k16 bytes) are built in
+  // the W ring
   L.wst = (uint32_t)NS * 128u;                                    // one W slice (32 k): NS rows of [hi16 64 B | hi8 32 B | lo8 32 B]
-  // + barriers / TMEM slot (512 B) + a0 [2][128] floats + the bias columns of the slice, [NS <= 256][b0 b1 0 0] floats
-  L.total = L.x_bytes + WRING * L.wst + 512u + 2u * 128u * 4u + 256u * 16u;
+  // + barriers / TMEM slot (512 B) + a0 [2][128] floats + the biases of the slice, b0 [256] and b1 [256] floats
+  L.total = L.x_bytes + WRING * L.wst + 512u + 2u * 128u * 4u + 2u * 256u * 4u;
   return L;
 }
 
@@ -221,22 +227,6 @@ __device__ __forceinline__ float lds32f(uint32_t a) {
   return v;
 }
 
-// fp32 pair (a, b) minus the fp16 pair packed in h2, as fp32: mixed-precision subtract (FHADD), one instruction per
-// element instead of a conversion and a subtraction.  Returns (hi.x - a, hi.y - b), i.e. MINUS the low parts.
-__device__ __forceinline__ void neg_lo_pair(uint32_t h2, float a, float b, float& d0, float& d1) {
-  asm("{\n\t.reg .b16 l, h;\n\t"
-      "mov.b32 {l, h}, %2;\n\t"
-      "sub.rn.f32.f16 %0, l, %3;\n\t"
-      "sub.rn.f32.f16 %1, h, %4;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "r"(h2), "f"(a), "f"(b));
-}
-__device__ __forceinline__ uint32_t e4m3x2_from_h2(uint32_t h2) {          // two fp16 -> two e4m3 (low 16 bits)
-  uint16_t r;
-  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
-  return r;
-}
-
 // eight channels (chunk xc of the block) of row r -> hi16 (128B swizzle) | hi8 | lo8 (64B swizzle) tiles of the block.
 // A role of the F16F8 split (common.cuh): hi8 = e4m3(hi16), lo8 = e4m3((x - hi16) 2^11); the fill is bound by the issue
 // slots of this conversion (~830 clk per block with every scheduler busy), hence the mixed-precision forms.
@@ -252,11 +242,11 @@ __device__ __forceinline__ void conv_x_row(uint32_t blk, uint32_t TS, int r, int
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    float n0, n1, n2, n3;
-    neg_lo_pair(h[2 * i], f[4 * i], f[4 * i + 1], n0, n1);
-    neg_lo_pair(h[2 * i + 1], f[4 * i + 2], f[4 * i + 3], n2, n3);
-    h8[i] = e4m3x2_from_h2(h[2 * i]) | (e4m3x2_from_h2(h[2 * i + 1]) << 16);
-    l8[i] = e4m3x2(n0 * -2048.f, n1 * -2048.f) | (e4m3x2(n2 * -2048.f, n3 * -2048.f) << 16);
+    float d0, d1, d2, d3;                                           // the low parts x - hi16 (exact; one FHADD each)
+    sub_h2(f[4 * i], f[4 * i + 1], h[2 * i], d0, d1);
+    sub_h2(f[4 * i + 2], f[4 * i + 3], h[2 * i + 1], d2, d3);
+    h8[i] = e4m3x2_h2(h[2 * i]) | (e4m3x2_h2(h[2 * i + 1]) << 16);
+    l8[i] = e4m3x2(d0 * 2048.f, d1 * 2048.f) | (e4m3x2(d2 * 2048.f, d3 * 2048.f) << 16);
   }
   const float m = fmaxf(__low2float(m2), __high2float(m2));      // (inf when a value is beyond the fp16 range)
   ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
@@ -268,8 +258,7 @@ __device__ __forceinline__ void conv_x_row(uint32_t blk, uint32_t TS, int r, int
 
 __global__ void __launch_bounds__(THREADS, 1)
 gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmS,
-                  const __grid_constant__ CUtensorMap tmB, Params p) {
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmS, Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -280,7 +269,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const uint32_t xb = base, w0 = xb + L.x_bytes, misc = w0 + WRING * L.wst;
   auto bar = [&](int i) { return misc + 8u * i; };
   const uint32_t tmem_slot = misc + 8u * NUM_BARS;
-  const uint32_t a0s_u = misc + 512u, bias_u = a0s_u + 1024u;        // a0 [2][128] floats; [NS][b0 b1 0 0] floats
+  const uint32_t a0s_u = misc + 512u, bias_u = a0s_u + 1024u;        // a0 [2][128] floats; b0 [256], b1 [256] floats
   // TMEM columns
   const uint32_t T0C = 0, T1C = (uint32_t)NS, A1H = 2u * NS, A1L = 2u * NS + 64u;
   const bool early = nsg <= ng - 1;       // the T1 tiles fit the X blocks that are dead before the last T0 step retires
@@ -298,7 +287,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     mbar_init(bar(B_T1), 1);
     mbar_init(bar(B_T1S), WORKERS / 32);
     mbar_init(bar(B_ACC), 1);
-    mbar_init(bar(B_XFREE), 1);
+    mbar_init(bar(B_OFREE), 1);
     mbar_init(bar(B_XRET), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -345,10 +334,11 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       ++gs;
     };
     auto x_loads = [&](int it, int b, int n0) {
-      if (it > 0) mbar_wait(bar(B_XFREE), (uint32_t)(it - 1) & 1u);   // the previous output tile has left the region
-      // bias columns of the slice: columns [2d, 2d + 4) of rows [n0, n0 + NS) of the packed fp32 weights
-      mbar_expect_tx(bar(B_BIAS), (uint32_t)NS * 16u);
-      tma_load_2d(bias_u, &tmB, bar(B_BIAS), 2 * d, n0);
+      if (it > 0) mbar_wait(bar(B_ACC), (uint32_t)(it - 1) & 1u);     // GEMM B of the previous item has retired: the region is dead
+      // biases of the slice: b0[n0 .. n0 + NS) and b1[n0 .. n0 + NS), two bulk copies
+      mbar_expect_tx(bar(B_BIAS), (uint32_t)NS * 8u);
+      bulk_load(bias_u, p.bias2 + n0, (uint32_t)NS * 4u, bar(B_BIAS));
+      bulk_load(bias_u + 1024u, p.bias2 + p.dff + n0, (uint32_t)NS * 4u, bar(B_BIAS));
       for (int g = 0; g < ng; ++g) {
         if (p.dbg & 1) { mbar_arrive(bar(B_XRAW + g)); continue; }
         mbar_expect_tx(bar(B_XRAW + g), (uint32_t)K * 256u);
@@ -376,8 +366,11 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       for (int item = cta; item < items; item += gridDim.x, ++it) {
         const int n0 = (item % nslice) * NS, b = item / nslice;
         if (it > 0) {
-          for (int s = 0; s < WRING; ++s) w_step(s, n0);
+          // the next item's X is requested as soon as the region is dead -- while the workers are still in the previous
+          // epilogue; the W ring holds that epilogue's output tile until its stores have read it
           x_loads(it, b, n0);
+          mbar_wait(bar(B_OFREE), (uint32_t)(it - 1) & 1u);
+          for (int s = 0; s < WRING; ++s) w_step(s, n0);
         }
         for (int s = WRING; s < s_a1; ++s) w_step(s, n0);
         if (p.a1_tma) {
@@ -388,9 +381,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             mbar_arrive(bar(B_A1RAW));
           } else {
             mbar_expect_tx(bar(B_A1RAW), (uint32_t)(K * K) * 4u);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(xb), "l"(p.adj + ((long long)b * 2 + 1) * K * K), "r"((uint32_t)(K * K) * 4u), "r"(bar(B_A1RAW))
-                         : "memory");
+            bulk_load(xb, p.adj + ((long long)b * 2 + 1) * K * K, (uint32_t)(K * K) * 4u, bar(B_A1RAW));
           }
         }
         for (int s = s_a1; s < 4 * ng; ++s) w_step(s, n0);
@@ -475,10 +466,12 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int col0 = part * cw + sc * 16;
         uint32_t u0[16], u1[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 bb = lds64f(bias_u + (uint32_t)(col0 + j) * 16u);     // broadcast read
-          u0[j] = __float_as_uint(bb.x * p.w_scale);
-          u1[j] = __float_as_uint(bb.y * p.w_scale);
+        for (int j = 0; j < 4; ++j) {                                         // broadcast reads
+          const float4 q0 = lds128f(bias_u + (uint32_t)(col0 + 4 * j) * 4u), q1 = lds128f(bias_u + 1024u + (uint32_t)(col0 + 4 * j) * 4u);
+          u0[4 * j] = __float_as_uint(q0.x * p.w_scale); u0[4 * j + 1] = __float_as_uint(q0.y * p.w_scale);
+          u0[4 * j + 2] = __float_as_uint(q0.z * p.w_scale); u0[4 * j + 3] = __float_as_uint(q0.w * p.w_scale);
+          u1[4 * j] = __float_as_uint(q1.x * p.w_scale); u1[4 * j + 1] = __float_as_uint(q1.y * p.w_scale);
+          u1[4 * j + 2] = __float_as_uint(q1.z * p.w_scale); u1[4 * j + 3] = __float_as_uint(q1.w * p.w_scale);
         }
         tmem_st16_nowait(t_row + T0C + (uint32_t)col0, u0);
         tmem_st16_nowait(t_row + T1C + (uint32_t)col0, u1);
@@ -492,14 +485,19 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const uint32_t blk = xb + (uint32_t)g * L.blk;
         mbar_wait(bar(B_XRAW + g), par);
         if (it == 0 && tid == 0 && g == 0) stamp(19);
+        // (the eight lanes of a row read 32 B each at a pitch of 32 B: lanes 4..7 take their upper 16 bytes first, so
+        // that each 128-bit load of a quarter-warp covers all 32 banks once)
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;   // rows >= K: zero
+        const uint32_t sw = (uint32_t)(xc >> 2) * 16u;
         if (xr0 < K) {
-          v0 = lds128f(blk + xr0 * 256 + xc * 32);
-          v1 = lds128f(blk + xr0 * 256 + xc * 32 + 16);
+          const float4 t0 = lds128f(blk + xr0 * 256 + xc * 32 + sw), t1 = lds128f(blk + xr0 * 256 + xc * 32 + (sw ^ 16u));
+          v0 = sw ? t1 : t0;
+          v1 = sw ? t0 : t1;
         }
         if (xr0 + 64 < K) {
-          v2 = lds128f(blk + (xr0 + 64) * 256 + xc * 32);
-          v3 = lds128f(blk + (xr0 + 64) * 256 + xc * 32 + 16);
+          const float4 t0 = lds128f(blk + (xr0 + 64) * 256 + xc * 32 + sw), t1 = lds128f(blk + (xr0 + 64) * 256 + xc * 32 + (sw ^ 16u));
+          v2 = sw ? t1 : t0;
+          v3 = sw ? t0 : t1;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");   // every worker holds its part of the block
         if (it == 0 && tid == 0 && g == 0) stamp(20);
@@ -599,61 +597,65 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       for (int pass = 0; pass < 2; ++pass) {                         // pass 0: fp32 rows of Y, pass 1: split rows
         if (pass == 0 ? p.Y == nullptr : p.split_out == nullptr) continue;
         if (pass == 1 && p.Y) {                                      // (both outputs: the tile region is used twice)
-          if (tid == 0) bulk_wait_read();
+          if (warp == 0 && elect_one()) bulk_wait_read();
           asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
         }
+        // 64 columns per round (16 per part): each round completes two fp32 tiles / one hi and one lo tile, whose stores go
+        // out while the next round is computed -- only the last round's stores are exposed at the end of the kernel
 #pragma unroll 1
         for (int sc = 0; sc < nsub; ++sc) {
-          const int col0 = part * cw + sc * 16;
+          // (requesting the next round's accumulators before the barrier keeps 32 more registers live across it: the
+          // spills that caused turned a 3.3 K clk epilogue into 9 K -- shared memory leaves almost no L1 for local memory)
+          const int col0 = sc * 64 + part * 16;
           float t0[16], d2[16];
           tmem_ld16_nowait(t_row + T0C + (uint32_t)col0, t0);
           tmem_ld16_nowait(t_row + T1C + (uint32_t)col0, d2);
           tmem_ld_wait();
-          if (row >= K) continue;
-          float y[16];
+          if (row < K) {
+            float y[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = fmaxf(fmaf(t0[j], sa, d2[j]), 0.f);
-          if (pass == 0) {
-            const uint32_t tile = xb + (uint32_t)(col0 >> 5) * TS;   // 32-column group
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128(tile + swz128(row, ((col0 & 31) >> 2) + j), __float_as_uint(y[4 * j]), __float_as_uint(y[4 * j + 1]),
-                     __float_as_uint(y[4 * j + 2]), __float_as_uint(y[4 * j + 3]));
-          } else {
-            uint32_t h[8], l[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) split_pair(y[2 * j], y[2 * j + 1], h[j], l[j]);
-            const uint32_t tile = xb + (uint32_t)(col0 >> 6) * TS;   // 64-column group: hi tiles [0, nsg), lo tiles [nsg, 2 nsg)
-            const uint32_t o0 = tile + swz128(row, (col0 & 63) >> 3), o1 = tile + swz128(row, ((col0 & 63) >> 3) + 1);
-            sts128(o0, h[0], h[1], h[2], h[3]);
-            sts128(o1, h[4], h[5], h[6], h[7]);
-            sts128(o0 + (uint32_t)nsg * TS, l[0], l[1], l[2], l[3]);
-            sts128(o1 + (uint32_t)nsg * TS, l[4], l[5], l[6], l[7]);
-          }
-        }
-        proxy_fence();                                               // generic-proxy writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");   // the tile is complete
-        if (warp == 0 && elect_one()) {
-          if (!(p.dbg & 2)) {
+            for (int j = 0; j < 16; ++j) y[j] = fmaxf(fmaf(t0[j], sa, d2[j]), 0.f);
             if (pass == 0) {
-              for (int g = 0; g < NS / 32; ++g) tma_store_2d(&tmY, xb + (uint32_t)g * TS, n0 + 32 * g, b * K);
+              const uint32_t tile = w0 + (uint32_t)(col0 >> 5) * TS;   // 32-column group
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(tile + swz128(row, ((col0 & 31) >> 2) + j), __float_as_uint(y[4 * j]), __float_as_uint(y[4 * j + 1]),
+                       __float_as_uint(y[4 * j + 2]), __float_as_uint(y[4 * j + 3]));
             } else {
-              for (int g = 0; g < nsg; ++g) {
-                tma_store_2d(&tmS, xb + (uint32_t)g * TS, n0 + 64 * g, b * K);
-                tma_store_2d(&tmS, xb + (uint32_t)(nsg + g) * TS, p.split_kp + n0 + 64 * g, b * K);
-              }
+              uint32_t h[8], l[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) split_pair(y[2 * j], y[2 * j + 1], h[j], l[j]);
+              const uint32_t tile = w0 + (uint32_t)sc * TS;            // 64-column group: hi tiles [0, nsg), lo tiles [nsg, 2 nsg)
+              const uint32_t o0 = tile + swz128(row, part * 2), o1 = tile + swz128(row, part * 2 + 1);
+              sts128(o0, h[0], h[1], h[2], h[3]);
+              sts128(o1, h[4], h[5], h[6], h[7]);
+              sts128(o0 + (uint32_t)nsg * TS, l[0], l[1], l[2], l[3]);
+              sts128(o1 + (uint32_t)nsg * TS, l[4], l[5], l[6], l[7]);
             }
           }
-          bulk_commit();
+          proxy_fence();                                             // generic-proxy writes -> visible to the TMA engine
+          asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); // the round's tiles are complete
+          if (warp == 0 && elect_one()) {
+            if (!(p.dbg & 2)) {
+              if (pass == 0) {
+                tma_store_2d(&tmY, w0 + (uint32_t)(2 * sc) * TS, n0 + 64 * sc, b * K);
+                tma_store_2d(&tmY, w0 + (uint32_t)(2 * sc + 1) * TS, n0 + 64 * sc + 32, b * K);
+              } else {
+                tma_store_2d(&tmS, w0 + (uint32_t)sc * TS, n0 + 64 * sc, b * K);
+                tma_store_2d(&tmS, w0 + (uint32_t)(nsg + sc) * TS, p.split_kp + n0 + 64 * sc, b * K);
+              }
+            }
+            bulk_commit();
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (it == 0 && tid == 0) stamp(9);
       if (warp == 0) {
-        // the tile has been read out: the TMA thread may load the next item's X over it
+        // the tiles have been read out: the TMA thread may load the next item's W slices over them
         if (elect_one()) {
           bulk_wait_read();
-          mbar_arrive(bar(B_XFREE));
+          mbar_arrive(bar(B_OFREE));
         }
         __syncwarp();
       }
@@ -721,26 +723,24 @@ extern "C" int ec_gcn_fused2_set_cta_limit(int ctas) {   // 0 = one CTA per SM; 
 
 extern "C" int ec_gcn_fused2_slice(int K, int d, int dff) { return gf2::pick_slice(K, d, dff); }
 
-extern "C" int ec_gcn_fused2(const float* X, const float* adj, const float* Wp, const void* W3, int Kp, float w_scale,
+extern "C" int ec_gcn_fused2(const float* X, const float* adj, const float* bias2, const void* W3, int Kp, float w_scale,
                              float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream) {
-  EC_REQUIRE(X && adj && Wp && W3 && (Y || split_out), "ec_gcn_fused2: null pointer");
+  EC_REQUIRE(X && adj && bias2 && W3 && (Y || split_out), "ec_gcn_fused2: null pointer");
   const int NS = gf2::pick_slice(K, d, dff);
   EC_REQUIRE(NS > 0, "ec_gcn_fused2: unsupported shape (K <= 128, d in {64,128,256}, dff %% 64 == 0, shared memory)");
   EC_REQUIRE(Kp % 64 == 0 && Kp >= 2 * d, "ec_gcn_fused2: Kp must be a multiple of 64 and >= 2d");
   EC_REQUIRE(w_scale > 0.f, "ec_gcn_fused2: bad weight scale");
-  EC_REQUIRE(aligned16(X) && aligned16(adj) && aligned16(W3) && aligned16(Wp) && (!Y || aligned16(Y)) && (!split_out || aligned16(split_out)),
+  EC_REQUIRE(aligned16(X) && aligned16(adj) && aligned16(W3) && aligned16(bias2) && (!Y || aligned16(Y)) && (!split_out || aligned16(split_out)),
              "ec_gcn_fused2: operands must be 16-byte aligned");
   EC_REQUIRE(!split_out || (split_kp % 8 == 0 && split_kp >= dff), "ec_gcn_fused2: bad split_kp");
   if (B == 0) return EC_OK;
   const int k16 = (K + 15) / 16 * 16;
   const uint32_t smem = gf2::make_layout(k16, d, NS).total + 1024u;
   EC_CUDA((cudaError_t)ensure_dynamic_smem(gf2::gcn_fused2_kernel, (int)gf2::SMEM_LIMIT));
-  CUtensorMap tmW, tmX, tmY, tmS, tmB;
+  CUtensorMap tmW, tmX, tmY, tmS;
   int rc = tc::get_tensor_map_slice32(W3, dff, Kp, NS, &tmW);
   if (rc) return rc;
   rc = tc::get_tensor_map_f32(X, (long long)B * K, d, K, 64, false, &tmX);   // one box = the K rows of a sample x 64 channels
-  if (rc) return rc;
-  rc = tc::get_tensor_map_f32(Wp, dff, 2 * d + 4, NS, 4, false, &tmB);       // bias columns [2d, 2d + 4) of a slice's rows
   if (rc) return rc;
   tmY = tmS = tmX;
   if (Y) {
@@ -753,7 +753,7 @@ extern "C" int ec_gcn_fused2(const float* X, const float* adj, const float* Wp, 
     if (rc) return rc;
   }
   gf2::Params p;
-  p.X = X; p.adj = adj; p.Wp = Wp; p.Y = Y; p.split_out = (__half*)split_out; p.split_kp = split_kp;
+  p.X = X; p.adj = adj; p.bias2 = bias2; p.Y = Y; p.split_out = (__half*)split_out; p.split_kp = split_kp;
   p.B = B; p.K = K; p.d = d; p.dff = dff; p.NS = NS; p.k16 = k16; p.Kp = Kp; p.out_scale = 1.0f / w_scale; p.w_scale = w_scale;
   const int kb_ret = d / 64 > 1 ? 1 : 0;
   p.a1_tma = (K % 4 == 0) && (uint32_t)(kb_ret + 1) * gf2::make_layout(k16, d, NS).blk >= (uint32_t)(K * K) * 4u;
@@ -765,6 +765,6 @@ extern "C" int ec_gcn_fused2(const float* X, const float* adj, const float* Wp, 
   const int items = B * (dff / NS);
   int grid = items < sms ? items : sms;
   if (gf2_cta_limit > 0 && grid > gf2_cta_limit) grid = gf2_cta_limit;
-  launch_pdl(gf2::gcn_fused2_kernel, dim3(grid), dim3(gf2::THREADS), (size_t)smem, (cudaStream_t)stream, tmW, tmX, tmY, tmS, tmB, p);
+  launch_pdl(gf2::gcn_fused2_kernel, dim3(grid), dim3(gf2::THREADS), (size_t)smem, (cudaStream_t)stream, tmW, tmX, tmY, tmS, p);
   return check_launch("ec_gcn_fused2");
 }

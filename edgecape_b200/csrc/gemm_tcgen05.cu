@@ -586,12 +586,12 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int u = 0; u < 16; ++u) y[u] = (gcol + u < p.N) ? y[u] * p.split_scale : 0.f;
           uint32_t h[8];
-          float2 f[8];
+          float2 f[8];                                                  // the low parts y - hi16 (exact; one FHADD each)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
             h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-            f[i] = __half22float2(hh);
+            sub_h2(y[2 * i], y[2 * i + 1], h[i], f[i].x, f[i].y);
           }
           // the previous block has been read out of shared memory: the issuing thread waits for its bulk stores' reads
           // only here, after its own conversions, so the TMA engine drains the tile under everybody's arithmetic
@@ -609,7 +609,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint32_t l[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const __half2 ll = __floats2half2_rn(y[2 * i] - f[i].x, y[2 * i + 1] - f[i].y);
+                  const __half2 ll = __floats2half2_rn(f[i].x, f[i].y);
                   l[i] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
                 *reinterpret_cast<uint4*>(orow + 2 * p.split_kp + 2 * gcol) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -619,9 +619,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 float m = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  h8[i] = e4m3x2(f[2 * i].x, f[2 * i].y) | (e4m3x2(f[2 * i + 1].x, f[2 * i + 1].y) << 16);
-                  l8[i] = e4m3x2((y[4 * i] - f[2 * i].x) * 2048.f, (y[4 * i + 1] - f[2 * i].y) * 2048.f) |
-                          (e4m3x2((y[4 * i + 2] - f[2 * i + 1].x) * 2048.f, (y[4 * i + 3] - f[2 * i + 1].y) * 2048.f) << 16);
+                  h8[i] = e4m3x2_h2(h[2 * i]) | (e4m3x2_h2(h[2 * i + 1]) << 16);
+                  l8[i] = e4m3x2(f[2 * i].x * 2048.f, f[2 * i].y * 2048.f) | (e4m3x2(f[2 * i + 1].x * 2048.f, f[2 * i + 1].y * 2048.f) << 16);
                   m = fmaxf(m, fmaxf(fmaxf(fabsf(y[4 * i]), fabsf(y[4 * i + 1])), fmaxf(fabsf(y[4 * i + 2]), fabsf(y[4 * i + 3]))));
                 }
                 ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
@@ -643,7 +642,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t l[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const __half2 ll = __floats2half2_rn(y[2 * i] - f[i].x, y[2 * i + 1] - f[i].y);
+              const __half2 ll = __floats2half2_rn(f[i].x, f[i].y);
               l[i] = *reinterpret_cast<const uint32_t*>(&ll);
             }
             uint8_t* lrow = blk + 16384 + row_l * 128;
@@ -654,9 +653,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float m = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              h8[i] = e4m3x2(f[2 * i].x, f[2 * i].y) | (e4m3x2(f[2 * i + 1].x, f[2 * i + 1].y) << 16);
-              l8[i] = e4m3x2((y[4 * i] - f[2 * i].x) * 2048.f, (y[4 * i + 1] - f[2 * i].y) * 2048.f) |
-                      (e4m3x2((y[4 * i + 2] - f[2 * i + 1].x) * 2048.f, (y[4 * i + 3] - f[2 * i + 1].y) * 2048.f) << 16);
+              h8[i] = e4m3x2_h2(h[2 * i]) | (e4m3x2_h2(h[2 * i + 1]) << 16);
+              l8[i] = e4m3x2(f[2 * i].x * 2048.f, f[2 * i].y * 2048.f) | (e4m3x2(f[2 * i + 1].x * 2048.f, f[2 * i + 1].y * 2048.f) << 16);
               m = fmaxf(m, fmaxf(fmaxf(fabsf(y[4 * i]), fabsf(y[4 * i + 1])), fmaxf(fabsf(y[4 * i + 2]), fabsf(y[4 * i + 3]))));
             }
             ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);

@@ -590,6 +590,19 @@ def gcn_tc_ok(B, K):
 GCN_FUSED = int(os.environ.get("EDGECAPE_GCN_FUSED", "2"))
 
 
+def _gcn_bias_pair(Wp, d):
+    """The bias columns [2d], [2d+1] of the packed GCN weights as one contiguous [2, dff] array (cached with the split
+    weights: one strided copy per checkpoint)."""
+    key = (id(Wp), Wp.data_ptr(), Wp._version, tuple(Wp.shape), "gcn_bias2")
+    hit = _SPLIT_WEIGHTS.get(key)
+    if hit is not None and hit[0]() is Wp:
+        return hit[1]
+    b2 = empty(2, Wp.shape[0], device=Wp.device)
+    b2.copy_(Wp[:, 2 * d:2 * d + 2].t())          # (weight repacking, once per checkpoint)
+    _SPLIT_WEIGHTS[key] = (weakref.ref(Wp), b2)
+    return b2
+
+
 def gcn_fused_ok(B, K, d, dff):
     """Does gcn() run as ONE kernel for this shape (either formulation)?"""
     if not (GCN_FUSED and gcn_tc_ok(B, K)):
@@ -620,8 +633,12 @@ def gcn(x, adj, Wp, out=None, split="no"):
         elif out is None:
             out = empty(B, K, dff, device=x.device)
         assert out is None or out.is_contiguous()
-        _lib.call("ec_gcn_fused2" if v2 else "ec_gcn_fused", _p(x), _p(adj), _p(Wp), w2.data.data_ptr(), w2.Kp,
-                  float(w2.scale), _p(out), so_ptr, dff, B, K, d, dff, _stream())
+        if v2:
+            _lib.call("ec_gcn_fused2", _p(x), _p(adj), _p(_gcn_bias_pair(Wp, d)), w2.data.data_ptr(), w2.Kp, float(w2.scale),
+                      _p(out), so_ptr, dff, B, K, d, dff, _stream())
+        else:
+            _lib.call("ec_gcn_fused", _p(x), _p(adj), _p(Wp), w2.data.data_ptr(), w2.Kp, float(w2.scale), _p(out), so_ptr,
+                      dff, B, K, d, dff, _stream())
         return so if split == "only" else ((out, so) if split == "also" else out)
     if gcn_tc_ok(B, K):
         Kp = _kp(2 * d + 4)

@@ -301,14 +301,15 @@ int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* 
 /* Second formulation of the same layer (csrc/gcn_fused2_tcgen05.cu, the default): project first,
  *   T0 = X W0^T, T1 = X W1^T (running while X is still being read; cross terms of the fp32-grade split on e4m3
  *   tensor cores), D2 = A1 T1 with A1 in tensor memory, Y = relu(a0 (T0 + b0) + D2 + rowsum(A1) b1);
- * persistent CTAs over (sample, channel slice) items.  Same arguments as ec_gcn_fused except that W3 [dff, 4*Kp bytes]
+ * persistent CTAs over (sample, channel slice) items.  Arguments as ec_gcn_fused except that bias2 [2][dff] holds the
+ * bias columns of Wp contiguously (b0 then b1; they are preloaded into the accumulators) and W3 [dff, 4*Kp bytes]
  * is the F16F8 B-role form of Wp * w_scale with its planes interleaved per 32 columns (ec_split_f16f8 with
  * role 2): the weights stream in 32-deep k-slices.  Same shape gate (ec_gcn_fused2_slice). */
 int ec_gcn_fused2_slice(int K, int d, int dff);
 int ec_gcn_fused2_set_debug(int flags);               /* profiling experiments only: 1 = skip the A1 / X loads, 2 = skip the stores */
 int ec_gcn_fused2_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] int64 clock stamps of each CTA's first item */
 int ec_gcn_fused2_set_cta_limit(int ctas);            /* profiling: at most this many persistent CTAs (0 = one per SM) */
-int ec_gcn_fused2(const float* X, const float* adj, const float* Wp, const void* W3, int Kp, float w_scale,
+int ec_gcn_fused2(const float* X, const float* adj, const float* bias2, const void* W3, int Kp, float w_scale,
                   float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream);
 
 /* ----------------------------------------------------------------------------- head ops
