@@ -447,6 +447,9 @@ struct ParamsT {
   const float* hops;                // [n_hops, B, Lq, Lk] Markov hop matrices, or NULL
   const float *hw0, *hb0, *hw1, *hb1;   // Linear(n_hops, hidden), Linear(hidden, H)
   int n_hops, hidden;
+  int split_fmt;                    // row format of split_out: EC_SPLIT_F16X2, or EC_SPLIT_F16F8 (head dim 64: the consumer is
+                                    // ec_gemm_f16f8, e.g. the ViT proj GEMM) -- ec_attention_split_fmt_next
+  unsigned long long* overflow;     // F16F8 output: {beyond e4m3, beyond fp16} event counters
 };
 
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column fp16 box
@@ -717,6 +720,53 @@ attention_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   stamp(9);
 }
 
+
+// One thread's 16 output columns (part `part` of a 64-wide head) -> 16-byte chunks of its row of the [row][256 B] staging
+// tile.  F16X2: chunks [0, 8) = hi16, [8, 16) = lo16.  F16F8 (A role, common.cuh): chunks [0, 8) = hi16, [8, 12) = hi8,
+// [12, 16) = lo8.  Chunks are XOR-swizzled by the row.
+__device__ __forceinline__ void stage_split16(uint8_t* stg, int row, int part, const float* o, int fmt, uint32_t& ovf) {
+  uint32_t h[8];
+  float dl[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __half2 hh = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    sub_h2(o[2 * i], o[2 * i + 1], h[i], dl[2 * i], dl[2 * i + 1]);
+  }
+  uint8_t* r = stg + row * 256;
+  const int sw = row & 15;
+  *reinterpret_cast<uint4*>(r + (((2 * part) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(r + (((2 * part + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+  if (fmt == EC_SPLIT_F16X2) {
+    uint32_t l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2 ll = __floats2half2_rn(dl[2 * i], dl[2 * i + 1]);
+      l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(r + (((8 + 2 * part) ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(r + (((9 + 2 * part) ^ sw) << 4)) = make_uint4(l[4], l[5], l[6], l[7]);
+  } else {
+    uint32_t h8[4], l8[4];
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h8[i] = e4m3x2_h2(h[2 * i]) | (e4m3x2_h2(h[2 * i + 1]) << 16);
+      l8[i] = e4m3x2(dl[4 * i] * 2048.f, dl[4 * i + 1] * 2048.f) | (e4m3x2(dl[4 * i + 2] * 2048.f, dl[4 * i + 3] * 2048.f) << 16);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(o[4 * i]), fabsf(o[4 * i + 1])), fmaxf(fabsf(o[4 * i + 2]), fabsf(o[4 * i + 3]))));
+    }
+    ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
+    *reinterpret_cast<uint4*>(r + (((8 + part) ^ sw) << 4)) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+    *reinterpret_cast<uint4*>(r + (((12 + part) ^ sw) << 4)) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+  }
+}
+// chunk c of the staged row -> its place in the split row of `kp` columns (head h of width 64): a pointer in halves
+__device__ __forceinline__ __half* split_chunk_dst(__half* row, int kp, int h, int c, int fmt) {
+  if (fmt == EC_SPLIT_F16X2) return row + h * 64 + (c < 8 ? c * 8 : kp + (c - 8) * 8);
+  if (c < 8) return row + h * 64 + c * 8;                                    // hi16: halves [0, kp)
+  if (c < 12) return row + kp + h * 32 + (c - 8) * 8;                        // hi8: bytes [2 kp, 3 kp)
+  return row + kp + kp / 2 + h * 32 + (c - 12) * 8;                          // lo8: bytes [3 kp, 4 kp)
+}
 // ---------------------------------------------------------------------------------------------------------
 // P-in-TMEM variant (the default).  The shared-memory P path above is bound by shared-memory bandwidth in the
 // P V phase: per 64-key chunk the MMAs re-read P three times (48 KB) and V three times (24 KB) and the softmax
@@ -1101,6 +1151,7 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int q = 0; q < NPART; ++q) tot += xsum[q * BM + row];
     const float inv = tot > 0.f ? 1.0f / tot : 0.f;    // fully masked row -> 0 (as the fp32 kernels)
     constexpr int OW = D / NPART;
+    uint32_t ovf = 0;
     if (OW * part < p.dv) {                            // warp-uniform: head dim 32 keeps parts 0 and 1
       float o[OW];
       tmem_ld16(t_row + (p.wide ? 384 : 512 - 64 * p.NB) + OW * part, o);
@@ -1126,13 +1177,17 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         // store wavefronts per CTA, ~2K clk of LSU time).  Instead the tile goes through shared memory (dead by
         // now: every MMA has retired) as [row][hi 128 B | lo 128 B], 16-byte chunks XOR-swizzled by the row, and
         // is written out as whole 128-byte lines: 16 lanes per row.
+        if (p.split_fmt == EC_SPLIT_F16F8) {             // (head dim 64) [hi16 | hi8 | lo8] chunks
+          stage_split16(gbase, row, part, o, EC_SPLIT_F16F8, ovf);
+        } else {
 #pragma unroll
-        for (int j = 0; j < OW / 8; ++j) {
-          uint4 hi, lo;
-          split8(o + 8 * j, hi, lo);
-          const int c = (OW / 8) * part + j;             // 16-byte chunk of the hi half; lo is chunk 8 + c
-          *reinterpret_cast<uint4*>(gbase + row * 256 + ((c ^ (row & 15)) << 4)) = hi;
-          *reinterpret_cast<uint4*>(gbase + row * 256 + (((8 + c) ^ (row & 15)) << 4)) = lo;
+          for (int j = 0; j < OW / 8; ++j) {
+            uint4 hi, lo;
+            split8(o + 8 * j, hi, lo);
+            const int c = (OW / 8) * part + j;           // 16-byte chunk of the hi half; lo is chunk 8 + c
+            *reinterpret_cast<uint4*>(gbase + row * 256 + ((c ^ (row & 15)) << 4)) = hi;
+            *reinterpret_cast<uint4*>(gbase + row * 256 + (((8 + c) ^ (row & 15)) << 4)) = lo;
+          }
         }
       }
     }
@@ -1143,13 +1198,15 @@ attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int r = 8 * w16 + 2 * it + (lane >> 4), c = lane & 15;
-        if (q0 + r < p.Lq && (c & 7) < nch) {
+        if (q0 + r < p.Lq && ((c & 7) < nch || p.split_fmt == EC_SPLIT_F16F8)) {
           const uint4 v = *reinterpret_cast<const uint4*>(gbase + r * 256 + ((c ^ (r & 15)) << 4));
-          __half* sp = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp) + h * p.dv +
-                       (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
+          __half* srow = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp);
+          __half* sp = p.split_fmt == EC_SPLIT_F16F8 ? split_chunk_dst(srow, p.split_kp, h, c, EC_SPLIT_F16F8)
+                                                     : srow + h * p.dv + (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
           *reinterpret_cast<uint4*>(sp) = v;
         }
       }
+      report_overflow(p.overflow, ovf);
     }
     stamp(7);
   }
@@ -1356,6 +1413,7 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_oe);                 // phase 0 of bar_oe ("nothing to drain"); the epilogue of tile t completes phase t + 1
     const int tr_it = n_it > 2 ? 2 : n_it - 1;        // traced tile: the third one (steady state of the pipeline)
+    uint32_t ovf = 0;                                 // F16F8 output: values beyond the e4m3 / fp16 range seen by this thread
     for (int it = 0; it < n_it; ++it) {
       int b, h, q0;
       tile_of(it, b, h, q0);
@@ -1451,23 +1509,15 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (p.split_out) {
         // through the staging tile (the V region: every MMA reading V has retired) as [row][hi 128 B | lo 128 B],
         // 16-byte chunks XOR-swizzled by the row, written out as whole 128-byte lines: 16 lanes per row
-#pragma unroll
-        for (int j = 0; j < OW / 8; ++j) {
-          uint4 hi, lo;
-          split8(o + 8 * j, hi, lo);
-          const int c = (OW / 8) * part + j;
-          *reinterpret_cast<uint4*>(stg + row * 256 + ((c ^ (row & 15)) << 4)) = hi;
-          *reinterpret_cast<uint4*>(stg + row * 256 + (((8 + c) ^ (row & 15)) << 4)) = lo;
-        }
+        stage_split16(stg, row, part, o, p.split_fmt, ovf);
         softmax_sync();
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const int r = 8 * warp + 2 * k4 + (lane >> 4), c = lane & 15;
           if (q0 + r < p.Lq) {
             const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 256 + ((c ^ (r & 15)) << 4));
-            __half* sp = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp) + h * D +
-                         (c < 8 ? c * 8 : p.split_kp + (c - 8) * 8);
-            *reinterpret_cast<uint4*>(sp) = v;
+            __half* srow = p.split_out + ((long long)b * p.Lq + q0 + r) * (2 * p.split_kp);
+            *reinterpret_cast<uint4*>(split_chunk_dst(srow, p.split_kp, h, c, p.split_fmt)) = v;
           }
         }
       }
@@ -1477,6 +1527,7 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (lane == 0) mbar_arrive(bar_oe);
       if (it == tr_it) stamp(7);
     }
+    report_overflow(p.overflow, ovf);
   }
   tc_fence_before();
   __syncthreads();
@@ -1492,6 +1543,7 @@ struct HopArm {   // armed by ec_attention_hop_bias_next, consumed by the next e
   int n_hops = 0, hidden = 0;
 };
 static thread_local HopArm g_hop;
+static thread_local int g_out_fmt = EC_SPLIT_F16X2;   // armed by ec_attention_split_fmt_next, consumed by the next ec_attention_tc_split
 static int g_variant = 0;   // 0: persistent pipelined kernel where it applies, else P in TMEM + wide P V MMAs; 3: never the persistent kernel; 2: P in TMEM, three N = 64 MMAs per k-step; 1: P through shared memory
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
@@ -1554,6 +1606,14 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   }
   const atc::HopArm hop = atc::g_hop;                  // (consumed: applies to this call only)
   atc::g_hop = atc::HopArm();
+  const int out_fmt = atc::g_out_fmt;
+  atc::g_out_fmt = EC_SPLIT_F16X2;
+  EC_REQUIRE(out_fmt == EC_SPLIT_F16X2 || (split_out && dv == 64), "ec_attention_tc_split: F16F8 output rows need head dim 64 and split_out");
+  unsigned long long* ovf_counters = nullptr;
+  if (out_fmt == EC_SPLIT_F16F8) {
+    ovf_counters = overflow_counters();
+    if (!ovf_counters) return EC_ERR_CUDA;
+  }
   EC_REQUIRE(!hop.hops || !bias, "ec_attention_tc_split: an additive bias tensor and the fused hop-bias MLP exclude each other");
   EC_REQUIRE(!hop.hops || (hop.n_hops <= 8 && hop.hidden * (hop.n_hops + 2) + 1 <= 112),
              "ec_attention_tc_split: hop-bias MLP too large for the fused form (n_hops <= 8, hidden * (n_hops + 2) < 112)");
@@ -1584,7 +1644,7 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
   atc::ParamsT p{O, B, H, Lq, Lk, NB, LB, ldo, so, scale, (__half*)split_out, split_kp, q_col, k_col, v_col,
                  q_kp, k_kp, v_kp, q_rows, k_rows, atc::g_trace, atc::g_trace_n,
                  (atc::g_variant != 2 && NB == 1 && LB <= 384) ? 1 : 0, dv, key_mask, bias,
-                 hop.hops, hop.w0, hop.b0, hop.w1, hop.b1, hop.n_hops, hop.hidden};
+                 hop.hops, hop.w0, hop.b0, hop.w1, hop.b1, hop.n_hops, hop.hidden, out_fmt, ovf_counters};
   dim3 grid(cdiv(Lq, atc::BM), H, B);
   // the persistent, pipelined kernel takes the plain head-dim-64 attentions whose Q + K + V tiles fit shared memory
   // together (the ViT blocks up to 368 tokens; variant 3 = force off for A/B measurements)
@@ -1628,6 +1688,7 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
                  (cudaStream_t)stream, tmQ, tmK, tmV, p);
     }
   } else {
+    EC_REQUIRE(out_fmt == EC_SPLIT_F16X2, "ec_attention_tc_split: variant 1 (A/B only) writes F16X2 rows only");
     atc::attention_tc_tma_kernel<<<grid, atc::THREADS_T, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   }
   return check_launch("ec_attention_tc_split");
@@ -1638,6 +1699,12 @@ extern "C" int ec_attention_hop_bias_next(const float* hops, int n_hops, int hid
   EC_REQUIRE(hops && w0 && b0 && w1 && b1 && n_hops > 0 && hidden > 0, "ec_attention_hop_bias_next: bad arguments");
   atc::g_hop.hops = hops; atc::g_hop.n_hops = n_hops; atc::g_hop.hidden = hidden;
   atc::g_hop.w0 = w0; atc::g_hop.b0 = b0; atc::g_hop.w1 = w1; atc::g_hop.b1 = b1;
+  return EC_OK;
+}
+
+extern "C" int ec_attention_split_fmt_next(int fmt) {
+  EC_REQUIRE(fmt == EC_SPLIT_F16X2 || fmt == EC_SPLIT_F16F8, "ec_attention_split_fmt_next: EC_SPLIT_F16X2 or EC_SPLIT_F16F8");
+  atc::g_out_fmt = fmt;
   return EC_OK;
 }
 

@@ -101,6 +101,10 @@ F16X2, F16F8 = 0, 1
 F16F8_I32 = 2      # weights only: the F16F8 B-role planes interleaved per 32 columns, [hi16 x 32 | hi8 x 32 | lo8 x 32] (the fused
                    # GCN streams its weights in 32-deep k-slices: one TMA box with 128-byte rows then holds a whole slice)
 GEMM_F8 = os.environ.get("EDGECAPE_GEMM_F8", "1") != "0"
+# EDGECAPE_PROJ_F8=1: the ViT attention writes F16F8 rows and the proj GEMM runs on ec_gemm_f16f8 too.  Off by default: proj
+# (K = 768, 128x128 tiles, 3.3 waves) is bound by per-tile latency, not by tensor time -- measured 4.20 vs 4.23 ms of GEMM
+# time per step, no change of the step (profiles/r03_h_bench_proj_f8_{0,1}.json) -- so it keeps three fp16 products.
+PROJ_F8 = os.environ.get("EDGECAPE_PROJ_F8", "0") != "0"
 F8_MIN_M = 2048
 _SPLIT_WEIGHTS = {}
 
@@ -398,7 +402,7 @@ def attention(q, k, v, nheads, scale=None, key_mask=None, bias=None, out=None, s
 
 
 def attention_split(q2, q_col, q_rows, k2, k_col, v2, v_col, k_rows, B, nheads, Lq, Lk, D, scale=None,
-                    key_mask=None, bias=None, out=None, split="only", hop=None):
+                    key_mask=None, bias=None, out=None, split="only", hop=None, out_fmt=F16X2):
     """softmax(Q K^T * scale + bias, masked) V on split-fp16 operands (the split outputs of the projections):
     head h of Q is columns q_col + D*h of each half of q2, rows b*q_rows + i; K / V likewise with k_rows rows
     per batch element.  TMA-fed tcgen05 kernel with the probabilities in TMEM.  D in (32, 64)."""
@@ -416,8 +420,9 @@ def attention_split(q2, q_col, q_rows, k2, k_col, v2, v_col, k_rows, B, nheads, 
         out = None
     sp, sp_ptr = None, None
     if split != "no":
-        sp = SplitOperand(empty(B * Lq, 2 * C, dtype=torch.float16, device=dev), B * Lq, C, C, 1.0)
+        sp = SplitOperand(empty(B * Lq, 2 * C, dtype=torch.float16, device=dev), B * Lq, C, C, 1.0, out_fmt)
         sp_ptr = sp.data.data_ptr()
+    assert out_fmt == F16X2 or (sp is not None and D == 64), "F16F8 attention output rows: head dim 64, split output"
     if scale is None:
         scale = D ** -0.5
     if key_mask is not None:
@@ -435,6 +440,8 @@ def attention_split(q2, q_col, q_rows, k2, k_col, v2, v_col, k_rows, B, nheads, 
             assert t_.is_contiguous()
         assert w1.shape[0] == nheads
         _lib.call("ec_attention_hop_bias_next", _p(attn_adj), attn_adj.shape[0], w0.shape[0], _p(w0), _p(b0), _p(w1), _p(b1))
+    if out_fmt != F16X2:
+        _lib.call("ec_attention_split_fmt_next", int(out_fmt))
     _lib.call("ec_attention_tc_split", q2.data.data_ptr(), q2.rows, q2.Kp, q_col, q_rows, k2.data.data_ptr(), k2.rows,
               k2.Kp, k_col, v2.data.data_ptr(), v2.rows, v2.Kp, v_col, k_rows, _p(out), B, nheads, Lq, Lk, ldo, so_,
               float(scale), D, _p(key_mask), _p(bias), sp_ptr, C if sp is not None else 0, _stream())
@@ -459,13 +466,14 @@ def hop_fused_ok(n_hops, hidden):
     return n_hops <= 8 and hidden * (n_hops + 2) + 1 <= 112
 
 
-def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only", key_mask=None, bias=None, hop=None):
+def attention_packed_split(qkv2, B, N, nheads, scale=None, out=None, split="only", key_mask=None, bias=None, hop=None,
+                           out_fmt=F16X2):
     """Self-attention over a packed split-fp16 QKV operand (the split output of the QKV GEMM):
     qkv2 rows = B*N tokens, columns [q | k | v] of C = nheads*D each per half."""
     C = qkv2.K // 3
     assert qkv2.rows == B * N and qkv2.Kp == qkv2.K
     return attention_split(qkv2, 0, N, qkv2, C, qkv2, 2 * C, N, B, nheads, N, N, C // nheads, scale=scale,
-                           key_mask=key_mask, bias=bias, out=out, split=split, hop=hop)
+                           key_mask=key_mask, bias=bias, out=out, split=split, hop=hop, out_fmt=out_fmt)
 
 
 def gather_blocks(src, idx, out=None):

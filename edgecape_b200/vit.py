@@ -96,16 +96,19 @@ class DinoVisionTransformerB200(PackedMixin, ParamTree):
             # before it (LayerNorm, attention, GELU epilogue); only the residual stream t stays fp32
             packed_attn = ops.ATTENTION_TC and ops.ATTENTION_TMA and C // H == 64 and N <= 768 and (3 * C) % 64 == 0
             # the large linears run with their cross terms on e4m3 (ec_gemm_f16f8): their A operands are produced in
-            # F16F8 rows by the LayerNorms / the fc1 epilogue; q, k, v and the attention output stay F16X2 (the
-            # attention kernel and the proj GEMM -- short K, 128x128 tiles -- consume those)
+            # F16F8 rows by the LayerNorms, the fc1 epilogue and (for proj) the attention kernel; q, k, v stay F16X2 (the
+            # attention kernel consumes those).  EDGECAPE_PROJ_F8=0 keeps the proj GEMM on three fp16 products.
             f8 = ops.F16F8 if ops.f8_linear_ok(Btot * N, getattr(self.blocks, "0").mlp.fc1.weight) else ops.F16X2
+            proj_f8 = (f8 == ops.F16F8 and packed_attn and ops.PROJ_F8
+                       and ops.f8_linear_ok(Btot * N, getattr(self.blocks, "0").attn.proj.weight))
             for i in range(self.depth):
                 blk = getattr(self.blocks, str(i))
                 y2 = ops.layernorm(t2, blk.norm1.weight, blk.norm1.bias, 1e-6, split="only", split_fmt=f8)
                 if packed_attn:
                     # the QKV GEMM writes q, k, v already split; the attention kernel TMA-loads them
                     _, qkv2 = ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, split_out=True, fp32_out=False)
-                    a2 = ops.attention_packed_split(qkv2, Btot, N, H)
+                    # (attention output rows in the format the proj GEMM takes: F16F8 where it runs on ec_gemm_f16f8)
+                    a2 = ops.attention_packed_split(qkv2, Btot, N, H, out_fmt=ops.F16F8 if proj_f8 else ops.F16X2)
                 else:
                     ops.linear(y2, blk.attn.qkv.weight, blk.attn.qkv.bias, out=qkv.view(Btot * N, 3 * C))
                     a2 = ops.attention(qkv[:, :, 0:C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, split="only")

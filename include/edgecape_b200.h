@@ -224,6 +224,10 @@ int ec_attention_tc(const float* Q, const float* K, const float* V, float* O, in
  * Limits: n_hops <= 8, hidden * (n_hops + 2) < 112 (else use ec_hop_bias + the bias argument). */
 int ec_attention_hop_bias_next(const float* hops, int n_hops, int hidden, const float* w0, const float* b0,
                                const float* w1, const float* b1);
+/* Arms the NEXT ec_attention_tc_split call on this thread to write its split_out rows in the format `fmt`:
+ * EC_SPLIT_F16X2 (the default) or EC_SPLIT_F16F8 (A role; head dim 64 only) -- the format ec_gemm_f16f8 consumes, so that
+ * the projection behind a ViT attention (dino.py Attention.proj) runs its cross terms on e4m3 like qkv / fc1 / fc2. */
+int ec_attention_split_fmt_next(int fmt);
 int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
                           const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
                           int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H,

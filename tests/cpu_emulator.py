@@ -242,7 +242,7 @@ def ec_attention_tc(Q, K, V, O, B, H, Lq, Lk, D, ldq, ldk, ldv, ldo, sq, sk, sv,
     if O:
         arr(O, (B, Lq, H, D), (so, ldo, D, 1))[...] = o
     if split_out:
-        _write_split(split_out, split_kp, o.reshape(B * Lq, H * D))
+        _write_split(split_out, split_kp, o.reshape(B * Lq, H * D), out_fmt)
 
 
 _HOP_NEXT = []
@@ -252,9 +252,17 @@ def ec_attention_hop_bias_next(hops, n_hops, hidden, w0, b0, w1, b1):
     _HOP_NEXT.append((hops, n_hops, hidden, w0, b0, w1, b1))
 
 
+_FMT_NEXT = []
+
+
+def ec_attention_split_fmt_next(fmt):
+    _FMT_NEXT.append(int(fmt))
+
+
 def ec_attention_tc_split(Q2, q_total, q_kp, q_col, q_rows, K2, k_total, k_kp, k_col, V2, v_total, v_kp, v_col, k_rows,
                           O, B, H, Lq, Lk, ldo, so, scale, D, key_mask, bias, split_out, split_kp, stream):
     hop = _HOP_NEXT.pop() if _HOP_NEXT else None           # armed for this call only
+    out_fmt = _FMT_NEXT.pop() if _FMT_NEXT else 0
     assert not _HOP_NEXT and not (hop and bias)
     assert D in (32, 64) and Lk <= (768 if (D == 64 and not key_mask and not bias and not hop) else 448)
 

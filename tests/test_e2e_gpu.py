@@ -63,6 +63,7 @@ def test_detector_matches_reference_golden(name, tensor_cores, golden_dir, monke
     if tensor_cores == "f8":
         monkeypatch.setattr(ops, "F8_MIN_M", 64)
         monkeypatch.setattr(ops, "GEMM_F8", True)
+        monkeypatch.setattr(ops, "PROJ_F8", True)      # ... and the ViT proj GEMM on F16F8 attention output rows
         tensor_cores = True
     monkeypatch.setattr(ops, "TENSOR_CORES", tensor_cores)
     golden = dict(np.load(os.path.join(golden_dir, name + ".npz")))

@@ -592,6 +592,34 @@ def test_attention_tma_on_split_qkv(B, N, H, monkeypatch):
     close(sp.data[:, :C].float() + sp.data[:, C:].float(), want.reshape(B * N, C), tol=5e-6, what="attention_tma split")
 
 
+@pytest.mark.parametrize("B,N,H", [(2, 325, 12), (1, 64, 1), (2, 130, 4), (1, 730, 16), (2, 449, 3)])
+def test_attention_writes_f16f8_rows(B, N, H):
+    """ec_attention_split_fmt_next(EC_SPLIT_F16F8): the split output rows in the [hi16 | hi8 | lo8] format ec_gemm_f16f8
+    consumes (the ViT proj GEMM), from the persistent kernel (<= 368 tokens) and the one-tile-per-CTA kernel: the hi16
+    plane is bit-identical to the F16X2 output, hi8 = e4m3(hi16), lo8 = e4m3(lo 2^11); then the proj-shaped GEMM on it."""
+    C = H * 64
+    D = dev()
+    qkv2 = ops.split_f16(rnd(B * N, 3 * C, seed=21).to(D))
+    ref = ops.attention_packed_split(qkv2, B, N, H)
+    got = ops.attention_packed_split(qkv2, B, N, H, out_fmt=ops.F16F8)
+    assert got.fmt == ops.F16F8 and got.Kp == C
+    hi16, lo16 = ref.data[:, :C], ref.data[:, C:].float()
+    raw = got.data.view(torch.uint8).view(B * N, 4 * C)
+    assert torch.equal(raw[:, :2 * C].contiguous().view(torch.float16), hi16)
+    h8 = raw[:, 2 * C:3 * C].contiguous().view(torch.float8_e4m3fn).float()
+    l8 = raw[:, 3 * C:].contiguous().view(torch.float8_e4m3fn).float()
+    assert torch.equal(h8, hi16.float().to(torch.float8_e4m3fn).float())
+    # (the kernel rounds the exact fp32 low part, lo16 is that part rounded to fp16 first: at most one e4m3 step apart)
+    exp_l8 = (lo16 * 2048.0).to(torch.float8_e4m3fn).float()
+    assert bool(((l8 - exp_l8).abs() <= 0.13 * exp_l8.abs() + 2.0 ** -9).all())
+    assert float((l8 != exp_l8).float().mean()) < 0.05
+    # ... and as the A operand of the F16F8 GEMM against the F16X2 pair
+    w = rnd(C, C, seed=22, scale=C ** -0.5).to(D)
+    y8 = ops.gemm_tc(got, ops.split_weight(w, ops.F16F8))
+    y16 = ops.gemm_tc(ref, ops.split_weight(w, ops.F16X2))
+    close(y8, y16, tol=3e-5, what="proj on F16F8 attention rows")
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk,Dh,masked,biased", [
     (2, 8, 100, 100, 32, True, True),      # decoder self-attention over keypoints: fixed key mask + hop bias
     (2, 8, 424, 424, 32, True, False),     # encoder self-attention over image + keypoint tokens
