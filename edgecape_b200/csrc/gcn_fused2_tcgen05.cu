@@ -1,28 +1,38 @@
 // Fused GCN feed-forward for sm_100a, second formulation (encoder_decoder.py:508-524 of the reference):
 //     Y[b,w,:] = relu( a0[b,w] * (X[b,w,:] W0^T + b0) + sum_v A1[b,w,v] (X[b,v,:] W1^T + b1) )
-// evaluated PROJECT-FIRST:   T0 = X W0^T,  T1 = X W1^T,  D2 = A1 T1,
-//     Y = relu( a0 (T0 + b0) + D2 + rowsum(A1) b1 ).
+// evaluated PROJECT-FIRST:   T0 = X W0^T + b0,  T1 = X W1^T + b1,  D2 = A1 T1 (= A1 X W1^T + rowsum(A1) b1),
+//     Y = relu( a0 T0 + D2 ).
 // The first formulation (gcn_fused_tcgen05.cu: aggregate first) is a chain  fill -> A1 X -> [a0 X | A1 X] W^T  in which
 // nothing overlaps: at batch 64 the launch is one wave and its time is that chain (fill 6.1 K clk, GEMM 1 3.0 K, GEMM 2
 // 10.3 K, epilogue 4.1 K).  Here the large product (X W^T, 2 d NS MACs per row) depends on X alone, so it runs WHILE X is
 // being filled, one 64-channel block behind the workers; X is only ever a K-major A operand, which lets the cross terms
 // of the fp32-grade split run on e4m3 tensor cores exactly as in gemm_tcgen05.cu (hi16.hi16 on kind::f16, lo8.hi8 and
 // hi8.lo8 on kind::f8f6f4: 2 instead of 3 units of tensor time); the small product A1 T1 takes A1 from TENSOR MEMORY
-// (packed fp16 hi / lo written by the workers with tcgen05.st -- A1 never touches shared memory) and T1 as an MN-major B
-// operand the workers drain out of TMEM, rescale and split into the shared memory the retired X blocks occupied.
-// a0 enters in the epilogue (two accumulators), so there is no rescale pass and no "a0 != 1" special case.
+// (packed fp16 hi / lo written by the workers with tcgen05.st) and T1 as an MN-major B operand the workers drain out of
+// TMEM, rescale and split into the shared memory the retired X blocks occupied.  The biases are preloaded into the
+// accumulators and a0 enters in the epilogue (two accumulators): no rescale pass, no row sums, no "a0 != 1" special case.
 //
 // CTA = persistent worker over items (sample b, slice of NS output channels).  Warps 0..15: workers (fill, drain,
-// epilogue); warp 16: MMA issue; warp 17: TMA (W ring).  Per item:
-//   fill      X[b] -> ng blocks of [hi16 (128B swizzle) | hi8 | lo8 (64B swizzle)] K-major tiles, one mbarrier per block;
-//             A1[b] -> TMEM columns (row w = lane, k = v packed two per column), partial row sums to shared memory
-//   GEMM A    per block kb: T0 += X_kb W0_kb^T, T1 += X_kb W1_kb^T (W through a two-stage TMA ring of F16F8 B-role tiles);
-//             in the last block T1 goes first, so its drain overlaps the last T0 step
+// epilogue); warp 16: MMA issue; warp 17: TMA.  Per item:
+//   TMA       raw X[b] as ng blocks [K rows x 64 channels] INTO the regions of their own tiles; the biases of the slice (two
+//             bulk copies); W in 32-deep slices through a ring of four (one box of 128-byte rows [hi16 | hi8 | lo8] each:
+//             the weights are packed with their planes interleaved per 32 columns, ec_split_f16f8 role 2); A1[b] as one
+//             bulk copy into X blocks 0 / 1 once GEMM A has consumed them; the NEXT item's X as soon as GEMM B has retired
+//   init      T0 = b0 w_scale, T1 = b1 w_scale (tcgen05.st)
+//   fill      per block: raw rows -> registers -> CTA barrier -> [hi16 (128B swizzle) | hi8 | lo8 (64B swizzle)] K-major
+//             tiles over the same bytes, one mbarrier per block
+//   GEMM A    per block kb: T0 += X_kb W0_kb^T, T1 += X_kb W1_kb^T; in the last block T1 goes first, so its drain overlaps
+//             the last T0 step
+//   A1        raw rows (shared memory) -> packed fp16 hi | lo -> TMEM columns (row w = lane, k = v two per column)
 //   drain     T1 / w_scale -> fp16 hi | lo, [v][64 n] MN-major tiles over X blocks 0 .. NS/64-1
 //   GEMM B    D2 (the T1 columns) = A1 . T1, three fp16 products, A from TMEM
-//   epilogue  relu(a0 (T0 / w_scale + b0) + D2 + rs b1) through a per-warp staging tile, fp32 rows and / or split rows
-// Shared memory (K = 100, d = 256, NS = 192): X 4 x 28 KB, W ring 2 x 48 KB (stage 1 doubles as the epilogue staging
-// area once its last tile is consumed).  TMEM: T0 [0, NS), T1 / D2 [NS, 2 NS), A1 hi [2 NS, +64), A1 lo [2 NS + 64, +64).
+//   epilogue  relu(a0 T0 / w_scale + D2), 64 columns per round into 128B-swizzled tiles in the W ring (idle by then), each
+//             round's tiles leave by TMA tensor stores while the next round is computed
+// Shared memory (K = 100, d = 256, NS = 192): X 4 x 28 KB, W ring 4 x 24 KB.  TMEM: T0 [0, NS), T1 / D2 [NS, 2 NS), A1 hi
+// [2 NS, +64), A1 lo [2 NS + 64, +64).  The worker branch runs at the 96-register limit of an 18-warp CTA and shared memory
+// takes nearly all of the L1: a spill in a hot path costs an L2 round trip (profiles/r03_gcn2_development.md, steps 2 / 5),
+// which is why the fill is single buffered and shared memory is addressed by 32-bit shared addresses.
+// Measured: 13.1 us at B = 64 (aggregate-first kernel 15.3), 318 us at B = 2048 (455): 0.23 / 0.29 of the HBM roofline.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -184,7 +194,7 @@ struct Params {
 
 // barrier indices (8 bytes each)
 constexpr int WRING = 4;                 // W ring: four slices of 32 k (see the TMA producer)
-enum { W_FULL = 0, W_EMPTY = 4, B_XRAW = 8, B_XRD = 12, B_XF = 16, B_T1 = 20, B_T1S = 21, B_ACC = 22, B_OFREE = 23, B_XRET = 24,
+enum { W_FULL = 0, W_EMPTY = 4, B_XRAW = 8, B_XF = 16, B_T1 = 20, B_T1S = 21, B_ACC = 22, B_OFREE = 23, B_XRET = 24,
        B_A1RAW = 25, B_BIAS = 26, NUM_BARS = 32 };
 
 struct Layout {
@@ -283,7 +293,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   };
 
   if (tid == 0) {
-    for (int g = 0; g < MAX_G; ++g) { mbar_init(bar(B_XF + g), WORKERS / 32); mbar_init(bar(B_XRD + g), WORKERS / 32); }
+    for (int g = 0; g < MAX_G; ++g) mbar_init(bar(B_XF + g), WORKERS / 32);
     mbar_init(bar(B_T1), 1);
     mbar_init(bar(B_T1S), WORKERS / 32);
     mbar_init(bar(B_ACC), 1);
@@ -311,12 +321,12 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // tiles will occupy (4 bytes per element either way); the workers read a block into registers, synchronise and
     // write the tiles over it.  No thread holds X in registers across a global-memory latency, and all of X is in
     // flight at once.  (Loaded through registers with a two-block ring the values were spilled, and each spill store
-    // waited for its load: the blocks arrived one latency apart, profiles/r03_a_gcn2_trace.log.)
+    // waited for its load: the blocks arrived one latency apart, profiles/r03_gcn2_development.md.)
     const bool leader = elect_one();
     uint32_t gs = 0;
     // W streams in slices of 32 k through a ring of four (24 KB each at NS = 192): with two 48 KB stages of 64 k a
     // stage could only be re-requested when its UMMAs had retired, i.e. one request in flight per SM against an L2
-    // latency of ~1.4 K clk -- 1.2 K clk per 784 clk of math (profiles/r03_a_gcn2_trace.log).  A slice is ONE box with
+    // latency of ~1.4 K clk -- 1.2 K clk per 784 clk of math (profiles/r03_gcn2_development.md).  A slice is ONE box with
     // 128-byte rows [hi16 x 32 | hi8 x 32 | lo8 x 32] (the weights are packed with the planes interleaved per 32 columns:
     // ec_split_f16f8, role 2).
     auto w_step = [&](int s, int n0) {
@@ -463,7 +473,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       mbar_wait(bar(B_BIAS), par);
 #pragma unroll 1
       for (int sc = 0; sc < nsub; ++sc) {
-        const int col0 = part * cw + sc * 16;
+        const int col0 = sc * 64 + part * 16;      // the columns this thread reads back in the epilogue
         uint32_t u0[16], u1[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                                         // broadcast reads
@@ -588,7 +598,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       // Results are assembled in shared memory (the X / T1 region) as 128-byte-row, 128B-swizzled tiles -- 32 fp32 or 64
       // fp16 columns wide: each lane writes 16-byte pieces of its own row, conflict free -- and leave through a few TMA
       // tensor stores.  (From registers, 77 KB of 16-byte stores per CTA cost 3.7 K clk at ~26 B/clk per SM and could not
-      // overlap the next item; one bulk copy per row cost as much in issue time.  profiles/r03_a_gcn2_trace.log)
+      // overlap the next item; one bulk copy per row cost as much in issue time.  profiles/r03_gcn2_development.md)
       mbar_wait(bar(B_ACC), par);
       tc_fence_after();
       if (it == 0 && tid == 0) stamp(8);

@@ -6,7 +6,7 @@ import torch
 sys.path.insert(0, ".")
 from edgecape_b200 import ops  # noqa: E402
 
-fused = "--two-kernel" not in sys.argv
+fused = 0 if "--two-kernel" in sys.argv else (1 if "--aggregate-first" in sys.argv else 2)   # 2: gcn_fused2_tcgen05.cu
 D = torch.device("cuda")
 ops.TENSOR_CORES, ops.GCN_FUSED = True, fused
 B, K, d, dff = 64, 100, 256, 384
