@@ -97,6 +97,39 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// ---- two CTAs per sample (TWO): distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void sts128_cluster(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquires the peer CTA's writes
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -182,7 +215,9 @@ struct Params {
   float* Y;            // [B, K, dff] or NULL
   __half* split_out;   // [B*K, 2*split_kp] = [hi | lo] of Y, or NULL
   int split_kp;
-  int B, K, d, dff, NS, k16, Kp;
+  int B, K, d, dff, NS, k16, Kp;   // k16 = K rounded up to 16: the depth of GEMM B
+  int Kt, kt16;        // rows of one CTA's tile (K, or K / 2 when two CTAs share a sample) and Kt rounded up to 16
+  int kb_ret;          // after this k-block of GEMM A the first X blocks are dead: A1 may land there
   float out_scale;     // 1 / (power-of-two scale of the split weights)
   float w_scale;       // that scale
   int a1_tma;          // A1[b] arrives as one bulk copy into the retired X blocks 0 and 1 (else: per-thread loads)
@@ -195,15 +230,19 @@ struct Params {
 // barrier indices (8 bytes each)
 constexpr int WRING = 4;                 // W ring: four slices of 32 k (see the TMA producer)
 enum { W_FULL = 0, W_EMPTY = 4, B_XRAW = 8, B_XF = 16, B_T1 = 20, B_T1S = 21, B_ACC = 22, B_OFREE = 23, B_XRET = 24,
-       B_A1RAW = 25, B_BIAS = 26, NUM_BARS = 32 };
+       B_A1RAW = 25, B_BIAS = 26, B_PEER = 27, NUM_BARS = 32 };
 
 struct Layout {
   uint32_t blk, x_bytes, wst, total;
 };
-__host__ __device__ inline Layout make_layout(int k16, int d, int NS) {
+// kt16: rows of the CTA's X tile (rounded up to 16); k16: depth of GEMM B = rows of the T1 tiles (== kt16 unless two CTAs
+// share a sample)
+__host__ __device__ inline Layout make_layout(int kt16, int k16, int d, int NS) {
   Layout L;
-  L.blk = (uint32_t)k16 * 256u;                                   // one X block: hi16 (k16 x 128 B) | hi8 | lo8 (k16 x 64 B each)
+  L.blk = (uint32_t)kt16 * 256u;                                  // one X block: hi16 (kt16 x 128 B) | hi8 | lo8 (kt16 x 64 B each)
   L.x_bytes = (uint32_t)(d / 64) * L.blk;
+  const uint32_t t1 = (uint32_t)(NS / 64) * (uint32_t)k16 * 256u; // T1 tiles: NS / 64 groups of hi | lo [k16 x 128 B]
+  if (L.x_bytes < t1) L.x_bytes = t1;
   // ... the region later holds A1 (raw) and the T1 tiles (NS <= d: they fit); the output tiles (4 NS k16 bytes) are built in
   // the W ring
   L.wst = (uint32_t)NS * 128u;                                    // one W slice (32 k): NS rows of [hi16 64 B | hi8 32 B | lo8 32 B]
@@ -266,36 +305,49 @@ __device__ __forceinline__ void conv_x_row(uint32_t blk, uint32_t TS, int r, int
   sts64(o8 + TS / 2, l8[0], l8[1]);
 }
 
+// TWO = false: one CTA per (sample, slice) item, K <= 128.
+// TWO = true : a cluster of two CTAs per item, K in (128, 256] (configs[4]: K = 200): CTA r owns rows [r K/2, (r+1) K/2) of
+//              the sample -- its X rows, its rows of A1 (all K columns, 2 x k16/2 TMEM columns), its rows of T0 / T1 / Y.
+//              GEMM B needs T1 of ALL rows: each CTA drains its T1 rows into BOTH CTAs' T1 tiles (st.shared::cluster), after
+//              the peer has signalled that its X region is dead (B_PEER), and GEMM B waits for both halves (B_T1S counts the
+//              sixteen local warps and the peer's sixteen).
+template <bool TWO>
 __global__ void __launch_bounds__(THREADS, 1)
 gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmS, Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const int K = p.K, d = p.d, NS = p.NS, k16 = p.k16;
+  const int K = p.K, d = p.d, NS = p.NS, k16 = p.k16, Kt = p.Kt, kt16 = p.kt16;
   const int ng = d / 64, nsg = NS / 64, ksteps = k16 / 16;
-  const Layout L = make_layout(k16, d, NS);
-  const uint32_t TS = (uint32_t)k16 * 128u;                        // one [k16 rows x 128 B] tile
+  const Layout L = make_layout(kt16, k16, d, NS);
+  const uint32_t TS = (uint32_t)kt16 * 128u;                       // one [kt16 rows x 128 B] tile (X, output)
+  const uint32_t TS2 = (uint32_t)k16 * 128u;                       // one [k16 rows x 128 B] T1 tile (== TS unless TWO)
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;              // which half of the sample's rows
+  const int row0 = (int)rank * Kt;                                 // first row of this CTA's tile within the sample
   const uint32_t xb = base, w0 = xb + L.x_bytes, misc = w0 + WRING * L.wst;
   auto bar = [&](int i) { return misc + 8u * i; };
   const uint32_t tmem_slot = misc + 8u * NUM_BARS;
   const uint32_t a0s_u = misc + 512u, bias_u = a0s_u + 1024u;        // a0 [2][128] floats; b0 [256], b1 [256] floats
   // TMEM columns
-  const uint32_t T0C = 0, T1C = (uint32_t)NS, A1H = 2u * NS, A1L = 2u * NS + 64u;
-  const bool early = nsg <= ng - 1;       // the T1 tiles fit the X blocks that are dead before the last T0 step retires
-  const int kb_ret = ng > 1 ? 1 : 0;      // after this k-block X blocks 0 (and 1) are dead: A1 may land there
+  const uint32_t T0C = 0, T1C = (uint32_t)NS, A1H = 2u * NS, A1L = 2u * NS + (uint32_t)k16 / 2u;
+  // the T1 tiles fit the X blocks that are dead before the last T0 step retires (never with a peer writing into them)
+  const bool early = !TWO && nsg <= ng - 1;
+  const int kb_ret = p.kb_ret;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int nslice = p.dff / NS, items = p.B * nslice;
-  const int cta = blockIdx.x;
+  const int cta = TWO ? (int)blockIdx.x / 2 : (int)blockIdx.x;     // worker (CTA or CTA pair) index
+  const int nworkers = TWO ? (int)gridDim.x / 2 : (int)gridDim.x;
   auto stamp = [&](int i) {
-    if (p.trace && cta < p.trace_n) p.trace[cta * 32 + i] = clock64();
+    if (p.trace && (int)blockIdx.x < p.trace_n) p.trace[blockIdx.x * 32 + i] = clock64();
   };
 
   if (tid == 0) {
     for (int g = 0; g < MAX_G; ++g) mbar_init(bar(B_XF + g), WORKERS / 32);
     mbar_init(bar(B_T1), 1);
-    mbar_init(bar(B_T1S), WORKERS / 32);
+    mbar_init(bar(B_T1S), (TWO ? 2 : 1) * (WORKERS / 32));
+    mbar_init(bar(B_PEER), WORKERS / 32);
     mbar_init(bar(B_ACC), 1);
     mbar_init(bar(B_OFREE), 1);
     mbar_init(bar(B_XRET), 1);
@@ -309,6 +361,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   auto setup_sync = [&]() -> uint32_t {
     tc_fence_before();
     asm volatile("bar.sync 0;" ::: "memory");
+    if (TWO) cluster_sync_all();           // the peer's barriers are initialised before any remote arrive
     tc_fence_after();
     pdl_launch_dependents();
     return *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
@@ -351,8 +404,8 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       bulk_load(bias_u + 1024u, p.bias2 + p.dff + n0, (uint32_t)NS * 4u, bar(B_BIAS));
       for (int g = 0; g < ng; ++g) {
         if (p.dbg & 1) { mbar_arrive(bar(B_XRAW + g)); continue; }
-        mbar_expect_tx(bar(B_XRAW + g), (uint32_t)K * 256u);
-        tma_load_2d(xb + (uint32_t)g * L.blk, &tmX, bar(B_XRAW + g), g * 64, b * K);
+        mbar_expect_tx(bar(B_XRAW + g), (uint32_t)Kt * 256u);
+        tma_load_2d(xb + (uint32_t)g * L.blk, &tmX, bar(B_XRAW + g), g * 64, b * K + row0);
       }
     };
     if (leader) {
@@ -373,7 +426,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     if (leader) {
       int it = 0;
       const int s_a1 = min(4 * (kb_ret + 1) + WRING, 4 * ng);      // slices that can go out before X blocks 0 / 1 retire
-      for (int item = cta; item < items; item += gridDim.x, ++it) {
+      for (int item = cta; item < items; item += nworkers, ++it) {
         const int n0 = (item % nslice) * NS, b = item / nslice;
         if (it > 0) {
           // the next item's X is requested as soon as the region is dead -- while the workers are still in the previous
@@ -390,8 +443,8 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           if (p.dbg & 1) {
             mbar_arrive(bar(B_A1RAW));
           } else {
-            mbar_expect_tx(bar(B_A1RAW), (uint32_t)(K * K) * 4u);
-            bulk_load(xb, p.adj + ((long long)b * 2 + 1) * K * K, (uint32_t)(K * K) * 4u, bar(B_A1RAW));
+            mbar_expect_tx(bar(B_A1RAW), (uint32_t)(Kt * K) * 4u);    // this CTA's rows of A1, all K columns
+            bulk_load(xb, p.adj + (((long long)b * 2 + 1) * K + row0) * K, (uint32_t)(Kt * K) * 4u, bar(B_A1RAW));
           }
         }
         for (int s = s_a1; s < 4 * ng; ++s) w_step(s, n0);
@@ -405,7 +458,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       uint32_t gs = 0;
       int it = 0;
       const uint32_t idesc_a = make_idesc(NS), idesc_b = make_idesc(NS) | (1u << 16);
-      for (int item = cta; item < items; item += gridDim.x, ++it) {
+      for (int item = cta; item < items; item += nworkers, ++it) {
         const uint32_t par = (uint32_t)it & 1u;
         for (int kb = 0; kb < ng; ++kb) {
           mbar_wait(bar(B_XF + kb), par);
@@ -437,12 +490,12 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           if (kb == kb_ret) umma_commit(bar(B_XRET));                // X blocks 0 .. kb_ret are dead
         }
         if (it == 0) stamp(16);
-        mbar_wait(bar(B_T1S), par);
+        if (TWO) mbar_wait_cluster(bar(B_T1S), par); else mbar_wait(bar(B_T1S), par);
         tc_fence_after();
         if (it == 0) stamp(17);
         {
           // GEMM B: D2[128 x NS] = A1 (TMEM, k16 deep) . T1 (MN-major rows v, NS columns in nsg tiles TS apart)
-          const uint64_t t_hi = make_desc_mn(xb, TS), t_lo = make_desc_mn(xb + (uint32_t)nsg * TS, TS);
+          const uint64_t t_hi = make_desc_mn(xb, TS2), t_lo = make_desc_mn(xb + (uint32_t)nsg * TS2, TS2);
           const uint32_t d2 = tmem_base + T1C, ah = tmem_base + A1H, al = tmem_base + A1L;
           for (int k = 0; k < ksteps; ++k) umma_ts(d2, al + 8 * k, t_hi + 128 * k, idesc_b, k ? 1u : 0u);
           for (int k = 0; k < ksteps; ++k) umma_ts(d2, ah + 8 * k, t_lo + 128 * k, idesc_b, 1u);
@@ -463,7 +516,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int cw = NS / 4, nsub = cw / 16;                           // columns per part, 16-column sub-chunks (<= 3)
     uint32_t ovf = 0;
     int it = 0;
-    for (int item = cta; item < items; item += gridDim.x, ++it) {
+    for (int item = cta; item < items; item += nworkers, ++it) {
       const uint32_t par = (uint32_t)it & 1u;
       const int b = item / nslice, n0 = (item % nslice) * NS;
       if (it == 0 && tid == 0) stamp(0);
@@ -499,20 +552,20 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // that each 128-bit load of a quarter-warp covers all 32 banks once)
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;   // rows >= K: zero
         const uint32_t sw = (uint32_t)(xc >> 2) * 16u;
-        if (xr0 < K) {
+        if (xr0 < Kt) {
           const float4 t0 = lds128f(blk + xr0 * 256 + xc * 32 + sw), t1 = lds128f(blk + xr0 * 256 + xc * 32 + (sw ^ 16u));
           v0 = sw ? t1 : t0;
           v1 = sw ? t0 : t1;
         }
-        if (xr0 + 64 < K) {
+        if (xr0 + 64 < Kt) {
           const float4 t0 = lds128f(blk + (xr0 + 64) * 256 + xc * 32 + sw), t1 = lds128f(blk + (xr0 + 64) * 256 + xc * 32 + (sw ^ 16u));
           v2 = sw ? t1 : t0;
           v3 = sw ? t0 : t1;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");   // every worker holds its part of the block
         if (it == 0 && tid == 0 && g == 0) stamp(20);
-        if (xr0 < k16) conv_x_row(blk, TS, xr0, xc, v0, v1, ovf);
-        if (xr0 + 64 < k16) conv_x_row(blk, TS, xr0 + 64, xc, v2, v3, ovf);
+        if (xr0 < kt16) conv_x_row(blk, TS, xr0, xc, v0, v1, ovf);
+        if (xr0 + 64 < kt16) conv_x_row(blk, TS, xr0 + 64, xc, v2, v3, ovf);
         if (it == 0 && tid == 0 && g == 0) stamp(21);
         proxy_fence();
         __syncwarp();
@@ -520,79 +573,103 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (it == 0 && tid == 0) stamp(1 + g);
       }
       // diagonal of plane 0 (used by the epilogue; the load latency hides behind the wait for A1)
-      if (tid < 128) sts32f(a0s_u + par * 512u + (uint32_t)tid * 4u, tid < K ? __ldg(p.adj + (long long)b * 2 * K * K + (long long)tid * K + tid) : 0.f);
-      // ---- A1 row of this thread: k range [32 part, +32), zero beyond K -> TMEM, packed fp16 pairs (k = 2j, 2j+1 in
-      // column j of the hi / lo ranges)
-      {
+      if (tid < 128)
+        sts32f(a0s_u + par * 512u + (uint32_t)tid * 4u,
+               tid < Kt ? __ldg(p.adj + (long long)b * 2 * K * K + (long long)(row0 + tid) * K + row0 + tid) : 0.f);
+      // ---- A1 row of this thread -> TMEM, packed fp16 pairs (k = 2j, 2j+1 in column j of the hi / lo ranges), zero beyond
+      // K.  A part covers 32 k (K <= 128) or 64 k in two rounds (TWO: K <= 256).
+      if (p.a1_tma) mbar_wait(bar(B_A1RAW), par);
+#pragma unroll 1
+      for (int rd = 0; rd < (TWO ? 2 : 1); ++rd) {
+        const int kq = (TWO ? 64 : 32) * part + 32 * rd;              // first k of this round
         float av[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) av[j] = 0.f;
         if (p.a1_tma) {
-          mbar_wait(bar(B_A1RAW), par);
-          if (row < K && !(p.dbg & 1)) {
-            const uint32_t src = xb + (uint32_t)(row * K + part * 32) * 4u;   // raw rows of K floats
+          if (row < Kt && !(p.dbg & 1)) {
+            const uint32_t src = xb + (uint32_t)(row * K + kq) * 4u;   // raw rows of K floats
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (part * 32 + 4 * j < K) {
+              if (kq + 4 * j < K) {
                 const float4 t = lds128f(src + 16u * j);
                 av[4 * j] = t.x; av[4 * j + 1] = t.y; av[4 * j + 2] = t.z; av[4 * j + 3] = t.w;
               }
           }
-        } else if (row < K && !(p.dbg & 1)) {
-          const float* src = p.adj + ((long long)b * 2 + 1) * K * K + (long long)row * K + part * 32;
+        } else if (row < Kt && !(p.dbg & 1)) {
+          const float* src = p.adj + (((long long)b * 2 + 1) * K + row0 + row) * K + kq;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (part * 32 + j < K) av[j] = __ldg(src + j);
+            if (kq + j < K) av[j] = __ldg(src + j);
         }
+        if (kq < k16) {                                                // (warp-uniform) columns beyond k16 / 2 do not exist
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {          // 16 k values = one k-step = 8 columns at a time
-          uint32_t hi[8], lo[8];
+          for (int hf = 0; hf < 2; ++hf) {        // 16 k values = one k-step = 8 columns at a time
+            if (kq + 16 * hf >= k16) break;
+            uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) split_pair(av[16 * hf + 2 * j], av[16 * hf + 2 * j + 1], hi[j], lo[j]);
-          tmem_st8_nowait(t_row + A1H + 16u * part + 8u * hf, hi);
-          tmem_st8_nowait(t_row + A1L + 16u * part + 8u * hf, lo);
+            for (int j = 0; j < 8; ++j) split_pair(av[16 * hf + 2 * j], av[16 * hf + 2 * j + 1], hi[j], lo[j]);
+            tmem_st8_nowait(t_row + A1H + (uint32_t)(kq / 2 + 8 * hf), hi);
+            tmem_st8_nowait(t_row + A1L + (uint32_t)(kq / 2 + 8 * hf), lo);
+          }
         }
-        tmem_st_wait();
       }
+      tmem_st_wait();
       // every warp has read its part of the raw A1 before anybody writes T1 tiles over it
       asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
       if (it == 0 && tid == 0) stamp(5);
-      // ---- drain T1 (scaled back by 1 / w_scale) into MN-major tiles [v][64 n]: hi tiles [0, nsg), lo tiles [nsg, 2 nsg)
+      // ---- drain T1 (scaled back by 1 / w_scale) into MN-major tiles [v][64 n]: hi tiles [0, nsg), lo tiles [nsg, 2 nsg),
+      // k16 rows each; this CTA's rows are v = row0 + row (TWO: written into the peer's tiles as well); rows [K, k16) zero
       mbar_wait(bar(B_T1), par);
       tc_fence_after();
       if (it == 0 && tid == 0) stamp(6);
+      if (TWO) {
+        // the peer's X region (raw A1, X tiles) is dead once ITS sixteen warps have got here
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa(bar(B_PEER), rank ^ 1u));
+        mbar_wait_cluster(bar(B_PEER), par);
+      }
       {
         float r[3][16];
 #pragma unroll
         for (int sc = 0; sc < 3; ++sc)
           if (sc < nsub) tmem_ld16_nowait(t_row + T1C + (uint32_t)(part * cw + sc * 16), r[sc]);
         tmem_ld_wait();
-        if (row < k16) {
+        // rows of data, plus (last CTA of the sample) the zero rows that pad K to k16
+        const bool data = row < Kt, pad = (!TWO || rank == 1u) && row >= Kt && row0 + row < k16;
+        if (data || pad) {
 #pragma unroll
           for (int sc = 0; sc < 3; ++sc) {
             if (sc >= nsub) break;
             const int col = part * cw + sc * 16;
-            const uint32_t tile = xb + (uint32_t)(col >> 6) * TS;
+            const uint32_t tile = xb + (uint32_t)(col >> 6) * TS2;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint32_t h[4], l[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float v0 = row < K ? r[sc][8 * i + 2 * j] * p.out_scale : 0.f;
-                const float v1 = row < K ? r[sc][8 * i + 2 * j + 1] * p.out_scale : 0.f;
+                const float v0 = data ? r[sc][8 * i + 2 * j] * p.out_scale : 0.f;
+                const float v1 = data ? r[sc][8 * i + 2 * j + 1] * p.out_scale : 0.f;
                 split_pair(v0, v1, h[j], l[j]);
               }
-              const uint32_t off = tile + swz128(row, ((col & 63) >> 3) + i);
+              const uint32_t off = tile + swz128(row0 + row, ((col & 63) >> 3) + i);
               sts128(off, h[0], h[1], h[2], h[3]);
-              sts128(off + (uint32_t)nsg * TS, l[0], l[1], l[2], l[3]);
+              sts128(off + (uint32_t)nsg * TS2, l[0], l[1], l[2], l[3]);
+              if (TWO) {
+                const uint32_t roff = mapa(off, rank ^ 1u);
+                sts128_cluster(roff, h[0], h[1], h[2], h[3]);
+                sts128_cluster(roff + (uint32_t)nsg * TS2, l[0], l[1], l[2], l[3]);
+              }
             }
           }
         }
       }
-      proxy_fence();
+      if (TWO) asm volatile("fence.proxy.async;" ::: "memory"); else proxy_fence();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_T1S));
+      if (lane == 0) {
+        mbar_arrive(bar(B_T1S));
+        if (TWO) mbar_arrive_remote(mapa(bar(B_T1S), rank ^ 1u));
+      }
       if (it == 0 && tid == 0) stamp(7);
       // ---- epilogue: this thread owns row `row` and columns [part NS/4, +NS/4) of the slice: y = relu(a0 T0 / w_scale + D2).
       // Results are assembled in shared memory (the X / T1 region) as 128-byte-row, 128B-swizzled tiles -- 32 fp32 or 64
@@ -621,7 +698,7 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           tmem_ld16_nowait(t_row + T0C + (uint32_t)col0, t0);
           tmem_ld16_nowait(t_row + T1C + (uint32_t)col0, d2);
           tmem_ld_wait();
-          if (row < K) {
+          if (row < Kt) {
             float y[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) y[j] = fmaxf(fmaf(t0[j], sa, d2[j]), 0.f);
@@ -648,11 +725,11 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           if (warp == 0 && elect_one()) {
             if (!(p.dbg & 2)) {
               if (pass == 0) {
-                tma_store_2d(&tmY, w0 + (uint32_t)(2 * sc) * TS, n0 + 64 * sc, b * K);
-                tma_store_2d(&tmY, w0 + (uint32_t)(2 * sc + 1) * TS, n0 + 64 * sc + 32, b * K);
+                tma_store_2d(&tmY, w0 + (uint32_t)(2 * sc) * TS, n0 + 64 * sc, b * K + row0);
+                tma_store_2d(&tmY, w0 + (uint32_t)(2 * sc + 1) * TS, n0 + 64 * sc + 32, b * K + row0);
               } else {
-                tma_store_2d(&tmS, w0 + (uint32_t)sc * TS, n0 + 64 * sc, b * K);
-                tma_store_2d(&tmS, w0 + (uint32_t)(nsg + sc) * TS, p.split_kp + n0 + 64 * sc, b * K);
+                tma_store_2d(&tmS, w0 + (uint32_t)sc * TS, n0 + 64 * sc, b * K + row0);
+                tma_store_2d(&tmS, w0 + (uint32_t)(nsg + sc) * TS, p.split_kp + n0 + 64 * sc, b * K + row0);
               }
             }
             bulk_commit();
@@ -678,23 +755,43 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   if (threadIdx.x == 0) stamp(11);
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();             // the peer's last remote stores / arrives have landed before this CTA's memory goes
   if (warp == WORKERS / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 constexpr uint32_t SMEM_LIMIT = 227u * 1024u;
 
-// slice width for (K, d, dff), or 0 when this kernel cannot take the shape
-inline int pick_slice(int K, int d, int dff) {
-  if (K < 1 || K > 128 || (d != 64 && d != 128 && d != 256) || dff % 64) return 0;
-  const int k16 = (K + 15) / 16 * 16;
+// Shape plan: slice width NS (0 = this kernel cannot take the shape), one or two CTAs per (sample, slice) item and the
+// row / depth geometry that follows.
+struct Plan {
+  int NS, two, Kt, kt16, k16, kb_ret, a1_tma;
+};
+inline Plan make_plan(int K, int d, int dff) {
+  Plan pl = {0, 0, 0, 0, 0, 0, 0};
+  if (K < 1 || K > 256 || (d != 64 && d != 128 && d != 256) || dff % 64) return pl;
+  const int two = K > 128;
+  if (two && (K % 8 != 0)) return pl;                               // two equal row tiles whose rows start 16-byte aligned
+  const int Kt = two ? K / 2 : K;
+  const int kt16 = (Kt + 15) / 16 * 16, k16 = (K + 15) / 16 * 16;
   const int cand[3] = {192, 128, 64};
   for (int i = 0; i < 3; ++i) {
     const int NS = cand[i];
-    if (dff % NS || NS > d) continue;                               // the T1 tiles (NS x k16 x 4 B) live in the X region
-    if (make_layout(k16, d, NS).total + 1024u <= SMEM_LIMIT) return NS;
+    if (dff % NS || NS > d) continue;                               // (single CTA: the T1 tiles live in the X region, NS <= d)
+    if (2 * NS + k16 > 512) continue;                               // TMEM: T0 | T1 | A1 hi | A1 lo
+    const Layout L = make_layout(kt16, k16, d, NS);
+    if (L.total + 1024u > SMEM_LIMIT) continue;
+    pl.NS = NS; pl.two = two; pl.Kt = Kt; pl.kt16 = kt16; pl.k16 = k16;
+    // A1 (this CTA's Kt rows x K columns, raw fp32) lands in the first X blocks once GEMM A has consumed them
+    const int ng = d / 64;
+    const uint32_t a1_bytes = (uint32_t)Kt * (uint32_t)K * 4u;
+    int kb = (int)((a1_bytes + L.blk - 1) / L.blk) - 1;
+    pl.a1_tma = (K % 4 == 0) && kb <= ng - 1;
+    pl.kb_ret = pl.a1_tma ? (kb < 0 ? 0 : kb) : 0;
+    return pl;
   }
-  return 0;
+  return pl;
 }
+inline int pick_slice(int K, int d, int dff) { return make_plan(K, d, dff).NS; }
 
 static int sm_count() {
   constexpr int MAX_DEV = 64;
@@ -736,45 +833,65 @@ extern "C" int ec_gcn_fused2_slice(int K, int d, int dff) { return gf2::pick_sli
 extern "C" int ec_gcn_fused2(const float* X, const float* adj, const float* bias2, const void* W3, int Kp, float w_scale,
                              float* Y, void* split_out, int split_kp, int B, int K, int d, int dff, void* stream) {
   EC_REQUIRE(X && adj && bias2 && W3 && (Y || split_out), "ec_gcn_fused2: null pointer");
-  const int NS = gf2::pick_slice(K, d, dff);
-  EC_REQUIRE(NS > 0, "ec_gcn_fused2: unsupported shape (K <= 128, d in {64,128,256}, dff %% 64 == 0, shared memory)");
+  const gf2::Plan pl = gf2::make_plan(K, d, dff);
+  const int NS = pl.NS;
+  EC_REQUIRE(NS > 0, "ec_gcn_fused2: unsupported shape (K <= 128, or K <= 256 and a multiple of 8; d in {64,128,256}; dff %% 64 == 0; shared memory / TMEM)");
   EC_REQUIRE(Kp % 64 == 0 && Kp >= 2 * d, "ec_gcn_fused2: Kp must be a multiple of 64 and >= 2d");
   EC_REQUIRE(w_scale > 0.f, "ec_gcn_fused2: bad weight scale");
   EC_REQUIRE(aligned16(X) && aligned16(adj) && aligned16(W3) && aligned16(bias2) && (!Y || aligned16(Y)) && (!split_out || aligned16(split_out)),
              "ec_gcn_fused2: operands must be 16-byte aligned");
   EC_REQUIRE(!split_out || (split_kp % 8 == 0 && split_kp >= dff), "ec_gcn_fused2: bad split_kp");
   if (B == 0) return EC_OK;
-  const int k16 = (K + 15) / 16 * 16;
-  const uint32_t smem = gf2::make_layout(k16, d, NS).total + 1024u;
-  EC_CUDA((cudaError_t)ensure_dynamic_smem(gf2::gcn_fused2_kernel, (int)gf2::SMEM_LIMIT));
+  const uint32_t smem = gf2::make_layout(pl.kt16, pl.k16, d, NS).total + 1024u;
+  EC_CUDA((cudaError_t)ensure_dynamic_smem(gf2::gcn_fused2_kernel<false>, (int)gf2::SMEM_LIMIT));
+  EC_CUDA((cudaError_t)ensure_dynamic_smem(gf2::gcn_fused2_kernel<true>, (int)gf2::SMEM_LIMIT));
   CUtensorMap tmW, tmX, tmY, tmS;
   int rc = tc::get_tensor_map_slice32(W3, dff, Kp, NS, &tmW);
   if (rc) return rc;
-  rc = tc::get_tensor_map_f32(X, (long long)B * K, d, K, 64, false, &tmX);   // one box = the K rows of a sample x 64 channels
+  rc = tc::get_tensor_map_f32(X, (long long)B * K, d, pl.Kt, 64, false, &tmX);   // one box = a CTA's rows of a sample x 64 channels
   if (rc) return rc;
   tmY = tmS = tmX;
   if (Y) {
-    rc = tc::get_tensor_map_f32(Y, (long long)B * K, dff, K, 32, true, &tmY);
+    rc = tc::get_tensor_map_f32(Y, (long long)B * K, dff, pl.Kt, 32, true, &tmY);
     if (rc) return rc;
   }
   if (split_out) {
     EC_REQUIRE(split_kp % 64 == 0, "ec_gcn_fused2: split_kp must be a multiple of 64");
-    rc = tc::get_tensor_map(split_out, B * K, split_kp, K, &tmS);
+    rc = tc::get_tensor_map(split_out, B * K, split_kp, pl.Kt, &tmS);
     if (rc) return rc;
   }
   gf2::Params p;
   p.X = X; p.adj = adj; p.bias2 = bias2; p.Y = Y; p.split_out = (__half*)split_out; p.split_kp = split_kp;
-  p.B = B; p.K = K; p.d = d; p.dff = dff; p.NS = NS; p.k16 = k16; p.Kp = Kp; p.out_scale = 1.0f / w_scale; p.w_scale = w_scale;
-  const int kb_ret = d / 64 > 1 ? 1 : 0;
-  p.a1_tma = (K % 4 == 0) && (uint32_t)(kb_ret + 1) * gf2::make_layout(k16, d, NS).blk >= (uint32_t)(K * K) * 4u;
+  p.B = B; p.K = K; p.d = d; p.dff = dff; p.NS = NS; p.k16 = pl.k16; p.Kp = Kp; p.out_scale = 1.0f / w_scale; p.w_scale = w_scale;
+  p.Kt = pl.Kt; p.kt16 = pl.kt16; p.kb_ret = pl.kb_ret; p.a1_tma = pl.a1_tma;
   p.overflow = overflow_counters();
   if (!p.overflow) return EC_ERR_CUDA;
   p.trace = gf2_trace; p.trace_n = gf2_trace_n; p.dbg = gf2_debug;
   const int sms = gf2::sm_count();
   EC_REQUIRE(sms > 0, "ec_gcn_fused2: no current CUDA device");
   const int items = B * (dff / NS);
-  int grid = items < sms ? items : sms;
-  if (gf2_cta_limit > 0 && grid > gf2_cta_limit) grid = gf2_cta_limit;
-  launch_pdl(gf2::gcn_fused2_kernel, dim3(grid), dim3(gf2::THREADS), (size_t)smem, (cudaStream_t)stream, tmW, tmX, tmY, tmS, p);
+  if (!pl.two) {
+    int grid = items < sms ? items : sms;
+    if (gf2_cta_limit > 0 && grid > gf2_cta_limit) grid = gf2_cta_limit;
+    launch_pdl(gf2::gcn_fused2_kernel<false>, dim3(grid), dim3(gf2::THREADS), (size_t)smem, (cudaStream_t)stream, tmW, tmX, tmY, tmS, p);
+  } else {
+    int pairs = items < sms / 2 ? items : sms / 2;
+    if (gf2_cta_limit > 1 && pairs > gf2_cta_limit / 2) pairs = gf2_cta_limit / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(gf2::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    EC_CUDA(cudaLaunchKernelEx(&cfg, gf2::gcn_fused2_kernel<true>, tmW, tmX, tmY, tmS, p));
+  }
   return check_launch("ec_gcn_fused2");
 }

@@ -128,10 +128,10 @@ class _GraphedForward:
         # pipeline: pre-launched dependents sit on SMs (a GEMM CTA holds 213 KB of shared memory) while they wait, which
         # keeps the other stream's kernels out -- both graphs concurrently: 7.98 ms with PDL in the head graph, 7.25 ms
         # without.  test_cfg['pdl'] = 'none' (default) | 'head' | 'all'; EDGECAPE_PDL=0 forces none.
-        pdl = str(model.test_cfg.get("pdl", "none"))
+        pdl = str(os.environ.get("EDGECAPE_PDL_GRAPHS", model.test_cfg.get("pdl", "none")))     # ... | 'vit' (backbone graph only)
         env_off = os.environ.get("EDGECAPE_PDL", "1") == "0"
         for s in self.slots:
-            _lib.call("ec_set_pdl", int(pdl == "all" and not env_off))
+            _lib.call("ec_set_pdl", int(pdl in ("all", "vit") and not env_off))
             s.graph_vit = torch.cuda.CUDAGraph()
             with torch.cuda.graph(s.graph_vit, stream=self._capture_lo):
                 s.feat_q, s.feats_s = model.extract_features(s.img_s, s.img_q, s.inv)

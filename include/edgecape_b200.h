@@ -308,7 +308,9 @@ int ec_gcn_fused(const float* X, const float* adj, const float* Wp, const void* 
  * persistent CTAs over (sample, channel slice) items.  Arguments as ec_gcn_fused except that bias2 [2][dff] holds the
  * bias columns of Wp contiguously (b0 then b1; they are preloaded into the accumulators) and W3 [dff, 4*Kp bytes]
  * is the F16F8 B-role form of Wp * w_scale with its planes interleaved per 32 columns (ec_split_f16f8 with
- * role 2): the weights stream in 32-deep k-slices.  Same shape gate (ec_gcn_fused2_slice). */
+ * role 2): the weights stream in 32-deep k-slices.  Shape gate ec_gcn_fused2_slice: K <= 128 (one CTA per sample and
+ * channel slice), or K <= 256 and a multiple of 8 (a cluster of two CTAs, each owning half of the sample's rows: configs[4],
+ * K = 200); d in {64, 128, 256}; dff a multiple of 64. */
 int ec_gcn_fused2_slice(int K, int d, int dff);
 int ec_gcn_fused2_set_debug(int flags);               /* profiling experiments only: 1 = skip the A1 / X loads, 2 = skip the stores */
 int ec_gcn_fused2_set_trace(void* buf, int n_ctas);   /* profiling: [n_ctas][32] int64 clock stamps of each CTA's first item */

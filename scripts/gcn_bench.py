@@ -49,6 +49,12 @@ if __name__ == "__main__":
         for B in (64, 16, 74, 148, 2048):
             run(B, 100, 256, 384, True, iters=50 if B < 1000 else 5, fused=fused)
         run(64, 100, 256, 768, True, fused=fused)
+    if "--k200" in sys.argv:      # configs[4]: 200 keypoints -- clusters of two CTAs vs the two-launch path
+        for B in (4, 32, 256):
+            for fused in (2, 0):
+                run(B, 200, 256, 384, True, iters=20, fused=fused)
+        for fused in (2, 0):
+            run(4, 200, 256, 1024, True, iters=20, fused=fused)
     if "--fused-only" in sys.argv:
         sys.exit(0)
     for tc in (True, False):

@@ -38,6 +38,15 @@ def test_fused_gcn_shape_gate():
     assert lib.ec_gcn_fused_slice(200, 256, 384) == 0         # configs[4]: K > 128
     assert lib.ec_gcn_fused_slice(100, 192, 384) == 0         # d must be 64, 128 or 256
     assert lib.ec_gcn_fused_slice(100, 256, 100) == 0
+    # the project-first kernel (the default): one CTA per item up to K = 128, a cluster of two CTAs up to K = 256
+    assert lib.ec_gcn_fused2_slice(100, 256, 384) == 192
+    assert lib.ec_gcn_fused2_slice(100, 256, 1024) == 128
+    assert lib.ec_gcn_fused2_slice(128, 256, 384) == 128
+    assert lib.ec_gcn_fused2_slice(200, 256, 384) == 128      # configs[4]: two CTAs of 100 rows, TMEM 2 x 128 + 208 columns
+    assert lib.ec_gcn_fused2_slice(256, 256, 384) == 128
+    assert lib.ec_gcn_fused2_slice(204, 256, 384) == 0        # K > 128 must be a multiple of 8
+    assert lib.ec_gcn_fused2_slice(300, 256, 384) == 0
+    assert lib.ec_gcn_fused2_slice(100, 192, 384) == 0
 
 
 def test_registries_hold_the_reference_names():
