@@ -357,32 +357,20 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // CTA-wide setup barrier (executed inside each role's branch; bar.sync 0 counts arrivals wherever they come from)
-  auto setup_sync = [&]() -> uint32_t {
-    tc_fence_before();
-    asm volatile("bar.sync 0;" ::: "memory");
-    if (TWO) cluster_sync_all();           // the peer's barriers are initialised before any remote arrive
-    tc_fence_after();
-    pdl_launch_dependents();
-    return *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
-  };
-  uint32_t tmem_base = 0;
-
-  if (warp == WORKERS / 32 + 1) {
-    // ------------------------------------------------------------------ TMA producer: raw X blocks, A1, the W ring
-    // X[b] arrives as ng raw fp32 blocks [K rows x 64 channels] (256-byte rows), each INTO the region its converted
-    // tiles will occupy (4 bytes per element either way); the workers read a block into registers, synchronise and
-    // write the tiles over it.  No thread holds X in registers across a global-memory latency, and all of X is in
-    // flight at once.  (Loaded through registers with a two-block ring the values were spilled, and each spill store
-    // waited for its load: the blocks arrived one latency apart, profiles/r03_gcn2_development.md.)
-    const bool leader = elect_one();
-    uint32_t gs = 0;
-    // W streams in slices of 32 k through a ring of four (24 KB each at NS = 192): with two 48 KB stages of 64 k a
-    // stage could only be re-requested when its UMMAs had retired, i.e. one request in flight per SM against an L2
-    // latency of ~1.4 K clk -- 1.2 K clk per 784 clk of math (profiles/r03_gcn2_development.md).  A slice is ONE box with
-    // 128-byte rows [hi16 x 32 | hi8 x 32 | lo8 x 32] (the weights are packed with the planes interleaved per 32 columns:
-    // ec_split_f16f8, role 2).
-    auto w_step = [&](int s, int n0) {
+  // ------------------------------------------------------------------ TMA producer (warp 17): raw X blocks, A1, the W ring
+  // X[b] arrives as ng raw fp32 blocks [K rows x 64 channels] (256-byte rows), each INTO the region its converted
+  // tiles will occupy (4 bytes per element either way); the workers read a block into registers, synchronise and
+  // write the tiles over it.  No thread holds X in registers across a global-memory latency, and all of X is in
+  // flight at once.  (Loaded through registers with a two-block ring the values were spilled, and each spill store
+  // waited for its load: the blocks arrived one latency apart, profiles/r03_gcn2_development.md.)
+  bool leader = false;                     // (TMA warp) the elected lane
+  uint32_t gs = 0;                         // (TMA warp) W slices requested so far
+  // W streams in slices of 32 k through a ring of four (24 KB each at NS = 192): with two 48 KB stages of 64 k a
+  // stage could only be re-requested when its UMMAs had retired, i.e. one request in flight per SM against an L2
+  // latency of ~1.4 K clk -- 1.2 K clk per 784 clk of math (profiles/r03_gcn2_development.md).  A slice is ONE box with
+  // 128-byte rows [hi16 x 32 | hi8 x 32 | lo8 x 32] (the weights are packed with the planes interleaved per 32 columns:
+  // ec_split_f16f8, role 2).
+  auto w_step = [&](int s, int n0) {
       const int kb = s >> 2, hh = (s >> 1) & 1, sub = s & 1, half = (kb == ng - 1) ? 1 - hh : hh;
       const int st = (int)(gs & (WRING - 1));
       if (gs >= WRING) mbar_wait(bar(W_EMPTY + st), ((gs / WRING) - 1u) & 1u);
@@ -408,6 +396,10 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         tma_load_2d(xb + (uint32_t)g * L.blk, &tmX, bar(B_XRAW + g), g * 64, b * K + row0);
       }
     };
+  if (warp == WORKERS / 32 + 1) {
+    // before the CTA-wide setup barrier: the TMA thread initialises its own barriers and requests the first item's
+    // operands, so their latency overlaps the TMEM allocation and the barrier
+    leader = elect_one();
     if (leader) {
       for (int s = 0; s < WRING; ++s) { mbar_init(bar(W_FULL + s), 1); mbar_init(bar(W_EMPTY + s), 1); }
       for (int g = 0; g < MAX_G; ++g) mbar_init(bar(B_XRAW + g), 1);
@@ -422,7 +414,16 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       }
     }
     __syncwarp();
-    setup_sync();
+  }
+  // CTA-wide setup barrier
+  tc_fence_before();
+  __syncthreads();
+  if (TWO) cluster_sync_all();             // the peer's barriers are initialised before any remote arrive
+  tc_fence_after();
+  pdl_launch_dependents();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+
+  if (warp == WORKERS / 32 + 1) {
     if (leader) {
       int it = 0;
       const int s_a1 = min(4 * (kb_ret + 1) + WRING, 4 * ng);      // slices that can go out before X blocks 0 / 1 retire
@@ -452,7 +453,6 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   } else if (warp == WORKERS / 32) {
     // ------------------------------------------------------------------ MMA issuer
-    tmem_base = setup_sync();
     pdl_wait();
     if (elect_one()) {
       uint32_t gs = 0;
@@ -508,7 +508,6 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   } else {
     // ------------------------------------------------------------------ workers (16 warps)
     pdl_wait();
-    tmem_base = setup_sync();
     const int quarter = warp & 3, part = warp >> 2;                 // TMEM lane quarter; column part
     const int row = quarter * 32 + lane;                             // this thread's TMEM lane = matrix row
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
