@@ -153,6 +153,39 @@ def test_f16f8_planes_reconstruct_and_layernorm_writes_them():
     assert torch.equal(so_ln.data.view(torch.uint8), want.data.view(torch.uint8))
 
 
+def _interleave32(std, Kp):
+    """role-1 rows [hi16 | hi8 | lo8] -> role-2 rows: 128 bytes per 32-column slice, [hi16 x 32 | hi8 x 32 | lo8 x 32]."""
+    M = std.shape[0]
+    h16 = std[:, :2 * Kp].reshape(M, Kp // 32, 64)
+    h8 = std[:, 2 * Kp:3 * Kp].reshape(M, Kp // 32, 32)
+    l8 = std[:, 3 * Kp:].reshape(M, Kp // 32, 32)
+    return torch.cat((h16, h8, l8), dim=2).reshape(M, 4 * Kp)
+
+
+def test_interleaved_weight_rows_on_the_emulated_abi(monkeypatch):
+    """ec_split_f16f8 role 2 (the weight format of ec_gcn_fused2: planes interleaved per 32 columns) holds the bytes of
+    role 1, re-ordered."""
+    cpu_emulator.install(monkeypatch)
+    _, w, _ = _case(K=200, N=72)
+    std = ops.split_f16(w, 1024.0, fmt=ops.F16F8, role=1)
+    il = ops.split_f16(w, 1024.0, fmt=ops.F16F8_I32, role=1)
+    assert il.Kp == std.Kp
+    a = std.data.view(torch.uint8).view(72, 4 * std.Kp)
+    b = il.data.view(torch.uint8).view(72, 4 * std.Kp)
+    assert torch.equal(b, _interleave32(a, std.Kp))
+
+
+@pytest.mark.gpu
+def test_interleaved_weight_rows_hold_the_same_bytes():
+    """ec_split_f16f8 role 2 on the device: bit-identical to the role-1 rows re-ordered per 32-column slice."""
+    w = (torch.randn(384, 516, generator=torch.Generator().manual_seed(5)) * 0.05).cuda()
+    std = ops.split_f16(w, 4096.0, fmt=ops.F16F8, role=1)
+    il = ops.split_f16(w, 4096.0, fmt=ops.F16F8_I32, role=1)
+    a = std.data.view(torch.uint8).view(384, 4 * std.Kp)
+    b = il.data.view(torch.uint8).view(384, 4 * std.Kp)
+    assert torch.equal(b, _interleave32(a, std.Kp))
+
+
 @pytest.mark.gpu
 def test_f16f8_range_events_are_counted_and_degrade_gracefully():
     """An activation beyond 448 (e4m3 saturates) only loses its cross terms: the result stays within plain-fp16
