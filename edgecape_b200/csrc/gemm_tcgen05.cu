@@ -343,7 +343,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t ph = (uint32_t)(j / RING - 1) & 1u;
             if (TWO) mbar_wait_cluster(ring_empty(r), ph); else mbar_wait(ring_empty(r), ph);
           }
-          tile = p.sched ? atomicAdd(p.sched, 1) : worker + j * num_workers;
+          // dynamic scheduling from the SECOND tile on: the first one is the worker's own index (a launch with dynamic tiles has
+          // more tiles than workers), so no global atomic round trip sits in front of the first TMA load
+          tile = (p.sched && j > 0) ? num_workers + atomicAdd(p.sched, 1) : worker + j * num_workers;
           if (tile >= num_tiles) tile = -1;
           ring_tile_ptr[r] = tile;
           if (TWO) st_shared_cluster(mapa(ring_tile + 4u * r, 1), tile);
