@@ -815,6 +815,11 @@ template <bool HOP>
 __global__ void __launch_bounds__(THREADS_TS, 1)
 attention_tc_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, ParamsT p) {
+  if (threadIdx.x == 64) {   // the TMA unit fetches a descriptor on its first use: start those fetches now
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -1248,6 +1253,13 @@ attention_tc_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKp,
                        const __grid_constant__ CUtensorMap tmVp, ParamsP pp) {
   const ParamsT& p = pp.t;
+  if (threadIdx.x == 64) {   // the TMA unit fetches a descriptor on its first use: start those fetches now
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKp) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVp) : "memory");
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));

@@ -353,6 +353,13 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     mbar_init(bar(B_XRET), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid == 32) {
+    // the TMA unit fetches a descriptor on its first use: start those fetches now
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    if (p.Y) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    if (p.split_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
+  }
   if (warp == WORKERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");

@@ -294,6 +294,19 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int m_tiles = (p.M + TM - 1) / TM, n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
 
+  if (warp == 0 && lane == 1) {
+    // the TMA unit fetches a descriptor on its first use: start those fetches now, under the barrier set-up
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (F8) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA8) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB8) : "memory");
+    }
+    if (p.split_tma) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO16) : "memory");
+      if (p.split_fmt == EC_SPLIT_F16F8) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO8) : "memory");
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (TWO ? 2 : 1) * EPI_WARPS); }
