@@ -32,7 +32,7 @@
 // [2 NS, +64), A1 lo [2 NS + 64, +64).  The worker branch runs at the 96-register limit of an 18-warp CTA and shared memory
 // takes nearly all of the L1: a spill in a hot path costs an L2 round trip (profiles/r03_gcn2_development.md, steps 2 / 5),
 // which is why the fill is single buffered and shared memory is addressed by 32-bit shared addresses.
-// Measured: 13.1 us at B = 64 (aggregate-first kernel 15.3), 318 us at B = 2048 (455): 0.23 / 0.29 of the HBM roofline.
+// Measured: 12.3 us at B = 64 (aggregate-first kernel 15.3), 298 us at B = 2048 (455): 0.24 / 0.31 of the HBM roofline.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -414,10 +414,10 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       mbar_init(bar(B_BIAS), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       pdl_wait();
-      if (cta < items) {                   // the first item's loads go out before the CTA has finished setting up
-        const int n0 = (cta % nslice) * NS;
-        for (int s = 0; s < WRING; ++s) w_step(s, n0);
+      if (cta < items) {                   // the first item's loads go out before the CTA has finished setting up:
+        const int n0 = (cta % nslice) * NS;   // X (from HBM, and converted before it is of use) ahead of W (from L2)
         x_loads(0, cta / nslice, n0);
+        for (int s = 0; s < WRING; ++s) w_step(s, n0);
       }
     }
     __syncwarp();
@@ -754,7 +754,8 @@ gcn_fused2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       }
       if (it == 0 && tid == 0) stamp(10);
     }
-    if (warp == 0 && elect_one()) bulk_wait_all();
+    // (the last stores have been waited for as far as their READS of shared memory go -- B_OFREE above; their writes are
+    // complete when the grid is)
     __syncwarp();
     report_overflow(p.overflow, ovf);
   }

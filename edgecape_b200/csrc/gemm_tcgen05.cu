@@ -843,7 +843,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     report_overflow(p.overflow, ovf);
-    if (p.split_tma && warp == 2) tma_store_wait_all();   // the issuing thread's bulk stores have been written
+    // the issuing thread's bulk stores have READ their shared-memory tiles (their writes are complete when the grid is)
+    if (p.split_tma && warp == 2) tma_store_wait_read();
   }
   tc_fence_before();
   if (TWO) cluster_sync(); else __syncthreads();   // the peer's shared memory / barriers stay alive until both are done
