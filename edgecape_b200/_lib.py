@@ -35,6 +35,8 @@ SIGNATURES = {
     "ec_tc_set_split_tma": (c_int, [c_int]),
     "ec_tc_set_trace": (c_int, [c_fp]),
     "ec_tc_set_dynamic": (c_int, [c_int]),
+    "ec_tc_set_ksplit": (c_int, [c_int]),
+    "ec_tc_ksplit_launches": (c_ll, []),
     "ec_set_pdl": (c_int, [c_int]),
     "ec_tc_set_debug": (c_int, [c_int]),
     "ec_attention_tc_set_trace": (c_int, [c_fp, c_int]),

@@ -162,6 +162,13 @@ struct TcParams {
   long long* trace;    // profiling (ec_tc_set_trace): per leader CTA {MMA thread total clk, clk waiting for an accumulator, clk waiting for operands, tiles}
   int split_tma;       // split_out is the only output: the epilogue assembles 128 x 64 blocks in shared memory and TMA-stores them
   int* sched;          // dynamic tile scheduler: {next tile, finished workers} of this launch (zero on entry), or NULL
+  // K-split of the TAIL tiles (ksplit > 1; fp32-output epilogue without activation only).  Work units [0, whole_units) are
+  // whole tiles; every later tile is ksplit units of num_kb / ksplit k-blocks each.  Unit p of a tile accumulates onto
+  // what unit p - 1 wrote -- C += colscale (acc out_scale), in that fixed order, so the result does not depend on which
+  // worker ran what -- and waits for it through tile_flags[tile - whole_units] (one arrival per epilogue warp).  With
+  // the tail cut in thirds a 1.66-wave GEMM (fc2) costs 1.67 tile times instead of 2.
+  int ksplit, whole_units, tail_tiles;
+  int* tile_flags;
 };
 
 // ---- cluster / 2-CTA helpers (cta_group::2: one UMMA spans the tensor cores and shared memory of an SM pair)
@@ -242,6 +249,21 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on 
                : "memory");
 }
 
+struct Unit {
+  int tile, kb0, nkb, part;   // part: -1 = a whole tile, else the K-part of a split tile
+};
+// Units are numbered part-major -- part 0 of every tail tile, then part 1 of every tail tile, ... -- so that a part's
+// predecessor was handed out a whole round of tail tiles earlier and has (nearly always) stored its result by the time the
+// part's own main loop ends.  (Tile-major numbering put the three parts of a tile on three workers at the same moment: each
+// epilogue then waited for another worker's, which waited for a third -- chains through the in-order epilogues that made
+// fc2 38 % SLOWER than without the split.)
+__device__ __forceinline__ Unit decode_unit(int u, const TcParams& p) {
+  if (p.ksplit <= 1 || u < p.whole_units) return {u, 0, p.num_kb, -1};
+  const int v = u - p.whole_units, n = p.num_kb / p.ksplit, tail = p.tail_tiles;
+  const int part = v / tail;
+  return {p.whole_units + (v - part * tail), part * n, n, part};
+}
+
 // TWO = false: one CTA per 128 x BN tile (cta_group::1).
 // TWO = true : a cluster of two CTAs per 256 x 256 tile (cta_group::2, BN must be 256): each CTA stages its own
 //              128 rows of A and 128 rows of B (64 KB per k-block, 3 stages), the leader issues M = 256 UMMAs that
@@ -293,6 +315,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_workers = TWO ? (int)gridDim.x / 2 : (int)gridDim.x;
   const int m_tiles = (p.M + TM - 1) / TM, n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
+  const int num_units = p.ksplit > 1 ? p.whole_units + (num_tiles - p.whole_units) * p.ksplit : num_tiles;
 
   if (warp == 0 && lane == 1) {
     // the TMA unit fetches a descriptor on its first use: start those fetches now, under the barrier set-up
@@ -359,7 +382,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // dynamic scheduling from the SECOND tile on: the first one is the worker's own index (a launch with dynamic tiles has
           // more tiles than workers), so no global atomic round trip sits in front of the first TMA load
           tile = (p.sched && j > 0) ? num_workers + atomicAdd(p.sched, 1) : worker + j * num_workers;
-          if (tile >= num_tiles) tile = -1;
+          if (tile >= num_units) tile = -1;
           ring_tile_ptr[r] = tile;
           if (TWO) st_shared_cluster(mapa(ring_tile + 4u * r, 1), tile);
           mbar_arrive(ring_full(r));
@@ -369,12 +392,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ring_release(j, tile);
         }
         if (tile < 0) break;
-        const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
+        const Unit un = decode_unit(tile, p);
+        const int tm = p.n_fastest ? un.tile / n_tiles : un.tile % m_tiles, tn = p.n_fastest ? un.tile % n_tiles : un.tile / m_tiles;
         const int m0 = tm * TM + rank * BM, n0 = tn * BN + rank * B_ROWS;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = un.kb0; kb < un.kb0 + un.nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sb = base + stage * STAGE_BYTES;
-          if ((p.dbg & 1) && (j > 0 || kb >= STAGES)) {   // experiment: operands stay resident after the first fill
+          if ((p.dbg & 1) && (j > 0 || kb - un.kb0 >= STAGES)) {   // experiment: operands stay resident after the first fill
             if (rank == 0) mbar_arrive(full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
@@ -433,7 +457,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.trace) { tr_acc += clock64() - c0; ++tr_tiles; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int nkb = decode_unit(tile, p).nkb;                  // (a K-part of a split tail tile: fewer k-blocks)
+        for (int kb = 0; kb < nkb; ++kb) {
           if (p.trace) c0 = clock64();
           mbar_wait(full_bar(stage), phase);
           if (p.trace) tr_full += clock64() - c0;
@@ -523,7 +548,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) ring_release(t, tile);
       if (tile < 0) break;
       const int acc = t & 1;
-      const int tm = p.n_fastest ? tile / n_tiles : tile % m_tiles, tn = p.n_fastest ? tile % n_tiles : tile / m_tiles;
+      const Unit un = decode_unit(tile, p);
+      const int tm = p.n_fastest ? un.tile / n_tiles : un.tile % m_tiles, tn = p.n_fastest ? un.tile % n_tiles : un.tile / m_tiles;
       const int m0 = tm * TM + rank * BM, n0 = tn * BN;
       if (p.split_tma) {
         // ------------------------------------------------------------ split-only output through TMA stores
@@ -700,6 +726,22 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // the first sub-chunk's are requested before waiting for the MMAs and every later one a sub-chunk ahead:
       // loaded at the point of use, the four dependent L2 round trips per sub-chunk (the in-place store to C
       // may alias R, so the compiler cannot hoist them) were the exposed tail of the narrow GEMMs.
+      // K-parts of a split tail tile: part 0 is the ordinary epilogue; a later part adds colscale (acc out_scale) to what the
+      // previous part stored -- its "residual" is C, without bias -- once that part's stores are visible
+      const bool later_part = un.part > 0;
+      const bool has_res = later_part || p.R != nullptr;
+      if (later_part) {
+        const int need = un.part * EPI_WARPS * (TWO ? 2 : 1);      // one arrival per epilogue warp of every earlier part
+        if (lane == 0) {
+          const int* f = p.tile_flags + (un.tile - p.whole_units);
+          int v;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v < need) __nanosleep(64);
+          } while (v < need);
+        }
+        __syncwarp();
+      }
       auto load_res = [&](int sc, float4* out) {
         const int gcol = n0 + sc * 16 + c4;
 #pragma unroll
@@ -707,8 +749,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int row = m0 + quarter * 32 + i * 8 + sub_row;
           if (sc >= NSUB || gcol >= p.N || row >= p.M) continue;
-          const float* rp = p.R + (long long)(p.res_rows > 0 ? row % p.res_rows : row) * p.ldr + gcol;
-          if (gcol + 3 < p.N && p.vec_r) {
+          const float* rp = later_part
+                                ? (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
+                                               : p.C + (long long)row * p.ldc) + gcol
+                                : p.R + (long long)(p.res_rows > 0 ? row % p.res_rows : row) * p.ldr + gcol;
+          if (gcol + 3 < p.N && (later_part ? p.vec_c : p.vec_r)) {
             out[i] = *reinterpret_cast<const float4*>(rp);
           } else {
             out[i].x = rp[0];
@@ -728,7 +773,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (gc + u < p.N) {
-              if (p.bias) bb[u] = __ldg(p.bias + gc + u);
+              if (p.bias && !later_part) bb[u] = __ldg(p.bias + gc + u);
               if (p.colscale) ss[u] = __ldg(p.colscale + gc + u);
             }
         }
@@ -737,7 +782,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       };
       float4 rcur[4], rnext[4], bcur, scur, bnext, snext;
       load_bs(group, bcur, scur);
-      if (p.R) load_res(group, rcur);
+      if (has_res) load_res(group, rcur);
       mbar_wait(tfull_bar(acc), (t >> 1) & 1);
       tc_fence_after();
       if (p.dbg & 8) {   // experiment: no epilogue at all (the accumulator is handed straight back)
@@ -753,7 +798,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int sc = group; sc < NSUB; sc += NGROUP) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + sc * 16), r);
-        if (p.R) load_res(sc + NGROUP, rnext);
+        if (has_res) load_res(sc + NGROUP, rnext);
         load_bs(sc + NGROUP, bnext, snext);
         if (sc + NGROUP >= NSUB) {
           // this warp has drained its share of the accumulator: hand it back to the MMA warp early
@@ -807,10 +852,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 4; ++u) y[i][u] *= sv[u];
             }
-            if (p.R) {
+            if (has_res) {
               const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
 #pragma unroll
-              for (int u = 0; u < 4; ++u) y[i][u] = (p.res_mode == EC_RES_GATE) ? (y[i][u] + 1.0f) * rr[u] : rr[u] + y[i][u];
+              for (int u = 0; u < 4; ++u)
+                y[i][u] = (p.res_mode == EC_RES_GATE && !later_part) ? (y[i][u] + 1.0f) * rr[u] : rr[u] + y[i][u];
             }
             if (p.C && !(p.dbg & 4)) {
               float* cp = (p.seg_c > 0 ? p.C + (long long)(row / p.seg_c) * p.seg_stride_c + (long long)(row % p.seg_c) * p.ldc
@@ -834,12 +880,18 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         __syncwarp();
-        if (p.R) {
+        if (has_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
         }
         bcur = bnext;
         scur = snext;
+      }
+      if (un.part >= 0 && un.part + 1 < p.ksplit) {
+        // this warp's share of the part is stored: publish it to the next part of the tile
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.tile_flags + (un.tile - p.whole_units), 1);
       }
     }
     report_overflow(p.overflow, ovf);
@@ -853,6 +905,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (atomicAdd(p.sched + 1, 1) == num_workers - 1) {
       atomicExch(p.sched, 0);
       atomicExch(p.sched + 1, 0);
+      if (p.ksplit > 1)      // (plain stores: a chain of atomics here cost a round trip each, ~40 us for fc2's 49 flags)
+        for (int i = 0; i < num_tiles - p.whole_units; ++i) reinterpret_cast<volatile int*>(p.tile_flags)[i] = 0;
     }
   }
   if (warp == 1) {
@@ -999,10 +1053,14 @@ static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, C
 // per-device function attribute) and the tile counters of the dynamic scheduler.  Created under a mutex on the first
 // call made with that device current -- which therefore must not be inside a stream capture (cudaMalloc / cudaMemset).
 constexpr unsigned EAGER_SLOTS = 4096, GRAPH_SLOTS = 61440;
+// flag regions of the K-split tail (TcParams::tile_flags): FLAGS_PER_REGION ints each; eager launches cycle through a small
+// ring, launches recorded into a CUDA graph keep theirs (when the pool runs out a launch simply does not split)
+constexpr unsigned FLAGS_PER_REGION = 160, EAGER_FLAG_REGIONS = 256, GRAPH_FLAG_REGIONS = 4096;
 struct DevState {
   int num_sms = 0;
   int* sched_base = nullptr;
-  std::atomic<unsigned> eager_seq{0}, graph_seq{0};
+  int* flag_base = nullptr;
+  std::atomic<unsigned> eager_seq{0}, graph_seq{0}, eager_flag_seq{0}, graph_flag_seq{0};
 };
 std::atomic<long long> g_mode_launches[6];   // launches per tile mode: 128x128, 128x256, CTA-pair 256x256; [3..5] = the F16F8 kernels
 
@@ -1027,6 +1085,9 @@ static DevState* dev_state() {
   const size_t bytes = (size_t)(EAGER_SLOTS + GRAPH_SLOTS) * 2 * sizeof(int);
   if (e == cudaSuccess) e = cudaMalloc(&d->sched_base, bytes);
   if (e == cudaSuccess) e = cudaMemset(d->sched_base, 0, bytes);
+  const size_t fbytes = (size_t)(EAGER_FLAG_REGIONS + GRAPH_FLAG_REGIONS) * FLAGS_PER_REGION * sizeof(int);
+  if (e == cudaSuccess) e = cudaMalloc(&d->flag_base, fbytes);
+  if (e == cudaSuccess) e = cudaMemset(d->flag_base, 0, fbytes);
   if (e != cudaSuccess) {
     set_error("ec_gemm_f16x3: per-device setup failed on device %d: %s (the first call on a device allocates the tile "
               "counters and must not be inside a stream capture)", dev, cudaGetErrorString(e));
@@ -1108,6 +1169,14 @@ extern "C" int ec_tc_set_dynamic(int on) {
   ec_tc_dynamic = on ? 1 : 0;
   return EC_OK;
 }
+// K-split of the tail tiles (TcParams::ksplit): EDGECAPE_GEMM_KSPLIT=0 / ec_tc_set_ksplit(0) switches it off
+static int ec_tc_ksplit = -1;
+static std::atomic<long long> g_ksplit_launches{0};
+extern "C" int ec_tc_set_ksplit(int on) {
+  ec_tc_ksplit = on ? 1 : 0;
+  return EC_OK;
+}
+extern "C" long long ec_tc_ksplit_launches() { return g_ksplit_launches.load(std::memory_order_relaxed); }
 static int ec_tc_cta_limit = 0;  // 0 = every SM; else the persistent grids use at most this many CTAs
 extern "C" int ec_tc_set_cta_limit(int ctas) {
   EC_REQUIRE(ctas >= 0, "ec_tc_set_cta_limit: negative");
@@ -1253,6 +1322,37 @@ static int gemm_split_launch(const char* what, bool f8, const void* A2, const vo
     } else {
       const unsigned g = ds->graph_seq.fetch_add(1);
       if (g < tc::GRAPH_SLOTS) p.sched = ds->sched_base + 2 * (tc::EAGER_SLOTS + g);
+    }
+  }
+  // K-split of the tail: when the last wave is partly empty, cut its tiles into three K-parts so that they fill it (fc2:
+  // 123 pair tiles on 74 pairs = 2 tile times -> 74 whole tiles + 49 x 3 parts = 1.67; proj: 492 tiles on 148 CTAs = 4 -> 3.33)
+  p.ksplit = 1; p.whole_units = 0; p.tail_tiles = 0; p.tile_flags = nullptr;
+  if (ec_tc_ksplit < 0) {
+    const char* e = getenv("EDGECAPE_GEMM_KSPLIT");
+    ec_tc_ksplit = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (ec_tc_ksplit && p.sched && C && !split_out && act == EC_ACT_NONE && res_mode != EC_RES_GATE && p.num_kb % 3 == 0 &&
+      p.num_kb >= 12) {
+    const long long tiles = mode == 512 ? pair_tiles : (long long)cdiv(M, tc::BM) * cdiv(N, BN);
+    const long long workers = mode == 512 ? sched_ctas / 2 : sched_ctas;
+    const long long whole = tiles / workers * workers, tail = tiles - whole;
+    if (whole > 0 && tail > 0 && 3 * tail <= 2 * workers && tail <= (long long)tc::FLAGS_PER_REGION) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      EC_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
+      unsigned region = ~0u;
+      if (cap == cudaStreamCaptureStatusNone) {
+        region = ds->eager_flag_seq.fetch_add(1) % tc::EAGER_FLAG_REGIONS;
+      } else {
+        const unsigned g = ds->graph_flag_seq.fetch_add(1);
+        if (g < tc::GRAPH_FLAG_REGIONS) region = tc::EAGER_FLAG_REGIONS + g;
+      }
+      if (region != ~0u) {
+        p.ksplit = 3;
+        g_ksplit_launches.fetch_add(1, std::memory_order_relaxed);
+        p.whole_units = (int)whole;
+        p.tail_tiles = (int)tail;
+        p.tile_flags = ds->flag_base + (size_t)region * tc::FLAGS_PER_REGION;
+      }
     }
   }
   tc::g_mode_launches[(f8 ? 3 : 0) + (mode == 512 ? 2 : (mode == 256 ? 1 : 0))].fetch_add(1, std::memory_order_relaxed);

@@ -135,6 +135,8 @@ int ec_tc_set_cta_limit(int ctas);
  * CTA whose SM is busy with another stream's kernel takes fewer tiles instead of stalling the launch; 0 = static
  * round-robin.  EDGECAPE_GEMM_DYNAMIC=0 selects static at start-up. */
 int ec_tc_set_dynamic(int on);
+int ec_tc_set_ksplit(int on);      /* K-split of the tail tiles of fp32-output GEMMs whose last wave is partly empty (EDGECAPE_GEMM_KSPLIT) */
+long long ec_tc_ksplit_launches(void);   /* launches that used it so far (tests) */
 /* programmatic dependent launch of the library's kernels (default on; EDGECAPE_PDL=0 or ec_set_pdl(0) = plain
  * stream-ordered launches, for A/B measurements) */
 int ec_set_pdl(int on);

@@ -251,3 +251,40 @@ def test_split_only_epilogue_through_tma_stores(M, N, K, fmt_in, tile_n):
     finally:
         ops._lib.call("ec_tc_set_split_tma", 1)
         ops._lib.call("ec_tc_set_tile_n", 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,fmt", [(10400, 768, 3072, 1), (10400, 768, 768, 0), (10400, 768, 768, 1), (5200, 768, 3072, 1)],
+                         ids=["fc2_pair_f8", "proj_f16x3", "proj_f8", "fc2_batch8"])
+def test_gemm_ksplit_tail(M, N, K, fmt):
+    """ec_tc_set_ksplit(1): the tiles of a partly empty last wave are cut into three K-parts that accumulate onto one
+    another IN A FIXED ORDER through C (residual in place, LayerScale, bias): close to fp64, to the unsplit launch, and
+    bit-identical from run to run."""
+    from edgecape_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.02).cuda()
+    b = (torch.randn(N, generator=g) * 0.1).cuda()
+    ls = torch.rand(N, generator=g).cuda()
+    t0 = torch.randn(M, N, generator=g).cuda()
+    a = ops.split_f16(x, fmt=fmt, role=0)
+    ws = ops.split_weight(w, fmt)
+    want = (t0.double() + ls.double() * (x.double() @ w.double().T + b.double())).float()
+
+    def run():
+        t = t0.clone()
+        ops.gemm_tc(a, ws, out=t, bias=b, colscale=ls, residual=t)
+        return t
+    ref = run()
+    n0 = lib.ec_tc_ksplit_launches()
+    lib.ec_tc_set_ksplit(1)
+    try:
+        y1, y2 = run(), run()
+    finally:
+        lib.ec_tc_set_ksplit(0)
+    assert lib.ec_tc_ksplit_launches() - n0 == 2, "the K-split did not engage at this shape"
+    assert torch.equal(y1, y2)
+    scale = want.abs().max().item()
+    assert (y1 - want).abs().max().item() / scale < 3e-5
+    assert (y1 - ref).abs().max().item() / scale < 2e-5
