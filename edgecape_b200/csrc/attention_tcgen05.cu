@@ -764,8 +764,8 @@ __device__ __forceinline__ void stage_split16(uint8_t* stg, int row, int part, c
 __device__ __forceinline__ __half* split_chunk_dst(__half* row, int kp, int h, int c, int fmt) {
   if (fmt == EC_SPLIT_F16X2) return row + h * 64 + (c < 8 ? c * 8 : kp + (c - 8) * 8);
   if (c < 8) return row + h * 64 + c * 8;                                    // hi16: halves [0, kp)
-  if (c < 12) return row + kp + h * 32 + (c - 8) * 8;                        // hi8: bytes [2 kp, 3 kp)
-  return row + kp + kp / 2 + h * 32 + (c - 12) * 8;                          // lo8: bytes [3 kp, 4 kp)
+  // e4m3 planes: the head's 64 columns are one block of 128 bytes at byte 2 kp + 128 h: hi8 chunks [0, 4), lo8 chunks [4, 8)
+  return row + kp + h * 64 + (c - 8) * 8;
 }
 // ---------------------------------------------------------------------------------------------------------
 // P-in-TMEM variant (the default).  The shared-memory P path above is bound by shared-memory bandwidth in the

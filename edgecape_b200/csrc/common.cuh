@@ -112,12 +112,17 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 // ---- split operand rows.  A matrix [rows, K] feeds the tensor-core GEMMs as rows of 4*Kp bytes in one of two formats
 // (Kp = K rounded up to 64, zero padded; `fmt` = EC_SPLIT_F16X2 / EC_SPLIT_F16F8, include/edgecape_b200.h):
 //   F16X2: [ hi16 : Kp halves | lo16 : Kp halves ]                 three fp16 products (ec_gemm_f16x3)
-//   F16F8: [ hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp bytes ]  fp16 hi.hi + two e4m3 cross terms (ec_gemm_f16f8)
+//   F16F8: [ hi16 : Kp halves | per 64-column block: hi8 x 64, lo8 x 64 ]  fp16 hi.hi + two e4m3 cross terms (ec_gemm_f16f8);
+//          the two e4m3 planes are interleaved per 64 columns so that ONE TMA box with 128-byte rows (whole L2 lines) holds
+//          both planes of a 64-deep k-block -- boxes with 64-byte rows moved measurably slower (qkv 65.9 -> 63.8 us, fc2
+//          94.3 -> 90.0 us in the timing experiment, profiles/r03_w_gemm_e4m3_box_rows.log)
 // F16F8 plane scales are static powers of two, so every product carries the same scale and all three accumulate into
 // one fp32 accumulator:  A role (activations): hi8 = e4m3(hi16), lo8 = e4m3((a - hi16) 2^11);
 //                        B role (weights, pre-scaled by s_w): hi8 = e4m3(hi16 2^-11), lo8 = e4m3(b s_w - hi16).
 // e4m3 saturates at 448: an activation beyond that only degrades ITS cross terms to plain-fp16 accuracy (the hi16 plane
 // carries the value); beyond 65504 hi16 itself overflows.  Both events are counted (ec_overflow_count).
+// byte offset of the hi8 entry of column c in an F16F8 row of kp columns; the lo8 entry sits 64 bytes further
+__host__ __device__ inline int f8_off(int kp, int c) { return 2 * kp + 128 * (c >> 6) + (c & 63); }
 __device__ __forceinline__ uint32_t e4m3x2(float a, float b) {
   return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);   // a in the low byte
 }
@@ -140,8 +145,8 @@ __device__ __forceinline__ void store_split4(uint8_t* row, int kp, int c, float 
     *reinterpret_cast<uint2*>(row + 2 * kp + 2 * c) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   } else {
-    *reinterpret_cast<uint32_t*>(row + 2 * kp + c) = e4m3x2_h2(u01) | (e4m3x2_h2(u23) << 16);
-    *reinterpret_cast<uint32_t*>(row + 3 * kp + c) = e4m3x2(d0 * 2048.f, d1 * 2048.f) | (e4m3x2(d2 * 2048.f, d3 * 2048.f) << 16);
+    *reinterpret_cast<uint32_t*>(row + f8_off(kp, c)) = e4m3x2_h2(u01) | (e4m3x2_h2(u23) << 16);
+    *reinterpret_cast<uint32_t*>(row + f8_off(kp, c) + 64) = e4m3x2(d0 * 2048.f, d1 * 2048.f) | (e4m3x2(d2 * 2048.f, d3 * 2048.f) << 16);
     const float m = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
     flags |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
   }
@@ -167,7 +172,7 @@ __device__ __forceinline__ void store_split8(uint8_t* row, int kp, int c, const 
     }
     *reinterpret_cast<uint4*>(row + 2 * kp + 2 * c) = make_uint4(l[0], l[1], l[2], l[3]);
   } else {
-    *reinterpret_cast<uint2*>(row + 2 * kp + c) =
+    *reinterpret_cast<uint2*>(row + f8_off(kp, c)) =
         make_uint2(e4m3x2_h2(h[0]) | (e4m3x2_h2(h[1]) << 16), e4m3x2_h2(h[2]) | (e4m3x2_h2(h[3]) << 16));
     uint32_t l8[4];
     float m = 0.f;
@@ -176,7 +181,7 @@ __device__ __forceinline__ void store_split8(uint8_t* row, int kp, int c, const 
       l8[i] = e4m3x2(dl[2 * i] * 2048.f, dl[2 * i + 1] * 2048.f);
       m = fmaxf(m, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));
     }
-    *reinterpret_cast<uint2*>(row + 3 * kp + c) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
+    *reinterpret_cast<uint2*>(row + f8_off(kp, c) + 64) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
     flags |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
   }
 }

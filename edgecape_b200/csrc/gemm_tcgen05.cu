@@ -89,11 +89,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
-// K-major, 64B-swizzled tile of e4m3 bytes: rows of 64 B, 8-row atoms of 512 B, layout type 4 (SWIZZLE_64B).
-// Hardware facts behind it: scripts/probes/f8_mma_probe.cu, profiles/r01_ao_f8_mma_probe.log.
-__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
-}
 // kind::f16 instruction descriptor (Cfg<BN>::IDESC): D = f32, A = B = f16, both K-major, M = 128, N = BN.
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -411,11 +406,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             tma_load_2d_2sm(sb + 0 * TILE_BYTES, &tmA, lbar, kb * BK, m0);
             tma_load_2d_2sm(sb + 2 * TILE_BYTES, &tmB, lbar, kb * BK, n0);
-            if (F8) {
-              tma_load_2d_2sm(sb + TILE_BYTES, &tmA8, lbar, 2 * p.Kp + kb * BK, m0);
-              tma_load_2d_2sm(sb + TILE_BYTES + TILE_BYTES / 2, &tmA8, lbar, 3 * p.Kp + kb * BK, m0);
-              tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB8, lbar, 2 * p.Kp + kb * BK, n0);
-              tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2, &tmB8, lbar, 3 * p.Kp + kb * BK, n0);
+            if (F8) {     // both e4m3 planes of the k-block: ONE box of 128-byte rows [hi8 x 64 | lo8 x 64] per operand
+              tma_load_2d_2sm(sb + TILE_BYTES, &tmA8, lbar, 2 * p.Kp + 2 * kb * BK, m0);
+              tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB8, lbar, 2 * p.Kp + 2 * kb * BK, n0);
             } else {
               tma_load_2d_2sm(sb + 1 * TILE_BYTES, &tmA, lbar, p.Kp + kb * BK, m0);
               tma_load_2d_2sm(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, lbar, p.Kp + kb * BK, n0);
@@ -425,10 +418,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d(sb + 0 * TILE_BYTES, &tmA, full_bar(stage), kb * BK, m0);
             tma_load_2d(sb + 2 * TILE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
             if (F8) {
-              tma_load_2d(sb + TILE_BYTES, &tmA8, full_bar(stage), 2 * p.Kp + kb * BK, m0);
-              tma_load_2d(sb + TILE_BYTES + TILE_BYTES / 2, &tmA8, full_bar(stage), 3 * p.Kp + kb * BK, m0);
-              tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB8, full_bar(stage), 2 * p.Kp + kb * BK, n0);
-              tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2, &tmB8, full_bar(stage), 3 * p.Kp + kb * BK, n0);
+              tma_load_2d(sb + TILE_BYTES, &tmA8, full_bar(stage), 2 * p.Kp + 2 * kb * BK, m0);
+              tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB8, full_bar(stage), 2 * p.Kp + 2 * kb * BK, n0);
             } else {
               tma_load_2d(sb + 1 * TILE_BYTES, &tmA, full_bar(stage), p.Kp + kb * BK, m0);
               tma_load_2d(sb + 2 * TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), p.Kp + kb * BK, n0);
@@ -467,9 +458,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t a_hi = make_smem_desc(sb + 0 * TILE_BYTES), b_hi = make_smem_desc(sb + 2 * TILE_BYTES);
           if (F8) {
             // cross terms first (e4m3, K = 32 per UMMA, descriptors advance 32 B), then hi16 . hi16
-            const uint64_t a_h8 = make_smem_desc_sw64(sb + TILE_BYTES), a_l8 = make_smem_desc_sw64(sb + TILE_BYTES + TILE_BYTES / 2);
-            const uint64_t b_h8 = make_smem_desc_sw64(sb + 2 * TILE_BYTES + B_TILE_BYTES);
-            const uint64_t b_l8 = make_smem_desc_sw64(sb + 2 * TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2);
+            // e4m3 tiles: rows of 128 B in 128B swizzle, hi8 in bytes [0, 64) and lo8 in [64, 128) of each row -- the lo8 operand
+            // is the same tile entered 64 bytes (4 x 16 B) into the row, like a K advance
+            const uint64_t a_h8 = make_smem_desc(sb + TILE_BYTES), a_l8 = a_h8 + 4;
+            const uint64_t b_h8 = make_smem_desc(sb + 2 * TILE_BYTES + B_TILE_BYTES), b_l8 = b_h8 + 4;
             if (TWO) {
 #pragma unroll
               for (int k = 0; k < BK / 32; ++k) umma_f8_2sm(tmem_d, a_l8 + 2 * k, b_h8 + 2 * k, IDESC, (kb | k) ? 1u : 0u);
@@ -562,7 +554,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // the transposition, and consecutive rows hit distinct bank groups by construction of the swizzle), and
         // one thread stores the block with two or three bulk tensor copies (whole 128-byte lines; rows >= M are
         // clipped by the tensor map, columns >= N inside the padded width are the zero padding of the operand).
-        uint8_t* blk = smem_raw + (epi_base - smem_u32(smem_raw));      // [hi16 16 KB | lo16 16 KB] or [hi16 | hi8 8 KB | lo8 8 KB]
+        uint8_t* blk = smem_raw + (epi_base - smem_u32(smem_raw));      // [hi16 16 KB | lo16 16 KB] or [hi16 16 KB | hi8 + lo8 16 KB]
         const uint32_t blk_u32 = epi_base;
         const int row_l = quarter * 32 + lane;                          // row of the 128-row block = TMEM lane
         // bias / LayerScale of a block: ONE coalesced load per warp (lane u holds column u of the 16), fetched a block
@@ -665,8 +657,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   m = fmaxf(m, fmaxf(fmaxf(fabsf(y[4 * i]), fabsf(y[4 * i + 1])), fmaxf(fabsf(y[4 * i + 2]), fabsf(y[4 * i + 3]))));
                 }
                 ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
-                *reinterpret_cast<uint4*>(orow + 2 * p.split_kp + gcol) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
-                *reinterpret_cast<uint4*>(orow + 3 * p.split_kp + gcol) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+                *reinterpret_cast<uint4*>(orow + f8_off(p.split_kp, gcol)) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                *reinterpret_cast<uint4*>(orow + f8_off(p.split_kp, gcol) + 64) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
               }
             }
             continue;
@@ -699,10 +691,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               m = fmaxf(m, fmaxf(fmaxf(fabsf(y[4 * i]), fabsf(y[4 * i + 1])), fmaxf(fabsf(y[4 * i + 2]), fabsf(y[4 * i + 3]))));
             }
             ovf |= (m > 448.f ? 1u : 0u) | (m > 65504.f ? 2u : 0u);
-            // e4m3 planes: 16 columns = the 16-byte chunk `group` of the row's 64 bytes (64B swizzle)
-            const uint32_t off8 = (uint32_t)(row_l * 64 + ((group ^ ((row_l >> 1) & 3)) << 4));
-            *reinterpret_cast<uint4*>(blk + 16384 + off8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
-            *reinterpret_cast<uint4*>(blk + 24576 + off8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+            // e4m3 planes: ONE tile of 128-byte rows (128B swizzle), hi8 of the block's 64 columns in chunks [0, 4), lo8 in
+            // chunks [4, 8): this lane's 16 columns are chunk `group` of each
+            *reinterpret_cast<uint4*>(blk + 16384 + row_l * 128 + ((group ^ (row_l & 7)) << 4)) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+            *reinterpret_cast<uint4*>(blk + 16384 + row_l * 128 + (((4 + group) ^ (row_l & 7)) << 4)) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
           }
           fence_proxy_async_smem();                                     // generic-proxy writes -> visible to the TMA engine
           epi_bar_sync();                                               // the block is complete
@@ -712,8 +704,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.split_fmt == EC_SPLIT_F16X2) {
                 tma_store_2d(&tmO16, blk_u32 + 16384, p.split_kp + col0, m0);
               } else {
-                tma_store_2d(&tmO8, blk_u32 + 16384, 2 * p.split_kp + col0, m0);
-                tma_store_2d(&tmO8, blk_u32 + 24576, 3 * p.split_kp + col0, m0);
+                tma_store_2d(&tmO8, blk_u32 + 16384, 2 * p.split_kp + 2 * col0, m0);   // byte column 2 kp + 128 (col0 / 64)
               }
               tma_store_commit();                                       // (reads awaited at the top of the next block)
             }
@@ -935,7 +926,7 @@ __global__ void split_f16_kernel(const float* __restrict__ X, __half* __restrict
   row[(Kp + k) >> 1] = lo;
 }
 
-// X [M, K] fp32 -> F16F8 rows [hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp bytes] of X*scale, zero padded to Kp.
+// X [M, K] fp32 -> F16F8 rows [hi16 : Kp halves | per 64 columns: hi8 x 64, lo8 x 64] of X*scale, zero padded to Kp.
 // role 0 = A operand (activations), 1 = B operand (weights): the plane scales at the top of common.cuh's split section.
 __global__ void split_f16f8_kernel(const float* __restrict__ X, uint8_t* __restrict__ out, int M, int K, int ldx, int seg,
                                    long long seg_stride, int Kp, float scale, int role, unsigned long long* overflow) {
@@ -973,8 +964,8 @@ __global__ void split_f16f8_kernel(const float* __restrict__ X, uint8_t* __restr
     }
     *reinterpret_cast<uint2*>(row + 2 * k) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-    *reinterpret_cast<uint32_t*>(row + 2 * Kp + k) = e4m3x2(f01.x * s, f01.y * s) | (e4m3x2(f23.x * s, f23.y * s) << 16);
-    *reinterpret_cast<uint32_t*>(row + 3 * Kp + k) =
+    *reinterpret_cast<uint32_t*>(row + f8_off(Kp, k)) = e4m3x2(f01.x * s, f01.y * s) | (e4m3x2(f23.x * s, f23.y * s) << 16);
+    *reinterpret_cast<uint32_t*>(row + f8_off(Kp, k) + 64) =
         e4m3x2(v[0] - f01.x, v[1] - f01.y) | (e4m3x2(v[2] - f23.x, v[3] - f23.y) << 16);
   }
 }
@@ -999,7 +990,7 @@ static EncodeTiledFn get_encode() {
 
 struct MapKey {
   const void* ptr;
-  int rows, kp, box_rows;   // box_rows < 0: the byte view of an F16F8 operand (64-byte boxes, 64B swizzle)
+  int rows, kp, box_rows;   // box_rows < 0: the byte view of an F16F8 operand (128-byte boxes)
   bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kp == o.kp && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
@@ -1010,8 +1001,8 @@ struct MapKeyHash {
 };
 
 // halves view (bytes == false): dims {2 Kp halves, rows}, 64-half x box_rows boxes, 128B swizzle -- the hi16 | lo16 planes.
-// byte view (bytes == true): dims {4 Kp bytes, rows}, 64-byte x box_rows boxes, 64B swizzle -- the hi8 | lo8 planes of an
-// F16F8 operand, at byte columns 2 Kp and 3 Kp of the same rows.
+// byte view (kind 1): dims {4 Kp bytes, rows}, 128-byte x box_rows boxes, 128B swizzle -- both e4m3 planes of a 64-column
+// block of an F16F8 operand ([hi8 x 64 | lo8 x 64] at byte column 2 Kp + 128 (k / 64) of the same rows).
 // slice view (kind 2): dims {4 Kp bytes, rows}, 128-byte x box_rows boxes, 128B swizzle -- one 32-deep k-slice of an operand
 // whose planes are interleaved per 32 columns (ec_split_f16f8 role 2; gcn_fused2_tcgen05.cu streams its weights so).
 static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, CUtensorMap* out, int kind) {
@@ -1032,12 +1023,12 @@ static int get_tensor_map_any(const void* ptr, int rows, int kp, int box_rows, C
   }
   cuuint64_t dims[2] = {(cuuint64_t)(bytes ? 4 * kp : 2 * kp), (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(4 * kp)};
-  cuuint32_t box[2] = {(cuuint32_t)(kind == 2 ? 2 * BK : BK), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(kind == 0 ? BK : 2 * BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %d kp %d)", (int)r, ptr, rows, kp);

@@ -86,8 +86,10 @@ int ec_gemm_f16x3(const void* A2, const void* B2, float* C, int M, int N, int Kp
 
 /* The same contraction in 2 instead of 3 units of tensor time: a_hi.b_hi on fp16 UMMAs, the two cross terms
  * a_lo.b_hi + a_hi.b_lo -- which only need ~11 bits of relative accuracy -- on e4m3 UMMAs (kind::f8f6f4, twice the
- * contraction depth per clock).  Operand rows are EC_SPLIT_F16F8: [hi16 : Kp halves | hi8 : Kp bytes | lo8 : Kp
- * bytes], 4*Kp bytes as EC_SPLIT_F16X2's [hi16 | lo16].  The plane scales are static powers of two --
+ * contraction depth per clock).  Operand rows are EC_SPLIT_F16F8: [hi16 : Kp halves | per 64 columns:
+ * hi8 x 64, lo8 x 64] (hi8 of column c at byte 2 Kp + 128 (c / 64) + c % 64, lo8 64 bytes behind it; Kp % 64 == 0), 4*Kp
+ * bytes as EC_SPLIT_F16X2's [hi16 | lo16] -- so both e4m3 planes of a 64-deep k-block arrive in ONE TMA box of
+ * 128-byte rows.  The plane scales are static powers of two --
  *   A role (activations): hi8 = e4m3(hi16),          lo8 = e4m3((a - hi16) * 2^11)
  *   B role (weights * s_w): hi8 = e4m3(hi16 * 2^-11), lo8 = e4m3(b * s_w - hi16)
  * -- so every product carries s_w and all three accumulate into ONE fp32 TMEM accumulator (out_scale = 1 / s_w undoes

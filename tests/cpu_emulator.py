@@ -116,6 +116,17 @@ def _f8_values(b):
     return torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).to(torch.float32).numpy()
 
 
+def _f8_planes_get(o, Kp):
+    """[hi8 | lo8] planes (each [rows, Kp] bytes) out of F16F8 rows: behind the hi16 plane the two planes are interleaved
+    per 64 columns, [hi8 x 64 | lo8 x 64] per block (include/edgecape_b200.h)."""
+    e = o[:, 2 * Kp:].reshape(o.shape[0], Kp // 64, 2, 64)
+    return (np.ascontiguousarray(e[:, :, 0]).reshape(o.shape[0], Kp), np.ascontiguousarray(e[:, :, 1]).reshape(o.shape[0], Kp))
+
+
+def _f8_planes_put(o, Kp, h8, l8):
+    o[:, 2 * Kp:] = np.stack((h8.reshape(-1, Kp // 64, 64), l8.reshape(-1, Kp // 64, 64)), axis=2).reshape(o.shape[0], 2 * Kp)
+
+
 def _write_split(ptr, kp, y, fmt=0):
     """rows in EC_SPLIT_F16X2 ([hi16 | lo16]) or EC_SPLIT_F16F8 ([hi16 | hi8 | lo8], A role) format."""
     M, N = y.shape
@@ -130,8 +141,10 @@ def _write_split(ptr, kp, y, fmt=0):
         o = arr(ptr, (M, 4 * kp), dtype=np.uint8)
         o[...] = 0
         o[:, :2 * kp].view(np.float16)[:, :N] = hi
-        o[:, 2 * kp:2 * kp + N] = _f8_bytes(hi.astype(np.float32))
-        o[:, 3 * kp:3 * kp + N] = _f8_bytes(lo * np.float32(2.0 ** 11))
+        h8, l8 = np.zeros((M, kp), dtype=np.uint8), np.zeros((M, kp), dtype=np.uint8)
+        h8[:, :N] = _f8_bytes(hi.astype(np.float32))
+        l8[:, :N] = _f8_bytes(lo * np.float32(2.0 ** 11))
+        _f8_planes_put(o, kp, h8, l8)
 
 
 def _gemm_epilogue(y, M, N, C, ldc, seg_c, seg_stride_c, bias, act, colscale, R, ldr, res_mode, res_rows, split_out,
@@ -489,8 +502,10 @@ def ec_split_f16f8(X, out, M, K, ldx, seg, seg_stride, Kp, scale, role, stream):
         o[...] = np.concatenate([h16.view(np.uint8).reshape(M, Kp // 32, 64), h8.reshape(M, Kp // 32, 32),
                                  l8.reshape(M, Kp // 32, 32)], axis=2).reshape(M, 4 * Kp)
         return
-    o[:, 2 * Kp:2 * Kp + K] = _f8_bytes(hi.astype(np.float32) * np.float32(s_hi))
-    o[:, 3 * Kp:3 * Kp + K] = _f8_bytes(lo * np.float32(s_lo))
+    h8, l8 = np.zeros((M, Kp), dtype=np.uint8), np.zeros((M, Kp), dtype=np.uint8)
+    h8[:, :K] = _f8_bytes(hi.astype(np.float32) * np.float32(s_hi))
+    l8[:, :K] = _f8_bytes(lo * np.float32(s_lo))
+    _f8_planes_put(o, Kp, h8, l8)
 
 
 def ec_gemm_f16f8(A3, B3, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias, act, colscale, R, ldr, res_mode,
@@ -498,7 +513,8 @@ def ec_gemm_f16f8(A3, B3, C, M, N, Kp, ldc, seg_c, seg_stride_c, out_scale, bias
     def planes(ptr, nrows):
         o = arr(ptr, (nrows, 4 * Kp), dtype=np.uint8)
         h16 = o[:, :2 * Kp].view(np.float16).astype(np.float32)
-        return h16, _f8_values(o[:, 2 * Kp:3 * Kp]), _f8_values(o[:, 3 * Kp:])
+        h8, l8 = _f8_planes_get(o, Kp)
+        return h16, _f8_values(h8), _f8_values(l8)
     a16, ah8, al8 = planes(A3, M)
     b16, bh8, bl8 = planes(B3, N)
     y = T((al8 @ bh8.T + ah8 @ bl8.T + a16 @ b16.T) * np.float32(out_scale))

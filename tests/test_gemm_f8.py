@@ -142,8 +142,9 @@ def test_f16f8_planes_reconstruct_and_layernorm_writes_them():
     so = ops.split_f16(x, fmt=ops.F16F8, role=0)
     raw = so.data.view(torch.uint8).reshape(650, 4 * 768)
     hi16 = raw[:, :2 * 768].contiguous().view(torch.float16).float()
-    hi8 = raw[:, 2 * 768:3 * 768].contiguous().view(torch.float8_e4m3fn).float()
-    lo8 = raw[:, 3 * 768:].contiguous().view(torch.float8_e4m3fn).float()
+    e = raw[:, 2 * 768:].reshape(650, 768 // 64, 2, 64)          # per 64 columns: [hi8 x 64 | lo8 x 64]
+    hi8 = e[:, :, 0].reshape(650, 768).contiguous().view(torch.float8_e4m3fn).float()
+    lo8 = e[:, :, 1].reshape(650, 768).contiguous().view(torch.float8_e4m3fn).float()
     assert torch.equal(hi16, x.half().float())
     assert torch.equal(hi8, hi16.to(torch.float8_e4m3fn).float())
     assert ((hi16 + lo8 / 2048.0) - x).abs().max().item() <= 2.0 ** -15 * x.abs().max().item()
@@ -157,8 +158,9 @@ def _interleave32(std, Kp):
     """role-1 rows [hi16 | hi8 | lo8] -> role-2 rows: 128 bytes per 32-column slice, [hi16 x 32 | hi8 x 32 | lo8 x 32]."""
     M = std.shape[0]
     h16 = std[:, :2 * Kp].reshape(M, Kp // 32, 64)
-    h8 = std[:, 2 * Kp:3 * Kp].reshape(M, Kp // 32, 32)
-    l8 = std[:, 3 * Kp:].reshape(M, Kp // 32, 32)
+    e = std[:, 2 * Kp:].reshape(M, Kp // 64, 2, 64)              # role 1: per 64 columns [hi8 x 64 | lo8 x 64]
+    h8 = e[:, :, 0].reshape(M, Kp // 32, 32)
+    l8 = e[:, :, 1].reshape(M, Kp // 32, 32)
     return torch.cat((h16, h8, l8), dim=2).reshape(M, 4 * Kp)
 
 

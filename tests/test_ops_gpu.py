@@ -610,8 +610,9 @@ def test_attention_writes_f16f8_rows(B, N, H):
     hi16, lo16 = ref.data[:, :C], ref.data[:, C:].float()
     raw = got.data.view(torch.uint8).view(B * N, 4 * C)
     assert torch.equal(raw[:, :2 * C].contiguous().view(torch.float16), hi16)
-    h8 = raw[:, 2 * C:3 * C].contiguous().view(torch.float8_e4m3fn).float()
-    l8 = raw[:, 3 * C:].contiguous().view(torch.float8_e4m3fn).float()
+    e = raw[:, 2 * C:].reshape(B * N, H, 2, 64)                     # per 64 columns (= per head): [hi8 x 64 | lo8 x 64]
+    h8 = e[:, :, 0].reshape(B * N, C).contiguous().view(torch.float8_e4m3fn).float()
+    l8 = e[:, :, 1].reshape(B * N, C).contiguous().view(torch.float8_e4m3fn).float()
     assert torch.equal(h8, hi16.float().to(torch.float8_e4m3fn).float())
     # (the kernel rounds the exact fp32 low part, lo16 is that part rounded to fp16 first: at most one e4m3 step apart)
     exp_l8 = (lo16 * 2048.0).to(torch.float8_e4m3fn).float()
