@@ -232,6 +232,9 @@ class _GraphedForward:
         return h
 
 
+VIT_CHAINS = int(os.environ.get("EDGECAPE_VIT_CHAINS", "1"))
+
+
 def _hashable(v):
     """img_metas values (lists of numpy arrays / scalars) as nested tuples; None stays None."""
     if v is None:
@@ -492,8 +495,21 @@ class EdgeCape(nn.Module):
         feat_q [B,S,C] and a list of feats_s [B,S,C] (cls row dropped by striding, no copy).
         With `inv` (int32 [B], support de-duplication) every img_s[j] holds only the n_u distinct support images and
         row b of feats_s[j] is the feature block of image inv[b]."""
-        tok, _ = self.encoder_query.forward_tokens([img_q] + list(img_s))
         B = img_q.shape[0]
+        if VIT_CHAINS == 2 and inv is None and img_q.is_cuda:
+            # experiment (EDGECAPE_VIT_CHAINS=2, off by default): the query images and the support images as two
+            # independent ViT passes on two streams, so that one chain's kernels fill the partly empty last wave of the
+            # other's GEMMs (fc2 / proj run 1.66 waves of pair tiles on the whole batch)
+            cur = torch.cuda.current_stream(img_q.device)
+            side = self._chain_stream = getattr(self, "_chain_stream", None) or torch.cuda.Stream(device=img_q.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                tok_s, _ = self.encoder_query.forward_tokens(list(img_s))
+            tok_q, _ = self.encoder_query.forward_tokens([img_q])
+            cur.wait_stream(side)
+            tok_s.record_stream(cur)
+            return tok_q[:, 1:, :], [tok_s[i * B:(i + 1) * B, 1:, :] for i in range(len(img_s))]
+        tok, _ = self.encoder_query.forward_tokens([img_q] + list(img_s))
         feat_q = tok[:B, 1:, :]
         if inv is None:
             feats_s = [tok[(i + 1) * B:(i + 2) * B, 1:, :] for i in range(len(img_s))]
