@@ -111,7 +111,7 @@ _SPLIT_WEIGHTS = {}
 
 class SplitOperand:
     """Split form of an fp32 matrix (scaled by `scale`, a power of two): fp16 [rows, 2*Kp] holding 4*Kp bytes per
-    row in the format `fmt` (F16X2: [hi | lo] halves; F16F8: [hi16 | hi8 | lo8])."""
+    row in the format `fmt` (F16X2: [hi | lo] halves; F16F8: [hi16 | per 64 columns: hi8, lo8])."""
     __slots__ = ("data", "rows", "K", "Kp", "scale", "fmt")
 
     def __init__(self, data, rows, K, Kp, scale, fmt=F16X2):
