@@ -94,7 +94,7 @@ ATTENTION_TC = os.environ.get("EDGECAPE_ATTN_TC", "1") != "0"     # tcgen05 atte
 ATTENTION_TMA = os.environ.get("EDGECAPE_ATTN_TMA", "1") != "0"   # TMA-fed variant on pre-split QKV (ViT)
 TC_MIN_M, TC_MIN_N, TC_MIN_K = 64, 32, 32
 # Split-operand row formats (include/edgecape_b200.h): F16X2 = [hi16 | lo16] for ec_gemm_f16x3 and the attention
-# kernels, F16F8 = [hi16 | hi8 | lo8] for ec_gemm_f16f8 (a_hi.b_hi on fp16, both cross terms on e4m3: 2 instead of 3
+# kernels, F16F8 = [hi16 | hi8, lo8 interleaved per 64 columns] for ec_gemm_f16f8 (a_hi.b_hi on fp16, both cross terms on e4m3: 2 instead of 3
 # units of tensor time).  EDGECAPE_GEMM_F8=0 keeps every linear on three fp16 products; with it on (default) the
 # large linears (M >= F8_MIN_M rows: the ViT's qkv / fc1 / fc2 at bench batch sizes) take the F16F8 kernel.
 F16X2, F16F8 = 0, 1

@@ -128,7 +128,7 @@ def _f8_planes_put(o, Kp, h8, l8):
 
 
 def _write_split(ptr, kp, y, fmt=0):
-    """rows in EC_SPLIT_F16X2 ([hi16 | lo16]) or EC_SPLIT_F16F8 ([hi16 | hi8 | lo8], A role) format."""
+    """rows in EC_SPLIT_F16X2 ([hi16 | lo16]) or EC_SPLIT_F16F8 ([hi16 | per 64 columns: hi8, lo8], A role) format."""
     M, N = y.shape
     y = y.astype(np.float32)
     hi = y.astype(np.float16)
@@ -484,7 +484,7 @@ def ec_markov_powers(hops, max_hop, B, K, stream):
 
 
 def ec_split_f16f8(X, out, M, K, ldx, seg, seg_stride, Kp, scale, role, stream):
-    """[hi16 | hi8 | lo8] planes (include/edgecape_b200.h, EC_SPLIT_F16F8): role 0 = activations, 1 = weights."""
+    """[hi16 | per 64 columns: hi8, lo8] rows (include/edgecape_b200.h, EC_SPLIT_F16F8): role 0 = activations, 1 = weights."""
     x = _get(rows(X, M, K, ldx, seg, seg_stride)).astype(np.float32) * np.float32(scale)
     hi = x.astype(np.float16)
     lo = x - hi.astype(np.float32)

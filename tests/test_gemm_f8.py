@@ -53,6 +53,30 @@ def test_f16f8_operand_format_on_the_emulated_abi(monkeypatch):
     assert torch.equal(ln[1].data.view(torch.uint8), again.data.view(torch.uint8))
 
 
+def test_f16f8_byte_offsets_on_the_emulated_abi(monkeypatch):
+    """The byte layout include/edgecape_b200.h documents: hi16 of column c at byte 2 c, hi8 at 2 Kp + 128 (c // 64) + c % 64,
+    lo8 64 bytes behind it -- for both roles, checked entry by entry."""
+    cpu_emulator.install(monkeypatch)
+    x, w, _ = _case(M=5, K=200, N=3)
+    for t, role, s_hi, s_lo in ((x, 0, 1.0, 2048.0), (w * 1024.0, 1, 2.0 ** -11, 1.0)):
+        so = ops.split_f16(t, fmt=ops.F16F8, role=role)
+        Kp = so.Kp
+        assert Kp == 256
+        raw = so.data.view(torch.uint8).reshape(t.shape[0], 4 * Kp)
+        hi = t.half()
+        lo = t - hi.float()
+        for r in range(t.shape[0]):
+            for c in (0, 1, 63, 64, 65, 127, 128, 199):
+                off = 2 * Kp + 128 * (c // 64) + c % 64
+                assert raw[r, 2 * c:2 * c + 2].view(torch.float16).item() == hi[r, c].item()
+                assert raw[r, off:off + 1].view(torch.float8_e4m3fn).float().item() == \
+                    (hi[r, c].float() * s_hi).to(torch.float8_e4m3fn).float().item()
+                assert raw[r, off + 64:off + 65].view(torch.float8_e4m3fn).float().item() == \
+                    (lo[r, c] * s_lo).to(torch.float8_e4m3fn).float().item()
+            assert not raw[r, 2 * 200:2 * Kp].any()                      # zero padding of the hi16 plane
+            assert not raw[r, 2 * Kp + 128 * 3 + 8:2 * Kp + 128 * 3 + 64].any()   # columns 200 .. 255 of the hi8 plane
+
+
 def test_vit_host_orchestration_with_f8_linears(monkeypatch, golden_dir):
     """The ViT's F16F8 chain (LayerNorm -> qkv, LayerNorm -> fc1 -> fc2 on ec_gemm_f16f8; q, k, v / attention output /
     proj on F16X2) through the emulated ABI against the golden features of the unmodified reference."""
@@ -155,7 +179,7 @@ def test_f16f8_planes_reconstruct_and_layernorm_writes_them():
 
 
 def _interleave32(std, Kp):
-    """role-1 rows [hi16 | hi8 | lo8] -> role-2 rows: 128 bytes per 32-column slice, [hi16 x 32 | hi8 x 32 | lo8 x 32]."""
+    """role-1 rows [hi16 | per 64 columns: hi8, lo8] -> role-2 rows: 128 bytes per 32-column slice, [hi16 x 32 | hi8 x 32 | lo8 x 32]."""
     M = std.shape[0]
     h16 = std[:, :2 * Kp].reshape(M, Kp // 32, 64)
     e = std[:, 2 * Kp:].reshape(M, Kp // 64, 2, 64)              # role 1: per 64 columns [hi8 x 64 | lo8 x 64]

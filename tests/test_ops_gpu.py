@@ -598,7 +598,7 @@ def test_attention_tma_on_split_qkv(B, N, H, monkeypatch):
 
 @pytest.mark.parametrize("B,N,H", [(2, 325, 12), (1, 64, 1), (2, 130, 4), (1, 730, 16), (2, 449, 3)])
 def test_attention_writes_f16f8_rows(B, N, H):
-    """ec_attention_split_fmt_next(EC_SPLIT_F16F8): the split output rows in the [hi16 | hi8 | lo8] format ec_gemm_f16f8
+    """ec_attention_split_fmt_next(EC_SPLIT_F16F8): the split output rows in the [hi16 | per 64 columns: hi8, lo8] format ec_gemm_f16f8
     consumes (the ViT proj GEMM), from the persistent kernel (<= 368 tokens) and the one-tile-per-CTA kernel: the hi16
     plane is bit-identical to the F16X2 output, hi8 = e4m3(hi16), lo8 = e4m3(lo 2^11); then the proj-shaped GEMM on it."""
     C = H * 64
