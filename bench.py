@@ -572,6 +572,13 @@ def run_ours(args):
                             "all_gemm_ms_per_step": roof["all_ms"] / args.steps, "peak_source": peak_src}
     if nsk is not None:
         line["north_star_kernels"] = nsk
+    # range events of the e4m3 / fp16 planes over everything this process ran (device-side counters of every F16F8
+    # producer): 0 / 0 on the synthetic weights; a real checkpoint with outlier activations would show up here
+    try:
+        ev = ops.overflow_count()
+        line["f16f8_range_events"] = {"beyond_e4m3_448": ev[0], "beyond_fp16_65504": ev[1]}
+    except Exception as exc:           # (a diagnostic must not cost the bench line)
+        line["f16f8_range_events"] = {"error": str(exc)}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cb, _, want = cpu_reference_rate(args, 3, 1)
