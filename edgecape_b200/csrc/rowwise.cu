@@ -60,14 +60,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         sp[split_kp + c] = __float2half_rn(o - hf);
       } else {
         uint8_t* b8 = reinterpret_cast<uint8_t*>(sp);
-        b8[2 * split_kp + c] = (uint8_t)(e4m3x2(hf, 0.f) & 0xff);
-        b8[3 * split_kp + c] = (uint8_t)(e4m3x2((o - hf) * 2048.f, 0.f) & 0xff);
+        b8[f8_off(split_kp, c)] = (uint8_t)(e4m3x2(hf, 0.f) & 0xff);
+        b8[f8_off(split_kp, c) + 64] = (uint8_t)(e4m3x2((o - hf) * 2048.f, 0.f) & 0xff);
         ovf |= (fabsf(o) > 448.f ? 1u : 0u) | (fabsf(o) > 65504.f ? 2u : 0u);
       }
     }
   }
-  if (sp)   // zero padding: all-zero bytes are +0 in fp16 and in e4m3
-    for (int c = C + lane; c < split_kp; c += 32) { sp[c] = __float2half_rn(0.f); sp[split_kp + c] = __float2half_rn(0.f); }
+  if (sp)   // zero padding of columns [C, split_kp): all-zero bytes are +0 in fp16 and in e4m3
+    for (int c = C + lane; c < split_kp; c += 32) {
+      sp[c] = __float2half_rn(0.f);
+      if (split_fmt == EC_SPLIT_F16X2) {
+        sp[split_kp + c] = __float2half_rn(0.f);
+      } else {
+        uint8_t* b8 = reinterpret_cast<uint8_t*>(sp);
+        b8[f8_off(split_kp, c)] = 0;
+        b8[f8_off(split_kp, c) + 64] = 0;
+      }
+    }
   report_overflow(overflow, ovf);
 }
 

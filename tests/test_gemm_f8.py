@@ -178,6 +178,23 @@ def test_f16f8_planes_reconstruct_and_layernorm_writes_them():
     assert torch.equal(so_ln.data.view(torch.uint8), want.data.view(torch.uint8))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [200, 72, 320])
+def test_layernorm_scalar_path_writes_f16f8_rows(C):
+    """Widths that are not a multiple of 128 take the scalar LayerNorm kernel: its F16F8 rows (values and the zero padding up
+    to Kp) are the bytes ec_split_f16f8 writes from the fp32 result."""
+    D = _dev()
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(77, C, generator=g) * 2).to(D)
+    w, b = torch.rand(C, generator=g).to(D) + 0.5, torch.randn(C, generator=g).to(D)
+    y, so = ops.layernorm(x, w, b, 1e-6, split="also", split_fmt=ops.F16F8)
+    want = ops.split_f16(y, fmt=ops.F16F8, role=0)
+    assert so.Kp == want.Kp == (C + 63) // 64 * 64
+    assert torch.equal(so.data.view(torch.uint8), want.data.view(torch.uint8))
+    ref = torch.nn.functional.layer_norm(x.double(), (C,), w.double(), b.double(), 1e-6)
+    assert (y.double() - ref).abs().max().item() < 1e-5
+
+
 def _interleave32(std, Kp):
     """role-1 rows [hi16 | per 64 columns: hi8, lo8] -> role-2 rows: 128 bytes per 32-column slice, [hi16 x 32 | hi8 x 32 | lo8 x 32]."""
     M = std.shape[0]
