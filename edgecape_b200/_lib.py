@@ -56,6 +56,7 @@ SIGNATURES = {
                                       c_fp, c_int, c_fp]),
     "ec_attention_hop_bias_next": (c_int, [c_fp, c_int, c_int, c_fp, c_fp, c_fp, c_fp]),
     "ec_attention_split_fmt_next": (c_int, [c_int]),
+    "ec_attention_set_cta_limit": (c_int, [c_int]),
     "ec_hop_bias": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "ec_mask_accumulate": (c_int, [c_fp, c_fp, c_int, c_int, c_fp]),
     "ec_kp_masks": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_fp]),

@@ -1557,6 +1557,7 @@ struct HopArm {   // armed by ec_attention_hop_bias_next, consumed by the next e
 static thread_local HopArm g_hop;
 static thread_local int g_out_fmt = EC_SPLIT_F16X2;   // armed by ec_attention_split_fmt_next, consumed by the next ec_attention_tc_split
 static int g_variant = 0;   // 0: persistent pipelined kernel where it applies, else P in TMEM + wide P V MMAs; 3: never the persistent kernel; 2: P in TMEM, three N = 64 MMAs per k-step; 1: P through shared memory
+static int g_cta_limit = 0;   // 0 = one persistent CTA per SM; else at most this many (ec_attention_set_cta_limit)
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
 
@@ -1682,7 +1683,8 @@ extern "C" int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp,
       }
       atc::ParamsP pp{p, rows_k, nfull, r16, cdiv(Lq, atc::BM), cdiv(Lq, atc::BM) * H * B};
       pp.t.wide = 1;
-      const int ctas = pp.n_tiles < num_sms ? pp.n_tiles : num_sms;
+      int ctas = pp.n_tiles < num_sms ? pp.n_tiles : num_sms;
+      if (atc::g_cta_limit > 0 && ctas > atc::g_cta_limit) ctas = atc::g_cta_limit;   // (ec_attention_set_cta_limit)
       launch_pdl(atc::attention_tc_ps_kernel, dim3(ctas), dim3(atc::THREADS_TS), ps_smem, (cudaStream_t)stream, tmQ, tmK,
                  tmV, tmKp, tmVp, pp);
       return check_launch("ec_attention_tc_split");
@@ -1717,6 +1719,12 @@ extern "C" int ec_attention_hop_bias_next(const float* hops, int n_hops, int hid
 extern "C" int ec_attention_split_fmt_next(int fmt) {
   EC_REQUIRE(fmt == EC_SPLIT_F16X2 || fmt == EC_SPLIT_F16F8, "ec_attention_split_fmt_next: EC_SPLIT_F16X2 or EC_SPLIT_F16F8");
   atc::g_out_fmt = fmt;
+  return EC_OK;
+}
+
+extern "C" int ec_attention_set_cta_limit(int ctas) {
+  EC_REQUIRE(ctas >= 0, "ec_attention_set_cta_limit: negative");
+  atc::g_cta_limit = ctas;
   return EC_OK;
 }
 

@@ -137,8 +137,17 @@ class _GraphedForward:
                 s.feat_q, s.feats_s = model.extract_features(s.img_s, s.img_q, s.inv)
             _lib.call("ec_set_pdl", int(pdl in ("all", "head") and not env_off))
             s.graph_head = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(s.graph_head, pool=s.graph_vit.pool(), stream=self._capture_hi):
-                s.out, s.preds = self._head(s, s.feat_q, s.feats_s)
+            # experiment (EDGECAPE_HEAD_CTAS=n, off by default): the head's persistent kernels (GEMMs, attention, GCN) on at
+            # most n CTAs, so that they run BESIDE the next batch's backbone GEMMs rather than in front of them (grid sizes
+            # are fixed at capture; results do not depend on the number of workers)
+            for fn in ("ec_tc_set_cta_limit", "ec_attention_set_cta_limit", "ec_gcn_fused2_set_cta_limit"):
+                _lib.call(fn, HEAD_CTAS)
+            try:
+                with torch.cuda.graph(s.graph_head, pool=s.graph_vit.pool(), stream=self._capture_hi):
+                    s.out, s.preds = self._head(s, s.feat_q, s.feats_s)
+            finally:
+                for fn in ("ec_tc_set_cta_limit", "ec_attention_set_cta_limit", "ec_gcn_fused2_set_cta_limit"):
+                    _lib.call(fn, 0)
             L, _, K, _ = s.out[0].shape
             s.host_out = tuple(t.pin_memory() for t in (torch.empty(L + 1, B, K, 2), torch.empty(2, K, K),
                                                         torch.empty(B, K, 3)))
@@ -233,6 +242,7 @@ class _GraphedForward:
 
 
 VIT_CHAINS = int(os.environ.get("EDGECAPE_VIT_CHAINS", "1"))
+HEAD_CTAS = int(os.environ.get("EDGECAPE_HEAD_CTAS", "0"))
 
 
 def _hashable(v):

@@ -232,6 +232,10 @@ int ec_attention_hop_bias_next(const float* hops, int n_hops, int hidden, const 
  * EC_SPLIT_F16X2 (the default) or EC_SPLIT_F16F8 (A role; head dim 64 only) -- the format ec_gemm_f16f8 consumes, so that
  * the projection behind a ViT attention (dino.py Attention.proj) runs its cross terms on e4m3 like qkv / fc1 / fc2. */
 int ec_attention_split_fmt_next(int fmt);
+/* Experiment switch (like ec_tc_set_cta_limit / ec_gcn_fused2_set_cta_limit): the persistent attention kernel launches at most
+ * `ctas` CTAs (0 = one per SM).  Grid sizes are fixed when a CUDA graph is captured: the detector's EDGECAPE_HEAD_CTAS narrows the
+ * head graph's persistent kernels so that they run beside the next batch's backbone instead of in front of it. */
+int ec_attention_set_cta_limit(int ctas);
 int ec_attention_tc_split(const void* Q2, int q_total_rows, int q_kp, int q_col, int q_rows,
                           const void* K2, int k_total_rows, int k_kp, int k_col, const void* V2,
                           int v_total_rows, int v_kp, int v_col, int k_rows, float* O, int B, int H,
